@@ -1,0 +1,57 @@
+"""Small model configs shared by ``make_golden.py`` (which runs the reference on them)
+and by the tests (which replay the stored reference outputs).  Constructor kwargs are
+the reference's own (vit.py:104-121, rankvit.py:158-175, residualvit.py:390-415,
+adavit.py:229-248, moevit.py:210-224)."""
+
+_BASE = dict(image_size=64, patch_size=8, num_layers=4, num_heads=2, hidden_dim=128, mlp_dim=256, num_classes=10)
+
+CASES = {
+    # dh = 32, odd token count (17)
+    "vit_d64_h2": dict(
+        family="vit", batch=4, weight_seed=11, image_seed=21,
+        cfg=dict(image_size=32, patch_size=8, num_layers=3, num_heads=2, hidden_dim=64, mlp_dim=128, num_classes=10)),
+    # dh = 64, registers + two class tokens (sum readout, vit.py:242-243)
+    "vit_d128_regs": dict(
+        family="vit", batch=3, weight_seed=12, image_seed=22,
+        cfg=dict(image_size=48, patch_size=16, num_layers=2, num_heads=2, hidden_dim=128, mlp_dim=256,
+                 num_classes=7, num_registers=2, num_class_tokens=2)),
+    "rankvit_b05": dict(
+        family="rankvit", batch=4, weight_seed=13, image_seed=23, budget=0.5,
+        cfg=dict(_BASE, rankvit_layers=[1, 3])),
+    "rankvit_list": dict(
+        family="rankvit", batch=4, weight_seed=13, image_seed=24, budget=[1, 0.5, 1, 0.25],
+        cfg=dict(_BASE, rankvit_layers=[1, 3])),
+    "residual_learnable_b04": dict(
+        family="residualvit", batch=4, weight_seed=14, image_seed=25, budget=0.4,
+        cfg=dict(_BASE, gate_type="sigmoid", gate_temp=1.0, gate_bias=0.0, gate_threshold=0.5,
+                 add_budget_token="learnable", residual_layers=["attention+mlp"] * 4)),
+    "residual_learnable_b08": dict(
+        family="residualvit", batch=4, weight_seed=14, image_seed=25, budget=0.8,
+        cfg=dict(_BASE, gate_type="sigmoid", gate_temp=1.0, gate_bias=0.0, gate_threshold=0.5,
+                 add_budget_token="learnable", residual_layers=["attention+mlp"] * 4)),
+    # gate biases calibrated so every layer keeps a mid-range fraction
+    "residual_learnable_cal04": dict(
+        family="residualvit", batch=4, weight_seed=18, image_seed=29, budget=0.4, calibrate=0.4,
+        cfg=dict(_BASE, gate_type="sigmoid", gate_temp=1.0, gate_bias=0.0, gate_threshold=0.5,
+                 add_budget_token="learnable", residual_layers=["attention+mlp"] * 4)),
+    "residual_fixed_b05": dict(
+        family="residualvit", batch=3, weight_seed=15, image_seed=26, budget=0.5,
+        cfg=dict(_BASE, gate_type="sigmoid", gate_temp=1.0, gate_bias=0.0, gate_threshold=0.5,
+                 add_budget_token=True, residual_layers=["attention+mlp"] * 4)),
+    "avit": dict(
+        family="adavit", batch=4, weight_seed=16, image_seed=27,
+        cfg=dict(_BASE, num_layers=6, eps=0.01, gate_scale=3.0, gate_center=-0.3)),
+    "moevit": dict(
+        family="moevit", batch=4, weight_seed=17, image_seed=28,
+        cfg=dict(_BASE, num_layers=3, mlp_moes=[1, 4, 2])),
+}
+
+
+def build_case(case):
+    """(state_dict, images) of a case, regenerated from its seeds."""
+    from oracle import weights as ow
+    sd = ow.make_state_dict(case["family"], case["cfg"], seed=case["weight_seed"])
+    if case.get("calibrate") is not None:
+        sd = ow.calibrate_residual_gates(sd, case["cfg"], case["calibrate"])
+    images = ow.synthetic_images(case["batch"], case["cfg"]["image_size"], seed=case["image_seed"])
+    return sd, images
