@@ -1,0 +1,116 @@
+"""ctypes binding of ``libpeekvit_b200.so`` (the C ABI declared in ``include/peekvit_b200.h``).
+
+There is no fallback: if the CUDA library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from typing import Dict, List, Optional
+
+from . import build as _build
+
+c_void_p, c_int, c_float, c_longlong = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+PK_EPI_BIAS_BF16 = 0
+PK_EPI_BIAS_GELU_BF16 = 1
+PK_EPI_BIAS_RESID_F32 = 2
+PK_EPI_BIAS_F32 = 3
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", c_void_p), ("W", c_void_p),
+        ("M", c_int), ("N", c_int), ("K", c_int),
+        ("lda", c_longlong), ("ldw", c_longlong),
+        ("bias", c_void_p), ("epilogue", c_int),
+        ("out", c_void_p), ("ldo", c_longlong),
+        ("resid", c_void_p), ("ldr", c_longlong),
+        ("rowscale", c_void_p),
+        ("rows_per_group", c_int), ("group_stride", c_int), ("group_offset", c_int), ("resid_is_pos", c_int),
+        ("m_dev", c_void_p), ("block_n", c_int), ("max_ctas", c_int),
+    ]
+
+
+class AttentionArgs(C.Structure):
+    _fields_ = [
+        ("qkv", c_void_p), ("out", c_void_p),
+        ("batch", c_int), ("num_heads", c_int), ("head_dim", c_int),
+        ("seq_len", c_int), ("cu_seqlens", c_void_p), ("max_seq_len", c_int),
+        ("scale", c_float),
+        ("key_mult", c_void_p), ("extra_kv", c_void_p), ("extra_mult", c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol include/peekvit_b200.h declares
+SIGNATURES: Dict[str, tuple] = {
+    "pk_abi_version": (c_int, []),
+    "pk_init": (c_int, [c_int]),
+    "pk_last_error": (C.c_char_p, []),
+    "pk_num_sms": (c_int, []),
+    "pk_device_flag": (c_int, [c_int]),
+    "pk_gemm_bf16": (c_int, [C.POINTER(GemmArgs), c_void_p]),
+    "pk_patchify": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "pk_fill_token_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p]),
+    "pk_layernorm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pk_attention_fwd": (c_int, [C.POINTER(AttentionArgs), c_void_p]),
+    "pk_cls_head": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "pk_token_norm_score": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "pk_topk_select": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "pk_gather_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+}
+
+HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "peekvit_b200.h")
+
+
+def header_symbols() -> List[str]:
+    """Function names declared in include/peekvit_b200.h."""
+    with open(HEADER) as f:
+        src = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(pk_[a-z0-9_]+)\s*\(", src)))
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load (building first if the library is absent) and type every entry point."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path) or os.environ.get("PEEKVIT_B200_REBUILD") == "1":
+        path = _build.build(force=True)
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.pk_abi_version() != 1:
+        raise RuntimeError(f"libpeekvit_b200 ABI {lib.pk_abi_version()} != 1; rebuild with `python -m peekvit_b200.build --force`")
+    _lib = lib
+    return lib
+
+
+class PkError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().pk_last_error()
+        raise PkError(f"{what or 'peekvit_b200'} failed (status {rc}): {msg.decode() if msg else ''}")
+
+
+_initialised_device: Optional[int] = None
+
+
+def init(device_index: int) -> C.CDLL:
+    """Create the library context on ``device_index`` (must be a B200 / sm_100a)."""
+    global _initialised_device
+    lib = load()
+    if _initialised_device != device_index:
+        check(lib.pk_init(device_index), "pk_init")
+        _initialised_device = device_index
+    return lib

@@ -1,0 +1,326 @@
+// peekvit_b200 — tcgen05/TMEM/TMA GEMM with fused epilogues (sm_100a).
+//
+//   C[M,N] = A[M,K] (bf16, row-major) x W[N,K]^T (bf16, row-major = nn.Linear layout), f32 accumulate
+//
+// replaces the reference's cuBLAS/cuDNN call sites on the encoder forward path:
+//   K1 conv_proj patch GEMM + bias + pos_embedding      (reference models/vit.py:212, :92)
+//   K3 MHA packed in-projection + bias                   (models/blocks.py:94 -> in_proj)
+//   K5 MHA out-projection + bias + residual              (models/vit.py:49-51)
+//   K6 fc1 + bias + exact GELU                           (models/blocks.py:81-82)
+//   K7 fc2 + bias + residual                             (models/blocks.py:83, vit.py:55)
+//
+// Design (one CTA per SM, persistent over output tiles, warp-specialised):
+//   warp 0      TMA producer: A tile 128x64 and W tile BNx64 (128-byte swizzle) into a smem ring
+//   warp 1      MMA issuer: one thread issues tcgen05.mma 128xBNx16, accumulators in TMEM,
+//               two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue: tcgen05.ld (thread = row) -> padded smem transpose -> coalesced 16-byte
+//               global accesses (thread = 4 columns) with bias / GELU / row-scale / residual fused
+// Barriers: full[s]/empty[s] (TMA <-> MMA), tmem_full[a]/tmem_empty[a] (MMA <-> epilogue).
+// Every mbarrier wait is bounded (pk_common.cuh) so a protocol bug cannot hang the GPU.
+#include "pk_common.cuh"
+#include "../../include/peekvit_b200.h"
+
+namespace pk {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;           // 64 bf16 = 128 B = one swizzle row
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 128 + kEpiWarps * 32;
+constexpr int kStagePitch = 36;   // floats per staged row (32 + 4 pad): conflict-free v4 access
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BN == 256 ? 3 : (BN == 192 ? 4 : 5);
+  static constexpr int kStagingBytes = kEpiWarps * 32 * kStagePitch * 4;
+  static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;
+};
+
+struct GemmKernelParams {
+  int M, N, K;
+  const int* m_dev;
+  const float* bias;
+  void* out;
+  long long ldo;
+  const float* resid;
+  long long ldr;
+  const float* rowscale;
+  int rows_per_group, group_stride, group_offset, resid_is_pos;
+  unsigned int* flag;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmKernelParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128-byte swizzle needs 1024-byte aligned tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_ab = smem;
+  float* staging = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
+  uint64_t* full_bar = bars;                       // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = warp_id();
+  const int lane = lane_id();
+  const int M = p.m_dev ? min(*p.m_dev, p.M) : p.M;
+  const int m_tiles = (M + kBM - 1) / kBM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = p.K / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tfull_bar[a]), 1);
+      mbar_init(smem_u32(&tempty_bar[a]), kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      bool ok = true;
+      for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
+        const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (!mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u, p.flag, 0x100u + s)) { ok = false; break; }
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          mbar_expect_tx(fb, Cfg::kStageBytes);
+          const uint32_t a_dst = smem_u32(smem_ab + s * Cfg::kStageBytes);
+          tma_load_2d(a_dst, &tmap_a, fb, kb * kBK, m_blk * kBM);
+          tma_load_2d(a_dst + Cfg::kABytes, &tmap_b, fb, kb * kBK, n_blk * BN);
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      bool ok = true;
+      for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
+        if (!mbar_wait(smem_u32(&tempty_bar[as]), aph ^ 1u, p.flag, 0x200u + as)) break;
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (!mbar_wait(smem_u32(&full_bar[s]), ph, p.flag, 0x300u + s)) { ok = false; break; }
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem_ab + s * Cfg::kStageBytes);
+          const uint64_t a_desc = umma_desc_kmajor_sw128(a_addr);
+          const uint64_t b_desc = umma_desc_kmajor_sw128(a_addr + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr>>4) field
+            umma_bf16(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));            // frees the smem slot when these MMAs retire
+          if (kb == num_kb - 1) umma_commit(smem_u32(&tfull_bar[as]));
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
+        }
+        if (++as == 2) { as = 0; aph ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue warps
+    const int ew = warp - 4;
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = ew >> 2;               // which half of the tile's columns
+    constexpr int kChunksPerWarp = BN / 64; // 32-column chunks per warp
+    float* stg = staging + ew * 32 * kStagePitch;
+    const int c4 = lane & 7;                // phase 2: this lane's 4-column group inside the chunk
+    const int r_sub = lane >> 3;            // phase 2: row inside each 4-row group
+    int as = 0;
+    uint32_t aph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+      if (!mbar_wait(smem_u32(&tfull_bar[as]), aph, p.flag, 0x400u + as)) break;
+      tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+#pragma unroll 1
+      for (int ch = 0; ch < kChunksPerWarp; ++ch) {
+        const int col0 = half * (BN / 2) + ch * 32;
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + static_cast<uint32_t>(col0), v);
+        tmem_ld_wait();
+        if (ch == kChunksPerWarp - 1) {
+          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+        }
+        // phase 1: thread = row, 32 consecutive f32 -> padded smem
+        float4* srow = reinterpret_cast<float4*>(stg + lane * kStagePitch);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          srow[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        __syncwarp();
+        // phase 2: thread = 4 columns, 8 lanes cover one 128-B row segment, 4 rows per instruction
+        const int gcol = n_blk * BN + col0 + c4 * 4;
+        const bool col_ok = gcol < p.N;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok && p.bias) b4 = *reinterpret_cast<const float4*>(p.bias + gcol);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + r_sub;
+          const int grow = m_blk * kBM + q * 32 + rr;
+          if (grow < M && col_ok) {
+            float4 a = *reinterpret_cast<const float4*>(stg + rr * kStagePitch + c4 * 4);
+            a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+            long long orow = grow;
+            long long rrow = grow;
+            if (p.rows_per_group > 0) {
+              const int g = grow / p.rows_per_group, pos = grow - g * p.rows_per_group;
+              orow = static_cast<long long>(g) * p.group_stride + p.group_offset + pos;
+              rrow = p.resid_is_pos ? static_cast<long long>(p.group_offset + pos) : orow;
+            }
+            if constexpr (EPI == PK_EPI_BIAS_GELU_BF16) {
+              a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
+            }
+            if constexpr (EPI == PK_EPI_BIAS_RESID_F32) {
+              if (p.rowscale) {
+                const float sc = p.rowscale[grow];
+                a.x *= sc; a.y *= sc; a.z *= sc; a.w *= sc;
+              }
+              const float4 r4 = *reinterpret_cast<const float4*>(p.resid + rrow * p.ldr + gcol);
+              a.x += r4.x; a.y += r4.y; a.z += r4.z; a.w += r4.w;
+            }
+            if constexpr (EPI == PK_EPI_BIAS_BF16 || EPI == PK_EPI_BIAS_GELU_BF16) {
+              uint2 o = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
+              *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + gcol) = o;
+            } else {
+              *reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.ldo + gcol) = a;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (++as == 2) { as = 0; aph ^= 1u; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN, int EPI>
+static int launch_gemm(const pk_gemm_args* a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  auto kfn = gemm_bf16_tcgen05_kernel<BN, EPI>;
+  if (!attr_set) {
+    PK_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_2d(&ta, a->A, static_cast<uint64_t>(a->M), static_cast<uint64_t>(a->K),
+                             static_cast<uint64_t>(a->lda), kBM, kBK);
+  if (rc != PK_OK) return rc;
+  rc = make_tmap_bf16_2d(&tb, a->W, static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->K),
+                         static_cast<uint64_t>(a->ldw), BN, kBK);
+  if (rc != PK_OK) return rc;
+  GemmKernelParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.m_dev = a->m_dev;
+  p.bias = a->bias;
+  p.out = a->out; p.ldo = a->ldo;
+  p.resid = a->resid; p.ldr = a->ldr;
+  p.rowscale = a->rowscale;
+  p.rows_per_group = a->rows_per_group; p.group_stride = a->group_stride;
+  p.group_offset = a->group_offset; p.resid_is_pos = a->resid_is_pos;
+  p.flag = device_flag_ptr();
+  const int m_tiles = (a->M + kBM - 1) / kBM, n_tiles = (a->N + BN - 1) / BN;
+  int grid = m_tiles * n_tiles;
+  const int sms = a->max_ctas > 0 ? a->max_ctas : num_sms();
+  if (grid > sms) grid = sms;
+  if (grid < 1) grid = 1;
+  kfn<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  return check_cuda(cudaGetLastError(), "gemm_bf16_tcgen05_kernel launch");
+}
+
+template <int BN>
+static int dispatch_epi(const pk_gemm_args* a, cudaStream_t stream) {
+  switch (a->epilogue) {
+    case PK_EPI_BIAS_BF16: return launch_gemm<BN, PK_EPI_BIAS_BF16>(a, stream);
+    case PK_EPI_BIAS_GELU_BF16: return launch_gemm<BN, PK_EPI_BIAS_GELU_BF16>(a, stream);
+    case PK_EPI_BIAS_RESID_F32: return launch_gemm<BN, PK_EPI_BIAS_RESID_F32>(a, stream);
+    case PK_EPI_BIAS_F32: return launch_gemm<BN, PK_EPI_BIAS_F32>(a, stream);
+  }
+  set_last_error("pk_gemm_bf16: unknown epilogue %d", a->epilogue);
+  return PK_ERR_INVALID;
+}
+
+// Tile width: the widest of {256,192,128} that wastes the fewest padded columns.
+int pick_block_n(int N) {
+  int best = 128;
+  long long best_cost = -1;
+  const int cands[3] = {192, 256, 128};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    const long long padded = static_cast<long long>((N + bn - 1) / bn) * bn;
+    if (best_cost < 0 || padded < best_cost) { best_cost = padded; best = bn; }
+  }
+  return best;
+}
+
+}  // namespace pk
+
+extern "C" int pk_gemm_bf16(const pk_gemm_args* a, void* stream) {
+  using namespace pk;
+  PK_REQUIRE(a != nullptr, "pk_gemm_bf16: null args");
+  PK_REQUIRE(a->M >= 0 && a->N > 0 && a->K > 0, "pk_gemm_bf16: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
+  PK_REQUIRE(a->K % kBK == 0, "pk_gemm_bf16: K=%d must be a multiple of %d", a->K, kBK);
+  PK_REQUIRE(a->N % 4 == 0, "pk_gemm_bf16: N=%d must be a multiple of 4", a->N);
+  PK_REQUIRE(a->lda % 8 == 0 && a->ldw % 8 == 0, "pk_gemm_bf16: lda/ldw must be multiples of 8 elements (TMA 16-B strides)");
+  PK_REQUIRE((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->W) & 15) == 0,
+             "pk_gemm_bf16: A/W must be 16-byte aligned");
+  PK_REQUIRE(a->out != nullptr && a->ldo % 4 == 0, "pk_gemm_bf16: out null or ldo not a multiple of 4");
+  if (a->epilogue == PK_EPI_BIAS_RESID_F32)
+    PK_REQUIRE(a->resid != nullptr && a->ldr % 4 == 0, "pk_gemm_bf16: residual epilogue needs resid with ldr %% 4 == 0");
+  if (a->M == 0) return PK_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int bn = a->block_n > 0 ? a->block_n : pick_block_n(a->N);
+  switch (bn) {
+    case 128: return dispatch_epi<128>(a, s);
+    case 192: return dispatch_epi<192>(a, s);
+    case 256: return dispatch_epi<256>(a, s);
+  }
+  set_last_error("pk_gemm_bf16: unsupported block_n %d", bn);
+  return PK_ERR_INVALID;
+}

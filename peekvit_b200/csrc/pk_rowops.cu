@@ -1,0 +1,340 @@
+// peekvit_b200 — HBM-bound row kernels: patchify, token rows, LayerNorm, class head,
+// RankViT token score / stable top-k / compaction.  128-bit coalesced accesses, one warp
+// per token row, warp-shuffle reductions, fp32 statistics.
+#include "pk_common.cuh"
+#include "../../include/peekvit_b200.h"
+
+namespace pk {
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// ------------------------------------------------------------------------------ patchify
+// One thread = 8 consecutive K elements (16-byte bf16 store) of one patch row.
+__global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out,
+                                int S, int p, int n_side, long long total_chunks) {
+  const int chunks_per_prow = p / 8;           // 8-wide chunks per (c,i) row of a patch
+  const int Kp = 3 * p * p;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total_chunks;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long e = idx * 8;                     // linear output element
+    const long long row = e / Kp;              // b*P + patch
+    const int k = static_cast<int>(e - row * Kp);
+    const int c = k / (p * p);
+    const int i = (k - c * p * p) / p;
+    const int j = k - c * p * p - i * p;
+    const int P = n_side * n_side;
+    const long long b = row / P;
+    const int patch = static_cast<int>(row - b * P);
+    const int py = patch / n_side, px = patch - py * n_side;
+    const float* src = img + ((b * 3 + c) * S + (py * p + i)) * (long long)S + px * p + j;
+    const float4 a = ldg4(src), d = ldg4(src + 4);
+    uint4 o;
+    o.x = pack_bf16(a.x, a.y); o.y = pack_bf16(a.z, a.w);
+    o.z = pack_bf16(d.x, d.y); o.w = pack_bf16(d.z, d.w);
+    *reinterpret_cast<uint4*>(out + e) = o;
+    (void)chunks_per_prow;
+  }
+}
+
+// ------------------------------------------------------------------------------ token rows
+__global__ void fill_token_rows_kernel(float* __restrict__ x, int batch, int seq_stride, int row_offset, int n_tokens,
+                                       int dim, const float* __restrict__ tokens, const float* __restrict__ pos, float scale) {
+  const int d4 = dim / 4;
+  const long long total = (long long)batch * n_tokens * d4;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = static_cast<int>(idx % d4);
+    const long long r = idx / d4;
+    const int t = static_cast<int>(r % n_tokens);
+    const long long b = r / n_tokens;
+    float4 v = make_float4(scale, scale, scale, scale);
+    if (tokens) {
+      const float4 tk = ldg4(tokens + (long long)t * dim + c * 4);
+      v = make_float4(scale * tk.x, scale * tk.y, scale * tk.z, scale * tk.w);
+    }
+    if (pos) {
+      const float4 pe = ldg4(pos + (long long)(row_offset + t) * dim + c * 4);
+      v.x += pe.x; v.y += pe.y; v.z += pe.z; v.w += pe.w;
+    }
+    *reinterpret_cast<float4*>(x + (b * seq_stride + row_offset + t) * (long long)dim + c * 4) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------ LayerNorm
+// One warp per row; the row lives in registers (<= MAXV float4 per lane), two-pass statistics.
+template <int MAXV>
+__device__ __forceinline__ void ln_row_load(const float* __restrict__ row, int d4, int lane, float4 (&v)[MAXV], float& sum) {
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < d4) {
+      v[i] = *reinterpret_cast<const float4*>(row + c * 4);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+template <int MAXV>
+__device__ __forceinline__ void ln_row_stats(const float4 (&v)[MAXV], int d4, int lane, int dim, float sum, float eps,
+                                             float& mean, float& rstd) {
+  mean = warp_sum(sum) / static_cast<float>(dim);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (lane + i * 32 < d4) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float var = warp_sum(sq) / static_cast<float>(dim);
+  rstd = 1.0f / sqrtf(var + eps);
+}
+
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float eps, int rows, int dim, const float* __restrict__ rowscale,
+                      const int* __restrict__ row_index, const int* __restrict__ rows_dev) {
+  const int lane = lane_id();
+  const int d4 = dim / 4;
+  const int nrows = rows_dev ? min(*rows_dev, rows) : rows;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int r = blockIdx.x * (blockDim.x >> 5) + warp_id(); r < nrows; r += warps_total) {
+    const long long src = row_index ? row_index[r] : r;
+    float4 v[MAXV];
+    float sum, mean, rstd;
+    ln_row_load<MAXV>(x + src * dim, d4, lane, v, sum);
+    ln_row_stats<MAXV>(v, d4, lane, dim, sum, eps, mean, rstd);
+    const float sc = rowscale ? rowscale[r] : 1.0f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + i * 32;
+      if (c < d4) {
+        const float4 g = ldg4(gamma + c * 4), b = ldg4(beta + c * 4);
+        const float o0 = sc * fmaf((v[i].x - mean) * rstd, g.x, b.x);
+        const float o1 = sc * fmaf((v[i].y - mean) * rstd, g.y, b.y);
+        const float o2 = sc * fmaf((v[i].z - mean) * rstd, g.z, b.z);
+        const float o3 = sc * fmaf((v[i].w - mean) * rstd, g.w, b.w);
+        *reinterpret_cast<uint2*>(y + (long long)r * dim + c * 4) = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ class head
+// CTA = kHeadGroup samples: LN of their class rows into smem (fp32), then every warp sweeps
+// classes, streaming head_w rows (L2-resident) and dotting against the staged samples.
+constexpr int kHeadGroup = 8;
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+cls_head_kernel(const float* __restrict__ x, int batch, int seq_len, const int* __restrict__ cu_seqlens, int n_cls, int dim,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                const float* __restrict__ head_w, const float* __restrict__ head_b, int num_classes, float* __restrict__ logits) {
+  extern __shared__ float feat[];   // [kHeadGroup][dim]
+  const int lane = lane_id(), warp = warp_id();
+  const int d4 = dim / 4;
+  const int b0 = blockIdx.x * kHeadGroup;
+  {
+    const int b = b0 + warp;        // 8 warps <-> 8 samples
+    float4 acc[MAXV];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b < batch) {
+      const long long row0 = cu_seqlens ? cu_seqlens[b] : (long long)b * seq_len;
+      for (int t = 0; t < n_cls; ++t) {
+        float4 v[MAXV];
+        float sum, mean, rstd;
+        ln_row_load<MAXV>(x + (row0 + t) * dim, d4, lane, v, sum);
+        ln_row_stats<MAXV>(v, d4, lane, dim, sum, eps, mean, rstd);
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+          const int c = lane + i * 32;
+          if (c < d4) {
+            const float4 g = ldg4(gamma + c * 4), be = ldg4(beta + c * 4);
+            acc[i].x += fmaf((v[i].x - mean) * rstd, g.x, be.x);
+            acc[i].y += fmaf((v[i].y - mean) * rstd, g.y, be.y);
+            acc[i].z += fmaf((v[i].z - mean) * rstd, g.z, be.z);
+            acc[i].w += fmaf((v[i].w - mean) * rstd, g.w, be.w);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + i * 32;
+      if (c < d4) *reinterpret_cast<float4*>(feat + warp * dim + c * 4) = acc[i];
+    }
+  }
+  __syncthreads();
+  for (int cls = warp; cls < num_classes; cls += (blockDim.x >> 5)) {
+    float part[kHeadGroup];
+#pragma unroll
+    for (int s = 0; s < kHeadGroup; ++s) part[s] = 0.f;
+    for (int c = lane; c < d4; c += 32) {
+      const float4 w = ldg4(head_w + (long long)cls * dim + c * 4);
+#pragma unroll
+      for (int s = 0; s < kHeadGroup; ++s) {
+        const float4 f = *reinterpret_cast<const float4*>(feat + s * dim + c * 4);
+        part[s] += (w.x * f.x + w.y * f.y) + (w.z * f.z + w.w * f.w);
+      }
+    }
+    const float bias = head_b ? head_b[cls] : 0.f;
+#pragma unroll
+    for (int s = 0; s < kHeadGroup; ++s) {
+      const float tot = warp_sum(part[s]);
+      if (lane == 0 && b0 + s < batch) logits[(long long)(b0 + s) * num_classes + cls] = tot + bias;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ RankViT
+__global__ void __launch_bounds__(256)
+token_norm_score_kernel(const float* __restrict__ x, float* __restrict__ scores, int batch, int seq_len, int dim) {
+  const int lane = lane_id();
+  const int n = seq_len - 1;
+  const long long total = (long long)batch * n;
+  const int d4 = dim / 4;
+  const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r = blockIdx.x * (long long)(blockDim.x >> 5) + warp_id(); r < total; r += warps_total) {
+    const long long b = r / n;
+    const int i = static_cast<int>(r - b * n);
+    const float* row = x + (b * seq_len + 1 + i) * dim;
+    float sq = 0.f;
+    for (int c = lane; c < d4; c += 32) {
+      const float4 v = *reinterpret_cast<const float4*>(row + c * 4);
+      sq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+    sq = warp_sum(sq);
+    if (lane == 0) scores[r] = sqrtf(sq);
+  }
+}
+
+// Exact stable descending rank by counting: rank_i = #{j : s_j > s_i or (s_j == s_i and j < i)}.
+// Every token gets a distinct rank, so the first k ranks are the reference's argsort[:k] with
+// ties broken to the lowest index; O(n^2) compares per row out of shared memory (n <= 4096).
+__global__ void __launch_bounds__(256)
+topk_select_kernel(const float* __restrict__ scores, int* __restrict__ kept, int n, int k) {
+  extern __shared__ float s_sc[];
+  const float* row = scores + (long long)blockIdx.x * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s_sc[i] = row[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float si = s_sc[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const float sj = s_sc[j];
+      rank += (sj > si) || (sj == si && j < i);
+    }
+    if (rank < k) kept[(long long)blockIdx.x * k + rank] = i;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ x, float* __restrict__ y, const int* __restrict__ kept, int batch, int seq_len,
+                   int k, int dim) {
+  const int lane = lane_id();
+  const int d4 = dim / 4;
+  const long long total = (long long)batch * (k + 1);
+  const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r = blockIdx.x * (long long)(blockDim.x >> 5) + warp_id(); r < total; r += warps_total) {
+    const long long b = r / (k + 1);
+    const int o = static_cast<int>(r - b * (k + 1));
+    const int src_tok = o == 0 ? 0 : 1 + kept[b * k + (o - 1)];
+    const float4* src = reinterpret_cast<const float4*>(x + (b * seq_len + src_tok) * dim);
+    float4* dst = reinterpret_cast<float4*>(y + r * dim);
+    for (int c = lane; c < d4; c += 32) dst[c] = src[c];
+  }
+}
+
+static int grid_for(long long work_items, int per_block, int max_blocks_per_sm = 8) {
+  long long g = (work_items + per_block - 1) / per_block;
+  const long long cap = (long long)num_sms() * max_blocks_per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace pk
+
+using namespace pk;
+
+extern "C" int pk_patchify(const float* images, void* patches, int batch, int image_size, int patch_size, void* stream) {
+  PK_REQUIRE(images && patches, "pk_patchify: null pointer");
+  PK_REQUIRE(patch_size % 8 == 0 && image_size % patch_size == 0, "pk_patchify: patch_size %d must be a multiple of 8 dividing image_size %d",
+             patch_size, image_size);
+  if (batch == 0) return PK_OK;
+  const int n_side = image_size / patch_size;
+  const long long total = (long long)batch * n_side * n_side * 3 * patch_size * patch_size / 8;
+  patchify_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      images, static_cast<__nv_bfloat16*>(patches), image_size, patch_size, n_side, total);
+  return check_cuda(cudaGetLastError(), "patchify_kernel");
+}
+
+extern "C" int pk_fill_token_rows(float* x, int batch, int seq_stride, int row_offset, int n_tokens, int dim,
+                                  const float* tokens, const float* pos, float scale, void* stream) {
+  PK_REQUIRE(x && dim % 4 == 0, "pk_fill_token_rows: null x or dim %% 4 != 0");
+  if (batch == 0 || n_tokens == 0) return PK_OK;
+  const long long total = (long long)batch * n_tokens * (dim / 4);
+  fill_token_rows_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, batch, seq_stride, row_offset, n_tokens, dim, tokens, pos, scale);
+  return check_cuda(cudaGetLastError(), "fill_token_rows_kernel");
+}
+
+extern "C" int pk_layernorm_bf16(const float* x, void* y, const float* gamma, const float* beta, float eps, int rows, int dim,
+                                 const float* rowscale, const int* row_index, const int* rows_dev, void* stream) {
+  PK_REQUIRE(x && y && gamma && beta, "pk_layernorm_bf16: null pointer");
+  PK_REQUIRE(dim % 4 == 0 && dim >= 4 && dim <= 1024, "pk_layernorm_bf16: dim %d must be a multiple of 4 in [4,1024]", dim);
+  if (rows == 0) return PK_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(rows, 8);
+  __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y);
+  const int maxv = (dim / 4 + 31) / 32;
+  if (maxv <= 2) layernorm_bf16_kernel<2><<<grid, 256, 0, s>>>(x, yb, gamma, beta, eps, rows, dim, rowscale, row_index, rows_dev);
+  else if (maxv <= 3) layernorm_bf16_kernel<3><<<grid, 256, 0, s>>>(x, yb, gamma, beta, eps, rows, dim, rowscale, row_index, rows_dev);
+  else if (maxv <= 6) layernorm_bf16_kernel<6><<<grid, 256, 0, s>>>(x, yb, gamma, beta, eps, rows, dim, rowscale, row_index, rows_dev);
+  else layernorm_bf16_kernel<8><<<grid, 256, 0, s>>>(x, yb, gamma, beta, eps, rows, dim, rowscale, row_index, rows_dev);
+  return check_cuda(cudaGetLastError(), "layernorm_bf16_kernel");
+}
+
+extern "C" int pk_cls_head(const float* x, int batch, int seq_len, const int* cu_seqlens, int n_cls, int dim, const float* gamma,
+                           const float* beta, float eps, const float* head_w, const float* head_b, int num_classes, float* logits,
+                           void* stream) {
+  PK_REQUIRE(x && gamma && beta && head_w && logits, "pk_cls_head: null pointer");
+  PK_REQUIRE(dim % 4 == 0 && dim <= 1024 && n_cls >= 1, "pk_cls_head: dim %d must be a multiple of 4, <= 1024", dim);
+  if (batch == 0) return PK_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = (batch + kHeadGroup - 1) / kHeadGroup;
+  const size_t smem = (size_t)kHeadGroup * dim * sizeof(float);
+  const int maxv = (dim / 4 + 31) / 32;
+  if (maxv <= 3)
+    cls_head_kernel<3><<<grid, 256, smem, s>>>(x, batch, seq_len, cu_seqlens, n_cls, dim, gamma, beta, eps, head_w, head_b, num_classes, logits);
+  else
+    cls_head_kernel<8><<<grid, 256, smem, s>>>(x, batch, seq_len, cu_seqlens, n_cls, dim, gamma, beta, eps, head_w, head_b, num_classes, logits);
+  return check_cuda(cudaGetLastError(), "cls_head_kernel");
+}
+
+extern "C" int pk_token_norm_score(const float* x, float* scores, int batch, int seq_len, int dim, void* stream) {
+  PK_REQUIRE(x && scores && dim % 4 == 0 && seq_len >= 1, "pk_token_norm_score: bad arguments");
+  const long long total = (long long)batch * (seq_len - 1);
+  if (total == 0) return PK_OK;
+  token_norm_score_kernel<<<grid_for(total, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, scores, batch, seq_len, dim);
+  return check_cuda(cudaGetLastError(), "token_norm_score_kernel");
+}
+
+extern "C" int pk_topk_select(const float* scores, int* kept, int batch, int n, int k, void* stream) {
+  PK_REQUIRE(scores && kept, "pk_topk_select: null pointer");
+  PK_REQUIRE(n >= 0 && n <= 4096 && k >= 0 && k <= n, "pk_topk_select: need 0 <= k <= n <= 4096 (n=%d k=%d)", n, k);
+  if (batch == 0 || k == 0) return PK_OK;
+  topk_select_kernel<<<batch, 256, (size_t)n * sizeof(float), static_cast<cudaStream_t>(stream)>>>(scores, kept, n, k);
+  return check_cuda(cudaGetLastError(), "topk_select_kernel");
+}
+
+extern "C" int pk_gather_rows(const float* x, float* y, const int* kept, int batch, int seq_len, int k, int dim, void* stream) {
+  PK_REQUIRE(x && y && (kept || k == 0) && dim % 4 == 0, "pk_gather_rows: bad arguments");
+  const long long total = (long long)batch * (k + 1);
+  if (total == 0) return PK_OK;
+  gather_rows_kernel<<<grid_for(total, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, kept, batch, seq_len, k, dim);
+  return check_cuda(cudaGetLastError(), "gather_rows_kernel");
+}

@@ -1,0 +1,134 @@
+// peekvit_b200 — per-process runtime: error text, device context, TMA descriptor cache.
+#include "pk_common.cuh"
+#include "../../include/peekvit_b200.h"
+
+#include <cstdarg>
+#include <mutex>
+#include <unordered_map>
+
+namespace pk {
+
+static thread_local char tl_error[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return PK_OK;
+  set_last_error("CUDA error %d (%s) in %s", static_cast<int>(e), cudaGetErrorString(e), what);
+  return PK_ERR_CUDA;
+}
+
+struct Context {
+  int device = -1;
+  int sms = 0;
+  unsigned int* flag = nullptr;
+  PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+};
+static Context g_ctx;
+static std::mutex g_mu;
+
+int num_sms() { return g_ctx.sms > 0 ? g_ctx.sms : 148; }
+unsigned int* device_flag_ptr() { return g_ctx.flag; }
+
+static int init_context(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_ctx.device == device && g_ctx.flag) return PK_OK;
+  PK_CHECK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PK_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_last_error("peekvit_b200 needs an sm_100a device (B200); device %d is sm_%d%d", device, prop.major, prop.minor);
+    return PK_ERR_UNSUPPORTED;
+  }
+  g_ctx.sms = prop.multiProcessorCount;
+  PK_CHECK_CUDA(cudaMalloc(&g_ctx.flag, sizeof(unsigned int)));
+  PK_CHECK_CUDA(cudaMemset(g_ctx.flag, 0, sizeof(unsigned int)));
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  PK_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled not available from the driver");
+    return PK_ERR_UNSUPPORTED;
+  }
+  g_ctx.encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  g_ctx.device = device;
+  return PK_OK;
+}
+
+struct TmapKey {
+  const void* base;
+  uint64_t rows, cols, ld;
+  uint32_t box_rows, box_cols;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base);
+    h = h * 1000003u ^ k.rows;
+    h = h * 1000003u ^ k.cols;
+    h = h * 1000003u ^ k.ld;
+    h = h * 1000003u ^ (static_cast<size_t>(k.box_rows) << 16 | k.box_cols);
+    return h;
+  }
+};
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                      uint32_t box_rows, uint32_t box_cols) {
+  if (!g_ctx.encode) {
+    set_last_error("pk_init() has not been called");
+    return PK_ERR_INVALID;
+  }
+  TmapKey key{base, rows, cols, ld_elems, box_rows, box_cols};
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_tmaps.find(key);
+  if (it != g_tmaps.end()) {
+    *out = it->second;
+    return PK_OK;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = g_ctx.encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%llu cols=%llu ld=%llu box=%ux%u", static_cast<int>(r), base,
+                   (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows, box_cols);
+    return PK_ERR_CUDA;
+  }
+  if (g_tmaps.size() > 8192) g_tmaps.clear();
+  g_tmaps.emplace(key, *out);
+  return PK_OK;
+}
+
+}  // namespace pk
+
+extern "C" int pk_abi_version(void) { return PK_ABI_VERSION; }
+
+extern "C" int pk_init(int device) { return pk::init_context(device); }
+
+extern "C" const char* pk_last_error(void) { return pk::tl_error; }
+
+extern "C" int pk_num_sms(void) { return pk::num_sms(); }
+
+extern "C" int pk_device_flag(int reset) {
+  using namespace pk;
+  if (!g_ctx.flag) {
+    set_last_error("pk_init() has not been called");
+    return PK_ERR_INVALID;
+  }
+  unsigned int v = 0;
+  PK_CHECK_CUDA(cudaDeviceSynchronize());
+  PK_CHECK_CUDA(cudaMemcpy(&v, g_ctx.flag, sizeof(v), cudaMemcpyDeviceToHost));
+  if (reset && v != 0) PK_CHECK_CUDA(cudaMemset(g_ctx.flag, 0, sizeof(unsigned int)));
+  return static_cast<int>(v);
+}
