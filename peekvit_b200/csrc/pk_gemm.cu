@@ -165,12 +165,43 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint32_t aph = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+      const int row_base = m_blk * kBM + q * 32 + r_sub;       // + it*4 in phase 2
+      // Residual operands do not depend on the accumulators: fetch the first chunk's rows before
+      // blocking on the MMA, and chunk c+1's while chunk c is processed (keeps 8 independent
+      // 16-byte loads in flight per lane instead of a load->add->store chain).
+      float4 rnext[8];
+      auto load_resid = [&](int ch, float4 (&dst)[8]) {
+        if constexpr (EPI == PK_EPI_BIAS_RESID_F32) {
+          const int gcol = n_blk * BN + half * (BN / 2) + ch * 32 + c4 * 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int grow = row_base + it * 4;
+            dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (grow < M && gcol < p.N) {
+              long long rrow = grow;
+              if (p.rows_per_group > 0) {
+                const int g = grow / p.rows_per_group, pos = grow - g * p.rows_per_group;
+                rrow = p.resid_is_pos ? static_cast<long long>(p.group_offset + pos)
+                                      : static_cast<long long>(g) * p.group_stride + p.group_offset + pos;
+              }
+              dst[it] = *reinterpret_cast<const float4*>(p.resid + rrow * p.ldr + gcol);
+            }
+          }
+        }
+      };
+      load_resid(0, rnext);
       if (!mbar_wait(smem_u32(&tfull_bar[as]), aph, p.flag, 0x400u + as)) break;
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
-#pragma unroll 1
+#pragma unroll
       for (int ch = 0; ch < kChunksPerWarp; ++ch) {
         const int col0 = half * (BN / 2) + ch * 32;
+        float4 rcur[8];
+        if constexpr (EPI == PK_EPI_BIAS_RESID_F32) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) rcur[it] = rnext[it];
+          if (ch + 1 < kChunksPerWarp) load_resid(ch + 1, rnext);
+        }
         uint32_t v[32];
         tmem_ld_32x32(t_row + static_cast<uint32_t>(col0), v);
         tmem_ld_wait();
@@ -195,16 +226,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int rr = it * 4 + r_sub;
-          const int grow = m_blk * kBM + q * 32 + rr;
+          const int grow = row_base + it * 4;
           if (grow < M && col_ok) {
             float4 a = *reinterpret_cast<const float4*>(stg + rr * kStagePitch + c4 * 4);
             a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
             long long orow = grow;
-            long long rrow = grow;
             if (p.rows_per_group > 0) {
               const int g = grow / p.rows_per_group, pos = grow - g * p.rows_per_group;
               orow = static_cast<long long>(g) * p.group_stride + p.group_offset + pos;
-              rrow = p.resid_is_pos ? static_cast<long long>(p.group_offset + pos) : orow;
             }
             if constexpr (EPI == PK_EPI_BIAS_GELU_BF16) {
               a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
@@ -214,8 +243,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const float sc = p.rowscale[grow];
                 a.x *= sc; a.y *= sc; a.z *= sc; a.w *= sc;
               }
-              const float4 r4 = *reinterpret_cast<const float4*>(p.resid + rrow * p.ldr + gcol);
-              a.x += r4.x; a.y += r4.y; a.z += r4.z; a.w += r4.w;
+              a.x += rcur[it].x; a.y += rcur[it].y; a.z += rcur[it].z; a.w += rcur[it].w;
             }
             if constexpr (EPI == PK_EPI_BIAS_BF16 || EPI == PK_EPI_BIAS_GELU_BF16) {
               uint2 o = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));

@@ -318,6 +318,10 @@ class _ModelBase(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return runner.run(self, x)
 
+    def forward_host(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Host batch in, host logits out; H2D copies overlap compute (runner.run_host)."""
+        return runner.run_host(self, x_host, out_host)
+
 
 class VisionTransformer(_ModelBase):
     """Drop-in for reference models/vit.py:100-315."""

@@ -16,7 +16,16 @@ from ._lib import (AttentionArgs, GemmArgs, PK_EPI_BIAS_BF16, PK_EPI_BIAS_F32, P
                    PK_EPI_BIAS_RESID_F32, check)
 
 
+# Launch accounting for bench.py: every wrapper below launches exactly one kernel of ours.
+launch_count = 0
+# When a list is installed here, gemm() brackets its launch with CUDA events on the launching
+# stream and appends (start, end, flops): the live per-kernel timing the roofline line needs.
+gemm_timeline = None
+
+
 def _lib_for(t: torch.Tensor):
+    global launch_count
+    launch_count += 1
     if not t.is_cuda:
         raise RuntimeError("peekvit_b200 kernels need CUDA tensors on a B200; there is no CPU path")
     return _lib.init(t.device.index if t.device.index is not None else torch.cuda.current_device())
@@ -69,6 +78,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
     args.resid_is_pos = int(resid_is_pos)
     args.m_dev = _ptr(m_dev, torch.int32)
     args.block_n, args.max_ctas = block_n, max_ctas
+    if gemm_timeline is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.pk_gemm_bf16(C.byref(args), _stream()), "pk_gemm_bf16")
+        e1.record()
+        gemm_timeline.append((e0, e1, 2.0 * M * N * K))
+        return out
     check(lib.pk_gemm_bf16(C.byref(args), _stream()), "pk_gemm_bf16")
     return out
 

@@ -1,0 +1,324 @@
+"""GPU parity tests of every C-ABI kernel against the torch fp32 expression at the cited
+reference call site.  All calls go through ``peekvit_b200.ops`` -> ctypes -> libpeekvit_b200.so.
+
+Tolerances (written here on purpose): fp32 outputs 2e-5 relative to max|ref| (fp32 accumulate of
+bf16 operands is compared with an fp32 matmul of the *same* bf16-rounded operands); bf16 outputs
+1e-2 relative (north star), typically 3e-3 = one bf16 rounding; index outputs bit-exact.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+TOL_F32 = 2e-5
+TOL_BF16 = 1e-2
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from peekvit_b200 import ops as _ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return _ops
+
+
+def rel_err(got, ref):
+    got, ref = got.float(), ref.float()
+    return ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item()
+
+
+def _operands(M, N, K, seed=0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    a = (torch.randn(M, K, device=DEV, generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV, generator=g) * 0.1
+    return a, w, bias
+
+
+# ------------------------------------------------------------------ GEMM (K1,K3,K5,K6,K7)
+@pytest.mark.parametrize("shape", [(1, 64, 64), (127, 192, 64), (128, 128, 128), (129, 256, 64), (300, 768, 768),
+                                   (1000, 2304, 768), (1576, 3072, 768), (257, 768, 3072), (64, 128, 192),
+                                   (394, 1152, 384), (785 * 2, 768, 256), (33, 576, 192), (513, 1000, 768)])
+@pytest.mark.parametrize("block_n", [0, 128, 192, 256])
+def test_gemm_f32(ops, shape, block_n):
+    from peekvit_b200._lib import PK_EPI_BIAS_F32
+    M, N, K = shape
+    a, w, bias = _operands(M, N, K)
+    out = torch.full((M, N), float("nan"), device=DEV)
+    ops.gemm(a, w, bias, out, PK_EPI_BIAS_F32, block_n=block_n)
+    assert ops.device_flag() == 0
+    assert rel_err(out, a.float() @ w.float().t() + bias) < TOL_F32
+
+
+def test_gemm_epilogues(ops):
+    from peekvit_b200._lib import PK_EPI_BIAS_BF16, PK_EPI_BIAS_GELU_BF16, PK_EPI_BIAS_RESID_F32
+    M, N, K = 1000, 768, 768
+    a, w, bias = _operands(M, N, K, seed=1)
+    acc = a.float() @ w.float().t() + bias
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, w, bias, out, PK_EPI_BIAS_BF16)
+    assert rel_err(out, acc) < TOL_BF16
+    ops.gemm(a, w, bias, out, PK_EPI_BIAS_GELU_BF16)
+    assert rel_err(out, torch.nn.functional.gelu(acc)) < TOL_BF16      # exact (erf) GELU, blocks.py:82
+    x = torch.randn(M, N, device=DEV)
+    x0, rs = x.clone(), torch.rand(M, device=DEV)
+    ops.gemm(a, w, bias, x, PK_EPI_BIAS_RESID_F32, resid=x, rowscale=rs)   # in place on the residual stream
+    assert rel_err(x, rs[:, None] * acc + x0) < TOL_F32
+    ops.gemm(a, w, None, x, PK_EPI_BIAS_RESID_F32, resid=x0)               # no bias, out-of-place residual
+    assert rel_err(x, a.float() @ w.float().t() + x0) < TOL_F32
+    assert ops.device_flag() == 0
+
+
+def test_gelu_epilogue_accuracy_fp32_grid(ops):
+    """The in-kernel erf (A&S 7.1.26) against torch's exact GELU over a dense grid, before bf16
+    rounding matters: identity weight trick (acc = x exactly representable in bf16)."""
+    from peekvit_b200._lib import PK_EPI_BIAS_GELU_BF16
+    K = 64
+    xs = torch.linspace(-8, 8, 128 * 64, device=DEV).to(torch.bfloat16).view(128, 64)
+    eye = torch.eye(K, device=DEV, dtype=torch.bfloat16)
+    out = torch.empty(128, 64, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(xs, eye, None, out, PK_EPI_BIAS_GELU_BF16)
+    ref = torch.nn.functional.gelu(xs.float())
+    # within one bf16 ulp of torch's exact GELU everywhere on the grid
+    assert ((out.float() - ref).abs() <= ref.abs() * 2.0 ** -8 + 2e-6).all()
+
+
+def test_gemm_patch_remap_and_device_m(ops):
+    from peekvit_b200._lib import PK_EPI_BIAS_F32, PK_EPI_BIAS_RESID_F32
+    G, P, seq, off, D, Kp = 5, 60, 66, 3, 256, 192
+    a, w, bias = _operands(G * P, D, Kp, seed=2)
+    pos = torch.randn(seq, D, device=DEV)
+    x = torch.zeros(G * seq, D, device=DEV)
+    ops.gemm(a, w, bias, x, PK_EPI_BIAS_RESID_F32, resid=pos, rows_per_group=P, group_stride=seq, group_offset=off,
+             resid_is_pos=True)
+    ref = torch.zeros(G, seq, D, device=DEV)
+    ref[:, off:off + P] = (a.float() @ w.float().t() + bias).view(G, P, D) + pos[off:off + P]
+    assert rel_err(x, ref.view(G * seq, D)) < TOL_F32
+    assert (x.view(G, seq, D)[:, :off] == 0).all() and (x.view(G, seq, D)[:, off + P:] == 0).all()
+    M, N, K = 1000, 384, 384
+    a, w, _ = _operands(M, N, K, seed=3)
+    out = torch.zeros(M, N, device=DEV)
+    for m in (0, 1, 333, 1000):
+        out.zero_()
+        ops.gemm(a, w, None, out, PK_EPI_BIAS_F32, m_dev=torch.tensor([m], device=DEV, dtype=torch.int32))
+        ref = a.float() @ w.float().t()
+        if m:
+            assert rel_err(out[:m], ref[:m]) < TOL_F32
+        assert (out[m:] == 0).all()
+    assert ops.device_flag() == 0
+
+
+def test_gemm_rejects_bad_arguments(ops):
+    from peekvit_b200._lib import PK_EPI_BIAS_F32, PkError
+    a, w, bias = _operands(64, 64, 96)          # K not a multiple of 64
+    with pytest.raises(PkError):
+        ops.gemm(a, w, bias, torch.empty(64, 64, device=DEV), PK_EPI_BIAS_F32)
+    with pytest.raises(TypeError):
+        ops.gemm(a.float(), w, bias, torch.empty(64, 64, device=DEV), PK_EPI_BIAS_F32)
+    with pytest.raises(RuntimeError):
+        ops.layernorm(torch.randn(4, 64), torch.ones(64), torch.zeros(64), 1e-5)   # CPU tensor: no CPU path
+
+
+def test_gemm_linearity_full_size(ops):
+    """Size-independent property at the BASELINE config-B layer shape (M = 197*256 rows):
+    GEMM(a, w1 + w2) == GEMM(a, w1) + GEMM(a, w2) with exactly representable operands."""
+    from peekvit_b200._lib import PK_EPI_BIAS_F32
+    M, N, K = 197 * 256, 768, 768
+    g = torch.Generator(device=DEV).manual_seed(5)
+    a = torch.randint(-4, 5, (M, K), device=DEV, generator=g).to(torch.bfloat16)
+    w1 = torch.randint(-4, 5, (N, K), device=DEV, generator=g).to(torch.bfloat16)
+    w2 = torch.randint(-4, 5, (N, K), device=DEV, generator=g).to(torch.bfloat16)
+    o1, o2, o3 = (torch.empty(M, N, device=DEV) for _ in range(3))
+    ops.gemm(a, w1, None, o1, PK_EPI_BIAS_F32)
+    ops.gemm(a, w2, None, o2, PK_EPI_BIAS_F32)
+    ops.gemm(a, (w1.float() + w2.float()).to(torch.bfloat16), None, o3, PK_EPI_BIAS_F32)
+    assert torch.equal(o1 + o2, o3)             # small integers: every partial sum is exact in fp32
+    assert ops.device_flag() == 0
+
+
+# ------------------------------------------------------------------ LayerNorm (K2)
+@pytest.mark.parametrize("D", [64, 128, 192, 256, 384, 768, 1024])
+@pytest.mark.parametrize("eps", [1e-5, 1e-6])
+def test_layernorm(ops, D, eps):
+    g = torch.Generator(device=DEV).manual_seed(D)
+    x = torch.randn(1237, D, device=DEV, generator=g) * 2 + 0.3
+    gamma, beta = torch.randn(D, device=DEV, generator=g), torch.randn(D, device=DEV, generator=g)
+    y = ops.layernorm(x, gamma, beta, eps)
+    assert rel_err(y, torch.nn.functional.layer_norm(x, (D,), gamma, beta, eps)) < TOL_BF16
+
+
+def test_layernorm_rowscale_gather_devrows(ops):
+    x = torch.randn(1000, 384, device=DEV)
+    gamma, beta = torch.randn(384, device=DEV), torch.randn(384, device=DEV)
+    rs = torch.rand(500, device=DEV)
+    idx = torch.randperm(1000, device=DEV)[:500].to(torch.int32)
+    y = ops.layernorm(x, gamma, beta, 1e-6, rowscale=rs, row_index=idx)
+    ref = rs[:, None] * torch.nn.functional.layer_norm(x[idx.long()], (384,), gamma, beta, 1e-6)
+    assert rel_err(y, ref) < TOL_BF16
+    y = torch.zeros(1000, 384, device=DEV, dtype=torch.bfloat16)
+    ops.layernorm(x, gamma, beta, 1e-5, y, rows_dev=torch.tensor([123], device=DEV, dtype=torch.int32))
+    assert (y[123:] == 0).all() and y[:123].abs().sum() > 0
+    # zero rows (a masked ResidualViT token): LN(0) = beta
+    y = ops.layernorm(torch.zeros(3, 384, device=DEV), gamma, beta, 1e-6)
+    assert rel_err(y, beta.expand(3, -1)) < TOL_BF16
+
+
+# ------------------------------------------------------------------ attention (K4)
+def ref_attention(qkv, B, H, dh, lens, key_mult=None, extra_kv=None, extra_mult=None):
+    """softmax(q k^T / sqrt(dh) [+ log mult]) v per sample and head, fp32 (torch functional MHA math)."""
+    D = H * dh
+    out = torch.zeros(qkv.shape[0], D, device=qkv.device)
+    start = 0
+    for b in range(B):
+        n = lens[b]
+        blk = qkv[start:start + n].float()
+        q, k, v = (blk[:, i * D:(i + 1) * D].view(n, H, dh).transpose(0, 1) for i in range(3))
+        bias = torch.zeros(n, device=qkv.device) if key_mult is None else key_mult[start:start + n].log()
+        if extra_kv is not None and extra_mult[b] > 0:
+            k = torch.cat([k, extra_kv[:D].float().view(H, 1, dh)], 1)
+            v = torch.cat([v, extra_kv[D:].float().view(H, 1, dh)], 1)
+            bias = torch.cat([bias, extra_mult[b:b + 1].log()])
+        o = torch.softmax((q @ k.transpose(1, 2)) / math.sqrt(dh) + bias, -1) @ v
+        out[start:start + n] = o.transpose(0, 1).reshape(n, D)
+        start += n
+    return out
+
+
+@pytest.mark.parametrize("cfg", [(3, 2, 64, 17), (2, 12, 64, 197), (2, 8, 32, 785), (4, 6, 64, 64), (1, 3, 64, 1),
+                                 (2, 2, 32, 65), (3, 6, 64, 198), (1, 12, 64, 257)])
+def test_attention_dense(ops, cfg):
+    B, H, dh, N = cfg
+    D = H * dh
+    qkv = torch.randn(B * N, 3 * D, device=DEV).to(torch.bfloat16)
+    out = torch.zeros(B * N, D, device=DEV, dtype=torch.bfloat16)
+    ops.attention(qkv, out, B, H, dh, seq_len=N)
+    assert rel_err(out, ref_attention(qkv, B, H, dh, [N] * B)) < TOL_BF16
+
+
+def test_attention_ragged_multiplicity_virtual_key(ops):
+    B, H, dh = 6, 6, 64
+    D = H * dh
+    lens = [3, 70, 198, 1, 129, 64]
+    cu = torch.tensor([0] + torch.tensor(lens).cumsum(0).tolist(), device=DEV, dtype=torch.int32)
+    rows = sum(lens)
+    qkv = torch.randn(rows, 3 * D, device=DEV).to(torch.bfloat16)
+    out = torch.zeros(rows, D, device=DEV, dtype=torch.bfloat16)
+    ops.attention(qkv, out, B, H, dh, cu_seqlens=cu, max_seq_len=max(lens))
+    assert rel_err(out, ref_attention(qkv, B, H, dh, lens)) < TOL_BF16
+    km = torch.randint(1, 40, (rows,), device=DEV).float()
+    km[5] = 0.0                                          # multiplicity 0 = dead row: never attended to
+    ekv = (torch.randn(2 * D, device=DEV) * 0.5).to(torch.bfloat16)
+    em = torch.tensor([0.0, 5.0, 100.0, 7.0, 0.0, 1.0], device=DEV)   # sample 5: 64 keys + virtual key -> second tile
+    ops.attention(qkv, out, B, H, dh, cu_seqlens=cu, max_seq_len=max(lens), key_mult=km, extra_kv=ekv, extra_mult=em)
+    assert rel_err(out, ref_attention(qkv, B, H, dh, lens, km, ekv, em)) < TOL_BF16
+
+
+def test_attention_equals_dense_reference_with_zero_tokens(ops):
+    """The compaction identity the sparse models rely on: M zeroed tokens
+    inside a dense sequence == one virtual bias key with multiplicity M."""
+    H, dh, n_live, n_dead = 6, 64, 50, 30
+    D = H * dh
+    bias_kv = (torch.randn(2 * D, device=DEV) * 0.3).to(torch.bfloat16)
+    live = torch.randn(n_live, 3 * D, device=DEV).to(torch.bfloat16)
+    dead = torch.cat([torch.zeros(D, device=DEV, dtype=torch.bfloat16), bias_kv]).expand(n_dead, -1)   # k=b_k, v=b_v
+    dense = torch.cat([live, dead]).contiguous()
+    out_dense = torch.zeros(n_live + n_dead, D, device=DEV, dtype=torch.bfloat16)
+    ops.attention(dense, out_dense, 1, H, dh, seq_len=n_live + n_dead)
+    out_sparse = torch.zeros(n_live, D, device=DEV, dtype=torch.bfloat16)
+    ops.attention(live.contiguous(), out_sparse, 1, H, dh, seq_len=n_live, extra_kv=bias_kv,
+                  extra_mult=torch.tensor([float(n_dead)], device=DEV))
+    assert rel_err(out_sparse, out_dense[:n_live]) < TOL_BF16
+
+
+# ------------------------------------------------------------------ patchify / token rows / head (K1,K8)
+@pytest.mark.parametrize("S,p", [(64, 8), (224, 16), (32, 8), (224, 8), (48, 16)])
+def test_patchify(ops, S, p):
+    img = torch.randn(3, 3, S, S, device=DEV)
+    got = ops.patchify(img, p)
+    ref = torch.nn.functional.unfold(img, kernel_size=p, stride=p).transpose(1, 2).reshape(3 * (S // p) ** 2, 3 * p * p)
+    assert torch.equal(got, ref.to(torch.bfloat16))        # (c,i,j) K order == conv_proj.weight.reshape(D,-1)
+
+
+def test_patch_embed_matches_conv2d(ops):
+    """patchify + GEMM(+bias+pos) == Conv2d(k=s=p) + flatten + transpose + pos (vit.py:212-220,:92)."""
+    from peekvit_b200._lib import PK_EPI_BIAS_RESID_F32
+    B, S, p, D = 4, 64, 8, 128
+    img = torch.randn(B, 3, S, S, device=DEV)
+    wt = (torch.randn(D, 3, p, p, device=DEV) / math.sqrt(3 * p * p))
+    bias, pos = torch.randn(D, device=DEV) * 0.1, torch.randn(65, D, device=DEV) * 0.02
+    x = torch.zeros(B * 65, D, device=DEV)
+    ops.gemm(ops.patchify(img, p), wt.reshape(D, -1).to(torch.bfloat16).contiguous(), bias, x, PK_EPI_BIAS_RESID_F32, resid=pos,
+             rows_per_group=64, group_stride=65, group_offset=1, resid_is_pos=True)
+    ref = torch.nn.functional.conv2d(img.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float(), bias, stride=p)
+    ref = ref.reshape(B, D, 64).permute(0, 2, 1) + pos[1:]
+    assert rel_err(x.view(B, 65, D)[:, 1:], ref) < TOL_F32
+
+
+def test_fill_token_rows(ops):
+    B, seq, T, D = 3, 20, 2, 256
+    x = torch.zeros(B * seq, D, device=DEV)
+    tok, pos = torch.randn(T, D, device=DEV), torch.randn(seq, D, device=DEV)
+    ops.fill_token_rows(x, B, seq, 1, tok, pos, scale=0.4)
+    ref = torch.zeros(B, seq, D, device=DEV)
+    ref[:, 1:1 + T] = 0.4 * tok + pos[1:1 + T]
+    assert rel_err(x, ref.view(B * seq, D)) < 1e-6
+    x.zero_()
+    ops.fill_token_rows(x, B, seq, seq - 1, None, None, scale=0.7, n_tokens=1)
+    xv = x.view(B, seq, D)
+    assert (xv[:, -1] == 0.7).all() and (xv[:, :-1] == 0).all()
+
+
+@pytest.mark.parametrize("cfg", [(5, 128, 10, 1), (19, 768, 1000, 1), (4, 384, 7, 2), (1, 64, 10, 1), (9, 256, 10, 1)])
+def test_cls_head(ops, cfg):
+    B, D, C, T = cfg
+    seq = 11
+    x = torch.randn(B * seq, D, device=DEV)
+    gamma, beta = torch.randn(D, device=DEV), torch.randn(D, device=DEV)
+    hw, hb = torch.randn(C, D, device=DEV) / math.sqrt(D), torch.randn(C, device=DEV)
+    got = ops.cls_head(x, B, seq, T, gamma, beta, 1e-5, hw, hb)
+    f = torch.nn.functional.layer_norm(x.view(B, seq, D)[:, :T], (D,), gamma, beta, 1e-5).sum(1)    # class-token SUM
+    assert rel_err(got, f @ hw.t() + hb) < TOL_F32
+    cu = (torch.arange(B + 1, device=DEV) * seq).to(torch.int32)
+    got2 = ops.cls_head(x, B, 0, T, gamma, beta, 1e-5, hw, hb, cu_seqlens=cu)
+    assert torch.equal(got, got2)
+
+
+# ------------------------------------------------------------------ RankViT kernels (K9,K10,K11)
+def test_token_norm_score(ops):
+    B, seq, D = 7, 197, 768
+    x = torch.randn(B * seq, D, device=DEV)
+    sc = ops.token_norm_score(x, B, seq)
+    assert rel_err(sc, torch.norm(x.view(B, seq, D)[:, 1:], dim=-1)) < 1e-6
+
+
+@pytest.mark.parametrize("n,k", [(196, 1), (196, 98), (196, 196), (784, 392), (49, 25), (1, 1), (4096, 1000)])
+def test_topk_bit_exact(ops, n, k):
+    sc = torch.randn(5, n, device=DEV)
+    kept = ops.topk_select(sc, k)
+    assert torch.equal(kept.long(), torch.argsort(sc, dim=-1, descending=True, stable=True)[:, :k])
+
+
+def test_topk_ties_lowest_index(ops):
+    adv = torch.tensor([[1., 3, 3, 0, 3, 1, -0., 0.], [2.] * 8, [0., -0., 0., 1e-45, -0., 5, 5, 5]], device=DEV)
+    for k in (1, 3, 8):
+        kept = ops.topk_select(adv, k)
+        assert torch.equal(kept.cpu().long(), torch.argsort(adv.cpu(), dim=-1, descending=True, stable=True)[:, :k])
+    assert ops.topk_select(adv, 3).cpu().tolist() == [[1, 2, 4], [0, 1, 2], [5, 6, 7]]
+    big = torch.randn(3, 4096, device=DEV).round(decimals=1)       # ~100 distinct values: ties everywhere
+    assert torch.equal(ops.topk_select(big, 1000).long(), torch.argsort(big, dim=-1, descending=True, stable=True)[:, :1000])
+
+
+def test_gather_rows_and_sort_and_drop(ops):
+    """score -> select -> compact == reference sort_and_drop (rankvit.py:55-77) on the same input."""
+    B, seq, D, budget = 6, 197, 768, 0.5
+    x = torch.randn(B * seq, D, device=DEV)
+    k = math.ceil((seq - 1) * budget)
+    kept = ops.topk_select(ops.token_norm_score(x, B, seq), k)
+    y = ops.gather_rows(x, kept, B, seq).view(B, k + 1, D)
+    xr = x.view(B, seq, D)
+    cls, tok = xr[:, :1], xr[:, 1:]
+    idx = torch.argsort(torch.norm(tok, dim=-1), dim=-1, descending=True, stable=True).unsqueeze(-1)
+    ref = torch.cat([cls, torch.gather(tok, 1, idx.expand(-1, -1, D))[:, :k]], 1)
+    assert torch.equal(y, ref)
