@@ -60,10 +60,15 @@ typedef struct pk_gemm_args {
   const float* rowscale; /* f32 [M] or NULL */
   /* Row remap for the patch-embedding GEMM (vit.py:212-236,:92): when rows_per_group > 0,
    * GEMM row m = g*rows_per_group + p is written to out row g*group_stride + group_offset + p,
-   * and the residual row is (group_offset + p) of a [seq, N] table when resid_is_pos != 0
+   * and the residual row is (pos_offset + p) of a [seq, N] table when resid_is_pos != 0
    * (pos_embedding), else the out row. */
-  int rows_per_group, group_stride, group_offset, resid_is_pos;
+  int rows_per_group, group_stride, group_offset, resid_is_pos, pos_offset;
   const int* m_dev;      /* optional device-side row count (<= M): ragged batches without a host sync */
+  const int* row_begin_dev; /* optional device-side first row: the launch covers rows [*row_begin_dev,
+                               *row_begin_dev + *m_dev) of A / out (one expert's segment of a grouped GEMM,
+                               moevit.py:54-59 computed for the routed tokens only) */
+  const int* out_row_index; /* optional int32 [rows]: GEMM row r is written to (and its residual read from)
+                               row out_row_index[r] (un-permute of expert-sorted tokens) */
   int block_n;           /* 0 = auto, or 128 / 192 / 256 */
   int max_ctas;          /* 0 = one CTA per SM */
 } pk_gemm_args;
@@ -124,6 +129,76 @@ int pk_token_norm_score(const float* x, float* scores, int batch, int seq_len, i
 int pk_topk_select(const float* scores, int* kept, int batch, int n, int k, void* stream);
 /* y[b, 0, :] = x[b, 0, :]; y[b, 1+r, :] = x[b, 1+kept[b,r], :]  (rankvit.py:71-77), f32 rows. */
 int pk_gather_rows(const float* x, float* y, const int* kept, int batch, int seq_len, int k, int dim, void* stream);
+
+/* ---- ragged-batch plumbing shared by the sparse models -------------------------------- */
+/* cu_out[0..n] = exclusive prefix sum of lens[0..n) (cu_out[n] = total, also written to *total_out). */
+int pk_exclusive_scan_i32(const int* lens, int n, int* cu_out, int* total_out, void* stream);
+
+/* Gather the kept rows of every sample into a new packed buffer:
+ * x_out[cu_out[b] + dst_local[r]] = scale_in[r] * x_in[r] for rows with dst_local[r] >= 0, carrying up to three
+ * per-row float attributes along.  ghost != 0 additionally zero-fills each sample's LAST output row
+ * (a0_out = 0, scale_out = 1): the ResidualViT ghost slot. */
+typedef struct pk_compact_args {
+  const float* x_in; float* x_out; int dim;
+  const int* cu_in; const int* cu_out; int batch;
+  int rows_in_cap;                 /* host-side upper bound on cu_in[batch] (grid sizing) */
+  const int* dst_local; const int* sample_of;
+  const float* scale_in; float* scale_out;
+  const float* a0_in; float* a0_out;
+  const float* a1_in; float* a1_out;
+  const float* a2_in; float* a2_out;
+  int ghost;
+} pk_compact_args;
+int pk_compact_rows(const pk_compact_args* args, void* stream);
+
+/* ---- K12/K13: ResidualViT budget gating (residualvit.py:47-74,197-244) ----------------- */
+/* thr_out[0] = 1 - mean over the batch and D of the budget-token rows (fixed budget: residualvit.py:208,:62). */
+int pk_budget_mean_threshold(const float* x, const int* cu_seqlens, int batch, int budget_pos, int dim, float* thr_out,
+                             void* stream);
+
+/* Per sample: threshold from its budget token, soft mask of every live row
+ *   mask = relu(sigmoid((w.x + b)/temp + gate_bias) - thr)         (sigmoid gate, blocks.py:62-69, residualvit.py:62-69)
+ *   mask = round(sigmoid(w.x + b))                                 (gumbel gate in eval, blocks.py:55-57)
+ * the keep decision (mask > 0 and multiplicity > 0; the first n_special rows always), the position of every
+ * kept row in the compacted sample, the new length (+1 ghost slot when gated) and the multiplicity folded
+ * into the virtual key / ghost row. */
+typedef struct pk_residual_gate_args {
+  const float* x; const int* cu_in; const float* mult_in;
+  int batch, dim, max_seq_len;
+  int n_special, budget_pos;       /* budget_pos = local row of the budget token, or -1 */
+  int gated;                       /* 0: plain layer (skip None): keep every live row with mask 1, no ghost */
+  const float* gate_w; float gate_b, gate_temp, gate_bias; int gate_type;   /* 0 sigmoid, 1 gumbel */
+  int thr_mode;                    /* 0: sigmoid(bt_w.budget_row + bt_b) per sample; 1: *thr_dev; 2: thr_const */
+  const float* bt_w; float bt_b; const float* thr_dev; float thr_const;
+  float* mask; int* dst_local; int* sample_of; int* new_len; float* mdrop;
+} pk_residual_gate_args;
+int pk_residual_gate_plan(const pk_residual_gate_args* args, void* stream);
+
+/* After the block: each sample's ghost row (its last row) becomes mlp0 = fc2(gelu(fc1.bias)) + fc2.bias with
+ * multiplicity mdrop[b] (what every dropped token equals when it leaves the reference block). */
+int pk_residual_ghost(float* x, float* mult, const int* cu_seqlens, const float* mdrop, const float* mlp0, int batch, int dim,
+                      void* stream);
+
+/* mask_pub[b,i] = mask[tok_row[b,i]] (the reference's block.mask, (B,N_img,1), utils/utils.py:100-122), then
+ * tok_row[b,i] moves to the compacted layout (dropped tokens -> the ghost row). */
+int pk_residual_publish(const float* mask, const int* dst_local, const int* cu_out, int* tok_row, float* mask_pub, int batch,
+                        int n_img, void* stream);
+
+/* ---- K14: AViT halting update + plan (adavit.py:140-219) -------------------------------- */
+typedef struct pk_avit_args {
+  const float* x; const int* cu_in; int batch, dim, seq_total;
+  float* c; float* R; const float* tokid;
+  float gate_scale, gate_center, eps; int last_layer, early_exit;
+  float* out_acc; float* rho; float* counter;
+  int* dst_local; int* sample_of; int* new_len; float* n_halted;
+} pk_avit_args;
+int pk_avit_halt_plan(const pk_avit_args* args, void* stream);
+
+/* ---- K15: MoE routing (moevit.py:23-32,49-61) ------------------------------------------- */
+/* expert[r] = argmax_e(LN(x[r]).gate_w[e] + gate_b[e]) (first maximum), then a stable counting sort:
+ * offsets[E+1], counts[E], src_of[pos] = original row of the pos-th expert-sorted row. */
+int pk_moe_route(const float* x, const float* gamma, const float* beta, float eps, const float* gate_w, const float* gate_b,
+                 int n_experts, int rows, int dim, int* expert, int* offsets, int* counts, int* src_of, void* stream);
 
 #ifdef __cplusplus
 }

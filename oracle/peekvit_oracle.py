@@ -132,11 +132,15 @@ def rank_keep_count(n_tokens: int, budget: float) -> int:
     return math.ceil(n_tokens * budget)
 
 
-def rankvit_forward(sd, cfg, images: Tensor, budget: Union[float, Sequence[float]] = 1.0) -> Tuple[Tensor, Dict]:
+def rankvit_forward(sd, cfg, images: Tensor, budget: Union[float, Sequence[float]] = 1.0,
+                    forced_kept: Optional[Dict[int, Tensor]] = None) -> Tuple[Tensor, Dict]:
     """``RankVisionTransformer.forward`` (reference rankvit.py:256-280); rank layers run
     ``sort_and_drop`` (rankvit.py:55-77) on the block's pre-LN input when
     ``current_budget != 1`` (rankvit.py:85-88): L2 norm over D, descending sort, keep the
-    first ``ceil(n*b)``, kept tokens in descending-norm order after the class token."""
+    first ``ceil(n*b)``, kept tokens in descending-norm order after the class token.
+    ``forced_kept`` (test hook) substitutes given index tensors for the selection of the listed
+    layers, to compare logits *given identical selections*: top-k is discontinuous, so a bf16-level
+    score perturbation can legitimately swap tokens at the cut."""
     rank_layers = list(cfg["rankvit_layers"])
     x = _tokens(images, sd, cfg)
     x = x + sd["encoder.pos_embedding"].to(x.dtype)
@@ -149,6 +153,9 @@ def rankvit_forward(sd, cfg, images: Tensor, budget: Union[float, Sequence[float
                 scores = torch.norm(tok, dim=-1)                       # rankvit.py:63
                 k = rank_keep_count(tok.shape[1], b)                   # rankvit.py:74
                 idx = stable_topk_desc(scores, k)                      # rankvit.py:67 (+tie rule)
+                if forced_kept is not None and i in forced_kept:
+                    assert forced_kept[i].shape == idx.shape
+                    idx = forced_kept[i].to(torch.int64)
                 kept = torch.gather(tok, 1, idx.unsqueeze(-1).expand(-1, -1, tok.shape[-1]))  # :71,75
                 x = torch.cat([cls, kept], dim=1)                      # :77
                 aux["scores"][i] = scores

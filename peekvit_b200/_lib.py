@@ -29,7 +29,8 @@ class GemmArgs(C.Structure):
         ("resid", c_void_p), ("ldr", c_longlong),
         ("rowscale", c_void_p),
         ("rows_per_group", c_int), ("group_stride", c_int), ("group_offset", c_int), ("resid_is_pos", c_int),
-        ("m_dev", c_void_p), ("block_n", c_int), ("max_ctas", c_int),
+        ("pos_offset", c_int),
+        ("m_dev", c_void_p), ("row_begin_dev", c_void_p), ("out_row_index", c_void_p), ("block_n", c_int), ("max_ctas", c_int),
     ]
 
 
@@ -40,6 +41,43 @@ class AttentionArgs(C.Structure):
         ("seq_len", c_int), ("cu_seqlens", c_void_p), ("max_seq_len", c_int),
         ("scale", c_float),
         ("key_mult", c_void_p), ("extra_kv", c_void_p), ("extra_mult", c_void_p),
+    ]
+
+
+class CompactArgs(C.Structure):
+    _fields_ = [
+        ("x_in", c_void_p), ("x_out", c_void_p), ("dim", c_int),
+        ("cu_in", c_void_p), ("cu_out", c_void_p), ("batch", c_int),
+        ("rows_in_cap", c_int),
+        ("dst_local", c_void_p), ("sample_of", c_void_p),
+        ("scale_in", c_void_p), ("scale_out", c_void_p),
+        ("a0_in", c_void_p), ("a0_out", c_void_p),
+        ("a1_in", c_void_p), ("a1_out", c_void_p),
+        ("a2_in", c_void_p), ("a2_out", c_void_p),
+        ("ghost", c_int),
+    ]
+
+
+class ResidualGateArgs(C.Structure):
+    _fields_ = [
+        ("x", c_void_p), ("cu_in", c_void_p), ("mult_in", c_void_p),
+        ("batch", c_int), ("dim", c_int), ("max_seq_len", c_int),
+        ("n_special", c_int), ("budget_pos", c_int),
+        ("gated", c_int),
+        ("gate_w", c_void_p), ("gate_b", c_float), ("gate_temp", c_float), ("gate_bias", c_float), ("gate_type", c_int),
+        ("thr_mode", c_int),
+        ("bt_w", c_void_p), ("bt_b", c_float), ("thr_dev", c_void_p), ("thr_const", c_float),
+        ("mask", c_void_p), ("dst_local", c_void_p), ("sample_of", c_void_p), ("new_len", c_void_p), ("mdrop", c_void_p),
+    ]
+
+
+class AvitArgs(C.Structure):
+    _fields_ = [
+        ("x", c_void_p), ("cu_in", c_void_p), ("batch", c_int), ("dim", c_int), ("seq_total", c_int),
+        ("c", c_void_p), ("R", c_void_p), ("tokid", c_void_p),
+        ("gate_scale", c_float), ("gate_center", c_float), ("eps", c_float), ("last_layer", c_int), ("early_exit", c_int),
+        ("out_acc", c_void_p), ("rho", c_void_p), ("counter", c_void_p),
+        ("dst_local", c_void_p), ("sample_of", c_void_p), ("new_len", c_void_p), ("n_halted", c_void_p),
     ]
 
 
@@ -59,6 +97,15 @@ SIGNATURES: Dict[str, tuple] = {
     "pk_token_norm_score": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pk_topk_select": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pk_gather_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "pk_exclusive_scan_i32": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "pk_compact_rows": (c_int, [C.POINTER(CompactArgs), c_void_p]),
+    "pk_budget_mean_threshold": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pk_residual_gate_plan": (c_int, [C.POINTER(ResidualGateArgs), c_void_p]),
+    "pk_residual_ghost": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "pk_residual_publish": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "pk_avit_halt_plan": (c_int, [C.POINTER(AvitArgs), c_void_p]),
+    "pk_moe_route": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_void_p]),
 }
 
 HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "peekvit_b200.h")

@@ -50,7 +50,9 @@ struct GemmKernelParams {
   const float* resid;
   long long ldr;
   const float* rowscale;
-  int rows_per_group, group_stride, group_offset, resid_is_pos;
+  int rows_per_group, group_stride, group_offset, resid_is_pos, pos_offset;
+  const int* row_begin_dev;
+  const int* out_row_index;
   unsigned int* flag;
 };
 
@@ -73,7 +75,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   const int warp = warp_id();
   const int lane = lane_id();
-  const int M = p.m_dev ? min(*p.m_dev, p.M) : p.M;
+  const int row0 = p.row_begin_dev ? *p.row_begin_dev : 0;     // first row of this launch's segment
+  const int M = p.m_dev ? max(0, min(*p.m_dev, p.M - row0)) : p.M;
   const int m_tiles = (M + kBM - 1) / kBM;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
@@ -116,7 +119,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const uint32_t fb = smem_u32(&full_bar[s]);
           mbar_expect_tx(fb, Cfg::kStageBytes);
           const uint32_t a_dst = smem_u32(smem_ab + s * Cfg::kStageBytes);
-          tma_load_2d(a_dst, &tmap_a, fb, kb * kBK, m_blk * kBM);
+          tma_load_2d(a_dst, &tmap_a, fb, kb * kBK, row0 + m_blk * kBM);
           tma_load_2d(a_dst + Cfg::kABytes, &tmap_b, fb, kb * kBK, n_blk * BN);
           if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
         }
@@ -175,13 +178,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const int gcol = n_blk * BN + half * (BN / 2) + ch * 32 + c4 * 4;
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
-            const int grow = row_base + it * 4;
+            const int lrow = row_base + it * 4;
             dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (grow < M && gcol < p.N) {
-              long long rrow = grow;
+            if (lrow < M && gcol < p.N) {
+              const int grow = row0 + lrow;
+              long long rrow = p.out_row_index ? p.out_row_index[grow] : grow;
               if (p.rows_per_group > 0) {
                 const int g = grow / p.rows_per_group, pos = grow - g * p.rows_per_group;
-                rrow = p.resid_is_pos ? static_cast<long long>(p.group_offset + pos)
+                rrow = p.resid_is_pos ? static_cast<long long>(p.pos_offset + pos)
                                       : static_cast<long long>(g) * p.group_stride + p.group_offset + pos;
               }
               dst[it] = *reinterpret_cast<const float4*>(p.resid + rrow * p.ldr + gcol);
@@ -193,7 +197,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       if (!mbar_wait(smem_u32(&tfull_bar[as]), aph, p.flag, 0x400u + as)) break;
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
-#pragma unroll
+      // fully unrolled only where the residual double-buffer needs register renaming; the GELU
+      // body is large and thrashes the instruction cache when replicated per chunk
+#pragma unroll (EPI == PK_EPI_BIAS_RESID_F32 ? kChunksPerWarp : 1)
       for (int ch = 0; ch < kChunksPerWarp; ++ch) {
         const int col0 = half * (BN / 2) + ch * 32;
         float4 rcur[8];
@@ -226,11 +232,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int rr = it * 4 + r_sub;
-          const int grow = row_base + it * 4;
-          if (grow < M && col_ok) {
+          const int lrow = row_base + it * 4;
+          if (lrow < M && col_ok) {
+            const int grow = row0 + lrow;
             float4 a = *reinterpret_cast<const float4*>(stg + rr * kStagePitch + c4 * 4);
             a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
-            long long orow = grow;
+            long long orow = p.out_row_index ? p.out_row_index[grow] : grow;
             if (p.rows_per_group > 0) {
               const int g = grow / p.rows_per_group, pos = grow - g * p.rows_per_group;
               orow = static_cast<long long>(g) * p.group_stride + p.group_offset + pos;
@@ -291,7 +298,8 @@ static int launch_gemm(const pk_gemm_args* a, cudaStream_t stream) {
   p.resid = a->resid; p.ldr = a->ldr;
   p.rowscale = a->rowscale;
   p.rows_per_group = a->rows_per_group; p.group_stride = a->group_stride;
-  p.group_offset = a->group_offset; p.resid_is_pos = a->resid_is_pos;
+  p.group_offset = a->group_offset; p.resid_is_pos = a->resid_is_pos; p.pos_offset = a->pos_offset;
+  p.row_begin_dev = a->row_begin_dev; p.out_row_index = a->out_row_index;
   p.flag = device_flag_ptr();
   const int m_tiles = (a->M + kBM - 1) / kBM, n_tiles = (a->N + BN - 1) / BN;
   int grid = m_tiles * n_tiles;

@@ -1,0 +1,531 @@
+// peekvit_b200 — token-sparsification kernels: ResidualViT budget gating, AViT halting, MoE
+// routing, and the ragged-batch compaction they share.  All HBM/latency-bound: one warp per
+// token row with 128-bit loads and shuffle reductions, one CTA per sample for the per-sample
+// plans (prefix sums by warp ballot), no host synchronisation anywhere — row counts stay on
+// the device and the GEMM / LayerNorm / attention kernels read them (m_dev / rows_dev /
+// cu_seqlens).
+//
+// Exact reformulations of the reference's dense masked forward:
+//   ResidualViT (models/residualvit.py:197-260): a dropped token is a zero row that still acts as a
+//     key (k = b_k, v = b_v) and leaves the block as the constant mlp(0).  Rows carry a
+//     multiplicity; dropped rows of a sample are folded into one virtual key (attention kernel)
+//     and one "ghost" row mlp(0) appended after the block, which may be re-admitted later.
+//   AViT (models/adavit.py:140-219): halted tokens are zero rows -> virtual key; only the class
+//     row's ACT-weighted output reaches the head, so a sample retires when its class token halts.
+//   MoE (models/moevit.py:49-61): one-hot arg-max routing -> only the chosen expert is computed.
+#include "pk_common.cuh"
+#include "../../include/peekvit_b200.h"
+
+namespace pk {
+
+__device__ __forceinline__ float row_dot(const float* __restrict__ row, const float* __restrict__ w, int d4, int lane) {
+  float acc = 0.f;
+  for (int c = lane; c < d4; c += 32) {
+    const float4 a = *reinterpret_cast<const float4*>(row + c * 4);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(w + c * 4));
+    acc += (a.x * b.x + a.y * b.y) + (a.z * b.z + a.w * b.w);
+  }
+  return warp_sum(acc);
+}
+__device__ __forceinline__ float sigmoidf_exact(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Warp-0 exclusive prefix over `len` keep flags held in shared memory; returns kept count.
+__device__ __forceinline__ int plan_prefix(const unsigned char* s_keep, int* __restrict__ dst_local, long long start, int len,
+                                           int lane) {
+  int base = 0;
+  for (int j0 = 0; j0 < len; j0 += 32) {
+    const int j = j0 + lane;
+    const bool k = j < len && s_keep[j];
+    const unsigned bal = __ballot_sync(0xffffffffu, k);
+    if (j < len) dst_local[start + j] = k ? base + __popc(bal & ((1u << lane) - 1u)) : -1;
+    base += __popc(bal);
+  }
+  return base;
+}
+
+// ------------------------------------------------------------------ ResidualViT: threshold (fixed budget)
+// thr = 1 - mean(budget token over the whole batch and D)   (residualvit.py:208 + :62)
+__global__ void __launch_bounds__(1024)
+budget_mean_threshold_kernel(const float* __restrict__ x, const int* __restrict__ cu, int batch, int budget_pos, int dim,
+                             float* __restrict__ thr_out) {
+  __shared__ float s_part[32];
+  float acc = 0.f;
+  const int total = batch * dim;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int b = i / dim, d = i - b * dim;
+    acc += x[(static_cast<long long>(cu[b]) + budget_pos) * dim + d];
+  }
+  acc = warp_sum(acc);
+  if (lane_id() == 0) s_part[warp_id()] = acc;
+  __syncthreads();
+  if (warp_id() == 0) {
+    float v = lane_id() < (blockDim.x >> 5) ? s_part[lane_id()] : 0.f;
+    v = warp_sum(v);
+    if (lane_id() == 0) thr_out[0] = 1.0f - v / static_cast<float>(total);
+  }
+}
+
+// ------------------------------------------------------------------ ResidualViT: gate + per-sample plan
+struct ResidualGateParams {
+  const float* x;            // [rows, D] block input, packed
+  const int* cu_in;          // [B+1]
+  const float* mult_in;      // [rows]
+  int dim, n_special, budget_pos;   // specials occupy local rows [0, n_special); budget token at budget_pos (or -1)
+  const float* gate_w; float gate_b, inv_temp, gate_bias; int gate_type;     // 0 sigmoid, 1 gumbel(eval)
+  int thr_mode;              // 0: sigmoid(bt_w . budget_row + bt_b); 1: *thr_dev; 2: thr_const
+  const float* bt_w; float bt_b; const float* thr_dev; float thr_const;
+  int gated;                 // 0 -> plain layer: every live row kept with mask 1, no ghost
+  float* mask;               // [rows] soft mask per input row (specials 1)
+  int* dst_local;            // [rows] index inside the compacted sample, -1 = dropped
+  int* sample_of;            // [rows]
+  int* new_len;              // [B]
+  float* mdrop;              // [B] multiplicity folded into the virtual key / ghost row
+};
+
+__global__ void __launch_bounds__(256)
+residual_gate_plan_kernel(const ResidualGateParams p) {
+  extern __shared__ unsigned char s_keep[];
+  __shared__ float s_thr, s_drop[8];
+  const int b = blockIdx.x, lane = lane_id(), warp = warp_id();
+  const long long start = p.cu_in[b];
+  const int len = p.cu_in[b + 1] - p.cu_in[b];
+  const int d4 = p.dim / 4;
+  if (warp == 0) {
+    float thr = p.thr_const;
+    if (p.thr_mode == 0) thr = sigmoidf_exact(row_dot(p.x + (start + p.budget_pos) * p.dim, p.bt_w, d4, lane) + p.bt_b);
+    else if (p.thr_mode == 1) thr = p.thr_dev[0];
+    if (lane == 0) s_thr = thr;
+  }
+  __syncthreads();
+  const float thr = s_thr;
+  float dropped = 0.f;
+  for (int j = warp; j < len; j += 8) {
+    const long long r = start + j;
+    const float mult = p.mult_in[r];
+    float m = 1.0f;
+    bool keep = true;
+    if (j >= p.n_special) {
+      if (p.gated) {
+        const float logit = row_dot(p.x + r * p.dim, p.gate_w, d4, lane) + p.gate_b;
+        if (p.gate_type == 0) m = fmaxf(sigmoidf_exact(logit * p.inv_temp + p.gate_bias) - thr, 0.f);
+        else m = rintf(sigmoidf_exact(logit));
+      }
+      keep = (m > 0.f) && (mult > 0.f);
+      if (!keep) dropped += mult;
+    }
+    if (lane == 0) {
+      p.mask[r] = m;
+      p.sample_of[r] = b;
+      s_keep[j] = keep ? 1 : 0;
+    }
+  }
+  if (lane == 0) s_drop[warp] = dropped;
+  __syncthreads();
+  if (warp == 0) {
+    const int kept = plan_prefix(s_keep, p.dst_local, start, len, lane);
+    if (lane == 0) {
+      float md = 0.f;
+      for (int w = 0; w < 8; ++w) md += s_drop[w];
+      p.new_len[b] = kept + (p.gated ? 1 : 0);       // + ghost slot
+      p.mdrop[b] = md;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ exclusive scan of per-sample lengths
+__global__ void __launch_bounds__(1024)
+exclusive_scan_kernel(const int* __restrict__ len, int n, int* __restrict__ cu_out, int* __restrict__ total_out) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = lane_id(), warp = warp_id();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < n ? len[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    const int excl = carry + (warp ? s_warp[warp - 1] : 0) + incl - v;
+    if (i < n) cu_out[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    cu_out[n] = s_carry;
+    if (total_out) total_out[0] = s_carry;
+  }
+}
+
+// ------------------------------------------------------------------ compaction of packed rows
+struct CompactParams {
+  const float* x_in; float* x_out; int dim;
+  const int* cu_in; const int* cu_out; int batch;
+  const int* dst_local; const int* sample_of;
+  const float* scale_in;                 // optional per input row (ResidualViT soft mask): out = scale * in
+  float* scale_out;                      // optional per output row
+  const float* a0_in; float* a0_out;     // optional per-row attributes carried along (multiplicity / c / R / token id)
+  const float* a1_in; float* a1_out;
+  const float* a2_in; float* a2_out;
+  int ghost;                             // ResidualViT: zero-initialise each sample's last output row (a0 = 0, scale = 1)
+};
+
+__global__ void __launch_bounds__(256)
+compact_rows_kernel(const CompactParams p) {
+  const int lane = lane_id();
+  const int d4 = p.dim / 4;
+  const int rows_in = p.cu_in[p.batch];
+  const int items = rows_in + (p.ghost ? p.batch : 0);
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int it = blockIdx.x * (blockDim.x >> 5) + warp_id(); it < items; it += warps_total) {
+    if (it < rows_in) {
+      const int dl = p.dst_local[it];
+      if (dl < 0) continue;
+      const int b = p.sample_of[it];
+      const long long dst = static_cast<long long>(p.cu_out[b]) + dl;
+      const float sc = p.scale_in ? p.scale_in[it] : 1.0f;
+      const float4* src = reinterpret_cast<const float4*>(p.x_in + static_cast<long long>(it) * p.dim);
+      float4* out = reinterpret_cast<float4*>(p.x_out + dst * p.dim);
+      for (int c = lane; c < d4; c += 32) {
+        float4 v = src[c];
+        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+        out[c] = v;
+      }
+      if (lane == 0) {
+        if (p.scale_out) p.scale_out[dst] = sc;
+        if (p.a0_out) p.a0_out[dst] = p.a0_in[it];
+        if (p.a1_out) p.a1_out[dst] = p.a1_in[it];
+        if (p.a2_out) p.a2_out[dst] = p.a2_in[it];
+      }
+    } else {
+      const int b = it - rows_in;
+      const long long dst = static_cast<long long>(p.cu_out[b + 1]) - 1;
+      float4* out = reinterpret_cast<float4*>(p.x_out + dst * p.dim);
+      for (int c = lane; c < d4; c += 32) out[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane == 0) {
+        if (p.scale_out) p.scale_out[dst] = 1.0f;
+        if (p.a0_out) p.a0_out[dst] = 0.0f;     // multiplicity 0: inert as a key during this layer
+      }
+    }
+  }
+}
+
+// After the block: the ghost row becomes mlp(0) standing for mdrop[b] dropped tokens (residualvit.py:258-260
+// evaluated on a zero row: fc2(gelu(fc1.bias)) + fc2.bias).
+__global__ void __launch_bounds__(256)
+residual_ghost_kernel(float* __restrict__ x, float* __restrict__ mult, const int* __restrict__ cu, const float* __restrict__ mdrop,
+                      const float* __restrict__ mlp0, int batch, int dim) {
+  const int lane = lane_id(), d4 = dim / 4;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int b = blockIdx.x * (blockDim.x >> 5) + warp_id(); b < batch; b += warps_total) {
+    const long long dst = static_cast<long long>(cu[b + 1]) - 1;
+    float4* out = reinterpret_cast<float4*>(x + dst * dim);
+    for (int c = lane; c < d4; c += 32) out[c] = __ldg(reinterpret_cast<const float4*>(mlp0 + c * 4));
+    if (lane == 0) mult[dst] = mdrop[b];
+  }
+}
+
+// Publish the soft mask per original image token (reference block.mask, (B, N_img, 1)) and move the
+// token -> packed-row map to the compacted layout (dropped tokens now point at the ghost row).
+__global__ void residual_publish_kernel(const float* __restrict__ mask, const int* __restrict__ dst_local, const int* __restrict__ cu_out,
+                                        int* __restrict__ tok_row, float* __restrict__ mask_pub, int batch, int n_img) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * n_img) return;
+  const int b = i / n_img;
+  const int r = tok_row[i];
+  mask_pub[i] = mask[r];
+  const int dl = dst_local[r];
+  tok_row[i] = dl >= 0 ? cu_out[b] + dl : cu_out[b + 1] - 1;
+}
+
+// ------------------------------------------------------------------ AViT halting + per-sample plan
+struct AvitParams {
+  const float* x;          // [rows, D] block output, packed active rows
+  const int* cu_in; int dim, seq_total;
+  float* c; float* R; const float* tokid;     // per packed row state (token id stored as float)
+  float gate_scale, gate_center, eps; int last_layer, early_exit;
+  float* out_acc;          // [B, D] ACT-weighted class-token output (adavit.py:197,205,212-215)
+  float* rho; float* counter;                 // [B, seq_total] published per original token (may be NULL)
+  int* dst_local; int* sample_of; int* new_len; float* n_halted;   // n_halted[b] = seq_total - active after this layer
+};
+
+__global__ void __launch_bounds__(256)
+avit_halt_plan_kernel(const AvitParams p) {
+  extern __shared__ unsigned char s_keep[];
+  __shared__ float s_w;
+  __shared__ int s_cls_alive;
+  const int b = blockIdx.x, lane = lane_id(), warp = warp_id(), tid = threadIdx.x;
+  const long long start = p.cu_in[b];
+  const int len = p.cu_in[b + 1] - p.cu_in[b];
+  if (tid == 0) { s_w = 0.f; s_cls_alive = 0; }
+  __syncthreads();
+  for (int j = tid; j < len; j += blockDim.x) {
+    const long long r = start + j;
+    const float h = p.last_layer ? 1.0f : sigmoidf_exact(p.x[r * p.dim] * p.gate_scale - p.gate_center);   // adavit.py:74,186-187
+    const float c_new = p.c[r] + h;                                                                         // :190
+    const float Rv = p.R[r];
+    const bool reached = c_new > 1.0f - p.eps;                                                              // :195
+    const bool not_reached = c_new < 1.0f - p.eps;                                                          // :202
+    const float w = reached ? Rv : (not_reached ? h : 0.f);                                                 // :197,:205
+    p.c[r] = c_new;
+    p.R[r] = not_reached ? Rv - h : Rv;                                                                     // :204
+    const int tok = static_cast<int>(p.tokid[r]);
+    if (p.rho) {
+      p.rho[static_cast<long long>(b) * p.seq_total + tok] += 1.0f + (reached ? Rv : 0.f);                  // :191,:198
+      if (not_reached) p.counter[static_cast<long long>(b) * p.seq_total + tok] += 1.0f;                    // :207
+    }
+    s_keep[j] = not_reached ? 1 : 0;                                                                        // :210
+    p.sample_of[r] = b;
+    if (tok == 0) { s_w = w; s_cls_alive = not_reached ? 1 : 0; }
+  }
+  __syncthreads();
+  // class row is local row 0 while it is active
+  const bool has_cls = len > 0 && static_cast<int>(p.tokid[start]) == 0;
+  if (has_cls) {
+    const float w = s_w;
+    for (int d = tid; d < p.dim; d += blockDim.x) p.out_acc[static_cast<long long>(b) * p.dim + d] += w * p.x[start * p.dim + d];
+  }
+  if (p.early_exit && !(has_cls && s_cls_alive)) {
+    // the class token has halted: nothing later can change this sample's logits
+    for (int j = tid; j < len; j += blockDim.x) s_keep[j] = 0;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int kept = plan_prefix(s_keep, p.dst_local, start, len, lane);
+    if (lane == 0) {
+      p.new_len[b] = kept;
+      p.n_halted[b] = static_cast<float>(p.seq_total - kept);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ MoE routing
+// expert[r] = argmax_e ( LN(x[r]) . Wg[e] + bg[e] ), first maximum wins like torch.argmax
+// (moevit.py:23-32 + blocks.py:23-25).  LN is recomputed in fp32 so routing does not see bf16 rounding.
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+moe_route_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                 const float* __restrict__ gate_w, const float* __restrict__ gate_b, int n_experts, int rows, int dim,
+                 int* __restrict__ expert) {
+  const int lane = lane_id();
+  const int d4 = dim / 4;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int r = blockIdx.x * (blockDim.x >> 5) + warp_id(); r < rows; r += warps_total) {
+    float4 v[MAXV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + i * 32;
+      v[i] = c < d4 ? *reinterpret_cast<const float4*>(x + static_cast<long long>(r) * dim + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(sum) / dim;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+      if (lane + i * 32 < d4) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        sq += (a * a + b * b) + (c * c + d * d);
+      }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) / dim + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + i * 32;
+      if (c < d4) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c * 4)), be = __ldg(reinterpret_cast<const float4*>(beta + c * 4));
+        v[i].x = fmaf((v[i].x - mean) * rstd, g.x, be.x); v[i].y = fmaf((v[i].y - mean) * rstd, g.y, be.y);
+        v[i].z = fmaf((v[i].z - mean) * rstd, g.z, be.z); v[i].w = fmaf((v[i].w - mean) * rstd, g.w, be.w);
+      }
+    }
+    float best = -INFINITY;
+    int best_e = 0;
+    for (int e = 0; e < n_experts; ++e) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + i * 32;
+        if (c < d4) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(gate_w + static_cast<long long>(e) * dim + c * 4));
+          acc += (v[i].x * w.x + v[i].y * w.y) + (v[i].z * w.z + v[i].w * w.w);
+        }
+      }
+      acc = warp_sum(acc) + gate_b[e];
+      if (acc > best) { best = acc; best_e = e; }
+    }
+    if (lane == 0) expert[r] = best_e;
+  }
+}
+
+// Stable counting sort of rows by expert (single CTA; rows up to a few 10^5): offsets[E+1],
+// counts[E] and src_of[pos] = original row of the pos-th expert-sorted row.
+constexpr int kMaxExperts = 16;
+__global__ void __launch_bounds__(1024)
+moe_sort_kernel(const int* __restrict__ expert, int rows, int n_experts, int* __restrict__ offsets, int* __restrict__ counts,
+                int* __restrict__ src_of) {
+  __shared__ int s_cnt[kMaxExperts];
+  __shared__ int s_cursor[kMaxExperts];
+  __shared__ int s_wc[32][kMaxExperts];
+  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+  if (tid < kMaxExperts) s_cnt[tid] = 0;
+  __syncthreads();
+  for (int r = tid; r < rows; r += blockDim.x) atomicAdd(&s_cnt[expert[r]], 1);
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int e = 0; e < n_experts; ++e) {
+      s_cursor[e] = acc; offsets[e] = acc; counts[e] = s_cnt[e];
+      acc += s_cnt[e];
+    }
+    offsets[n_experts] = acc;
+  }
+  __syncthreads();
+  for (int base = 0; base < rows; base += 1024) {
+    const int r = base + tid;
+    const int e = r < rows ? expert[r] : -1;
+    int my_rank = 0;
+    for (int ex = 0; ex < n_experts; ++ex) {
+      const unsigned bal = __ballot_sync(0xffffffffu, e == ex);
+      if (e == ex) my_rank = __popc(bal & ((1u << lane) - 1u));
+      if (lane == 0) s_wc[warp][ex] = __popc(bal);
+    }
+    __syncthreads();
+    if (e >= 0) {
+      int pos = s_cursor[e] + my_rank;
+      for (int w = 0; w < warp; ++w) pos += s_wc[w][e];
+      src_of[pos] = r;
+    }
+    __syncthreads();
+    if (tid < n_experts) {
+      int add = 0;
+      for (int w = 0; w < 32; ++w) add += s_wc[w][tid];
+      s_cursor[tid] += add;
+    }
+    __syncthreads();
+  }
+}
+
+static int grid_rows(long long items, int per_block = 8, int max_per_sm = 8) {
+  long long g = (items + per_block - 1) / per_block;
+  const long long cap = static_cast<long long>(num_sms()) * max_per_sm;
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : static_cast<int>(g);
+}
+
+}  // namespace pk
+
+using namespace pk;
+
+extern "C" int pk_budget_mean_threshold(const float* x, const int* cu_seqlens, int batch, int budget_pos, int dim, float* thr_out,
+                                        void* stream) {
+  PK_REQUIRE(x && cu_seqlens && thr_out && batch > 0, "pk_budget_mean_threshold: bad arguments");
+  budget_mean_threshold_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(x, cu_seqlens, batch, budget_pos, dim, thr_out);
+  return check_cuda(cudaGetLastError(), "budget_mean_threshold_kernel");
+}
+
+extern "C" int pk_residual_gate_plan(const pk_residual_gate_args* a, void* stream) {
+  PK_REQUIRE(a && a->x && a->cu_in && a->mult_in && a->mask && a->dst_local && a->sample_of && a->new_len && a->mdrop,
+             "pk_residual_gate_plan: null pointer");
+  PK_REQUIRE(a->dim % 4 == 0 && a->max_seq_len > 0 && a->max_seq_len <= 16384, "pk_residual_gate_plan: bad dim/max_seq_len");
+  PK_REQUIRE(!a->gated || a->gate_w, "pk_residual_gate_plan: gated layer needs gate_w");
+  PK_REQUIRE(a->thr_mode != 0 || !a->gated || (a->bt_w && a->budget_pos >= 0), "pk_residual_gate_plan: learnable threshold needs bt_w and a budget row");
+  PK_REQUIRE(a->thr_mode != 1 || a->thr_dev, "pk_residual_gate_plan: thr_mode 1 needs thr_dev");
+  if (a->batch == 0) return PK_OK;
+  ResidualGateParams p;
+  p.x = a->x; p.cu_in = a->cu_in; p.mult_in = a->mult_in;
+  p.dim = a->dim; p.n_special = a->n_special; p.budget_pos = a->budget_pos;
+  p.gate_w = a->gate_w; p.gate_b = a->gate_b; p.inv_temp = 1.0f / a->gate_temp; p.gate_bias = a->gate_bias; p.gate_type = a->gate_type;
+  p.thr_mode = a->gated ? a->thr_mode : 2;
+  p.bt_w = a->bt_w; p.bt_b = a->bt_b; p.thr_dev = a->thr_dev; p.thr_const = a->thr_const;
+  p.gated = a->gated;
+  p.mask = a->mask; p.dst_local = a->dst_local; p.sample_of = a->sample_of; p.new_len = a->new_len; p.mdrop = a->mdrop;
+  residual_gate_plan_kernel<<<a->batch, 256, static_cast<size_t>(a->max_seq_len), static_cast<cudaStream_t>(stream)>>>(p);
+  return check_cuda(cudaGetLastError(), "residual_gate_plan_kernel");
+}
+
+extern "C" int pk_exclusive_scan_i32(const int* lens, int n, int* cu_out, int* total_out, void* stream) {
+  PK_REQUIRE(lens && cu_out && n >= 0, "pk_exclusive_scan_i32: bad arguments");
+  exclusive_scan_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(lens, n, cu_out, total_out);
+  return check_cuda(cudaGetLastError(), "exclusive_scan_kernel");
+}
+
+extern "C" int pk_compact_rows(const pk_compact_args* a, void* stream) {
+  PK_REQUIRE(a && a->x_in && a->x_out && a->cu_in && a->cu_out && a->dst_local && a->sample_of, "pk_compact_rows: null pointer");
+  PK_REQUIRE(a->dim % 4 == 0 && a->rows_in_cap >= 0, "pk_compact_rows: bad dim");
+  PK_REQUIRE((a->a0_in == nullptr) == (a->a0_out == nullptr) || a->ghost, "pk_compact_rows: attribute 0 in/out mismatch");
+  if (a->batch == 0) return PK_OK;
+  CompactParams p;
+  p.x_in = a->x_in; p.x_out = a->x_out; p.dim = a->dim;
+  p.cu_in = a->cu_in; p.cu_out = a->cu_out; p.batch = a->batch;
+  p.dst_local = a->dst_local; p.sample_of = a->sample_of;
+  p.scale_in = a->scale_in; p.scale_out = a->scale_out;
+  p.a0_in = a->a0_in; p.a0_out = a->a0_out; p.a1_in = a->a1_in; p.a1_out = a->a1_out; p.a2_in = a->a2_in; p.a2_out = a->a2_out;
+  p.ghost = a->ghost;
+  compact_rows_kernel<<<grid_rows(static_cast<long long>(a->rows_in_cap) + a->batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_cuda(cudaGetLastError(), "compact_rows_kernel");
+}
+
+extern "C" int pk_residual_ghost(float* x, float* mult, const int* cu_seqlens, const float* mdrop, const float* mlp0, int batch, int dim,
+                                 void* stream) {
+  PK_REQUIRE(x && mult && cu_seqlens && mdrop && mlp0 && dim % 4 == 0, "pk_residual_ghost: bad arguments");
+  if (batch == 0) return PK_OK;
+  residual_ghost_kernel<<<grid_rows(batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, mult, cu_seqlens, mdrop, mlp0, batch, dim);
+  return check_cuda(cudaGetLastError(), "residual_ghost_kernel");
+}
+
+extern "C" int pk_residual_publish(const float* mask, const int* dst_local, const int* cu_out, int* tok_row, float* mask_pub, int batch,
+                                   int n_img, void* stream) {
+  PK_REQUIRE(mask && dst_local && cu_out && tok_row && mask_pub, "pk_residual_publish: null pointer");
+  const int total = batch * n_img;
+  if (total == 0) return PK_OK;
+  residual_publish_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, dst_local, cu_out, tok_row, mask_pub,
+                                                                                               batch, n_img);
+  return check_cuda(cudaGetLastError(), "residual_publish_kernel");
+}
+
+extern "C" int pk_avit_halt_plan(const pk_avit_args* a, void* stream) {
+  PK_REQUIRE(a && a->x && a->cu_in && a->c && a->R && a->tokid && a->out_acc && a->dst_local && a->sample_of && a->new_len && a->n_halted,
+             "pk_avit_halt_plan: null pointer");
+  PK_REQUIRE((a->rho == nullptr) == (a->counter == nullptr), "pk_avit_halt_plan: rho and counter go together");
+  PK_REQUIRE(a->seq_total > 0 && a->seq_total <= 16384, "pk_avit_halt_plan: bad seq_total");
+  if (a->batch == 0) return PK_OK;
+  AvitParams p;
+  p.x = a->x; p.cu_in = a->cu_in; p.dim = a->dim; p.seq_total = a->seq_total;
+  p.c = a->c; p.R = a->R; p.tokid = a->tokid;
+  p.gate_scale = a->gate_scale; p.gate_center = a->gate_center; p.eps = a->eps; p.last_layer = a->last_layer; p.early_exit = a->early_exit;
+  p.out_acc = a->out_acc; p.rho = a->rho; p.counter = a->counter;
+  p.dst_local = a->dst_local; p.sample_of = a->sample_of; p.new_len = a->new_len; p.n_halted = a->n_halted;
+  avit_halt_plan_kernel<<<a->batch, 256, static_cast<size_t>(a->seq_total), static_cast<cudaStream_t>(stream)>>>(p);
+  return check_cuda(cudaGetLastError(), "avit_halt_plan_kernel");
+}
+
+extern "C" int pk_moe_route(const float* x, const float* gamma, const float* beta, float eps, const float* gate_w, const float* gate_b,
+                            int n_experts, int rows, int dim, int* expert, int* offsets, int* counts, int* src_of, void* stream) {
+  PK_REQUIRE(x && gamma && beta && gate_w && gate_b && expert && offsets && counts && src_of, "pk_moe_route: null pointer");
+  PK_REQUIRE(n_experts >= 1 && n_experts <= kMaxExperts, "pk_moe_route: 1 <= n_experts <= %d", kMaxExperts);
+  PK_REQUIRE(dim % 4 == 0 && dim <= 1024, "pk_moe_route: dim must be a multiple of 4, <= 1024");
+  if (rows == 0) return PK_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int maxv = (dim / 4 + 31) / 32;
+  if (maxv <= 3) moe_route_kernel<3><<<grid_rows(rows), 256, 0, s>>>(x, gamma, beta, eps, gate_w, gate_b, n_experts, rows, dim, expert);
+  else moe_route_kernel<8><<<grid_rows(rows), 256, 0, s>>>(x, gamma, beta, eps, gate_w, gate_b, n_experts, rows, dim, expert);
+  PK_CHECK_CUDA(cudaGetLastError());
+  moe_sort_kernel<<<1, 1024, 0, s>>>(expert, rows, n_experts, offsets, counts, src_of);
+  return check_cuda(cudaGetLastError(), "moe_sort_kernel");
+}

@@ -138,12 +138,12 @@ def pack_model(model, family: str) -> PackedModel:
                 raise NotImplementedError(f"ResidualViT skip mode {blk.skip!r} is a 'next' row (SURVEY.md §8 f3)")
             if blk.skip == "attention+mlp":
                 g = blk.residual_gate
-                extra.update(gate_w=_f32(g.projection.weight).reshape(-1), gate_b=_f32(g.projection.bias).reshape(-1),
+                extra.update(gate_w=_f32(g.projection.weight).reshape(-1), gate_b=float(g.projection.bias.detach().float().cpu()[0]),
                              gate_type=g.gate_type, gate_temp=float(g.temp), gate_bias=float(g.sigmoid_bias),
                              gate_threshold=g.threshold, budget_token=blk.budget_token, add_input=bool(blk.add_input))
                 if blk.budget_token == "learnable":
                     extra["bt_gate_w"] = _f32(blk.budget_token_gate.weight).reshape(-1)
-                    extra["bt_gate_b"] = _f32(blk.budget_token_gate.bias).reshape(-1)
+                    extra["bt_gate_b"] = float(blk.budget_token_gate.bias.detach().float().cpu()[0])
         if kind == "avit":
             extra.update(gate_scale=float(blk.gate_scale), gate_center=float(blk.gate_center))
         layers.append(LayerWeights(kind, _f32(blk.ln_1.weight), _f32(blk.ln_1.bias), _f32(blk.ln_2.weight), _f32(blk.ln_2.bias),
@@ -161,6 +161,27 @@ def pack_model(model, family: str) -> PackedModel:
         pos=_f32(model.encoder.pos_embedding.reshape(-1, D)),
         layers=layers, ln_w=_f32(model.encoder.ln.weight), ln_b=_f32(model.encoder.ln.bias), ln_eps=float(model.encoder.ln.eps),
         head_w=_f32(model.head.weight), head_b=_f32(model.head.bias))
+    if family == "residualvit":
+        if pm.n_cls != 1:
+            raise NotImplementedError("the B200 ResidualViT path supports num_class_tokens == 1 (all shipped configs)")
+        pm.extra["add_budget_token"] = model.add_budget_token
+        if model.add_budget_token in ("learnable", "learnable_interpolate"):
+            pm.extra["budget_token_1"] = _f32(model.learnable_budget_token_1.reshape(1, D))
+        if model.add_budget_token == "learnable_interpolate":
+            pm.extra["budget_token_2"] = _f32(model.learnable_budget_token_2.reshape(1, D))
+        for lw in pm.layers:
+            if lw.extra.get("skip") == "attention+mlp":
+                if lw.extra["add_input"]:
+                    raise NotImplementedError("add_input=True (residualvit.py:239-242) is a 'next' row (SURVEY.md §8 f3)")
+                blk = lw.module
+                # what a dropped (zero) row equals when it leaves the block: fc2(gelu(fc1.bias)) + fc2.bias
+                h = torch.nn.functional.gelu(blk.mlp.fc1.bias.detach().float())
+                lw.extra["mlp0"] = (torch.nn.functional.linear(h, blk.mlp.fc2.weight.detach().float(),
+                                                               blk.mlp.fc2.bias.detach().float())).contiguous()
+    if family == "adavit":
+        if pm.n_cls != 1:
+            raise NotImplementedError("the B200 AViT path supports num_class_tokens == 1 (all shipped configs)")
+        pm.extra["eps"] = float(model.eps)
     return pm
 
 
@@ -193,41 +214,67 @@ class Forward:
         self.pm, self.ws = pm, ws
 
     # ---------------------------------------------------------------- shared pieces
-    def embed(self, images: torch.Tensor, extra_rows: int = 0) -> torch.Tensor:
+    def embed(self, images: torch.Tensor, extra_rows: int = 0, shift: int = 0) -> torch.Tensor:
         """Patch GEMM (+conv bias +pos_embedding) and class/register rows -> x f32 [B*seq, D]
-        (reference vit.py:203-236, :92).  ``extra_rows`` reserves trailing rows per sample."""
+        (reference vit.py:203-236, :92).  ``shift`` local rows are left free right after the first
+        class token (ResidualViT budget token), ``extra_rows`` are reserved at the end of each sample."""
         pm = self.pm
         B = images.shape[0]
         P, D, T, R = pm.num_patches, pm.dim, pm.n_cls, pm.n_reg
-        seq = pm.seq_len + extra_rows
+        seq = pm.seq_len + shift + extra_rows
         patches = ops.patchify(images, pm.patch_size, self.ws.get("patches", (B * P, pm.w_patch.shape[1]), torch.bfloat16))
         x = self.ws.get("x", (B * seq, D), torch.float32)
         ops.gemm(patches, pm.w_patch, pm.b_patch, x, PK_EPI_BIAS_RESID_F32, resid=pm.pos,
-                 rows_per_group=P, group_stride=seq, group_offset=T + R, resid_is_pos=True)
-        ops.fill_token_rows(x, B, seq, 0, pm.cls_tokens, pm.pos)
+                 rows_per_group=P, group_stride=seq, group_offset=T + R + shift, resid_is_pos=True, pos_offset=T + R)
+        ops.fill_token_rows(x, B, seq, 0, pm.cls_tokens[:1], pm.pos)
+        if T > 1:
+            ops.fill_token_rows(x, B, seq, 1 + shift, pm.cls_tokens[1:], pm.pos, pos_offset=1)
         if R > 0:
-            ops.fill_token_rows(x, B, seq, T, pm.reg_tokens, pm.pos)
+            ops.fill_token_rows(x, B, seq, T + shift, pm.reg_tokens, pm.pos, pos_offset=T)
         return x
 
-    def dense_block(self, x: torch.Tensor, lw: LayerWeights, rows: int, batch: int, seq: int) -> None:
-        """ViTBlock on uniform-length samples, in place on the fp32 residual stream
-        (reference vit.py:45-55)."""
+    def attn_part(self, x, lw: LayerWeights, rows: int, batch: int, *, seq: int = 0, cu=None, max_len: int = 0, rows_dev=None,
+                  rowscale=None, key_mult=None, extra_mult=None) -> None:
+        """x += rowscale * out_proj(attention(in_proj(rowscale * LN1(x))))  (vit.py:48-51; residualvit.py:252-256)."""
         pm, ws = self.pm, self.ws
         D = pm.dim
-        aw, mw = lw.attn[0], lw.mlp[0]
-        F = mw.w_fc1.shape[0]
-        a = ops.layernorm(x, lw.ln1_w, lw.ln1_b, lw.eps, ws.get("ln", (rows, D), torch.bfloat16), rows=rows)
-        qkv = ops.gemm(a, aw.w_qkv, aw.b_qkv, ws.get("qkv", (rows, 3 * D), torch.bfloat16), PK_EPI_BIAS_BF16)
-        att = ops.attention(qkv, ws.get("att", (rows, D), torch.bfloat16), batch, pm.heads, D // pm.heads, seq_len=seq)
-        ops.gemm(att, aw.w_o, aw.b_o, x[:rows], PK_EPI_BIAS_RESID_F32, resid=x[:rows])
-        a = ops.layernorm(x, lw.ln2_w, lw.ln2_b, lw.eps, ws.get("ln", (rows, D), torch.bfloat16), rows=rows)
-        hid = ops.gemm(a, mw.w_fc1, mw.b_fc1, ws.get("hid", (rows, F), torch.bfloat16), PK_EPI_BIAS_GELU_BF16)
-        ops.gemm(hid, mw.w_fc2, mw.b_fc2, x[:rows], PK_EPI_BIAS_RESID_F32, resid=x[:rows])
+        aw = lw.attn[0]
+        a = ops.layernorm(x, lw.ln1_w, lw.ln1_b, lw.eps, ws.get("ln", (rows, D), torch.bfloat16), rows=rows, rowscale=rowscale,
+                          rows_dev=rows_dev)
+        qkv = ops.gemm(a, aw.w_qkv, aw.b_qkv, ws.get("qkv", (rows, 3 * D), torch.bfloat16), PK_EPI_BIAS_BF16, m_dev=rows_dev)
+        att = ops.attention(qkv, ws.get("att", (rows, D), torch.bfloat16), batch, pm.heads, D // pm.heads, seq_len=seq,
+                            cu_seqlens=cu, max_seq_len=max_len, key_mult=key_mult,
+                            extra_kv=aw.bias_kv if extra_mult is not None else None, extra_mult=extra_mult)
+        ops.gemm(att, aw.w_o, aw.b_o, x[:rows], PK_EPI_BIAS_RESID_F32, resid=x[:rows], rowscale=rowscale, m_dev=rows_dev)
 
-    def head(self, x: torch.Tensor, batch: int, seq: int, cu_seqlens=None) -> torch.Tensor:
+    def mlp_part(self, x, lw: LayerWeights, rows: int, *, rows_dev=None, rowscale=None) -> None:
+        """x += fc2(gelu(fc1(rowscale * LN2(x))))  (vit.py:53-55; residualvit.py:258-260)."""
+        pm, ws = self.pm, self.ws
+        D = pm.dim
+        mw = lw.mlp[0]
+        F = mw.w_fc1.shape[0]
+        a = ops.layernorm(x, lw.ln2_w, lw.ln2_b, lw.eps, ws.get("ln", (rows, D), torch.bfloat16), rows=rows, rowscale=rowscale,
+                          rows_dev=rows_dev)
+        hid = ops.gemm(a, mw.w_fc1, mw.b_fc1, ws.get("hid", (rows, F), torch.bfloat16), PK_EPI_BIAS_GELU_BF16, m_dev=rows_dev)
+        ops.gemm(hid, mw.w_fc2, mw.b_fc2, x[:rows], PK_EPI_BIAS_RESID_F32, resid=x[:rows], m_dev=rows_dev)
+
+    def dense_block(self, x: torch.Tensor, lw: LayerWeights, rows: int, batch: int, seq: int) -> None:
+        """ViTBlock on uniform-length samples, in place on the fp32 residual stream (vit.py:45-55)."""
+        self.attn_part(x, lw, rows, batch, seq=seq)
+        self.mlp_part(x, lw, rows)
+
+    def head(self, x: torch.Tensor, batch: int, seq: int, cu_seqlens=None, n_cls: Optional[int] = None) -> torch.Tensor:
         pm = self.pm
-        return ops.cls_head(x, batch, seq, pm.n_cls, pm.ln_w, pm.ln_b, pm.ln_eps, pm.head_w, pm.head_b,
+        return ops.cls_head(x, batch, seq, pm.n_cls if n_cls is None else n_cls, pm.ln_w, pm.ln_b, pm.ln_eps, pm.head_w, pm.head_b,
                             cu_seqlens=cu_seqlens, out=self.ws.get("logits", (batch, pm.num_classes), torch.float32))
+
+    def _const(self, name: str, builder):
+        """Device constants of the ragged paths (initial cu_seqlens, token ids ...), built once per shape."""
+        t = self.ws._bufs.get(("const", name))
+        if t is None:
+            t = builder()
+            self.ws._bufs[("const", name)] = t
+        return t
 
     # ---------------------------------------------------------------- plain ViT
     def vit(self, images: torch.Tensor) -> torch.Tensor:
@@ -260,10 +307,177 @@ class Forward:
                 flip ^= 1
                 ops.gather_rows(x, kept, B, seq, y)
                 if aux is not None:
-                    aux.setdefault("scores", {})[i] = scores
-                    aux.setdefault("kept", {})[i] = kept
+                    aux.setdefault("scores", {})[i] = scores.clone()
+                    aux.setdefault("kept", {})[i] = kept.clone()
                 x, seq = y, k + 1
             if aux is not None:
                 aux.setdefault("seq_lens", []).append(seq)
             self.dense_block(x, lw, B * seq, B, seq)
         return self.head(x, B, seq)
+
+    # ---------------------------------------------------------------- ResidualViT
+    def residualvit(self, images: torch.Tensor, budget: float, aux: Optional[dict] = None) -> torch.Tensor:
+        """Budget-token gating with real compaction (reference residualvit.py:587-616, block :197-260).
+        Local row layout of a sample: [cls, budget token, live image rows ..., ghost slot]."""
+        pm, ws = self.pm, self.ws
+        ex = pm.extra
+        abt = ex["add_budget_token"]
+        B, D, dev = images.shape[0], pm.dim, images.device
+        nb = 1 if abt else 0
+        n_special = 1 + nb
+        n_img = pm.seq_len - 1                                   # other class tokens / registers / patches are all gated
+        seq0 = pm.seq_len + nb
+        cap = seq0 + 1                                           # + ghost slot
+        rows_cap = B * cap
+        x = self.embed(images, shift=nb)
+        if abt:
+            if budget is None:
+                raise AssertionError("Budget token not set. Call set_budget() before forward() to evaluate the model on a chosen budget.")
+            if abt == "learnable":
+                ops.fill_token_rows(x, B, seq0, 1, ex["budget_token_1"], None, scale=float(budget))       # residualvit.py:572-576
+            elif abt == "learnable_interpolate":
+                tok = ex["budget_token_1"] * float(budget) + ex["budget_token_2"] * (1.0 - float(budget))  # :577-580
+                ops.fill_token_rows(x, B, seq0, 1, tok, None)
+            else:
+                ops.fill_token_rows(x, B, seq0, 1, None, None, scale=float(budget), n_tokens=1)           # :581-583
+        cu = self._const(f"cu0_{B}_{seq0}", lambda: (torch.arange(B + 1, device=dev, dtype=torch.int32) * seq0))
+        rows_dev = self._const(f"rows0_{B}_{seq0}", lambda: torch.tensor([B * seq0], device=dev, dtype=torch.int32))
+        mult = self._const(f"ones_{rows_cap}", lambda: torch.ones(rows_cap, device=dev, dtype=torch.float32))
+        tok_row0 = self._const(f"tokrow0_{B}_{seq0}_{n_special}", lambda: (
+            torch.arange(B, device=dev, dtype=torch.int32)[:, None] * seq0 + n_special
+            + torch.arange(n_img, device=dev, dtype=torch.int32)[None, :]).contiguous())
+        tok_row = ws.get("res_tok_row", (B, n_img), torch.int32)
+        tok_row.copy_(tok_row0)
+        have_mult = False
+        bufs = [ws.get("res_x0", (rows_cap, D), torch.float32), ws.get("res_x1", (rows_cap, D), torch.float32)]
+        mults = [ws.get("res_mult0", (rows_cap,), torch.float32), ws.get("res_mult1", (rows_cap,), torch.float32)]
+        cus = [ws.get("res_cu0", (B + 1,), torch.int32), ws.get("res_cu1", (B + 1,), torch.int32)]
+        rdevs = [ws.get("res_rows0", (1,), torch.int32), ws.get("res_rows1", (1,), torch.int32)]
+        mask = ws.get("res_mask", (rows_cap,), torch.float32)
+        rowscale = ws.get("res_rowscale", (rows_cap,), torch.float32)
+        dst_local = ws.get("res_dst", (rows_cap,), torch.int32)
+        sample_of = ws.get("res_sample", (rows_cap,), torch.int32)
+        new_len = ws.get("res_newlen", (B,), torch.int32)
+        mdrop = ws.get("res_mdrop", (B,), torch.float32)
+        thr_dev = ws.get("res_thr", (1,), torch.float32)
+        flip = 0
+        for i, lw in enumerate(pm.layers):
+            skip = lw.extra.get("skip")
+            if skip == "attention+mlp":
+                if not abt:
+                    raise RuntimeError("ResidualViT 'attention+mlp' layers need a budget token (the reference raises a shape "
+                                       "error here, residualvit.py:230-237)")
+                g = lw.extra
+                if g["gate_type"] == "gumbel" and abt != "learnable":
+                    raise AssertionError("Gumbel gate does not support budget")
+                thr_mode = 0 if abt == "learnable" else 1
+                if thr_mode == 1:
+                    ops.budget_mean_threshold(x, cu, B, 1, thr_dev)
+                ops.residual_gate_plan(x, cu, mult, B, cap, n_special=n_special, budget_pos=1, gated=True, gate_w=g["gate_w"],
+                                       gate_b=g["gate_b"], gate_temp=g["gate_temp"], gate_bias=g["gate_bias"],
+                                       gate_type=0 if g["gate_type"] == "sigmoid" else 1, thr_mode=thr_mode, bt_w=g.get("bt_gate_w"),
+                                       bt_b=g.get("bt_gate_b", 0.0), thr_dev=thr_dev,
+                                       mask=mask, dst_local=dst_local, sample_of=sample_of, new_len=new_len, mdrop=mdrop)
+                cu_out, rows_out, y, mult_out = cus[flip], rdevs[flip], bufs[flip], mults[flip]
+                flip ^= 1
+                ops.exclusive_scan(new_len, cu_out, rows_out)
+                ops.compact_rows(x, y, cu, cu_out, B, rows_cap, dst_local, sample_of, scale_in=mask, scale_out=rowscale,
+                                 attrs=[(mult, mult_out)], ghost=True)
+                if aux is not None:
+                    mask_pub = torch.empty(B, n_img, 1, device=dev, dtype=torch.float32)
+                    ops.residual_publish(mask, dst_local, cu_out, tok_row, mask_pub, B, n_img)
+                    aux.setdefault("masks", {})[i] = mask_pub
+                    aux.setdefault("rows", {})[i] = rows_out.clone()
+                x, cu, rows_dev, mult, have_mult = y, cu_out, rows_out, mult_out, True
+                self.attn_part(x, lw, rows_cap, B, cu=cu, max_len=cap, rows_dev=rows_dev, rowscale=rowscale, key_mult=mult,
+                               extra_mult=mdrop)
+                self.mlp_part(x, lw, rows_cap, rows_dev=rows_dev, rowscale=rowscale)
+                ops.residual_ghost(x, mult, cu, mdrop, g["mlp0"], B)
+            elif skip in (None, "none"):
+                self.attn_part(x, lw, rows_cap, B, cu=cu, max_len=cap, rows_dev=rows_dev, key_mult=mult if have_mult else None)
+                self.mlp_part(x, lw, rows_cap, rows_dev=rows_dev)
+            else:
+                raise NotImplementedError(f"skip mode {skip!r}")
+        return self.head(x, B, 0, cu_seqlens=cu, n_cls=1)
+
+    # ---------------------------------------------------------------- AdaViT (A-ViT)
+    def adavit(self, images: torch.Tensor, aux: Optional[dict] = None, early_exit: bool = True) -> torch.Tensor:
+        """ACT halting with real token removal (reference adavit.py:140-219): halted tokens leave the packed
+        batch and survive only as a virtual bias key; a sample retires once its class token halts."""
+        pm, ws = self.pm, self.ws
+        ex = pm.extra
+        B, D, seq, dev = images.shape[0], pm.dim, pm.seq_len, images.device
+        rows_cap = B * seq
+        x = self.embed(images)
+        cu = self._const(f"cu0_{B}_{seq}", lambda: (torch.arange(B + 1, device=dev, dtype=torch.int32) * seq))
+        rows_dev = self._const(f"rows0_{B}_{seq}", lambda: torch.tensor([B * seq], device=dev, dtype=torch.int32))
+        tokid0 = self._const(f"tokid0_{B}_{seq}", lambda: torch.arange(seq, device=dev, dtype=torch.float32).repeat(B).contiguous())
+        xs = [x, ws.get("avit_x1", (rows_cap, D), torch.float32)]
+        cs = [ws.get("avit_c0", (rows_cap,), torch.float32), ws.get("avit_c1", (rows_cap,), torch.float32)]
+        Rs = [ws.get("avit_R0", (rows_cap,), torch.float32), ws.get("avit_R1", (rows_cap,), torch.float32)]
+        toks = [ws.get("avit_tok0", (rows_cap,), torch.float32), ws.get("avit_tok1", (rows_cap,), torch.float32)]
+        cus = [ws.get("avit_cu0", (B + 1,), torch.int32), ws.get("avit_cu1", (B + 1,), torch.int32)]
+        rdevs = [ws.get("avit_rows0", (1,), torch.int32), ws.get("avit_rows1", (1,), torch.int32)]
+        cs[0].zero_()
+        Rs[0].fill_(1.0)
+        toks[0].copy_(tokid0)
+        out_acc = ws.get("avit_out", (B, D), torch.float32)
+        out_acc.zero_()
+        rho = torch.zeros(B, seq, device=dev, dtype=torch.float32)
+        counter = torch.ones(B, seq, device=dev, dtype=torch.float32)
+        dst_local = ws.get("avit_dst", (rows_cap,), torch.int32)
+        sample_of = ws.get("avit_sample", (rows_cap,), torch.int32)
+        new_len = ws.get("avit_newlen", (B,), torch.int32)
+        n_halted = ws.get("avit_nhalted", (B,), torch.float32)
+        cur = 0
+        L = len(pm.layers)
+        for i, lw in enumerate(pm.layers):
+            self.attn_part(xs[cur], lw, rows_cap, B, cu=cu, max_len=seq, rows_dev=rows_dev, extra_mult=n_halted if i > 0 else None)
+            self.mlp_part(xs[cur], lw, rows_cap, rows_dev=rows_dev)
+            if aux is not None:
+                aux.setdefault("rows", []).append(rows_dev.clone())
+            ops.avit_halt_plan(xs[cur], cu, B, seq, cs[cur], Rs[cur], toks[cur], gate_scale=lw.extra["gate_scale"],
+                               gate_center=lw.extra["gate_center"], eps=ex["eps"], last_layer=(i == L - 1), early_exit=early_exit,
+                               out_acc=out_acc, rho=rho, counter=counter, dst_local=dst_local, sample_of=sample_of,
+                               new_len=new_len, n_halted=n_halted)
+            if i == L - 1:
+                break
+            nxt = cur ^ 1
+            ops.exclusive_scan(new_len, cus[nxt], rdevs[nxt])
+            ops.compact_rows(xs[cur], xs[nxt], cu, cus[nxt], B, rows_cap, dst_local, sample_of,
+                             attrs=[(cs[cur], cs[nxt]), (Rs[cur], Rs[nxt]), (toks[cur], toks[nxt])])
+            cu, rows_dev, cur = cus[nxt], rdevs[nxt], nxt
+        if aux is not None:
+            aux["rho_token"], aux["counter_token"] = rho, counter
+        return self.head(out_acc, B, 1, n_cls=1)
+
+    # ---------------------------------------------------------------- MoE ViT
+    def moevit(self, images: torch.Tensor, aux: Optional[dict] = None) -> torch.Tensor:
+        """Expert MLPs computed only for the tokens routed to them (reference moevit.py:49-61 evaluates every
+        expert on every token and selects with a one-hot einsum)."""
+        pm, ws = self.pm, self.ws
+        B, seq, D, dev = images.shape[0], pm.seq_len, pm.dim, images.device
+        rows = B * seq
+        x = self.embed(images)
+        for i, lw in enumerate(pm.layers):
+            self.attn_part(x, lw, rows, B, seq=seq)
+            E = len(lw.mlp)
+            if E == 1:
+                self.mlp_part(x, lw, rows)
+                continue
+            expert = ws.get("moe_expert", (rows,), torch.int32)
+            offsets = ws.get(f"moe_off_{E}", (E + 1,), torch.int32)
+            counts = ws.get(f"moe_cnt_{E}", (E,), torch.int32)
+            src_of = ws.get("moe_src", (rows,), torch.int32)
+            ops.moe_route(x, lw.ln2_w, lw.ln2_b, lw.eps, lw.extra["mlp_gate_w"], lw.extra["mlp_gate_b"], rows, expert, offsets,
+                          counts, src_of)
+            a = ops.layernorm(x, lw.ln2_w, lw.ln2_b, lw.eps, ws.get("ln", (rows, D), torch.bfloat16), rows=rows, row_index=src_of)
+            F = lw.mlp[0].w_fc1.shape[0]
+            hid = ws.get("hid", (rows, F), torch.bfloat16)
+            for e, mw in enumerate(lw.mlp):
+                ops.gemm(a, mw.w_fc1, mw.b_fc1, hid, PK_EPI_BIAS_GELU_BF16, m_dev=counts[e:e + 1], row_begin_dev=offsets[e:e + 1])
+                ops.gemm(hid, mw.w_fc2, mw.b_fc2, x, PK_EPI_BIAS_RESID_F32, resid=x, m_dev=counts[e:e + 1],
+                         row_begin_dev=offsets[e:e + 1], out_row_index=src_of)
+            if aux is not None:
+                aux.setdefault("mlp_expert", {})[i] = expert.view(B, seq).clone()
+        return self.head(x, B, seq, n_cls=1)

@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (AttentionArgs, GemmArgs, PK_EPI_BIAS_BF16, PK_EPI_BIAS_F32, PK_EPI_BIAS_GELU_BF16,
+from ._lib import (AttentionArgs, AvitArgs, CompactArgs, GemmArgs, ResidualGateArgs, PK_EPI_BIAS_BF16, PK_EPI_BIAS_F32, PK_EPI_BIAS_GELU_BF16,
                    PK_EPI_BIAS_RESID_F32, check)
 
 
@@ -55,7 +55,9 @@ def _rowmajor(t: torch.Tensor, name: str) -> int:
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, epilogue: int, *,
          resid: Optional[torch.Tensor] = None, rowscale: Optional[torch.Tensor] = None,
          rows_per_group: int = 0, group_stride: int = 0, group_offset: int = 0, resid_is_pos: bool = False,
-         m_dev: Optional[torch.Tensor] = None, block_n: int = 0, max_ctas: int = 0, m: Optional[int] = None) -> torch.Tensor:
+         pos_offset: Optional[int] = None, m_dev: Optional[torch.Tensor] = None, row_begin_dev: Optional[torch.Tensor] = None,
+         out_row_index: Optional[torch.Tensor] = None, block_n: int = 0, max_ctas: int = 0,
+         m: Optional[int] = None) -> torch.Tensor:
     """out = epilogue(a @ w.T + bias): a bf16 [M,K], w bf16 [N,K] (nn.Linear layout)."""
     lib = _lib_for(a)
     lda, ldw, ldo = _rowmajor(a, "a"), _rowmajor(w, "w"), _rowmajor(out, "out")
@@ -76,7 +78,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
     args.rowscale = _ptr(rowscale, torch.float32)
     args.rows_per_group, args.group_stride, args.group_offset = rows_per_group, group_stride, group_offset
     args.resid_is_pos = int(resid_is_pos)
+    args.pos_offset = group_offset if pos_offset is None else pos_offset
     args.m_dev = _ptr(m_dev, torch.int32)
+    args.row_begin_dev = _ptr(row_begin_dev, torch.int32)
+    args.out_row_index = _ptr(out_row_index, torch.int32)
     args.block_n, args.max_ctas = block_n, max_ctas
     if gemm_timeline is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -102,16 +107,25 @@ def patchify(images: torch.Tensor, patch_size: int, out: Optional[torch.Tensor] 
 
 
 def fill_token_rows(x: torch.Tensor, batch: int, seq_stride: int, row_offset: int, tokens: Optional[torch.Tensor],
-                    pos: Optional[torch.Tensor], scale: float = 1.0, n_tokens: Optional[int] = None) -> None:
+                    pos: Optional[torch.Tensor], scale: float = 1.0, n_tokens: Optional[int] = None,
+                    pos_offset: Optional[int] = None) -> None:
+    """``pos_offset``: first pos_embedding row to use when it differs from ``row_offset`` (ResidualViT keeps
+    its budget token at local row 1, which shifts the other tokens but not their position rows)."""
     lib = _lib_for(x)
     dim = x.shape[-1]
     if tokens is not None:
         tokens = tokens.reshape(-1, dim)
         n_tokens = tokens.shape[0]
+    pos_ptr = None
     if pos is not None:
         pos = pos.reshape(-1, dim)
+        po = row_offset if pos_offset is None else pos_offset
+        if po + n_tokens > pos.shape[0]:
+            raise ValueError("pos_embedding has too few rows")
+        # the kernel indexes pos[row_offset + t]; shift the base so that lands on pos[po + t]
+        pos_ptr = _ptr(pos, torch.float32) + (po - row_offset) * dim * 4
     check(lib.pk_fill_token_rows(_ptr(x, torch.float32), batch, seq_stride, row_offset, n_tokens, dim,
-                                 _ptr(tokens, torch.float32), _ptr(pos, torch.float32), float(scale), _stream()),
+                                 _ptr(tokens, torch.float32), pos_ptr, float(scale), _stream()),
           "pk_fill_token_rows")
 
 
@@ -195,6 +209,90 @@ def gather_rows(x: torch.Tensor, kept: torch.Tensor, batch: int, seq_len: int, o
     check(lib.pk_gather_rows(_ptr(x, torch.float32), _ptr(out, torch.float32), _ptr(kept, torch.int32), batch, seq_len, k, dim,
                              _stream()), "pk_gather_rows")
     return out
+
+
+def exclusive_scan(lens: torch.Tensor, cu_out: torch.Tensor, total_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib_for(lens)
+    n = lens.numel()
+    check(lib.pk_exclusive_scan_i32(_ptr(lens, torch.int32), n, _ptr(cu_out, torch.int32), _ptr(total_out, torch.int32), _stream()),
+          "pk_exclusive_scan_i32")
+    return cu_out
+
+
+def compact_rows(x_in, x_out, cu_in, cu_out, batch: int, rows_in_cap: int, dst_local, sample_of, *, scale_in=None, scale_out=None,
+                 attrs=(), ghost: bool = False) -> None:
+    """attrs: up to three (in, out) pairs of per-row fp32 attributes."""
+    lib = _lib_for(x_in)
+    a = CompactArgs()
+    a.x_in, a.x_out, a.dim = _ptr(x_in, torch.float32), _ptr(x_out, torch.float32), x_in.shape[-1]
+    a.cu_in, a.cu_out, a.batch = _ptr(cu_in, torch.int32), _ptr(cu_out, torch.int32), batch
+    a.rows_in_cap = rows_in_cap
+    a.dst_local, a.sample_of = _ptr(dst_local, torch.int32), _ptr(sample_of, torch.int32)
+    a.scale_in, a.scale_out = _ptr(scale_in, torch.float32), _ptr(scale_out, torch.float32)
+    pairs = list(attrs) + [(None, None)] * (3 - len(attrs))
+    a.a0_in, a.a0_out = _ptr(pairs[0][0], torch.float32), _ptr(pairs[0][1], torch.float32)
+    a.a1_in, a.a1_out = _ptr(pairs[1][0], torch.float32), _ptr(pairs[1][1], torch.float32)
+    a.a2_in, a.a2_out = _ptr(pairs[2][0], torch.float32), _ptr(pairs[2][1], torch.float32)
+    a.ghost = int(ghost)
+    check(lib.pk_compact_rows(C.byref(a), _stream()), "pk_compact_rows")
+
+
+def budget_mean_threshold(x, cu, batch: int, budget_pos: int, thr_out) -> None:
+    lib = _lib_for(x)
+    check(lib.pk_budget_mean_threshold(_ptr(x, torch.float32), _ptr(cu, torch.int32), batch, budget_pos, x.shape[-1],
+                                       _ptr(thr_out, torch.float32), _stream()), "pk_budget_mean_threshold")
+
+
+def residual_gate_plan(x, cu_in, mult_in, batch: int, max_seq_len: int, *, n_special: int, budget_pos: int, gated: bool,
+                       gate_w=None, gate_b: float = 0.0, gate_temp: float = 1.0, gate_bias: float = 0.0, gate_type: int = 0,
+                       thr_mode: int = 2, bt_w=None, bt_b: float = 0.0, thr_dev=None, thr_const: float = 0.5,
+                       mask, dst_local, sample_of, new_len, mdrop) -> None:
+    lib = _lib_for(x)
+    a = ResidualGateArgs()
+    a.x, a.cu_in, a.mult_in = _ptr(x, torch.float32), _ptr(cu_in, torch.int32), _ptr(mult_in, torch.float32)
+    a.batch, a.dim, a.max_seq_len = batch, x.shape[-1], max_seq_len
+    a.n_special, a.budget_pos, a.gated = n_special, budget_pos, int(gated)
+    a.gate_w, a.gate_b, a.gate_temp, a.gate_bias, a.gate_type = _ptr(gate_w, torch.float32), gate_b, gate_temp, gate_bias, gate_type
+    a.thr_mode, a.bt_w, a.bt_b = thr_mode, _ptr(bt_w, torch.float32), bt_b
+    a.thr_dev, a.thr_const = _ptr(thr_dev, torch.float32), thr_const
+    a.mask, a.dst_local, a.sample_of = _ptr(mask, torch.float32), _ptr(dst_local, torch.int32), _ptr(sample_of, torch.int32)
+    a.new_len, a.mdrop = _ptr(new_len, torch.int32), _ptr(mdrop, torch.float32)
+    check(lib.pk_residual_gate_plan(C.byref(a), _stream()), "pk_residual_gate_plan")
+
+
+def residual_ghost(x, mult, cu, mdrop, mlp0, batch: int) -> None:
+    lib = _lib_for(x)
+    check(lib.pk_residual_ghost(_ptr(x, torch.float32), _ptr(mult, torch.float32), _ptr(cu, torch.int32), _ptr(mdrop, torch.float32),
+                                _ptr(mlp0, torch.float32), batch, x.shape[-1], _stream()), "pk_residual_ghost")
+
+
+def residual_publish(mask, dst_local, cu_out, tok_row, mask_pub, batch: int, n_img: int) -> None:
+    lib = _lib_for(mask)
+    check(lib.pk_residual_publish(_ptr(mask, torch.float32), _ptr(dst_local, torch.int32), _ptr(cu_out, torch.int32),
+                                  _ptr(tok_row, torch.int32), _ptr(mask_pub, torch.float32), batch, n_img, _stream()),
+          "pk_residual_publish")
+
+
+def avit_halt_plan(x, cu_in, batch: int, seq_total: int, c, R, tokid, *, gate_scale: float, gate_center: float, eps: float,
+                   last_layer: bool, early_exit: bool, out_acc, rho=None, counter=None, dst_local, sample_of, new_len, n_halted) -> None:
+    lib = _lib_for(x)
+    a = AvitArgs()
+    a.x, a.cu_in, a.batch, a.dim, a.seq_total = _ptr(x, torch.float32), _ptr(cu_in, torch.int32), batch, x.shape[-1], seq_total
+    a.c, a.R, a.tokid = _ptr(c, torch.float32), _ptr(R, torch.float32), _ptr(tokid, torch.float32)
+    a.gate_scale, a.gate_center, a.eps = gate_scale, gate_center, eps
+    a.last_layer, a.early_exit = int(last_layer), int(early_exit)
+    a.out_acc, a.rho, a.counter = _ptr(out_acc, torch.float32), _ptr(rho, torch.float32), _ptr(counter, torch.float32)
+    a.dst_local, a.sample_of = _ptr(dst_local, torch.int32), _ptr(sample_of, torch.int32)
+    a.new_len, a.n_halted = _ptr(new_len, torch.int32), _ptr(n_halted, torch.float32)
+    check(lib.pk_avit_halt_plan(C.byref(a), _stream()), "pk_avit_halt_plan")
+
+
+def moe_route(x, gamma, beta, eps: float, gate_w, gate_b, rows: int, expert, offsets, counts, src_of) -> None:
+    lib = _lib_for(x)
+    check(lib.pk_moe_route(_ptr(x, torch.float32), _ptr(gamma, torch.float32), _ptr(beta, torch.float32), float(eps),
+                           _ptr(gate_w, torch.float32), _ptr(gate_b, torch.float32), gate_w.shape[0], rows, x.shape[-1],
+                           _ptr(expert, torch.int32), _ptr(offsets, torch.int32), _ptr(counts, torch.int32),
+                           _ptr(src_of, torch.int32), _stream()), "pk_moe_route")
 
 
 def device_flag(reset: bool = True) -> int:

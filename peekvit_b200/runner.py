@@ -68,7 +68,55 @@ def _forward_chunk(model, fwd: engine.Forward, chunk: torch.Tensor, aux: Optiona
         return fwd.vit(chunk)
     if family == "rankvit":
         return fwd.rankvit(chunk, _rank_budgets(model), aux)
-    raise NotImplementedError(f"{type(model).__name__}: forward for family {family!r} is not built yet")
+    if family == "residualvit":
+        b = model.current_budget
+        return fwd.residualvit(chunk, None if b is None else float(b), aux)
+    if family == "adavit":
+        return fwd.adavit(chunk, aux, early_exit=bool(getattr(model, "pk_early_exit", True)))
+    if family == "moevit":
+        return fwd.moevit(chunk, aux)
+    raise NotImplementedError(f"{type(model).__name__}: unknown family {family!r}")
+
+
+def _micro_batch(model, B: int) -> int:
+    mb = int(getattr(model, "pk_micro_batch", DEFAULT_MICRO_BATCH))
+    if model._family == "residualvit" and model.add_budget_token and model.add_budget_token not in ("learnable", "learnable_interpolate"):
+        # a fixed-float budget token thresholds on the mean over the WHOLE batch (residualvit.py:208):
+        # the batch cannot be split without changing the reference semantics
+        return max(B, 1)
+    return mb
+
+
+def _merge_aux(total: dict, part: dict) -> None:
+    """Concatenate per-micro-batch side-state along the batch dimension."""
+    for k, v in part.items():
+        if isinstance(v, dict):
+            d = total.setdefault(k, {})
+            for kk, vv in v.items():
+                d.setdefault(kk, []).append(vv)
+        elif isinstance(v, list):
+            total.setdefault(k, []).append(v)
+        else:
+            total.setdefault(k, []).append(v)
+
+
+def _publish_side_state(model, merged: dict) -> None:
+    """The state the reference leaves on its modules after a forward: ResidualViT
+    block.mask (utils/utils.py:100-122), MoE gating_probs (utils/utils.py:76-94), AViT rho/counter
+    (utils/losses.py:155,175)."""
+    fam = model._family
+    if fam == "residualvit":
+        for i, parts in merged.get("masks", {}).items():
+            model.encoder.layers[i].mask = torch.cat(parts, dim=0)
+    elif fam == "adavit":
+        if "rho_token" in merged:
+            model.encoder.rho_token = torch.cat(merged["rho_token"], dim=0)
+            model.encoder.counter_token = torch.cat(merged["counter_token"], dim=0)
+    elif fam == "moevit":
+        for i, parts in merged.get("mlp_expert", {}).items():
+            blk = model.encoder.layers[i]
+            ids = torch.cat(parts, dim=0).long()
+            blk.mlp.gating_probs = torch.nn.functional.one_hot(ids, num_classes=blk.mlp.num_experts).float()
 
 
 def run(model, x: torch.Tensor, aux: Optional[dict] = None) -> torch.Tensor:
@@ -80,12 +128,24 @@ def run(model, x: torch.Tensor, aux: Optional[dict] = None) -> torch.Tensor:
     x = x.detach().to(torch.float32).contiguous()
     with torch.no_grad():
         fwd = engine.Forward(packed(model), workspace(model, dev))
-        mb = int(getattr(model, "pk_micro_batch", DEFAULT_MICRO_BATCH))
         B = x.shape[0]
+        mb = _micro_batch(model, B)
         out = torch.empty(B, model.num_classes, dtype=torch.float32, device=dev)
+        merged: dict = {}
+        want_state = model._family in ("residualvit", "adavit", "moevit") or aux is not None
         for s in range(0, B, mb):
             chunk = x[s:s + mb]
-            out[s:s + chunk.shape[0]].copy_(_forward_chunk(model, fwd, chunk, aux))
+            part = {} if want_state else None
+            out[s:s + chunk.shape[0]].copy_(_forward_chunk(model, fwd, chunk, part))
+            if part is not None:
+                _merge_aux(merged, part)
+        _publish_side_state(model, merged)
+        if aux is not None:
+            if model._family == "rankvit" and B <= mb:        # single chunk: hand the tensors through unchanged
+                for k, v in merged.items():
+                    aux[k] = {kk: vv[0] for kk, vv in v.items()} if isinstance(v, dict) else v[0]
+            else:
+                aux.update(merged)
     return out
 
 
@@ -103,7 +163,7 @@ def run_host(model, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = Non
     with torch.no_grad():
         ws = workspace(model, dev)
         fwd = engine.Forward(packed(model), ws)
-        mb = min(int(getattr(model, "pk_micro_batch", DEFAULT_MICRO_BATCH)), max(B, 1))
+        mb = min(_micro_batch(model, B), max(B, 1))
         st = _state(model)
         if "copy_stream" not in st:
             st["copy_stream"] = torch.cuda.Stream(device=dev)

@@ -309,6 +309,63 @@ def probe_model():
         report(f"vit_b16_throughput_mb{mb}", ms=ms, img_s=1024 / ms * 1e3, flag=ops.device_flag())
 
 
+def probe_sparse():
+    """ResidualViT / AViT / MoE drop-ins against the reference fixtures + the oracle, with the
+    per-layer diagnostics needed to debug compaction remotely."""
+    import numpy as np
+    from golden_cases import CASES, build_case
+    from peekvit_b200.models import build_model
+    from peekvit_b200 import runner
+    from oracle import peekvit_oracle as po
+    names = {"residualvit": "residualvit", "adavit": "adavit", "moevit": "vitmoe"}
+    for name, case in CASES.items():
+        fam = case["family"]
+        if fam not in names:
+            continue
+        try:
+            sd, images = build_case(case)
+            model = build_model(names[fam], case["cfg"])
+            model.load_state_dict(sd, strict=True)
+            model = model.to(DEV).eval()
+            if case.get("budget") is not None:
+                model.set_budget(case["budget"])
+            aux = {}
+            logits = runner.run(model, images.to(DEV), aux).cpu()
+            gold = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+            ref = torch.from_numpy(gold["logits"])
+            info = dict(err=rel_err(logits, ref), flag=ops.device_flag(), nan=int(torch.isnan(logits).sum()))
+            if fam == "residualvit":
+                for i, blk in enumerate(model.encoder.layers):
+                    if blk.mask is None:
+                        continue
+                    m, g = blk.mask.cpu(), torch.from_numpy(gold[f"mask_{i}"])
+                    info[f"L{i}"] = dict(shape=list(m.shape), keep=float((m > 0).float().mean()), keep_ref=float((g > 0).float().mean()),
+                                         agree=float(((m > 0) == (g > 0)).float().mean()), maxdiff=float((m - g).abs().max()),
+                                         rows=[int(r) for r in aux["rows"][i]] if "rows" in aux else None)
+            if fam == "adavit":
+                info["rows"] = [int(r[0]) for r in aux.get("rows", [[]])[0]] if aux.get("rows") else None
+                model.pk_early_exit = False
+                logits2 = runner.run(model, images.to(DEV)).cpu()
+                info["err_no_early_exit"] = rel_err(logits2, ref)
+                cnt, gcnt = model.encoder.counter_token.cpu(), torch.from_numpy(gold["counter_token"])
+                rho, grho = model.encoder.rho_token.cpu(), torch.from_numpy(gold["rho_token"])
+                info["counter_agree"] = float((cnt == gcnt).float().mean())
+                info["rho_maxdiff"] = float((rho - grho).abs().max())
+            if fam == "moevit":
+                for i, blk in enumerate(model.encoder.layers):
+                    gp = blk.mlp.gating_probs
+                    if gp is not None:
+                        info[f"route_agree_L{i}"] = float((gp.argmax(-1).cpu().numpy() == gold[f"mlp_gating_{i}"]).mean())
+            report(f"sparse_{name}", **info)
+        except Exception as e:  # keep going: one broken family must not hide the others
+            import traceback
+            report(f"sparse_{name}", exception=repr(e), tb=traceback.format_exc()[-1500:])
+            try:
+                ops.device_flag()
+            except Exception:
+                pass
+
+
 if __name__ == "__main__":
     which = sys.argv[1]
     out = None
@@ -316,7 +373,8 @@ if __name__ == "__main__":
         out = sys.argv[sys.argv.index("--json") + 1]
     print("device:", torch.cuda.get_device_name(0), flush=True)
     try:
-        {"gemm": probe_gemm, "ln": probe_ln, "attn": probe_attn, "rows": probe_rows, "rank": probe_rank, "model": probe_model}[which]()
+        {"gemm": probe_gemm, "ln": probe_ln, "attn": probe_attn, "rows": probe_rows, "rank": probe_rank, "model": probe_model,
+         "sparse": probe_sparse}[which]()
     finally:
         if out:
             os.makedirs(os.path.dirname(out), exist_ok=True)
