@@ -15,7 +15,7 @@ DEV = "cuda:0"
 TOL_LOGITS = 1e-2
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 NAMES = {"vit": "vit", "rankvit": "RankVisionTransformer", "residualvit": "residualvit", "adavit": "adavit", "moevit": "vitmoe"}
-BUILT = ("vit", "rankvit")
+BUILT = ("vit", "rankvit", "residualvit", "adavit", "moevit")
 
 
 def _model(case):
@@ -51,6 +51,31 @@ def test_model_matches_reference_fixture(name):
             g = ref[f"kept_{i}"]
             overlap = np.mean([len(set(a) & set(b)) / len(a) for a, b in zip(kept.cpu().numpy().tolist(), g.tolist())])
             assert overlap >= 0.9
+    if case["family"] == "residualvit":
+        # published side-state: block.mask (B, N_img, 1) soft gate values (utils/utils.py:100-122).  Values are
+        # continuous in the activations (bf16 band); a keep/drop flag can only differ at a near-tie with the
+        # threshold, where the soft value itself is ~0.
+        agree = []
+        for i, blk in enumerate(model.encoder.layers):
+            g = torch.from_numpy(ref[f"mask_{i}"])
+            m = blk.mask.cpu()
+            assert m.shape == g.shape
+            assert (m - g).abs().max().item() < 5e-3
+            agree.append(((m > 0) == (g > 0)).float().mean().item())
+        assert np.mean(agree) >= 0.9
+    if case["family"] == "adavit":
+        assert model.encoder.rho_token.shape == ref["rho_token"].shape
+        model.pk_early_exit = False           # exact per-token ACT bookkeeping needs every sample run to the end
+        logits2 = runner.run(model, images.to(DEV)).cpu().numpy()
+        assert np.abs(logits2 - ref["logits"]).max() / scale < TOL_LOGITS
+        cnt = model.encoder.counter_token.cpu().numpy()
+        assert (cnt == ref["counter_token"]).mean() >= 0.97        # a halting near-tie may move a token by one layer
+    if case["family"] == "moevit":
+        for i, blk in enumerate(model.encoder.layers):
+            if blk.mlp.gating_probs is not None:
+                gp = blk.mlp.gating_probs
+                assert gp.shape[-1] == blk.mlp.num_experts and torch.all(gp.sum(-1) == 1)
+                assert (gp.argmax(-1).cpu().numpy() == ref[f"mlp_gating_{i}"]).mean() >= 0.98
 
 
 def test_vit_tiny_config_a_against_oracle():
@@ -134,7 +159,7 @@ def test_module_contract_on_device():
         model(x)
     model.eval()
     assert model(x).shape == (2, 10)
-    with pytest.raises(RuntimeError):          # wrong image size (torch._assert)
+    with pytest.raises(AssertionError):        # wrong image size (torch._assert, vit.py:206-207)
         model(torch.randn(2, 3, 40, 40, device=DEV))
     with pytest.raises(RuntimeError):          # CPU input to a CUDA model
         model(torch.randn(2, 3, 32, 32))
@@ -145,3 +170,33 @@ def test_module_contract_on_device():
     assert torch.allclose(model(x), y0 + 1.0, atol=1e-6)
     del model.encoder.layers[1]
     assert model(x).shape == (2, 10) and not torch.equal(model(x), y0 + 1.0)
+
+
+def test_residualvit_really_compacts_and_scales_with_budget():
+    """ViT-S shape (BASELINE config C), calibrated gates: the packed row count per layer follows the budget,
+    logits stay within the bf16 band of the oracle, and masks are published per layer."""
+    from oracle import peekvit_oracle as po, weights as ow
+    from peekvit_b200 import runner
+    from peekvit_b200.models import ResidualVisionTransformer
+    cfg = dict(image_size=224, patch_size=16, num_layers=12, num_heads=6, hidden_dim=384, mlp_dim=1536, num_classes=1000,
+               gate_type="sigmoid", gate_temp=1.0, gate_bias=0.0, gate_threshold=0.5, add_budget_token="learnable",
+               residual_layers=["attention+mlp"] * 12)
+    sd = ow.make_state_dict("residualvit", cfg, seed=4321)
+    sd = ow.calibrate_residual_gates(sd, cfg, 0.4, images=ow.synthetic_images(2, 224, seed=99))
+    images = ow.synthetic_images(6, 224, seed=1234)
+    model = ResidualVisionTransformer(**cfg)
+    model.load_state_dict(sd)
+    model = model.to(DEV).eval()
+    model.set_budget(0.4)
+    aux = {}
+    logits = runner.run(model, images.to(DEV), aux).cpu()
+    ref, oaux = po.forward("residualvit", sd, cfg, images, 0.4)
+    err = ((logits - ref).abs().max() / ref.abs().max()).item()
+    rows = [int(r[0][0]) for _, r in sorted(aux["rows"].items())]
+    keep = [float((m > 0).float().mean()) for _, m in sorted(oaux["masks"].items())]
+    print(f"residualvit ViT-S budget 0.4: rel err {err:.3e}; packed rows/layer {rows} (dense {6 * 198}); oracle keep {keep}")
+    assert err < TOL_LOGITS
+    assert max(rows) <= 6 * 199 and np.mean(rows) < 0.75 * 6 * 198          # survivors only
+    for i, blk in enumerate(model.encoder.layers):
+        assert blk.mask.shape == (6, 196, 1)
+        assert (blk.mask.cpu() - oaux["masks"][i]).abs().max().item() < 5e-3
