@@ -196,12 +196,13 @@ def main():
     labels = torch.randint(0, CFG_B["num_classes"], (B,), device=dev, generator=g)
     counts = torch.zeros(2, dtype=torch.int64, device=dev)
 
+    from peekvit_b200 import sharding
+    total_t = torch.tensor(B, device=dev)
+
     def step():
         logits = model(images)
-        counts[0] = (logits.argmax(1) == labels).sum()
-        counts[1] = B
-        if world > 1:
-            dist.all_reduce(counts)          # the eval loop's accuracy count (validate/test.py:120-127)
+        # the eval loop's accuracy count (validate/test.py:120-127): the only cross-GPU exchange
+        counts.copy_(sharding.reduce_counts((logits.argmax(1) == labels).sum(), total_t))
         return logits
 
     def barrier():

@@ -4,6 +4,8 @@
 #include "pk_common.cuh"
 #include "../../include/peekvit_b200.h"
 
+#include <algorithm>
+
 namespace pk {
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -168,7 +170,10 @@ cls_head_kernel(const float* __restrict__ x, int batch, int seq_len, const int* 
     }
   }
   __syncthreads();
-  for (int cls = warp; cls < num_classes; cls += (blockDim.x >> 5)) {
+  // blockIdx.y splits the classes so small batches still fill the machine
+  const int per = (num_classes + gridDim.y - 1) / gridDim.y;
+  const int cls_begin = blockIdx.y * per, cls_end = min(num_classes, cls_begin + per);
+  for (int cls = cls_begin + warp; cls < cls_end; cls += (blockDim.x >> 5)) {
     float part[kHeadGroup];
 #pragma unroll
     for (int s = 0; s < kHeadGroup; ++s) part[s] = 0.f;
@@ -305,7 +310,10 @@ extern "C" int pk_cls_head(const float* x, int batch, int seq_len, const int* cu
   PK_REQUIRE(dim % 4 == 0 && dim <= 1024 && n_cls >= 1, "pk_cls_head: dim %d must be a multiple of 4, <= 1024", dim);
   if (batch == 0) return PK_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int grid = (batch + kHeadGroup - 1) / kHeadGroup;
+  const int groups = (batch + kHeadGroup - 1) / kHeadGroup;
+  int chunks = (2 * num_sms() + groups - 1) / groups;                 // aim at >= 2 CTAs per SM
+  chunks = std::max(1, std::min(chunks, (num_classes + 7) / 8));      // at least one class per warp
+  const dim3 grid(groups, chunks);
   const size_t smem = (size_t)kHeadGroup * dim * sizeof(float);
   const int maxv = (dim / 4 + 31) / 32;
   if (maxv <= 3)

@@ -153,6 +153,9 @@ def test_rankvit_b16_budget_sweep_against_oracle():
 def test_module_contract_on_device():
     from peekvit_b200.models import VisionTransformer
     model = VisionTransformer(image_size=32, patch_size=8, num_layers=2, num_heads=2, hidden_dim=64, mlp_dim=128, num_classes=10)
+    with torch.no_grad():       # random-init head / class token are zero (vit.py:165,186-188): make logits non-vacuous
+        model.head.weight.normal_(std=0.1)
+        model.class_tokens.normal_(std=0.5)
     model = model.to(DEV)
     x = torch.randn(2, 3, 32, 32, device=DEV)
     with pytest.raises(RuntimeError):          # training mode: inference path only
@@ -165,11 +168,16 @@ def test_module_contract_on_device():
         model(torch.randn(2, 3, 32, 32))
     # prepacked weights follow in-place parameter updates and layer deletion
     y0 = model(x)
+    assert y0.abs().max() > 1e-3
     with torch.no_grad():
         model.head.bias.add_(1.0)
     assert torch.allclose(model(x), y0 + 1.0, atol=1e-6)
-    del model.encoder.layers[1]
-    assert model(x).shape == (2, 10) and not torch.equal(model(x), y0 + 1.0)
+    del model.encoder.layers[1]                # topology.py:177-178 / vit.py:312-313
+    y1 = model(x)
+    assert y1.shape == (2, 10) and not torch.allclose(y1, y0 + 1.0, atol=1e-4)
+    # host-resident batch: same logits through the double-buffered H2D path
+    yh = model.forward_host(x.cpu().pin_memory())
+    assert yh.device.type == "cpu" and torch.allclose(yh, y1.cpu(), atol=1e-6)
 
 
 def test_residualvit_really_compacts_and_scales_with_budget():
