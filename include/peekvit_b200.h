@@ -71,6 +71,7 @@ typedef struct pk_gemm_args {
                                row out_row_index[r] (un-permute of expert-sorted tokens) */
   int block_n;           /* 0 = auto, or 128 / 192 / 256 */
   int max_ctas;          /* 0 = one CTA per SM */
+  int epilogue_mode;     /* 0 = auto (TMA tile store when rows are contiguous), 2 = force the SIMT epilogue */
 } pk_gemm_args;
 
 int pk_gemm_bf16(const pk_gemm_args* args, void* stream);

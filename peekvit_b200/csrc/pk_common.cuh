@@ -150,6 +150,79 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap,
       : "memory");
 }
 
+// 2-D tiled store shared -> global (bulk async group); out-of-bounds rows/columns are clipped.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+// ---------------------------------------------------------------- packed fp32x2 math (FFMA2 on sm_100)
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// Exact-GELU of two values at once: same Abramowitz–Stegun erfc as gelu_erf(), polynomial and
+// products on the packed FFMA2 pipe, 0.5 folded into the coefficients:
+//   h = 0.5*erfc(|x|/sqrt2);  gelu(x) = x * (0.5 + sign(x) * (0.5 - h))
+__device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1) {
+  const float z0 = fabsf(x0) * 0.70710678118654752f, z1 = fabsf(x1) * 0.70710678118654752f;
+  const uint64_t z = f2_pack(z0, z1);
+  const uint64_t d = f2_fma(f2_pack(0.3275911f, 0.3275911f), z, f2_pack(1.0f, 1.0f));
+  float d0, d1;
+  f2_unpack(d, d0, d1);
+  const uint64_t t = f2_pack(rcp_approx(d0), rcp_approx(d1));
+  uint64_t p = f2_fma(f2_pack(0.5f * 1.061405429f, 0.5f * 1.061405429f), t, f2_pack(0.5f * -1.453152027f, 0.5f * -1.453152027f));
+  p = f2_fma(p, t, f2_pack(0.5f * 1.421413741f, 0.5f * 1.421413741f));
+  p = f2_fma(p, t, f2_pack(0.5f * -0.284496736f, 0.5f * -0.284496736f));
+  p = f2_fma(p, t, f2_pack(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+  p = f2_mul(p, t);
+  const uint64_t a = f2_mul(f2_mul(z, z), f2_pack(-1.4426950408889634f, -1.4426950408889634f));   // -z^2 * log2(e)
+  float a0, a1;
+  f2_unpack(a, a0, a1);
+  const uint64_t h = f2_mul(p, f2_pack(ex2_approx(a0), ex2_approx(a1)));                                    // 0.5*erfc(z)
+  const uint64_t g = f2_fma(h, f2_pack(-1.0f, -1.0f), f2_pack(0.5f, 0.5f));                        // 0.5 - h  (>= 0)
+  float g0, g1;
+  f2_unpack(g, g0, g1);
+  g0 = copysignf(g0, x0);
+  g1 = copysignf(g1, x1);
+  const uint64_t x = f2_pack(x0, x1);
+  const uint64_t r = f2_fma(x, f2_pack(g0, g1), f2_mul(x, f2_pack(0.5f, 0.5f)));
+  f2_unpack(r, x0, x1);
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
@@ -215,5 +288,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int b_mn_ma
 // (box_rows x 64)-element box and 128-byte swizzle.  Cached by key.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                       uint32_t box_rows, uint32_t box_cols);
+// General form: elem_bytes 2 (bf16) or 4 (f32); swizzle_bytes 128 or 64 (= box_cols * elem_bytes).
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                 uint32_t box_rows, uint32_t box_cols, int swizzle_bytes);
 
 }  // namespace pk

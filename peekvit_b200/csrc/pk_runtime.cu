@@ -64,8 +64,10 @@ struct TmapKey {
   const void* base;
   uint64_t rows, cols, ld;
   uint32_t box_rows, box_cols;
+  int elem_bytes, swizzle;
   bool operator==(const TmapKey& o) const {
-    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols;
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols &&
+           elem_bytes == o.elem_bytes && swizzle == o.swizzle;
   }
 };
 struct TmapKeyHash {
@@ -75,18 +77,19 @@ struct TmapKeyHash {
     h = h * 1000003u ^ k.cols;
     h = h * 1000003u ^ k.ld;
     h = h * 1000003u ^ (static_cast<size_t>(k.box_rows) << 16 | k.box_cols);
+    h = h * 1000003u ^ static_cast<size_t>(k.elem_bytes * 1024 + k.swizzle);
     return h;
   }
 };
 static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
 
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                      uint32_t box_rows, uint32_t box_cols) {
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                 uint32_t box_rows, uint32_t box_cols, int swizzle_bytes) {
   if (!g_ctx.encode) {
     set_last_error("pk_init() has not been called");
     return PK_ERR_INVALID;
   }
-  TmapKey key{base, rows, cols, ld_elems, box_rows, box_cols};
+  TmapKey key{base, rows, cols, ld_elems, box_rows, box_cols, elem_bytes, swizzle_bytes};
   std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_tmaps.find(key);
   if (it != g_tmaps.end()) {
@@ -94,20 +97,28 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
     return PK_OK;
   }
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint64_t gstride[1] = {ld_elems * static_cast<uint64_t>(elem_bytes)};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estride[2] = {1, 1};
-  CUresult r = g_ctx.encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
+  CUresult r = g_ctx.encode(out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_last_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%llu cols=%llu ld=%llu box=%ux%u", static_cast<int>(r), base,
-                   (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows, box_cols);
+    set_last_error("cuTensorMapEncodeTiled failed (%d): base=%p elem=%d rows=%llu cols=%llu ld=%llu box=%ux%u swizzle=%d", static_cast<int>(r),
+                   base, elem_bytes, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows, box_cols,
+                   swizzle_bytes);
     return PK_ERR_CUDA;
   }
   if (g_tmaps.size() > 8192) g_tmaps.clear();
   g_tmaps.emplace(key, *out);
   return PK_OK;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                      uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_2d(out, base, 2, rows, cols, ld_elems, box_rows, box_cols, 128);
 }
 
 }  // namespace pk

@@ -52,6 +52,28 @@ def test_gemm_f32(ops, shape, block_n):
     assert rel_err(out, a.float() @ w.float().t() + bias) < TOL_F32
 
 
+@pytest.mark.parametrize("shape", [(127, 192, 64), (300, 768, 768), (1000, 2304, 768), (513, 1000, 768)])
+def test_gemm_simt_epilogue_path(ops, shape):
+    """epilogue_mode=2 forces the per-row-predicated SIMT epilogue that remapped / segmented rows use."""
+    from peekvit_b200._lib import PK_EPI_BIAS_BF16, PK_EPI_BIAS_F32, PK_EPI_BIAS_GELU_BF16, PK_EPI_BIAS_RESID_F32
+    M, N, K = shape
+    a, w, bias = _operands(M, N, K, seed=9)
+    acc = a.float() @ w.float().t() + bias
+    out = torch.full((M, N), float("nan"), device=DEV)
+    ops.gemm(a, w, bias, out, PK_EPI_BIAS_F32, epilogue_mode=2)
+    assert rel_err(out, acc) < TOL_F32
+    x = torch.randn(M, N, device=DEV)
+    x0 = x.clone()
+    ops.gemm(a, w, bias, x, PK_EPI_BIAS_RESID_F32, resid=x, epilogue_mode=2)
+    assert rel_err(x, acc + x0) < TOL_F32
+    ob = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, w, bias, ob, PK_EPI_BIAS_GELU_BF16, epilogue_mode=2)
+    assert rel_err(ob, torch.nn.functional.gelu(acc)) < TOL_BF16
+    ops.gemm(a, w, bias, ob, PK_EPI_BIAS_BF16, epilogue_mode=2)
+    assert rel_err(ob, acc) < TOL_BF16
+    assert ops.device_flag() == 0
+
+
 def test_gemm_epilogues(ops):
     from peekvit_b200._lib import PK_EPI_BIAS_BF16, PK_EPI_BIAS_GELU_BF16, PK_EPI_BIAS_RESID_F32
     M, N, K = 1000, 768, 768
