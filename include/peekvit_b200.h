@@ -72,6 +72,8 @@ typedef struct pk_gemm_args {
   int block_n;           /* 0 = auto, or 128 / 192 / 256 */
   int max_ctas;          /* 0 = one CTA per SM */
   int epilogue_mode;     /* 0 = auto (TMA tile store when rows are contiguous), 2 = force the SIMT epilogue */
+  int cta_pair;          /* 0 = auto (CTA-pair 256 x block_n tiles, tcgen05 cta_group::2, when rows are contiguous),
+                            1 = single-CTA 128 x block_n kernel, 2 = force the CTA-pair kernel */
 } pk_gemm_args;
 
 int pk_gemm_bf16(const pk_gemm_args* args, void* stream);

@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
         ("rows_per_group", c_int), ("group_stride", c_int), ("group_offset", c_int), ("resid_is_pos", c_int),
         ("pos_offset", c_int),
         ("m_dev", c_void_p), ("row_begin_dev", c_void_p), ("out_row_index", c_void_p), ("block_n", c_int), ("max_ctas", c_int),
-        ("epilogue_mode", c_int),
+        ("epilogue_mode", c_int), ("cta_pair", c_int),
     ]
 
 

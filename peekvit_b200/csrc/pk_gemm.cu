@@ -492,8 +492,10 @@ static int dispatch_epi(const pk_gemm_args* a, cudaStream_t stream) {
   return PK_ERR_INVALID;
 }
 
-// Tile width: the widest of {256,192,128} that wastes the fewest padded columns.
+// Tile width: 256 when it divides N (fewest A re-reads, best measured), else the width of
+// {192, 256, 128} that wastes the fewest padded columns.
 int pick_block_n(int N) {
+  if (N % 256 == 0) return 256;
   int best = 128;
   long long best_cost = -1;
   const int cands[3] = {192, 256, 128};
@@ -504,6 +506,10 @@ int pick_block_n(int N) {
   }
   return best;
 }
+
+// pk_gemm2.cu: CTA-pair (cta_group::2) kernel for plain row mappings
+bool pair_gemm_eligible(const pk_gemm_args* a);
+int launch_pair_gemm(const pk_gemm_args* a, cudaStream_t stream);
 
 }  // namespace pk
 
@@ -521,6 +527,8 @@ extern "C" int pk_gemm_bf16(const pk_gemm_args* a, void* stream) {
     PK_REQUIRE(a->resid != nullptr && a->ldr % 4 == 0, "pk_gemm_bf16: residual epilogue needs resid with ldr %% 4 == 0");
   if (a->M == 0) return PK_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a->cta_pair != 1 && pair_gemm_eligible(a) && (a->cta_pair == 2 || a->M > 256)) return launch_pair_gemm(a, s);
+  PK_REQUIRE(a->cta_pair != 2, "pk_gemm_bf16: the CTA-pair kernel needs contiguous rows, 16-byte aligned rows and N %% 8 == 0");
   const int bn = a->block_n > 0 ? a->block_n : pick_block_n(a->N);
   switch (bn) {
     case 128: return dispatch_epi<128>(a, s);

@@ -1,0 +1,503 @@
+// peekvit_b200 — CTA-pair (cta_group::2) tcgen05 GEMM with fused epilogues (sm_100a).
+//
+//   C[M,N] = A[M,K] (bf16, row-major) x W[N,K]^T (bf16, nn.Linear layout), f32 accumulate in TMEM
+//
+// The dense-rows fast path of pk_gemm_bf16 (same call sites as pk_gemm.cu: reference
+// models/blocks.py:94 in-proj, vit.py:49-51 out-proj + residual, blocks.py:81-83 fc1+GELU / fc2
+// + residual).  Two CTAs on neighbouring SMs (one cluster) own one 256 x BN output tile:
+//   * each CTA TMA-loads its own 128 rows of A and its own BN/2 rows of W per 64-wide K block
+//     (the pair reads every operand byte once: half the shared-memory and L2 traffic per FLOP of
+//     a 128 x BN single-CTA tile);
+//   * the leader CTA's single MMA thread issues tcgen05.mma.cta_group::2 (M = 256); each CTA's
+//     128 x BN slice of the accumulator lands in its own TMEM;
+//   * completion is multicast to both CTAs' barriers with tcgen05.commit ... multicast::cluster.
+// Per CTA: warp 0 = TMA producer, warp 1 = MMA issuer (leader only), warp 2 = TMEM allocator,
+// warps 4-11 = epilogue (tcgen05.ld -> registers -> swizzled smem -> TMA store; the fp32 residual
+// tile is TMA-loaded into the same smem slot two chunks ahead).  Two accumulator stages, so the
+// epilogue of tile i overlaps the MMAs of tile i+1.  Every mbarrier wait is bounded.
+#include "pk_common.cuh"
+#include "../../include/peekvit_b200.h"
+
+namespace pk {
+
+constexpr int kP_BM = 128;          // rows per CTA (256 per pair)
+constexpr int kP_BK = 64;           // 64 bf16 = one 128-byte swizzle row
+constexpr int kP_EpiWarps = 8;
+constexpr int kP_Threads = 128 + kP_EpiWarps * 32;
+constexpr int kP_BufBytes = 4096;   // one 32-row x 128-byte staging tile
+
+template <int BN, int EPI>
+struct PairCfg {
+  static constexpr bool kOutBf16 = (EPI == PK_EPI_BIAS_BF16 || EPI == PK_EPI_BIAS_GELU_BF16);
+  static constexpr bool kResid = (EPI == PK_EPI_BIAS_RESID_F32);
+  static constexpr int kUnits = BN / 64;                                      // 32-column accumulator units per warp
+  static constexpr int kUnitsPerStore = (kOutBf16 && kUnits % 2 == 0) ? 2 : 1; // bf16: 64 columns = one 128-byte row
+  static constexpr int kChunks = kUnits / kUnitsPerStore;                     // TMA stores per warp per tile
+  static constexpr int kStoreCols = 32 * kUnitsPerStore;
+  static constexpr int kStoreSwizzle = kOutBf16 ? (kUnitsPerStore == 2 ? 128 : 64) : 128;
+  static constexpr int kBufs = kResid ? 3 : 2;                                // staging buffers per epilogue warp
+  static constexpr int kABytes = kP_BM * kP_BK * 2;
+  static constexpr int kBBytes = (BN / 2) * kP_BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = kP_EpiWarps * kBufs * kP_BufBytes;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kBudget = 232448 - 1024 - kBarBytes - kStagingBytes;
+  static constexpr int kStagesRaw = kBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;
+  static_assert(kStages >= 3, "too few pipeline stages");
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
+};
+
+struct PairParams {
+  int M, N, K;
+  const int* m_dev;
+  const float* bias;
+  void* out;
+  long long ldo;
+  const float* rowscale;
+  unsigned int* flag;
+};
+
+// ---------------------------------------------------------------- cluster / cta_group::2 PTX
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA load into this CTA's smem; the byte count is credited to `bar` (a shared::cluster address:
+// the leader CTA's full barrier).
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void* tmap, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+// D[tmem, both CTAs] (+)= A[smem, both CTAs] * B[smem, both CTAs]^T ; issued by the leader CTA only.
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on the barrier at this smem offset in BOTH CTAs once all MMAs issued so far have completed.
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP_Threads, 1)
+gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+                      const PairParams p) {
+  using Cfg = PairCfg<BN, EPI>;
+  constexpr bool kOutBf16 = Cfg::kOutBf16;
+  constexpr bool kResid = Cfg::kResid;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_ab = smem;
+  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
+  uint64_t* full_bar = bars;                       // [kStages]   (the leader's copy is the live one)
+  uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]   per CTA, arrived by the multicast commit
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]         per CTA, arrived by the multicast commit
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]         leader's copy: 2 x kP_EpiWarps arrivals
+  uint64_t* res_bar = tempty_bar + 2;              // [kP_EpiWarps][3] residual-tile loads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 3 * kP_EpiWarps);
+
+  const int warp = warp_id();
+  const int lane = lane_id();
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int M = p.m_dev ? max(0, min(*p.m_dev, p.M)) : p.M;
+  const int m_tiles = (M + 2 * kP_BM - 1) / (2 * kP_BM);
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = p.K / kP_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
+    if constexpr (kResid) tma_prefetch_desc(&tmap_res);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tfull_bar[a]), 1);
+      mbar_init(smem_u32(&tempty_bar[a]), 2 * kP_EpiWarps);
+    }
+    for (int i = 0; i < 3 * kP_EpiWarps; ++i) mbar_init(smem_u32(&res_bar[i]), 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(smem_u32(tmem_slot), Cfg::kTmemCols);
+    tmem_relinquish_pair();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();                 // both CTAs' barriers and TMEM are ready before any cross-CTA signal
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    // The whole warp runs the loop (warp-uniform control flow keeps addresses and coordinates in
+    // uniform registers); one elected lane issues.
+    int s = 0;
+    uint32_t ph = 0;
+    const int a_row_off = static_cast<int>(rank) * kP_BM;
+    const int b_row_off = static_cast<int>(rank) * (BN / 2);
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+      bool ok = true;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ok = __all_sync(0xffffffffu, mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u, p.flag, 0x1100u + s));
+        if (!ok) break;
+        if (elect_one()) {
+          const uint32_t fb_local = smem_u32(&full_bar[s]);
+          if (rank == 0) mbar_expect_tx(fb_local, 2 * Cfg::kStageBytes);   // both CTAs' bytes land on the leader's barrier
+          const uint32_t fb = mapa_u32(fb_local, 0);
+          const uint32_t a_dst = smem_u32(smem_ab + s * Cfg::kStageBytes);
+          tma_load_2d_pair(a_dst, &tmap_a, fb, kb * kP_BK, m_blk * 2 * kP_BM + a_row_off);
+          tma_load_2d_pair(a_dst + Cfg::kABytes, &tmap_b, fb, kb * kP_BK, n_blk * BN + b_row_off);
+        }
+        __syncwarp();
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
+      }
+      if (!ok) break;
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+    // Warp-uniform loop, one elected lane issues: a divergent single-lane loop makes the compiler
+    // shuttle every descriptor through ELECT / R2UR.BROADCAST sequences (~160 instructions per K
+    // block, measured 760 cycles against 512 cycles of tensor work).
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kP_BM, BN);
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&tempty_bar[as]), aph ^ 1u, p.flag, 0x1200u + as))) break;
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        bool ok = true;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ok = __all_sync(0xffffffffu, mbar_wait(smem_u32(&full_bar[s]), ph, p.flag, 0x1300u + s));
+          if (!ok) break;
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint32_t a_addr = smem_u32(smem_ab + s * Cfg::kStageBytes);
+            const uint64_t a_desc = umma_desc_kmajor_sw128(a_addr);
+            const uint64_t b_desc = umma_desc_kmajor_sw128(a_addr + Cfg::kABytes);
+#pragma unroll
+            for (int k = 0; k < kP_BK / 16; ++k) {
+              umma_bf16_pair(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_pair(smem_u32(&empty_bar[s]));          // frees the slot in both CTAs
+            if (kb == num_kb - 1) umma_commit_pair(smem_u32(&tfull_bar[as]));
+          }
+          __syncwarp();
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
+        }
+        if (!ok) break;
+        if (++as == 2) { as = 0; aph ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue warps (both CTAs)
+    const int ew = warp - 4;
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = ew >> 2;               // which half of the tile's columns
+    constexpr int kUnits = Cfg::kUnits;
+    constexpr int kUPS = Cfg::kUnitsPerStore;
+    constexpr int kChunks = Cfg::kChunks;
+    constexpr int kBufs = Cfg::kBufs;
+    uint8_t* ebuf = staging + ew * kBufs * kP_BufBytes;                 // 1024-byte aligned
+    const uint32_t ebuf_u32 = smem_u32(ebuf);
+    uint64_t* rbar = res_bar + 3 * ew;
+    const int my_tiles = pair < num_tiles ? (num_tiles - pair + num_pairs - 1) / num_pairs : 0;
+    const uint32_t total_chunks = static_cast<uint32_t>(my_tiles) * kChunks;
+    const int row_in_pair = static_cast<int>(rank) * kP_BM + q * 32;
+    // residual tile of chunk `ch` of tile `tt` -> staging buffer g % 3   (lane 0 only)
+    auto issue_resid = [&](uint32_t g, int tt, int ch) {
+      const uint32_t b = g % 3u;
+      const uint32_t bar = smem_u32(&rbar[b]);
+      mbar_expect_tx(bar, kP_BufBytes);
+      tma_load_2d(ebuf_u32 + b * kP_BufBytes, &tmap_res, bar, (tt % n_tiles) * BN + half * (BN / 2) + ch * Cfg::kStoreCols,
+                  (tt / n_tiles) * 2 * kP_BM + row_in_pair);
+    };
+    if constexpr (kResid) {
+      if (lane == 0) {
+        if (total_chunks > 0) issue_resid(0, pair, 0);
+        if (total_chunks > 1) issue_resid(1, pair, 1);
+      }
+    }
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t tempty_leader0 = mapa_u32(smem_u32(&tempty_bar[0]), 0);
+    const uint32_t tempty_leader1 = mapa_u32(smem_u32(&tempty_bar[1]), 0);
+    uint32_t g = 0;                           // running chunk counter of this warp
+    int as = 0;
+    uint32_t aph = 0;
+    bool ok = true;
+    for (int t = pair; t < num_tiles && ok; t += num_pairs) {
+      const int m_blk = t / n_tiles;
+      const int row_base = m_blk * 2 * kP_BM + row_in_pair;                                // this warp's first row
+      const int grow = row_base + lane;
+      const bool full_tile = row_base + 32 <= M;                                           // warp-uniform
+      float sc = 1.0f;
+      if constexpr (kResid) {
+        if (p.rowscale && grow < M) sc = p.rowscale[grow];
+      }
+      if (!mbar_wait(smem_u32(&tfull_bar[as]), aph, p.flag, 0x1400u + as)) { ok = false; break; }
+      tcgen05_fence_after();
+      const uint32_t t_col0 = t_lane + static_cast<uint32_t>(as * BN + half * (BN / 2));
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(t_col0, va);
+#pragma unroll
+      for (int u = 0; u < kUnits; ++u) {
+        uint32_t (&v)[32] = (u & 1) ? vb : va;
+        uint32_t (&vn)[32] = (u & 1) ? va : vb;
+        const int ch = u / kUPS;              // store chunk inside the tile
+        const int sub = u % kUPS;             // unit inside the store chunk
+        const uint32_t b = kResid ? (g % 3u) : (g & 1u);
+        uint8_t* bufp = ebuf + b * kP_BufBytes;
+        const int col0 = (t % n_tiles) * BN + half * (BN / 2) + u * 32;     // first output column of this unit
+        float4 bias4[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          bias4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias && col0 + 4 * j < p.N) bias4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
+        }
+        tmem_ld_wait();                                                     // unit u is in registers
+        if (u + 1 < kUnits) {
+          tmem_ld_32x32(t_col0 + static_cast<uint32_t>((u + 1) * 32), vn);  // overlaps the math below
+        } else {
+          // every TMEM read of this accumulator stage is done: hand it back to the leader's MMA thread
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(as == 0 ? tempty_leader0 : tempty_leader1);
+        }
+        if (sub == 0) {
+          if constexpr (kResid) {
+            if (!mbar_wait(smem_u32(&rbar[b]), (g / 3u) & 1u, p.flag, 0x1500u + ew)) { ok = false; break; }
+          } else {
+            if (lane == 0) bulk_wait_read<1>();     // the store issued two chunks ago no longer reads this buffer
+            __syncwarp();
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = bias4[j];
+          float a0 = __uint_as_float(v[4 * j]) + b4.x, a1 = __uint_as_float(v[4 * j + 1]) + b4.y;
+          float a2 = __uint_as_float(v[4 * j + 2]) + b4.z, a3 = __uint_as_float(v[4 * j + 3]) + b4.w;
+          if constexpr (EPI == PK_EPI_BIAS_GELU_BF16) {
+            gelu_erf_x2(a0, a1);
+            gelu_erf_x2(a2, a3);
+          }
+          if constexpr (kResid) {
+            // 128-byte rows, 16-byte chunk j of row r lives at chunk j ^ (r & 7) (SWIZZLE_128B)
+            const float4 r4 = *reinterpret_cast<const float4*>(bufp + lane * 128 + ((j ^ (lane & 7)) << 4));
+            a0 = fmaf(a0, sc, r4.x); a1 = fmaf(a1, sc, r4.y); a2 = fmaf(a2, sc, r4.z); a3 = fmaf(a3, sc, r4.w);
+          }
+          if constexpr (kOutBf16) {
+            v[2 * j] = pack_bf16(a0, a1);
+            v[2 * j + 1] = pack_bf16(a2, a3);
+          } else {
+            v[4 * j] = __float_as_uint(a0); v[4 * j + 1] = __float_as_uint(a1);
+            v[4 * j + 2] = __float_as_uint(a2); v[4 * j + 3] = __float_as_uint(a3);
+          }
+        }
+        if (full_tile) {
+          if constexpr (kOutBf16) {
+            if constexpr (kUPS == 2) {
+              // 128-byte rows of 64 bf16: this unit fills 16-byte chunks sub*4 .. sub*4+3 (SWIZZLE_128B)
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(bufp + lane * 128 + (((sub * 4 + j) ^ (lane & 7)) << 4)) =
+                    make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              // 64-byte rows, 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3) (SWIZZLE_64B)
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(bufp + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                    make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(bufp + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (sub == kUPS - 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmap_out, ebuf_u32 + b * kP_BufBytes, col0 - sub * 32, row_base);
+              bulk_commit();
+            }
+          }
+        } else {
+          // partial row tile: rows >= M must stay untouched -> predicated row stores from registers.
+          // An empty bulk group keeps the one-group-per-chunk accounting of the buffer ring.
+          if (sub == kUPS - 1 && lane == 0) bulk_commit();
+        }
+        if (!full_tile && grow < M) {
+          if constexpr (kOutBf16) {
+            __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(grow) * p.ldo + col0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (col0 + 8 * j < p.N) *reinterpret_cast<uint4*>(orow + 8 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            float* orow = static_cast<float*>(p.out) + static_cast<long long>(grow) * p.ldo + col0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (col0 + 4 * j < p.N) *reinterpret_cast<uint4*>(orow + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        }
+        if (sub == kUPS - 1) {
+          if constexpr (kResid) {
+            // buffer (g+2)%3 was last read by the store of chunk g-1: one chunk of work ago
+            if (lane == 0 && g + 2 < total_chunks) {
+              bulk_wait_read<1>();
+              if (ch + 2 < kChunks) issue_resid(g + 2, t, ch + 2);
+              else issue_resid(g + 2, t + num_pairs, ch + 2 - kChunks);
+            }
+          }
+          ++g;
+        }
+      }
+      if (++as == 2) { as = 0; aph ^= 1u; }
+    }
+    if (lane == 0) bulk_wait_read<0>();     // smem must outlive the last stores' reads
+  }
+
+  __syncwarp();
+  tcgen05_fence_before();
+  cluster_sync_all();                       // no CTA leaves (or frees TMEM) while its peer may still signal it
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN, int EPI>
+static int launch_pair(const pk_gemm_args* a, cudaStream_t stream) {
+  using Cfg = PairCfg<BN, EPI>;
+  static bool attr_set = false;
+  auto kfn = gemm_bf16_pair_kernel<BN, EPI>;
+  if (!attr_set) {
+    PK_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  CUtensorMap ta, tb, tout, tres;
+  int rc = make_tmap_bf16_2d(&ta, a->A, static_cast<uint64_t>(a->M), static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->lda),
+                             kP_BM, kP_BK);
+  if (rc != PK_OK) return rc;
+  rc = make_tmap_bf16_2d(&tb, a->W, static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->ldw), BN / 2,
+                         kP_BK);
+  if (rc != PK_OK) return rc;
+  rc = make_tmap_2d(&tout, a->out, Cfg::kOutBf16 ? 2 : 4, static_cast<uint64_t>(a->M), static_cast<uint64_t>(a->N),
+                    static_cast<uint64_t>(a->ldo), 32, Cfg::kStoreCols, Cfg::kStoreSwizzle);
+  if (rc != PK_OK) return rc;
+  tres = tout;
+  if (Cfg::kResid) {
+    rc = make_tmap_2d(&tres, a->resid, 4, static_cast<uint64_t>(a->M), static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->ldr), 32,
+                      32, 128);
+    if (rc != PK_OK) return rc;
+  }
+  PairParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.m_dev = a->m_dev;
+  p.bias = a->bias;
+  p.out = a->out; p.ldo = a->ldo;
+  p.rowscale = a->rowscale;
+  p.flag = device_flag_ptr();
+  const int m_tiles = (a->M + 2 * kP_BM - 1) / (2 * kP_BM), n_tiles = (a->N + BN - 1) / BN;
+  int pairs = m_tiles * n_tiles;
+  const int sms = a->max_ctas > 0 ? a->max_ctas : num_sms();
+  if (pairs > sms / 2) pairs = sms / 2;
+  if (pairs < 1) pairs = 1;
+  kfn<<<2 * pairs, kP_Threads, Cfg::kSmemBytes, stream>>>(ta, tb, tout, tres, p);
+  return check_cuda(cudaGetLastError(), "gemm_bf16_pair_kernel launch");
+}
+
+template <int BN>
+static int dispatch_pair_epi(const pk_gemm_args* a, cudaStream_t stream) {
+  switch (a->epilogue) {
+    case PK_EPI_BIAS_BF16: return launch_pair<BN, PK_EPI_BIAS_BF16>(a, stream);
+    case PK_EPI_BIAS_GELU_BF16: return launch_pair<BN, PK_EPI_BIAS_GELU_BF16>(a, stream);
+    case PK_EPI_BIAS_RESID_F32: return launch_pair<BN, PK_EPI_BIAS_RESID_F32>(a, stream);
+    case PK_EPI_BIAS_F32: return launch_pair<BN, PK_EPI_BIAS_F32>(a, stream);
+  }
+  set_last_error("pk_gemm_bf16: unknown epilogue %d", a->epilogue);
+  return PK_ERR_INVALID;
+}
+
+// Pair tile width: the widest of {256, 192, 128} that wastes the fewest padded columns.
+static int pick_pair_block_n(int N) {
+  int best = 128;
+  long long best_cost = -1;
+  const int cands[3] = {256, 192, 128};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    const long long padded = static_cast<long long>((N + bn - 1) / bn) * bn;
+    if (best_cost < 0 || padded < best_cost) { best_cost = padded; best = bn; }
+  }
+  return best;
+}
+
+// The pair kernel needs plain row mapping (TMA tile stores), 16-byte aligned rows and N % 8 == 0.
+bool pair_gemm_eligible(const pk_gemm_args* a) {
+  if (a->epilogue_mode == 2) return false;
+  if (a->rows_per_group > 0 || a->row_begin_dev || a->out_row_index) return false;
+  const bool bf = a->epilogue == PK_EPI_BIAS_BF16 || a->epilogue == PK_EPI_BIAS_GELU_BF16;
+  const long long eb = bf ? 2 : 4;
+  if ((a->ldo * eb) % 16 != 0 || (reinterpret_cast<uintptr_t>(a->out) & 15) != 0) return false;
+  if (a->N % 8 != 0) return false;
+  if (a->epilogue == PK_EPI_BIAS_RESID_F32 && ((a->ldr * 4) % 16 != 0 || (reinterpret_cast<uintptr_t>(a->resid) & 15) != 0)) return false;
+  return true;
+}
+
+int launch_pair_gemm(const pk_gemm_args* a, cudaStream_t stream) {
+  const int bn = a->block_n > 0 ? a->block_n : pick_pair_block_n(a->N);
+  switch (bn) {
+    case 128: return dispatch_pair_epi<128>(a, stream);
+    case 192: return dispatch_pair_epi<192>(a, stream);
+    case 256: return dispatch_pair_epi<256>(a, stream);
+  }
+  set_last_error("pk_gemm_bf16: unsupported block_n %d", bn);
+  return PK_ERR_INVALID;
+}
+
+}  // namespace pk

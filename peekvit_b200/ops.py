@@ -57,7 +57,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
          rows_per_group: int = 0, group_stride: int = 0, group_offset: int = 0, resid_is_pos: bool = False,
          pos_offset: Optional[int] = None, m_dev: Optional[torch.Tensor] = None, row_begin_dev: Optional[torch.Tensor] = None,
          out_row_index: Optional[torch.Tensor] = None, block_n: int = 0, max_ctas: int = 0,
-         m: Optional[int] = None, epilogue_mode: int = 0) -> torch.Tensor:
+         m: Optional[int] = None, epilogue_mode: int = 0, cta_pair: int = 0) -> torch.Tensor:
     """out = epilogue(a @ w.T + bias): a bf16 [M,K], w bf16 [N,K] (nn.Linear layout)."""
     lib = _lib_for(a)
     lda, ldw, ldo = _rowmajor(a, "a"), _rowmajor(w, "w"), _rowmajor(out, "out")
@@ -84,6 +84,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
     args.out_row_index = _ptr(out_row_index, torch.int32)
     args.block_n, args.max_ctas = block_n, max_ctas
     args.epilogue_mode = epilogue_mode
+    args.cta_pair = cta_pair
     if gemm_timeline is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

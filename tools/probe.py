@@ -128,6 +128,81 @@ def probe_gemm():
         report(f"cublas_time_{name}", ms=ms, tflops=2.0 * Mbig * N * K / ms / 1e9)
 
 
+def probe_gemm2():
+    """CTA-pair (cta_group::2) kernel: every epilogue, partial tiles, device-side M, then timing vs the
+    single-CTA kernel and cuBLAS on the ViT-B shapes."""
+    torch.manual_seed(0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    shapes = [(256, 256, 64), (512, 256, 128), (300, 768, 768), (1000, 2304, 768), (1576, 3072, 768), (257, 768, 3072),
+              (1000, 384, 384), (777, 1152, 384), (197 * 64, 2304, 768), (600, 1000, 768)]
+    for (M, N, K) in shapes:
+        a = (torch.randn(M, K, device=DEV) * 0.5).to(torch.bfloat16)
+        w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).to(torch.bfloat16)
+        bias = torch.randn(N, device=DEV) * 0.1
+        acc = a.float() @ w.float().t() + bias
+        for bn in (0, 128, 192, 256):
+            out = torch.full((M, N), float("nan"), device=DEV)
+            ops.gemm(a, w, bias, out, PK_EPI_BIAS_F32, block_n=bn, cta_pair=2)
+            flag = ops.device_flag()
+            err = rel_err(out, acc)
+            bad = ~((out - acc).abs() <= 1e-3 * acc.abs().max())
+            extra = {}
+            if bad.any():
+                rows = bad.any(1).nonzero().flatten()
+                cols = bad.any(0).nonzero().flatten()
+                extra = dict(bad_frac=bad.float().mean().item(), bad_rows=rows[:8].tolist(), n_bad_rows=int(rows.numel()),
+                             bad_cols=cols[:8].tolist(), n_bad_cols=int(cols.numel()), nan=int(torch.isnan(out).sum()),
+                             sample_got=out[rows[0], cols[0]].item(), sample_ref=acc[rows[0], cols[0]].item())
+            report(f"pair_f32_M{M}_N{N}_K{K}_bn{bn}", err=err, flag=flag, **extra)
+            if flag:
+                return
+        for bn in (0, 128, 192):
+            outb = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+            ops.gemm(a, w, bias, outb, PK_EPI_BIAS_BF16, block_n=bn, cta_pair=2)
+            e1 = rel_err(outb, acc)
+            ops.gemm(a, w, bias, outb, PK_EPI_BIAS_GELU_BF16, block_n=bn, cta_pair=2)
+            e2 = rel_err(outb, torch.nn.functional.gelu(acc))
+            x = torch.randn(M, N, device=DEV)
+            rs = torch.rand(M, device=DEV)
+            x0 = x.clone()
+            ops.gemm(a, w, bias, x, PK_EPI_BIAS_RESID_F32, resid=x, rowscale=rs, block_n=bn, cta_pair=2)
+            e3 = rel_err(x, rs[:, None] * acc + x0)
+            report(f"pair_epi_M{M}_N{N}_K{K}_bn{bn}", bf16=e1, gelu=e2, resid=e3, flag=ops.device_flag())
+    # device-side M: rows >= m_dev stay untouched
+    M, N, K = 1000, 768, 384
+    a = (torch.randn(M, K, device=DEV) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).to(torch.bfloat16)
+    ref = a.float() @ w.float().t()
+    for md in (0, 1, 333, 512, 1000):
+        mdev = torch.tensor([md], device=DEV, dtype=torch.int32)
+        out = torch.zeros(M, N, device=DEV)
+        ops.gemm(a, w, None, out, PK_EPI_BIAS_F32, m_dev=mdev, cta_pair=2)
+        outb = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+        ops.gemm(a, w, None, outb, PK_EPI_BIAS_BF16, m_dev=mdev, cta_pair=2)
+        x = torch.ones(M, N, device=DEV)
+        ops.gemm(a, w, None, x, PK_EPI_BIAS_RESID_F32, resid=x, m_dev=mdev, cta_pair=2)
+        report(f"pair_mdev_{md}", err=rel_err(out[:md], ref[:md]) if md else 0.0, errb=rel_err(outb[:md], ref[:md]) if md else 0.0,
+               errr=rel_err(x[:md], ref[:md] + 1) if md else 0.0,
+               untouched=bool((out[md:] == 0).all() and (outb[md:] == 0).all() and (x[md:] == 1).all()), flag=ops.device_flag())
+    # timing on the ViT-B shapes (B=256 images)
+    Mbig = 197 * 256
+    for (N, K, epi, name) in [(2304, 768, PK_EPI_BIAS_BF16, "qkv"), (768, 768, PK_EPI_BIAS_RESID_F32, "proj"),
+                              (3072, 768, PK_EPI_BIAS_GELU_BF16, "fc1"), (768, 3072, PK_EPI_BIAS_RESID_F32, "fc2")]:
+        a = (torch.randn(Mbig, K, device=DEV) * 0.5).to(torch.bfloat16)
+        w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).to(torch.bfloat16)
+        bias = torch.randn(N, device=DEV) * 0.1
+        bf = epi in (PK_EPI_BIAS_BF16, PK_EPI_BIAS_GELU_BF16)
+        out = torch.empty(Mbig, N, device=DEV, dtype=torch.bfloat16 if bf else torch.float32)
+        resid = None if bf else out
+        for bn in (128, 256):
+            ms = time_ms(lambda: ops.gemm(a, w, bias, out, epi, resid=resid, block_n=bn, cta_pair=2))
+            report(f"pair_time_{name}_bn{bn}", ms=ms, tflops=2.0 * Mbig * N * K / ms / 1e9, flag=ops.device_flag())
+        ms = time_ms(lambda: ops.gemm(a, w, bias, out, epi, resid=resid, block_n=256, cta_pair=1))
+        report(f"single_time_{name}_bn256", ms=ms, tflops=2.0 * Mbig * N * K / ms / 1e9, flag=ops.device_flag())
+        ms = time_ms(lambda: torch.nn.functional.linear(a, w))
+        report(f"cublas_time_{name}", ms=ms, tflops=2.0 * Mbig * N * K / ms / 1e9)
+
+
 def probe_ln():
     torch.manual_seed(1)
     for D in (64, 128, 192, 256, 384, 768, 1024):
@@ -373,7 +448,7 @@ if __name__ == "__main__":
         out = sys.argv[sys.argv.index("--json") + 1]
     print("device:", torch.cuda.get_device_name(0), flush=True)
     try:
-        {"gemm": probe_gemm, "ln": probe_ln, "attn": probe_attn, "rows": probe_rows, "rank": probe_rank, "model": probe_model,
+        {"gemm": probe_gemm, "gemm2": probe_gemm2, "ln": probe_ln, "attn": probe_attn, "rows": probe_rows, "rank": probe_rank, "model": probe_model,
          "sparse": probe_sparse}[which]()
     finally:
         if out:
