@@ -18,6 +18,8 @@
 #include "pk_common.cuh"
 #include "../../include/peekvit_b200.h"
 
+#include <cstdlib>
+
 namespace pk {
 
 constexpr int kP_BM = 128;          // rows per CTA (256 per pair)
@@ -26,10 +28,12 @@ constexpr int kP_EpiWarps = 8;
 constexpr int kP_Threads = 128 + kP_EpiWarps * 32;
 constexpr int kP_BufBytes = 4096;   // one 32-row x 128-byte staging tile
 
-template <int BN, int EPI>
+// RED: the residual epilogue is in place (out == resid), so the add is done by a TMA reduction
+// (cp.reduce.async.bulk.tensor .add, executed at L2) and the residual tile never visits shared memory.
+template <int BN, int EPI, bool RED>
 struct PairCfg {
   static constexpr bool kOutBf16 = (EPI == PK_EPI_BIAS_BF16 || EPI == PK_EPI_BIAS_GELU_BF16);
-  static constexpr bool kResid = (EPI == PK_EPI_BIAS_RESID_F32);
+  static constexpr bool kResid = (EPI == PK_EPI_BIAS_RESID_F32) && !RED;
   static constexpr int kUnits = BN / 64;                                      // 32-column accumulator units per warp
   static constexpr int kUnitsPerStore = (kOutBf16 && kUnits % 2 == 0) ? 2 : 1; // bf16: 64 columns = one 128-byte row
   static constexpr int kChunks = kUnits / kUnitsPerStore;                     // TMA stores per warp per tile
@@ -58,6 +62,8 @@ struct PairParams {
   long long ldo;
   const float* rowscale;
   unsigned int* flag;
+  int l2_prefetch;
+  int debug;      // PK_GEMM_DEBUG bits (timing experiments only): 1 = no operand loads, 2 = no epilogue math/stores
 };
 
 // ---------------------------------------------------------------- cluster / cta_group::2 PTX
@@ -112,12 +118,12 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 }
 __device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool RED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP_Threads, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                       const PairParams p) {
-  using Cfg = PairCfg<BN, EPI>;
+  using Cfg = PairCfg<BN, EPI, RED>;
   constexpr bool kOutBf16 = Cfg::kOutBf16;
   constexpr bool kResid = Cfg::kResid;
   extern __shared__ uint8_t smem_raw[];
@@ -178,6 +184,27 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     uint32_t ph = 0;
     const int a_row_off = static_cast<int>(rank) * kP_BM;
     const int b_row_off = static_cast<int>(rank) * (BN / 2);
+    // L2 prefetch runs kPrefetch K blocks ahead of the smem ring (across tile boundaries): operands
+    // streamed from HBM arrive in L2 before their TMA load is issued, so the ring only has to cover
+    // L2 latency.
+    constexpr int kPrefetch = Cfg::kStages + 4;
+    int pf_t = pair, pf_kb = 0;
+    auto prefetch_next = [&]() {        // elected lane
+      if (pf_t < num_tiles) {
+        tma_prefetch_l2_2d(&tmap_a, pf_kb * kP_BK, (pf_t / n_tiles) * 2 * kP_BM + a_row_off);
+        tma_prefetch_l2_2d(&tmap_b, pf_kb * kP_BK, (pf_t % n_tiles) * BN + b_row_off);
+      }
+    };
+    auto prefetch_advance = [&]() {     // whole warp (keeps the iterator warp-uniform)
+      if (++pf_kb == num_kb) { pf_kb = 0; pf_t += num_pairs; }
+    };
+    if (p.l2_prefetch) {
+      for (int i = 0; i < kPrefetch; ++i) {
+        if (elect_one()) prefetch_next();
+        __syncwarp();
+        prefetch_advance();
+      }
+    }
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const int m_blk = t / n_tiles, n_blk = t % n_tiles;
       bool ok = true;
@@ -186,13 +213,19 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         if (!ok) break;
         if (elect_one()) {
           const uint32_t fb_local = smem_u32(&full_bar[s]);
+          if (p.debug & 1) {
+            if (rank == 0) mbar_arrive(fb_local);
+          } else {
           if (rank == 0) mbar_expect_tx(fb_local, 2 * Cfg::kStageBytes);   // both CTAs' bytes land on the leader's barrier
           const uint32_t fb = mapa_u32(fb_local, 0);
           const uint32_t a_dst = smem_u32(smem_ab + s * Cfg::kStageBytes);
           tma_load_2d_pair(a_dst, &tmap_a, fb, kb * kP_BK, m_blk * 2 * kP_BM + a_row_off);
           tma_load_2d_pair(a_dst + Cfg::kABytes, &tmap_b, fb, kb * kP_BK, n_blk * BN + b_row_off);
+          }
+          if (p.l2_prefetch) prefetch_next();
         }
         __syncwarp();
+        if (p.l2_prefetch) prefetch_advance();
         if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
       }
       if (!ok) break;
@@ -258,7 +291,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                   (tt / n_tiles) * 2 * kP_BM + row_in_pair);
     };
     if constexpr (kResid) {
-      if (lane == 0) {
+      if (lane == 0 && !(p.debug & 2)) {
         if (total_chunks > 0) issue_resid(0, pair, 0);
         if (total_chunks > 1) issue_resid(1, pair, 1);
       }
@@ -276,7 +309,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       const int grow = row_base + lane;
       const bool full_tile = row_base + 32 <= M;                                           // warp-uniform
       float sc = 1.0f;
-      if constexpr (kResid) {
+      if constexpr (kResid || RED) {
         if (p.rowscale && grow < M) sc = p.rowscale[grow];
       }
       if (!mbar_wait(smem_u32(&tfull_bar[as]), aph, p.flag, 0x1400u + as)) { ok = false; break; }
@@ -308,6 +341,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(as == 0 ? tempty_leader0 : tempty_leader1);
         }
+        if (p.debug & 2) continue;
         if (sub == 0) {
           if constexpr (kResid) {
             if (!mbar_wait(smem_u32(&rbar[b]), (g / 3u) & 1u, p.flag, 0x1500u + ew)) { ok = false; break; }
@@ -329,6 +363,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             // 128-byte rows, 16-byte chunk j of row r lives at chunk j ^ (r & 7) (SWIZZLE_128B)
             const float4 r4 = *reinterpret_cast<const float4*>(bufp + lane * 128 + ((j ^ (lane & 7)) << 4));
             a0 = fmaf(a0, sc, r4.x); a1 = fmaf(a1, sc, r4.y); a2 = fmaf(a2, sc, r4.z); a3 = fmaf(a3, sc, r4.w);
+          }
+          if constexpr (RED) {
+            a0 *= sc; a1 *= sc; a2 *= sc; a3 *= sc;
           }
           if constexpr (kOutBf16) {
             v[2 * j] = pack_bf16(a0, a1);
@@ -363,7 +400,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&tmap_out, ebuf_u32 + b * kP_BufBytes, col0 - sub * 32, row_base);
+              if constexpr (RED) tma_reduce_add_2d(&tmap_out, ebuf_u32 + b * kP_BufBytes, col0 - sub * 32, row_base);
+              else tma_store_2d(&tmap_out, ebuf_u32 + b * kP_BufBytes, col0 - sub * 32, row_base);
               bulk_commit();
             }
           }
@@ -382,7 +420,15 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             float* orow = static_cast<float*>(p.out) + static_cast<long long>(grow) * p.ldo + col0;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              if (col0 + 4 * j < p.N) *reinterpret_cast<uint4*>(orow + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (col0 + 4 * j < p.N) {
+                float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                       __uint_as_float(v[4 * j + 3]));
+                if constexpr (RED) {          // each element belongs to exactly one thread: plain read-modify-write
+                  const float4 r = *reinterpret_cast<const float4*>(orow + 4 * j);
+                  o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                }
+                *reinterpret_cast<float4*>(orow + 4 * j) = o;
+              }
           }
         }
         if (sub == kUPS - 1) {
@@ -411,11 +457,39 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   }
 }
 
-template <int BN, int EPI>
+// PK_GEMM_L2_PREFETCH=1 enables the producer's L2 prefetch (measured slower on B200: 1359 -> 1236 TFLOP/s on the
+// in-proj shape; kept for experiments).
+static int pair_l2_prefetch() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PK_GEMM_L2_PREFETCH");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+// PK_GEMM_TMA_REDUCE=0 keeps the staged-residual epilogue for in-place residual GEMMs (A/B experiments).
+static int pair_tma_reduce() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PK_GEMM_TMA_REDUCE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
+}
+static int pair_debug() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PK_GEMM_DEBUG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+template <int BN, int EPI, bool RED = false>
 static int launch_pair(const pk_gemm_args* a, cudaStream_t stream) {
-  using Cfg = PairCfg<BN, EPI>;
+  using Cfg = PairCfg<BN, EPI, RED>;
   static bool attr_set = false;
-  auto kfn = gemm_bf16_pair_kernel<BN, EPI>;
+  auto kfn = gemm_bf16_pair_kernel<BN, EPI, RED>;
   if (!attr_set) {
     PK_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
@@ -443,6 +517,8 @@ static int launch_pair(const pk_gemm_args* a, cudaStream_t stream) {
   p.out = a->out; p.ldo = a->ldo;
   p.rowscale = a->rowscale;
   p.flag = device_flag_ptr();
+  p.l2_prefetch = pair_l2_prefetch();
+  p.debug = pair_debug();
   const int m_tiles = (a->M + 2 * kP_BM - 1) / (2 * kP_BM), n_tiles = (a->N + BN - 1) / BN;
   int pairs = m_tiles * n_tiles;
   const int sms = a->max_ctas > 0 ? a->max_ctas : num_sms();
@@ -457,7 +533,10 @@ static int dispatch_pair_epi(const pk_gemm_args* a, cudaStream_t stream) {
   switch (a->epilogue) {
     case PK_EPI_BIAS_BF16: return launch_pair<BN, PK_EPI_BIAS_BF16>(a, stream);
     case PK_EPI_BIAS_GELU_BF16: return launch_pair<BN, PK_EPI_BIAS_GELU_BF16>(a, stream);
-    case PK_EPI_BIAS_RESID_F32: return launch_pair<BN, PK_EPI_BIAS_RESID_F32>(a, stream);
+    case PK_EPI_BIAS_RESID_F32:
+      // in-place residual (x += ...): let the TMA reduction do the add at L2
+      if (a->resid == a->out && a->ldr == a->ldo && pair_tma_reduce()) return launch_pair<BN, PK_EPI_BIAS_RESID_F32, true>(a, stream);
+      return launch_pair<BN, PK_EPI_BIAS_RESID_F32>(a, stream);
     case PK_EPI_BIAS_F32: return launch_pair<BN, PK_EPI_BIAS_F32>(a, stream);
   }
   set_last_error("pk_gemm_bf16: unknown epilogue %d", a->epilogue);
