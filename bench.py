@@ -180,7 +180,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: peekvit_b200 has no CPU path (use --impl reference for the CPU arm)")
     import torch.distributed as dist
-    from peekvit_b200 import ops
+    from peekvit_b200 import ops, runner
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
@@ -272,7 +272,7 @@ def main():
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "vit_b_16 224px forward (p16 D768 H12 F3072 L12 C1000), random-init weights re-randomised (seed 4321)",
-                       "images_per_gpu_per_step": B, "global_batch": world * B, "micro_batch": int(getattr(model, "pk_micro_batch", 128)),
+                       "images_per_gpu_per_step": B, "global_batch": world * B, "micro_batch": int(getattr(model, "pk_micro_batch", runner.DEFAULT_MICRO_BATCH)),
                        "parallelism": f"dp{world} (sample-sharded, replicated weights)",
                        "l2": "inputs 1.2 GB/step and activations per micro-batch exceed the 126 MB L2",
                        "accumulate": "fp32 (TMEM), fp32 residual stream / LayerNorm / softmax statistics"},

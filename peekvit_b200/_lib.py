@@ -42,6 +42,7 @@ class AttentionArgs(C.Structure):
         ("seq_len", c_int), ("cu_seqlens", c_void_p), ("max_seq_len", c_int),
         ("scale", c_float),
         ("key_mult", c_void_p), ("extra_kv", c_void_p), ("extra_mult", c_void_p),
+        ("impl", c_int),
     ]
 
 

@@ -260,6 +260,10 @@ attention_fwd_kernel(const AttParams p) {
   }
 }
 
+// pk_attention_tc.cu: tcgen05/TMEM kernel for uniform 128 < n <= 256, head_dim 64
+bool attention_tc_eligible(const pk_attention_args* a);
+int launch_attention_tc(const pk_attention_args* a, cudaStream_t stream);
+
 }  // namespace pk
 
 extern "C" int pk_attention_fwd(const pk_attention_args* a, void* stream) {
@@ -270,6 +274,8 @@ extern "C" int pk_attention_fwd(const pk_attention_args* a, void* stream) {
   PK_REQUIRE(a->cu_seqlens || a->seq_len > 0, "pk_attention_fwd: need cu_seqlens or seq_len");
   PK_REQUIRE((a->extra_kv == nullptr) == (a->extra_mult == nullptr), "pk_attention_fwd: extra_kv and extra_mult go together");
   if (a->batch == 0 || a->max_seq_len == 0) return PK_OK;
+  if (attention_tc_eligible(a)) return launch_attention_tc(a, static_cast<cudaStream_t>(stream));
+  PK_REQUIRE(a->impl != 2, "pk_attention_fwd: the tcgen05 kernel needs uniform 128 < seq_len <= 256, head_dim 64, no key multiplicities");
   AttParams p;
   p.qkv = static_cast<const __nv_bfloat16*>(a->qkv);
   p.out = static_cast<__nv_bfloat16*>(a->out);

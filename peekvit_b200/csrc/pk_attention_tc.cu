@@ -1,0 +1,370 @@
+// peekvit_b200 — tcgen05/TMEM attention for the dense ViT shape (sm_100a).
+//
+// Replaces nn.MultiheadAttention's core (reference models/blocks.py:93-95) for uniform-length
+// samples with 128 < n <= 256 tokens and head_dim 64 (ViT-B/16 and ViT-S/16 at 224 px: n = 197/198).
+// Other shapes (ragged batches, key multiplicities, n <= 128, n > 256, head_dim 32) take the
+// general mma.sync kernel in pk_attention.cu.
+//
+// One work item = one (sample, head).  Persistent CTAs, warp-specialised:
+//   warp 0      TMA producer: Q (two 128-row tiles), K and V (n_pad x 64, 128-byte swizzle) of the
+//               next item into a 2-slot shared-memory ring.  The tensor map is 3-D
+//               (column, token-in-sample, sample), so rows past the end of a sample are zero-filled
+//               instead of leaking the next sample's tokens.
+//   warp 1      MMA issuer.  Per 128-query tile r (a TMEM "region" of 256 columns):
+//                 S_r = Q_r K^T      tcgen05.mma  A,B from smem (K-major), 128 x n_pad fp32 in TMEM
+//                 O_r = P_r V        tcgen05.mma  A = P_r from TMEM (bf16, written by the softmax
+//                                    warps over the dead S columns), B = V from smem (MN-major)
+//   warps 4-7   softmax + output of tile 0;  warps 8-11 the same for tile 1.  A thread owns one query
+//               row (= one TMEM lane): row max and row sum need no shuffles.  Two passes over the
+//               S row in TMEM (max, then exp2/sum/pack), P stored back with tcgen05.st; after PV the
+//               thread reads its O row, scales by 1/sum and writes 128 contiguous bytes.
+// The two regions are software-pipelined against each other: while the softmax warps of one tile run,
+// the tensor core works on the other tile / the next item.  Every mbarrier wait is bounded.
+#include "pk_common.cuh"
+#include "../../include/peekvit_b200.h"
+
+namespace pk {
+
+constexpr int kTcThreads = 384;
+constexpr int kTcDH = 64;
+constexpr int kTcQTileBytes = 128 * 128;            // 128 query rows x 64 bf16
+constexpr int kTcMaxKeys = 256;
+constexpr int kTcKVBytes = kTcMaxKeys * 128;        // slot size for K (and V): up to 256 keys x 64 bf16
+constexpr int kTcSlotBytes = 2 * kTcQTileBytes + 2 * kTcKVBytes;   // 96 KB
+constexpr int kTcSlots = 2;
+constexpr int kTcBarBytes = 256;
+constexpr int kTcSmemBytes = kTcSlots * kTcSlotBytes + kTcBarBytes + 1024;
+constexpr int kTcRegionCols = 256;                  // TMEM columns per query tile
+constexpr int kTcOCol = 128;                        // O accumulator at region columns [128, 192)
+
+struct TcAttParams {
+  __nv_bfloat16* out;
+  int batch, num_heads, seq_len, n_pad;             // n_pad = seq_len rounded up to 16
+  float scale_log2;
+  unsigned int* flag;
+};
+
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem, bf16 pairs per column] * B[smem desc]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// MN-major, 128-byte-swizzled operand (V: rows = keys (K dim), 64 contiguous head-dim elements = MN):
+// 8-key groups 1024 B apart (SBO); a single 64-element MN atom, so LBO is unused.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__device__ __forceinline__ void tmem_ld_32x32_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32_x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// One 16-column group of the S row -> 8 packed bf16x2 probabilities; returns the partial row sum.
+__device__ __forceinline__ float softmax_group16(const uint32_t* s, uint32_t* p, float scale_log2, float neg_max_scaled, int col0, int n) {
+  float sum = 0.f;
+#pragma unroll
+  for (int e = 0; e < 16; e += 2) {
+    float p0 = ex2_approx(fmaf(__uint_as_float(s[e]), scale_log2, neg_max_scaled));
+    float p1 = ex2_approx(fmaf(__uint_as_float(s[e + 1]), scale_log2, neg_max_scaled));
+    if (col0 + e >= n) p0 = 0.f;
+    if (col0 + e + 1 >= n) p1 = 0.f;
+    sum += p0 + p1;
+    p[e >> 1] = pack_bf16(p0, p1);
+  }
+  return sum;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_constant__ CUtensorMap tmap_kv, const TcAttParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcSlots * kTcSlotBytes);
+  uint64_t* kv_full = bars;            // [2] slot loaded (tx bytes)
+  uint64_t* kv_empty = bars + 2;       // [2] slot consumed (umma commit)
+  uint64_t* s_full = bars + 4;         // [2] region: S ready (umma commit)
+  uint64_t* p_ready = bars + 6;        // [2] region: P written (4 warp arrivals)
+  uint64_t* o_full = bars + 8;         // [2] region: O ready (umma commit)
+  uint64_t* s_free = bars + 10;        // [2] region: O read out, region reusable (4 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = warp_id();
+  const int lane = lane_id();
+  const int n = p.seq_len, n_pad = p.n_pad;
+  const int D = p.num_heads * kTcDH;
+  const int num_items = p.batch * p.num_heads;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q128);
+    tma_prefetch_desc(&tmap_kv);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&kv_full[i]), 1);
+      mbar_init(smem_u32(&kv_empty[i]), 1);
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&p_ready[i]), 4);
+      mbar_init(smem_u32(&o_full[i]), 1);
+      mbar_init(smem_u32(&s_free[i]), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int slot = 0;
+    uint32_t ph = 0;
+    const uint32_t bytes = static_cast<uint32_t>(2 * kTcQTileBytes + 2 * n_pad * 128);
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&kv_empty[slot]), ph ^ 1u, p.flag, 0x2100u + slot))) break;
+      if (elect_one()) {
+        const int b = item / p.num_heads, h = item - b * p.num_heads;
+        const uint32_t bar = smem_u32(&kv_full[slot]);
+        const uint32_t base = smem_u32(smem + slot * kTcSlotBytes);
+        mbar_expect_tx(bar, bytes);
+        tma_load_3d(base, &tmap_q128, bar, h * kTcDH, 0, b);
+        tma_load_3d(base + kTcQTileBytes, &tmap_q128, bar, h * kTcDH, 128, b);
+        tma_load_3d(base + 2 * kTcQTileBytes, &tmap_kv, bar, D + h * kTcDH, 0, b);
+        tma_load_3d(base + 2 * kTcQTileBytes + kTcKVBytes, &tmap_kv, bar, 2 * D + h * kTcDH, 0, b);
+      }
+      __syncwarp();
+      if (++slot == kTcSlots) { slot = 0; ph ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc_qk = umma_idesc_bf16(128, n_pad);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, kTcDH, /*b_mn_major=*/1);
+    int slot = 0;
+    uint32_t ph = 0, rph = 0;            // rph: per-item phase of the region barriers
+    const int k_steps_pv = n_pad / 16;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&kv_full[slot]), ph, p.flag, 0x2200u + slot))) break;
+      tcgen05_fence_after();
+      const uint32_t base = smem_u32(smem + slot * kTcSlotBytes);
+      bool ok = true;
+      // S_r = Q_r K^T for both query tiles
+      for (int r = 0; r < 2 && ok; ++r) {
+        ok = __all_sync(0xffffffffu, mbar_wait(smem_u32(&s_free[r]), rph ^ 1u, p.flag, 0x2300u + r));
+        if (!ok) break;
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t a_desc = umma_desc_kmajor_sw128(base + r * kTcQTileBytes);
+          const uint64_t b_desc = umma_desc_kmajor_sw128(base + 2 * kTcQTileBytes);
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(r * kTcRegionCols);
+#pragma unroll
+          for (int k = 0; k < kTcDH / 16; ++k)
+            umma_bf16(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc_qk, k != 0 ? 1u : 0u);
+          umma_commit(smem_u32(&s_full[r]));
+        }
+        __syncwarp();
+      }
+      // O_r = P_r V
+      for (int r = 0; r < 2 && ok; ++r) {
+        ok = __all_sync(0xffffffffu, mbar_wait(smem_u32(&p_ready[r]), rph, p.flag, 0x2400u + r));
+        if (!ok) break;
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t v_desc = umma_desc_mnmajor_sw128(base + 2 * kTcQTileBytes + kTcKVBytes);
+          const uint32_t p_tmem = tmem_base + static_cast<uint32_t>(r * kTcRegionCols);
+          const uint32_t o_tmem = p_tmem + kTcOCol;
+          for (int k = 0; k < k_steps_pv; ++k)      // 16 keys per step: 8 TMEM columns of P, 2048 B of V
+            umma_bf16_ts(o_tmem, p_tmem + static_cast<uint32_t>(8 * k), v_desc + static_cast<uint64_t>(128 * k), idesc_pv, k != 0 ? 1u : 0u);
+          umma_commit(smem_u32(&o_full[r]));
+          if (r == 1) umma_commit(smem_u32(&kv_empty[slot]));   // every MMA of this item has retired
+        }
+        __syncwarp();
+      }
+      if (!ok) break;
+      rph ^= 1u;
+      if (++slot == kTcSlots) { slot = 0; ph ^= 1u; }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax + output warps
+    const int r = (warp - 4) >> 2;               // query tile / TMEM region
+    const int q = warp & 3;                      // TMEM lane quarter
+    const int row = r * 128 + q * 32 + lane;     // query row inside the sample
+    const bool row_ok = row < n;
+    const bool warp_has_rows = r * 128 + q * 32 < n;          // warp-uniform: idle warps only keep the barrier protocol alive
+    const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(r * kTcRegionCols);
+    const int n32 = n_pad / 32;                  // full 32-column chunks
+    const bool tail16 = (n_pad & 31) != 0;       // plus one 16-column chunk
+    const float scale_log2 = p.scale_log2;
+    uint32_t rph = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int b = item / p.num_heads, h = item - b * p.num_heads;
+      if (!mbar_wait(smem_u32(&s_full[r]), rph, p.flag, 0x2500u + r)) break;
+      tcgen05_fence_after();
+      if (!warp_has_rows) {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&p_ready[r]));
+        if (!mbar_wait(smem_u32(&o_full[r]), rph, p.flag, 0x2600u + r)) break;
+        tcgen05_fence_after();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s_free[r]));
+        rph ^= 1u;
+        continue;
+      }
+      // pass 1: row maximum
+      float mx = -INFINITY;
+      for (int j = 0; j < n32; ++j) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_base + static_cast<uint32_t>(32 * j), v);
+        tmem_ld_wait();
+        if (32 * j + 32 <= n) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) if (32 * j + e < n) mx = fmaxf(mx, __uint_as_float(v[e]));
+        }
+      }
+      if (tail16) {
+        uint32_t v[16];
+        tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(32 * n32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) if (32 * n32 + e < n) mx = fmaxf(mx, __uint_as_float(v[e]));
+      }
+      const float neg_max_scaled = -mx * scale_log2;
+      // pass 2: p = exp2(s*scale - max*scale), row sum, bf16 P written over the S columns
+      float sum = 0.f;
+      for (int j = 0; j < n32; ++j) {
+        uint32_t v[32], pk[16];
+        tmem_ld_32x32(t_base + static_cast<uint32_t>(32 * j), v);
+        tmem_ld_wait();
+        sum += softmax_group16(v, pk, scale_log2, neg_max_scaled, 32 * j, n);
+        sum += softmax_group16(v + 16, pk + 8, scale_log2, neg_max_scaled, 32 * j + 16, n);
+        tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * j), pk);
+        tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * j + 8), pk + 8);
+      }
+      if (tail16) {
+        uint32_t v[16], pk[8];
+        tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(32 * n32), v);
+        tmem_ld_wait();
+        sum += softmax_group16(v, pk, scale_log2, neg_max_scaled, 32 * n32, n);
+        tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * n32), pk);
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&p_ready[r]));
+      const float inv = 1.0f / sum;
+      // O row: 64 fp32 -> scaled bf16 -> 128 contiguous bytes of out[b*n + row, h*64 ...]
+      if (!mbar_wait(smem_u32(&o_full[r]), rph, p.flag, 0x2600u + r)) break;
+      tcgen05_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32(t_base + kTcOCol, o0);
+      tmem_ld_32x32(t_base + kTcOCol + 32, o1);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_free[r]));
+      if (row_ok) {
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * n + row) * D + h * kTcDH);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          dst[c] = make_uint4(pack_bf16(__uint_as_float(o0[8 * c]) * inv, __uint_as_float(o0[8 * c + 1]) * inv),
+                              pack_bf16(__uint_as_float(o0[8 * c + 2]) * inv, __uint_as_float(o0[8 * c + 3]) * inv),
+                              pack_bf16(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv),
+                              pack_bf16(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv));
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          dst[4 + c] = make_uint4(pack_bf16(__uint_as_float(o1[8 * c]) * inv, __uint_as_float(o1[8 * c + 1]) * inv),
+                                  pack_bf16(__uint_as_float(o1[8 * c + 2]) * inv, __uint_as_float(o1[8 * c + 3]) * inv),
+                                  pack_bf16(__uint_as_float(o1[8 * c + 4]) * inv, __uint_as_float(o1[8 * c + 5]) * inv),
+                                  pack_bf16(__uint_as_float(o1[8 * c + 6]) * inv, __uint_as_float(o1[8 * c + 7]) * inv));
+      }
+      rph ^= 1u;
+    }
+  }
+
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// 3-D view of the packed qkv buffer: (column, token in sample, sample)
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t ld_elems,
+                      uint32_t box_rows);
+
+bool attention_tc_eligible(const pk_attention_args* a) {
+  if (a->impl == 1) return false;
+  if (a->cu_seqlens || a->key_mult || a->extra_kv || a->extra_mult) return false;
+  if (a->head_dim != kTcDH) return false;
+  if (a->seq_len <= 128 || a->seq_len > kTcMaxKeys) return false;
+  if ((reinterpret_cast<uintptr_t>(a->qkv) & 15) != 0 || (reinterpret_cast<uintptr_t>(a->out) & 15) != 0) return false;
+  return true;
+}
+
+int launch_attention_tc(const pk_attention_args* a, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PK_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+    attr_set = true;
+  }
+  const int D = a->num_heads * kTcDH;
+  const int n = a->seq_len;
+  const int n_pad = (n + 15) / 16 * 16;
+  CUtensorMap tq, tkv;
+  int rc = make_tmap_bf16_3d(&tq, a->qkv, 3ull * D, static_cast<uint64_t>(n), static_cast<uint64_t>(a->batch), 3ull * D, 128);
+  if (rc != PK_OK) return rc;
+  rc = make_tmap_bf16_3d(&tkv, a->qkv, 3ull * D, static_cast<uint64_t>(n), static_cast<uint64_t>(a->batch), 3ull * D,
+                         static_cast<uint32_t>(n_pad));
+  if (rc != PK_OK) return rc;
+  TcAttParams p;
+  p.out = static_cast<__nv_bfloat16*>(a->out);
+  p.batch = a->batch;
+  p.num_heads = a->num_heads;
+  p.seq_len = n;
+  p.n_pad = n_pad;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.flag = device_flag_ptr();
+  const long long items = static_cast<long long>(a->batch) * a->num_heads;
+  int grid = num_sms();
+  if (items < grid) grid = static_cast<int>(items);
+  attention_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(tq, tkv, p);
+  return check_cuda(cudaGetLastError(), "attention_tc_kernel launch");
+}
+
+}  // namespace pk

@@ -116,6 +116,40 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t ro
   return PK_OK;
 }
 
+// 3-D bf16 view (column, row in sample, sample) of a packed [batch*rows, ld] buffer; box = 64 columns x
+// box_rows rows x 1 sample, 128-byte swizzle.  Rows past `rows` of a sample are out of bounds (zero-filled
+// on load, clipped on store) instead of aliasing the next sample.
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps3;
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t ld_elems,
+                      uint32_t box_rows) {
+  if (!g_ctx.encode) {
+    set_last_error("pk_init() has not been called");
+    return PK_ERR_INVALID;
+  }
+  TmapKey key{base, rows, cols, ld_elems, box_rows, static_cast<uint32_t>(batch), 2, 128};
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_tmaps3.find(key);
+  if (it != g_tmaps3.end()) {
+    *out = it->second;
+    return PK_OK;
+  }
+  cuuint64_t gdim[3] = {cols, rows, batch};
+  cuuint64_t gstride[2] = {ld_elems * 2ull, rows * ld_elems * 2ull};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estride[3] = {1, 1, 1};
+  CUresult r = g_ctx.encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estride,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(3d) failed (%d): base=%p cols=%llu rows=%llu batch=%llu ld=%llu box_rows=%u", static_cast<int>(r),
+                   base, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)batch, (unsigned long long)ld_elems, box_rows);
+    return PK_ERR_CUDA;
+  }
+  if (g_tmaps3.size() > 4096) g_tmaps3.clear();
+  g_tmaps3.emplace(key, *out);
+  return PK_OK;
+}
+
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                       uint32_t box_rows, uint32_t box_cols) {
   return make_tmap_2d(out, base, 2, rows, cols, ld_elems, box_rows, box_cols, 128);

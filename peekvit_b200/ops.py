@@ -148,7 +148,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 def attention(qkv: torch.Tensor, out: torch.Tensor, batch: int, num_heads: int, head_dim: int, *, seq_len: int = 0,
               cu_seqlens: Optional[torch.Tensor] = None, max_seq_len: int = 0, key_mult: Optional[torch.Tensor] = None,
-              extra_kv: Optional[torch.Tensor] = None, extra_mult: Optional[torch.Tensor] = None) -> torch.Tensor:
+              extra_kv: Optional[torch.Tensor] = None, extra_mult: Optional[torch.Tensor] = None, impl: int = 0) -> torch.Tensor:
     lib = _lib_for(qkv)
     D = num_heads * head_dim
     if qkv.shape[-1] != 3 * D or not qkv.is_contiguous() or not out.is_contiguous():
@@ -163,6 +163,7 @@ def attention(qkv: torch.Tensor, out: torch.Tensor, batch: int, num_heads: int, 
     a.key_mult = _ptr(key_mult, torch.float32)
     a.extra_kv = _ptr(extra_kv, torch.bfloat16)
     a.extra_mult = _ptr(extra_mult, torch.float32)
+    a.impl = impl
     check(lib.pk_attention_fwd(C.byref(a), _stream()), "pk_attention_fwd")
     return out
 

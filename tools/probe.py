@@ -203,6 +203,42 @@ def probe_gemm2():
         report(f"cublas_time_{name}", ms=ms, tflops=2.0 * Mbig * N * K / ms / 1e9)
 
 
+def probe_attn2():
+    """tcgen05/TMEM attention (uniform 128 < n <= 256, dh 64) against the fp32 expression and the general kernel."""
+    torch.manual_seed(2)
+    for (B, H, N) in [(1, 1, 197), (2, 12, 197), (3, 6, 198), (2, 3, 129), (2, 2, 256), (2, 2, 144), (5, 4, 145), (300, 12, 197)]:
+        dh = 64
+        D = H * dh
+        qkv = (torch.randn(B * N, 3 * D, device=DEV) * (1.5 if B < 100 else 1.0)).to(torch.bfloat16)
+        out = torch.full((B * N, D), float("nan"), device=DEV, dtype=torch.bfloat16)
+        ops.attention(qkv, out, B, H, dh, seq_len=N, impl=2)
+        flag = ops.device_flag()
+        out1 = torch.zeros(B * N, D, device=DEV, dtype=torch.bfloat16)
+        ops.attention(qkv, out1, B, H, dh, seq_len=N, impl=1)
+        if B < 100:
+            ref = ref_attention(qkv, B, H, dh, [N] * B)
+        else:
+            ref = out1.float()
+        bad = ~((out.float() - ref).abs() <= 2e-2 * ref.abs().max())
+        extra = {}
+        if bad.any():
+            rows = bad.any(1).nonzero().flatten()
+            cols = bad.any(0).nonzero().flatten()
+            extra = dict(bad_frac=bad.float().mean().item(), bad_rows=rows[:10].tolist(), n_bad_rows=int(rows.numel()),
+                         bad_cols=cols[:10].tolist(), n_bad_cols=int(cols.numel()), nan=int(torch.isnan(out.float()).sum()),
+                         got=out[rows[0], cols[0]].item(), ref=ref[rows[0], cols[0]].item())
+        report(f"attn_tc_B{B}_H{H}_N{N}", err=rel_err(out, ref), err_general=rel_err(out1, ref), flag=flag, **extra)
+        if flag:
+            return
+    B, H, N, dh = 256, 12, 197, 64
+    D = H * dh
+    qkv = torch.randn(B * N, 3 * D, device=DEV).to(torch.bfloat16)
+    out = torch.zeros(B * N, D, device=DEV, dtype=torch.bfloat16)
+    for impl in (1, 2):
+        ms = time_ms(lambda: ops.attention(qkv, out, B, H, dh, seq_len=N, impl=impl))
+        report(f"attn_time_impl{impl}_B{B}", ms=ms, tflops=4.0 * B * H * N * N * dh / ms / 1e9, flag=ops.device_flag())
+
+
 def probe_ln():
     torch.manual_seed(1)
     for D in (64, 128, 192, 256, 384, 768, 1024):
@@ -448,7 +484,7 @@ if __name__ == "__main__":
         out = sys.argv[sys.argv.index("--json") + 1]
     print("device:", torch.cuda.get_device_name(0), flush=True)
     try:
-        {"gemm": probe_gemm, "gemm2": probe_gemm2, "ln": probe_ln, "attn": probe_attn, "rows": probe_rows, "rank": probe_rank, "model": probe_model,
+        {"gemm": probe_gemm, "gemm2": probe_gemm2, "attn2": probe_attn2, "ln": probe_ln, "attn": probe_attn, "rows": probe_rows, "rank": probe_rank, "model": probe_model,
          "sparse": probe_sparse}[which]()
     finally:
         if out:
