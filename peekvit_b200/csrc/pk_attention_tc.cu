@@ -33,7 +33,8 @@ constexpr int kTcKVBytes = kTcMaxKeys * 128;        // slot size for K (and V): 
 constexpr int kTcSlotBytes = 2 * kTcQTileBytes + 2 * kTcKVBytes;   // 96 KB
 constexpr int kTcSlots = 2;
 constexpr int kTcBarBytes = 256;
-constexpr int kTcSmemBytes = kTcSlots * kTcSlotBytes + kTcBarBytes + 1024;
+constexpr int kTcOutStageBytes = 8 * 4096;           // one 32-row x 128-byte output tile per softmax warp
+constexpr int kTcSmemBytes = kTcSlots * kTcSlotBytes + kTcOutStageBytes + kTcBarBytes + 1024;
 constexpr int kTcRegionCols = 256;                  // TMEM columns per query tile
 constexpr int kTcOCol = 128;                        // O accumulator at region columns [128, 192)
 
@@ -87,26 +88,61 @@ __device__ __forceinline__ void tmem_st_32x32_x8(uint32_t taddr, const uint32_t*
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// Running maximum over 16 columns of the S row (3-input max: 8 instructions); columns >= n are skipped
+// when MASK (only the last 16-column group of a row can hold padding).
+template <bool MASK>
+__device__ __forceinline__ float row_max16(const uint32_t* s, float mx, int col0, int n) {
+  if constexpr (!MASK) {
+    // four independent 3-input max chains, then a 2-level combine (short dependency chains)
+    float m0 = fmax3(__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]));
+    float m1 = fmax3(__uint_as_float(s[3]), __uint_as_float(s[4]), __uint_as_float(s[5]));
+    float m2 = fmax3(__uint_as_float(s[6]), __uint_as_float(s[7]), __uint_as_float(s[8]));
+    float m3 = fmax3(__uint_as_float(s[9]), __uint_as_float(s[10]), __uint_as_float(s[11]));
+    m0 = fmax3(m0, __uint_as_float(s[12]), __uint_as_float(s[13]));
+    m1 = fmax3(m1, __uint_as_float(s[14]), __uint_as_float(s[15]));
+    mx = fmax3(mx, fmax3(m0, m1, m2), m3);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) if (col0 + e < n) mx = fmaxf(mx, __uint_as_float(s[e]));
+  }
+  return mx;
+}
 // One 16-column group of the S row -> 8 packed bf16x2 probabilities; returns the partial row sum.
+template <bool MASK>
 __device__ __forceinline__ float softmax_group16(const uint32_t* s, uint32_t* p, float scale_log2, float neg_max_scaled, int col0, int n) {
-  float sum = 0.f;
+  float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
   for (int e = 0; e < 16; e += 2) {
     float p0 = ex2_approx(fmaf(__uint_as_float(s[e]), scale_log2, neg_max_scaled));
     float p1 = ex2_approx(fmaf(__uint_as_float(s[e + 1]), scale_log2, neg_max_scaled));
-    if (col0 + e >= n) p0 = 0.f;
-    if (col0 + e + 1 >= n) p1 = 0.f;
-    sum += p0 + p1;
+    if constexpr (MASK) {
+      if (col0 + e >= n) p0 = 0.f;
+      if (col0 + e + 1 >= n) p1 = 0.f;
+    }
+    sum0 += p0;
+    sum1 += p1;
     p[e >> 1] = pack_bf16(p0, p1);
   }
-  return sum;
+  return sum0 + sum1;
 }
 
+template <int NPAD>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_constant__ CUtensorMap tmap_kv, const TcAttParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcSlots * kTcSlotBytes);
+  uint8_t* out_stage = smem + kTcSlots * kTcSlotBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kTcOutStageBytes);
   uint64_t* kv_full = bars;            // [2] slot loaded (tx bytes)
   uint64_t* kv_empty = bars + 2;       // [2] slot consumed (umma commit)
   uint64_t* s_full = bars + 4;         // [2] region: S ready (umma commit)
@@ -117,7 +153,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
 
   const int warp = warp_id();
   const int lane = lane_id();
-  const int n = p.seq_len, n_pad = p.n_pad;
+  const int n = p.seq_len;
+  constexpr int n_pad = NPAD;
   const int D = p.num_heads * kTcDH;
   const int num_items = p.batch * p.num_heads;
 
@@ -145,8 +182,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Register rebalancing (first statement of every role): producer / MMA / allocator warps need few
+  // registers, the softmax warps keep half an S row resident.
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
+    setmaxnreg_dec<56>();
     int slot = 0;
     uint32_t ph = 0;
     const uint32_t bytes = static_cast<uint32_t>(2 * kTcQTileBytes + 2 * n_pad * 128);
@@ -167,11 +207,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc_qk = umma_idesc_bf16(128, n_pad);
+    setmaxnreg_dec<56>();
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(128, NPAD);
     constexpr uint32_t idesc_pv = umma_idesc_bf16(128, kTcDH, /*b_mn_major=*/1);
     int slot = 0;
     uint32_t ph = 0, rph = 0;            // rph: per-item phase of the region barriers
-    const int k_steps_pv = n_pad / 16;
+    constexpr int k_steps_pv = NPAD / 16;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&kv_full[slot]), ph, p.flag, 0x2200u + slot))) break;
       tcgen05_fence_after();
@@ -202,6 +243,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
           const uint64_t v_desc = umma_desc_mnmajor_sw128(base + 2 * kTcQTileBytes + kTcKVBytes);
           const uint32_t p_tmem = tmem_base + static_cast<uint32_t>(r * kTcRegionCols);
           const uint32_t o_tmem = p_tmem + kTcOCol;
+#pragma unroll
           for (int k = 0; k < k_steps_pv; ++k)      // 16 keys per step: 8 TMEM columns of P, 2048 B of V
             umma_bf16_ts(o_tmem, p_tmem + static_cast<uint32_t>(8 * k), v_desc + static_cast<uint64_t>(128 * k), idesc_pv, k != 0 ? 1u : 0u);
           umma_commit(smem_u32(&o_full[r]));
@@ -213,16 +255,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
       rph ^= 1u;
       if (++slot == kTcSlots) { slot = 0; ph ^= 1u; }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    setmaxnreg_dec<56>();
+  } else {
     // ------------------------------------------------------------------ softmax + output warps
+    setmaxnreg_inc<208>();
     const int r = (warp - 4) >> 2;               // query tile / TMEM region
     const int q = warp & 3;                      // TMEM lane quarter
     const int row = r * 128 + q * 32 + lane;     // query row inside the sample
     const bool row_ok = row < n;
     const bool warp_has_rows = r * 128 + q * 32 < n;          // warp-uniform: idle warps only keep the barrier protocol alive
     const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(r * kTcRegionCols);
-    const int n32 = n_pad / 32;                  // full 32-column chunks
-    const bool tail16 = (n_pad & 31) != 0;       // plus one 16-column chunk
+    // The S row is NPAD columns = NC chunks of 32 (+ one 16-column tail).  The last KC chunks and the tail stay in
+    // registers between the two passes; the first NT chunks are read from TMEM twice, with the next chunk's load
+    // in flight while the current one is processed.
+    constexpr int NC = NPAD / 32;
+    constexpr bool TAIL = (NPAD % 32) != 0;
+    constexpr int KC = NC < 3 ? NC : 3;
+    constexpr int NT = NC - KC;
+    constexpr int KEEP = KC * 32 + (TAIL ? 16 : 0);
     const float scale_log2 = p.scale_log2;
     uint32_t rph = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -241,45 +292,71 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
         rph ^= 1u;
         continue;
       }
-      // pass 1: row maximum
+      uint32_t keep[KEEP];
+      uint32_t ta[32], tb[32];
+      // ---- pass 1: row maximum
       float mx = -INFINITY;
-      for (int j = 0; j < n32; ++j) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_base + static_cast<uint32_t>(32 * j), v);
-        tmem_ld_wait();
-        if (32 * j + 32 <= n) {
+      // kept chunks first (their loads overlap the transient chunks' processing)
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) if (32 * j + e < n) mx = fmaxf(mx, __uint_as_float(v[e]));
-        }
+      for (int c = 0; c < KC; ++c) {
+        uint32_t (&dst)[32] = *reinterpret_cast<uint32_t (*)[32]>(&keep[32 * c]);
+        tmem_ld_32x32(t_base + static_cast<uint32_t>(32 * (NT + c)), dst);
       }
-      if (tail16) {
-        uint32_t v[16];
-        tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(32 * n32), v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 16; ++e) if (32 * n32 + e < n) mx = fmaxf(mx, __uint_as_float(v[e]));
+      if constexpr (TAIL) {
+        uint32_t (&dst)[16] = *reinterpret_cast<uint32_t (*)[16]>(&keep[32 * KC]);
+        tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(32 * NC), dst);
       }
+      if constexpr (NT > 0) tmem_ld_32x32(t_base, ta);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        uint32_t (&cur)[32] = (j & 1) ? tb : ta;
+        uint32_t (&nxt)[32] = (j & 1) ? ta : tb;
+        if (j + 1 < NT) tmem_ld_32x32(t_base + static_cast<uint32_t>(32 * (j + 1)), nxt);
+        mx = row_max16<false>(cur, mx, 0, n);
+        mx = row_max16<false>(cur + 16, mx, 0, n);
+        if (j + 1 < NT) tmem_ld_wait();
+      }
+#pragma unroll
+      for (int c = 0; c < KC; ++c) {
+        mx = row_max16<false>(&keep[32 * c], mx, 0, n);
+        if (!TAIL && c == KC - 1) mx = row_max16<true>(&keep[32 * c + 16], mx, 32 * (NT + c) + 16, n);
+        else mx = row_max16<false>(&keep[32 * c + 16], mx, 0, n);
+      }
+      if constexpr (TAIL) mx = row_max16<true>(&keep[32 * KC], mx, 32 * NC, n);
       const float neg_max_scaled = -mx * scale_log2;
-      // pass 2: p = exp2(s*scale - max*scale), row sum, bf16 P written over the S columns
+      // ---- pass 2: p = exp2(s*scale - max*scale), row sum, bf16 P written over the S columns (in column order:
+      // P of chunk j lands on S columns that were consumed by chunk j/2)
       float sum = 0.f;
-      for (int j = 0; j < n32; ++j) {
-        uint32_t v[32], pk[16];
-        tmem_ld_32x32(t_base + static_cast<uint32_t>(32 * j), v);
+      if constexpr (NT > 0) {
+        tmem_ld_32x32(t_base, ta);
         tmem_ld_wait();
-        sum += softmax_group16(v, pk, scale_log2, neg_max_scaled, 32 * j, n);
-        sum += softmax_group16(v + 16, pk + 8, scale_log2, neg_max_scaled, 32 * j + 16, n);
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        uint32_t (&cur)[32] = (j & 1) ? tb : ta;
+        uint32_t (&nxt)[32] = (j & 1) ? ta : tb;
+        if (j + 1 < NT) tmem_ld_32x32(t_base + static_cast<uint32_t>(32 * (j + 1)), nxt);
+        uint32_t pk[16];
+        sum += softmax_group16<false>(cur, pk, scale_log2, neg_max_scaled, 0, n);
+        sum += softmax_group16<false>(cur + 16, pk + 8, scale_log2, neg_max_scaled, 0, n);
+        if (j + 1 < NT) tmem_ld_wait();          // the next chunk is in registers before its columns may be overwritten
         tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * j), pk);
         tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * j + 8), pk + 8);
       }
-      if (tail16) {
-        uint32_t v[16], pk[8];
-        tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(32 * n32), v);
-        tmem_ld_wait();
-        sum += softmax_group16(v, pk, scale_log2, neg_max_scaled, 32 * n32, n);
-        tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * n32), pk);
+#pragma unroll
+      for (int c = 0; c < KC; ++c) {
+        uint32_t pk[16];
+        sum += softmax_group16<false>(&keep[32 * c], pk, scale_log2, neg_max_scaled, 0, n);
+        if (!TAIL && c == KC - 1) sum += softmax_group16<true>(&keep[32 * c + 16], pk + 8, scale_log2, neg_max_scaled, 32 * (NT + c) + 16, n);
+        else sum += softmax_group16<false>(&keep[32 * c + 16], pk + 8, scale_log2, neg_max_scaled, 0, n);
+        tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * (NT + c)), pk);
+        tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * (NT + c) + 8), pk + 8);
+      }
+      if constexpr (TAIL) {
+        uint32_t pk[8];
+        sum += softmax_group16<true>(&keep[32 * KC], pk, scale_log2, neg_max_scaled, 32 * NC, n);
+        tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * NC), pk);
       }
       tmem_st_wait();
       tcgen05_fence_before();
@@ -296,20 +373,36 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s_free[r]));
-      if (row_ok) {
-        uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * n + row) * D + h * kTcDH);
+      // bf16 row -> this warp's swizzled staging tile -> coalesced 128-byte row stores (4 rows per instruction)
+      {
+        uint8_t* stg = out_stage + (warp - 4) * 4096;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          dst[c] = make_uint4(pack_bf16(__uint_as_float(o0[8 * c]) * inv, __uint_as_float(o0[8 * c + 1]) * inv),
-                              pack_bf16(__uint_as_float(o0[8 * c + 2]) * inv, __uint_as_float(o0[8 * c + 3]) * inv),
-                              pack_bf16(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv),
-                              pack_bf16(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv));
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+              make_uint4(pack_bf16(__uint_as_float(o0[8 * c]) * inv, __uint_as_float(o0[8 * c + 1]) * inv),
+                         pack_bf16(__uint_as_float(o0[8 * c + 2]) * inv, __uint_as_float(o0[8 * c + 3]) * inv),
+                         pack_bf16(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv),
+                         pack_bf16(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv));
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          dst[4 + c] = make_uint4(pack_bf16(__uint_as_float(o1[8 * c]) * inv, __uint_as_float(o1[8 * c + 1]) * inv),
-                                  pack_bf16(__uint_as_float(o1[8 * c + 2]) * inv, __uint_as_float(o1[8 * c + 3]) * inv),
-                                  pack_bf16(__uint_as_float(o1[8 * c + 4]) * inv, __uint_as_float(o1[8 * c + 5]) * inv),
-                                  pack_bf16(__uint_as_float(o1[8 * c + 6]) * inv, __uint_as_float(o1[8 * c + 7]) * inv));
+          *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + c) ^ (lane & 7)) << 4)) =
+              make_uint4(pack_bf16(__uint_as_float(o1[8 * c]) * inv, __uint_as_float(o1[8 * c + 1]) * inv),
+                         pack_bf16(__uint_as_float(o1[8 * c + 2]) * inv, __uint_as_float(o1[8 * c + 3]) * inv),
+                         pack_bf16(__uint_as_float(o1[8 * c + 4]) * inv, __uint_as_float(o1[8 * c + 5]) * inv),
+                         pack_bf16(__uint_as_float(o1[8 * c + 6]) * inv, __uint_as_float(o1[8 * c + 7]) * inv));
+        __syncwarp();
+        const int row0 = r * 128 + q * 32;
+        __nv_bfloat16* obase = p.out + (static_cast<long long>(b) * n + row0) * D + h * kTcDH;
+        const int cc = lane & 7, rr = lane >> 3;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int lr = 4 * i + rr;
+          if (row0 + lr < n) {
+            const uint4 val = *reinterpret_cast<const uint4*>(stg + lr * 128 + ((cc ^ (lr & 7)) << 4));
+            *reinterpret_cast<uint4*>(obase + static_cast<long long>(lr) * D + cc * 8) = val;
+          }
+        }
+        __syncwarp();
       }
       rph ^= 1u;
     }
@@ -338,11 +431,6 @@ bool attention_tc_eligible(const pk_attention_args* a) {
 }
 
 int launch_attention_tc(const pk_attention_args* a, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    PK_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
-    attr_set = true;
-  }
   const int D = a->num_heads * kTcDH;
   const int n = a->seq_len;
   const int n_pad = (n + 15) / 16 * 16;
@@ -363,7 +451,23 @@ int launch_attention_tc(const pk_attention_args* a, cudaStream_t stream) {
   const long long items = static_cast<long long>(a->batch) * a->num_heads;
   int grid = num_sms();
   if (items < grid) grid = static_cast<int>(items);
-  attention_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(tq, tkv, p);
+  switch (n_pad) {
+#define PK_TC_CASE(NP)                                                                                                  \
+  case NP: {                                                                                                            \
+    static bool attr_set = false;                                                                                       \
+    if (!attr_set) {                                                                                                    \
+      PK_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes)); \
+      attr_set = true;                                                                                                  \
+    }                                                                                                                   \
+    attention_tc_kernel<NP><<<grid, kTcThreads, kTcSmemBytes, stream>>>(tq, tkv, p);                                    \
+    break;                                                                                                              \
+  }
+    PK_TC_CASE(144) PK_TC_CASE(160) PK_TC_CASE(176) PK_TC_CASE(192) PK_TC_CASE(208) PK_TC_CASE(224) PK_TC_CASE(240) PK_TC_CASE(256)
+#undef PK_TC_CASE
+    default:
+      set_last_error("pk_attention_fwd: unsupported padded length %d", n_pad);
+      return PK_ERR_INVALID;
+  }
   return check_cuda(cudaGetLastError(), "attention_tc_kernel launch");
 }
 
