@@ -263,6 +263,7 @@ attention_fwd_kernel(const AttParams p) {
 // pk_attention_tc.cu: tcgen05/TMEM kernel for uniform 128 < n <= 256, head_dim 64
 bool attention_tc_eligible(const pk_attention_args* a);
 int launch_attention_tc(const pk_attention_args* a, cudaStream_t stream);
+int attention_trace_copy(unsigned long long* host_dst);
 
 }  // namespace pk
 
@@ -293,4 +294,12 @@ extern "C" int pk_attention_fwd(const pk_attention_args* a, void* stream) {
   if (a->head_dim == 64) attention_fwd_kernel<64><<<grid, kAttThreads, 0, s>>>(p);
   else attention_fwd_kernel<32><<<grid, kAttThreads, 0, s>>>(p);
   return check_cuda(cudaGetLastError(), "attention_fwd_kernel");
+}
+
+// Debug aid (not part of the product path): copies the PK_ATT_TRACE=1 event table (16 items x 12 warps x 8 events of
+// clock64 stamps from CTA 0 of the last tcgen05 attention launch) to host memory.
+extern "C" int pk_attention_trace(unsigned long long* host_dst) {
+  PK_REQUIRE(host_dst != nullptr, "pk_attention_trace: null destination");
+  PK_CHECK_CUDA(cudaDeviceSynchronize());
+  return pk::attention_trace_copy(host_dst);
 }

@@ -23,6 +23,8 @@
 #include "pk_common.cuh"
 #include "../../include/peekvit_b200.h"
 
+#include <cstdlib>
+
 namespace pk {
 
 constexpr int kTcThreads = 384;
@@ -36,13 +38,22 @@ constexpr int kTcBarBytes = 256;
 constexpr int kTcOutStageBytes = 8 * 4096;           // one 32-row x 128-byte output tile per softmax warp
 constexpr int kTcSmemBytes = kTcSlots * kTcSlotBytes + kTcOutStageBytes + kTcBarBytes + 1024;
 constexpr int kTcRegionCols = 256;                  // TMEM columns per query tile
-constexpr int kTcOCol = 128;                        // O accumulator at region columns [128, 192)
+constexpr int kTcOCol = 128;
+#ifndef PK_TC_POLY
+#define PK_TC_POLY 0
+#endif
+// Of every 4 column pairs, how many take the FMA-pipe exp2 instead of the MUFU.  Measured on B200 (B=256, H=12,
+// n=197): 0 -> 102 us, 1 -> 108 us, 2 -> 105-114 us: the packed-FMA polynomial costs as much pipe time as the MUFU op
+// it replaces, so the default is 0 (all MUFU).
+constexpr int kTcPoly = PK_TC_POLY;                        // O accumulator at region columns [128, 192)
 
 struct TcAttParams {
   __nv_bfloat16* out;
   int batch, num_heads, seq_len, n_pad;             // n_pad = seq_len rounded up to 16
   float scale_log2;
   unsigned int* flag;
+  unsigned long long* trace;   // PK_ATT_TRACE=1: CTA 0 records clock64 at pipeline events (tools/attn_trace.py)
+  int debug;      // PK_ATT_DEBUG bits (timing experiments only): 1 = no row-max pass, 2 = no exp pass, 4 = no output store
 };
 
 __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
@@ -86,6 +97,10 @@ __device__ __forceinline__ void tmem_st_32x32_x8(uint32_t taddr, const uint32_t*
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
       : "memory");
 }
+// trace slot layout: [item(0..15)][warp(0..11)][event(0..7)]
+__device__ __forceinline__ void tc_trace(const TcAttParams& p, int it, int ev) {
+  if (p.trace && blockIdx.x == 0 && it < 16 && (threadIdx.x & 31) == 0) p.trace[(it * 12 + (threadIdx.x >> 5)) * 8 + ev] = clock64();
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
@@ -117,23 +132,67 @@ __device__ __forceinline__ float row_max16(const uint32_t* s, float mx, int col0
   }
   return mx;
 }
+// exp2 of two non-positive arguments on the FMA pipe (the MUFU pipe is the softmax bottleneck: 4 lanes/clk/SMSP).
+// Cody-Waite split x = n + f, n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial (max rel. error
+// 7.5e-5, far below the bf16 rounding of P); 2^n by adding n to the exponent field.  Packed f32x2 arithmetic.
+__device__ __forceinline__ void exp2_poly_x2(uint64_t x, float& r0, float& r1) {
+  float x0, x1;
+  f2_unpack(x, x0, x1);
+  x0 = fmaxf(x0, -125.0f);                     // keep n inside the exponent range (result ~ 2^-125 = 0 for P)
+  x1 = fmaxf(x1, -125.0f);
+  const uint64_t xc = f2_pack(x0, x1);
+  const uint64_t t = f2_add(xc, f2_pack(12582912.0f, 12582912.0f));        // 1.5 * 2^23: n lands in the low mantissa bits
+  const uint64_t nn = f2_add(t, f2_pack(-12582912.0f, -12582912.0f));
+  const uint64_t f = f2_fma(nn, f2_pack(-1.0f, -1.0f), xc);
+  uint64_t q = f2_fma(f2_pack(0.055171288549900055f, 0.055171288549900055f), f, f2_pack(0.24261046946048737f, 0.24261046946048737f));
+  q = f2_fma(q, f, f2_pack(0.6932609677314758f, 0.6932609677314758f));
+  q = f2_fma(q, f, f2_pack(0.9999281167984009f, 0.9999281167984009f));
+  float q0, q1, t0, t1;
+  f2_unpack(q, q0, q1);
+  f2_unpack(t, t0, t1);
+  r0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  r1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+
 // One 16-column group of the S row -> 8 packed bf16x2 probabilities; returns the partial row sum.
-template <bool MASK>
+// POLY of every 4 column pairs take the FMA-pipe exp2, the rest the MUFU.
+template <bool MASK, int POLY>
 __device__ __forceinline__ float softmax_group16(const uint32_t* s, uint32_t* p, float scale_log2, float neg_max_scaled, int col0, int n) {
-  float sum0 = 0.f, sum1 = 0.f;
+  if constexpr (MASK) {
+    float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-  for (int e = 0; e < 16; e += 2) {
-    float p0 = ex2_approx(fmaf(__uint_as_float(s[e]), scale_log2, neg_max_scaled));
-    float p1 = ex2_approx(fmaf(__uint_as_float(s[e + 1]), scale_log2, neg_max_scaled));
-    if constexpr (MASK) {
+    for (int e = 0; e < 16; e += 2) {
+      float p0 = ex2_approx(fmaf(__uint_as_float(s[e]), scale_log2, neg_max_scaled));
+      float p1 = ex2_approx(fmaf(__uint_as_float(s[e + 1]), scale_log2, neg_max_scaled));
       if (col0 + e >= n) p0 = 0.f;
       if (col0 + e + 1 >= n) p1 = 0.f;
+      sum0 += p0;
+      sum1 += p1;
+      p[e >> 1] = pack_bf16(p0, p1);
     }
-    sum0 += p0;
-    sum1 += p1;
-    p[e >> 1] = pack_bf16(p0, p1);
+    return sum0 + sum1;
+  } else {
+    const uint64_t sc2 = f2_pack(scale_log2, scale_log2), nm2 = f2_pack(neg_max_scaled, neg_max_scaled);
+    uint64_t acc = f2_pack(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint64_t x = f2_fma(f2_pack(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sc2, nm2);
+      float p0, p1;
+      if ((i & 3) < POLY) {
+        exp2_poly_x2(x, p0, p1);
+      } else {
+        float x0, x1;
+        f2_unpack(x, x0, x1);
+        p0 = ex2_approx(x0);
+        p1 = ex2_approx(x1);
+      }
+      acc = f2_add(acc, f2_pack(p0, p1));
+      p[i] = pack_bf16(p0, p1);
+    }
+    float a0, a1;
+    f2_unpack(acc, a0, a1);
+    return a0 + a1;
   }
-  return sum0 + sum1;
 }
 
 template <int NPAD>
@@ -214,7 +273,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
     uint32_t ph = 0, rph = 0;            // rph: per-item phase of the region barriers
     constexpr int k_steps_pv = NPAD / 16;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int it = (item - blockIdx.x) / gridDim.x;
       if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&kv_full[slot]), ph, p.flag, 0x2200u + slot))) break;
+      tc_trace(p, it, 0);
       tcgen05_fence_after();
       const uint32_t base = smem_u32(smem + slot * kTcSlotBytes);
       bool ok = true;
@@ -233,11 +294,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
           umma_commit(smem_u32(&s_full[r]));
         }
         __syncwarp();
+        tc_trace(p, it, 1 + r);
       }
       // O_r = P_r V
       for (int r = 0; r < 2 && ok; ++r) {
         ok = __all_sync(0xffffffffu, mbar_wait(smem_u32(&p_ready[r]), rph, p.flag, 0x2400u + r));
         if (!ok) break;
+        tc_trace(p, it, 3 + r);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t v_desc = umma_desc_mnmajor_sw128(base + 2 * kTcQTileBytes + kTcKVBytes);
@@ -250,6 +313,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
           if (r == 1) umma_commit(smem_u32(&kv_empty[slot]));   // every MMA of this item has retired
         }
         __syncwarp();
+        tc_trace(p, it, 5 + r);
       }
       if (!ok) break;
       rph ^= 1u;
@@ -278,8 +342,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
     uint32_t rph = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int b = item / p.num_heads, h = item - b * p.num_heads;
+      const int it = (item - blockIdx.x) / gridDim.x;
+      tc_trace(p, it, 0);
       if (!mbar_wait(smem_u32(&s_full[r]), rph, p.flag, 0x2500u + r)) break;
       tcgen05_fence_after();
+      tc_trace(p, it, 1);
       if (!warp_has_rows) {
         tcgen05_fence_before();
         __syncwarp();
@@ -296,6 +363,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
       uint32_t ta[32], tb[32];
       // ---- pass 1: row maximum
       float mx = -INFINITY;
+      if (p.debug & 1) mx = 0.f;
+      else {
       // kept chunks first (their loads overlap the transient chunks' processing)
 #pragma unroll
       for (int c = 0; c < KC; ++c) {
@@ -324,10 +393,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
         else mx = row_max16<false>(&keep[32 * c + 16], mx, 0, n);
       }
       if constexpr (TAIL) mx = row_max16<true>(&keep[32 * KC], mx, 32 * NC, n);
+      }
       const float neg_max_scaled = -mx * scale_log2;
+      tc_trace(p, it, 2);
       // ---- pass 2: p = exp2(s*scale - max*scale), row sum, bf16 P written over the S columns (in column order:
       // P of chunk j lands on S columns that were consumed by chunk j/2)
       float sum = 0.f;
+      if (p.debug & 2) sum = 1.f;
+      else {
       if constexpr (NT > 0) {
         tmem_ld_32x32(t_base, ta);
         tmem_ld_wait();
@@ -338,8 +411,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
         uint32_t (&nxt)[32] = (j & 1) ? ta : tb;
         if (j + 1 < NT) tmem_ld_32x32(t_base + static_cast<uint32_t>(32 * (j + 1)), nxt);
         uint32_t pk[16];
-        sum += softmax_group16<false>(cur, pk, scale_log2, neg_max_scaled, 0, n);
-        sum += softmax_group16<false>(cur + 16, pk + 8, scale_log2, neg_max_scaled, 0, n);
+        sum += softmax_group16<false, kTcPoly>(cur, pk, scale_log2, neg_max_scaled, 0, n);
+        sum += softmax_group16<false, kTcPoly>(cur + 16, pk + 8, scale_log2, neg_max_scaled, 0, n);
         if (j + 1 < NT) tmem_ld_wait();          // the next chunk is in registers before its columns may be overwritten
         tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * j), pk);
         tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * j + 8), pk + 8);
@@ -347,25 +420,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
 #pragma unroll
       for (int c = 0; c < KC; ++c) {
         uint32_t pk[16];
-        sum += softmax_group16<false>(&keep[32 * c], pk, scale_log2, neg_max_scaled, 0, n);
-        if (!TAIL && c == KC - 1) sum += softmax_group16<true>(&keep[32 * c + 16], pk + 8, scale_log2, neg_max_scaled, 32 * (NT + c) + 16, n);
-        else sum += softmax_group16<false>(&keep[32 * c + 16], pk + 8, scale_log2, neg_max_scaled, 0, n);
+        sum += softmax_group16<false, kTcPoly>(&keep[32 * c], pk, scale_log2, neg_max_scaled, 0, n);
+        if (!TAIL && c == KC - 1) sum += softmax_group16<true, kTcPoly>(&keep[32 * c + 16], pk + 8, scale_log2, neg_max_scaled, 32 * (NT + c) + 16, n);
+        else sum += softmax_group16<false, kTcPoly>(&keep[32 * c + 16], pk + 8, scale_log2, neg_max_scaled, 0, n);
         tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * (NT + c)), pk);
         tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * (NT + c) + 8), pk + 8);
       }
       if constexpr (TAIL) {
         uint32_t pk[8];
-        sum += softmax_group16<true>(&keep[32 * KC], pk, scale_log2, neg_max_scaled, 32 * NC, n);
+        sum += softmax_group16<true, kTcPoly>(&keep[32 * KC], pk, scale_log2, neg_max_scaled, 32 * NC, n);
         tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * NC), pk);
+      }
       }
       tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&p_ready[r]));
+      tc_trace(p, it, 3);
       const float inv = 1.0f / sum;
       // O row: 64 fp32 -> scaled bf16 -> 128 contiguous bytes of out[b*n + row, h*64 ...]
       if (!mbar_wait(smem_u32(&o_full[r]), rph, p.flag, 0x2600u + r)) break;
       tcgen05_fence_after();
+      tc_trace(p, it, 4);
       uint32_t o0[32], o1[32];
       tmem_ld_32x32(t_base + kTcOCol, o0);
       tmem_ld_32x32(t_base + kTcOCol + 32, o1);
@@ -373,8 +449,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s_free[r]));
+      tc_trace(p, it, 5);
       // bf16 row -> this warp's swizzled staging tile -> coalesced 128-byte row stores (4 rows per instruction)
-      {
+      if (!(p.debug & 4)) {
         uint8_t* stg = out_stage + (warp - 4) * 4096;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
@@ -391,6 +468,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
                          pack_bf16(__uint_as_float(o1[8 * c + 4]) * inv, __uint_as_float(o1[8 * c + 5]) * inv),
                          pack_bf16(__uint_as_float(o1[8 * c + 6]) * inv, __uint_as_float(o1[8 * c + 7]) * inv));
         __syncwarp();
+        tc_trace(p, it, 7);
         const int row0 = r * 128 + q * 32;
         __nv_bfloat16* obase = p.out + (static_cast<long long>(b) * n + row0) * D + h * kTcDH;
         const int cc = lane & 7, rr = lane >> 3;
@@ -404,6 +482,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
         }
         __syncwarp();
       }
+      tc_trace(p, it, 6);
       rph ^= 1u;
     }
   }
@@ -420,6 +499,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
 // 3-D view of the packed qkv buffer: (column, token in sample, sample)
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t ld_elems,
                       uint32_t box_rows);
+
+// PK_ATT_TRACE=1: a 16 x 12 x 8 table of clock64 stamps written by CTA 0 (debug; read back with pk_attention_trace()).
+static unsigned long long* g_tc_trace = nullptr;
+static unsigned long long* tc_trace_buffer() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("PK_ATT_TRACE");
+    on = (e && e[0] == '1') ? 1 : 0;
+    if (on) {
+      if (cudaMalloc(&g_tc_trace, 16 * 12 * 8 * sizeof(unsigned long long)) != cudaSuccess) g_tc_trace = nullptr;
+      else cudaMemset(g_tc_trace, 0, 16 * 12 * 8 * sizeof(unsigned long long));
+    }
+  }
+  return g_tc_trace;
+}
+int attention_trace_copy(unsigned long long* host_dst) {
+  if (!g_tc_trace) return PK_ERR_INVALID;
+  return check_cuda(cudaMemcpy(host_dst, g_tc_trace, 16 * 12 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost), "trace copy");
+}
 
 bool attention_tc_eligible(const pk_attention_args* a) {
   if (a->impl == 1) return false;
@@ -448,6 +546,12 @@ int launch_attention_tc(const pk_attention_args* a, cudaStream_t stream) {
   p.n_pad = n_pad;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.flag = device_flag_ptr();
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("PK_ATT_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
+  p.trace = tc_trace_buffer();
   const long long items = static_cast<long long>(a->batch) * a->num_heads;
   int grid = num_sms();
   if (items < grid) grid = static_cast<int>(items);
