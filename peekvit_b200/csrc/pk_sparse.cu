@@ -99,24 +99,47 @@ residual_gate_plan_kernel(const ResidualGateParams p) {
   __syncthreads();
   const float thr = s_thr;
   float dropped = 0.f;
-  for (int j = warp; j < len; j += 8) {
-    const long long r = start + j;
-    const float mult = p.mult_in[r];
-    float m = 1.0f;
-    bool keep = true;
-    if (j >= p.n_special) {
-      if (p.gated) {
-        const float logit = row_dot(p.x + r * p.dim, p.gate_w, d4, lane) + p.gate_b;
-        if (p.gate_type == 0) m = fmaxf(sigmoidf_exact(logit * p.inv_temp + p.gate_bias) - thr, 0.f);
-        else m = rintf(sigmoidf_exact(logit));
+  // Four rows per warp iteration with all their loads issued before the first reduction: a one-row-at-a-time
+  // loop is a chain of exposed DRAM round trips (measured 18.5 us per layer on ViT-S, B=256).
+  const float4* __restrict__ w4 = reinterpret_cast<const float4*>(p.gate_w);
+  for (int j0 = warp; j0 < len; j0 += 32) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.gated) {
+      for (int c = lane; c < d4; c += 32) {
+        const float4 wv = __ldg(w4 + c);
+        float4 xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + 8 * u;
+          xv[u] = (j < len && j >= p.n_special) ? *reinterpret_cast<const float4*>(p.x + (start + j) * p.dim + c * 4)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] += (xv[u].x * wv.x + xv[u].y * wv.y) + (xv[u].z * wv.z + xv[u].w * wv.w);
       }
-      keep = (m > 0.f) && (mult > 0.f);
-      if (!keep) dropped += mult;
     }
-    if (lane == 0) {
-      p.mask[r] = m;
-      p.sample_of[r] = b;
-      s_keep[j] = keep ? 1 : 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 8 * u;
+      if (j >= len) break;                       // warp-uniform
+      const long long r = start + j;
+      const float mult = p.mult_in[r];
+      float m = 1.0f;
+      bool keep = true;
+      if (j >= p.n_special) {
+        if (p.gated) {
+          const float logit = warp_sum(acc[u]) + p.gate_b;
+          if (p.gate_type == 0) m = fmaxf(sigmoidf_exact(logit * p.inv_temp + p.gate_bias) - thr, 0.f);
+          else m = rintf(sigmoidf_exact(logit));
+        }
+        keep = (m > 0.f) && (mult > 0.f);
+        if (!keep) dropped += mult;
+      }
+      if (lane == 0) {
+        p.mask[r] = m;
+        p.sample_of[r] = b;
+        s_keep[j] = keep ? 1 : 0;
+      }
     }
   }
   if (lane == 0) s_drop[warp] = dropped;

@@ -66,56 +66,75 @@ USE_CUDA_GRAPHS = os.environ.get("PEEKVIT_B200_CUDA_GRAPHS", "1") != "0"
 _MAX_GRAPHS = 32
 
 
-def _vit_graphed(model, fwd: engine.Forward, chunk: torch.Tensor) -> Optional[torch.Tensor]:
-    """Replay the dense ViT launch sequence of one micro-batch from a CUDA graph.
+def _clone_tree(v):
+    if isinstance(v, torch.Tensor):
+        return v.clone()
+    if isinstance(v, dict):
+        return {k: _clone_tree(x) for k, x in v.items()}
+    if isinstance(v, (list, tuple)):
+        return type(v)(_clone_tree(x) for x in v)
+    return v
 
-    The sequence is static: every kernel reads its operands from workspace buffers with stable
-    addresses and from the prepacked weights, so a graph captured for (input pointer, shape, weight
-    pack) is valid until one of them changes.  Not used while bench.py brackets GEMM launches with
-    events (the events would be captured instead of recorded)."""
+
+def _graphed(model, fwd: engine.Forward, chunk: torch.Tensor, aux: Optional[dict], extra_key, fn) -> Optional[torch.Tensor]:
+    """Replay the launch sequence of one micro-batch from a CUDA graph.
+
+    Every family's sequence is static: kernels read their operands from workspace buffers with stable
+    addresses and from the prepacked weights, and ragged row counts live in device memory (grids are
+    sized for the upper bound), so a graph captured for (input pointer, shape, weight pack, budget) is
+    valid until one of them changes.  ``fn(chunk, aux_dict)`` runs the eager forward.  Side-state tensors
+    produced inside the graph are static too, so they are cloned out after every replay.  Not used while
+    bench.py brackets GEMM launches with events (the events would be captured instead of recorded)."""
     from . import ops
     if not USE_CUDA_GRAPHS or ops.gemm_timeline is not None or torch.cuda.is_current_stream_capturing():
         return None
     st = _state(model)
     graphs = st.setdefault("graphs", {})
-    key = (chunk.data_ptr(), tuple(chunk.shape), id(fwd.pm), torch.cuda.current_stream().cuda_stream)
+    key = (chunk.data_ptr(), tuple(chunk.shape), id(fwd.pm), aux is not None, extra_key)
     hit = graphs.get(key)
     if hit is None:
         if len(graphs) >= _MAX_GRAPHS:
             graphs.clear()
-        fwd.vit(chunk)                                   # warm-up outside capture: TMA descriptor cache, func attributes
+        fn(chunk, {} if aux is not None else None)       # warm-up outside capture: descriptor cache, func attributes, constants
         torch.cuda.current_stream().synchronize()
         n0 = ops.launch_count
         g = torch.cuda.CUDAGraph()
+        static_aux = {} if aux is not None else None
         with torch.cuda.graph(g):
-            out = fwd.vit(chunk)
-        hit = (g, out, ops.launch_count - n0, chunk)     # keep `chunk` alive: the graph reads its storage
+            out = fn(chunk, static_aux)
+        hit = (g, out, static_aux, ops.launch_count - n0, chunk)     # keep `chunk` alive: the graph reads its storage
         graphs[key] = hit
         ops.launch_count = n0
-    g, out, n_launch, _ = hit
+    g, out, static_aux, n_launch, _ = hit
     g.replay()
     ops.launch_count += n_launch
+    if aux is not None:
+        aux.update(_clone_tree(static_aux))
     return out
 
 
 def _forward_chunk(model, fwd: engine.Forward, chunk: torch.Tensor, aux: Optional[dict]) -> torch.Tensor:
     family = model._family
     if family == "vit":
-        if aux is None:
-            out = _vit_graphed(model, fwd, chunk)
-            if out is not None:
-                return out
-        return fwd.vit(chunk)
-    if family == "rankvit":
-        return fwd.rankvit(chunk, _rank_budgets(model), aux)
-    if family == "residualvit":
+        fn, key = (lambda c, a: fwd.vit(c)), None
+    elif family == "rankvit":
+        budgets = _rank_budgets(model)
+        fn, key = (lambda c, a: fwd.rankvit(c, budgets, a)), tuple(sorted(budgets.items()))
+    elif family == "residualvit":
         b = model.current_budget
-        return fwd.residualvit(chunk, None if b is None else float(b), aux)
-    if family == "adavit":
-        return fwd.adavit(chunk, aux, early_exit=bool(getattr(model, "pk_early_exit", True)))
-    if family == "moevit":
-        return fwd.moevit(chunk, aux)
-    raise NotImplementedError(f"{type(model).__name__}: unknown family {family!r}")
+        b = None if b is None else float(b)
+        fn, key = (lambda c, a: fwd.residualvit(c, b, a)), b
+    elif family == "adavit":
+        ee = bool(getattr(model, "pk_early_exit", True))
+        fn, key = (lambda c, a: fwd.adavit(c, a, early_exit=ee)), ee
+    elif family == "moevit":
+        fn, key = (lambda c, a: fwd.moevit(c, a)), None
+    else:
+        raise NotImplementedError(f"{type(model).__name__}: unknown family {family!r}")
+    out = _graphed(model, fwd, chunk, aux, key, fn)
+    if out is not None:
+        return out
+    return fn(chunk, aux)
 
 
 def _micro_batch(model, B: int) -> int:
