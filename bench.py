@@ -132,6 +132,11 @@ def run_reference(args, rank, world):
     """--impl reference: the reference algorithm on the host CPU (oracle port), rank 0 only."""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 for its workers; the CPU arm uses every host core this process may run on
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     from oracle import peekvit_oracle as po, weights as ow
     sd = ow.make_state_dict("vit", CFG_B, seed=4321)
     chunk = 32

@@ -119,7 +119,7 @@ typedef struct pk_attention_args {
 
 int pk_attention_fwd(const pk_attention_args* args, void* stream);
 /* Debug aid: with PK_ATT_TRACE=1 in the environment, CTA 0 of the tcgen05 attention kernel records clock64 stamps of its
- * pipeline events; this copies the 16 x 12 x 8 table (items x warps x events) to `host_dst` (1536 uint64). */
+ * pipeline events; this copies the 16 x 16 x 8 table (items x warps x events) to `host_dst` (2048 uint64). */
 int pk_attention_trace(unsigned long long* host_dst);
 
 /* ---- K2(final)+K8: final LayerNorm on class rows, class-token sum, head (vit.py:95,242-246) */

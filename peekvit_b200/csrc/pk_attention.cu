@@ -296,7 +296,7 @@ extern "C" int pk_attention_fwd(const pk_attention_args* a, void* stream) {
   return check_cuda(cudaGetLastError(), "attention_fwd_kernel");
 }
 
-// Debug aid (not part of the product path): copies the PK_ATT_TRACE=1 event table (16 items x 12 warps x 8 events of
+// Debug aid (not part of the product path): copies the PK_ATT_TRACE=1 event table (16 items x 16 warps x 8 events of
 // clock64 stamps from CTA 0 of the last tcgen05 attention launch) to host memory.
 extern "C" int pk_attention_trace(unsigned long long* host_dst) {
   PK_REQUIRE(host_dst != nullptr, "pk_attention_trace: null destination");

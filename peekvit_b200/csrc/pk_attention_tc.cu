@@ -27,16 +27,28 @@
 
 namespace pk {
 
-constexpr int kTcThreads = 384;
+constexpr int kTcThreads = 512;                      // 16 warps: TMA, 2 MMA issuers, 1 idle, 8 softmax, 4 output
+constexpr int kTcRegsSoftmax = 168;                 // 8 warps x 32 x 168 + 8 warps x 32 x 88 = 65536 registers
+constexpr int kTcRegsOther = 88;
 constexpr int kTcDH = 64;
 constexpr int kTcQTileBytes = 128 * 128;            // 128 query rows x 64 bf16
 constexpr int kTcMaxKeys = 256;
-constexpr int kTcKVBytes = kTcMaxKeys * 128;        // slot size for K (and V): up to 256 keys x 64 bf16
-constexpr int kTcSlotBytes = 2 * kTcQTileBytes + 2 * kTcKVBytes;   // 96 KB
-constexpr int kTcSlots = 2;
+// Shared-memory rings.  Q (both tiles) and K of an item are dead as soon as both S = Q K^T are done, V only after
+// both PV: the Q/K ring (2 slots) is released right after the QK MMAs, V has its own, deeper ring, so the ~2 us TMA
+// latency of the next items' operands is off the critical path of the two staggered regions.
+template <int NPAD>
+struct TcSmem {
+  static constexpr int kKBytes = NPAD * 128;                          // NPAD keys x 64 bf16 (multiple of 1024 since NPAD % 16 == 0 -> 2048)
+  static constexpr int kQKSlotBytes = 2 * kTcQTileBytes + kKBytes;
+  static constexpr int kQKSlots = 2;
+  static constexpr int kVSlots = NPAD <= 224 ? 3 : 2;
+  static constexpr int kVOff = kQKSlots * kQKSlotBytes;
+  static constexpr int kStageOff = kVOff + kVSlots * kKBytes;
+  static constexpr int kBytes = kStageOff + 4 * 4096 /* output staging */ + 1024 /* inv_sum */ + 256 /* barriers */ + 1024 /* alignment */;
+  static_assert(kBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
+};
 constexpr int kTcBarBytes = 256;
-constexpr int kTcOutStageBytes = 8 * 4096;           // one 32-row x 128-byte output tile per softmax warp
-constexpr int kTcSmemBytes = kTcSlots * kTcSlotBytes + kTcOutStageBytes + kTcBarBytes + 1024;
+constexpr int kTcOutStageBytes = 4 * 4096;           // one 32-row x 128-byte output tile per output warp
 constexpr int kTcRegionCols = 256;                  // TMEM columns per query tile
 constexpr int kTcOCol = 128;
 #ifndef PK_TC_POLY
@@ -56,6 +68,12 @@ struct TcAttParams {
   int debug;      // PK_ATT_DEBUG bits (timing experiments only): 1 = no row-max pass, 2 = no exp pass, 4 = no output store
 };
 
+// 3-D tiled store shared -> global (bulk async group); rows past the end of the sample are clipped by the tensor map.
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -97,9 +115,9 @@ __device__ __forceinline__ void tmem_st_32x32_x8(uint32_t taddr, const uint32_t*
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
       : "memory");
 }
-// trace slot layout: [item(0..15)][warp(0..11)][event(0..7)]
+// trace slot layout: [item(0..15)][warp(0..15)][event(0..7)]
 __device__ __forceinline__ void tc_trace(const TcAttParams& p, int it, int ev) {
-  if (p.trace && blockIdx.x == 0 && it < 16 && (threadIdx.x & 31) == 0) p.trace[(it * 12 + (threadIdx.x >> 5)) * 8 + ev] = clock64();
+  if (p.trace && blockIdx.x == 0 && it < 16 && (threadIdx.x & 31) == 0) p.trace[(it * 16 + (threadIdx.x >> 5)) * 8 + ev] = clock64();
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -197,18 +215,24 @@ __device__ __forceinline__ float softmax_group16(const uint32_t* s, uint32_t* p,
 
 template <int NPAD>
 __global__ void __launch_bounds__(kTcThreads, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_constant__ CUtensorMap tmap_kv, const TcAttParams p) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_constant__ CUtensorMap tmap_kv,
+                    const __grid_constant__ CUtensorMap tmap_out, const TcAttParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* out_stage = smem + kTcSlots * kTcSlotBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kTcOutStageBytes);
-  uint64_t* kv_full = bars;            // [2] slot loaded (tx bytes)
-  uint64_t* kv_empty = bars + 2;       // [2] slot consumed (umma commit)
-  uint64_t* s_full = bars + 4;         // [2] region: S ready (umma commit)
-  uint64_t* p_ready = bars + 6;        // [2] region: P written (4 warp arrivals)
-  uint64_t* o_full = bars + 8;         // [2] region: O ready (umma commit)
-  uint64_t* s_free = bars + 10;        // [2] region: O read out, region reusable (4 warp arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  using SM = TcSmem<NPAD>;
+  uint8_t* out_stage = smem + SM::kStageOff;
+  float* inv_sum = reinterpret_cast<float*>(out_stage + kTcOutStageBytes);          // [2 regions][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kTcOutStageBytes + 1024);
+  uint64_t* qk_full = bars;            // [2] Q/K slot loaded (tx bytes)
+  uint64_t* qk_empty = bars + 2;       // [2] Q/K slot consumed (one umma commit per MMA warp, after its QK)
+  uint64_t* v_full = bars + 4;         // [3] V slot loaded (tx bytes)
+  uint64_t* v_empty = bars + 7;        // [3] V slot consumed (one umma commit per MMA warp, after its PV)
+  uint64_t* s_full = bars + 10;        // [2] region: S ready (umma commit)
+  uint64_t* p_ready = bars + 12;       // [2] region: P written, row sums published (4 softmax-warp arrivals)
+  uint64_t* o_full = bars + 14;        // [2] region: O ready (umma commit)
+  uint64_t* s_free = bars + 16;        // [2] region: O read out, region reusable (4 output-warp arrivals)
+  uint64_t* sum_ready = bars + 18;     // [2] region: inv_sum[r] valid for the output warps (4 softmax-warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = warp_id();
   const int lane = lane_id();
@@ -220,15 +244,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q128);
     tma_prefetch_desc(&tmap_kv);
+    tma_prefetch_desc(&tmap_out);
   }
   if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(smem_u32(&v_full[i]), 1);
+      mbar_init(smem_u32(&v_empty[i]), 2);
+    }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&kv_full[i]), 1);
-      mbar_init(smem_u32(&kv_empty[i]), 1);
+      mbar_init(smem_u32(&qk_full[i]), 1);
+      mbar_init(smem_u32(&qk_empty[i]), 2);
       mbar_init(smem_u32(&s_full[i]), 1);
       mbar_init(smem_u32(&p_ready[i]), 4);
       mbar_init(smem_u32(&o_full[i]), 1);
       mbar_init(smem_u32(&s_free[i]), 4);
+      mbar_init(smem_u32(&sum_ready[i]), 4);
     }
     fence_mbar_init();
   }
@@ -241,250 +271,258 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // Register rebalancing (first statement of every role): producer / MMA / allocator warps need few
-  // registers, the softmax warps keep half an S row resident.
+  // Register rebalancing is the first statement of every role: the softmax warps keep half an S row resident.
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    setmaxnreg_dec<56>();
-    int slot = 0;
-    uint32_t ph = 0;
-    const uint32_t bytes = static_cast<uint32_t>(2 * kTcQTileBytes + 2 * n_pad * 128);
+    setmaxnreg_dec<kTcRegsOther>();
+    int qs = 0, vs = 0;
+    uint32_t qph = 0, vph = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&kv_empty[slot]), ph ^ 1u, p.flag, 0x2100u + slot))) break;
+      const int b = item / p.num_heads, h = item - b * p.num_heads;
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&qk_empty[qs]), qph ^ 1u, p.flag, 0x2100u + qs))) break;
+      tc_trace(p, (item - blockIdx.x) / gridDim.x, 0);
       if (elect_one()) {
-        const int b = item / p.num_heads, h = item - b * p.num_heads;
-        const uint32_t bar = smem_u32(&kv_full[slot]);
-        const uint32_t base = smem_u32(smem + slot * kTcSlotBytes);
-        mbar_expect_tx(bar, bytes);
+        const uint32_t bar = smem_u32(&qk_full[qs]);
+        const uint32_t base = smem_u32(smem + qs * SM::kQKSlotBytes);
+        mbar_expect_tx(bar, SM::kQKSlotBytes);
         tma_load_3d(base, &tmap_q128, bar, h * kTcDH, 0, b);
         tma_load_3d(base + kTcQTileBytes, &tmap_q128, bar, h * kTcDH, 128, b);
         tma_load_3d(base + 2 * kTcQTileBytes, &tmap_kv, bar, D + h * kTcDH, 0, b);
-        tma_load_3d(base + 2 * kTcQTileBytes + kTcKVBytes, &tmap_kv, bar, 2 * D + h * kTcDH, 0, b);
       }
       __syncwarp();
-      if (++slot == kTcSlots) { slot = 0; ph ^= 1u; }
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&v_empty[vs]), vph ^ 1u, p.flag, 0x2110u + vs))) break;
+      tc_trace(p, (item - blockIdx.x) / gridDim.x, 1);
+      if (elect_one()) {
+        const uint32_t bar = smem_u32(&v_full[vs]);
+        mbar_expect_tx(bar, SM::kKBytes);
+        tma_load_3d(smem_u32(smem + SM::kVOff + vs * SM::kKBytes), &tmap_kv, bar, 2 * D + h * kTcDH, 0, b);
+      }
+      __syncwarp();
+      if (++qs == SM::kQKSlots) { qs = 0; qph ^= 1u; }
+      if (++vs == SM::kVSlots) { vs = 0; vph ^= 1u; }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    setmaxnreg_dec<56>();
+  } else if (warp == 1 || warp == 2) {
+    // ------------------------------------------------------------------ MMA issuers: warp 1 -> query tile 0, warp 2 -> tile 1
+    // One issuer per region, so neither region ever waits behind the other's barrier.  Region 1 starts half a
+    // period late (after region 0's first softmax): the two softmax groups then use the MUFU alternately instead
+    // of in lockstep, and the tensor core works for one region while the other is in its softmax.
+    setmaxnreg_dec<kTcRegsOther>();
+    const int r = warp - 1;
     constexpr uint32_t idesc_qk = umma_idesc_bf16(128, NPAD);
     constexpr uint32_t idesc_pv = umma_idesc_bf16(128, kTcDH, /*b_mn_major=*/1);
-    int slot = 0;
-    uint32_t ph = 0, rph = 0;            // rph: per-item phase of the region barriers
     constexpr int k_steps_pv = NPAD / 16;
+    const uint32_t s_tmem = tmem_base + static_cast<uint32_t>(r * kTcRegionCols);
+    int qs = 0, vs = 0;
+    uint32_t qph = 0, vph = 0, rph = 0;
+    bool first = true;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int it = (item - blockIdx.x) / gridDim.x;
-      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&kv_full[slot]), ph, p.flag, 0x2200u + slot))) break;
-      tc_trace(p, it, 0);
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&qk_full[qs]), qph, p.flag, 0x2200u + qs))) break;
+      tc_trace(p, it, 4);
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&s_free[r]), rph ^ 1u, p.flag, 0x2300u + r))) break;
+      if (first && r == 1) {
+        if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&p_ready[0]), 0u, p.flag, 0x2310u))) break;
+      }
+      first = false;
       tcgen05_fence_after();
-      const uint32_t base = smem_u32(smem + slot * kTcSlotBytes);
-      bool ok = true;
-      // S_r = Q_r K^T for both query tiles
-      for (int r = 0; r < 2 && ok; ++r) {
-        ok = __all_sync(0xffffffffu, mbar_wait(smem_u32(&s_free[r]), rph ^ 1u, p.flag, 0x2300u + r));
-        if (!ok) break;
-        tcgen05_fence_after();
-        if (elect_one()) {
-          const uint64_t a_desc = umma_desc_kmajor_sw128(base + r * kTcQTileBytes);
-          const uint64_t b_desc = umma_desc_kmajor_sw128(base + 2 * kTcQTileBytes);
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(r * kTcRegionCols);
+      const uint32_t base = smem_u32(smem + qs * SM::kQKSlotBytes);
+      tc_trace(p, it, 0);
+      if (elect_one()) {                       // S_r = Q_r K^T
+        const uint64_t a_desc = umma_desc_kmajor_sw128(base + r * kTcQTileBytes);
+        const uint64_t b_desc = umma_desc_kmajor_sw128(base + 2 * kTcQTileBytes);
 #pragma unroll
-          for (int k = 0; k < kTcDH / 16; ++k)
-            umma_bf16(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc_qk, k != 0 ? 1u : 0u);
-          umma_commit(smem_u32(&s_full[r]));
-        }
-        __syncwarp();
-        tc_trace(p, it, 1 + r);
+        for (int k = 0; k < kTcDH / 16; ++k)
+          umma_bf16(s_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(smem_u32(&s_full[r]));
+        umma_commit(smem_u32(&qk_empty[qs]));     // Q/K of this item are dead once both regions' QK have retired
       }
-      // O_r = P_r V
-      for (int r = 0; r < 2 && ok; ++r) {
-        ok = __all_sync(0xffffffffu, mbar_wait(smem_u32(&p_ready[r]), rph, p.flag, 0x2400u + r));
-        if (!ok) break;
-        tc_trace(p, it, 3 + r);
-        tcgen05_fence_after();
-        if (elect_one()) {
-          const uint64_t v_desc = umma_desc_mnmajor_sw128(base + 2 * kTcQTileBytes + kTcKVBytes);
-          const uint32_t p_tmem = tmem_base + static_cast<uint32_t>(r * kTcRegionCols);
-          const uint32_t o_tmem = p_tmem + kTcOCol;
+      __syncwarp();
+      tc_trace(p, it, 1);
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&p_ready[r]), rph, p.flag, 0x2400u + r))) break;
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&v_full[vs]), vph, p.flag, 0x2410u + vs))) break;
+      tcgen05_fence_after();
+      tc_trace(p, it, 2);
+      if (elect_one()) {                       // O_r = P_r V
+        const uint64_t v_desc = umma_desc_mnmajor_sw128(smem_u32(smem + SM::kVOff + vs * SM::kKBytes));
+        const uint32_t o_tmem = s_tmem + kTcOCol;
 #pragma unroll
-          for (int k = 0; k < k_steps_pv; ++k)      // 16 keys per step: 8 TMEM columns of P, 2048 B of V
-            umma_bf16_ts(o_tmem, p_tmem + static_cast<uint32_t>(8 * k), v_desc + static_cast<uint64_t>(128 * k), idesc_pv, k != 0 ? 1u : 0u);
-          umma_commit(smem_u32(&o_full[r]));
-          if (r == 1) umma_commit(smem_u32(&kv_empty[slot]));   // every MMA of this item has retired
-        }
-        __syncwarp();
-        tc_trace(p, it, 5 + r);
+        for (int k = 0; k < k_steps_pv; ++k)      // 16 keys per step: 8 TMEM columns of P, 2048 B of V
+          umma_bf16_ts(o_tmem, s_tmem + static_cast<uint32_t>(8 * k), v_desc + static_cast<uint64_t>(128 * k), idesc_pv, k != 0 ? 1u : 0u);
+        umma_commit(smem_u32(&o_full[r]));
+        umma_commit(smem_u32(&v_empty[vs]));      // 2 arrivals (one per region) free the V slot
       }
-      if (!ok) break;
+      __syncwarp();
+      tc_trace(p, it, 3);
       rph ^= 1u;
-      if (++slot == kTcSlots) { slot = 0; ph ^= 1u; }
+      if (++qs == SM::kQKSlots) { qs = 0; qph ^= 1u; }
+      if (++vs == SM::kVSlots) { vs = 0; vph ^= 1u; }
     }
-  } else if (warp < 4) {
-    setmaxnreg_dec<56>();
-  } else {
-    // ------------------------------------------------------------------ softmax + output warps
-    setmaxnreg_inc<208>();
+  } else if (warp == 3) {
+    setmaxnreg_dec<kTcRegsOther>();
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ softmax warps (4 per query tile)
+    setmaxnreg_inc<kTcRegsSoftmax>();
     const int r = (warp - 4) >> 2;               // query tile / TMEM region
     const int q = warp & 3;                      // TMEM lane quarter
-    const int row = r * 128 + q * 32 + lane;     // query row inside the sample
-    const bool row_ok = row < n;
     const bool warp_has_rows = r * 128 + q * 32 < n;          // warp-uniform: idle warps only keep the barrier protocol alive
     const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(r * kTcRegionCols);
     // The S row is NPAD columns = NC chunks of 32 (+ one 16-column tail).  The last KC chunks and the tail stay in
-    // registers between the two passes; the first NT chunks are read from TMEM twice, with the next chunk's load
-    // in flight while the current one is processed.
+    // registers between the two passes; the first NT chunks are read from TMEM twice.
     constexpr int NC = NPAD / 32;
     constexpr bool TAIL = (NPAD % 32) != 0;
-    constexpr int KC = NC < 3 ? NC : 3;
+    constexpr int KC = NC < 2 ? NC : 2;
     constexpr int NT = NC - KC;
     constexpr int KEEP = KC * 32 + (TAIL ? 16 : 0);
     const float scale_log2 = p.scale_log2;
     uint32_t rph = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int b = item / p.num_heads, h = item - b * p.num_heads;
       const int it = (item - blockIdx.x) / gridDim.x;
       tc_trace(p, it, 0);
       if (!mbar_wait(smem_u32(&s_full[r]), rph, p.flag, 0x2500u + r)) break;
       tcgen05_fence_after();
       tc_trace(p, it, 1);
-      if (!warp_has_rows) {
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&p_ready[r]));
-        if (!mbar_wait(smem_u32(&o_full[r]), rph, p.flag, 0x2600u + r)) break;
-        tcgen05_fence_after();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s_free[r]));
-        rph ^= 1u;
-        continue;
-      }
-      uint32_t keep[KEEP];
-      uint32_t ta[32], tb[32];
-      // ---- pass 1: row maximum
-      float mx = -INFINITY;
-      if (p.debug & 1) mx = 0.f;
-      else {
-      // kept chunks first (their loads overlap the transient chunks' processing)
+      if (warp_has_rows) {
+        uint32_t keep[KEEP];
+        uint32_t ta[32];
+        // ---- pass 1: row maximum (the kept chunks' loads overlap the transient chunks' processing)
+        float mx = -INFINITY;
+        if (p.debug & 1) mx = 0.f;
 #pragma unroll
-      for (int c = 0; c < KC; ++c) {
-        uint32_t (&dst)[32] = *reinterpret_cast<uint32_t (*)[32]>(&keep[32 * c]);
-        tmem_ld_32x32(t_base + static_cast<uint32_t>(32 * (NT + c)), dst);
-      }
-      if constexpr (TAIL) {
-        uint32_t (&dst)[16] = *reinterpret_cast<uint32_t (*)[16]>(&keep[32 * KC]);
-        tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(32 * NC), dst);
-      }
-      if constexpr (NT > 0) tmem_ld_32x32(t_base, ta);
-      tmem_ld_wait();
+        for (int c = 0; c < KC; ++c) {
+          uint32_t (&dst)[32] = *reinterpret_cast<uint32_t (*)[32]>(&keep[32 * c]);
+          tmem_ld_32x32(t_base + static_cast<uint32_t>(32 * (NT + c)), dst);
+        }
+        if constexpr (TAIL) {
+          uint32_t (&dst)[16] = *reinterpret_cast<uint32_t (*)[16]>(&keep[32 * KC]);
+          tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(32 * NC), dst);
+        }
+        if (!(p.debug & 1)) {
+#pragma unroll 1
+          for (int j = 0; j < NT; ++j) {
+            tmem_ld_32x32(t_base + static_cast<uint32_t>(32 * j), ta);
+            tmem_ld_wait();
+            mx = row_max16<false>(ta, mx, 0, n);
+            mx = row_max16<false>(ta + 16, mx, 0, n);
+          }
+          if constexpr (NT == 0) tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        uint32_t (&cur)[32] = (j & 1) ? tb : ta;
-        uint32_t (&nxt)[32] = (j & 1) ? ta : tb;
-        if (j + 1 < NT) tmem_ld_32x32(t_base + static_cast<uint32_t>(32 * (j + 1)), nxt);
-        mx = row_max16<false>(cur, mx, 0, n);
-        mx = row_max16<false>(cur + 16, mx, 0, n);
-        if (j + 1 < NT) tmem_ld_wait();
-      }
+          for (int c = 0; c < KC; ++c) {
+            mx = row_max16<false>(&keep[32 * c], mx, 0, n);
+            if (!TAIL && c == KC - 1) mx = row_max16<true>(&keep[32 * c + 16], mx, 32 * (NT + c) + 16, n);
+            else mx = row_max16<false>(&keep[32 * c + 16], mx, 0, n);
+          }
+          if constexpr (TAIL) mx = row_max16<true>(&keep[32 * KC], mx, 32 * NC, n);
+        } else {
+          tmem_ld_wait();
+        }
+        const float neg_max_scaled = -mx * scale_log2;
+        tc_trace(p, it, 2);
+        // ---- pass 2: p = exp2(s*scale - max*scale), row sum, bf16 P written over the S columns (in column order:
+        // P of chunk j lands on S columns that were consumed by chunk j/2)
+        float sum = 0.f;
+        if (p.debug & 2) sum = 1.f;
+        else {
+#pragma unroll 1
+          for (int j = 0; j < NT; ++j) {
+            tmem_ld_32x32(t_base + static_cast<uint32_t>(32 * j), ta);
+            tmem_ld_wait();
+            uint32_t pk[16];
+            sum += softmax_group16<false, kTcPoly>(ta, pk, scale_log2, neg_max_scaled, 0, n);
+            sum += softmax_group16<false, kTcPoly>(ta + 16, pk + 8, scale_log2, neg_max_scaled, 0, n);
+            tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * j), pk);
+            tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * j + 8), pk + 8);
+          }
 #pragma unroll
-      for (int c = 0; c < KC; ++c) {
-        mx = row_max16<false>(&keep[32 * c], mx, 0, n);
-        if (!TAIL && c == KC - 1) mx = row_max16<true>(&keep[32 * c + 16], mx, 32 * (NT + c) + 16, n);
-        else mx = row_max16<false>(&keep[32 * c + 16], mx, 0, n);
-      }
-      if constexpr (TAIL) mx = row_max16<true>(&keep[32 * KC], mx, 32 * NC, n);
-      }
-      const float neg_max_scaled = -mx * scale_log2;
-      tc_trace(p, it, 2);
-      // ---- pass 2: p = exp2(s*scale - max*scale), row sum, bf16 P written over the S columns (in column order:
-      // P of chunk j lands on S columns that were consumed by chunk j/2)
-      float sum = 0.f;
-      if (p.debug & 2) sum = 1.f;
-      else {
-      if constexpr (NT > 0) {
-        tmem_ld_32x32(t_base, ta);
-        tmem_ld_wait();
-      }
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        uint32_t (&cur)[32] = (j & 1) ? tb : ta;
-        uint32_t (&nxt)[32] = (j & 1) ? ta : tb;
-        if (j + 1 < NT) tmem_ld_32x32(t_base + static_cast<uint32_t>(32 * (j + 1)), nxt);
-        uint32_t pk[16];
-        sum += softmax_group16<false, kTcPoly>(cur, pk, scale_log2, neg_max_scaled, 0, n);
-        sum += softmax_group16<false, kTcPoly>(cur + 16, pk + 8, scale_log2, neg_max_scaled, 0, n);
-        if (j + 1 < NT) tmem_ld_wait();          // the next chunk is in registers before its columns may be overwritten
-        tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * j), pk);
-        tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * j + 8), pk + 8);
-      }
-#pragma unroll
-      for (int c = 0; c < KC; ++c) {
-        uint32_t pk[16];
-        sum += softmax_group16<false, kTcPoly>(&keep[32 * c], pk, scale_log2, neg_max_scaled, 0, n);
-        if (!TAIL && c == KC - 1) sum += softmax_group16<true, kTcPoly>(&keep[32 * c + 16], pk + 8, scale_log2, neg_max_scaled, 32 * (NT + c) + 16, n);
-        else sum += softmax_group16<false, kTcPoly>(&keep[32 * c + 16], pk + 8, scale_log2, neg_max_scaled, 0, n);
-        tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * (NT + c)), pk);
-        tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * (NT + c) + 8), pk + 8);
-      }
-      if constexpr (TAIL) {
-        uint32_t pk[8];
-        sum += softmax_group16<true, kTcPoly>(&keep[32 * KC], pk, scale_log2, neg_max_scaled, 32 * NC, n);
-        tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * NC), pk);
-      }
-      }
-      tmem_st_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&p_ready[r]));
-      tc_trace(p, it, 3);
-      const float inv = 1.0f / sum;
-      // O row: 64 fp32 -> scaled bf16 -> 128 contiguous bytes of out[b*n + row, h*64 ...]
-      if (!mbar_wait(smem_u32(&o_full[r]), rph, p.flag, 0x2600u + r)) break;
-      tcgen05_fence_after();
-      tc_trace(p, it, 4);
-      uint32_t o0[32], o1[32];
-      tmem_ld_32x32(t_base + kTcOCol, o0);
-      tmem_ld_32x32(t_base + kTcOCol + 32, o1);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&s_free[r]));
-      tc_trace(p, it, 5);
-      // bf16 row -> this warp's swizzled staging tile -> coalesced 128-byte row stores (4 rows per instruction)
-      if (!(p.debug & 4)) {
-        uint8_t* stg = out_stage + (warp - 4) * 4096;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
-              make_uint4(pack_bf16(__uint_as_float(o0[8 * c]) * inv, __uint_as_float(o0[8 * c + 1]) * inv),
-                         pack_bf16(__uint_as_float(o0[8 * c + 2]) * inv, __uint_as_float(o0[8 * c + 3]) * inv),
-                         pack_bf16(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv),
-                         pack_bf16(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv));
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + c) ^ (lane & 7)) << 4)) =
-              make_uint4(pack_bf16(__uint_as_float(o1[8 * c]) * inv, __uint_as_float(o1[8 * c + 1]) * inv),
-                         pack_bf16(__uint_as_float(o1[8 * c + 2]) * inv, __uint_as_float(o1[8 * c + 3]) * inv),
-                         pack_bf16(__uint_as_float(o1[8 * c + 4]) * inv, __uint_as_float(o1[8 * c + 5]) * inv),
-                         pack_bf16(__uint_as_float(o1[8 * c + 6]) * inv, __uint_as_float(o1[8 * c + 7]) * inv));
-        __syncwarp();
-        tc_trace(p, it, 7);
-        const int row0 = r * 128 + q * 32;
-        __nv_bfloat16* obase = p.out + (static_cast<long long>(b) * n + row0) * D + h * kTcDH;
-        const int cc = lane & 7, rr = lane >> 3;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int lr = 4 * i + rr;
-          if (row0 + lr < n) {
-            const uint4 val = *reinterpret_cast<const uint4*>(stg + lr * 128 + ((cc ^ (lr & 7)) << 4));
-            *reinterpret_cast<uint4*>(obase + static_cast<long long>(lr) * D + cc * 8) = val;
+          for (int c = 0; c < KC; ++c) {
+            uint32_t pk[16];
+            sum += softmax_group16<false, kTcPoly>(&keep[32 * c], pk, scale_log2, neg_max_scaled, 0, n);
+            if (!TAIL && c == KC - 1) sum += softmax_group16<true, kTcPoly>(&keep[32 * c + 16], pk + 8, scale_log2, neg_max_scaled, 32 * (NT + c) + 16, n);
+            else sum += softmax_group16<false, kTcPoly>(&keep[32 * c + 16], pk + 8, scale_log2, neg_max_scaled, 0, n);
+            tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * (NT + c)), pk);
+            tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * (NT + c) + 8), pk + 8);
+          }
+          if constexpr (TAIL) {
+            uint32_t pk[8];
+            sum += softmax_group16<true, kTcPoly>(&keep[32 * KC], pk, scale_log2, neg_max_scaled, 32 * NC, n);
+            tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * NC), pk);
           }
         }
-        __syncwarp();
+        inv_sum[r * 128 + q * 32 + lane] = 1.0f / sum;
+        tmem_st_wait();
       }
-      tc_trace(p, it, 6);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&p_ready[r]));
+        mbar_arrive(smem_u32(&sum_ready[r]));
+      }
+      tc_trace(p, it, 3);
       rph ^= 1u;
     }
+  } else {
+    // ------------------------------------------------------------------ output warps (one per TMEM lane quarter, both regions)
+    setmaxnreg_dec<kTcRegsOther>();
+    const int q = warp & 3;
+    uint8_t* stg = out_stage + q * 4096;
+    uint32_t rph = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int it = (item - blockIdx.x) / gridDim.x;
+      const int b = item / p.num_heads, h = item - b * p.num_heads;
+      bool ok = true;
+      for (int r = 0; r < 2; ++r) {
+        const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(r * kTcRegionCols);
+        const int row0 = r * 128 + q * 32;
+        if (!mbar_wait(smem_u32(&sum_ready[r]), rph, p.flag, 0x2700u + r)) { ok = false; break; }
+        if (!mbar_wait(smem_u32(&o_full[r]), rph, p.flag, 0x2600u + r)) { ok = false; break; }
+        tcgen05_fence_after();
+        tc_trace(p, it, r * 3 + 0);
+        const bool has_rows = row0 < n;          // warp-uniform
+        const float inv = inv_sum[r * 128 + q * 32 + lane];
+        // O row: 64 fp32 out of TMEM first (the region is handed back as early as possible), then scaled bf16 into
+        // this warp's swizzled staging tile
+        uint32_t o0[32], o1[32];
+        if (has_rows) {
+          tmem_ld_32x32(t_base + kTcOCol, o0);
+          tmem_ld_32x32(t_base + kTcOCol + 32, o1);
+          tmem_ld_wait();
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s_free[r]));         // the region may take the next item's S
+        if (has_rows && !(p.debug & 4)) {
+          if (lane == 0) bulk_wait_read<0>();                     // the previous store has drained this staging tile
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                make_uint4(pack_bf16(__uint_as_float(o0[8 * c]) * inv, __uint_as_float(o0[8 * c + 1]) * inv),
+                           pack_bf16(__uint_as_float(o0[8 * c + 2]) * inv, __uint_as_float(o0[8 * c + 3]) * inv),
+                           pack_bf16(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv),
+                           pack_bf16(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv));
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + c) ^ (lane & 7)) << 4)) =
+                make_uint4(pack_bf16(__uint_as_float(o1[8 * c]) * inv, __uint_as_float(o1[8 * c + 1]) * inv),
+                           pack_bf16(__uint_as_float(o1[8 * c + 2]) * inv, __uint_as_float(o1[8 * c + 3]) * inv),
+                           pack_bf16(__uint_as_float(o1[8 * c + 4]) * inv, __uint_as_float(o1[8 * c + 5]) * inv),
+                           pack_bf16(__uint_as_float(o1[8 * c + 6]) * inv, __uint_as_float(o1[8 * c + 7]) * inv));
+        }
+        tc_trace(p, it, r * 3 + 1);
+        if (has_rows && !(p.debug & 4)) {
+          // one TMA store of the 32-row x 64-column tile to out[b, row0 .., h*64 ..] (rows >= n clipped by the 3-D map)
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmap_out, smem_u32(stg), h * kTcDH, row0, b);
+            bulk_commit();
+          }
+        }
+        tc_trace(p, it, r * 3 + 2);
+      }
+      if (!ok) break;
+      rph ^= 1u;
+    }
+    if (lane == 0) bulk_wait_read<0>();       // smem must outlive the last store's reads
   }
 
   __syncwarp();
@@ -508,15 +546,15 @@ static unsigned long long* tc_trace_buffer() {
     const char* e = getenv("PK_ATT_TRACE");
     on = (e && e[0] == '1') ? 1 : 0;
     if (on) {
-      if (cudaMalloc(&g_tc_trace, 16 * 12 * 8 * sizeof(unsigned long long)) != cudaSuccess) g_tc_trace = nullptr;
-      else cudaMemset(g_tc_trace, 0, 16 * 12 * 8 * sizeof(unsigned long long));
+      if (cudaMalloc(&g_tc_trace, 16 * 16 * 8 * sizeof(unsigned long long)) != cudaSuccess) g_tc_trace = nullptr;
+      else cudaMemset(g_tc_trace, 0, 16 * 16 * 8 * sizeof(unsigned long long));
     }
   }
   return g_tc_trace;
 }
 int attention_trace_copy(unsigned long long* host_dst) {
   if (!g_tc_trace) return PK_ERR_INVALID;
-  return check_cuda(cudaMemcpy(host_dst, g_tc_trace, 16 * 12 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost), "trace copy");
+  return check_cuda(cudaMemcpy(host_dst, g_tc_trace, 16 * 16 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost), "trace copy");
 }
 
 bool attention_tc_eligible(const pk_attention_args* a) {
@@ -537,6 +575,10 @@ int launch_attention_tc(const pk_attention_args* a, cudaStream_t stream) {
   if (rc != PK_OK) return rc;
   rc = make_tmap_bf16_3d(&tkv, a->qkv, 3ull * D, static_cast<uint64_t>(n), static_cast<uint64_t>(a->batch), 3ull * D,
                          static_cast<uint32_t>(n_pad));
+  if (rc != PK_OK) return rc;
+  CUtensorMap tout;
+  rc = make_tmap_bf16_3d(&tout, a->out, static_cast<uint64_t>(D), static_cast<uint64_t>(n), static_cast<uint64_t>(a->batch),
+                         static_cast<uint64_t>(D), 32);
   if (rc != PK_OK) return rc;
   TcAttParams p;
   p.out = static_cast<__nv_bfloat16*>(a->out);
@@ -560,10 +602,10 @@ int launch_attention_tc(const pk_attention_args* a, cudaStream_t stream) {
   case NP: {                                                                                                            \
     static bool attr_set = false;                                                                                       \
     if (!attr_set) {                                                                                                    \
-      PK_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes)); \
+      PK_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<NP>::kBytes)); \
       attr_set = true;                                                                                                  \
     }                                                                                                                   \
-    attention_tc_kernel<NP><<<grid, kTcThreads, kTcSmemBytes, stream>>>(tq, tkv, p);                                    \
+    attention_tc_kernel<NP><<<grid, kTcThreads, TcSmem<NP>::kBytes, stream>>>(tq, tkv, tout, p);                              \
     break;                                                                                                              \
   }
     PK_TC_CASE(144) PK_TC_CASE(160) PK_TC_CASE(176) PK_TC_CASE(192) PK_TC_CASE(208) PK_TC_CASE(224) PK_TC_CASE(240) PK_TC_CASE(256)

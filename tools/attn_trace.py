@@ -13,15 +13,20 @@ out = torch.zeros(B * N, D, device="cuda", dtype=torch.bfloat16)
 for _ in range(2):
     ops.attention(qkv, out, B, H, dh, seq_len=N, impl=2)
 torch.cuda.synchronize()
-buf = np.zeros(16 * 12 * 8, dtype=np.uint64)
+buf = np.zeros(16 * 16 * 8, dtype=np.uint64)
 _lib.check(_lib.load().pk_attention_trace(buf.ctypes.data), "trace")
-t = buf.reshape(16, 12, 8).astype(np.int64)
+t = buf.reshape(16, 16, 8).astype(np.int64)
 t0 = t[t > 0].min()
 t = np.where(t > 0, t - t0, -1)
-names_mma = ["kv_full", "qk0_issued", "qk1_issued", "p0_ready", "p1_ready", "pv0_issued", "pv1_issued"]
-names_sm = ["loop_top", "s_full", "max_done", "p_written", "o_full", "o_read", "stored", "staged"]
-for it in range(5, 8):
+names_mma = ["ready", "qk_issued", "p_ready", "pv_issued", "kv_full"]
+names_sm = ["loop_top", "s_full", "max_done", "p_written"]
+names_out = ["r0_o_full", "r0_staged", "r0_stored", "r1_o_full", "r1_staged", "r1_stored"]
+for it in range(7, 9):
     print(f"--- item {it}")
-    print("  mma  ", {n: int(t[it, 1, e]) for e, n in enumerate(names_mma)})
-    for w in (4, 5, 8, 10):
-        print(f"  warp{w}", {n: int(t[it, w, e]) for e, n in enumerate(names_sm)})
+    print("  tma   ", {"qk_slot_free": int(t[it, 0, 0]), "v_slot_free": int(t[it, 0, 1])})
+    for w in (1, 2):
+        print(f"  mma{w - 1} ", {n: int(t[it, w, e]) for e, n in enumerate(names_mma)})
+    for w in (4, 8):
+        print(f"  soft{w}", {n: int(t[it, w, e]) for e, n in enumerate(names_sm)})
+    for w in (12, 13, 14, 15):
+        print(f"  out{w}", {n: int(t[it, w, e]) for e, n in enumerate(names_out)})
