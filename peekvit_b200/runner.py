@@ -32,6 +32,7 @@ def packed(model) -> engine.PackedModel:
     if st["fp"] != fp:
         st["pm"] = engine.pack_model(model, model._family)
         st["fp"] = fp
+        st.pop("graphs", None)          # captured launch sequences point at the old weight pack
     return st["pm"]
 
 

@@ -344,3 +344,90 @@ def test_gather_rows_and_sort_and_drop(ops):
     idx = torch.argsort(torch.norm(tok, dim=-1), dim=-1, descending=True, stable=True).unsqueeze(-1)
     ref = torch.cat([cls, torch.gather(tok, 1, idx.expand(-1, -1, D))[:, :k]], 1)
     assert torch.equal(y, ref)
+
+
+# ------------------------------------------------------------------ CTA-pair GEMM (cta_group::2) and the single-CTA kernel, forced
+@pytest.mark.parametrize("shape", [(256, 256, 64), (300, 768, 768), (1000, 2304, 768), (257, 768, 3072), (777, 1152, 384),
+                                   (600, 1000, 768), (197 * 40, 3072, 768)])
+@pytest.mark.parametrize("cta_pair", [1, 2])
+def test_gemm_both_kernels_all_epilogues(ops, shape, cta_pair):
+    """cta_pair=2 forces the 256 x BN tcgen05 cta_group::2 kernel, 1 the 128 x BN single-CTA kernel; same results.
+    The in-place residual epilogue of the pair kernel adds through a TMA reduction at L2 (x += ...)."""
+    from peekvit_b200._lib import PK_EPI_BIAS_BF16, PK_EPI_BIAS_F32, PK_EPI_BIAS_GELU_BF16, PK_EPI_BIAS_RESID_F32
+    M, N, K = shape
+    a, w, bias = _operands(M, N, K, seed=3)
+    acc = a.float() @ w.float().t() + bias
+    for bn in (0, 128):
+        out = torch.full((M, N), float("nan"), device=DEV)
+        ops.gemm(a, w, bias, out, PK_EPI_BIAS_F32, block_n=bn, cta_pair=cta_pair)
+        assert rel_err(out, acc) < TOL_F32
+        outb = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+        ops.gemm(a, w, bias, outb, PK_EPI_BIAS_BF16, block_n=bn, cta_pair=cta_pair)
+        assert rel_err(outb, acc) < TOL_BF16
+        ops.gemm(a, w, bias, outb, PK_EPI_BIAS_GELU_BF16, block_n=bn, cta_pair=cta_pair)
+        assert rel_err(outb, torch.nn.functional.gelu(acc)) < TOL_BF16
+        x = torch.randn(M, N, device=DEV)
+        rs = torch.rand(M, device=DEV)
+        x0 = x.clone()
+        ops.gemm(a, w, bias, x, PK_EPI_BIAS_RESID_F32, resid=x, rowscale=rs, block_n=bn, cta_pair=cta_pair)      # in place
+        assert rel_err(x, rs[:, None] * acc + x0) < TOL_F32
+        y = torch.empty(M, N, device=DEV)
+        ops.gemm(a, w, bias, y, PK_EPI_BIAS_RESID_F32, resid=x0, block_n=bn, cta_pair=cta_pair)                  # out of place
+        assert rel_err(y, acc + x0) < TOL_F32
+    assert ops.device_flag() == 0
+
+
+@pytest.mark.parametrize("m_dev", [0, 1, 255, 256, 333, 1000])
+def test_pair_gemm_device_side_row_count(ops, m_dev):
+    """Ragged batches: rows >= *m_dev must stay untouched (bit-exact), rows below match."""
+    from peekvit_b200._lib import PK_EPI_BIAS_BF16, PK_EPI_BIAS_F32, PK_EPI_BIAS_RESID_F32
+    M, N, K = 1000, 768, 384
+    a, w, _ = _operands(M, N, K, seed=5)
+    ref = a.float() @ w.float().t()
+    md = torch.tensor([m_dev], device=DEV, dtype=torch.int32)
+    out = torch.full((M, N), 7.0, device=DEV)
+    ops.gemm(a, w, None, out, PK_EPI_BIAS_F32, m_dev=md, cta_pair=2)
+    outb = torch.full((M, N), 7.0, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, w, None, outb, PK_EPI_BIAS_BF16, m_dev=md, cta_pair=2)
+    x = torch.ones(M, N, device=DEV)
+    ops.gemm(a, w, None, x, PK_EPI_BIAS_RESID_F32, resid=x, m_dev=md, cta_pair=2)
+    assert bool((out[m_dev:] == 7).all()) and bool((outb[m_dev:] == 7).all()) and bool((x[m_dev:] == 1).all())
+    if m_dev:
+        assert rel_err(out[:m_dev], ref[:m_dev]) < TOL_F32
+        assert rel_err(outb[:m_dev], ref[:m_dev]) < TOL_BF16
+        assert rel_err(x[:m_dev], ref[:m_dev] + 1) < TOL_F32
+    assert ops.device_flag() == 0
+
+
+# ------------------------------------------------------------------ tcgen05 / TMEM attention (uniform 128 < n <= 256, head_dim 64)
+@pytest.mark.parametrize("cfg", [(1, 1, 197), (2, 12, 197), (3, 6, 198), (2, 3, 129), (2, 2, 256), (2, 2, 144), (5, 4, 145),
+                                 (3, 2, 160), (2, 2, 176), (2, 2, 192), (2, 2, 209), (2, 2, 225), (2, 2, 241)])
+def test_attention_tcgen05(ops, cfg):
+    """impl=2 forces the tcgen05/TMEM kernel (every padded length 144..256); impl=1 the general mma.sync kernel."""
+    B, H, N = cfg
+    dh, D = 64, H * 64
+    g = torch.Generator(device=DEV).manual_seed(B * 1000 + N)
+    qkv = (torch.randn(B * N, 3 * D, device=DEV, generator=g) * 1.5).to(torch.bfloat16)
+    out = torch.full((B * N, D), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.attention(qkv, out, B, H, dh, seq_len=N, impl=2)
+    assert ops.device_flag() == 0
+    blk = qkv.float().view(B, N, 3, H, dh)
+    q, k, v = blk[:, :, 0].transpose(1, 2), blk[:, :, 1].transpose(1, 2), blk[:, :, 2].transpose(1, 2)
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), -1) @ v).transpose(1, 2).reshape(B * N, D)
+    assert rel_err(out, ref) < TOL_BF16
+    out1 = torch.zeros_like(out)
+    ops.attention(qkv, out1, B, H, dh, seq_len=N, impl=1)
+    assert rel_err(out1, ref) < TOL_BF16
+
+
+def test_attention_tcgen05_full_size_rows_sum_property(ops):
+    """BASELINE config size (256 images x 12 heads x 197 tokens): with V = ones every output element is exactly 1
+    (softmax rows sum to one), whatever Q and K are: a size-independent check of the P V path and the row sums."""
+    B, H, N, dh = 256, 12, 197, 64
+    D = H * dh
+    qkv = torch.randn(B * N, 3 * D, device=DEV).to(torch.bfloat16)
+    qkv[:, 2 * D:] = 1.0
+    out = torch.zeros(B * N, D, device=DEV, dtype=torch.bfloat16)
+    ops.attention(qkv, out, B, H, dh, seq_len=N, impl=2)
+    assert ops.device_flag() == 0
+    assert float((out.float() - 1.0).abs().max()) < 1e-2
