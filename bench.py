@@ -204,10 +204,17 @@ def main():
     from peekvit_b200 import sharding
     total_t = torch.tensor(B, device=dev)
 
+    local_counts = torch.zeros(2, dtype=torch.int64, device=dev)
+
     def step():
         logits = model(images)
-        # the eval loop's accuracy count (validate/test.py:120-127): the only cross-GPU exchange
-        counts.copy_(sharding.reduce_counts((logits.argmax(1) == labels).sum(), total_t))
+        # the eval loop's accuracy count (validate/test.py:120-127) fused on the device (pk_argmax_count); the only
+        # cross-GPU exchange is the all-reduce of the two counters
+        local_counts.zero_()
+        ops.argmax_count(logits, labels, local_counts)
+        if world > 1:
+            counts.copy_(local_counts)
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
         return logits
 
     def barrier():

@@ -129,6 +129,12 @@ int pk_cls_head(const float* x, int batch, int seq_len, const int* cu_seqlens, i
                 const float* gamma, const float* beta, float eps,
                 const float* head_w, const float* head_b, int num_classes, float* logits, void* stream);
 
+/* ---- eval loop: top-1 prediction and accuracy counts on the device (validate/test.py:116-129 does
+ * logits.argmax + torchmetrics on the host side).  pred_out[b] = first arg-max of logits[b, :] (int32, optional);
+ * if labels (int64) and counts (int64[2]) are given: counts[0] += #(pred == label), counts[1] += batch. */
+int pk_argmax_count(const float* logits, const long long* labels, int batch, int num_classes, int* pred_out,
+                    long long* counts, void* stream);
+
 /* ---- K9/K10/K11: RankViT sort_and_drop (rankvit.py:55-77) ----------------------------- */
 /* scores[b, i] = || x[b, 1+i, :] ||_2 for the n = seq_len-1 non-class tokens (rankvit.py:63). */
 int pk_token_norm_score(const float* x, float* scores, int batch, int seq_len, int dim, void* stream);
@@ -207,6 +213,10 @@ int pk_avit_halt_plan(const pk_avit_args* args, void* stream);
  * offsets[E+1], counts[E], src_of[pos] = original row of the pos-th expert-sorted row. */
 int pk_moe_route(const float* x, const float* gamma, const float* beta, float eps, const float* gate_w, const float* gate_b,
                  int n_experts, int rows, int dim, int* expert, int* offsets, int* counts, int* src_of, void* stream);
+
+/* x[src_of[r], :] += y[r, :] for r < rows: un-permute + residual add of expert outputs computed in expert-sorted order
+ * (moevit.py:54-61; src_of from pk_moe_route is a permutation, so no two rows collide). */
+int pk_scatter_add_rows(float* x, const float* y, const int* src_of, int rows, int dim, void* stream);
 
 #ifdef __cplusplus
 }

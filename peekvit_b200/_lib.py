@@ -97,6 +97,7 @@ SIGNATURES: Dict[str, tuple] = {
     "pk_attention_fwd": (c_int, [C.POINTER(AttentionArgs), c_void_p]),
     "pk_attention_trace": (c_int, [c_void_p]),
     "pk_cls_head": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "pk_argmax_count": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "pk_token_norm_score": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pk_topk_select": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pk_gather_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -107,6 +108,7 @@ SIGNATURES: Dict[str, tuple] = {
     "pk_residual_ghost": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "pk_residual_publish": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "pk_avit_halt_plan": (c_int, [C.POINTER(AvitArgs), c_void_p]),
+    "pk_scatter_add_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "pk_moe_route": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p]),
 }

@@ -24,27 +24,33 @@ namespace pk {
 
 constexpr int kP_BM = 128;          // rows per CTA (256 per pair)
 constexpr int kP_BK = 64;           // 64 bf16 = one 128-byte swizzle row
-constexpr int kP_EpiWarps = 8;
-constexpr int kP_Threads = 128 + kP_EpiWarps * 32;
 constexpr int kP_BufBytes = 4096;   // one 32-row x 128-byte staging tile
 
 // RED: the residual epilogue is in place (out == resid), so the add is done by a TMA reduction
 // (cp.reduce.async.bulk.tensor .add, executed at L2) and the residual tile never visits shared memory.
-template <int BN, int EPI, bool RED>
+// EW epilogue warps per CTA: 8 (two per TMEM lane quarter, each owning half the tile's columns) or 16 (four per
+// quarter, a quarter of the columns each: the GELU epilogue is latency-bound with two warps per scheduler).
+template <int BN, int EPI, bool RED, int EW = 8>
 struct PairCfg {
+  static constexpr int kEpiWarps = EW;
+  static constexpr int kThreads = 128 + EW * 32;
+  static constexpr int kParts = EW / 4;                                       // column parts of the tile
+  static constexpr int kPartCols = BN / kParts;
   static constexpr bool kOutBf16 = (EPI == PK_EPI_BIAS_BF16 || EPI == PK_EPI_BIAS_GELU_BF16);
   static constexpr bool kResid = (EPI == PK_EPI_BIAS_RESID_F32) && !RED;
-  static constexpr int kUnits = BN / 64;                                      // 32-column accumulator units per warp
+  static constexpr int kUnits = kPartCols / 32;                                // 32-column accumulator units per warp
+  static_assert(kPartCols % 32 == 0, "tile width must split into 32-column units per epilogue warp");
   static constexpr int kUnitsPerStore = (kOutBf16 && kUnits % 2 == 0) ? 2 : 1; // bf16: 64 columns = one 128-byte row
   static constexpr int kChunks = kUnits / kUnitsPerStore;                     // TMA stores per warp per tile
   static constexpr int kStoreCols = 32 * kUnitsPerStore;
   static constexpr int kStoreSwizzle = kOutBf16 ? (kUnitsPerStore == 2 ? 128 : 64) : 128;
-  static constexpr int kBufs = kResid ? 3 : 2;                                // staging buffers per epilogue warp
+  static constexpr int kBufs = EW == 16 ? 1 : (kResid ? 3 : 2);               // staging buffers per epilogue warp
+  static_assert(EW == 8 || !kResid, "the staged-residual epilogue needs its 3-deep ring (8 epilogue warps)");
   static constexpr int kABytes = kP_BM * kP_BK * 2;
   static constexpr int kBBytes = (BN / 2) * kP_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = kP_EpiWarps * kBufs * kP_BufBytes;
-  static constexpr int kBarBytes = 512;
+  static constexpr int kStagingBytes = EW * kBufs * kP_BufBytes;
+  static constexpr int kBarBytes = 1024;
   static constexpr int kBudget = 232448 - 1024 - kBarBytes - kStagingBytes;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -57,6 +63,7 @@ struct PairCfg {
 struct PairParams {
   int M, N, K;
   const int* m_dev;
+  const int* row_begin_dev;
   const float* bias;
   void* out;
   long long ldo;
@@ -118,12 +125,13 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 }
 __device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
 
-template <int BN, int EPI, bool RED>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP_Threads, 1)
+template <int BN, int EPI, bool RED, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + EW * 32, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                       const PairParams p) {
-  using Cfg = PairCfg<BN, EPI, RED>;
+  using Cfg = PairCfg<BN, EPI, RED, EW>;
+  constexpr int kP_EpiWarps = EW;
   constexpr bool kOutBf16 = Cfg::kOutBf16;
   constexpr bool kResid = Cfg::kResid;
   extern __shared__ uint8_t smem_raw[];
@@ -143,7 +151,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
-  const int M = p.m_dev ? max(0, min(*p.m_dev, p.M)) : p.M;
+  const int row0 = p.row_begin_dev ? *p.row_begin_dev : 0;     // first row of this launch's segment (MoE expert segments)
+  const int M = p.m_dev ? max(0, min(*p.m_dev, p.M - row0)) : p.M - row0;
   const int m_tiles = (M + 2 * kP_BM - 1) / (2 * kP_BM);
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
@@ -191,7 +200,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     int pf_t = pair, pf_kb = 0;
     auto prefetch_next = [&]() {        // elected lane
       if (pf_t < num_tiles) {
-        tma_prefetch_l2_2d(&tmap_a, pf_kb * kP_BK, (pf_t / n_tiles) * 2 * kP_BM + a_row_off);
+        tma_prefetch_l2_2d(&tmap_a, pf_kb * kP_BK, row0 + (pf_t / n_tiles) * 2 * kP_BM + a_row_off);
         tma_prefetch_l2_2d(&tmap_b, pf_kb * kP_BK, (pf_t % n_tiles) * BN + b_row_off);
       }
     };
@@ -219,7 +228,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           if (rank == 0) mbar_expect_tx(fb_local, 2 * Cfg::kStageBytes);   // both CTAs' bytes land on the leader's barrier
           const uint32_t fb = mapa_u32(fb_local, 0);
           const uint32_t a_dst = smem_u32(smem_ab + s * Cfg::kStageBytes);
-          tma_load_2d_pair(a_dst, &tmap_a, fb, kb * kP_BK, m_blk * 2 * kP_BM + a_row_off);
+          tma_load_2d_pair(a_dst, &tmap_a, fb, kb * kP_BK, row0 + m_blk * 2 * kP_BM + a_row_off);
           tma_load_2d_pair(a_dst + Cfg::kABytes, &tmap_b, fb, kb * kP_BK, n_blk * BN + b_row_off);
           }
           if (p.l2_prefetch) prefetch_next();
@@ -271,7 +280,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     // ------------------------------------------------------------------ epilogue warps (both CTAs)
     const int ew = warp - 4;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = ew >> 2;               // which half of the tile's columns
+    const int half = ew >> 2;               // which part of the tile's columns (kParts of them)
+    constexpr int kPartCols = Cfg::kPartCols;
     constexpr int kUnits = Cfg::kUnits;
     constexpr int kUPS = Cfg::kUnitsPerStore;
     constexpr int kChunks = Cfg::kChunks;
@@ -287,8 +297,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       const uint32_t b = g % 3u;
       const uint32_t bar = smem_u32(&rbar[b]);
       mbar_expect_tx(bar, kP_BufBytes);
-      tma_load_2d(ebuf_u32 + b * kP_BufBytes, &tmap_res, bar, (tt % n_tiles) * BN + half * (BN / 2) + ch * Cfg::kStoreCols,
-                  (tt / n_tiles) * 2 * kP_BM + row_in_pair);
+      tma_load_2d(ebuf_u32 + b * kP_BufBytes, &tmap_res, bar, (tt % n_tiles) * BN + half * kPartCols + ch * Cfg::kStoreCols,
+                  row0 + (tt / n_tiles) * 2 * kP_BM + row_in_pair);
     };
     if constexpr (kResid) {
       if (lane == 0 && !(p.debug & 2)) {
@@ -305,16 +315,17 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     bool ok = true;
     for (int t = pair; t < num_tiles && ok; t += num_pairs) {
       const int m_blk = t / n_tiles;
-      const int row_base = m_blk * 2 * kP_BM + row_in_pair;                                // this warp's first row
+      const int row_base = row0 + m_blk * 2 * kP_BM + row_in_pair;                         // this warp's first row
       const int grow = row_base + lane;
-      const bool full_tile = row_base + 32 <= M;                                           // warp-uniform
+      const int row_end = row0 + M;                                                        // rows >= row_end stay untouched
+      const bool full_tile = row_base + 32 <= row_end;                                     // warp-uniform
       float sc = 1.0f;
       if constexpr (kResid || RED) {
-        if (p.rowscale && grow < M) sc = p.rowscale[grow];
+        if (p.rowscale && grow < row_end) sc = p.rowscale[grow];
       }
       if (!mbar_wait(smem_u32(&tfull_bar[as]), aph, p.flag, 0x1400u + as)) { ok = false; break; }
       tcgen05_fence_after();
-      const uint32_t t_col0 = t_lane + static_cast<uint32_t>(as * BN + half * (BN / 2));
+      const uint32_t t_col0 = t_lane + static_cast<uint32_t>(as * BN + half * kPartCols);
       uint32_t va[32], vb[32];
       tmem_ld_32x32(t_col0, va);
 #pragma unroll
@@ -323,9 +334,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         uint32_t (&vn)[32] = (u & 1) ? va : vb;
         const int ch = u / kUPS;              // store chunk inside the tile
         const int sub = u % kUPS;             // unit inside the store chunk
-        const uint32_t b = kResid ? (g % 3u) : (g & 1u);
+        const uint32_t b = kBufs == 1 ? 0u : (kResid ? (g % 3u) : (g & 1u));
         uint8_t* bufp = ebuf + b * kP_BufBytes;
-        const int col0 = (t % n_tiles) * BN + half * (BN / 2) + u * 32;     // first output column of this unit
+        const int col0 = (t % n_tiles) * BN + half * kPartCols + u * 32;     // first output column of this unit
         float4 bias4[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -346,7 +357,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           if constexpr (kResid) {
             if (!mbar_wait(smem_u32(&rbar[b]), (g / 3u) & 1u, p.flag, 0x1500u + ew)) { ok = false; break; }
           } else {
-            if (lane == 0) bulk_wait_read<1>();     // the store issued two chunks ago no longer reads this buffer
+            // the store that last used this buffer (two chunks ago; the previous one with a single buffer) has drained
+            if (lane == 0) { if constexpr (kBufs == 1) bulk_wait_read<0>(); else bulk_wait_read<1>(); }
             __syncwarp();
           }
         }
@@ -410,7 +422,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           // An empty bulk group keeps the one-group-per-chunk accounting of the buffer ring.
           if (sub == kUPS - 1 && lane == 0) bulk_commit();
         }
-        if (!full_tile && grow < M) {
+        if (!full_tile && grow < row_end) {
           if constexpr (kOutBf16) {
             __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(grow) * p.ldo + col0;
 #pragma unroll
@@ -476,6 +488,16 @@ static int pair_tma_reduce() {
   }
   return v;
 }
+// PK_GEMM_GELU_WARPS=16 gives the GELU epilogue four warps per scheduler (measured slower on B200: fc1 1234 -> 1166 TFLOP/s;
+// kept for experiments).
+static int pair_gelu_warps() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PK_GEMM_GELU_WARPS");
+    v = (e && atoi(e) == 16) ? 16 : 8;
+  }
+  return v;
+}
 static int pair_debug() {
   static int v = -1;
   if (v < 0) {
@@ -485,11 +507,11 @@ static int pair_debug() {
   return v;
 }
 
-template <int BN, int EPI, bool RED = false>
+template <int BN, int EPI, bool RED = false, int EW = 8>
 static int launch_pair(const pk_gemm_args* a, cudaStream_t stream) {
-  using Cfg = PairCfg<BN, EPI, RED>;
+  using Cfg = PairCfg<BN, EPI, RED, EW>;
   static bool attr_set = false;
-  auto kfn = gemm_bf16_pair_kernel<BN, EPI, RED>;
+  auto kfn = gemm_bf16_pair_kernel<BN, EPI, RED, EW>;
   if (!attr_set) {
     PK_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
@@ -513,6 +535,7 @@ static int launch_pair(const pk_gemm_args* a, cudaStream_t stream) {
   PairParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.m_dev = a->m_dev;
+  p.row_begin_dev = a->row_begin_dev;
   p.bias = a->bias;
   p.out = a->out; p.ldo = a->ldo;
   p.rowscale = a->rowscale;
@@ -524,7 +547,7 @@ static int launch_pair(const pk_gemm_args* a, cudaStream_t stream) {
   const int sms = a->max_ctas > 0 ? a->max_ctas : num_sms();
   if (pairs > sms / 2) pairs = sms / 2;
   if (pairs < 1) pairs = 1;
-  kfn<<<2 * pairs, kP_Threads, Cfg::kSmemBytes, stream>>>(ta, tb, tout, tres, p);
+  kfn<<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tout, tres, p);
   return check_cuda(cudaGetLastError(), "gemm_bf16_pair_kernel launch");
 }
 
@@ -532,7 +555,11 @@ template <int BN>
 static int dispatch_pair_epi(const pk_gemm_args* a, cudaStream_t stream) {
   switch (a->epilogue) {
     case PK_EPI_BIAS_BF16: return launch_pair<BN, PK_EPI_BIAS_BF16>(a, stream);
-    case PK_EPI_BIAS_GELU_BF16: return launch_pair<BN, PK_EPI_BIAS_GELU_BF16>(a, stream);
+    case PK_EPI_BIAS_GELU_BF16:
+      if constexpr (BN != 192) {
+        if (pair_gelu_warps() == 16) return launch_pair<BN, PK_EPI_BIAS_GELU_BF16, false, 16>(a, stream);
+      }
+      return launch_pair<BN, PK_EPI_BIAS_GELU_BF16>(a, stream);
     case PK_EPI_BIAS_RESID_F32:
       // in-place residual (x += ...): let the TMA reduction do the add at L2
       if (a->resid == a->out && a->ldr == a->ldo && pair_tma_reduce()) return launch_pair<BN, PK_EPI_BIAS_RESID_F32, true>(a, stream);
@@ -559,7 +586,7 @@ static int pick_pair_block_n(int N) {
 // The pair kernel needs plain row mapping (TMA tile stores), 16-byte aligned rows and N % 8 == 0.
 bool pair_gemm_eligible(const pk_gemm_args* a) {
   if (a->epilogue_mode == 2) return false;
-  if (a->rows_per_group > 0 || a->row_begin_dev || a->out_row_index) return false;
+  if (a->rows_per_group > 0 || a->out_row_index) return false;
   const bool bf = a->epilogue == PK_EPI_BIAS_BF16 || a->epilogue == PK_EPI_BIAS_GELU_BF16;
   const long long eb = bf ? 2 : 4;
   if ((a->ldo * eb) % 16 != 0 || (reinterpret_cast<uintptr_t>(a->out) & 15) != 0) return false;

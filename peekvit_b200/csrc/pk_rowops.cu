@@ -323,6 +323,51 @@ extern "C" int pk_cls_head(const float* x, int batch, int seq_len, const int* cu
   return check_cuda(cudaGetLastError(), "cls_head_kernel");
 }
 
+// ------------------------------------------------------------------ eval-loop accuracy (validate/test.py:116-129)
+// One warp per sample: first-maximum arg-max over the classes (torch.argmax semantics; NaN logits never win),
+// compared with the label; counts[0] += #correct, counts[1] += #samples (64-bit atomics).
+__global__ void __launch_bounds__(256)
+argmax_count_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int batch, int num_classes,
+                    int* __restrict__ pred_out, unsigned long long* __restrict__ counts) {
+  const int lane = lane_id();
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  unsigned long long correct = 0, seen = 0;
+  for (int b = blockIdx.x * (blockDim.x >> 5) + warp_id(); b < batch; b += warps_total) {
+    float best = -INFINITY;
+    int best_i = 0x7fffffff;
+    for (int c = lane; c < num_classes; c += 32) {
+      const float v = logits[static_cast<long long>(b) * num_classes + c];
+      if (v > best) { best = v; best_i = c; }            // strict: the lowest index of a tie stays
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+    }
+    if (best_i == 0x7fffffff) best_i = 0;
+    if (lane == 0) {
+      if (pred_out) pred_out[b] = best_i;
+      if (labels) correct += (labels[b] == best_i) ? 1ull : 0ull;
+      seen += 1ull;
+    }
+  }
+  if (lane == 0 && counts && seen) {
+    if (correct) atomicAdd(&counts[0], correct);
+    atomicAdd(&counts[1], seen);
+  }
+}
+
+extern "C" int pk_argmax_count(const float* logits, const long long* labels, int batch, int num_classes, int* pred_out,
+                               long long* counts, void* stream) {
+  PK_REQUIRE(logits && num_classes > 0 && batch >= 0, "pk_argmax_count: bad arguments");
+  PK_REQUIRE(pred_out || counts, "pk_argmax_count: need pred_out and/or counts");
+  if (batch == 0) return PK_OK;
+  argmax_count_kernel<<<grid_for(batch, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, labels, batch, num_classes, pred_out, reinterpret_cast<unsigned long long*>(counts));
+  return check_cuda(cudaGetLastError(), "argmax_count_kernel");
+}
+
 extern "C" int pk_token_norm_score(const float* x, float* scores, int batch, int seq_len, int dim, void* stream) {
   PK_REQUIRE(x && scores && dim % 4 == 0 && seq_len >= 1, "pk_token_norm_score: bad arguments");
   const long long total = (long long)batch * (seq_len - 1);

@@ -538,6 +538,33 @@ extern "C" int pk_avit_halt_plan(const pk_avit_args* a, void* stream) {
   return check_cuda(cudaGetLastError(), "avit_halt_plan_kernel");
 }
 
+// ------------------------------------------------------------------ un-permute of expert-sorted rows (moevit.py:54-61)
+// x[src_of[r], :] += y[r, :]: the expert MLP outputs were computed in expert-sorted order by plain (fast-path) GEMMs;
+// every destination row is written by exactly one source row, so this is a gather-add without atomics.
+__global__ void __launch_bounds__(256)
+scatter_add_rows_kernel(float* __restrict__ x, const float* __restrict__ y, const int* __restrict__ src_of, int rows, int dim) {
+  const int lane = lane_id(), d4 = dim / 4;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int r = blockIdx.x * (blockDim.x >> 5) + warp_id(); r < rows; r += warps_total) {
+    const long long dst = src_of[r];
+    const float4* src = reinterpret_cast<const float4*>(y + static_cast<long long>(r) * dim);
+    float4* out = reinterpret_cast<float4*>(x + dst * dim);
+    for (int c = lane; c < d4; c += 32) {
+      const float4 a = src[c];
+      float4 b = out[c];
+      b.x += a.x; b.y += a.y; b.z += a.z; b.w += a.w;
+      out[c] = b;
+    }
+  }
+}
+
+extern "C" int pk_scatter_add_rows(float* x, const float* y, const int* src_of, int rows, int dim, void* stream) {
+  PK_REQUIRE(x && y && src_of && dim % 4 == 0 && rows >= 0, "pk_scatter_add_rows: bad arguments");
+  if (rows == 0) return PK_OK;
+  scatter_add_rows_kernel<<<grid_rows(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, src_of, rows, dim);
+  return check_cuda(cudaGetLastError(), "scatter_add_rows_kernel");
+}
+
 extern "C" int pk_moe_route(const float* x, const float* gamma, const float* beta, float eps, const float* gate_w, const float* gate_b,
                             int n_experts, int rows, int dim, int* expert, int* offsets, int* counts, int* src_of, void* stream) {
   PK_REQUIRE(x && gamma && beta && gate_w && gate_b && expert && offsets && counts && src_of, "pk_moe_route: null pointer");

@@ -474,10 +474,14 @@ class Forward:
             a = ops.layernorm(x, lw.ln2_w, lw.ln2_b, lw.eps, ws.get("ln", (rows, D), torch.bfloat16), rows=rows, row_index=src_of)
             F = lw.mlp[0].w_fc1.shape[0]
             hid = ws.get("hid", (rows, F), torch.bfloat16)
+            # Expert-sorted rows: each expert's segment [offsets[e], offsets[e] + counts[e]) runs through the CTA-pair GEMMs
+            # (device-side segment start and length); the fc2 outputs land in sorted order and one gather-add un-permutes
+            # them into the residual stream.
+            y_sorted = ws.get("moe_y", (rows, D), torch.float32)
             for e, mw in enumerate(lw.mlp):
                 ops.gemm(a, mw.w_fc1, mw.b_fc1, hid, PK_EPI_BIAS_GELU_BF16, m_dev=counts[e:e + 1], row_begin_dev=offsets[e:e + 1])
-                ops.gemm(hid, mw.w_fc2, mw.b_fc2, x, PK_EPI_BIAS_RESID_F32, resid=x, m_dev=counts[e:e + 1],
-                         row_begin_dev=offsets[e:e + 1], out_row_index=src_of)
+                ops.gemm(hid, mw.w_fc2, mw.b_fc2, y_sorted, PK_EPI_BIAS_F32, m_dev=counts[e:e + 1], row_begin_dev=offsets[e:e + 1])
+            ops.scatter_add_rows(x, y_sorted, src_of, rows)
             if aux is not None:
                 aux.setdefault("mlp_expert", {})[i] = expert.view(B, seq).clone()
         return self.head(x, B, seq, n_cls=1)

@@ -182,6 +182,20 @@ def cls_head(x: torch.Tensor, batch: int, seq_len: int, n_cls: int, gamma, beta,
     return out
 
 
+def argmax_count(logits: torch.Tensor, labels: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None,
+                 pred: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """Top-1 prediction (int32) and/or accuracy counts (int64 [correct, total], accumulated) on the device."""
+    lib = _lib_for(logits)
+    if logits.dim() != 2 or not logits.is_contiguous():
+        raise ValueError("logits must be contiguous [batch, classes]")
+    B, C_ = logits.shape
+    if pred is None and counts is None:
+        pred = torch.empty(B, dtype=torch.int32, device=logits.device)
+    check(lib.pk_argmax_count(_ptr(logits, torch.float32), _ptr(labels, torch.int64), B, C_, _ptr(pred, torch.int32),
+                              _ptr(counts, torch.int64), _stream()), "pk_argmax_count")
+    return pred if pred is not None else counts
+
+
 def token_norm_score(x: torch.Tensor, batch: int, seq_len: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib_for(x)
     dim = x.shape[-1]
@@ -301,3 +315,12 @@ def moe_route(x, gamma, beta, eps: float, gate_w, gate_b, rows: int, expert, off
 def device_flag(reset: bool = True) -> int:
     """Watchdog word of the tcgen05 kernels (0 = healthy). Synchronises the device."""
     return _lib.load().pk_device_flag(int(reset))
+
+
+def scatter_add_rows(x: torch.Tensor, y: torch.Tensor, src_of: torch.Tensor, rows: Optional[int] = None) -> torch.Tensor:
+    """x[src_of[r]] += y[r] (un-permute + residual add of expert-sorted rows)."""
+    lib = _lib_for(x)
+    n = y.shape[0] if rows is None else rows
+    check(lib.pk_scatter_add_rows(_ptr(x, torch.float32), _ptr(y, torch.float32), _ptr(src_of, torch.int32), n, x.shape[-1], _stream()),
+          "pk_scatter_add_rows")
+    return x

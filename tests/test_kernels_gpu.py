@@ -431,3 +431,21 @@ def test_attention_tcgen05_full_size_rows_sum_property(ops):
     ops.attention(qkv, out, B, H, dh, seq_len=N, impl=2)
     assert ops.device_flag() == 0
     assert float((out.float() - 1.0).abs().max()) < 1e-2
+
+
+def test_argmax_count(ops):
+    """pk_argmax_count == torch.argmax (first maximum on ties) and the accuracy counters accumulate."""
+    g = torch.Generator(device=DEV).manual_seed(4)
+    logits = torch.randn(1000, 1000, device=DEV, generator=g).round(decimals=1)      # plenty of exact ties
+    labels = torch.randint(0, 1000, (1000,), device=DEV, generator=g)
+    ref = logits.argmax(1)
+    labels[::3] = ref[::3]
+    pred = ops.argmax_count(logits)
+    assert torch.equal(pred.long(), ref)
+    counts = torch.zeros(2, dtype=torch.int64, device=DEV)
+    ops.argmax_count(logits, labels, counts)
+    ops.argmax_count(logits[:10], labels[:10], counts)
+    exp = int((ref == labels).sum()) + int((ref[:10] == labels[:10]).sum())
+    assert counts.tolist() == [exp, 1010]
+    small = torch.tensor([[1.0, 3.0, 3.0], [float("nan"), 0.0, -1.0]], device=DEV)
+    assert ops.argmax_count(small).tolist() == [1, 1]
