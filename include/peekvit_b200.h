@@ -74,9 +74,28 @@ typedef struct pk_gemm_args {
   int epilogue_mode;     /* 0 = auto (TMA tile store when rows are contiguous), 2 = force the SIMT epilogue */
   int cta_pair;          /* 0 = auto (CTA-pair 256 x block_n tiles, tcgen05 cta_group::2, when rows are contiguous),
                             1 = single-CTA 128 x block_n kernel, 2 = force the CTA-pair kernel */
+  /* LayerNorm fused across two GEMMs (x -> LN -> Linear, vit.py:48-55) instead of a LayerNorm kernel in between.
+   * Producer (PK_EPI_BIAS_RESID_F32 only): besides out, write xb_out = bf16(out) and, per row, the partial
+   * (sum, sum of squares) of each column tile into row_stats[row][part][2], part < pk_gemm_row_stat_parts(N). */
+  void* xb_out;          /* bf16 [M, N], leading dimension ldxb, or NULL */
+  long long ldxb;
+  float* row_stats;      /* f32 [M][parts][2] */
+  /* Consumer (PK_EPI_BIAS_BF16 / _GELU_BF16): A is such a raw bf16 copy and W carries the LayerNorm gain
+   * (W' = bf16(gamma * W)); with mean/rstd of row r from ln_stats (summed over ln_parts slots, ln_dim elements, eps):
+   *   out[r,n] = act( rstd_r * acc[r,n] - rstd_r * mean_r * ln_c1[n] + bias[n] ),
+   *   ln_c1[n] = sum_k W'[n,k],  bias[n] = linear bias[n] + sum_k beta[k] * W[n,k]. */
+  const float* ln_stats; /* f32 [M][ln_parts][2] or NULL */
+  const float* ln_c1;    /* f32 [N] */
+  int ln_parts, ln_dim;
+  float ln_eps;
 } pk_gemm_args;
 
 int pk_gemm_bf16(const pk_gemm_args* args, void* stream);
+/* Number of statistics slots per row the LayerNorm-producer epilogue writes for an N-column output. */
+int pk_gemm_row_stat_parts(int N);
+/* Statistics + raw bf16 copy of rows that do not come out of a producer GEMM (the embedding output):
+ * xb[r,:] = bf16(x[r,:]); row_stats[r][0] = (sum, sum of squares); row_stats[r][1..parts) = 0. */
+int pk_row_stats_cast(const float* x, void* xb, float* row_stats, int rows, int dim, int parts, void* stream);
 
 /* ---- K1: patchify (the im2col half of conv_proj, vit.py:212-220) --------------------- */
 /* images f32 [B,3,S,S] NCHW -> patches bf16 [B*(S/p)^2, 3*p*p], K order (c,i,j) to match

@@ -32,6 +32,8 @@ class GemmArgs(C.Structure):
         ("pos_offset", c_int),
         ("m_dev", c_void_p), ("row_begin_dev", c_void_p), ("out_row_index", c_void_p), ("block_n", c_int), ("max_ctas", c_int),
         ("epilogue_mode", c_int), ("cta_pair", c_int),
+        ("xb_out", c_void_p), ("ldxb", c_longlong), ("row_stats", c_void_p),
+        ("ln_stats", c_void_p), ("ln_c1", c_void_p), ("ln_parts", c_int), ("ln_dim", c_int), ("ln_eps", c_float),
     ]
 
 
@@ -91,6 +93,8 @@ SIGNATURES: Dict[str, tuple] = {
     "pk_num_sms": (c_int, []),
     "pk_device_flag": (c_int, [c_int]),
     "pk_gemm_bf16": (c_int, [C.POINTER(GemmArgs), c_void_p]),
+    "pk_gemm_row_stat_parts": (c_int, [c_int]),
+    "pk_row_stats_cast": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pk_patchify": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pk_fill_token_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p]),
     "pk_layernorm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

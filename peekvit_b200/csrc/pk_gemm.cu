@@ -11,7 +11,7 @@
 //
 // Design (one CTA per SM, persistent over output tiles, warp-specialised):
 //   warp 0      TMA producer: A tile 128x64 and W tile BNx64 (128-byte swizzle) into a smem ring
-//   warp 1      MMA issuer: one thread issues tcgen05.mma 128xBNx16, accumulators in TMEM,
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma 128xBNx16, accumulators in TMEM,
 //               two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1
 //   warp 2      TMEM allocator
 //   warps 4-11  epilogue, two flavours:
@@ -123,37 +123,42 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
+    // (warp-uniform loop, one elected lane issues: see pk_gemm2.cu for why a lane-0 loop is slow)
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_blk = t / n_tiles, n_blk = t % n_tiles;
       bool ok = true;
-      for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
-        const int m_blk = t / n_tiles, n_blk = t % n_tiles;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          if (!mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u, p.flag, 0x100u + s)) { ok = false; break; }
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ok = __all_sync(0xffffffffu, mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u, p.flag, 0x100u + s));
+        if (!ok) break;
+        if (elect_one()) {
           const uint32_t fb = smem_u32(&full_bar[s]);
           mbar_expect_tx(fb, Cfg::kStageBytes);
           const uint32_t a_dst = smem_u32(smem_ab + s * Cfg::kStageBytes);
           tma_load_2d(a_dst, &tmap_a, fb, kb * kBK, row0 + m_blk * kBM);
           tma_load_2d(a_dst + Cfg::kABytes, &tmap_b, fb, kb * kBK, n_blk * BN);
-          if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
         }
+        __syncwarp();
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
       }
+      if (!ok) break;
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
-      int s = 0, as = 0;
-      uint32_t ph = 0, aph = 0;
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane)
+    constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+    int s = 0, as = 0;
+    uint32_t ph = 0, aph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&tempty_bar[as]), aph ^ 1u, p.flag, 0x200u + as))) break;
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
       bool ok = true;
-      for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
-        if (!mbar_wait(smem_u32(&tempty_bar[as]), aph ^ 1u, p.flag, 0x200u + as)) break;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ok = __all_sync(0xffffffffu, mbar_wait(smem_u32(&full_bar[s]), ph, p.flag, 0x300u + s));
+        if (!ok) break;
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          if (!mbar_wait(smem_u32(&full_bar[s]), ph, p.flag, 0x300u + s)) { ok = false; break; }
-          tcgen05_fence_after();
+        if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem_ab + s * Cfg::kStageBytes);
           const uint64_t a_desc = umma_desc_kmajor_sw128(a_addr);
           const uint64_t b_desc = umma_desc_kmajor_sw128(a_addr + Cfg::kABytes);
@@ -165,10 +170,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           umma_commit(smem_u32(&empty_bar[s]));            // frees the smem slot when these MMAs retire
           if (kb == num_kb - 1) umma_commit(smem_u32(&tfull_bar[as]));
-          if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
         }
-        if (++as == 2) { as = 0; aph ^= 1u; }
+        __syncwarp();
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
       }
+      if (!ok) break;
+      if (++as == 2) { as = 0; aph ^= 1u; }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue warps
@@ -510,6 +517,7 @@ int pick_block_n(int N) {
 // pk_gemm2.cu: CTA-pair (cta_group::2) kernel for plain row mappings
 bool pair_gemm_eligible(const pk_gemm_args* a);
 int launch_pair_gemm(const pk_gemm_args* a, cudaStream_t stream);
+int pair_row_stat_parts(int N);
 
 }  // namespace pk
 
@@ -527,6 +535,22 @@ extern "C" int pk_gemm_bf16(const pk_gemm_args* a, void* stream) {
     PK_REQUIRE(a->resid != nullptr && a->ldr % 4 == 0, "pk_gemm_bf16: residual epilogue needs resid with ldr %% 4 == 0");
   if (a->M == 0) return PK_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool ln_fused = a->xb_out != nullptr || a->ln_stats != nullptr;
+  if (ln_fused) {
+    PK_REQUIRE(pair_gemm_eligible(a) && a->cta_pair != 1 && a->block_n == 0,
+               "pk_gemm_bf16: the fused-LayerNorm epilogues need the CTA-pair kernel (contiguous rows, aligned, block_n auto)");
+    if (a->xb_out) {
+      PK_REQUIRE(a->epilogue == PK_EPI_BIAS_RESID_F32 && a->row_stats != nullptr && a->ldxb % 8 == 0 &&
+                     (reinterpret_cast<uintptr_t>(a->xb_out) & 15) == 0,
+                 "pk_gemm_bf16: xb_out needs the residual epilogue, row_stats and a 16-byte aligned bf16 buffer");
+    }
+    if (a->ln_stats) {
+      PK_REQUIRE((a->epilogue == PK_EPI_BIAS_BF16 || a->epilogue == PK_EPI_BIAS_GELU_BF16) && a->ln_c1 != nullptr && a->ln_parts > 0 &&
+                     a->ln_dim > 0,
+                 "pk_gemm_bf16: ln_stats needs a bf16 epilogue, ln_c1, ln_parts and ln_dim");
+    }
+    return launch_pair_gemm(a, s);
+  }
   if (a->cta_pair != 1 && pair_gemm_eligible(a) && (a->cta_pair == 2 || a->M > 256)) return launch_pair_gemm(a, s);
   PK_REQUIRE(a->cta_pair != 2, "pk_gemm_bf16: the CTA-pair kernel needs contiguous rows, 16-byte aligned rows and N %% 8 == 0");
   const int bn = a->block_n > 0 ? a->block_n : pick_block_n(a->N);
@@ -538,3 +562,5 @@ extern "C" int pk_gemm_bf16(const pk_gemm_args* a, void* stream) {
   set_last_error("pk_gemm_bf16: unsupported block_n %d", bn);
   return PK_ERR_INVALID;
 }
+
+extern "C" int pk_gemm_row_stat_parts(int N) { return N > 0 ? pk::pair_row_stat_parts(N) : 0; }

@@ -30,7 +30,11 @@ constexpr int kP_BufBytes = 4096;   // one 32-row x 128-byte staging tile
 // (cp.reduce.async.bulk.tensor .add, executed at L2) and the residual tile never visits shared memory.
 // EW epilogue warps per CTA: 8 (two per TMEM lane quarter, each owning half the tile's columns) or 16 (four per
 // quarter, a quarter of the columns each: the GELU epilogue is latency-bound with two warps per scheduler).
-template <int BN, int EPI, bool RED, int EW = 8>
+// LN: 0 = plain; 1 = LayerNorm *producer* (residual epilogue that also emits a bf16 copy of the new residual row and
+// per-row partial sums / sums of squares); 2 = LayerNorm *consumer* (bf16 epilogues whose A operand is that raw bf16 copy
+// and whose weights carry the LayerNorm gain: out = rstd*acc - rstd*mean*c1[n] + c2[n]).  Together they remove the separate
+// LayerNorm kernel: x -> LN -> Linear becomes one GEMM epilogue feeding the next GEMM (vit.py:48-55).
+template <int BN, int EPI, bool RED, int EW = 8, int LN = 0>
 struct PairCfg {
   static constexpr int kEpiWarps = EW;
   static constexpr int kThreads = 128 + EW * 32;
@@ -45,11 +49,14 @@ struct PairCfg {
   static constexpr int kStoreCols = 32 * kUnitsPerStore;
   static constexpr int kStoreSwizzle = kOutBf16 ? (kUnitsPerStore == 2 ? 128 : 64) : 128;
   static constexpr int kBufs = EW == 16 ? 1 : (kResid ? 3 : 2);               // staging buffers per epilogue warp
-  static_assert(EW == 8 || !kResid, "the staged-residual epilogue needs its 3-deep ring (8 epilogue warps)");
+  static_assert(EW != 16 || !kResid, "the staged-residual epilogue needs its 3-deep ring");
   static constexpr int kABytes = kP_BM * kP_BK * 2;
   static constexpr int kBBytes = (BN / 2) * kP_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = EW * kBufs * kP_BufBytes;
+  static constexpr int kSlotBytes = kP_BufBytes + (LN == 1 ? 2048 : 0);           // + a 32x32 bf16 tile for the LN producer
+  static constexpr int kStagingBytes = EW * kBufs * kSlotBytes;
+  static_assert(LN != 1 || (kResid && EW == 4), "the LN producer is the staged-residual epilogue with one warp per lane quarter");
+  static_assert(LN != 2 || kOutBf16, "the LN consumer is a bf16 epilogue");
   static constexpr int kBarBytes = 1024;
   static constexpr int kBudget = 232448 - 1024 - kBarBytes - kStagingBytes;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
@@ -70,6 +77,16 @@ struct PairParams {
   const float* rowscale;
   unsigned int* flag;
   int l2_prefetch;
+  // LayerNorm producer (LN == 1)
+  void* xb_out;            // bf16 copy of the result rows (partial-tile path; full tiles go through tmap_xb)
+  long long ldxb;
+  float* row_stats;        // [rows][stat_parts][2]: partial (sum, sum of squares) of this launch's column tile
+  int stat_parts;
+  // LayerNorm consumer (LN == 2)
+  const float* ln_stats;   // [rows][ln_parts][2]
+  const float* ln_c1;      // [N]: sum_k W'[n,k]
+  int ln_parts;
+  float ln_inv_dim, ln_eps;
   int debug;      // PK_GEMM_DEBUG bits (timing experiments only): 1 = no operand loads, 2 = no epilogue math/stores
 };
 
@@ -125,12 +142,12 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 }
 __device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
 
-template <int BN, int EPI, bool RED, int EW>
+template <int BN, int EPI, bool RED, int EW, int LN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + EW * 32, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-                      const PairParams p) {
-  using Cfg = PairCfg<BN, EPI, RED, EW>;
+                      const __grid_constant__ CUtensorMap tmap_xb, const PairParams p) {
+  using Cfg = PairCfg<BN, EPI, RED, EW, LN>;
   constexpr int kP_EpiWarps = EW;
   constexpr bool kOutBf16 = Cfg::kOutBf16;
   constexpr bool kResid = Cfg::kResid;
@@ -163,6 +180,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_out);
     if constexpr (kResid) tma_prefetch_desc(&tmap_res);
+    if constexpr (LN == 1) tma_prefetch_desc(&tmap_xb);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -286,7 +304,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     constexpr int kUPS = Cfg::kUnitsPerStore;
     constexpr int kChunks = Cfg::kChunks;
     constexpr int kBufs = Cfg::kBufs;
-    uint8_t* ebuf = staging + ew * kBufs * kP_BufBytes;                 // 1024-byte aligned
+    constexpr int kSlot = Cfg::kSlotBytes;
+    uint8_t* ebuf = staging + ew * kBufs * kSlot;                       // 1024-byte aligned
     const uint32_t ebuf_u32 = smem_u32(ebuf);
     uint64_t* rbar = res_bar + 3 * ew;
     const int my_tiles = pair < num_tiles ? (num_tiles - pair + num_pairs - 1) / num_pairs : 0;
@@ -297,7 +316,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       const uint32_t b = g % 3u;
       const uint32_t bar = smem_u32(&rbar[b]);
       mbar_expect_tx(bar, kP_BufBytes);
-      tma_load_2d(ebuf_u32 + b * kP_BufBytes, &tmap_res, bar, (tt % n_tiles) * BN + half * kPartCols + ch * Cfg::kStoreCols,
+      tma_load_2d(ebuf_u32 + b * kSlot, &tmap_res, bar, (tt % n_tiles) * BN + half * kPartCols + ch * Cfg::kStoreCols,
                   row0 + (tt / n_tiles) * 2 * kP_BM + row_in_pair);
     };
     if constexpr (kResid) {
@@ -323,6 +342,23 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       if constexpr (kResid || RED) {
         if (p.rowscale && grow < row_end) sc = p.rowscale[grow];
       }
+      float ln_alpha = 1.0f, ln_beta = 0.0f;       // LN consumer: out = alpha*acc + (beta*c1[n] + c2[n])
+      if constexpr (LN == 2) {
+        if (grow < row_end) {
+          float s1 = 0.f, s2 = 0.f;
+          const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + static_cast<long long>(grow) * p.ln_parts;
+          for (int i = 0; i < p.ln_parts; ++i) {
+            const float2 v2 = st[i];
+            s1 += v2.x;
+            s2 += v2.y;
+          }
+          const float mean = s1 * p.ln_inv_dim;
+          const float var = fmaxf(s2 * p.ln_inv_dim - mean * mean, 0.f);
+          ln_alpha = 1.0f / sqrtf(var + p.ln_eps);
+          ln_beta = -ln_alpha * mean;
+        }
+      }
+      float st_sum = 0.f, st_sq = 0.f;             // LN producer: this row's partial statistics over the tile's columns
       if (!mbar_wait(smem_u32(&tfull_bar[as]), aph, p.flag, 0x1400u + as)) { ok = false; break; }
       tcgen05_fence_after();
       const uint32_t t_col0 = t_lane + static_cast<uint32_t>(as * BN + half * kPartCols);
@@ -335,13 +371,20 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const int ch = u / kUPS;              // store chunk inside the tile
         const int sub = u % kUPS;             // unit inside the store chunk
         const uint32_t b = kBufs == 1 ? 0u : (kResid ? (g % 3u) : (g & 1u));
-        uint8_t* bufp = ebuf + b * kP_BufBytes;
+        uint8_t* bufp = ebuf + b * kSlot;
         const int col0 = (t % n_tiles) * BN + half * kPartCols + u * 32;     // first output column of this unit
         float4 bias4[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           bias4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.bias && col0 + 4 * j < p.N) bias4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
+          if constexpr (LN == 2) {
+            if (col0 + 4 * j < p.N) {
+              const float4 c1 = __ldg(reinterpret_cast<const float4*>(p.ln_c1 + col0 + 4 * j));
+              bias4[j].x = fmaf(c1.x, ln_beta, bias4[j].x); bias4[j].y = fmaf(c1.y, ln_beta, bias4[j].y);
+              bias4[j].z = fmaf(c1.z, ln_beta, bias4[j].z); bias4[j].w = fmaf(c1.w, ln_beta, bias4[j].w);
+            }
+          }
         }
         tmem_ld_wait();                                                     // unit u is in registers
         if (u + 1 < kUnits) {
@@ -362,11 +405,18 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             __syncwarp();
           }
         }
+        uint32_t xbp[LN == 1 ? 16 : 1];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 b4 = bias4[j];
-          float a0 = __uint_as_float(v[4 * j]) + b4.x, a1 = __uint_as_float(v[4 * j + 1]) + b4.y;
-          float a2 = __uint_as_float(v[4 * j + 2]) + b4.z, a3 = __uint_as_float(v[4 * j + 3]) + b4.w;
+          float a0, a1, a2, a3;
+          if constexpr (LN == 2) {
+            a0 = fmaf(__uint_as_float(v[4 * j]), ln_alpha, b4.x); a1 = fmaf(__uint_as_float(v[4 * j + 1]), ln_alpha, b4.y);
+            a2 = fmaf(__uint_as_float(v[4 * j + 2]), ln_alpha, b4.z); a3 = fmaf(__uint_as_float(v[4 * j + 3]), ln_alpha, b4.w);
+          } else {
+            a0 = __uint_as_float(v[4 * j]) + b4.x; a1 = __uint_as_float(v[4 * j + 1]) + b4.y;
+            a2 = __uint_as_float(v[4 * j + 2]) + b4.z; a3 = __uint_as_float(v[4 * j + 3]) + b4.w;
+          }
           if constexpr (EPI == PK_EPI_BIAS_GELU_BF16) {
             gelu_erf_x2(a0, a1);
             gelu_erf_x2(a2, a3);
@@ -378,6 +428,14 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           }
           if constexpr (RED) {
             a0 *= sc; a1 *= sc; a2 *= sc; a3 *= sc;
+          }
+          if constexpr (LN == 1) {
+            if (col0 + 4 * j < p.N) {
+              st_sum += (a0 + a1) + (a2 + a3);
+              st_sq += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+            }
+            xbp[2 * j] = pack_bf16(a0, a1);
+            xbp[2 * j + 1] = pack_bf16(a2, a3);
           }
           if constexpr (kOutBf16) {
             v[2 * j] = pack_bf16(a0, a1);
@@ -407,13 +465,21 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             for (int j = 0; j < 8; ++j)
               *reinterpret_cast<uint4*>(bufp + lane * 128 + ((j ^ (lane & 7)) << 4)) =
                   make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if constexpr (LN == 1) {
+              // bf16 copy: 64-byte rows, 16-byte chunk j of row r at chunk j ^ ((r >> 1) & 3) (SWIZZLE_64B)
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(bufp + kP_BufBytes + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                    make_uint4(xbp[4 * j], xbp[4 * j + 1], xbp[4 * j + 2], xbp[4 * j + 3]);
+            }
           }
           if (sub == kUPS - 1) {
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              if constexpr (RED) tma_reduce_add_2d(&tmap_out, ebuf_u32 + b * kP_BufBytes, col0 - sub * 32, row_base);
-              else tma_store_2d(&tmap_out, ebuf_u32 + b * kP_BufBytes, col0 - sub * 32, row_base);
+              if constexpr (RED) tma_reduce_add_2d(&tmap_out, ebuf_u32 + b * kSlot, col0 - sub * 32, row_base);
+              else tma_store_2d(&tmap_out, ebuf_u32 + b * kSlot, col0 - sub * 32, row_base);
+              if constexpr (LN == 1) tma_store_2d(&tmap_xb, ebuf_u32 + b * kSlot + kP_BufBytes, col0, row_base);
               bulk_commit();
             }
           }
@@ -441,6 +507,12 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 }
                 *reinterpret_cast<float4*>(orow + 4 * j) = o;
               }
+            if constexpr (LN == 1) {
+              __nv_bfloat16* xrow = static_cast<__nv_bfloat16*>(p.xb_out) + static_cast<long long>(grow) * p.ldxb + col0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (col0 + 8 * j < p.N) *reinterpret_cast<uint4*>(xrow + 8 * j) = make_uint4(xbp[4 * j], xbp[4 * j + 1], xbp[4 * j + 2], xbp[4 * j + 3]);
+            }
           }
         }
         if (sub == kUPS - 1) {
@@ -454,6 +526,11 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           }
           ++g;
         }
+      }
+      if constexpr (LN == 1) {
+        // this row's (sum, sum of squares) over the tile's BN columns -> slot n_blk of its statistics record
+        if (ok && grow < row_end)
+          reinterpret_cast<float2*>(p.row_stats)[static_cast<long long>(grow) * p.stat_parts + (t % n_tiles)] = make_float2(st_sum, st_sq);
       }
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
@@ -507,11 +584,11 @@ static int pair_debug() {
   return v;
 }
 
-template <int BN, int EPI, bool RED = false, int EW = 8>
+template <int BN, int EPI, bool RED = false, int EW = 8, int LN = 0>
 static int launch_pair(const pk_gemm_args* a, cudaStream_t stream) {
-  using Cfg = PairCfg<BN, EPI, RED, EW>;
+  using Cfg = PairCfg<BN, EPI, RED, EW, LN>;
   static bool attr_set = false;
-  auto kfn = gemm_bf16_pair_kernel<BN, EPI, RED, EW>;
+  auto kfn = gemm_bf16_pair_kernel<BN, EPI, RED, EW, LN>;
   if (!attr_set) {
     PK_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
@@ -532,7 +609,18 @@ static int launch_pair(const pk_gemm_args* a, cudaStream_t stream) {
                       32, 128);
     if (rc != PK_OK) return rc;
   }
+  CUtensorMap txb = tout;
+  if (LN == 1) {
+    rc = make_tmap_2d(&txb, a->xb_out, 2, static_cast<uint64_t>(a->M), static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->ldxb), 32,
+                      32, 64);
+    if (rc != PK_OK) return rc;
+  }
   PairParams p;
+  p.xb_out = a->xb_out; p.ldxb = a->ldxb; p.row_stats = a->row_stats;
+  p.stat_parts = (a->N + BN - 1) / BN;
+  p.ln_stats = a->ln_stats; p.ln_c1 = a->ln_c1; p.ln_parts = a->ln_parts;
+  p.ln_inv_dim = a->ln_dim > 0 ? 1.0f / static_cast<float>(a->ln_dim) : 0.f;
+  p.ln_eps = a->ln_eps;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.m_dev = a->m_dev;
   p.row_begin_dev = a->row_begin_dev;
@@ -547,20 +635,24 @@ static int launch_pair(const pk_gemm_args* a, cudaStream_t stream) {
   const int sms = a->max_ctas > 0 ? a->max_ctas : num_sms();
   if (pairs > sms / 2) pairs = sms / 2;
   if (pairs < 1) pairs = 1;
-  kfn<<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tout, tres, p);
+  kfn<<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tout, tres, txb, p);
   return check_cuda(cudaGetLastError(), "gemm_bf16_pair_kernel launch");
 }
 
 template <int BN>
 static int dispatch_pair_epi(const pk_gemm_args* a, cudaStream_t stream) {
   switch (a->epilogue) {
-    case PK_EPI_BIAS_BF16: return launch_pair<BN, PK_EPI_BIAS_BF16>(a, stream);
+    case PK_EPI_BIAS_BF16:
+      if (a->ln_stats) return launch_pair<BN, PK_EPI_BIAS_BF16, false, 8, 2>(a, stream);
+      return launch_pair<BN, PK_EPI_BIAS_BF16>(a, stream);
     case PK_EPI_BIAS_GELU_BF16:
+      if (a->ln_stats) return launch_pair<BN, PK_EPI_BIAS_GELU_BF16, false, 8, 2>(a, stream);
       if constexpr (BN != 192) {
         if (pair_gelu_warps() == 16) return launch_pair<BN, PK_EPI_BIAS_GELU_BF16, false, 16>(a, stream);
       }
       return launch_pair<BN, PK_EPI_BIAS_GELU_BF16>(a, stream);
     case PK_EPI_BIAS_RESID_F32:
+      if (a->xb_out) return launch_pair<BN, PK_EPI_BIAS_RESID_F32, false, 4, 1>(a, stream);
       // in-place residual (x += ...): let the TMA reduction do the add at L2
       if (a->resid == a->out && a->ldr == a->ldo && pair_tma_reduce()) return launch_pair<BN, PK_EPI_BIAS_RESID_F32, true>(a, stream);
       return launch_pair<BN, PK_EPI_BIAS_RESID_F32>(a, stream);
@@ -593,6 +685,12 @@ bool pair_gemm_eligible(const pk_gemm_args* a) {
   if (a->N % 8 != 0) return false;
   if (a->epilogue == PK_EPI_BIAS_RESID_F32 && ((a->ldr * 4) % 16 != 0 || (reinterpret_cast<uintptr_t>(a->resid) & 15) != 0)) return false;
   return true;
+}
+
+// Number of per-row statistics slots the LN-producer epilogue writes for an N-column output (= column tiles).
+int pair_row_stat_parts(int N) {
+  const int bn = pick_pair_block_n(N);
+  return (N + bn - 1) / bn;
 }
 
 int launch_pair_gemm(const pk_gemm_args* a, cudaStream_t stream) {

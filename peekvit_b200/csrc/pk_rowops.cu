@@ -323,6 +323,36 @@ extern "C" int pk_cls_head(const float* x, int batch, int seq_len, const int* cu
   return check_cuda(cudaGetLastError(), "cls_head_kernel");
 }
 
+// ------------------------------------------------------------------ LayerNorm statistics + raw bf16 copy (fused-LN GEMM chain)
+__global__ void __launch_bounds__(256)
+row_stats_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, float* __restrict__ stats, int rows, int dim, int parts) {
+  const int lane = lane_id(), d4 = dim / 4;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int r = blockIdx.x * (blockDim.x >> 5) + warp_id(); r < rows; r += warps_total) {
+    const float4* src = reinterpret_cast<const float4*>(x + static_cast<long long>(r) * dim);
+    uint2* dst = reinterpret_cast<uint2*>(xb + static_cast<long long>(r) * dim);
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < d4; c += 32) {
+      const float4 v = src[c];
+      s1 += (v.x + v.y) + (v.z + v.w);
+      s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      dst[c] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    float2* st = reinterpret_cast<float2*>(stats) + static_cast<long long>(r) * parts;
+    if (lane < parts) st[lane] = lane == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
+  }
+}
+
+extern "C" int pk_row_stats_cast(const float* x, void* xb, float* row_stats, int rows, int dim, int parts, void* stream) {
+  PK_REQUIRE(x && xb && row_stats && dim % 4 == 0 && parts >= 1 && parts <= 32 && rows >= 0, "pk_row_stats_cast: bad arguments");
+  if (rows == 0) return PK_OK;
+  row_stats_cast_kernel<<<grid_for(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(xb), row_stats, rows, dim, parts);
+  return check_cuda(cudaGetLastError(), "row_stats_cast_kernel");
+}
+
 // ------------------------------------------------------------------ eval-loop accuracy (validate/test.py:116-129)
 // One warp per sample: first-maximum arg-max over the classes (torch.argmax semantics; NaN logits never win),
 // compared with the label; counts[0] += #correct, counts[1] += #samples (64-bit atomics).

@@ -18,8 +18,17 @@ from typing import Any, Dict, List, Optional, Sequence, Union
 
 import torch
 
+import os
+
 from . import ops
 from ._lib import PK_EPI_BIAS_BF16, PK_EPI_BIAS_F32, PK_EPI_BIAS_GELU_BF16, PK_EPI_BIAS_RESID_F32
+
+
+# LayerNorm folded across GEMMs: 0 = separate LayerNorm kernels everywhere; 1 = ln_1 folded into the in-projection (the
+# previous layer's fc2 epilogue emits the bf16 row copy + statistics), ln_2 a kernel; 2 = both folded.  Measured on ViT-B/16
+# (B200, 256-image micro-batch): the GELU epilogue of fc1 is on the critical path of that GEMM, so folding ln_2 into it costs
+# more (+41 us) than the LayerNorm kernel it removes (42 us) -> default 1.
+LN_FOLD = int(os.environ.get("PEEKVIT_B200_LN_FOLD", "1"))
 
 
 def _f32(t: torch.Tensor) -> torch.Tensor:
@@ -104,6 +113,21 @@ def _pack_mlp(mlp) -> MlpWeights:
     return MlpWeights(_bf16(mlp.fc1.weight), _f32(mlp.fc1.bias), _bf16(mlp.fc2.weight), _f32(mlp.fc2.bias))
 
 
+def _pack_ln_fold(blk) -> Dict[str, torch.Tensor]:
+    """Operands of the LayerNorm-fused GEMM chain (include/peekvit_b200.h, pk_gemm_args.ln_*):
+    LN(x) @ W^T + b  ==  rstd * (x @ (gamma*W)^T) - rstd*mean * c1 + c2  with  c1 = sum_k (gamma*W)[n,k],
+    c2 = b + W @ beta.  The gain is folded into the bf16 weight from the fp32 master; c1 sums the *rounded*
+    folded weight so the mean term cancels exactly what the tensor core accumulates."""
+    def fold(w, b, g, be):
+        w32, g32, be32 = w.detach().float(), g.detach().float(), be.detach().float()
+        wf = (w32 * g32[None, :]).to(torch.bfloat16).contiguous()
+        return wf, wf.float().sum(1).contiguous(), (b.detach().float() + w32 @ be32).contiguous()
+    mha = blk.self_attention.self_attention
+    w_qkv, c1_qkv, c2_qkv = fold(mha.in_proj_weight, mha.in_proj_bias, blk.ln_1.weight, blk.ln_1.bias)
+    w_fc1, c1_fc1, c2_fc1 = fold(blk.mlp.fc1.weight, blk.mlp.fc1.bias, blk.ln_2.weight, blk.ln_2.bias)
+    return dict(w_qkv=w_qkv, c1_qkv=c1_qkv, c2_qkv=c2_qkv, w_fc1=w_fc1, c1_fc1=c1_fc1, c2_fc1=c2_fc1)
+
+
 def _block_kind(blk) -> str:
     name = type(blk).__name__
     return {"ViTBlock": "vit", "RankViTBlock": "rank", "ResidualViTBlock": "residual", "AViTBlock": "avit",
@@ -146,6 +170,8 @@ def pack_model(model, family: str) -> PackedModel:
                     extra["bt_gate_b"] = float(blk.budget_token_gate.bias.detach().float().cpu()[0])
         if kind == "avit":
             extra.update(gate_scale=float(blk.gate_scale), gate_center=float(blk.gate_center))
+        if kind in ("vit", "rank"):
+            extra["fold"] = _pack_ln_fold(blk)
         layers.append(LayerWeights(kind, _f32(blk.ln_1.weight), _f32(blk.ln_1.bias), _f32(blk.ln_2.weight), _f32(blk.ln_2.bias),
                                    float(blk.ln_1.eps), attn, mlps, extra, blk))
     D = model.hidden_dim
@@ -263,6 +289,43 @@ class Forward:
         self.attn_part(x, lw, rows, batch, seq=seq)
         self.mlp_part(x, lw, rows)
 
+    # ---- LayerNorm fused across GEMMs (dense layers of ViT / RankViT)
+    def fold_ok(self, rows: int) -> bool:
+        """The fused chain runs on the CTA-pair GEMM: more than one 256-row tile and 16-byte aligned rows."""
+        return LN_FOLD > 0 and rows > 256 and self.pm.dim % 8 == 0
+
+    def fold_begin(self, x: torch.Tensor, rows: int):
+        """bf16 copy + row statistics of a residual stream that did not come out of a producer GEMM."""
+        D = self.pm.dim
+        xb = self.ws.get("xb", (rows, D), torch.bfloat16)
+        stats = self.ws.get("ln_stats", (rows, ops.gemm_row_stat_parts(D), 2), torch.float32)
+        ops.row_stats_cast(x, xb, stats, rows)
+        return xb, stats
+
+    def dense_block_fused(self, x, lw: LayerWeights, rows: int, batch: int, seq: int, xb, stats, emit_last: bool) -> None:
+        """ViTBlock (vit.py:45-55) without LayerNorm kernels: ln_1 / ln_2 are folded into the in-proj and fc1 GEMMs
+        (gain in the weight, mean / rstd applied in the epilogue from per-row statistics) and the out-proj / fc2
+        epilogues emit the bf16 copy and the statistics of the row they just produced."""
+        pm, ws = self.pm, self.ws
+        D = pm.dim
+        aw, mw, f = lw.attn[0], lw.mlp[0], lw.extra["fold"]
+        F = mw.w_fc1.shape[0]
+        qkv = ops.gemm(xb, f["w_qkv"], f["c2_qkv"], ws.get("qkv", (rows, 3 * D), torch.bfloat16), PK_EPI_BIAS_BF16,
+                       ln_stats=stats, ln_c1=f["c1_qkv"], ln_dim=D, ln_eps=lw.eps)
+        att = ops.attention(qkv, ws.get("att", (rows, D), torch.bfloat16), batch, pm.heads, D // pm.heads, seq_len=seq)
+        if LN_FOLD >= 2:
+            ops.gemm(att, aw.w_o, aw.b_o, x[:rows], PK_EPI_BIAS_RESID_F32, resid=x[:rows], xb_out=xb, row_stats=stats)
+            hid = ops.gemm(xb, f["w_fc1"], f["c2_fc1"], ws.get("hid", (rows, F), torch.bfloat16), PK_EPI_BIAS_GELU_BF16,
+                           ln_stats=stats, ln_c1=f["c1_fc1"], ln_dim=D, ln_eps=lw.eps)
+        else:
+            ops.gemm(att, aw.w_o, aw.b_o, x[:rows], PK_EPI_BIAS_RESID_F32, resid=x[:rows])
+            a = ops.layernorm(x, lw.ln2_w, lw.ln2_b, lw.eps, ws.get("ln", (rows, D), torch.bfloat16), rows=rows)
+            hid = ops.gemm(a, mw.w_fc1, mw.b_fc1, ws.get("hid", (rows, F), torch.bfloat16), PK_EPI_BIAS_GELU_BF16)
+        if emit_last:
+            ops.gemm(hid, mw.w_fc2, mw.b_fc2, x[:rows], PK_EPI_BIAS_RESID_F32, resid=x[:rows], xb_out=xb, row_stats=stats)
+        else:
+            ops.gemm(hid, mw.w_fc2, mw.b_fc2, x[:rows], PK_EPI_BIAS_RESID_F32, resid=x[:rows])
+
     def head(self, x: torch.Tensor, batch: int, seq: int, cu_seqlens=None, n_cls: Optional[int] = None) -> torch.Tensor:
         pm = self.pm
         return ops.cls_head(x, batch, seq, pm.n_cls if n_cls is None else n_cls, pm.ln_w, pm.ln_b, pm.ln_eps, pm.head_w, pm.head_b,
@@ -281,8 +344,14 @@ class Forward:
         pm = self.pm
         B, seq = images.shape[0], pm.seq_len
         x = self.embed(images)
-        for lw in pm.layers:
-            self.dense_block(x, lw, B * seq, B, seq)
+        rows = B * seq
+        if self.fold_ok(rows) and all("fold" in lw.extra for lw in pm.layers):
+            xb, stats = self.fold_begin(x, rows)
+            for i, lw in enumerate(pm.layers):
+                self.dense_block_fused(x, lw, rows, B, seq, xb, stats, emit_last=i + 1 < len(pm.layers))
+        else:
+            for lw in pm.layers:
+                self.dense_block(x, lw, rows, B, seq)
         return self.head(x, B, seq)
 
     # ---------------------------------------------------------------- RankViT

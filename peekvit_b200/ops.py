@@ -57,7 +57,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
          rows_per_group: int = 0, group_stride: int = 0, group_offset: int = 0, resid_is_pos: bool = False,
          pos_offset: Optional[int] = None, m_dev: Optional[torch.Tensor] = None, row_begin_dev: Optional[torch.Tensor] = None,
          out_row_index: Optional[torch.Tensor] = None, block_n: int = 0, max_ctas: int = 0,
-         m: Optional[int] = None, epilogue_mode: int = 0, cta_pair: int = 0) -> torch.Tensor:
+         m: Optional[int] = None, epilogue_mode: int = 0, cta_pair: int = 0,
+         xb_out: Optional[torch.Tensor] = None, row_stats: Optional[torch.Tensor] = None,
+         ln_stats: Optional[torch.Tensor] = None, ln_c1: Optional[torch.Tensor] = None, ln_dim: int = 0, ln_eps: float = 0.0) -> torch.Tensor:
     """out = epilogue(a @ w.T + bias): a bf16 [M,K], w bf16 [N,K] (nn.Linear layout)."""
     lib = _lib_for(a)
     lda, ldw, ldo = _rowmajor(a, "a"), _rowmajor(w, "w"), _rowmajor(out, "out")
@@ -85,6 +87,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
     args.block_n, args.max_ctas = block_n, max_ctas
     args.epilogue_mode = epilogue_mode
     args.cta_pair = cta_pair
+    args.xb_out = _ptr(xb_out, torch.bfloat16)
+    args.ldxb = _rowmajor(xb_out, "xb_out") if xb_out is not None else 0
+    args.row_stats = _ptr(row_stats, torch.float32)
+    args.ln_stats = _ptr(ln_stats, torch.float32)
+    args.ln_c1 = _ptr(ln_c1, torch.float32)
+    args.ln_parts = ln_stats.shape[1] if ln_stats is not None else 0
+    args.ln_dim, args.ln_eps = ln_dim, ln_eps
     if gemm_timeline is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -324,3 +333,16 @@ def scatter_add_rows(x: torch.Tensor, y: torch.Tensor, src_of: torch.Tensor, row
     check(lib.pk_scatter_add_rows(_ptr(x, torch.float32), _ptr(y, torch.float32), _ptr(src_of, torch.int32), n, x.shape[-1], _stream()),
           "pk_scatter_add_rows")
     return x
+
+
+def gemm_row_stat_parts(n: int) -> int:
+    """Statistics slots per row written by the LayerNorm-producer epilogue for an n-column output."""
+    return int(_lib.load().pk_gemm_row_stat_parts(n))
+
+
+def row_stats_cast(x: torch.Tensor, xb: torch.Tensor, stats: torch.Tensor, rows: Optional[int] = None) -> None:
+    """xb = bf16(x), stats[r][0] = (sum, sum of squares) of row r, other slots zero."""
+    lib = _lib_for(x)
+    n = x.shape[0] if rows is None else rows
+    check(lib.pk_row_stats_cast(_ptr(x, torch.float32), _ptr(xb, torch.bfloat16), _ptr(stats, torch.float32), n, x.shape[-1],
+                                stats.shape[1], _stream()), "pk_row_stats_cast")

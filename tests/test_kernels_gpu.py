@@ -449,3 +449,50 @@ def test_argmax_count(ops):
     assert counts.tolist() == [exp, 1010]
     small = torch.tensor([[1.0, 3.0, 3.0], [float("nan"), 0.0, -1.0]], device=DEV)
     assert ops.argmax_count(small).tolist() == [1, 1]
+
+
+@pytest.mark.parametrize("shape", [(1000, 768, 3072), (788, 384, 1536), (50432 // 8, 768, 2304), (300, 256, 768)])
+def test_gemm_layernorm_fused_chain(ops, shape):
+    """out-proj(+residual) -> LayerNorm -> fc1(+GELU) as two GEMMs with the LayerNorm folded across them
+    (producer epilogue: bf16 copy + row statistics; consumer epilogue: rstd / mean / folded gain), against the
+    fp32 expression x1 = x0 + att Wo^T + bo; y = gelu(LN(x1) W1^T + b1)  (vit.py:48-55)."""
+    from peekvit_b200._lib import PK_EPI_BIAS_BF16, PK_EPI_BIAS_GELU_BF16, PK_EPI_BIAS_RESID_F32
+    M, D, F = shape
+    g = torch.Generator(device=DEV).manual_seed(M + D)
+    att = (torch.randn(M, D, device=DEV, generator=g) * 0.5).to(torch.bfloat16)
+    wo = (torch.randn(D, D, device=DEV, generator=g) / math.sqrt(D)).to(torch.bfloat16)
+    bo = torch.randn(D, device=DEV, generator=g) * 0.1
+    x0 = torch.randn(M, D, device=DEV, generator=g) * 2 + 0.3            # non-zero mean: the fold must cancel it
+    gamma = 1 + 0.2 * torch.randn(D, device=DEV, generator=g)
+    beta = 0.1 * torch.randn(D, device=DEV, generator=g)
+    w1 = torch.randn(F, D, device=DEV, generator=g) / math.sqrt(D)
+    b1 = torch.randn(F, device=DEV, generator=g) * 0.1
+    eps = 1e-5
+    x1_ref = x0 + att.float() @ wo.float().t() + bo
+    ln_ref = torch.nn.functional.layer_norm(x1_ref, (D,), gamma, beta, eps)
+    lin_ref = ln_ref @ w1.t() + b1
+    # ours
+    P = ops.gemm_row_stat_parts(D)
+    x = x0.clone()
+    xb = torch.full((M, D), float("nan"), device=DEV, dtype=torch.bfloat16)
+    stats = torch.full((M, P, 2), float("nan"), device=DEV)
+    ops.gemm(att, wo, bo, x, PK_EPI_BIAS_RESID_F32, resid=x, xb_out=xb, row_stats=stats)
+    assert ops.device_flag() == 0
+    assert rel_err(x, x1_ref) < TOL_F32
+    assert rel_err(xb, x1_ref) < TOL_BF16
+    s = stats.sum(1)
+    assert rel_err(s[:, 0], x1_ref.sum(1)) < 1e-4 and rel_err(s[:, 1], (x1_ref * x1_ref).sum(1)) < 1e-4
+    w1f = (w1 * gamma[None, :]).to(torch.bfloat16)
+    c1 = w1f.float().sum(1)
+    c2 = b1 + w1 @ beta
+    out = torch.empty(M, F, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(xb, w1f, c2, out, PK_EPI_BIAS_BF16, ln_stats=stats, ln_c1=c1, ln_dim=D, ln_eps=eps)
+    assert rel_err(out, lin_ref) < TOL_BF16
+    ops.gemm(xb, w1f, c2, out, PK_EPI_BIAS_GELU_BF16, ln_stats=stats, ln_c1=c1, ln_dim=D, ln_eps=eps)
+    assert rel_err(out, torch.nn.functional.gelu(lin_ref)) < TOL_BF16
+    # statistics of rows that do not come from a producer GEMM
+    xb2 = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    st2 = torch.full((M, P, 2), float("nan"), device=DEV)
+    ops.row_stats_cast(x1_ref.contiguous(), xb2, st2)
+    assert rel_err(st2.sum(1)[:, 0], x1_ref.sum(1)) < 1e-5 and torch.equal(xb2, x1_ref.to(torch.bfloat16))
+    assert ops.device_flag() == 0
