@@ -223,7 +223,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // 128x256 tile).  Abramowitz–Stegun 7.1.28:  erfc(z) = 1 / (1 + a1 z + ... + a6 z^6)^16,  |err| <= 3e-7, z >= 0.
 //   h = 0.5*erfc(|x|/sqrt2);  gelu(x) = x * (0.5 + sign(x) * (0.5 - h))
 __device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1) {
-  const uint64_t z = f2_mul(f2_pack(fabsf(x0), fabsf(x1)), f2_pack(0.70710678118654752f, 0.70710678118654752f));
+  const uint64_t ax = f2_pack(fabsf(x0), fabsf(x1));
+  const uint64_t z = f2_mul(ax, f2_pack(0.70710678118654752f, 0.70710678118654752f));
   uint64_t s = f2_fma(f2_pack(0.0000430638f, 0.0000430638f), z, f2_pack(0.0002765672f, 0.0002765672f));
   s = f2_fma(s, z, f2_pack(0.0001520143f, 0.0001520143f));
   s = f2_fma(s, z, f2_pack(0.0092705272f, 0.0092705272f));
@@ -238,12 +239,8 @@ __device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1) {
   f2_unpack(s, s0, s1);
   const uint64_t r = f2_pack(rcp_approx(s0), rcp_approx(s1));                                      // erfc(z)
   const uint64_t g = f2_fma(r, f2_pack(-0.5f, -0.5f), f2_pack(0.5f, 0.5f));                        // 0.5 - h  (>= 0)
-  float g0, g1;
-  f2_unpack(g, g0, g1);
-  g0 = copysignf(g0, x0);
-  g1 = copysignf(g1, x1);
-  const uint64_t x = f2_pack(x0, x1);
-  const uint64_t o = f2_fma(x, f2_pack(g0, g1), f2_mul(x, f2_pack(0.5f, 0.5f)));
+  // x*(0.5 + sign(x)*g) = 0.5*x + |x|*g : no sign transfer needed
+  const uint64_t o = f2_fma(ax, g, f2_mul(f2_pack(x0, x1), f2_pack(0.5f, 0.5f)));
   f2_unpack(o, x0, x1);
 }
 

@@ -414,8 +414,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             a0 = fmaf(__uint_as_float(v[4 * j]), ln_alpha, b4.x); a1 = fmaf(__uint_as_float(v[4 * j + 1]), ln_alpha, b4.y);
             a2 = fmaf(__uint_as_float(v[4 * j + 2]), ln_alpha, b4.z); a3 = fmaf(__uint_as_float(v[4 * j + 3]), ln_alpha, b4.w);
           } else {
-            a0 = __uint_as_float(v[4 * j]) + b4.x; a1 = __uint_as_float(v[4 * j + 1]) + b4.y;
-            a2 = __uint_as_float(v[4 * j + 2]) + b4.z; a3 = __uint_as_float(v[4 * j + 3]) + b4.w;
+            f2_unpack(f2_add(f2_pack(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), f2_pack(b4.x, b4.y)), a0, a1);
+            f2_unpack(f2_add(f2_pack(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), f2_pack(b4.z, b4.w)), a2, a3);
           }
           if constexpr (EPI == PK_EPI_BIAS_GELU_BF16) {
             gelu_erf_x2(a0, a1);

@@ -365,6 +365,8 @@ class Forward:
         B, seq, D = images.shape[0], pm.seq_len, pm.dim
         x = self.embed(images)
         flip = 0
+        fold = None                                  # (xb, stats) of the current residual stream when valid
+        L = len(pm.layers)
         for i, lw in enumerate(pm.layers):
             b = budgets.get(i, 1.0) if lw.kind == "rank" else 1.0
             if lw.kind == "rank" and b != 1:
@@ -379,9 +381,17 @@ class Forward:
                     aux.setdefault("scores", {})[i] = scores.clone()
                     aux.setdefault("kept", {})[i] = kept.clone()
                 x, seq = y, k + 1
+                fold = None                          # new rows: the bf16 copy / statistics are stale
             if aux is not None:
                 aux.setdefault("seq_lens", []).append(seq)
-            self.dense_block(x, lw, B * seq, B, seq)
+            rows = B * seq
+            if self.fold_ok(rows) and "fold" in lw.extra:
+                if fold is None:
+                    fold = self.fold_begin(x, rows)
+                self.dense_block_fused(x, lw, rows, B, seq, fold[0], fold[1], emit_last=i + 1 < L)
+            else:
+                self.dense_block(x, lw, rows, B, seq)
+                fold = None
         return self.head(x, B, seq)
 
     # ---------------------------------------------------------------- ResidualViT
