@@ -13,7 +13,7 @@ import torch
 
 from . import engine
 
-DEFAULT_MICRO_BATCH = int(os.environ.get("PEEKVIT_B200_MICRO_BATCH", "256"))
+DEFAULT_MICRO_BATCH = int(os.environ.get("PEEKVIT_B200_MICRO_BATCH", "512"))
 
 
 def _state(model):
