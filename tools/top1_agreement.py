@@ -1,0 +1,24 @@
+"""Top-1 agreement and logit error of the CUDA path against the fp32 CPU oracle on N ViT-B/16 images."""
+import os, sys, time, json
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import peekvit_oracle as po, weights as ow
+from peekvit_b200.models import VisionTransformer
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+cfg = dict(image_size=224, patch_size=16, num_layers=12, num_heads=12, hidden_dim=768, mlp_dim=3072, num_classes=1000)
+sd = ow.make_state_dict("vit", cfg, seed=4321)
+images = ow.synthetic_images(N, 224, seed=1234)
+t0 = time.time()
+ref = torch.cat([po.forward("vit", sd, cfg, images[s:s + 32])[0] for s in range(0, N, 32)])
+t_cpu = time.time() - t0
+model = VisionTransformer(**cfg); model.load_state_dict(sd); model = model.cuda().eval()
+logits = model(images.cuda()).cpu()
+err = ((logits - ref).abs().max() / ref.abs().max()).item()
+agree = (logits.argmax(1) == ref.argmax(1)).float().mean().item()
+top2 = ref.topk(2, dim=1).values
+margin = (top2[:, 0] - top2[:, 1])
+dis = (logits.argmax(1) != ref.argmax(1)).nonzero().flatten()
+print(json.dumps(dict(images=N, rel_err=err, top1_agreement=agree, disagreements=int(dis.numel()),
+                      oracle_margin_at_disagreements=[round(float(margin[i]), 5) for i in dis[:8]],
+                      median_margin=float(margin.median()), max_abs_logit=float(ref.abs().max()), cpu_s=round(t_cpu, 1))))
