@@ -82,11 +82,48 @@ struct ResidualGateParams {
   float* mdrop;              // [B] multiplicity folded into the virtual key / ghost row
 };
 
+// Pass 1 (gated layers), one warp per packed row across the whole grid: the gate's GEMV and sigmoid
+//   g[r] = sigmoid((w.x_r + b)/temp + gate_bias)   (sigmoid gate)    or    round(sigmoid(w.x_r + b))   (gumbel gate in eval)
+// left in mask[r].  Streaming the rows grid-wide instead of one CTA per sample is what makes this HBM-bound
+// (the per-sample version reached 0.37 of the measured HBM peak).
+__global__ void __launch_bounds__(256)
+residual_gate_rows_kernel(const ResidualGateParams p, int batch) {
+  const int lane = lane_id(), d4 = p.dim / 4;
+  const int rows = p.cu_in[batch];
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const float4* __restrict__ w4 = reinterpret_cast<const float4*>(p.gate_w);
+  // four rows per warp iteration, all loads issued before the first reduction (memory-level parallelism)
+  for (int r0 = (blockIdx.x * (blockDim.x >> 5) + warp_id()) * 4; r0 < rows; r0 += warps_total * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = lane; c < d4; c += 32) {
+      const float4 wv = __ldg(w4 + c);
+      float4 xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        xv[u] = r0 + u < rows ? *reinterpret_cast<const float4*>(p.x + static_cast<long long>(r0 + u) * p.dim + c * 4)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] += (xv[u].x * wv.x + xv[u].y * wv.y) + (xv[u].z * wv.z + xv[u].w * wv.w);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (r0 + u >= rows) break;
+      const float logit = warp_sum(acc[u]) + p.gate_b;
+      float g;
+      if (p.gate_type == 0) g = sigmoidf_exact(logit * p.inv_temp + p.gate_bias);
+      else g = rintf(sigmoidf_exact(logit));
+      if (lane == 0) p.mask[r0 + u] = g;
+    }
+  }
+}
+
+// Pass 2, one CTA per sample: threshold from the budget token, soft mask, keep decisions, positions in the compacted
+// sample, new length (+1 ghost slot when gated) and the multiplicity folded into the virtual key / ghost row.
 __global__ void __launch_bounds__(256)
 residual_gate_plan_kernel(const ResidualGateParams p) {
   extern __shared__ unsigned char s_keep[];
   __shared__ float s_thr, s_drop[8];
-  const int b = blockIdx.x, lane = lane_id(), warp = warp_id();
+  const int b = blockIdx.x, lane = lane_id(), warp = warp_id(), tid = threadIdx.x;
   const long long start = p.cu_in[b];
   const int len = p.cu_in[b + 1] - p.cu_in[b];
   const int d4 = p.dim / 4;
@@ -99,49 +136,24 @@ residual_gate_plan_kernel(const ResidualGateParams p) {
   __syncthreads();
   const float thr = s_thr;
   float dropped = 0.f;
-  // Four rows per warp iteration with all their loads issued before the first reduction: a one-row-at-a-time
-  // loop is a chain of exposed DRAM round trips (measured 18.5 us per layer on ViT-S, B=256).
-  const float4* __restrict__ w4 = reinterpret_cast<const float4*>(p.gate_w);
-  for (int j0 = warp; j0 < len; j0 += 32) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (p.gated) {
-      for (int c = lane; c < d4; c += 32) {
-        const float4 wv = __ldg(w4 + c);
-        float4 xv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = j0 + 8 * u;
-          xv[u] = (j < len && j >= p.n_special) ? *reinterpret_cast<const float4*>(p.x + (start + j) * p.dim + c * 4)
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] += (xv[u].x * wv.x + xv[u].y * wv.y) + (xv[u].z * wv.z + xv[u].w * wv.w);
+  for (int j = tid; j < len; j += blockDim.x) {
+    const long long r = start + j;
+    const float mult = p.mult_in[r];
+    float m = 1.0f;
+    bool keep = true;
+    if (j >= p.n_special) {
+      if (p.gated) {
+        const float g = p.mask[r];                                  // pass 1
+        m = p.gate_type == 0 ? fmaxf(g - thr, 0.f) : g;
       }
+      keep = (m > 0.f) && (mult > 0.f);
+      if (!keep) dropped += mult;
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = j0 + 8 * u;
-      if (j >= len) break;                       // warp-uniform
-      const long long r = start + j;
-      const float mult = p.mult_in[r];
-      float m = 1.0f;
-      bool keep = true;
-      if (j >= p.n_special) {
-        if (p.gated) {
-          const float logit = warp_sum(acc[u]) + p.gate_b;
-          if (p.gate_type == 0) m = fmaxf(sigmoidf_exact(logit * p.inv_temp + p.gate_bias) - thr, 0.f);
-          else m = rintf(sigmoidf_exact(logit));
-        }
-        keep = (m > 0.f) && (mult > 0.f);
-        if (!keep) dropped += mult;
-      }
-      if (lane == 0) {
-        p.mask[r] = m;
-        p.sample_of[r] = b;
-        s_keep[j] = keep ? 1 : 0;
-      }
-    }
+    p.mask[r] = m;
+    p.sample_of[r] = b;
+    s_keep[j] = keep ? 1 : 0;
   }
+  dropped = warp_sum(dropped);
   if (lane == 0) s_drop[warp] = dropped;
   __syncthreads();
   if (warp == 0) {
@@ -478,7 +490,12 @@ extern "C" int pk_residual_gate_plan(const pk_residual_gate_args* a, void* strea
   p.bt_w = a->bt_w; p.bt_b = a->bt_b; p.thr_dev = a->thr_dev; p.thr_const = a->thr_const;
   p.gated = a->gated;
   p.mask = a->mask; p.dst_local = a->dst_local; p.sample_of = a->sample_of; p.new_len = a->new_len; p.mdrop = a->mdrop;
-  residual_gate_plan_kernel<<<a->batch, 256, static_cast<size_t>(a->max_seq_len), static_cast<cudaStream_t>(stream)>>>(p);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a->gated) {
+    residual_gate_rows_kernel<<<grid_rows(static_cast<long long>(a->batch) * a->max_seq_len), 256, 0, s>>>(p, a->batch);
+    PK_CHECK_CUDA(cudaGetLastError());
+  }
+  residual_gate_plan_kernel<<<a->batch, 256, static_cast<size_t>(a->max_seq_len), s>>>(p);
   return check_cuda(cudaGetLastError(), "residual_gate_plan_kernel");
 }
 
