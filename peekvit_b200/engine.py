@@ -238,6 +238,14 @@ class Forward:
 
     def __init__(self, pm: PackedModel, ws: Workspace):
         self.pm, self.ws = pm, ws
+        # set by the CUDA-graph runner: the im2col of the current micro-batch is already in the workspace, so the captured
+        # sequence does not depend on where the caller's image tensor lives
+        self.patches_ready = False
+
+    def patchify(self, images: torch.Tensor) -> torch.Tensor:
+        pm = self.pm
+        B, P = images.shape[0], pm.num_patches
+        return ops.patchify(images, pm.patch_size, self.ws.get("patches", (B * P, pm.w_patch.shape[1]), torch.bfloat16))
 
     # ---------------------------------------------------------------- shared pieces
     def embed(self, images: torch.Tensor, extra_rows: int = 0, shift: int = 0) -> torch.Tensor:
@@ -248,7 +256,10 @@ class Forward:
         B = images.shape[0]
         P, D, T, R = pm.num_patches, pm.dim, pm.n_cls, pm.n_reg
         seq = pm.seq_len + shift + extra_rows
-        patches = ops.patchify(images, pm.patch_size, self.ws.get("patches", (B * P, pm.w_patch.shape[1]), torch.bfloat16))
+        if self.patches_ready:
+            patches = self.ws.get("patches", (B * P, pm.w_patch.shape[1]), torch.bfloat16)
+        else:
+            patches = self.patchify(images)
         x = self.ws.get("x", (B * seq, D), torch.float32)
         ops.gemm(patches, pm.w_patch, pm.b_patch, x, PK_EPI_BIAS_RESID_F32, resid=pm.pos,
                  rows_per_group=P, group_stride=seq, group_offset=T + R + shift, resid_is_pos=True, pos_offset=T + R)

@@ -82,8 +82,8 @@ def _graphed(model, fwd: engine.Forward, chunk: torch.Tensor, aux: Optional[dict
 
     Every family's sequence is static: kernels read their operands from workspace buffers with stable
     addresses and from the prepacked weights, and ragged row counts live in device memory (grids are
-    sized for the upper bound), so a graph captured for (input pointer, shape, weight pack, budget) is
-    valid until one of them changes.  ``fn(chunk, aux_dict)`` runs the eager forward.  Side-state tensors
+    sized for the upper bound), so a graph captured for (shape, weight pack, budget) is valid until one
+    of them changes.  ``fn(chunk, aux_dict)`` runs the eager forward.  Side-state tensors
     produced inside the graph are static too, so they are cloned out after every replay.  Not used while
     bench.py brackets GEMM launches with events (the events would be captured instead of recorded)."""
     from . import ops
@@ -91,7 +91,9 @@ def _graphed(model, fwd: engine.Forward, chunk: torch.Tensor, aux: Optional[dict
         return None
     st = _state(model)
     graphs = st.setdefault("graphs", {})
-    key = (chunk.data_ptr(), tuple(chunk.shape), id(fwd.pm), aux is not None, extra_key)
+    # The only kernel that reads the caller's image tensor is the im2col: it is launched eagerly into a workspace buffer,
+    # and the graph (everything after it) is independent of where the images live.
+    key = (tuple(chunk.shape), id(fwd.pm), aux is not None, extra_key)
     hit = graphs.get(key)
     if hit is None:
         if len(graphs) >= _MAX_GRAPHS:
@@ -101,12 +103,17 @@ def _graphed(model, fwd: engine.Forward, chunk: torch.Tensor, aux: Optional[dict
         n0 = ops.launch_count
         g = torch.cuda.CUDAGraph()
         static_aux = {} if aux is not None else None
-        with torch.cuda.graph(g):
-            out = fn(chunk, static_aux)
-        hit = (g, out, static_aux, ops.launch_count - n0, chunk)     # keep `chunk` alive: the graph reads its storage
+        fwd.patches_ready = True
+        try:
+            with torch.cuda.graph(g):
+                out = fn(chunk, static_aux)
+        finally:
+            fwd.patches_ready = False
+        hit = (g, out, static_aux, ops.launch_count - n0)
         graphs[key] = hit
         ops.launch_count = n0
-    g, out, static_aux, n_launch, _ = hit
+    g, out, static_aux, n_launch = hit
+    fwd.patchify(chunk)
     g.replay()
     ops.launch_count += n_launch
     if aux is not None:
