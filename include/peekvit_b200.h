@@ -132,7 +132,7 @@ typedef struct pk_attention_args {
   const float* key_mult;    /* f32 [rows] or NULL */
   const void* extra_kv;     /* bf16 [2*D]: k-bias | v-bias, or NULL */
   const float* extra_mult;  /* f32 [batch] or NULL (<= 0 disables the virtual key for that sample) */
-  int impl;                 /* 0 = auto (tcgen05/TMEM kernel for uniform 128 < seq_len <= 256, head_dim 64, no
+  int impl;                 /* 0 = auto (tcgen05/TMEM kernel for uniform 64 < seq_len <= 256, head_dim 64, no
                                multiplicities; general mma.sync kernel otherwise), 1 = general kernel, 2 = tcgen05 kernel */
 } pk_attention_args;
 

@@ -1,7 +1,7 @@
 // peekvit_b200 — tcgen05/TMEM attention for the dense ViT shape (sm_100a).
 //
 // Replaces nn.MultiheadAttention's core (reference models/blocks.py:93-95) for uniform-length
-// samples with 128 < n <= 256 tokens and head_dim 64 (ViT-B/16 and ViT-S/16 at 224 px: n = 197/198).
+// samples with 64 < n <= 256 tokens and head_dim 64 (ViT-B/16 and ViT-S/16 at 224 px: n = 197/198).
 // Other shapes (ragged batches, key multiplicities, n <= 128, n > 256, head_dim 32) take the
 // general mma.sync kernel in pk_attention.cu.
 //
@@ -561,7 +561,12 @@ bool attention_tc_eligible(const pk_attention_args* a) {
   if (a->impl == 1) return false;
   if (a->cu_seqlens || a->key_mult || a->extra_kv || a->extra_mult) return false;
   if (a->head_dim != kTcDH) return false;
-  if (a->seq_len <= 128 || a->seq_len > kTcMaxKeys) return false;
+  // n <= 128 runs with the second query tile empty (its region only keeps the barrier protocol alive); PK_ATT_TC_MIN_SEQ
+  // (default 65: measured 92 vs 138 us at n = 99, but 68 vs 54 us at n = 50, B = 512, H = 12) is the shortest sequence routed here
+  static int min_seq = -1;
+  if (min_seq < 0) { const char* e = getenv("PK_ATT_TC_MIN_SEQ"); min_seq = e ? atoi(e) : 65; if (min_seq < 17) min_seq = 17; }
+  if (a->impl != 2 && a->seq_len < min_seq) return false;
+  if (a->seq_len < 17 || a->seq_len > kTcMaxKeys) return false;
   if ((reinterpret_cast<uintptr_t>(a->qkv) & 15) != 0 || (reinterpret_cast<uintptr_t>(a->out) & 15) != 0) return false;
   return true;
 }
@@ -608,6 +613,7 @@ int launch_attention_tc(const pk_attention_args* a, cudaStream_t stream) {
     attention_tc_kernel<NP><<<grid, kTcThreads, TcSmem<NP>::kBytes, stream>>>(tq, tkv, tout, p);                              \
     break;                                                                                                              \
   }
+    PK_TC_CASE(32) PK_TC_CASE(48) PK_TC_CASE(64) PK_TC_CASE(80) PK_TC_CASE(96) PK_TC_CASE(112) PK_TC_CASE(128)
     PK_TC_CASE(144) PK_TC_CASE(160) PK_TC_CASE(176) PK_TC_CASE(192) PK_TC_CASE(208) PK_TC_CASE(224) PK_TC_CASE(240) PK_TC_CASE(256)
 #undef PK_TC_CASE
     default:

@@ -401,9 +401,11 @@ def test_pair_gemm_device_side_row_count(ops, m_dev):
 
 # ------------------------------------------------------------------ tcgen05 / TMEM attention (uniform 128 < n <= 256, head_dim 64)
 @pytest.mark.parametrize("cfg", [(1, 1, 197), (2, 12, 197), (3, 6, 198), (2, 3, 129), (2, 2, 256), (2, 2, 144), (5, 4, 145),
-                                 (3, 2, 160), (2, 2, 176), (2, 2, 192), (2, 2, 209), (2, 2, 225), (2, 2, 241)])
+                                 (3, 2, 160), (2, 2, 176), (2, 2, 192), (2, 2, 209), (2, 2, 225), (2, 2, 241),
+                                 (3, 2, 17), (2, 3, 33), (2, 2, 50), (2, 2, 64), (3, 2, 80), (2, 12, 99), (2, 2, 113), (2, 2, 128)])
 def test_attention_tcgen05(ops, cfg):
-    """impl=2 forces the tcgen05/TMEM kernel (every padded length 144..256); impl=1 the general mma.sync kernel."""
+    """impl=2 forces the tcgen05/TMEM kernel (every padded length 32..256; n <= 128 runs with the second query tile
+    empty); impl=1 the general mma.sync kernel."""
     B, H, N = cfg
     dh, D = 64, H * 64
     g = torch.Generator(device=DEV).manual_seed(B * 1000 + N)
