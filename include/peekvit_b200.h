@@ -102,6 +102,13 @@ int pk_row_stats_cast(const float* x, void* xb, float* row_stats, int rows, int 
  * conv_proj.weight.reshape(D, 3*p*p). */
 int pk_patchify(const float* images, void* patches, int batch, int image_size, int patch_size, void* stream);
 
+/* Input path: uint8 HWC images [B,S,S,3] as decoded, with T.ToTensor (u/255) and T.Normalize
+ * ((t - mean_c)/std_c) (reference data/imagenette.py:69-73) fused into the im2col: 1 byte per pixel-channel is read
+ * (and copied host->device) instead of 4.  mean3 / std3 are HOST pointers to 3 floats.  Bit-identical patches to
+ * pk_patchify on the float tensor those transforms produce. */
+int pk_patchify_u8(const unsigned char* images_hwc, void* patches, int batch, int image_size, int patch_size,
+                   const float* mean3, const float* std3, void* stream);
+
 /* Rows of the residual stream that do not come from the patch GEMM: class / register tokens
  * (vit.py:230-236 then + pos_embedding, vit.py:92) and the ResidualViT budget token
  * (residualvit.py:572-583; it gets no pos_embedding, :338-345).

@@ -38,6 +38,37 @@ __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __
   }
 }
 
+// uint8 HWC images (what the decoder produces, before T.ToTensor/T.Normalize: reference data/imagenette.py:69-73):
+// ToTensor (u/255), Normalize ((t - mean_c)/std_c) and the im2col in one pass that reads 1 byte per pixel-channel.
+// Same fp32 operations in the same order as the torchvision transforms, so the bf16 patches equal patchify(float path).
+__global__ void patchify_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ out, int S, int p, int n_side,
+                                   long long total_chunks, float m0, float m1, float m2, float s0, float s1, float s2) {
+  const int Kp = 3 * p * p;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total_chunks;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long e = idx * 8;                     // linear output element
+    const long long row = e / Kp;              // b*P + patch
+    const int k = static_cast<int>(e - row * Kp);
+    const int c = k / (p * p);
+    const int i = (k - c * p * p) / p;
+    const int j = k - c * p * p - i * p;
+    const int P = n_side * n_side;
+    const long long b = row / P;
+    const int patch = static_cast<int>(row - b * P);
+    const int py = patch / n_side, px = patch - py * n_side;
+    const uint8_t* src = img + ((b * S + (py * p + i)) * (long long)S + px * p + j) * 3 + c;
+    const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+    const float sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    float v[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t] = (static_cast<float>(__ldg(src + 3 * t)) / 255.0f - mean) / sd;
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+    o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + e) = o;
+  }
+}
+
 // ------------------------------------------------------------------------------ token rows
 __global__ void fill_token_rows_kernel(float* __restrict__ x, int batch, int seq_stride, int row_offset, int n_tokens,
                                        int dim, const float* __restrict__ tokens, const float* __restrict__ pos, float scale) {
@@ -275,6 +306,19 @@ extern "C" int pk_patchify(const float* images, void* patches, int batch, int im
   patchify_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       images, static_cast<__nv_bfloat16*>(patches), image_size, patch_size, n_side, total);
   return check_cuda(cudaGetLastError(), "patchify_kernel");
+}
+
+extern "C" int pk_patchify_u8(const unsigned char* images_hwc, void* patches, int batch, int image_size, int patch_size,
+                              const float* mean3, const float* std3, void* stream) {
+  PK_REQUIRE(images_hwc && patches && mean3 && std3, "pk_patchify_u8: null pointer");
+  PK_REQUIRE(patch_size % 8 == 0 && image_size % patch_size == 0, "pk_patchify_u8: patch_size must be a multiple of 8 dividing image_size");
+  if (batch == 0) return PK_OK;
+  const int n_side = image_size / patch_size;
+  const long long total = (long long)batch * n_side * n_side * 3 * patch_size * patch_size / 8;
+  patchify_u8_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      images_hwc, static_cast<__nv_bfloat16*>(patches), image_size, patch_size, n_side, total, mean3[0], mean3[1], mean3[2], std3[0],
+      std3[1], std3[2]);
+  return check_cuda(cudaGetLastError(), "patchify_u8_kernel");
 }
 
 extern "C" int pk_fill_token_rows(float* x, int batch, int seq_stride, int row_offset, int n_tokens, int dim,

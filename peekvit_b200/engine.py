@@ -241,11 +241,16 @@ class Forward:
         # set by the CUDA-graph runner: the im2col of the current micro-batch is already in the workspace, so the captured
         # sequence does not depend on where the caller's image tensor lives
         self.patches_ready = False
+        self.input_norm = (ops.IMAGENET_MEAN, ops.IMAGENET_STD)      # Normalize statistics of the uint8 input path
 
     def patchify(self, images: torch.Tensor) -> torch.Tensor:
+        """im2col of float NCHW images, or of uint8 NHWC images with ToTensor + Normalize fused in."""
         pm = self.pm
         B, P = images.shape[0], pm.num_patches
-        return ops.patchify(images, pm.patch_size, self.ws.get("patches", (B * P, pm.w_patch.shape[1]), torch.bfloat16))
+        out = self.ws.get("patches", (B * P, pm.w_patch.shape[1]), torch.bfloat16)
+        if images.dtype == torch.uint8:
+            return ops.patchify_u8(images, pm.patch_size, out, *self.input_norm)
+        return ops.patchify(images, pm.patch_size, out)
 
     # ---------------------------------------------------------------- shared pieces
     def embed(self, images: torch.Tensor, extra_rows: int = 0, shift: int = 0) -> torch.Tensor:

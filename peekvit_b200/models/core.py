@@ -319,7 +319,10 @@ class _ModelBase(nn.Module):
         return runner.run(self, x)
 
     def forward_host(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Host batch in, host logits out; H2D copies overlap compute (runner.run_host)."""
+        """Host batch in, host logits out; H2D copies overlap compute (runner.run_host).  Besides the reference's float
+        (B,3,S,S) tensors this (and forward) accepts uint8 (B,S,S,3) images as decoded: ToTensor + Normalize
+        (data/imagenette.py:69-73; statistics in ``self.pk_input_norm = (mean, std)``, ImageNet by default) are then fused
+        into the im2col kernel and the host->device copy is 4x smaller."""
         return runner.run_host(self, x_host, out_host)
 
 

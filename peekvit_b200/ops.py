@@ -346,3 +346,22 @@ def row_stats_cast(x: torch.Tensor, xb: torch.Tensor, stats: torch.Tensor, rows:
     n = x.shape[0] if rows is None else rows
     check(lib.pk_row_stats_cast(_ptr(x, torch.float32), _ptr(xb, torch.bfloat16), _ptr(stats, torch.float32), n, x.shape[-1],
                                 stats.shape[1], _stream()), "pk_row_stats_cast")
+
+
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)      # reference data/imagenette.py:72
+
+
+def patchify_u8(images_hwc: torch.Tensor, patch_size: int, out: Optional[torch.Tensor] = None, mean=IMAGENET_MEAN,
+                std=IMAGENET_STD) -> torch.Tensor:
+    """uint8 [B,S,S,3] -> normalised bf16 patches [B*(S/p)^2, 3*p*p] (ToTensor + Normalize + im2col in one pass)."""
+    lib = _lib_for(images_hwc)
+    if images_hwc.dim() != 4 or images_hwc.shape[3] != 3 or images_hwc.shape[1] != images_hwc.shape[2] or not images_hwc.is_contiguous():
+        raise ValueError("images must be contiguous uint8 [B, S, S, 3]")
+    B, S = images_hwc.shape[0], images_hwc.shape[1]
+    P, Kp = (S // patch_size) ** 2, 3 * patch_size * patch_size
+    if out is None:
+        out = torch.empty(B * P, Kp, dtype=torch.bfloat16, device=images_hwc.device)
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    s = (C.c_float * 3)(*[float(v) for v in std])
+    check(lib.pk_patchify_u8(_ptr(images_hwc, torch.uint8), _ptr(out, torch.bfloat16), B, S, patch_size, m, s, _stream()), "pk_patchify_u8")
+    return out

@@ -58,6 +58,12 @@ def _check_model(model):
 
 
 def _check_images(model, x):
+    if x.dtype == torch.uint8:
+        # uint8 input path: decoded HWC images; ToTensor + Normalize run inside the im2col kernel
+        torch._assert(x.dim() == 4 and x.shape[3] == 3, f"Expected uint8 (batch, H, W, 3) got {tuple(x.shape)}")
+        torch._assert(x.shape[1] == model.image_size and x.shape[2] == model.image_size,
+                      f"Wrong image size! Expected {model.image_size} but got {tuple(x.shape[1:3])}!")
+        return
     torch._assert(x.dim() == 4 and x.shape[1] == 3, f"Expected (batch, 3, H, W) got {tuple(x.shape)}")
     torch._assert(x.shape[2] == model.image_size, f"Wrong image height! Expected {model.image_size} but got {x.shape[2]}!")
     torch._assert(x.shape[3] == model.image_size, f"Wrong image width! Expected {model.image_size} but got {x.shape[3]}!")
@@ -192,9 +198,10 @@ def run(model, x: torch.Tensor, aux: Optional[dict] = None) -> torch.Tensor:
     if x.device != dev:
         raise RuntimeError(f"input is on {x.device} but the model is on {dev}")
     _check_images(model, x)
-    x = x.detach().to(torch.float32).contiguous()
+    x = x.detach().contiguous() if x.dtype == torch.uint8 else x.detach().to(torch.float32).contiguous()
     with torch.no_grad():
         fwd = engine.Forward(packed(model), workspace(model, dev))
+        fwd.input_norm = getattr(model, "pk_input_norm", fwd.input_norm)
         B = x.shape[0]
         mb = _micro_batch(model, B)
         out = torch.empty(B, model.num_classes, dtype=torch.float32, device=dev)
@@ -224,12 +231,16 @@ def run_host(model, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = Non
     if x_host.device.type != "cpu":
         raise RuntimeError("run_host expects a CPU (ideally pinned) tensor; use model(x) for device tensors")
     _check_images(model, x_host)
-    if x_host.dtype != torch.float32 or not x_host.is_contiguous():
+    u8 = x_host.dtype == torch.uint8
+    if u8:
+        x_host = x_host.contiguous()
+    elif x_host.dtype != torch.float32 or not x_host.is_contiguous():
         x_host = x_host.to(torch.float32).contiguous()
     B, S = x_host.shape[0], model.image_size
     with torch.no_grad():
         ws = workspace(model, dev)
         fwd = engine.Forward(packed(model), ws)
+        fwd.input_norm = getattr(model, "pk_input_norm", fwd.input_norm)
         mb = min(_micro_batch(model, B), max(B, 1))
         st = _state(model)
         if "copy_stream" not in st:
@@ -237,7 +248,10 @@ def run_host(model, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = Non
             st["ready"] = [torch.cuda.Event(), torch.cuda.Event()]
             st["free"] = [torch.cuda.Event(), torch.cuda.Event()]
         copy_stream, ready, free = st["copy_stream"], st["ready"], st["free"]
-        bufs = [ws.get("img_stage0", (mb, 3, S, S), torch.float32), ws.get("img_stage1", (mb, 3, S, S), torch.float32)]
+        if u8:
+            bufs = [ws.get("img_stage0_u8", (mb, S, S, 3), torch.uint8), ws.get("img_stage1_u8", (mb, S, S, 3), torch.uint8)]
+        else:
+            bufs = [ws.get("img_stage0", (mb, 3, S, S), torch.float32), ws.get("img_stage1", (mb, 3, S, S), torch.float32)]
         out = ws.get("logits_all", (B, model.num_classes), torch.float32)
         cur = torch.cuda.current_stream(dev)
         for i in range(2):

@@ -232,3 +232,28 @@ def test_vit_b16_top1_agreement_outside_the_tolerance_band():
     clear = margin > 2 * TOL_LOGITS * scale
     assert bool(same[clear].all()), "top-1 differs on a sample whose fp32 margin is outside the bf16 tolerance band"
     assert same.float().mean().item() >= 0.97
+
+
+def test_uint8_input_path_matches_float_path():
+    """uint8 HWC images with ToTensor + Normalize fused into the im2col give bit-identical patches and
+    logits to the float path fed with the tensor the torchvision transforms produce (data/imagenette.py:69-73)."""
+    from peekvit_b200 import ops
+    from peekvit_b200.models import VisionTransformer
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (6, 64, 64, 3), generator=g, dtype=torch.uint8)
+    mean, std = torch.tensor(ops.IMAGENET_MEAN), torch.tensor(ops.IMAGENET_STD)
+    flt = ((u8.permute(0, 3, 1, 2).float().div(255) - mean[None, :, None, None]) / std[None, :, None, None]).contiguous()
+    p_u8 = ops.patchify_u8(u8.to(DEV), 16)
+    p_f = ops.patchify(flt.to(DEV), 16)
+    assert torch.equal(p_u8, p_f)
+    model = VisionTransformer(image_size=64, patch_size=16, num_layers=2, num_heads=2, hidden_dim=128, mlp_dim=256, num_classes=10)
+    with torch.no_grad():
+        model.head.weight.normal_(std=0.1)
+        model.class_tokens.normal_(std=0.5)
+    model = model.to(DEV).eval()
+    y_f = model(flt.to(DEV))
+    assert y_f.abs().max() > 1e-3
+    assert torch.equal(model(u8.to(DEV)), y_f)
+    assert torch.equal(model.forward_host(u8.pin_memory()), y_f.cpu())
+    with pytest.raises(AssertionError):
+        model(torch.zeros(2, 3, 64, 64, dtype=torch.uint8, device=DEV))       # uint8 must be HWC
