@@ -236,9 +236,11 @@ int pk_avit_halt_plan(const pk_avit_args* args, void* stream);
 
 /* ---- K15: MoE routing (moevit.py:23-32,49-61) ------------------------------------------- */
 /* expert[r] = argmax_e(LN(x[r]).gate_w[e] + gate_b[e]) (first maximum), then a stable counting sort:
- * offsets[E+1], counts[E], src_of[pos] = original row of the pos-th expert-sorted row. */
+ * offsets[E+1], counts[E], src_of[pos] = original row of the pos-th expert-sorted row.  n_experts <= 16. */
 int pk_moe_route(const float* x, const float* gamma, const float* beta, float eps, const float* gate_w, const float* gate_b,
-                 int n_experts, int rows, int dim, int* expert, int* offsets, int* counts, int* src_of, void* stream);
+                 int n_experts, int rows, int dim, int* expert, int* offsets, int* counts, int* src_of, int* sort_scratch,
+                 void* stream);
+#define PK_MOE_SORT_SCRATCH_INTS 4096 /* caller-owned scratch of the multi-block counting sort (256 chunks x 16 experts) */
 
 /* x[src_of[r], :] += y[r, :] for r < rows: un-permute + residual add of expert outputs computed in expert-sorted order
  * (moevit.py:54-61; src_of from pk_moe_route is a permutation, so no two rows collide). */

@@ -408,32 +408,68 @@ moe_route_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   }
 }
 
-// Stable counting sort of rows by expert (single CTA; rows up to a few 10^5): offsets[E+1],
-// counts[E] and src_of[pos] = original row of the pos-th expert-sorted row.
+// Stable counting sort of rows by expert in three small launches (a single-CTA version took 160 us for 10^5 rows):
+//   hist:    block g counts the experts of its contiguous chunk of rows        -> scratch[g][e]
+//   scan:    per expert, exclusive scan over the blocks + expert offsets        -> scratch[g][e] = first slot of (g, e)
+//   scatter: block g ranks its rows (warp ballots, in row order)               -> src_of[pos] = original row
+// offsets[E+1], counts[E]; src_of[pos] = original row of the pos-th expert-sorted row.
 constexpr int kMaxExperts = 16;
+constexpr int kSortBlocks = 256;      // upper bound on chunks; scratch = kSortBlocks * kMaxExperts ints
+
+__device__ __forceinline__ int moe_chunk_rows(int rows) {
+  int chunk = (rows + kSortBlocks - 1) / kSortBlocks;
+  chunk = (chunk + 1023) / 1024 * 1024;
+  return chunk < 1024 ? 1024 : chunk;
+}
+
 __global__ void __launch_bounds__(1024)
-moe_sort_kernel(const int* __restrict__ expert, int rows, int n_experts, int* __restrict__ offsets, int* __restrict__ counts,
-                int* __restrict__ src_of) {
+moe_hist_kernel(const int* __restrict__ expert, int rows, int n_experts, int* __restrict__ scratch) {
   __shared__ int s_cnt[kMaxExperts];
+  const int tid = threadIdx.x;
+  if (tid < kMaxExperts) s_cnt[tid] = 0;
+  __syncthreads();
+  const int chunk = moe_chunk_rows(rows);
+  const int begin = blockIdx.x * chunk, end = min(rows, begin + chunk);
+  for (int r = begin + tid; r < end; r += blockDim.x) atomicAdd(&s_cnt[expert[r]], 1);
+  __syncthreads();
+  if (tid < n_experts) scratch[blockIdx.x * kMaxExperts + tid] = s_cnt[tid];
+}
+
+__global__ void __launch_bounds__(32)
+moe_scan_kernel(int n_blocks, int n_experts, int* __restrict__ scratch, int* __restrict__ offsets, int* __restrict__ counts) {
+  __shared__ int s_tot[kMaxExperts];
+  const int e = threadIdx.x;
+  if (e < n_experts) {
+    int acc = 0;
+    for (int g = 0; g < n_blocks; ++g) {          // exclusive scan over the blocks of this expert's counts
+      const int c = scratch[g * kMaxExperts + e];
+      scratch[g * kMaxExperts + e] = acc;
+      acc += c;
+    }
+    s_tot[e] = acc;
+    counts[e] = acc;
+  }
+  __syncwarp();
+  if (e == 0) {
+    int acc = 0;
+    for (int x = 0; x < n_experts; ++x) { offsets[x] = acc; acc += s_tot[x]; }
+    offsets[n_experts] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+moe_scatter_kernel(const int* __restrict__ expert, int rows, int n_experts, const int* __restrict__ scratch,
+                   const int* __restrict__ offsets, int* __restrict__ src_of) {
   __shared__ int s_cursor[kMaxExperts];
   __shared__ int s_wc[32][kMaxExperts];
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
-  if (tid < kMaxExperts) s_cnt[tid] = 0;
+  if (tid < n_experts) s_cursor[tid] = offsets[tid] + scratch[blockIdx.x * kMaxExperts + tid];
   __syncthreads();
-  for (int r = tid; r < rows; r += blockDim.x) atomicAdd(&s_cnt[expert[r]], 1);
-  __syncthreads();
-  if (tid == 0) {
-    int acc = 0;
-    for (int e = 0; e < n_experts; ++e) {
-      s_cursor[e] = acc; offsets[e] = acc; counts[e] = s_cnt[e];
-      acc += s_cnt[e];
-    }
-    offsets[n_experts] = acc;
-  }
-  __syncthreads();
-  for (int base = 0; base < rows; base += 1024) {
+  const int chunk = moe_chunk_rows(rows);
+  const int begin = blockIdx.x * chunk, end = min(rows, begin + chunk);
+  for (int base = begin; base < end; base += 1024) {
     const int r = base + tid;
-    const int e = r < rows ? expert[r] : -1;
+    const int e = r < end ? expert[r] : -1;
     int my_rank = 0;
     for (int ex = 0; ex < n_experts; ++ex) {
       const unsigned bal = __ballot_sync(0xffffffffu, e == ex);
@@ -583,8 +619,9 @@ extern "C" int pk_scatter_add_rows(float* x, const float* y, const int* src_of, 
 }
 
 extern "C" int pk_moe_route(const float* x, const float* gamma, const float* beta, float eps, const float* gate_w, const float* gate_b,
-                            int n_experts, int rows, int dim, int* expert, int* offsets, int* counts, int* src_of, void* stream) {
-  PK_REQUIRE(x && gamma && beta && gate_w && gate_b && expert && offsets && counts && src_of, "pk_moe_route: null pointer");
+                            int n_experts, int rows, int dim, int* expert, int* offsets, int* counts, int* src_of, int* sort_scratch,
+                            void* stream) {
+  PK_REQUIRE(x && gamma && beta && gate_w && gate_b && expert && offsets && counts && src_of && sort_scratch, "pk_moe_route: null pointer");
   PK_REQUIRE(n_experts >= 1 && n_experts <= kMaxExperts, "pk_moe_route: 1 <= n_experts <= %d", kMaxExperts);
   PK_REQUIRE(dim % 4 == 0 && dim <= 1024, "pk_moe_route: dim must be a multiple of 4, <= 1024");
   if (rows == 0) return PK_OK;
@@ -593,6 +630,14 @@ extern "C" int pk_moe_route(const float* x, const float* gamma, const float* bet
   if (maxv <= 3) moe_route_kernel<3><<<grid_rows(rows), 256, 0, s>>>(x, gamma, beta, eps, gate_w, gate_b, n_experts, rows, dim, expert);
   else moe_route_kernel<8><<<grid_rows(rows), 256, 0, s>>>(x, gamma, beta, eps, gate_w, gate_b, n_experts, rows, dim, expert);
   PK_CHECK_CUDA(cudaGetLastError());
-  moe_sort_kernel<<<1, 1024, 0, s>>>(expert, rows, n_experts, offsets, counts, src_of);
-  return check_cuda(cudaGetLastError(), "moe_sort_kernel");
+  int chunk = (rows + kSortBlocks - 1) / kSortBlocks;
+  chunk = (chunk + 1023) / 1024 * 1024;
+  if (chunk < 1024) chunk = 1024;
+  const int n_blocks = (rows + chunk - 1) / chunk;
+  moe_hist_kernel<<<n_blocks, 1024, 0, s>>>(expert, rows, n_experts, sort_scratch);
+  PK_CHECK_CUDA(cudaGetLastError());
+  moe_scan_kernel<<<1, 32, 0, s>>>(n_blocks, n_experts, sort_scratch, offsets, counts);
+  PK_CHECK_CUDA(cudaGetLastError());
+  moe_scatter_kernel<<<n_blocks, 1024, 0, s>>>(expert, rows, n_experts, sort_scratch, offsets, src_of);
+  return check_cuda(cudaGetLastError(), "moe_scatter_kernel");
 }

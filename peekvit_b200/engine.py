@@ -565,7 +565,7 @@ class Forward:
             counts = ws.get(f"moe_cnt_{E}", (E,), torch.int32)
             src_of = ws.get("moe_src", (rows,), torch.int32)
             ops.moe_route(x, lw.ln2_w, lw.ln2_b, lw.eps, lw.extra["mlp_gate_w"], lw.extra["mlp_gate_b"], rows, expert, offsets,
-                          counts, src_of)
+                          counts, src_of, scratch=ws.get("moe_sort_scratch", (ops.MOE_SORT_SCRATCH_INTS,), torch.int32))
             a = ops.layernorm(x, lw.ln2_w, lw.ln2_b, lw.eps, ws.get("ln", (rows, D), torch.bfloat16), rows=rows, row_index=src_of)
             F = lw.mlp[0].w_fc1.shape[0]
             hid = ws.get("hid", (rows, F), torch.bfloat16)

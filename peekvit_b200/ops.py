@@ -313,12 +313,17 @@ def avit_halt_plan(x, cu_in, batch: int, seq_total: int, c, R, tokid, *, gate_sc
     check(lib.pk_avit_halt_plan(C.byref(a), _stream()), "pk_avit_halt_plan")
 
 
-def moe_route(x, gamma, beta, eps: float, gate_w, gate_b, rows: int, expert, offsets, counts, src_of) -> None:
+MOE_SORT_SCRATCH_INTS = 4096      # PK_MOE_SORT_SCRATCH_INTS
+
+
+def moe_route(x, gamma, beta, eps: float, gate_w, gate_b, rows: int, expert, offsets, counts, src_of, scratch=None) -> None:
     lib = _lib_for(x)
+    if scratch is None:
+        scratch = torch.empty(MOE_SORT_SCRATCH_INTS, dtype=torch.int32, device=x.device)
     check(lib.pk_moe_route(_ptr(x, torch.float32), _ptr(gamma, torch.float32), _ptr(beta, torch.float32), float(eps),
                            _ptr(gate_w, torch.float32), _ptr(gate_b, torch.float32), gate_w.shape[0], rows, x.shape[-1],
                            _ptr(expert, torch.int32), _ptr(offsets, torch.int32), _ptr(counts, torch.int32),
-                           _ptr(src_of, torch.int32), _stream()), "pk_moe_route")
+                           _ptr(src_of, torch.int32), _ptr(scratch, torch.int32), _stream()), "pk_moe_route")
 
 
 def device_flag(reset: bool = True) -> int:
