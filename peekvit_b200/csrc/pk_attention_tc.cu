@@ -383,7 +383,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
       tc_trace(p, it, 1);
       if (warp_has_rows) {
         uint32_t keep[KEEP];
-        uint32_t ta[32];
+        uint32_t ha[16], hb[16];
         // ---- pass 1: row maximum (the kept chunks' loads overlap the transient chunks' processing)
         float mx = -INFINITY;
         if (p.debug & 1) mx = 0.f;
@@ -397,14 +397,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
           tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(32 * NC), dst);
         }
         if (!(p.debug & 1)) {
-#pragma unroll 1
-          for (int j = 0; j < NT; ++j) {
-            tmem_ld_32x32(t_base + static_cast<uint32_t>(32 * j), ta);
-            tmem_ld_wait();
-            mx = row_max16<false>(ta, mx, 0, n);
-            mx = row_max16<false>(ta + 16, mx, 0, n);
+          // transient columns in 16-column steps, the next step's TMEM load in flight while the current one is reduced
+          if constexpr (NT > 0) tmem_ld_32x32_x16(t_base, ha);
+          tmem_ld_wait();                              // kept chunks + first transient step
+#pragma unroll
+          for (int j = 0; j < 2 * NT; ++j) {
+            uint32_t (&cur)[16] = (j & 1) ? hb : ha;
+            uint32_t (&nxt)[16] = (j & 1) ? ha : hb;
+            if (j + 1 < 2 * NT) tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(16 * (j + 1)), nxt);
+            mx = row_max16<false>(cur, mx, 0, n);
+            if (j + 1 < 2 * NT) tmem_ld_wait();
           }
-          if constexpr (NT == 0) tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < KC; ++c) {
             mx = row_max16<false>(&keep[32 * c], mx, 0, n);
@@ -422,15 +425,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
         float sum = 0.f;
         if (p.debug & 2) sum = 1.f;
         else {
-#pragma unroll 1
-          for (int j = 0; j < NT; ++j) {
-            tmem_ld_32x32(t_base + static_cast<uint32_t>(32 * j), ta);
+          if constexpr (NT > 0) {
+            tmem_ld_32x32_x16(t_base, ha);
             tmem_ld_wait();
-            uint32_t pk[16];
-            sum += softmax_group16<false, kTcPoly>(ta, pk, scale_log2, neg_max_scaled, 0, n);
-            sum += softmax_group16<false, kTcPoly>(ta + 16, pk + 8, scale_log2, neg_max_scaled, 0, n);
-            tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * j), pk);
-            tmem_st_32x32_x8(t_base + static_cast<uint32_t>(16 * j + 8), pk + 8);
+          }
+#pragma unroll
+          for (int j = 0; j < 2 * NT; ++j) {
+            uint32_t (&cur)[16] = (j & 1) ? hb : ha;
+            uint32_t (&nxt)[16] = (j & 1) ? ha : hb;
+            if (j + 1 < 2 * NT) tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(16 * (j + 1)), nxt);
+            uint32_t pk[8];
+            sum += softmax_group16<false, kTcPoly>(cur, pk, scale_log2, neg_max_scaled, 0, n);
+            if (j + 1 < 2 * NT) tmem_ld_wait();        // the next step is in registers before its columns may be overwritten
+            tmem_st_32x32_x8(t_base + static_cast<uint32_t>(8 * j), pk);
           }
 #pragma unroll
           for (int c = 0; c < KC; ++c) {
