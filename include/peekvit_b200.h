@@ -98,16 +98,19 @@ int pk_gemm_row_stat_parts(int N);
 int pk_row_stats_cast(const float* x, void* xb, float* row_stats, int rows, int dim, int parts, void* stream);
 
 /* ---- K1: patchify (the im2col half of conv_proj, vit.py:212-220) --------------------- */
-/* images f32 [B,3,S,S] NCHW -> patches bf16 [B*(S/p)^2, 3*p*p], K order (c,i,j) to match
- * conv_proj.weight.reshape(D, 3*p*p). */
-int pk_patchify(const float* images, void* patches, int batch, int image_size, int patch_size, void* stream);
+/* images f32 [B,3,S,S] NCHW -> patches bf16, K order (c,i,j) to match conv_proj.weight.reshape(D, 3*p*p).
+ * Patch q of sample b goes to row b*rows_per_sample + row_offset + q (rows_per_sample <= 0: densely packed,
+ * [B*(S/p)^2, 3*p*p]).  With rows_per_sample = tokens per sample the patch GEMM's rows ARE the token rows of the
+ * residual stream (class / register / budget rows stay zero in the operand and are masked by rowscale = 0). */
+int pk_patchify(const float* images, void* patches, int batch, int image_size, int patch_size, int rows_per_sample,
+                int row_offset, void* stream);
 
 /* Input path: uint8 HWC images [B,S,S,3] as decoded, with T.ToTensor (u/255) and T.Normalize
  * ((t - mean_c)/std_c) (reference data/imagenette.py:69-73) fused into the im2col: 1 byte per pixel-channel is read
  * (and copied host->device) instead of 4.  mean3 / std3 are HOST pointers to 3 floats.  Bit-identical patches to
  * pk_patchify on the float tensor those transforms produce. */
 int pk_patchify_u8(const unsigned char* images_hwc, void* patches, int batch, int image_size, int patch_size,
-                   const float* mean3, const float* std3, void* stream);
+                   const float* mean3, const float* std3, int rows_per_sample, int row_offset, void* stream);
 
 /* Rows of the residual stream that do not come from the patch GEMM: class / register tokens
  * (vit.py:230-236 then + pos_embedding, vit.py:92) and the ResidualViT budget token

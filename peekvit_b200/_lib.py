@@ -95,8 +95,8 @@ SIGNATURES: Dict[str, tuple] = {
     "pk_gemm_bf16": (c_int, [C.POINTER(GemmArgs), c_void_p]),
     "pk_gemm_row_stat_parts": (c_int, [c_int]),
     "pk_row_stats_cast": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "pk_patchify": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "pk_patchify_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, C.POINTER(c_float), C.POINTER(c_float), c_void_p]),
+    "pk_patchify": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pk_patchify_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, C.POINTER(c_float), C.POINTER(c_float), c_int, c_int, c_void_p]),
     "pk_fill_token_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p]),
     "pk_layernorm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pk_attention_fwd": (c_int, [C.POINTER(AttentionArgs), c_void_p]),

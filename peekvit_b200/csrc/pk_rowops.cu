@@ -13,7 +13,7 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // ------------------------------------------------------------------------------ patchify
 // One thread = 8 consecutive K elements (16-byte bf16 store) of one patch row.
 __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out,
-                                int S, int p, int n_side, long long total_chunks) {
+                                int S, int p, int n_side, long long total_chunks, int rows_per_sample, int row_offset) {
   const int chunks_per_prow = p / 8;           // 8-wide chunks per (c,i) row of a patch
   const int Kp = 3 * p * p;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total_chunks;
@@ -33,7 +33,7 @@ __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __
     uint4 o;
     o.x = pack_bf16(a.x, a.y); o.y = pack_bf16(a.z, a.w);
     o.z = pack_bf16(d.x, d.y); o.w = pack_bf16(d.z, d.w);
-    *reinterpret_cast<uint4*>(out + e) = o;
+    *reinterpret_cast<uint4*>(out + ((b * rows_per_sample + row_offset + patch) * (long long)Kp + k)) = o;
     (void)chunks_per_prow;
   }
 }
@@ -42,7 +42,8 @@ __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __
 // ToTensor (u/255), Normalize ((t - mean_c)/std_c) and the im2col in one pass that reads 1 byte per pixel-channel.
 // Same fp32 operations in the same order as the torchvision transforms, so the bf16 patches equal patchify(float path).
 __global__ void patchify_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ out, int S, int p, int n_side,
-                                   long long total_chunks, float m0, float m1, float m2, float s0, float s1, float s2) {
+                                   long long total_chunks, float m0, float m1, float m2, float s0, float s1, float s2,
+                                   int rows_per_sample, int row_offset) {
   const int Kp = 3 * p * p;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total_chunks;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -65,7 +66,7 @@ __global__ void patchify_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat1
     uint4 o;
     o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
     o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-    *reinterpret_cast<uint4*>(out + e) = o;
+    *reinterpret_cast<uint4*>(out + ((b * rows_per_sample + row_offset + patch) * (long long)Kp + k)) = o;
   }
 }
 
@@ -296,28 +297,33 @@ static int grid_for(long long work_items, int per_block, int max_blocks_per_sm =
 
 using namespace pk;
 
-extern "C" int pk_patchify(const float* images, void* patches, int batch, int image_size, int patch_size, void* stream) {
+extern "C" int pk_patchify(const float* images, void* patches, int batch, int image_size, int patch_size, int rows_per_sample,
+                           int row_offset, void* stream) {
   PK_REQUIRE(images && patches, "pk_patchify: null pointer");
   PK_REQUIRE(patch_size % 8 == 0 && image_size % patch_size == 0, "pk_patchify: patch_size %d must be a multiple of 8 dividing image_size %d",
              patch_size, image_size);
   if (batch == 0) return PK_OK;
   const int n_side = image_size / patch_size;
   const long long total = (long long)batch * n_side * n_side * 3 * patch_size * patch_size / 8;
+  if (rows_per_sample <= 0) { rows_per_sample = n_side * n_side; row_offset = 0; }
+  PK_REQUIRE(row_offset >= 0 && row_offset + n_side * n_side <= rows_per_sample, "pk_patchify: patches do not fit rows_per_sample");
   patchify_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      images, static_cast<__nv_bfloat16*>(patches), image_size, patch_size, n_side, total);
+      images, static_cast<__nv_bfloat16*>(patches), image_size, patch_size, n_side, total, rows_per_sample, row_offset);
   return check_cuda(cudaGetLastError(), "patchify_kernel");
 }
 
 extern "C" int pk_patchify_u8(const unsigned char* images_hwc, void* patches, int batch, int image_size, int patch_size,
-                              const float* mean3, const float* std3, void* stream) {
+                              const float* mean3, const float* std3, int rows_per_sample, int row_offset, void* stream) {
   PK_REQUIRE(images_hwc && patches && mean3 && std3, "pk_patchify_u8: null pointer");
   PK_REQUIRE(patch_size % 8 == 0 && image_size % patch_size == 0, "pk_patchify_u8: patch_size must be a multiple of 8 dividing image_size");
   if (batch == 0) return PK_OK;
   const int n_side = image_size / patch_size;
   const long long total = (long long)batch * n_side * n_side * 3 * patch_size * patch_size / 8;
+  if (rows_per_sample <= 0) { rows_per_sample = n_side * n_side; row_offset = 0; }
+  PK_REQUIRE(row_offset >= 0 && row_offset + n_side * n_side <= rows_per_sample, "pk_patchify_u8: patches do not fit rows_per_sample");
   patchify_u8_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       images_hwc, static_cast<__nv_bfloat16*>(patches), image_size, patch_size, n_side, total, mean3[0], mean3[1], mean3[2], std3[0],
-      std3[1], std3[2]);
+      std3[1], std3[2], rows_per_sample, row_offset);
   return check_cuda(cudaGetLastError(), "patchify_u8_kernel");
 }
 

@@ -29,6 +29,9 @@ from ._lib import PK_EPI_BIAS_BF16, PK_EPI_BIAS_F32, PK_EPI_BIAS_GELU_BF16, PK_E
 # (B200, 256-image micro-batch): the GELU epilogue of fc1 is on the critical path of that GEMM, so folding ln_2 into it costs
 # more (+41 us) than the LayerNorm kernel it removes (42 us) -> default 1.
 LN_FOLD = int(os.environ.get("PEEKVIT_B200_LN_FOLD", "1"))
+# 1: the im2col operand has one row per token, so the patch GEMM runs on the CTA-pair kernel and writes the residual
+# stream (and layer 0's LayerNorm statistics) directly; 0: densely packed patches + row-remap epilogue (single-CTA kernel)
+EMBED_TOKEN_ROWS = int(os.environ.get("PEEKVIT_B200_EMBED_TOKEN_ROWS", "1"))
 
 
 def _f32(t: torch.Tensor) -> torch.Tensor:
@@ -243,29 +246,86 @@ class Forward:
         self.patches_ready = False
         self.input_norm = (ops.IMAGENET_MEAN, ops.IMAGENET_STD)      # Normalize statistics of the uint8 input path
 
+    def _embed_geometry(self, batch: int):
+        """(tokens per sample of the embedded stream, shift rows after the first class token, token-row layout?).
+        With the token-row layout the im2col operand has one row per TOKEN (class / register / budget rows zero), so the
+        patch GEMM writes the residual stream in place of a row remap and runs on the CTA-pair kernel."""
+        pm = self.pm
+        shift = 1 if (pm.family == "residualvit" and pm.extra.get("add_budget_token")) else 0
+        seq = pm.seq_len + shift
+        token_rows = EMBED_TOKEN_ROWS and batch * seq > 256 and pm.dim % 8 == 0
+        return seq, shift, token_rows
+
+    def _patch_operand(self, batch: int) -> torch.Tensor:
+        pm = self.pm
+        seq, _, token_rows = self._embed_geometry(batch)
+        Kp = pm.w_patch.shape[1]
+        if not token_rows:
+            return self.ws.get("patches", (batch * pm.num_patches, Kp), torch.bfloat16)
+        key = ("patch_rows", batch, seq, Kp)
+        t = self.ws._bufs.get(key)
+        if t is None:                               # zeroed once: the non-patch rows are never written again
+            t = self.ws._bufs[key] = torch.zeros((batch * seq, Kp), dtype=torch.bfloat16, device=self.ws.device)
+        return t
+
     def patchify(self, images: torch.Tensor) -> torch.Tensor:
         """im2col of float NCHW images, or of uint8 NHWC images with ToTensor + Normalize fused in."""
         pm = self.pm
-        B, P = images.shape[0], pm.num_patches
-        out = self.ws.get("patches", (B * P, pm.w_patch.shape[1]), torch.bfloat16)
+        B = images.shape[0]
+        seq, shift, token_rows = self._embed_geometry(B)
+        out = self._patch_operand(B)
+        lay = dict(rows_per_sample=seq, row_offset=pm.n_cls + pm.n_reg + shift) if token_rows else {}
         if images.dtype == torch.uint8:
-            return ops.patchify_u8(images, pm.patch_size, out, *self.input_norm)
-        return ops.patchify(images, pm.patch_size, out)
+            return ops.patchify_u8(images, pm.patch_size, out, *self.input_norm, **lay)
+        return ops.patchify(images, pm.patch_size, out, **lay)
 
     # ---------------------------------------------------------------- shared pieces
-    def embed(self, images: torch.Tensor, extra_rows: int = 0, shift: int = 0) -> torch.Tensor:
+    def embed(self, images: torch.Tensor, shift: int = 0, emit_fold: Optional[bool] = None):
         """Patch GEMM (+conv bias +pos_embedding) and class/register rows -> x f32 [B*seq, D]
         (reference vit.py:203-236, :92).  ``shift`` local rows are left free right after the first
-        class token (ResidualViT budget token), ``extra_rows`` are reserved at the end of each sample."""
+        class token (ResidualViT budget token).  ``emit_fold`` not None: return (x, fold) where fold is the bf16 copy and
+        row statistics of x for a LayerNorm-folded first layer, or None when not asked for / the patch GEMM cannot emit them."""
         pm = self.pm
         B = images.shape[0]
         P, D, T, R = pm.num_patches, pm.dim, pm.n_cls, pm.n_reg
-        seq = pm.seq_len + shift + extra_rows
-        if self.patches_ready:
-            patches = self.ws.get("patches", (B * P, pm.w_patch.shape[1]), torch.bfloat16)
-        else:
-            patches = self.patchify(images)
+        seq, shift_g, token_rows = self._embed_geometry(B)
+        assert shift == shift_g
+        patches = self._patch_operand(B) if self.patches_ready else self.patchify(images)
         x = self.ws.get("x", (B * seq, D), torch.float32)
+        if token_rows:
+            dev = x.device
+
+            def build_init():
+                # what every sample's rows hold before the patch projection is added: class / register tokens + their
+                # positions, the position embedding alone on patch rows, zeros on the budget-token row
+                t = torch.zeros((B * seq, D), dtype=torch.float32, device=dev)
+                ops.fill_token_rows(t, B, seq, 0, pm.cls_tokens[:1], pm.pos)
+                if T > 1:
+                    ops.fill_token_rows(t, B, seq, 1 + shift, pm.cls_tokens[1:], pm.pos, pos_offset=1)
+                if R > 0:
+                    ops.fill_token_rows(t, B, seq, T + shift, pm.reg_tokens, pm.pos, pos_offset=T)
+                ops.fill_token_rows(t, B, seq, T + R + shift, None, pm.pos, pos_offset=T + R, n_tokens=P, scale=0.0)
+                return t
+
+            def build_scale():
+                rs = torch.zeros((B, seq), dtype=torch.float32, device=dev)
+                rs[:, T + R + shift:T + R + shift + P] = 1.0
+                return rs.reshape(-1)
+
+            consts = pm.__dict__.setdefault("_embed_consts", {})          # lives and dies with the weight pack
+            x_init = consts.get((B, seq))
+            if x_init is None:
+                x_init = consts[(B, seq)] = build_init()
+            rs = self._const(f"patch_rowscale_{B}_{seq}_{T}_{R}", build_scale)
+            fold = None
+            if emit_fold:
+                fold = (self.ws.get("xb", (B * seq, D), torch.bfloat16),
+                        self.ws.get("ln_stats", (B * seq, ops.gemm_row_stat_parts(D), 2), torch.float32))
+                ops.gemm(patches, pm.w_patch, pm.b_patch, x, PK_EPI_BIAS_RESID_F32, resid=x_init, rowscale=rs,
+                         xb_out=fold[0], row_stats=fold[1])
+            else:
+                ops.gemm(patches, pm.w_patch, pm.b_patch, x, PK_EPI_BIAS_RESID_F32, resid=x_init, rowscale=rs)
+            return x if emit_fold is None else (x, fold)
         ops.gemm(patches, pm.w_patch, pm.b_patch, x, PK_EPI_BIAS_RESID_F32, resid=pm.pos,
                  rows_per_group=P, group_stride=seq, group_offset=T + R + shift, resid_is_pos=True, pos_offset=T + R)
         ops.fill_token_rows(x, B, seq, 0, pm.cls_tokens[:1], pm.pos)
@@ -273,7 +333,7 @@ class Forward:
             ops.fill_token_rows(x, B, seq, 1 + shift, pm.cls_tokens[1:], pm.pos, pos_offset=1)
         if R > 0:
             ops.fill_token_rows(x, B, seq, T + shift, pm.reg_tokens, pm.pos, pos_offset=T)
-        return x
+        return x if emit_fold is None else (x, None)
 
     def attn_part(self, x, lw: LayerWeights, rows: int, batch: int, *, seq: int = 0, cu=None, max_len: int = 0, rows_dev=None,
                   rowscale=None, key_mult=None, extra_mult=None) -> None:
@@ -359,10 +419,11 @@ class Forward:
     def vit(self, images: torch.Tensor) -> torch.Tensor:
         pm = self.pm
         B, seq = images.shape[0], pm.seq_len
-        x = self.embed(images)
         rows = B * seq
-        if self.fold_ok(rows) and all("fold" in lw.extra for lw in pm.layers):
-            xb, stats = self.fold_begin(x, rows)
+        fold_all = self.fold_ok(rows) and all("fold" in lw.extra for lw in pm.layers)
+        x, fold = self.embed(images, emit_fold=fold_all)
+        if fold_all:
+            xb, stats = fold if fold is not None else self.fold_begin(x, rows)
             for i, lw in enumerate(pm.layers):
                 self.dense_block_fused(x, lw, rows, B, seq, xb, stats, emit_last=i + 1 < len(pm.layers))
         else:
@@ -379,9 +440,9 @@ class Forward:
         survivors only."""
         pm, ws = self.pm, self.ws
         B, seq, D = images.shape[0], pm.seq_len, pm.dim
-        x = self.embed(images)
+        # (xb, stats) of the current residual stream when valid; the patch GEMM emits them for layer 0
+        x, fold = self.embed(images, emit_fold=bool(pm.layers) and self.fold_ok(B * seq) and "fold" in pm.layers[0].extra)
         flip = 0
-        fold = None                                  # (xb, stats) of the current residual stream when valid
         L = len(pm.layers)
         for i, lw in enumerate(pm.layers):
             b = budgets.get(i, 1.0) if lw.kind == "rank" else 1.0

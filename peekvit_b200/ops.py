@@ -105,7 +105,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
     return out
 
 
-def patchify(images: torch.Tensor, patch_size: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def patchify(images: torch.Tensor, patch_size: int, out: Optional[torch.Tensor] = None, rows_per_sample: int = 0,
+             row_offset: int = 0) -> torch.Tensor:
     lib = _lib_for(images)
     if images.dim() != 4 or images.shape[1] != 3 or images.shape[2] != images.shape[3] or not images.is_contiguous():
         raise ValueError(f"images must be contiguous [B,3,S,S], got {tuple(images.shape)}")
@@ -113,7 +114,8 @@ def patchify(images: torch.Tensor, patch_size: int, out: Optional[torch.Tensor] 
     P, Kp = (S // patch_size) ** 2, 3 * patch_size * patch_size
     if out is None:
         out = torch.empty(B * P, Kp, dtype=torch.bfloat16, device=images.device)
-    check(lib.pk_patchify(_ptr(images, torch.float32), _ptr(out, torch.bfloat16), B, S, patch_size, _stream()), "pk_patchify")
+    check(lib.pk_patchify(_ptr(images, torch.float32), _ptr(out, torch.bfloat16), B, S, patch_size, rows_per_sample, row_offset,
+                          _stream()), "pk_patchify")
     return out
 
 
@@ -357,7 +359,7 @@ IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)      
 
 
 def patchify_u8(images_hwc: torch.Tensor, patch_size: int, out: Optional[torch.Tensor] = None, mean=IMAGENET_MEAN,
-                std=IMAGENET_STD) -> torch.Tensor:
+                std=IMAGENET_STD, rows_per_sample: int = 0, row_offset: int = 0) -> torch.Tensor:
     """uint8 [B,S,S,3] -> normalised bf16 patches [B*(S/p)^2, 3*p*p] (ToTensor + Normalize + im2col in one pass)."""
     lib = _lib_for(images_hwc)
     if images_hwc.dim() != 4 or images_hwc.shape[3] != 3 or images_hwc.shape[1] != images_hwc.shape[2] or not images_hwc.is_contiguous():
@@ -368,5 +370,6 @@ def patchify_u8(images_hwc: torch.Tensor, patch_size: int, out: Optional[torch.T
         out = torch.empty(B * P, Kp, dtype=torch.bfloat16, device=images_hwc.device)
     m = (C.c_float * 3)(*[float(v) for v in mean])
     s = (C.c_float * 3)(*[float(v) for v in std])
-    check(lib.pk_patchify_u8(_ptr(images_hwc, torch.uint8), _ptr(out, torch.bfloat16), B, S, patch_size, m, s, _stream()), "pk_patchify_u8")
+    check(lib.pk_patchify_u8(_ptr(images_hwc, torch.uint8), _ptr(out, torch.bfloat16), B, S, patch_size, m, s, rows_per_sample, row_offset,
+                             _stream()), "pk_patchify_u8")
     return out

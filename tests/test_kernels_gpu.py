@@ -263,6 +263,56 @@ def test_patchify(ops, S, p):
     assert torch.equal(got, ref.to(torch.bfloat16))        # (c,i,j) K order == conv_proj.weight.reshape(D,-1)
 
 
+@pytest.mark.parametrize("u8", [False, True])
+def test_patchify_token_row_layout(ops, u8):
+    """rows_per_sample / row_offset: patch q of sample b lands on row b*rows_per_sample + row_offset + q, other rows untouched."""
+    B, S, p, seq, off = 3, 64, 8, 67, 2
+    P = (S // p) ** 2
+    if u8:
+        img = torch.randint(0, 256, (B, S, S, 3), device=DEV, dtype=torch.uint8)
+        dense = ops.patchify_u8(img, p)
+        out = torch.full((B * seq, 3 * p * p), 7.0, device=DEV, dtype=torch.bfloat16)
+        ops.patchify_u8(img, p, out, rows_per_sample=seq, row_offset=off)
+    else:
+        img = torch.randn(B, 3, S, S, device=DEV)
+        dense = ops.patchify(img, p)
+        out = torch.full((B * seq, 3 * p * p), 7.0, device=DEV, dtype=torch.bfloat16)
+        ops.patchify(img, p, out, rows_per_sample=seq, row_offset=off)
+    o3 = out.view(B, seq, -1)
+    assert torch.equal(o3[:, off:off + P], dense.view(B, P, -1))
+    assert (o3[:, :off] == 7).all() and (o3[:, off + P:] == 7).all()
+
+
+def test_patch_embed_token_rows_matches_remap(ops):
+    """Token-row operand + rowscale-masked staged residual (CTA-pair kernel, with the LayerNorm producer outputs) gives the
+    same residual stream as the densely packed operand + row-remap epilogue, bit for bit."""
+    from peekvit_b200._lib import PK_EPI_BIAS_RESID_F32
+    B, S, p, D, T = 6, 64, 8, 128, 1
+    P, seq = 64, 65
+    img = torch.randn(B, 3, S, S, device=DEV)
+    w = (torch.randn(D, 3 * p * p, device=DEV) / math.sqrt(3 * p * p)).to(torch.bfloat16)
+    bias, pos, cls = torch.randn(D, device=DEV) * 0.1, torch.randn(seq, D, device=DEV) * 0.02, torch.randn(1, D, device=DEV)
+    x_ref = torch.zeros(B * seq, D, device=DEV)
+    ops.gemm(ops.patchify(img, p), w, bias, x_ref, PK_EPI_BIAS_RESID_F32, resid=pos, rows_per_group=P, group_stride=seq,
+             group_offset=T, resid_is_pos=True)
+    ops.fill_token_rows(x_ref, B, seq, 0, cls, pos)
+    a = torch.zeros(B * seq, 3 * p * p, device=DEV, dtype=torch.bfloat16)
+    ops.patchify(img, p, a, rows_per_sample=seq, row_offset=T)
+    x_init = torch.zeros(B * seq, D, device=DEV)
+    ops.fill_token_rows(x_init, B, seq, 0, cls, pos)
+    ops.fill_token_rows(x_init, B, seq, T, None, pos, n_tokens=P, scale=0.0)
+    rs = torch.zeros(B, seq, device=DEV)
+    rs[:, T:] = 1
+    x = torch.full((B * seq, D), float("nan"), device=DEV)
+    xb = torch.zeros(B * seq, D, device=DEV, dtype=torch.bfloat16)
+    stats = torch.zeros(B * seq, ops.gemm_row_stat_parts(D), 2, device=DEV)
+    ops.gemm(a, w, bias, x, PK_EPI_BIAS_RESID_F32, resid=x_init, rowscale=rs.reshape(-1), xb_out=xb, row_stats=stats, cta_pair=2)
+    assert torch.equal(x, x_ref)
+    assert torch.equal(xb, x_ref.to(torch.bfloat16))
+    s = stats.sum(1)
+    assert rel_err(s[:, 0], x_ref.sum(1)) < 1e-5 and rel_err(s[:, 1], (x_ref * x_ref).sum(1)) < 1e-5
+
+
 def test_patch_embed_matches_conv2d(ops):
     """patchify + GEMM(+bias+pos) == Conv2d(k=s=p) + flatten + transpose + pos (vit.py:212-220,:92)."""
     from peekvit_b200._lib import PK_EPI_BIAS_RESID_F32
