@@ -249,6 +249,10 @@ int pk_moe_route(const float* x, const float* gamma, const float* beta, float ep
  * (moevit.py:54-61; src_of from pk_moe_route is a permutation, so no two rows collide). */
 int pk_scatter_add_rows(float* x, const float* y, const int* src_of, int rows, int dim, void* stream);
 
+/* onehot[e*rows + r] = (expert[r] == e) as f32, e < n_experts: the per-expert rowscale with which the out-proj residual
+ * epilogue of attention experts accumulates only the rows routed to that expert (AttentionMoE.forward_moe, moevit.py:85-96). */
+int pk_expert_onehot(const int* expert, float* onehot, int rows, int n_experts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,6 @@ fixtures under ``tests/golden/``.  ``tests/test_oracle_golden.py`` replays them.
 from .weights import make_state_dict, synthetic_images, FAMILIES  # noqa: F401
 from .peekvit_oracle import (  # noqa: F401
     layer_norm, mha, mlp, patch_embed, vit_block, stable_topk_desc,
-    vit_forward, rankvit_forward, residualvit_forward, avit_forward, moevit_forward,
+    vit_forward, rankvit_forward, residualvit_forward, avit_forward, moevit_forward, eeresidualvit_forward,
     forward, flops_per_image,
 )

@@ -196,7 +196,8 @@ def _residual_plain(x: Tensor, sd, lp: str, H: int, mask: Union[Tensor, float]) 
     return x1 + mlp(y, sd, lp + ".mlp")
 
 
-def residualvit_forward(sd, cfg, images: Tensor, budget: float, stop_after_layer: Optional[int] = None) -> Tuple[Tensor, Dict]:
+def residualvit_forward(sd, cfg, images: Tensor, budget: float, stop_after_layer: Optional[int] = None,
+                        early_exits: Optional[List[Tensor]] = None) -> Tuple[Tensor, Dict]:
     """``ResidualVisionTransformer.forward`` in eval (reference residualvit.py:587-616):
     budget token built by ``_add_budget_token`` (:552-585) and appended last; encoder adds
     ``pos_embedding`` to all but the budget token (:335-348); blocks dispatch on ``skip``
@@ -249,7 +250,24 @@ def residualvit_forward(sd, cfg, images: Tensor, budget: float, stop_after_layer
             raise NotImplementedError(f"skip mode {skip!r} is outside the hot-path scope (SURVEY.md §8 f3)")
         if stop_after_layer is not None and i == stop_after_layer:
             return x, aux
+        if early_exits is not None:
+            hp = f"encoder.early_exit_heads.{i}"                           # eeresidualvit.py:73-75,94
+            e = layer_norm(x[:, 0:1], sd[hp + ".0.weight"], sd[hp + ".0.bias"], 1e-5)
+            early_exits.append(F.linear(e, sd[hp + ".1.weight"].to(dt), sd[hp + ".1.bias"].to(dt)).squeeze())
     return _head(x, sd, cfg), aux
+
+
+def eeresidualvit_forward(sd, cfg, images: Tensor, budget: float) -> Tuple[List[Tensor], Dict]:
+    """``EEResidualVisionTransformer.forward`` in eval (reference eeresidualvit.py:334-358): the ResidualViT forward
+    (same blocks, budget token appended last, :278-331) plus, after every layer, ``early_exit_heads[i]`` =
+    LayerNorm(1e-5) -> Linear applied to the first class token and squeezed (:91-96; the encoder is built with its default
+    ``num_class_tokens=1``, :193-209); returns ``early_exits + [final logits]``.  A falsy budget (None or 0) raises
+    ``ValueError`` (:308-309)."""
+    if not budget:
+        raise ValueError("Budget token not set. Call set_budget() before forward() to evaluate the model on a chosen budget.")
+    exits: List[Tensor] = []
+    logits, aux = residualvit_forward(sd, cfg, images, budget, early_exits=exits)
+    return exits + [logits], aux
 
 
 # --------------------------------------------------------------------------- AdaViT (A-ViT)
@@ -362,6 +380,8 @@ def forward(family: str, sd, cfg, images: Tensor, budget=None) -> Tuple[Tensor, 
             return avit_forward(sd, cfg, images)
         if family == "moevit":
             return moevit_forward(sd, cfg, images)
+        if family == "eeresidualvit":
+            return eeresidualvit_forward(sd, cfg, images, budget)
     raise ValueError(family)
 
 

@@ -17,7 +17,7 @@ from typing import Dict, Optional
 
 import torch
 
-FAMILIES = ("vit", "rankvit", "residualvit", "adavit", "moevit")
+FAMILIES = ("vit", "rankvit", "residualvit", "adavit", "moevit", "eeresidualvit")
 
 
 def _num_patches(cfg) -> int:
@@ -40,6 +40,9 @@ def make_state_dict(family: str, cfg: Dict, seed: int = 4321, gate_std: float = 
     adavit.py:300-324, moevit.py:240-265.
     """
     assert family in FAMILIES, family
+    ee = family == "eeresidualvit"           # same blocks as ResidualViT + one early-exit head per layer (eeresidualvit.py:73-75)
+    if ee:
+        family = "residualvit"
     g = torch.Generator().manual_seed(seed)
     D, F, L = cfg["hidden_dim"], cfg["mlp_dim"], cfg["num_layers"]
     C, p = cfg["num_classes"], cfg["patch_size"]
@@ -77,7 +80,7 @@ def make_state_dict(family: str, cfg: Dict, seed: int = 4321, gate_std: float = 
         abt = cfg.get("add_budget_token", False)
         if abt in ("learnable", "learnable_interpolate"):
             sd["learnable_budget_token_1"] = normal(1, 1, D, std=1.0)
-        if abt == "learnable_interpolate":
+        if abt == "learnable_interpolate" or (ee and abt == "learnable"):      # eeresidualvit.py:212-216 always creates both
             sd["learnable_budget_token_2"] = normal(1, 1, D, std=1.0)
     fan_in = 3 * p * p
     sd["conv_proj.weight"] = normal(D, 3, p, p, std=math.sqrt(1.0 / fan_in)).clamp_(-2 * math.sqrt(1.0 / fan_in), 2 * math.sqrt(1.0 / fan_in))
@@ -96,6 +99,8 @@ def make_state_dict(family: str, cfg: Dict, seed: int = 4321, gate_std: float = 
         if family == "moevit":
             ea = (cfg.get("attn_moes") or [1] * L)[i]
             linear(lp + ".self_attention.gating_network.gate", ea, D)
+            if ea > 1:
+                sd[lp + ".self_attention.gating_network.gate.weight"] *= 4.0
             for e in range(ea):
                 attention(lp + f".self_attention.experts.{e}.self_attention")
         else:
@@ -116,6 +121,10 @@ def make_state_dict(family: str, cfg: Dict, seed: int = 4321, gate_std: float = 
             sd[lp + ".budget_token_gate.weight"] = normal(1, D, std=1.0 / math.sqrt(D))
             sd[lp + ".budget_token_gate.bias"] = normal(1, std=0.1)
     layernorm("encoder.ln")
+    if ee:
+        for i in range(L):
+            layernorm(f"encoder.early_exit_heads.{i}.0")
+            linear(f"encoder.early_exit_heads.{i}.1", C, D)
     sd["head.weight"] = uniform(C, D, bound=1.0 / math.sqrt(D))
     sd["head.bias"] = normal(C, std=0.02)
     return sd

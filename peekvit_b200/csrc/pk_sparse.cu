@@ -618,6 +618,27 @@ extern "C" int pk_scatter_add_rows(float* x, const float* y, const int* src_of, 
   return check_cuda(cudaGetLastError(), "scatter_add_rows_kernel");
 }
 
+// One-hot routing weights of every expert: onehot[e*rows + r] = (expert[r] == e).  Used as the rowscale of the out-proj
+// residual epilogue of attention experts (moevit.py:89-96 combines the stacked expert outputs with the one-hot gate).
+__global__ void expert_onehot_kernel(const int* __restrict__ expert, float* __restrict__ onehot, int rows, int n_experts) {
+  const long long total = static_cast<long long>(rows) * n_experts;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int e = static_cast<int>(i / rows);
+    const int r = static_cast<int>(i % rows);
+    onehot[i] = expert[r] == e ? 1.0f : 0.0f;
+  }
+}
+
+extern "C" int pk_expert_onehot(const int* expert, float* onehot, int rows, int n_experts, void* stream) {
+  PK_REQUIRE(expert && onehot && rows >= 0 && n_experts >= 1, "pk_expert_onehot: bad arguments");
+  if (rows == 0) return PK_OK;
+  const long long total = static_cast<long long>(rows) * n_experts;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
+  expert_onehot_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(expert, onehot, rows, n_experts);
+  return check_cuda(cudaGetLastError(), "expert_onehot_kernel");
+}
+
 extern "C" int pk_moe_route(const float* x, const float* gamma, const float* beta, float eps, const float* gate_w, const float* gate_b,
                             int n_experts, int rows, int dim, int* expert, int* offsets, int* counts, int* src_of, int* sort_scratch,
                             void* stream) {

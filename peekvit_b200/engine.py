@@ -154,7 +154,8 @@ def pack_model(model, family: str) -> PackedModel:
                 extra["mlp_gate_w"] = _f32(blk.mlp.gating_network.gate.weight)
                 extra["mlp_gate_b"] = _f32(blk.mlp.gating_network.gate.bias)
             if len(attn) > 1:
-                raise NotImplementedError("attention-MoE layers (reference moevit.py:71-102) are a 'next' row (SURVEY.md §8 f3)")
+                extra["attn_gate_w"] = _f32(blk.self_attention.gating_network.gate.weight)
+                extra["attn_gate_b"] = _f32(blk.self_attention.gating_network.gate.bias)
         else:
             attn = [_pack_attn(blk.self_attention.self_attention)]
             mlps = [_pack_mlp(blk.mlp)]
@@ -190,13 +191,22 @@ def pack_model(model, family: str) -> PackedModel:
         pos=_f32(model.encoder.pos_embedding.reshape(-1, D)),
         layers=layers, ln_w=_f32(model.encoder.ln.weight), ln_b=_f32(model.encoder.ln.bias), ln_eps=float(model.encoder.ln.eps),
         head_w=_f32(model.head.weight), head_b=_f32(model.head.bias))
+    if family == "eeresidualvit":
+        # EEResidualVisionTransformer (eeresidualvit.py): the ResidualViT forward + one LayerNorm -> Linear head per layer on
+        # the first class token (:73-75,:91-96); its budget mode lives in ``.budget`` (:170)
+        family = pm.family = "residualvit"
+        pm.extra["ee_heads"] = [(_f32(h[0].weight), _f32(h[0].bias), float(h[0].eps), _f32(h[1].weight), _f32(h[1].bias))
+                                for h in model.encoder.early_exit_heads]
+        pm.extra["add_budget_token"] = model.budget
+    elif family == "residualvit":
+        pm.extra["add_budget_token"] = model.add_budget_token
     if family == "residualvit":
         if pm.n_cls != 1:
             raise NotImplementedError("the B200 ResidualViT path supports num_class_tokens == 1 (all shipped configs)")
-        pm.extra["add_budget_token"] = model.add_budget_token
-        if model.add_budget_token in ("learnable", "learnable_interpolate"):
+        model_abt = pm.extra["add_budget_token"]
+        if model_abt in ("learnable", "learnable_interpolate"):
             pm.extra["budget_token_1"] = _f32(model.learnable_budget_token_1.reshape(1, D))
-        if model.add_budget_token == "learnable_interpolate":
+        if model_abt == "learnable_interpolate":
             pm.extra["budget_token_2"] = _f32(model.learnable_budget_token_2.reshape(1, D))
         for lw in pm.layers:
             if lw.extra.get("skip") == "attention+mlp":
@@ -516,6 +526,10 @@ class Forward:
         new_len = ws.get("res_newlen", (B,), torch.int32)
         mdrop = ws.get("res_mdrop", (B,), torch.float32)
         thr_dev = ws.get("res_thr", (1,), torch.float32)
+        ee = ex.get("ee_heads")
+        if ee is not None and len(ee) != len(pm.layers):
+            raise RuntimeError("EEResidualViT: one early-exit head per encoder layer is required (eeresidualvit.py:93-94)")
+        exits = ws.get("ee_logits", (len(pm.layers) + 1, B, pm.num_classes), torch.float32) if ee is not None else None
         flip = 0
         for i, lw in enumerate(pm.layers):
             skip = lw.extra.get("skip")
@@ -554,6 +568,13 @@ class Forward:
                 self.mlp_part(x, lw, rows_cap, rows_dev=rows_dev)
             else:
                 raise NotImplementedError(f"skip mode {skip!r}")
+            if ee is not None:
+                # early-exit head of this layer on the first class token = local row 0 of every sample (eeresidualvit.py:94)
+                ln_w, ln_b, ln_eps, hw, hb = ee[i]
+                ops.cls_head(x, B, 0, 1, ln_w, ln_b, ln_eps, hw, hb, cu_seqlens=cu, out=exits[i])
+        if ee is not None:
+            ops.cls_head(x, B, 0, 1, pm.ln_w, pm.ln_b, pm.ln_eps, pm.head_w, pm.head_b, cu_seqlens=cu, out=exits[len(pm.layers)])
+            return exits
         return self.head(x, B, 0, cu_seqlens=cu, n_cls=1)
 
     # ---------------------------------------------------------------- AdaViT (A-ViT)
@@ -616,7 +637,27 @@ class Forward:
         rows = B * seq
         x = self.embed(images)
         for i, lw in enumerate(pm.layers):
-            self.attn_part(x, lw, rows, B, seq=seq)
+            EA = len(lw.attn)
+            if EA == 1:
+                self.attn_part(x, lw, rows, B, seq=seq)
+            else:
+                # AttentionMoE (moevit.py:71-102): every expert attends over ALL tokens of the sample (its own K / V), and a
+                # token takes the output of its arg-max expert.  Each expert's in-proj + attention runs densely, and the
+                # out-proj residual epilogue adds only the rows routed to it (rowscale = one-hot gate), which is the
+                # reference's stack + one-hot einsum without materialising (E, B, N, D).
+                expert = ws.get("amoe_expert", (rows,), torch.int32)
+                ops.moe_route(x, lw.ln1_w, lw.ln1_b, lw.eps, lw.extra["attn_gate_w"], lw.extra["attn_gate_b"], rows, expert,
+                              ws.get(f"moe_off_{EA}", (EA + 1,), torch.int32), ws.get(f"moe_cnt_{EA}", (EA,), torch.int32),
+                              ws.get("moe_src", (rows,), torch.int32),
+                              scratch=ws.get("moe_sort_scratch", (ops.MOE_SORT_SCRATCH_INTS,), torch.int32))
+                onehot = ops.expert_onehot(expert, EA, ws.get(f"amoe_onehot_{EA}", (EA, rows), torch.float32), rows)
+                a = ops.layernorm(x, lw.ln1_w, lw.ln1_b, lw.eps, ws.get("ln", (rows, D), torch.bfloat16), rows=rows)
+                for e, aw in enumerate(lw.attn):
+                    qkv = ops.gemm(a, aw.w_qkv, aw.b_qkv, ws.get("qkv", (rows, 3 * D), torch.bfloat16), PK_EPI_BIAS_BF16)
+                    att = ops.attention(qkv, ws.get("att", (rows, D), torch.bfloat16), B, pm.heads, D // pm.heads, seq_len=seq)
+                    ops.gemm(att, aw.w_o, aw.b_o, x, PK_EPI_BIAS_RESID_F32, resid=x, rowscale=onehot[e])
+                if aux is not None:
+                    aux.setdefault("attn_expert", {})[i] = expert.view(B, seq).clone()
             E = len(lw.mlp)
             if E == 1:
                 self.mlp_part(x, lw, rows)

@@ -1,3 +1,3 @@
 from .core import (VisionTransformer, RankVisionTransformer, ResidualVisionTransformer,  # noqa: F401
-                   AdaptiveVisionTransformer, VisionTransformerMoE)
+                   AdaptiveVisionTransformer, VisionTransformerMoE, EEResidualVisionTransformer)
 from .models import MODELS_MAP, build_model  # noqa: F401

@@ -181,6 +181,7 @@ class AttentionMoE(MoE):
         self.gating_network = TopKGate(input_dim, num_experts)
         self.num_experts = num_experts
         self.experts = nn.ModuleList([SelfAttention(input_dim, num_heads=num_heads, dropout=dropout) for _ in range(num_experts)])
+        self.gating_probs = None
 
     forward = _no_forward
 
@@ -245,6 +246,23 @@ class ResidualViTEncoder(_EncoderBase):
         self.num_special_tokens = num_class_tokens + num_registers
         self.budget_token = budget_token
         self.num_budget_tokens = 0 if not budget_token else 1
+
+
+class EEResidualViTEncoder(ResidualViTEncoder):
+    """models/eeresidualvit.py:17-96: the ResidualViT encoder plus ``early_exit_heads``, one
+    ``Sequential(LayerNorm, Linear(hidden_dim, num_classes))`` per layer."""
+
+    def __init__(self, seq_length, num_layers, num_heads, hidden_dim, mlp_dim, dropout, attention_dropout,
+                 residual_layers: Optional[List] = None, add_input: bool = False, num_class_tokens: int = 1, num_registers: int = 0,
+                 gate_type="gumbel", gate_temp: float = 1.0, gate_bias: float = 10.0, gate_threshold: float = 0.5,
+                 budget_token: Union[bool, List, Literal["learnable"]] = False, num_classes: int = 10):
+        super().__init__(seq_length, num_layers, num_heads, hidden_dim, mlp_dim, dropout, attention_dropout,
+                         residual_layers=residual_layers, add_input=add_input, num_class_tokens=num_class_tokens,
+                         num_registers=num_registers, gate_type=gate_type, gate_temp=gate_temp, gate_bias=gate_bias,
+                         gate_threshold=gate_threshold, budget_token=budget_token)
+        self.num_classes = num_classes
+        self.early_exit_heads = nn.ModuleList([nn.Sequential(nn.LayerNorm(hidden_dim), nn.Linear(hidden_dim, num_classes))
+                                               for _ in range(num_layers)])
 
 
 class AViTEncoder(_EncoderBase):
@@ -423,6 +441,53 @@ class ResidualVisionTransformer(_ModelBase):
                              "have to set it at the beginning of the training and then sample it during training. Use the "
                              "add_budget_token parameter to specify the budget sampling strategy.")
         self.current_budget = torch.tensor(budget, device=self.class_tokens.device)
+
+
+class EEResidualVisionTransformer(_ModelBase):
+    """Drop-in for reference models/eeresidualvit.py:100-363 (eval path): ResidualViT with an early-exit head after every
+    layer.  ``forward`` returns a list: the L early-exit logits (each ``.squeeze()``-d like the reference, :94), then the
+    final logits (:355-357)."""
+    _family = "eeresidualvit"
+
+    def __init__(self, image_size: int, patch_size: int, num_layers: int, num_heads: int, hidden_dim: int, mlp_dim: int,
+                 dropout: float = 0.0, attention_dropout: float = 0.0, num_classes: int = 1000,
+                 representation_size: Optional[int] = None, num_registers: int = 0, residual_layers: Optional[List] = None,
+                 add_input: bool = False, num_class_tokens: int = 1, gate_type: Literal["gumbel", "sigmoid"] = "gumbel",
+                 gate_temp: float = 1.0, gate_bias: float = 10.0, gate_threshold: float = 0.5,
+                 add_budget_token: Union[bool, List, Literal["learnable", "learnable_interpolate"]] = False):
+        super().__init__()
+        self.num_registers, self.num_class_tokens = num_registers, num_class_tokens
+        self.budget = add_budget_token
+        self.current_budget = None
+        self.gate_temp, self.gate_bias = gate_temp, gate_bias
+        self.residual_layers = residual_layers or ["attention+mlp"] * num_layers
+        seq_length = self._setup(image_size, patch_size, hidden_dim, mlp_dim, num_heads, num_classes, dropout, attention_dropout,
+                                 representation_size, num_class_tokens, num_registers)
+        self.num_special_tokens = num_class_tokens + num_registers
+        # like the reference (:193-209) the encoder is told about neither class-token count nor registers
+        self.encoder = EEResidualViTEncoder(seq_length, num_layers, num_heads, hidden_dim, mlp_dim, dropout, attention_dropout,
+                                            residual_layers=self.residual_layers, add_input=add_input, gate_type=gate_type,
+                                            gate_temp=gate_temp, gate_bias=gate_bias, gate_threshold=gate_threshold,
+                                            budget_token=add_budget_token, num_classes=num_classes)
+        self.seq_length = seq_length
+        if self.budget:
+            self.num_budget_tokens = 1
+        if self.budget == "learnable" or self.budget == "learnable_interpolate":
+            self.learnable_budget_token_1 = nn.Parameter(torch.randn(1, 1, hidden_dim))
+            self.learnable_budget_token_2 = nn.Parameter(torch.randn(1, 1, hidden_dim))     # always both (:212-216)
+        self._finish(hidden_dim, num_classes)
+
+    def set_budget(self, budget: float):
+        """models/eeresidualvit.py:361-362."""
+        self.current_budget = budget
+
+    def forward(self, x: torch.Tensor):
+        out = runner.run(self, x)                     # (L + 1, B, C)
+        n = out.shape[0] - 1
+        return [out[i].unsqueeze(1).squeeze() for i in range(n)] + [out[n]]
+
+    def forward_host(self, x_host, out_host=None):
+        raise NotImplementedError("forward_host returns one logits matrix; EEResidualViT's list output goes through model(x)")
 
 
 class AdaptiveVisionTransformer(_ModelBase):

@@ -1,13 +1,15 @@
 """Model registry with the reference's aliases (reference models/models.py:15-86) for the five
 families on the B200 hot path.  ``build_model`` keeps the reference signature; noise injection
 and layer stitching are outside the hot-path scope and raise."""
-from .core import (AdaptiveVisionTransformer, RankVisionTransformer, ResidualVisionTransformer, VisionTransformer,
-                   VisionTransformerMoE)
+from .core import (AdaptiveVisionTransformer, EEResidualVisionTransformer, RankVisionTransformer, ResidualVisionTransformer,
+                   VisionTransformer, VisionTransformerMoE)
 
 MODELS_MAP = {
     "visiontransformer": VisionTransformer, "VisionTransformer": VisionTransformer, "vit": VisionTransformer,
     "residualvisiontransformer": ResidualVisionTransformer, "ResidualVisionTransformer": ResidualVisionTransformer,
     "residualvit": ResidualVisionTransformer,
+    "EEResidualVisionTransformer": EEResidualVisionTransformer, "eeResidualVisionTransformer": EEResidualVisionTransformer,
+    "eeResidualvit": EEResidualVisionTransformer,
     "visiontransformermoe": VisionTransformerMoE, "VisionTransformerMoE": VisionTransformerMoE, "vitmoe": VisionTransformerMoE,
     "RankingVisionTransformer": RankVisionTransformer, "RankVisionTransformer": RankVisionTransformer,
     "AdaptiveVisionTransformer": AdaptiveVisionTransformer, "adavit": AdaptiveVisionTransformer,

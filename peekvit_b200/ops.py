@@ -342,6 +342,14 @@ def scatter_add_rows(x: torch.Tensor, y: torch.Tensor, src_of: torch.Tensor, row
     return x
 
 
+def expert_onehot(expert: torch.Tensor, n_experts: int, out: torch.Tensor, rows: Optional[int] = None) -> torch.Tensor:
+    """out[e, r] = (expert[r] == e) as f32."""
+    lib = _lib_for(expert)
+    n = expert.shape[0] if rows is None else rows
+    check(lib.pk_expert_onehot(_ptr(expert, torch.int32), _ptr(out, torch.float32), n, n_experts, _stream()), "pk_expert_onehot")
+    return out
+
+
 def gemm_row_stat_parts(n: int) -> int:
     """Statistics slots per row written by the LayerNorm-producer epilogue for an n-column output."""
     return int(_lib.load().pk_gemm_row_stat_parts(n))

@@ -138,6 +138,12 @@ def _forward_chunk(model, fwd: engine.Forward, chunk: torch.Tensor, aux: Optiona
         b = model.current_budget
         b = None if b is None else float(b)
         fn, key = (lambda c, a: fwd.residualvit(c, b, a)), b
+    elif family == "eeresidualvit":
+        b = getattr(model, "current_budget", None)
+        if model.budget and not b:                      # eeresidualvit.py:308-309 (a zero budget is "not set" there too)
+            raise ValueError("Budget token not set. Call set_budget() before forward() to evaluate the model on a chosen budget.")
+        b = None if b is None else float(b)
+        fn, key = (lambda c, a: fwd.residualvit(c, b, a)), b
     elif family == "adavit":
         ee = bool(getattr(model, "pk_early_exit", True))
         fn, key = (lambda c, a: fwd.adavit(c, a, early_exit=ee)), ee
@@ -153,7 +159,8 @@ def _forward_chunk(model, fwd: engine.Forward, chunk: torch.Tensor, aux: Optiona
 
 def _micro_batch(model, B: int) -> int:
     mb = int(getattr(model, "pk_micro_batch", DEFAULT_MICRO_BATCH))
-    if model._family == "residualvit" and model.add_budget_token and model.add_budget_token not in ("learnable", "learnable_interpolate"):
+    abt = model.add_budget_token if model._family == "residualvit" else model.budget if model._family == "eeresidualvit" else None
+    if abt and abt not in ("learnable", "learnable_interpolate"):
         # a fixed-float budget token thresholds on the mean over the WHOLE batch (residualvit.py:208):
         # the batch cannot be split without changing the reference semantics
         return max(B, 1)
@@ -178,7 +185,7 @@ def _publish_side_state(model, merged: dict) -> None:
     block.mask (utils/utils.py:100-122), MoE gating_probs (utils/utils.py:76-94), AViT rho/counter
     (utils/losses.py:155,175)."""
     fam = model._family
-    if fam == "residualvit":
+    if fam in ("residualvit", "eeresidualvit"):
         for i, parts in merged.get("masks", {}).items():
             model.encoder.layers[i].mask = torch.cat(parts, dim=0)
     elif fam == "adavit":
@@ -186,10 +193,11 @@ def _publish_side_state(model, merged: dict) -> None:
             model.encoder.rho_token = torch.cat(merged["rho_token"], dim=0)
             model.encoder.counter_token = torch.cat(merged["counter_token"], dim=0)
     elif fam == "moevit":
-        for i, parts in merged.get("mlp_expert", {}).items():
-            blk = model.encoder.layers[i]
-            ids = torch.cat(parts, dim=0).long()
-            blk.mlp.gating_probs = torch.nn.functional.one_hot(ids, num_classes=blk.mlp.num_experts).float()
+        for key, attr in (("mlp_expert", "mlp"), ("attn_expert", "self_attention")):
+            for i, parts in merged.get(key, {}).items():
+                moe = getattr(model.encoder.layers[i], attr)
+                ids = torch.cat(parts, dim=0).long()
+                moe.gating_probs = torch.nn.functional.one_hot(ids, num_classes=moe.num_experts).float()
 
 
 def run(model, x: torch.Tensor, aux: Optional[dict] = None) -> torch.Tensor:
@@ -204,13 +212,16 @@ def run(model, x: torch.Tensor, aux: Optional[dict] = None) -> torch.Tensor:
         fwd.input_norm = getattr(model, "pk_input_norm", fwd.input_norm)
         B = x.shape[0]
         mb = _micro_batch(model, B)
-        out = torch.empty(B, model.num_classes, dtype=torch.float32, device=dev)
+        multi = model._family == "eeresidualvit"        # (L + 1, B, C): one early exit per layer, then the final logits
+        out = torch.empty((len(model.encoder.layers) + 1, B, model.num_classes) if multi else (B, model.num_classes),
+                          dtype=torch.float32, device=dev)
         merged: dict = {}
-        want_state = model._family in ("residualvit", "adavit", "moevit") or aux is not None
+        want_state = model._family in ("residualvit", "eeresidualvit", "adavit", "moevit") or aux is not None
         for s in range(0, B, mb):
             chunk = x[s:s + mb]
             part = {} if want_state else None
-            out[s:s + chunk.shape[0]].copy_(_forward_chunk(model, fwd, chunk, part))
+            res = _forward_chunk(model, fwd, chunk, part)
+            (out[:, s:s + chunk.shape[0]] if multi else out[s:s + chunk.shape[0]]).copy_(res)
             if part is not None:
                 _merge_aux(merged, part)
         _publish_side_state(model, merged)
@@ -231,6 +242,8 @@ def run_host(model, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = Non
     if x_host.device.type != "cpu":
         raise RuntimeError("run_host expects a CPU (ideally pinned) tensor; use model(x) for device tensors")
     _check_images(model, x_host)
+    if model._family == "eeresidualvit":
+        raise NotImplementedError("forward_host returns one logits matrix; EEResidualViT's list output goes through model(x)")
     u8 = x_host.dtype == torch.uint8
     if u8:
         x_host = x_host.contiguous()

@@ -44,6 +44,15 @@ CASES = {
     "moevit": dict(
         family="moevit", batch=4, weight_seed=17, image_seed=28,
         cfg=dict(_BASE, num_layers=3, mlp_moes=[1, 4, 2])),
+    # attention experts (moevit.py:71-102) on layers 0 and 2, expert MLPs on layer 1
+    "moevit_attn": dict(
+        family="moevit", batch=4, weight_seed=21, image_seed=31,
+        cfg=dict(_BASE, num_layers=3, mlp_moes=[1, 2, 1], attn_moes=[2, 1, 3])),
+    # early-exit heads after every residual layer (eeresidualvit.py:73-96); outputs = exits + [final logits]
+    "eeresidual_learnable_cal04": dict(
+        family="eeresidualvit", batch=4, weight_seed=19, image_seed=30, budget=0.4, calibrate=0.4,
+        cfg=dict(_BASE, gate_type="sigmoid", gate_temp=1.0, gate_bias=0.0, gate_threshold=0.5,
+                 add_budget_token="learnable", residual_layers=["attention+mlp"] * 4)),
 }
 
 

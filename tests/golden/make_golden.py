@@ -43,7 +43,8 @@ def import_reference():
     from peekvit.models.residualvit import ResidualVisionTransformer
     from peekvit.models.adavit import AdaptiveVisionTransformer
     from peekvit.models.moevit import VisionTransformerMoE
-    return {"vit": VisionTransformer, "rankvit": RankVisionTransformer,
+    from peekvit.models.eeresidualvit import EEResidualVisionTransformer
+    return {"eeresidualvit": EEResidualVisionTransformer, "vit": VisionTransformer, "rankvit": RankVisionTransformer,
             "residualvit": ResidualVisionTransformer, "adavit": AdaptiveVisionTransformer,
             "moevit": VisionTransformerMoE}
 
@@ -85,12 +86,20 @@ def main():
                 assert torch.equal(logits, logits_default)
             else:
                 logits = model(images)
-        out["logits"] = logits.numpy()
         o_logits, aux = po.forward(fam, sd, cfg, images, budget)
+        if fam == "eeresidualvit":
+            # outputs are a list: one early exit per layer, then the final logits (eeresidualvit.py:355-357)
+            assert len(logits) == cfg["num_layers"] + 1 == len(o_logits)
+            for i, (r, o) in enumerate(zip(logits[:-1], o_logits[:-1])):
+                e = (o - r).abs().max().item() / r.abs().max().item()
+                assert e < 2e-5, (name, i, e)
+                out[f"exit_{i}"] = r.numpy()
+            logits, o_logits = logits[-1], o_logits[-1]
+        out["logits"] = logits.numpy()
         err = (o_logits - logits).abs().max().item() / logits.abs().max().item()
         print(f"{name:28s} max|logit|={logits.abs().max():.3f} oracle-vs-reference rel err {err:.2e}")
         assert err < 2e-5, (name, err)
-        if fam == "residualvit":
+        if fam in ("residualvit", "eeresidualvit"):
             for i, blk in enumerate(model.encoder.layers):
                 if getattr(blk, "mask", None) is not None:
                     out[f"mask_{i}"] = blk.mask.numpy()
@@ -108,6 +117,10 @@ def main():
                 if gp is not None:
                     out[f"mlp_gating_{i}"] = gp.argmax(-1).numpy().astype(np.int32)
                     assert torch.equal(aux["mlp_gating"][i], gp)
+                gp = getattr(blk.self_attention, "gating_probs", None)
+                if gp is not None:
+                    out[f"attn_gating_{i}"] = gp.argmax(-1).numpy().astype(np.int32)
+                    assert torch.equal(aux["attn_gating"][i], gp)
         if fam == "rankvit":
             for j, (i, idx) in enumerate(sorted(aux["kept"].items())):
                 # the reference's own (stable) argsort output, first k entries

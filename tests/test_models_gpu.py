@@ -14,8 +14,9 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 TOL_LOGITS = 1e-2
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-NAMES = {"vit": "vit", "rankvit": "RankVisionTransformer", "residualvit": "residualvit", "adavit": "adavit", "moevit": "vitmoe"}
-BUILT = ("vit", "rankvit", "residualvit", "adavit", "moevit")
+NAMES = {"vit": "vit", "rankvit": "RankVisionTransformer", "residualvit": "residualvit", "adavit": "adavit", "moevit": "vitmoe",
+         "eeresidualvit": "eeResidualvit"}
+BUILT = ("vit", "rankvit", "residualvit", "adavit", "moevit", "eeresidualvit")
 
 
 def _model(case):
@@ -35,9 +36,20 @@ def test_model_matches_reference_fixture(name):
     case = CASES[name]
     model, sd, images = _model(case)
     aux = {}
-    logits = runner.run(model, images.to(DEV), aux).cpu().numpy()
-    assert ops.device_flag() == 0
     ref = np.load(os.path.join(GOLD, name + ".npz"))
+    if case["family"] == "eeresidualvit":
+        # list output (eeresidualvit.py:355-357): L early exits, then the final logits
+        outs = model(images.to(DEV))
+        L = case["cfg"]["num_layers"]
+        assert isinstance(outs, list) and len(outs) == L + 1
+        for i in range(L):
+            r = ref[f"exit_{i}"]
+            assert tuple(outs[i].shape) == r.shape
+            assert np.abs(outs[i].cpu().numpy() - r).max() / np.abs(r).max() < TOL_LOGITS
+        logits = outs[-1].cpu().numpy()
+    else:
+        logits = runner.run(model, images.to(DEV), aux).cpu().numpy()
+    assert ops.device_flag() == 0
     scale = np.abs(ref["logits"]).max()
     assert np.abs(logits - ref["logits"]).max() / scale < TOL_LOGITS
     assert (logits.argmax(1) == ref["logits"].argmax(1)).mean() >= 0.75   # 3-4 images: at most one near-tie flip
@@ -51,7 +63,7 @@ def test_model_matches_reference_fixture(name):
             g = ref[f"kept_{i}"]
             overlap = np.mean([len(set(a) & set(b)) / len(a) for a, b in zip(kept.cpu().numpy().tolist(), g.tolist())])
             assert overlap >= 0.9
-    if case["family"] == "residualvit":
+    if case["family"] in ("residualvit", "eeresidualvit"):
         # published side-state: block.mask (B, N_img, 1) soft gate values (utils/utils.py:100-122).  Values are
         # continuous in the activations (bf16 band); a keep/drop flag can only differ at a near-tie with the
         # threshold, where the soft value itself is ~0.
@@ -76,6 +88,10 @@ def test_model_matches_reference_fixture(name):
                 gp = blk.mlp.gating_probs
                 assert gp.shape[-1] == blk.mlp.num_experts and torch.all(gp.sum(-1) == 1)
                 assert (gp.argmax(-1).cpu().numpy() == ref[f"mlp_gating_{i}"]).mean() >= 0.98
+            gp = blk.self_attention.gating_probs
+            if blk.self_attention.num_experts > 1:
+                assert gp.shape[-1] == blk.self_attention.num_experts and torch.all(gp.sum(-1) == 1)
+                assert (gp.argmax(-1).cpu().numpy() == ref[f"attn_gating_{i}"]).mean() >= 0.98
 
 
 def test_vit_tiny_config_a_against_oracle():

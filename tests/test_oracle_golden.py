@@ -18,6 +18,13 @@ def test_oracle_matches_reference_fixture(name):
     ref = np.load(os.path.join(GOLD, name + ".npz"))
     sd, images = build_case(case)
     logits, aux = po.forward(case["family"], sd, case["cfg"], images, case.get("budget"))
+    if case["family"] == "eeresidualvit":
+        # list output: one early exit per layer, then the final logits (eeresidualvit.py:355-357)
+        assert len(logits) == case["cfg"]["num_layers"] + 1
+        for i, e in enumerate(logits[:-1]):
+            r = ref[f"exit_{i}"]
+            assert e.shape == r.shape and np.abs(e.numpy() - r).max() / np.abs(r).max() < 1e-5
+        logits = logits[-1]
     scale = np.abs(ref["logits"]).max()
     assert scale > 0.1, "vacuous fixture (zero logits)"
     # fp32 tolerance of the north star: 1e-5 relative
@@ -27,7 +34,7 @@ def test_oracle_matches_reference_fixture(name):
         for i, idx in aux["kept"].items():
             assert np.array_equal(idx.numpy().astype(np.int32), ref[f"kept_{i}"])   # bit-exact index sets, in order
         assert list(ref["seq_lens"]) == aux["seq_lens"]
-    if fam == "residualvit":
+    if fam in ("residualvit", "eeresidualvit"):
         for i, m in aux["masks"].items():
             assert m.shape == ref[f"mask_{i}"].shape                                   # (B, N_img, 1)
             assert np.allclose(m.numpy(), ref[f"mask_{i}"], atol=2e-6)
@@ -38,6 +45,8 @@ def test_oracle_matches_reference_fixture(name):
     if fam == "moevit":
         for i, gp in aux["mlp_gating"].items():
             assert np.array_equal(gp.argmax(-1).numpy().astype(np.int32), ref[f"mlp_gating_{i}"])
+        for i, gp in aux["attn_gating"].items():
+            assert np.array_equal(gp.argmax(-1).numpy().astype(np.int32), ref[f"attn_gating_{i}"])
 
 
 def test_stable_topk_tie_rule():
