@@ -253,6 +253,14 @@ int pk_scatter_add_rows(float* x, const float* y, const int* src_of, int rows, i
  * epilogue of attention experts accumulates only the rows routed to that expert (AttentionMoE.forward_moe, moevit.py:85-96). */
 int pk_expert_onehot(const int* expert, float* onehot, int rows, int n_experts, void* stream);
 
+/* NoiseBlock.forward_snr (models/blocks.py:117-131): x[r,:] += noise[r,:] * sqrt(mean(x[r,:]^2) / 10^(snr_db/10)).
+ * The caller draws ``noise`` (torch.randn_like in the reference) and skips the call for snr_db == 0 like the reference. */
+int pk_noise_snr(float* x, const float* noise, int rows, int dim, float snr_db, void* stream);
+
+/* NoiseBlock.forward_token_drop (models/blocks.py:141-157): zero rows b*seq + tokens[j] for every sample b, j < n_tokens
+ * (the same randperm prefix for the whole batch). */
+int pk_zero_token_rows(float* x, int batch, int seq, const int* tokens, int n_tokens, int dim, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -108,14 +108,35 @@ def stable_topk_desc(scores: Tensor, k: int) -> Tensor:
     return torch.argsort(scores, dim=-1, descending=True, stable=True)[..., :k]
 
 
+def noise_block(x: Tensor, noise: Dict) -> Tensor:
+    """``NoiseBlock.forward`` (reference blocks.py:159-170) with the random draw passed in: ``noise['snr_db']`` +
+    ``noise['noise']`` (the ``randn_like`` tensor) -> ``forward_snr`` (:117-131; 0 dB means no noise there), or
+    ``noise['prob']`` + ``noise['perm']`` (the ``randperm`` result) -> ``forward_token_drop`` (:141-157)."""
+    if noise.get("snr_db") is not None:
+        if noise["snr_db"] == 0:
+            return x
+        power = torch.mean(x ** 2, dim=-1, keepdim=True)
+        return x + noise["noise"].to(x.dtype) * torch.sqrt(power / (10 ** (noise["snr_db"] / 10)))
+    if noise["prob"] == 0:
+        return x
+    keep = torch.ones_like(x)
+    keep[:, noise["perm"][:int(noise["prob"] * x.shape[1])], :] = 0
+    return x * keep
+
+
 # --------------------------------------------------------------------------- plain ViT
-def vit_forward(sd, cfg, images: Tensor) -> Tuple[Tensor, Dict]:
+def vit_forward(sd, cfg, images: Tensor, noise: Optional[Dict] = None) -> Tuple[Tensor, Dict]:
     """``VisionTransformer.forward`` (reference vit.py:224-248) with ``ViTEncoder.forward``
-    (vit.py:90-95): ``+pos_embedding``, L blocks, LN, cls sum, head."""
+    (vit.py:90-95): ``+pos_embedding``, L blocks, LN, cls sum, head.  ``noise`` (optional) describes a NoiseBlock spliced in
+    before block ``noise['layer']`` by ``add_noise`` (reference utils/utils.py:162-191)."""
     x = _tokens(images, sd, cfg)
     x = x + sd["encoder.pos_embedding"].to(x.dtype)
     for i in range(cfg["num_layers"]):
+        if noise is not None and noise["layer"] == i:
+            x = noise_block(x, noise)
         x = vit_block(x, sd, f"encoder.layers.{i}", cfg["num_heads"])
+    if noise is not None and noise["layer"] >= cfg["num_layers"]:
+        x = noise_block(x, noise)
     return _head(x, sd, cfg), {}
 
 

@@ -327,6 +327,62 @@ extern "C" int pk_patchify_u8(const unsigned char* images_hwc, void* patches, in
   return check_cuda(cudaGetLastError(), "patchify_u8_kernel");
 }
 
+// ------------------------------------------------------------------------------ NoiseBlock (blocks.py:100-188)
+// Gaussian noise at a signal-to-noise ratio: per token row, power = mean(x^2), x += noise * sqrt(power / 10^(snr_db/10))
+// (forward_snr, blocks.py:117-131).  One warp per row; the row is read twice (second pass from L1/L2).
+__global__ void noise_snr_kernel(float* __restrict__ x, const float* __restrict__ noise, int rows, int dim, float inv_snr_lin) {
+  const int lane = threadIdx.x & 31;
+  const int d4 = dim / 4;
+  for (long long r = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); r < rows; r += static_cast<long long>(gridDim.x) * (blockDim.x / 32)) {
+    float4* xr = reinterpret_cast<float4*>(x + r * dim);
+    const float4* nr = reinterpret_cast<const float4*>(noise + r * dim);
+    float ss = 0.f;
+    for (int c = lane; c < d4; c += 32) {
+      const float4 v = xr[c];
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss = warp_sum(ss);
+    const float sd = sqrtf(ss / static_cast<float>(dim) * inv_snr_lin);
+    for (int c = lane; c < d4; c += 32) {
+      float4 v = xr[c];
+      const float4 n = ldg4(reinterpret_cast<const float*>(nr + c));
+      v.x = fmaf(n.x, sd, v.x); v.y = fmaf(n.y, sd, v.y); v.z = fmaf(n.z, sd, v.z); v.w = fmaf(n.w, sd, v.w);
+      xr[c] = v;
+    }
+  }
+}
+
+extern "C" int pk_noise_snr(float* x, const float* noise, int rows, int dim, float snr_db, void* stream) {
+  PK_REQUIRE(x && noise && rows >= 0 && dim % 4 == 0 && dim >= 4, "pk_noise_snr: bad arguments");
+  if (rows == 0) return PK_OK;
+  const float inv_snr_lin = 1.0f / powf(10.0f, snr_db / 10.0f);
+  noise_snr_kernel<<<grid_for(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, noise, rows, dim, inv_snr_lin);
+  return check_cuda(cudaGetLastError(), "noise_snr_kernel");
+}
+
+// Token drop: rows (b, tokens[j]) of every sample are zeroed (forward_token_drop, blocks.py:141-157).
+__global__ void zero_token_rows_kernel(float* __restrict__ x, int batch, int seq, const int* __restrict__ tokens, int n_tokens, int dim) {
+  const int d4 = dim / 4;
+  const long long total = static_cast<long long>(batch) * n_tokens * d4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % d4);
+    const long long r = i / d4;
+    const int j = static_cast<int>(r % n_tokens);
+    const long long b = r / n_tokens;
+    reinterpret_cast<float4*>(x + (b * seq + tokens[j]) * static_cast<long long>(dim))[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+extern "C" int pk_zero_token_rows(float* x, int batch, int seq, const int* tokens, int n_tokens, int dim, void* stream) {
+  PK_REQUIRE(x && (tokens || n_tokens == 0) && batch >= 0 && seq > 0 && n_tokens >= 0 && n_tokens <= seq && dim % 4 == 0,
+             "pk_zero_token_rows: bad arguments");
+  if (batch == 0 || n_tokens == 0) return PK_OK;
+  const long long total = static_cast<long long>(batch) * n_tokens * (dim / 4);
+  zero_token_rows_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, batch, seq, tokens, n_tokens, dim);
+  return check_cuda(cudaGetLastError(), "zero_token_rows_kernel");
+}
+
 extern "C" int pk_fill_token_rows(float* x, int batch, int seq_stride, int row_offset, int n_tokens, int dim,
                                   const float* tokens, const float* pos, float scale, void* stream) {
   PK_REQUIRE(x && dim % 4 == 0, "pk_fill_token_rows: null x or dim %% 4 != 0");

@@ -134,7 +134,29 @@ def _pack_ln_fold(blk) -> Dict[str, torch.Tensor]:
 def _block_kind(blk) -> str:
     name = type(blk).__name__
     return {"ViTBlock": "vit", "RankViTBlock": "rank", "ResidualViTBlock": "residual", "AViTBlock": "avit",
-            "ViTBlockMoE": "moe"}.get(name, name)
+            "ViTBlockMoE": "moe", "NoiseBlock": "noise"}.get(name, name)
+
+
+def apply_noise(blk, x: torch.Tensor, batch: int, seq: int) -> None:
+    """NoiseBlock.forward (reference blocks.py:159-170) on the fp32 token rows x [batch*seq, D], in place.  The random
+    draws are torch's, like the reference (``randn_like`` on the device generator, ``randperm`` on the host generator):
+    Gaussian noise scaled per token to the requested SNR, or the same randomly chosen token positions zeroed in every
+    sample.  ``blk`` is read live, so ``set_value`` between forwards takes effect without repacking."""
+    rows, D = batch * seq, x.shape[-1]
+    if blk.snr_db is not None:
+        if blk.snr_db == 0:                      # blocks.py:125-127: an SNR of exactly 0 dB means "no noise" there
+            return
+        noise = torch.randn((batch, seq, D), dtype=torch.float32, device=x.device)
+        ops.noise_snr(x, noise.view(rows, D), float(blk.snr_db), rows)
+    elif blk.std is not None:
+        raise ValueError("std is not supported anymore. Please use snr instead.")
+    else:
+        if blk.prob == 0:
+            return
+        num_mask = int(blk.prob * seq)           # blocks.py:151 (TypeError for an unset block, like the reference)
+        idx = torch.randperm(seq)[:num_mask]
+        if num_mask > 0:
+            ops.zero_token_rows(x, batch, seq, idx.to(device=x.device, dtype=torch.int32))
 
 
 def pack_model(model, family: str) -> PackedModel:
@@ -142,10 +164,17 @@ def pack_model(model, family: str) -> PackedModel:
     layers: List[LayerWeights] = []
     for blk in model.encoder.layers:
         kind = _block_kind(blk)
+        if kind == "noise":
+            if family not in ("vit", "rankvit", "moevit"):
+                # the compacted ResidualViT / A-ViT row layouts do not materialise dropped rows, which independent per-row
+                # noise would make distinct (and the reference's A-ViT loop cannot run a NoiseBlock either, adavit.py:170-176)
+                raise NotImplementedError(f"NoiseBlock inside a {family} encoder is not supported on the B200 path")
+            layers.append(LayerWeights("noise", None, None, None, None, 0.0, [], [], {}, blk))
+            continue
         if kind not in ("vit", "rank", "residual", "avit", "moe"):
             raise NotImplementedError(
-                f"encoder.layers contains a {type(blk).__name__}; only the reference's transformer blocks run on the "
-                "B200 path (NoiseBlock splicing, reference utils/utils.py:162-191, is outside the hot-path scope)")
+                f"encoder.layers contains a {type(blk).__name__}; only the reference's transformer blocks and NoiseBlock "
+                "run on the B200 path")
         if kind == "moe":
             attn = [_pack_attn(e.self_attention) for e in blk.self_attention.experts]
             mlps = [_pack_mlp(e) for e in blk.mlp.experts]
@@ -183,7 +212,7 @@ def pack_model(model, family: str) -> PackedModel:
     n_reg = int(getattr(model, "num_registers", 0) or 0) if family != "moevit" else 0
     pm = PackedModel(
         family=family, image_size=model.image_size, patch_size=model.patch_size, dim=D,
-        heads=model.encoder.layers[0].num_heads if len(model.encoder.layers) else model.num_heads,
+        heads=next((b.num_heads for b in model.encoder.layers if hasattr(b, "num_heads")), model.num_heads),
         num_classes=model.num_classes, n_cls=cls.shape[1], n_reg=n_reg,
         w_patch=_bf16(model.conv_proj.weight.reshape(D, -1)), b_patch=_f32(model.conv_proj.bias),
         cls_tokens=_f32(cls.reshape(-1, D)),
@@ -225,8 +254,9 @@ def pack_model(model, family: str) -> PackedModel:
 
 
 def params_fingerprint(model) -> tuple:
-    """Changes whenever a parameter is rebound, moved or modified in place."""
-    return tuple((p.data_ptr(), p._version) for p in model.parameters()) + (len(model.encoder.layers),)
+    """Changes whenever a parameter is rebound, moved or modified in place, or ``encoder.layers`` is edited
+    (layers deleted, a parameter-free NoiseBlock spliced in)."""
+    return tuple((p.data_ptr(), p._version) for p in model.parameters()) + tuple(id(b) for b in model.encoder.layers)
 
 
 class Workspace:
@@ -438,7 +468,10 @@ class Forward:
                 self.dense_block_fused(x, lw, rows, B, seq, xb, stats, emit_last=i + 1 < len(pm.layers))
         else:
             for lw in pm.layers:
-                self.dense_block(x, lw, rows, B, seq)
+                if lw.kind == "noise":
+                    apply_noise(lw.module, x, B, seq)
+                else:
+                    self.dense_block(x, lw, rows, B, seq)
         return self.head(x, B, seq)
 
     # ---------------------------------------------------------------- RankViT
@@ -455,6 +488,10 @@ class Forward:
         flip = 0
         L = len(pm.layers)
         for i, lw in enumerate(pm.layers):
+            if lw.kind == "noise":
+                apply_noise(lw.module, x, B, seq)
+                fold = None
+                continue
             b = budgets.get(i, 1.0) if lw.kind == "rank" else 1.0
             if lw.kind == "rank" and b != 1:
                 n = seq - 1
@@ -637,6 +674,9 @@ class Forward:
         rows = B * seq
         x = self.embed(images)
         for i, lw in enumerate(pm.layers):
+            if lw.kind == "noise":
+                apply_noise(lw.module, x, B, seq)
+                continue
             EA = len(lw.attn)
             if EA == 1:
                 self.attn_part(x, lw, rows, B, seq=seq)

@@ -1,2 +1,2 @@
-"""Drop-ins for the parameter-bearing classes of reference models/blocks.py."""
-from .core import MLP, SelfAttention  # noqa: F401
+"""Drop-ins for the classes of reference models/blocks.py that the model families and utils.add_noise use."""
+from .core import MLP, SelfAttention, NoiseBlock  # noqa: F401

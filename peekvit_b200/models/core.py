@@ -54,6 +54,49 @@ class SelfAttention(nn.Module):
     forward = _no_forward
 
 
+class NoiseBlock(nn.Module):
+    """Drop-in for reference models/blocks.py:100-188: Gaussian noise at a signal-to-noise ratio (dB) or token dropping,
+    spliced into ``encoder.layers`` by ``add_noise`` (utils/utils.py:162-191).  Same constructor, setters and attributes;
+    inside a model forward the block runs as one kernel on the residual stream (peekvit_b200.engine), and calling it directly
+    on a (B, N, D) CUDA tensor does the same out of place.  Noise is drawn with ``torch.randn`` / ``torch.randperm`` from
+    torch's generators exactly like the reference, so seeding behaves the same."""
+
+    def __init__(self, noise_type: Literal["gaussian", "token_drop"] = "gaussian", snr=None, std=None, prob=None):
+        super().__init__()
+        self.noise_type = noise_type
+        self.snr_db, self.std, self.prob = snr, std, prob
+        if not any([snr, std, prob]):
+            print("Lazy initialization of noise block. Please set the noise parameters using set_snr, set_std or set_prob "
+                  "before using the block.")
+        if std:
+            raise ValueError("std is not supported anymore. Please use snr instead.")
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor):
+        from .. import engine
+        if not x.is_cuda:
+            raise RuntimeError("peekvit_b200 has no CPU path: NoiseBlock needs a CUDA tensor")
+        torch._assert(x.dim() == 3, f"Expected (batch_size, seq_length, hidden_dim) got {x.shape}")
+        B, N, D = x.shape
+        y = x.detach().to(torch.float32).contiguous().clone().view(B * N, D)
+        engine.apply_noise(self, y, B, N)
+        return y.view(B, N, D)
+
+    def set_snr(self, snr: float):
+        assert self.noise_type == "gaussian"
+        self.snr_db, self.std, self.prob = snr, None, None
+
+    def set_prob(self, prob: float):
+        assert self.noise_type == "token_drop"
+        self.snr_db, self.std, self.prob = None, None, prob
+
+    def set_value(self, value: float):
+        if self.noise_type == "gaussian":
+            self.set_snr(value)
+        else:
+            self.set_prob(value)
+
+
 class _BlockBase(nn.Module):
     def __init__(self, num_heads, hidden_dim, mlp_dim, dropout, attention_dropout, ln_eps=1e-5):
         super().__init__()

@@ -1,6 +1,11 @@
-"""Model registry with the reference's aliases (reference models/models.py:15-86) for the five
-families on the B200 hot path.  ``build_model`` keeps the reference signature; noise injection
-and layer stitching are outside the hot-path scope and raise."""
+"""Model registry with the reference's aliases (reference models/models.py:15-86) for the families on the B200 hot
+path.  ``build_model`` keeps the reference signature, including ``noise_args`` (a NoiseBlock spliced into
+``encoder.layers``, utils/utils.py:162-191) and ``remove_layers``."""
+from collections import OrderedDict
+
+import torch
+
+from .core import NoiseBlock
 from .core import (AdaptiveVisionTransformer, EEResidualVisionTransformer, RankVisionTransformer, ResidualVisionTransformer,
                    VisionTransformer, VisionTransformerMoE)
 
@@ -27,5 +32,21 @@ def build_model(model_class, model_args, noise_args=None, remove_layers=None):
     if remove_layers is not None:
         model.remove_layers(list(remove_layers))
     if noise_args is not None and noise_args != {}:
-        raise NotImplementedError("NoiseBlock injection (reference utils/utils.py:162-191) is outside the B200 hot-path scope")
+        noise_module = add_noise(model, **noise_args)
+        noise_module.set_value(0.0)                 # models.py:80-83: loaded with the noise switched off
+        print("Loaded model with noise. Noise will be set to 0.0, you can change this by calling "
+              "model.noise_module.set_value(new_noise_value)")
     return model
+
+
+def add_noise(model, layer: int, noise_type: str, std: float = None, snr: float = None, prob: float = None, **kwargs):
+    """Mirror of reference utils/utils.py:162-191: insert a NoiseBlock before ``encoder.layers[layer]`` and return it."""
+    noise_module = NoiseBlock(noise_type=noise_type, std=std, snr=snr, prob=prob)
+    new_layers = list(model.encoder.layers)
+    if new_layers and isinstance(new_layers[0], tuple):
+        new_layers.insert(layer, ("noise", noise_module))
+        model.encoder.layers = torch.nn.Sequential(OrderedDict(new_layers))
+    else:
+        new_layers.insert(layer, noise_module)
+        model.encoder.layers = torch.nn.Sequential(*new_layers)
+    return noise_module

@@ -350,6 +350,22 @@ def expert_onehot(expert: torch.Tensor, n_experts: int, out: torch.Tensor, rows:
     return out
 
 
+def noise_snr(x: torch.Tensor, noise: torch.Tensor, snr_db: float, rows: Optional[int] = None) -> torch.Tensor:
+    """x[r] += noise[r] * sqrt(mean(x[r]^2) / 10^(snr_db/10)), in place."""
+    lib = _lib_for(x)
+    n = x.shape[0] if rows is None else rows
+    check(lib.pk_noise_snr(_ptr(x, torch.float32), _ptr(noise, torch.float32), n, x.shape[-1], float(snr_db), _stream()), "pk_noise_snr")
+    return x
+
+
+def zero_token_rows(x: torch.Tensor, batch: int, seq: int, tokens: torch.Tensor) -> torch.Tensor:
+    """x[b*seq + tokens[j]] = 0 for every sample b, in place."""
+    lib = _lib_for(x)
+    check(lib.pk_zero_token_rows(_ptr(x, torch.float32), batch, seq, _ptr(tokens, torch.int32), tokens.numel(), x.shape[-1], _stream()),
+          "pk_zero_token_rows")
+    return x
+
+
 def gemm_row_stat_parts(n: int) -> int:
     """Statistics slots per row written by the LayerNorm-producer epilogue for an n-column output."""
     return int(_lib.load().pk_gemm_row_stat_parts(n))

@@ -95,6 +95,8 @@ def _graphed(model, fwd: engine.Forward, chunk: torch.Tensor, aux: Optional[dict
     from . import ops
     if not USE_CUDA_GRAPHS or ops.gemm_timeline is not None or torch.cuda.is_current_stream_capturing():
         return None
+    if any(lw.kind == "noise" for lw in fwd.pm.layers):      # fresh random draws (and host-side randperm) every forward
+        return None
     st = _state(model)
     graphs = st.setdefault("graphs", {})
     # The only kernel that reads the caller's image tensor is the im2col: it is launched eagerly into a workspace buffer,

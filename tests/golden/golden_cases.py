@@ -53,7 +53,30 @@ CASES = {
         family="eeresidualvit", batch=4, weight_seed=19, image_seed=30, budget=0.4, calibrate=0.4,
         cfg=dict(_BASE, gate_type="sigmoid", gate_temp=1.0, gate_bias=0.0, gate_threshold=0.5,
                  add_budget_token="learnable", residual_layers=["attention+mlp"] * 4)),
+    # NoiseBlock spliced in front of a block by add_noise (utils/utils.py:162-191; blocks.py:100-188)
+    "vit_noise_snr": dict(
+        family="vit", batch=3, weight_seed=22, image_seed=32, noise_seed=77,
+        noise=dict(layer=1, noise_type="gaussian", snr=10.0),
+        cfg=dict(_BASE, num_layers=3)),
+    "vit_noise_token_drop": dict(
+        family="vit", batch=3, weight_seed=22, image_seed=32, noise_seed=78,
+        noise=dict(layer=2, noise_type="token_drop", prob=0.3),
+        cfg=dict(_BASE, num_layers=3)),
 }
+
+
+def oracle_noise(case, device="cpu"):
+    """The random draw the NoiseBlock of ``case`` makes, regenerated from ``noise_seed`` on ``device``'s torch generator,
+    in the form ``oracle.peekvit_oracle.noise_block`` takes.  Call order matters: this must be the first consumer of the
+    generator after seeding, exactly like the forward it is compared with."""
+    import torch
+    nz, cfg = case["noise"], case["cfg"]
+    n_tok = (cfg["image_size"] // cfg["patch_size"]) ** 2 + cfg.get("num_class_tokens", 1) + cfg.get("num_registers", 0)
+    torch.manual_seed(case["noise_seed"])
+    if nz["noise_type"] == "gaussian":
+        return dict(layer=nz["layer"], snr_db=nz["snr"],
+                    noise=torch.randn(case["batch"], n_tok, cfg["hidden_dim"], device=device).cpu())
+    return dict(layer=nz["layer"], prob=nz["prob"], perm=torch.randperm(n_tok))
 
 
 def build_case(case):

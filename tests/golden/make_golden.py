@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import weights as ow  # noqa: E402
 from oracle import peekvit_oracle as po  # noqa: E402
-from golden_cases import CASES, build_case  # noqa: E402
+from golden_cases import CASES, build_case, oracle_noise  # noqa: E402
 
 
 def import_reference():
@@ -74,6 +74,12 @@ def main():
         model.eval()
         if budget is not None:
             model.set_budget(budget)
+        noise = None
+        if case.get("noise") is not None:
+            from peekvit.utils.utils import add_noise                    # the reference's own splice (utils/utils.py:162-191)
+            add_noise(model, **case["noise"])
+            noise = oracle_noise(case)                                   # same seed, drawn first: what the forward below draws
+            torch.manual_seed(case["noise_seed"])
         out = {}
         with torch.no_grad():
             if fam == "rankvit":
@@ -86,7 +92,14 @@ def main():
                 assert torch.equal(logits, logits_default)
             else:
                 logits = model(images)
-        o_logits, aux = po.forward(fam, sd, cfg, images, budget)
+        if noise is not None:
+            with torch.no_grad():
+                o_logits, aux = po.vit_forward(sd, cfg, images, noise=noise)
+            with torch.no_grad():
+                clean, _ = po.vit_forward(sd, cfg, images)
+            assert (clean - logits).abs().max() > 1e-3, "the noise block had no effect: vacuous fixture"
+        else:
+            o_logits, aux = po.forward(fam, sd, cfg, images, budget)
         if fam == "eeresidualvit":
             # outputs are a list: one early exit per layer, then the final logits (eeresidualvit.py:355-357)
             assert len(logits) == cfg["num_layers"] + 1 == len(o_logits)

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_cases import CASES, build_case
+from golden_cases import CASES, build_case, oracle_noise
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -30,7 +30,44 @@ def _model(case):
     return model, sd, images
 
 
-@pytest.mark.parametrize("name", [n for n in sorted(CASES) if CASES[n]["family"] in BUILT])
+@pytest.mark.parametrize("name", [n for n in sorted(CASES) if CASES[n].get("noise") is not None])
+def test_noise_block_matches_oracle_and_fixture(name):
+    """NoiseBlock spliced in by add_noise (utils/utils.py:162-191).  The draw comes from torch's generators like in the
+    reference: re-seeding and drawing the same tensor first gives the oracle the exact noise the CUDA path used.  Token
+    dropping draws its permutation on the host generator, so it also reproduces the reference fixture itself."""
+    from oracle import peekvit_oracle as po
+    from peekvit_b200 import ops
+    from peekvit_b200.models import add_noise, build_model, NoiseBlock
+    case = CASES[name]
+    model, sd, images = _model(case)
+    clean = model(images.to(DEV)).cpu()
+    nb = add_noise(model, **case["noise"])
+    assert isinstance(nb, NoiseBlock) and model.encoder.layers[case["noise"]["layer"]] is nb
+    torch.manual_seed(case["noise_seed"])
+    logits = model(images.to(DEV)).cpu()
+    assert ops.device_flag() == 0
+    with torch.no_grad():
+        ref, _ = po.vit_forward(sd, case["cfg"], images, noise=oracle_noise(case, device=DEV))
+    scale = ref.abs().max()
+    assert ((logits - ref).abs().max() / scale).item() < TOL_LOGITS
+    assert ((logits - clean).abs().max() / scale).item() > 5 * TOL_LOGITS          # the noise really acted
+    if case["noise"]["noise_type"] == "token_drop":
+        gold = np.load(os.path.join(GOLD, name + ".npz"))["logits"]
+        assert np.abs(logits.numpy() - gold).max() / np.abs(gold).max() < TOL_LOGITS
+    nb.set_value(0.0)                                   # 0 dB / probability 0 switch the block off (blocks.py:125-127,:145)
+    assert torch.equal(model(images.to(DEV)).cpu(), clean)
+    # standalone call on a (B, N, D) tensor
+    x = torch.randn(2, 7, 64, device=DEV)
+    g = NoiseBlock("gaussian", snr=5.0)
+    torch.manual_seed(3)
+    y = g(x)
+    torch.manual_seed(3)
+    n = torch.randn(2, 7, 64, device=DEV)
+    exp = x + n * torch.sqrt((x ** 2).mean(-1, keepdim=True) / 10 ** 0.5)
+    assert torch.allclose(y, exp, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", [n for n in sorted(CASES) if CASES[n]["family"] in BUILT and CASES[n].get("noise") is None])
 def test_model_matches_reference_fixture(name):
     from peekvit_b200 import ops, runner
     case = CASES[name]

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_cases import CASES, build_case
+from golden_cases import CASES, build_case, oracle_noise
 from oracle import peekvit_oracle as po
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -17,7 +17,12 @@ def test_oracle_matches_reference_fixture(name):
     case = CASES[name]
     ref = np.load(os.path.join(GOLD, name + ".npz"))
     sd, images = build_case(case)
-    logits, aux = po.forward(case["family"], sd, case["cfg"], images, case.get("budget"))
+    if case.get("noise") is not None:
+        # NoiseBlock cases: the reference drew from torch's CPU generator under noise_seed; the same draw is regenerated here
+        with torch.no_grad():
+            logits, aux = po.vit_forward(sd, case["cfg"], images, noise=oracle_noise(case))
+    else:
+        logits, aux = po.forward(case["family"], sd, case["cfg"], images, case.get("budget"))
     if case["family"] == "eeresidualvit":
         # list output: one early exit per layer, then the final logits (eeresidualvit.py:355-357)
         assert len(logits) == case["cfg"]["num_layers"] + 1
