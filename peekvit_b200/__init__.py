@@ -15,7 +15,7 @@ import types
 
 __version__ = "0.1.0"
 
-_SHIM_MODULES = ("vit", "rankvit", "residualvit", "eeresidualvit", "adavit", "moevit", "models", "blocks")
+_SHIM_MODULES = ("vit", "rankvit", "residualvit", "eeresidualvit", "adavit", "moevit", "models", "blocks", "adapters")
 
 
 def install_as_peekvit() -> None:
