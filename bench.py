@@ -327,7 +327,7 @@ def main():
                     "api": "VisionTransformer.forward_host(pinned images) -> pinned logits"},
             "e2e_uint8_input": {"value": world * B * e2e_steps / (e2e_u8_ms * 1e-3), "unit": "images/sec",
                                 "h2d_bytes_per_step": host_u8.numel(), "note": "same call with uint8 HWC images; ToTensor + Normalize fused into the im2col"},
-            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_pair_kernel (tcgen05 cta_group::2: QKV / out-proj / fc1+GELU / fc2) + gemm_bf16_tcgen05_kernel (patch GEMM)",
+            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_pair_kernel (tcgen05 cta_group::2: patch embedding / QKV / out-proj / fc1+GELU / fc2)",
                          "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                          "peak_source": peaks["source"], "traffic": traffic, "launches": len(timeline),
                          "avg_launch_ms": gemm_ms / max(len(timeline), 1), "share_of_step": gemm_ms / eager_ms,

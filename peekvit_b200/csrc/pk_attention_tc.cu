@@ -541,6 +541,344 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
   }
 }
 
+// ======================================================================================================================
+// Column-split variant ("tc3"): 16 softmax warps.  The per-region chain  S ready -> max -> exp -> PV -> O out -> region free
+// is what bounds the kernel (6400 cycles per item with the MUFU busy half of the time), and its longest link is the softmax
+// of one 128-row tile on four warps.  Here every TMEM lane quarter of a region is served by TWO warps that split the S row by
+// columns (16-column groups [0, G0) and [G0, G)): partial row maxima are exchanged through shared memory behind a 64-thread
+// named barrier, partial row sums are added by the output warp.  Each half packs its probabilities into the S columns it has
+// already consumed itself (half 0 at column 8j, half 1 at 16*G0 + 8(j - G0)), so the halves never touch each other's columns
+// and the PV MMA simply takes its A operand of k-step j from the matching address.  O moves to region columns [192, 256).
+// 24 warps: TMA, 2 MMA issuers, 1 idle, 16 softmax, 4 output; registers 88 (softmax) / 64 (others) = the whole 768 x 80 pool.
+constexpr int kTc3Threads = 768;
+constexpr int kTc3RegsSoftmax = 88;
+constexpr int kTc3RegsOther = 64;
+constexpr int kTc3OCol = 192;
+template <int NPAD>
+struct Tc3Smem {
+  using B = TcSmem<NPAD>;
+  static constexpr int kPartOff = B::kStageOff + kTcOutStageBytes;            // row-max and row-sum partials: [2][region][half][128] f32
+  static constexpr int kBarOff = kPartOff + 4096;
+  static constexpr int kBytes = kBarOff + 256 /* barriers */ + 1024 /* alignment */;
+  static_assert(kBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+// trace slots: warps 0-11 as they are, output warps 20-23 in slots 12-15
+__device__ __forceinline__ void tc3_trace(const TcAttParams& p, int it, int ev) {
+  if (p.trace && blockIdx.x == 0 && it < 16 && (threadIdx.x & 31) == 0) {
+    const int w = threadIdx.x >> 5;
+    const int slot = w < 12 ? w : (w >= 20 ? w - 8 : -1);
+    if (slot >= 0) p.trace[(it * 16 + slot) * 8 + ev] = clock64();
+  }
+}
+
+// Softmax of one item for the column groups of one half of the row.
+template <int NPAD, int HALF, int POLY>
+__device__ __forceinline__ void tc3_softmax_item(uint32_t t_base, int n, float scale_log2, float* mx_mine, const float* mx_other,
+                                                 float* sum_mine, int bar_id, const TcAttParams& p, int it) {
+  const int debug = p.debug;
+  constexpr int G = NPAD / 16, G0 = (G + 1) / 2;
+  constexpr int GB = HALF ? G0 : 0;                 // first 16-column group of this half
+  constexpr int GN = HALF ? G - G0 : G0;            // number of groups
+  constexpr int PCOL0 = HALF ? 16 * G0 : 0;         // where this half packs its probabilities
+  const uint32_t s_col = t_base + static_cast<uint32_t>(16 * GB);
+  uint32_t ha[16], hb[16];
+  // ---- pass 1: partial row maximum, the next group's TMEM load in flight while the current one is reduced
+  float mx = -INFINITY;
+  if (!(debug & 1)) {
+    tmem_ld_32x32_x16(s_col, ha);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < GN; ++j) {
+      uint32_t (&cur)[16] = (j & 1) ? hb : ha;
+      uint32_t (&nxt)[16] = (j & 1) ? ha : hb;
+      if (j + 1 < GN) tmem_ld_32x32_x16(s_col + static_cast<uint32_t>(16 * (j + 1)), nxt);
+      if (HALF == 1 && j == GN - 1) mx = row_max16<true>(cur, mx, 16 * (GB + j), n);     // only the row's last group can hold padding
+      else mx = row_max16<false>(cur, mx, 0, n);
+      if (j + 1 < GN) tmem_ld_wait();
+    }
+  } else {
+    mx = 0.f;
+  }
+  *mx_mine = mx;
+  tc3_trace(p, it, 4);
+  named_bar_sync(bar_id, 64);
+  mx = fmaxf(mx, *mx_other);
+  tc3_trace(p, it, 2);
+  const float neg_max_scaled = -mx * scale_log2;
+  // ---- pass 2: p = exp2(s*scale - max*scale), partial row sum, bf16 P packed over this half's own consumed S columns
+  float sum = 0.f;
+  if (!(debug & 2)) {
+    tmem_ld_32x32_x16(s_col, ha);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < GN; ++j) {
+      uint32_t (&cur)[16] = (j & 1) ? hb : ha;
+      uint32_t (&nxt)[16] = (j & 1) ? ha : hb;
+      if (j + 1 < GN) tmem_ld_32x32_x16(s_col + static_cast<uint32_t>(16 * (j + 1)), nxt);
+      uint32_t pk[8];
+      if (HALF == 1 && j == GN - 1) sum += softmax_group16<true, POLY>(cur, pk, scale_log2, neg_max_scaled, 16 * (GB + j), n);
+      else sum += softmax_group16<false, POLY>(cur, pk, scale_log2, neg_max_scaled, 0, n);
+      if (j + 1 < GN) tmem_ld_wait();
+      tmem_st_32x32_x8(t_base + static_cast<uint32_t>(PCOL0 + 8 * j), pk);   // lands on S group GB + j/2: already in registers
+    }
+  } else {
+    sum = 0.5f;
+  }
+  *sum_mine = sum;
+  tmem_st_wait();
+}
+
+template <int NPAD, int POLY = 0>
+__global__ void __launch_bounds__(kTc3Threads, 1)
+attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_constant__ CUtensorMap tmap_kv,
+                     const __grid_constant__ CUtensorMap tmap_out, const TcAttParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using SM = TcSmem<NPAD>;
+  using SM3 = Tc3Smem<NPAD>;
+  uint8_t* out_stage = smem + SM::kStageOff;
+  float* mx_part = reinterpret_cast<float*>(smem + SM3::kPartOff);                 // [region][half][128]
+  float* sum_part = mx_part + 512;                                                  // [region][half][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM3::kBarOff);
+  uint64_t* qk_full = bars;            // [2]
+  uint64_t* qk_empty = bars + 2;       // [2]
+  uint64_t* v_full = bars + 4;         // [3]
+  uint64_t* v_empty = bars + 7;        // [3]
+  uint64_t* s_full = bars + 10;        // [2] region: S ready (umma commit)
+  uint64_t* p_ready = bars + 12;       // [2] region: P written (8 softmax-warp arrivals)
+  uint64_t* o_full = bars + 14;        // [2] region: O ready (umma commit)
+  uint64_t* s_free = bars + 16;        // [2] region: O read out (4 output-warp arrivals)
+  uint64_t* sum_ready = bars + 18;     // [2] region: row-sum partials published (8 softmax-warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = warp_id();
+  const int lane = lane_id();
+  const int n = p.seq_len;
+  const int D = p.num_heads * kTcDH;
+  const int num_items = p.batch * p.num_heads;
+  constexpr int G = NPAD / 16, G0 = (G + 1) / 2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q128);
+    tma_prefetch_desc(&tmap_kv);
+    tma_prefetch_desc(&tmap_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(smem_u32(&v_full[i]), 1);
+      mbar_init(smem_u32(&v_empty[i]), 2);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&qk_full[i]), 1);
+      mbar_init(smem_u32(&qk_empty[i]), 2);
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&p_ready[i]), 8);
+      mbar_init(smem_u32(&o_full[i]), 1);
+      mbar_init(smem_u32(&s_free[i]), 4);
+      mbar_init(smem_u32(&sum_ready[i]), 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    setmaxnreg_dec<kTc3RegsOther>();
+    int qs = 0, vs = 0;
+    uint32_t qph = 0, vph = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int b = item / p.num_heads, h = item - b * p.num_heads;
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&qk_empty[qs]), qph ^ 1u, p.flag, 0x2100u + qs))) break;
+      tc3_trace(p, (item - blockIdx.x) / gridDim.x, 0);
+      if (elect_one()) {
+        const uint32_t bar = smem_u32(&qk_full[qs]);
+        const uint32_t base = smem_u32(smem + qs * SM::kQKSlotBytes);
+        mbar_expect_tx(bar, SM::kQKSlotBytes);
+        tma_load_3d(base, &tmap_q128, bar, h * kTcDH, 0, b);
+        tma_load_3d(base + kTcQTileBytes, &tmap_q128, bar, h * kTcDH, 128, b);
+        tma_load_3d(base + 2 * kTcQTileBytes, &tmap_kv, bar, D + h * kTcDH, 0, b);
+      }
+      __syncwarp();
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&v_empty[vs]), vph ^ 1u, p.flag, 0x2110u + vs))) break;
+      tc3_trace(p, (item - blockIdx.x) / gridDim.x, 1);
+      if (elect_one()) {
+        const uint32_t bar = smem_u32(&v_full[vs]);
+        mbar_expect_tx(bar, SM::kKBytes);
+        tma_load_3d(smem_u32(smem + SM::kVOff + vs * SM::kKBytes), &tmap_kv, bar, 2 * D + h * kTcDH, 0, b);
+      }
+      __syncwarp();
+      if (++qs == SM::kQKSlots) { qs = 0; qph ^= 1u; }
+      if (++vs == SM::kVSlots) { vs = 0; vph ^= 1u; }
+    }
+  } else if (warp == 1 || warp == 2) {
+    // ------------------------------------------------------------------ MMA issuers: warp 1 -> query tile 0, warp 2 -> tile 1
+    setmaxnreg_dec<kTc3RegsOther>();
+    const int r = warp - 1;
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(128, NPAD);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, kTcDH, /*b_mn_major=*/1);
+    const uint32_t s_tmem = tmem_base + static_cast<uint32_t>(r * kTcRegionCols);
+    int qs = 0, vs = 0;
+    uint32_t qph = 0, vph = 0, rph = 0;
+    bool first = true;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int it = (item - blockIdx.x) / gridDim.x;
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&qk_full[qs]), qph, p.flag, 0x2200u + qs))) break;
+      tc3_trace(p, it, 4);
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&s_free[r]), rph ^ 1u, p.flag, 0x2300u + r))) break;
+      if (first && r == 1) {
+        if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&p_ready[0]), 0u, p.flag, 0x2310u))) break;
+      }
+      first = false;
+      tcgen05_fence_after();
+      const uint32_t base = smem_u32(smem + qs * SM::kQKSlotBytes);
+      tc3_trace(p, it, 0);
+      if (elect_one()) {                       // S_r = Q_r K^T
+        const uint64_t a_desc = umma_desc_kmajor_sw128(base + r * kTcQTileBytes);
+        const uint64_t b_desc = umma_desc_kmajor_sw128(base + 2 * kTcQTileBytes);
+#pragma unroll
+        for (int k = 0; k < kTcDH / 16; ++k)
+          umma_bf16(s_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(smem_u32(&s_full[r]));
+        umma_commit(smem_u32(&qk_empty[qs]));
+      }
+      __syncwarp();
+      tc3_trace(p, it, 1);
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&p_ready[r]), rph, p.flag, 0x2400u + r))) break;
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&v_full[vs]), vph, p.flag, 0x2410u + vs))) break;
+      tcgen05_fence_after();
+      tc3_trace(p, it, 2);
+      if (elect_one()) {                       // O_r = P_r V; P of key group k sits where the half that owns it packed it
+        const uint64_t v_desc = umma_desc_mnmajor_sw128(smem_u32(smem + SM::kVOff + vs * SM::kKBytes));
+        const uint32_t o_tmem = s_tmem + kTc3OCol;
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+          const uint32_t p_col = k < G0 ? static_cast<uint32_t>(8 * k) : static_cast<uint32_t>(16 * G0 + 8 * (k - G0));
+          umma_bf16_ts(o_tmem, s_tmem + p_col, v_desc + static_cast<uint64_t>(128 * k), idesc_pv, k != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&o_full[r]));
+        umma_commit(smem_u32(&v_empty[vs]));
+      }
+      __syncwarp();
+      tc3_trace(p, it, 3);
+      rph ^= 1u;
+      if (++qs == SM::kQKSlots) { qs = 0; qph ^= 1u; }
+      if (++vs == SM::kVSlots) { vs = 0; vph ^= 1u; }
+    }
+  } else if (warp == 3) {
+    setmaxnreg_dec<kTc3RegsOther>();
+  } else if (warp < 20) {
+    // ------------------------------------------------------------------ softmax warps: 8 per query tile = 4 lane quarters x 2 column halves
+    setmaxnreg_inc<kTc3RegsSoftmax>();
+    const int r = (warp - 4) >> 3;               // query tile / TMEM region
+    const int half = ((warp - 4) >> 2) & 1;      // column half of the S row
+    const int q = warp & 3;                      // TMEM lane quarter
+    const bool warp_has_rows = r * 128 + q * 32 < n;          // warp-uniform, same for both halves of a quarter
+    const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(r * kTcRegionCols);
+    float* mx_mine = mx_part + (r * 2 + half) * 128 + q * 32 + lane;
+    const float* mx_other = mx_part + (r * 2 + (half ^ 1)) * 128 + q * 32 + lane;
+    float* sum_mine = sum_part + (r * 2 + half) * 128 + q * 32 + lane;
+    const int bar_id = 1 + r * 4 + q;
+    const float scale_log2 = p.scale_log2;
+    uint32_t rph = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int it = (item - blockIdx.x) / gridDim.x;
+      tc3_trace(p, it, 0);
+      if (!mbar_wait(smem_u32(&s_full[r]), rph, p.flag, 0x2500u + r)) break;
+      tcgen05_fence_after();
+      tc3_trace(p, it, 1);
+      if (warp_has_rows) {
+        if (half == 0) tc3_softmax_item<NPAD, 0, POLY>(t_base, n, scale_log2, mx_mine, mx_other, sum_mine, bar_id, p, it);
+        else tc3_softmax_item<NPAD, 1, POLY>(t_base, n, scale_log2, mx_mine, mx_other, sum_mine, bar_id, p, it);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&p_ready[r]));
+        mbar_arrive(smem_u32(&sum_ready[r]));
+      }
+      tc3_trace(p, it, 3);
+      rph ^= 1u;
+    }
+  } else {
+    // ------------------------------------------------------------------ output warps (one per TMEM lane quarter, both regions)
+    setmaxnreg_dec<kTc3RegsOther>();
+    const int q = warp & 3;
+    uint8_t* stg = out_stage + q * 4096;
+    uint32_t rph = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int it = (item - blockIdx.x) / gridDim.x;
+      const int b = item / p.num_heads, h = item - b * p.num_heads;
+      bool ok = true;
+      for (int r = 0; r < 2; ++r) {
+        const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(r * kTcRegionCols);
+        const int row0 = r * 128 + q * 32;
+        if (!mbar_wait(smem_u32(&sum_ready[r]), rph, p.flag, 0x2700u + r)) { ok = false; break; }
+        if (!mbar_wait(smem_u32(&o_full[r]), rph, p.flag, 0x2600u + r)) { ok = false; break; }
+        tcgen05_fence_after();
+        tc3_trace(p, it, r * 3 + 0);
+        const bool has_rows = row0 < n;          // warp-uniform
+        const float inv = 1.0f / (sum_part[(r * 2 + 0) * 128 + q * 32 + lane] + sum_part[(r * 2 + 1) * 128 + q * 32 + lane]);
+        // O row out of TMEM in two 32-column halves; the first is scaled and packed while the second is in flight
+        uint32_t o[32], pk0[16];
+        if (has_rows) {
+          tmem_ld_32x32(t_base + kTc3OCol, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) pk0[c] = pack_bf16(__uint_as_float(o[2 * c]) * inv, __uint_as_float(o[2 * c + 1]) * inv);
+          tmem_ld_32x32(t_base + kTc3OCol + 32, o);
+          tmem_ld_wait();
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s_free[r]));         // the region may take the next item's S
+        if (has_rows && !(p.debug & 4)) {
+          if (lane == 0) bulk_wait_read<0>();                     // the previous store has drained this staging tile
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                make_uint4(pk0[4 * c], pk0[4 * c + 1], pk0[4 * c + 2], pk0[4 * c + 3]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + c) ^ (lane & 7)) << 4)) =
+                make_uint4(pack_bf16(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv),
+                           pack_bf16(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv),
+                           pack_bf16(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv),
+                           pack_bf16(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv));
+          tc3_trace(p, it, r * 3 + 1);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmap_out, smem_u32(stg), h * kTcDH, row0, b);
+            bulk_commit();
+          }
+        }
+        tc3_trace(p, it, r * 3 + 2);
+      }
+      if (!ok) break;
+      rph ^= 1u;
+    }
+    if (lane == 0) bulk_wait_read<0>();       // smem must outlive the last store's reads
+  }
+
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // 3-D view of the packed qkv buffer: (column, token in sample, sample)
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t ld_elems,
                       uint32_t box_rows);
@@ -609,6 +947,43 @@ int launch_attention_tc(const pk_attention_args* a, cudaStream_t stream) {
   const long long items = static_cast<long long>(a->batch) * a->num_heads;
   int grid = num_sms();
   if (items < grid) grid = static_cast<int>(items);
+  // PK_ATT_TC_SPLIT=0 selects the 8-softmax-warp kernel (one thread per S row) instead of the column-split one
+  static int split = -1;
+  if (split < 0) { const char* e = getenv("PK_ATT_TC_SPLIT"); split = e ? atoi(e) : 1; }
+  static int poly = -1;        // experiment: PK_ATT_TC_POLY=1|2 of every 4 column pairs take the FMA-pipe exp2 (n_pad 208 only)
+  if (poly < 0) { const char* e = getenv("PK_ATT_TC_POLY"); poly = e ? atoi(e) : 0; }
+  if (split && n_pad == 208 && (poly == 1 || poly == 2)) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      PK_CHECK_CUDA(cudaFuncSetAttribute(attention_tc3_kernel<208, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc3Smem<208>::kBytes));
+      PK_CHECK_CUDA(cudaFuncSetAttribute(attention_tc3_kernel<208, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc3Smem<208>::kBytes));
+      attr_set = true;
+    }
+    if (poly == 1) attention_tc3_kernel<208, 1><<<grid, kTc3Threads, Tc3Smem<208>::kBytes, stream>>>(tq, tkv, tout, p);
+    else attention_tc3_kernel<208, 2><<<grid, kTc3Threads, Tc3Smem<208>::kBytes, stream>>>(tq, tkv, tout, p);
+    return check_cuda(cudaGetLastError(), "attention_tc3_kernel launch");
+  }
+  if (split) {
+    switch (n_pad) {
+#define PK_TC3_CASE(NP)                                                                                                 \
+  case NP: {                                                                                                            \
+    static bool attr_set = false;                                                                                       \
+    if (!attr_set) {                                                                                                    \
+      PK_CHECK_CUDA(cudaFuncSetAttribute(attention_tc3_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc3Smem<NP>::kBytes)); \
+      attr_set = true;                                                                                                  \
+    }                                                                                                                   \
+    attention_tc3_kernel<NP><<<grid, kTc3Threads, Tc3Smem<NP>::kBytes, stream>>>(tq, tkv, tout, p);                       \
+    break;                                                                                                              \
+  }
+      PK_TC3_CASE(32) PK_TC3_CASE(48) PK_TC3_CASE(64) PK_TC3_CASE(80) PK_TC3_CASE(96) PK_TC3_CASE(112) PK_TC3_CASE(128)
+      PK_TC3_CASE(144) PK_TC3_CASE(160) PK_TC3_CASE(176) PK_TC3_CASE(192) PK_TC3_CASE(208) PK_TC3_CASE(224) PK_TC3_CASE(240) PK_TC3_CASE(256)
+#undef PK_TC3_CASE
+      default:
+        set_last_error("pk_attention_fwd: unsupported padded length %d", n_pad);
+        return PK_ERR_INVALID;
+    }
+    return check_cuda(cudaGetLastError(), "attention_tc3_kernel launch");
+  }
   switch (n_pad) {
 #define PK_TC_CASE(NP)                                                                                                  \
   case NP: {                                                                                                            \

@@ -19,8 +19,9 @@ t = buf.reshape(16, 16, 8).astype(np.int64)
 t0 = t[t > 0].min()
 t = np.where(t > 0, t - t0, -1)
 names_mma = ["ready", "qk_issued", "p_ready", "pv_issued", "kv_full"]
-names_sm = ["loop_top", "s_full", "max_done", "p_written"]
+names_sm = ["loop_top", "s_full", "max_done", "p_written", "max_own"]
 names_out = ["r0_o_full", "r0_staged", "r0_stored", "r1_o_full", "r1_staged", "r1_stored"]
+# column-split kernel (default): warps 4-7 = region 0 / column half 0, 8-11 = region 0 / half 1; output warps in slots 12-15
 for it in range(7, 9):
     print(f"--- item {it}")
     print("  tma   ", {"qk_slot_free": int(t[it, 0, 0]), "v_slot_free": int(t[it, 0, 1])})
