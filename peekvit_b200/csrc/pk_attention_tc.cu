@@ -549,10 +549,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
 // named barrier, partial row sums are added by the output warp.  Each half packs its probabilities into the S columns it has
 // already consumed itself (half 0 at column 8j, half 1 at 16*G0 + 8(j - G0)), so the halves never touch each other's columns
 // and the PV MMA simply takes its A operand of k-step j from the matching address.  O moves to region columns [192, 256).
-// 24 warps: TMA, 2 MMA issuers, 1 idle, 16 softmax, 4 output; registers 88 (softmax) / 64 (others) = the whole 768 x 80 pool.
+// 24 warps: TMA, 2 MMA issuers, 1 idle, 16 softmax, 4 output; registers per role 40 / 56 / 40 / 80 / 88 out of the 768 x 80 pool.
 constexpr int kTc3Threads = 768;
-constexpr int kTc3RegsSoftmax = 88;
-constexpr int kTc3RegsOther = 64;
+constexpr int kTc3RegsSoftmax = 80;
+constexpr int kTc3RegsOther = 40;                  // TMA producer, idle warp
+constexpr int kTc3RegsMma = 56;
+constexpr int kTc3RegsOut = 88;                    // both 32-column halves of the O row in flight
 constexpr int kTc3OCol = 192;
 template <int NPAD>
 struct Tc3Smem {
@@ -584,19 +586,25 @@ __device__ __forceinline__ void tc3_softmax_item(uint32_t t_base, int n, float s
   constexpr int PCOL0 = HALF ? 16 * G0 : 0;         // where this half packs its probabilities
   const uint32_t s_col = t_base + static_cast<uint32_t>(16 * GB);
   uint32_t ha[16], hb[16];
-  // ---- pass 1: partial row maximum, the next group's TMEM load in flight while the current one is reduced
+  // ---- pass 1: partial row maximum.  The pass is bound by the TMEM load round trip (the 16 max instructions of a group are
+  // nothing against it), so it moves 32 columns per trip
   float mx = -INFINITY;
   if (!(debug & 1)) {
-    tmem_ld_32x32_x16(s_col, ha);
-    tmem_ld_wait();
+    constexpr int G32 = GN / 2;                     // 32-column steps; an odd group is left for a final 16-column step
 #pragma unroll
-    for (int j = 0; j < GN; ++j) {
-      uint32_t (&cur)[16] = (j & 1) ? hb : ha;
-      uint32_t (&nxt)[16] = (j & 1) ? ha : hb;
-      if (j + 1 < GN) tmem_ld_32x32_x16(s_col + static_cast<uint32_t>(16 * (j + 1)), nxt);
-      if (HALF == 1 && j == GN - 1) mx = row_max16<true>(cur, mx, 16 * (GB + j), n);     // only the row's last group can hold padding
-      else mx = row_max16<false>(cur, mx, 0, n);
-      if (j + 1 < GN) tmem_ld_wait();
+    for (int j = 0; j < G32; ++j) {
+      uint32_t w[32];
+      tmem_ld_32x32(s_col + static_cast<uint32_t>(32 * j), w);
+      tmem_ld_wait();
+      mx = row_max16<false>(w, mx, 0, n);
+      if (HALF == 1 && 2 * j + 1 == GN - 1) mx = row_max16<true>(w + 16, mx, 16 * (GB + 2 * j + 1), n);   // the row's last group can hold padding
+      else mx = row_max16<false>(w + 16, mx, 0, n);
+    }
+    if constexpr (GN % 2 == 1) {
+      tmem_ld_32x32_x16(s_col + static_cast<uint32_t>(32 * G32), ha);
+      tmem_ld_wait();
+      if (HALF == 1) mx = row_max16<true>(ha, mx, 16 * (GB + GN - 1), n);
+      else mx = row_max16<false>(ha, mx, 0, n);
     }
   } else {
     mx = 0.f;
@@ -721,7 +729,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
     }
   } else if (warp == 1 || warp == 2) {
     // ------------------------------------------------------------------ MMA issuers: warp 1 -> query tile 0, warp 2 -> tile 1
-    setmaxnreg_dec<kTc3RegsOther>();
+    setmaxnreg_dec<kTc3RegsMma>();
     const int r = warp - 1;
     constexpr uint32_t idesc_qk = umma_idesc_bf16(128, NPAD);
     constexpr uint32_t idesc_pv = umma_idesc_bf16(128, kTcDH, /*b_mn_major=*/1);
@@ -810,7 +818,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
     }
   } else {
     // ------------------------------------------------------------------ output warps (one per TMEM lane quarter, both regions)
-    setmaxnreg_dec<kTc3RegsOther>();
+    setmaxnreg_inc<kTc3RegsOut>();
     const int q = warp & 3;
     uint8_t* stg = out_stage + q * 4096;
     uint32_t rph = 0;
@@ -827,13 +835,10 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
         tc3_trace(p, it, r * 3 + 0);
         const bool has_rows = row0 < n;          // warp-uniform
         const float inv = 1.0f / (sum_part[(r * 2 + 0) * 128 + q * 32 + lane] + sum_part[(r * 2 + 1) * 128 + q * 32 + lane]);
-        // O row out of TMEM in two 32-column halves; the first is scaled and packed while the second is in flight
-        uint32_t o[32], pk0[16];
+        // O row: both 32-column halves in flight at once, so the region is handed back after a single TMEM round trip
+        uint32_t o0[32], o[32];
         if (has_rows) {
-          tmem_ld_32x32(t_base + kTc3OCol, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 16; ++c) pk0[c] = pack_bf16(__uint_as_float(o[2 * c]) * inv, __uint_as_float(o[2 * c + 1]) * inv);
+          tmem_ld_32x32(t_base + kTc3OCol, o0);
           tmem_ld_32x32(t_base + kTc3OCol + 32, o);
           tmem_ld_wait();
         }
@@ -846,7 +851,10 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
-                make_uint4(pk0[4 * c], pk0[4 * c + 1], pk0[4 * c + 2], pk0[4 * c + 3]);
+                make_uint4(pack_bf16(__uint_as_float(o0[8 * c]) * inv, __uint_as_float(o0[8 * c + 1]) * inv),
+                           pack_bf16(__uint_as_float(o0[8 * c + 2]) * inv, __uint_as_float(o0[8 * c + 3]) * inv),
+                           pack_bf16(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv),
+                           pack_bf16(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv));
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + c) ^ (lane & 7)) << 4)) =
