@@ -139,8 +139,8 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if not os.path.exists(path) or os.environ.get("PEEKVIT_B200_REBUILD") == "1":
+    path = os.environ.get("PEEKVIT_B200_LIB") or _build.LIB_PATH      # override: A/B runs of two builds on the same box
+    if path == _build.LIB_PATH and (not os.path.exists(path) or os.environ.get("PEEKVIT_B200_REBUILD") == "1"):
         path = _build.build(force=True)
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():

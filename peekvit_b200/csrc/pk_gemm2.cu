@@ -53,8 +53,13 @@ struct PairCfg {
   static constexpr int kABytes = kP_BM * kP_BK * 2;
   static constexpr int kBBytes = (BN / 2) * kP_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSlotBytes = kP_BufBytes + (LN == 1 ? 2048 : 0);           // + a 32x32 bf16 tile for the LN producer
-  static constexpr int kStagingBytes = EW * kBufs * kSlotBytes;
+  static constexpr int kSlotBytes = kP_BufBytes;
+  // LN producer: two 32x32 bf16 tiles per warp for the bf16 row copy.  They sit behind the residual ring instead of widening
+  // its three slots: 64 KB of staging instead of 72 KB is what lets the main loop keep 5 operand stages (fc2 streams its
+  // 620 MB A operand from DRAM; with 4 stages the tensor pipe idled a third of the time).
+  static constexpr int kXbBytes = LN == 1 ? 2 * 2048 : 0;
+  static constexpr int kWarpStagingBytes = kBufs * kSlotBytes + kXbBytes;
+  static constexpr int kStagingBytes = EW * kWarpStagingBytes;
   static_assert(LN != 1 || (kResid && EW == 4), "the LN producer is the staged-residual epilogue with one warp per lane quarter");
   static_assert(LN != 2 || kOutBf16, "the LN consumer is a bf16 epilogue");
   static constexpr int kBarBytes = 1024;
@@ -305,7 +310,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     constexpr int kChunks = Cfg::kChunks;
     constexpr int kBufs = Cfg::kBufs;
     constexpr int kSlot = Cfg::kSlotBytes;
-    uint8_t* ebuf = staging + ew * kBufs * kSlot;                       // 1024-byte aligned
+    uint8_t* ebuf = staging + ew * Cfg::kWarpStagingBytes;               // 1024-byte aligned
     const uint32_t ebuf_u32 = smem_u32(ebuf);
     uint64_t* rbar = res_bar + 3 * ew;
     const int my_tiles = pair < num_tiles ? (num_tiles - pair + num_pairs - 1) / num_pairs : 0;
@@ -469,7 +474,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
               // bf16 copy: 64-byte rows, 16-byte chunk j of row r at chunk j ^ ((r >> 1) & 3) (SWIZZLE_64B)
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<uint4*>(bufp + kP_BufBytes + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                *reinterpret_cast<uint4*>(ebuf + kBufs * kSlot + (g & 1u) * 2048 + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
                     make_uint4(xbp[4 * j], xbp[4 * j + 1], xbp[4 * j + 2], xbp[4 * j + 3]);
             }
           }
@@ -479,7 +484,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             if (lane == 0) {
               if constexpr (RED) tma_reduce_add_2d(&tmap_out, ebuf_u32 + b * kSlot, col0 - sub * 32, row_base);
               else tma_store_2d(&tmap_out, ebuf_u32 + b * kSlot, col0 - sub * 32, row_base);
-              if constexpr (LN == 1) tma_store_2d(&tmap_xb, ebuf_u32 + b * kSlot + kP_BufBytes, col0, row_base);
+              if constexpr (LN == 1) tma_store_2d(&tmap_xb, ebuf_u32 + kBufs * kSlot + (g & 1u) * 2048, col0, row_base);
               bulk_commit();
             }
           }
@@ -518,11 +523,16 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         if (sub == kUPS - 1) {
           if constexpr (kResid) {
             // buffer (g+2)%3 was last read by the store of chunk g-1: one chunk of work ago
-            if (lane == 0 && g + 2 < total_chunks) {
+            if (lane == 0 && (LN == 1 || g + 2 < total_chunks)) {
               bulk_wait_read<1>();
-              if (ch + 2 < kChunks) issue_resid(g + 2, t, ch + 2);
-              else issue_resid(g + 2, t + num_pairs, ch + 2 - kChunks);
+              if (g + 2 < total_chunks) {
+                if (ch + 2 < kChunks) issue_resid(g + 2, t, ch + 2);
+                else issue_resid(g + 2, t + num_pairs, ch + 2 - kChunks);
+              }
             }
+            // LN producer: the bf16 tile of chunk g+1 is the one chunk g-1 stored from; its drain (just waited for by lane 0)
+            // must be visible to every lane before they write it
+            if constexpr (LN == 1) __syncwarp();
           }
           ++g;
         }

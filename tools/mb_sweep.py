@@ -12,6 +12,6 @@ def timed(fn, n=5):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(n): fn()
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e3
-for mb in (256, 512, 683, 1024, 2048, 512, 256):
+for mb in [int(a) for a in sys.argv[1:]] or (256, 512, 683, 1024, 2048, 512, 256):
     model.pk_micro_batch = mb
     print(f"mb={mb}: device {timed(lambda: model(images)):.2f} host {timed(lambda: model.forward_host(host, out_host)):.2f}", flush=True)
