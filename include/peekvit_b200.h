@@ -261,6 +261,19 @@ int pk_noise_snr(float* x, const float* noise, int rows, int dim, float snr_db, 
  * (the same randperm prefix for the whole batch). */
 int pk_zero_token_rows(float* x, int batch, int seq, const int* tokens, int n_tokens, int dim, void* stream);
 
+/* ---- fp32-accurate mode (the reference's shipped dtype; north star: logits within 1e-5).  GEMMs run on the same bf16
+ * tcgen05 kernels with 3-way split operands: x = h + m + l in bf16, products {mm, lh, hl, mh, hm, hh} laid along K' = 6K,
+ * small terms first.  pk_split3_bf16 writes the ACTIVATION-side row [m|l|h|m|h|h] (out bf16 [rows, 6*dim]) of x f32 [rows, dim],
+ * optionally after mode 1 = exact erf GELU (blocks.py:82) or mode 2 = LayerNorm(gamma, beta, eps) (vit.py:48,53).  The matching
+ * WEIGHT-side row is [m|h|l|h|m|h]. */
+int pk_split3_bf16(const float* x, void* out, int rows, int dim, int mode, const float* gamma, const float* beta, float eps,
+                   void* stream);
+/* im2col of f32 NCHW images into split activation rows: patches6 bf16 [B*(S/p)^2, 6*3*p*p] (vit.py:203-222, fp32 mode). */
+int pk_patchify_split3(const float* images, void* patches6, int batch, int image_size, int patch_size, void* stream);
+/* fp32 attention core on the CUDA cores: qkv f32 [B*n, 3*H*dh] (q|k|v) -> out f32 [B*n, H*dh], uniform length n, dh 32 or 64
+ * (blocks.py:93-95, fp32 mode). */
+int pk_attention_f32(const float* qkv, float* out, int batch, int num_heads, int head_dim, int seq_len, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,266 @@
+// peekvit_b200 — fp32-accurate ("exact") mode kernels (sm_100a).
+//
+// The reference runs in fp32 as shipped; BASELINE's north star asks for logits within 1e-5 in an fp32 mode next to the
+// bf16 headline mode.  The GEMMs of this mode run on the SAME tcgen05 bf16 kernels: an fp32 value is split into three
+// bf16 terms x = h + m + l (8 + 8 + 8 mantissa bits, each difference exact in fp32), and the six products that matter
+//     m*m, l*h, h*l, m*h, h*m, h*h            (dropped: m*l, l*m, l*l ~ 2^-24)
+// are laid side by side along K, so one bf16 GEMM with K' = 6K accumulates them all in the fp32 TMEM accumulator.  The
+// small terms come FIRST: the tensor core aligns every partial sum to the running accumulator, so adding the 2^-16 terms
+// to an already large sum loses them (measured, tools/split_probe.py, K = 3072: big-first 3.1e-5, small-first 3.6e-6 of
+// max|out| against a float64 reference, where torch's own fp32 matmul has 2.2e-6).
+//   activations  A' = [ m | l | h | m | h | h ]      (pk_split3_bf16, optionally after LayerNorm or exact GELU)
+//   weights      W' = [ m | h | l | h | m | h ]      (prepacked on the host side once per weight version)
+// Attention runs in plain fp32 on the CUDA cores (pk_attention_f32): its share of the FLOPs is 4 %.
+#include "pk_common.cuh"
+#include "../../include/peekvit_b200.h"
+
+namespace pk {
+
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
+  h = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(h);
+  m = __float2bfloat16_rn(r1);
+  l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+}
+
+__device__ __forceinline__ uint2 pack4(__nv_bfloat16 a, __nv_bfloat16 b, __nv_bfloat16 c, __nv_bfloat16 d) {
+  return make_uint2(static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16),
+                    static_cast<uint32_t>(__bfloat16_as_ushort(c)) | (static_cast<uint32_t>(__bfloat16_as_ushort(d)) << 16));
+}
+
+// four consecutive fp32 values of one row -> the six K-wide segments of the split operand row (activation order)
+__device__ __forceinline__ void store_split4(__nv_bfloat16* orow, int K, int k, float4 v) {
+  __nv_bfloat16 h[4], m[4], l[4];
+  split3(v.x, h[0], m[0], l[0]);
+  split3(v.y, h[1], m[1], l[1]);
+  split3(v.z, h[2], m[2], l[2]);
+  split3(v.w, h[3], m[3], l[3]);
+  const uint2 ph = pack4(h[0], h[1], h[2], h[3]), pm = pack4(m[0], m[1], m[2], m[3]), pl = pack4(l[0], l[1], l[2], l[3]);
+  *reinterpret_cast<uint2*>(orow + 0 * K + k) = pm;
+  *reinterpret_cast<uint2*>(orow + 1 * K + k) = pl;
+  *reinterpret_cast<uint2*>(orow + 2 * K + k) = ph;
+  *reinterpret_cast<uint2*>(orow + 3 * K + k) = pm;
+  *reinterpret_cast<uint2*>(orow + 4 * K + k) = ph;
+  *reinterpret_cast<uint2*>(orow + 5 * K + k) = ph;
+}
+
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// MODE 0: split only; MODE 1: exact (erf) GELU first (reference blocks.py:82)
+template <int MODE>
+__global__ void split3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int K) {
+  const int k4 = K / 4;
+  const long long total = rows * k4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / k4;
+    const int k = static_cast<int>(i - r * k4) * 4;
+    float4 v = *reinterpret_cast<const float4*>(x + r * K + k);
+    if (MODE == 1) { v.x = gelu_exact(v.x); v.y = gelu_exact(v.y); v.z = gelu_exact(v.z); v.w = gelu_exact(v.w); }
+    store_split4(out + r * 6ll * K, K, k, v);
+  }
+}
+
+// LayerNorm (two-pass fp32 statistics, biased variance: nn.LayerNorm) then split.  One warp per row, the row in registers.
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+split3_layernorm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, float eps, int rows, int K) {
+  const int lane = lane_id();
+  const int d4 = K / 4;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int r = blockIdx.x * (blockDim.x >> 5) + warp_id(); r < rows; r += warps_total) {
+    float4 v[MAXV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + i * 32;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < d4) {
+        v[i] = *reinterpret_cast<const float4*>(x + static_cast<long long>(r) * K + c * 4);
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    }
+    const float mean = warp_sum(sum) / static_cast<float>(K);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + i * 32;
+      if (c < d4) {
+        const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+        sq += (a * a + b * b) + (cc * cc + d * d);
+      }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) / static_cast<float>(K) + eps);
+    __nv_bfloat16* orow = out + static_cast<long long>(r) * 6ll * K;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + i * 32;
+      if (c < d4) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + c * 4), b = *reinterpret_cast<const float4*>(beta + c * 4);
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * g.x + b.x;
+        o.y = (v[i].y - mean) * rstd * g.y + b.y;
+        o.z = (v[i].z - mean) * rstd * g.z + b.z;
+        o.w = (v[i].w - mean) * rstd * g.w + b.w;
+        store_split4(orow, K, c * 4, o);
+      }
+    }
+  }
+}
+
+// im2col of fp32 NCHW images straight into split rows (patch q of sample b -> row b*P + q, K order (c,i,j)).
+__global__ void patchify_split3_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int S, int p, int n_side,
+                                       long long total_chunks) {
+  const int Kp = 3 * p * p;
+  const int P = n_side * n_side;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total_chunks;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long e = idx * 4;
+    const long long row = e / Kp;
+    const int k = static_cast<int>(e - row * Kp);
+    const int c = k / (p * p);
+    const int i = (k - c * p * p) / p;
+    const int j = k - c * p * p - i * p;
+    const long long b = row / P;
+    const int patch = static_cast<int>(row - b * P);
+    const int py = patch / n_side, px = patch - py * n_side;
+    const float4 v = *reinterpret_cast<const float4*>(img + ((b * 3 + c) * S + (py * p + i)) * static_cast<long long>(S) + px * p + j);
+    store_split4(out + row * 6ll * Kp, Kp, k, v);
+  }
+}
+
+// ------------------------------------------------------------------------------ fp32 attention (CUDA cores)
+// softmax(q k^T * scale) v for uniform-length samples; qkv fp32 [B*n, 3*H*DH] (q | k | v, heads = DH-column slices), out fp32
+// [B*n, H*DH].  One thread = one query row (q and the output accumulator in registers); a CTA of 128 queries of one (sample,
+// head) streams K / V through shared memory in tiles of 32 keys (every lane reads the same key element: broadcast), with the
+// usual running max / sum per tile.
+template <int DH>
+__global__ void __launch_bounds__(128)
+attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int batch, int heads, int n, float scale) {
+  constexpr int KT = 32;
+  __shared__ __align__(16) float ks[KT][DH];
+  __shared__ __align__(16) float vs[KT][DH];
+  const int bh = blockIdx.y;
+  const int b = bh / heads, h = bh - b * heads;
+  const int D = heads * DH;
+  const int qi = blockIdx.x * 128 + threadIdx.x;
+  const bool valid = qi < n;
+  const float* base = qkv + static_cast<long long>(b) * n * 3 * D + h * DH;
+  float q[DH], o[DH];
+#pragma unroll
+  for (int d = 0; d < DH; d += 4) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) t = *reinterpret_cast<const float4*>(base + static_cast<long long>(qi) * 3 * D + d);
+    q[d] = t.x * scale; q[d + 1] = t.y * scale; q[d + 2] = t.z * scale; q[d + 3] = t.w * scale;   // q pre-scaled like nn.MultiheadAttention
+    o[d] = o[d + 1] = o[d + 2] = o[d + 3] = 0.f;
+  }
+  float mx = -INFINITY, sum = 0.f;
+  for (int j0 = 0; j0 < n; j0 += KT) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < KT * DH / 4; i += 128) {
+      const int j = i / (DH / 4), d = (i - j * (DH / 4)) * 4;
+      float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+      if (j0 + j < n) {
+        const float* row = base + static_cast<long long>(j0 + j) * 3 * D;
+        kk = *reinterpret_cast<const float4*>(row + D + d);
+        vv = *reinterpret_cast<const float4*>(row + 2 * D + d);
+      }
+      *reinterpret_cast<float4*>(&ks[j][d]) = kk;
+      *reinterpret_cast<float4*>(&vs[j][d]) = vv;
+    }
+    __syncthreads();
+    float s[KT];
+    float tmax = mx;
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int d = 0; d < DH; d += 4) {
+        const float4 kk = *reinterpret_cast<const float4*>(&ks[j][d]);
+        acc = fmaf(q[d], kk.x, acc); acc = fmaf(q[d + 1], kk.y, acc); acc = fmaf(q[d + 2], kk.z, acc); acc = fmaf(q[d + 3], kk.w, acc);
+      }
+      s[j] = (j0 + j < n) ? acc : -INFINITY;
+      tmax = fmaxf(tmax, s[j]);
+    }
+    const float corr = expf(mx - tmax);          // exp(-inf) = 0 on the first tile
+    mx = tmax;
+    sum *= corr;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) o[d] *= corr;
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+      const float pj = expf(s[j] - mx);           // masked keys: exp(-inf) = 0
+      sum += pj;
+#pragma unroll
+      for (int d = 0; d < DH; d += 4) {
+        const float4 vv = *reinterpret_cast<const float4*>(&vs[j][d]);
+        o[d] = fmaf(pj, vv.x, o[d]); o[d + 1] = fmaf(pj, vv.y, o[d + 1]); o[d + 2] = fmaf(pj, vv.z, o[d + 2]); o[d + 3] = fmaf(pj, vv.w, o[d + 3]);
+      }
+    }
+  }
+  if (valid) {
+    const float inv = 1.0f / sum;
+    float* orow = out + (static_cast<long long>(b) * n + qi) * D + h * DH;
+#pragma unroll
+    for (int d = 0; d < DH; d += 4)
+      *reinterpret_cast<float4*>(orow + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+  }
+}
+
+static int grid_1d(long long items, int per_block) {
+  const long long blocks = (items + per_block - 1) / per_block;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  return static_cast<int>(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+}  // namespace pk
+
+extern "C" int pk_split3_bf16(const float* x, void* out, int rows, int dim, int mode, const float* gamma, const float* beta, float eps,
+                              void* stream) {
+  using namespace pk;
+  PK_REQUIRE(x && out && rows >= 0 && dim > 0 && dim % 8 == 0, "pk_split3_bf16: null pointer or dim %% 8 != 0");
+  PK_REQUIRE(mode >= 0 && mode <= 2, "pk_split3_bf16: mode must be 0 (none), 1 (GELU) or 2 (LayerNorm)");
+  if (rows == 0) return PK_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  if (mode == 2) {
+    PK_REQUIRE(gamma && beta && dim <= 1024, "pk_split3_bf16: LayerNorm mode needs gamma / beta and dim <= 1024");
+    const int grid = grid_1d(rows, 8);
+    const int maxv = (dim / 4 + 31) / 32;
+    if (maxv <= 2) split3_layernorm_kernel<2><<<grid, 256, 0, s>>>(x, o, gamma, beta, eps, rows, dim);
+    else if (maxv <= 4) split3_layernorm_kernel<4><<<grid, 256, 0, s>>>(x, o, gamma, beta, eps, rows, dim);
+    else split3_layernorm_kernel<8><<<grid, 256, 0, s>>>(x, o, gamma, beta, eps, rows, dim);
+    return check_cuda(cudaGetLastError(), "split3_layernorm_kernel");
+  }
+  const long long total = static_cast<long long>(rows) * (dim / 4);
+  if (mode == 1) split3_kernel<1><<<grid_1d(total, 256), 256, 0, s>>>(x, o, rows, dim);
+  else split3_kernel<0><<<grid_1d(total, 256), 256, 0, s>>>(x, o, rows, dim);
+  return check_cuda(cudaGetLastError(), "split3_kernel");
+}
+
+extern "C" int pk_patchify_split3(const float* images, void* patches6, int batch, int image_size, int patch_size, void* stream) {
+  using namespace pk;
+  PK_REQUIRE(images && patches6, "pk_patchify_split3: null pointer");
+  PK_REQUIRE(patch_size % 8 == 0 && image_size % patch_size == 0, "pk_patchify_split3: patch_size must be a multiple of 8 dividing image_size");
+  if (batch == 0) return PK_OK;
+  const int n_side = image_size / patch_size;
+  const long long total = static_cast<long long>(batch) * n_side * n_side * 3 * patch_size * patch_size / 4;
+  patchify_split3_kernel<<<grid_1d(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      images, static_cast<__nv_bfloat16*>(patches6), image_size, patch_size, n_side, total);
+  return check_cuda(cudaGetLastError(), "patchify_split3_kernel");
+}
+
+extern "C" int pk_attention_f32(const float* qkv, float* out, int batch, int num_heads, int head_dim, int seq_len, float scale,
+                                void* stream) {
+  using namespace pk;
+  PK_REQUIRE(qkv && out && batch >= 0 && num_heads > 0 && seq_len > 0, "pk_attention_f32: bad arguments");
+  PK_REQUIRE(head_dim == 32 || head_dim == 64, "pk_attention_f32: head_dim must be 32 or 64");
+  if (batch == 0) return PK_OK;
+  const dim3 grid((seq_len + 127) / 128, batch * num_heads);
+  PK_REQUIRE(grid.y <= 65535u, "pk_attention_f32: batch * heads = %u exceeds 65535 (use smaller micro-batches)", grid.y);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (head_dim == 64) attention_f32_kernel<64><<<grid, 128, 0, s>>>(qkv, out, batch, num_heads, seq_len, scale);
+  else attention_f32_kernel<32><<<grid, 128, 0, s>>>(qkv, out, batch, num_heads, seq_len, scale);
+  return check_cuda(cudaGetLastError(), "attention_f32_kernel");
+}

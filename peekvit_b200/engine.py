@@ -22,6 +22,7 @@ import os
 
 from . import ops
 from ._lib import PK_EPI_BIAS_BF16, PK_EPI_BIAS_F32, PK_EPI_BIAS_GELU_BF16, PK_EPI_BIAS_RESID_F32
+from .ops import SPLIT_GELU, SPLIT_LAYERNORM, SPLIT_NONE
 
 
 # LayerNorm folded across GEMMs: 0 = separate LayerNorm kernels everywhere; 1 = ln_1 folded into the in-projection (the
@@ -220,6 +221,7 @@ def pack_model(model, family: str) -> PackedModel:
         pos=_f32(model.encoder.pos_embedding.reshape(-1, D)),
         layers=layers, ln_w=_f32(model.encoder.ln.weight), ln_b=_f32(model.encoder.ln.bias), ln_eps=float(model.encoder.ln.eps),
         head_w=_f32(model.head.weight), head_b=_f32(model.head.bias))
+    pm.extra["conv_weight"] = model.conv_proj.weight          # fp32 master, read lazily by the fp32-accurate mode
     if family == "eeresidualvit":
         # EEResidualVisionTransformer (eeresidualvit.py): the ResidualViT forward + one LayerNorm -> Linear head per layer on
         # the first class token (:73-75,:91-96); its budget mode lives in ``.budget`` (:170)
@@ -285,6 +287,8 @@ class Forward:
         # sequence does not depend on where the caller's image tensor lives
         self.patches_ready = False
         self.input_norm = (ops.IMAGENET_MEAN, ops.IMAGENET_STD)      # Normalize statistics of the uint8 input path
+        # fp32-accurate mode (runner: model.pk_precision = "fp32"): split-operand GEMMs, fp32 attention (csrc/pk_exact.cu)
+        self.exact = False
 
     def _embed_geometry(self, batch: int):
         """(tokens per sample of the embedded stream, shift rows after the first class token, token-row layout?).
@@ -405,6 +409,60 @@ class Forward:
         self.attn_part(x, lw, rows, batch, seq=seq)
         self.mlp_part(x, lw, rows)
 
+    # ---- fp32-accurate mode (the reference's shipped dtype): same tcgen05 GEMM kernels on 3-way split bf16 operands
+    def _exact_weights(self, lw: LayerWeights) -> Dict[str, torch.Tensor]:
+        """Split weight rows [m|h|l|h|m|h] of a block, built from the fp32 masters on first use."""
+        c = lw.extra.get("x3")
+        if c is None:
+            blk = lw.module
+            mha = blk.self_attention.self_attention
+            c = lw.extra["x3"] = dict(w_qkv=ops.split3_weight(mha.in_proj_weight), w_o=ops.split3_weight(mha.out_proj.weight),
+                                      w_fc1=ops.split3_weight(blk.mlp.fc1.weight), w_fc2=ops.split3_weight(blk.mlp.fc2.weight))
+        return c
+
+    def gemm_exact(self, a32: torch.Tensor, rows: int, w6: torch.Tensor, bias, out, epilogue: int, mode: int = SPLIT_NONE,
+                   gamma=None, beta=None, eps: float = 0.0, resid=None):
+        """out = epilogue(pre(a32) @ W^T + bias) at fp32 accuracy: pre = none / exact GELU / LayerNorm is applied by the
+        kernel that splits the activation rows, the product runs as one bf16 GEMM over K' = 6K."""
+        K = a32.shape[-1]
+        a6 = self.ws.get(f"a6_{K}", (rows, 6 * K), torch.bfloat16)
+        ops.split3(a32, a6, mode, gamma, beta, eps, rows=rows)
+        return ops.gemm(a6, w6, bias, out, epilogue, resid=resid)
+
+    def embed_exact(self, images: torch.Tensor) -> torch.Tensor:
+        pm = self.pm
+        if images.dtype != torch.float32:
+            raise NotImplementedError("the fp32-accurate mode takes float images (the uint8 input path is a bf16-mode feature)")
+        B = images.shape[0]
+        P, D, T, R, seq = pm.num_patches, pm.dim, pm.n_cls, pm.n_reg, pm.seq_len
+        Kp = pm.w_patch.shape[1]
+        w6 = pm.extra.get("w_patch6")
+        if w6 is None:
+            w6 = pm.extra["w_patch6"] = ops.split3_weight(pm.extra["conv_weight"].reshape(D, -1))
+        patches6 = ops.patchify_split3(images, pm.patch_size, self.ws.get("patches6", (B * P, 6 * Kp), torch.bfloat16))
+        x = self.ws.get("x", (B * seq, D), torch.float32)
+        ops.gemm(patches6, w6, pm.b_patch, x, PK_EPI_BIAS_RESID_F32, resid=pm.pos,
+                 rows_per_group=P, group_stride=seq, group_offset=T + R, resid_is_pos=True, pos_offset=T + R)
+        ops.fill_token_rows(x, B, seq, 0, pm.cls_tokens, pm.pos)
+        if R > 0:
+            ops.fill_token_rows(x, B, seq, T, pm.reg_tokens, pm.pos, pos_offset=T)
+        return x
+
+    def dense_block_exact(self, x: torch.Tensor, lw: LayerWeights, rows: int, batch: int, seq: int) -> None:
+        """ViTBlock (vit.py:45-55) at fp32 accuracy, in place on the residual stream."""
+        pm, ws = self.pm, self.ws
+        D = pm.dim
+        w, aw, mw = self._exact_weights(lw), lw.attn[0], lw.mlp[0]
+        F = mw.b_fc1.shape[0]
+        xr = x[:rows]
+        qkv = self.gemm_exact(xr, rows, w["w_qkv"], aw.b_qkv, ws.get("qkv32", (rows, 3 * D), torch.float32), PK_EPI_BIAS_F32,
+                              SPLIT_LAYERNORM, lw.ln1_w, lw.ln1_b, lw.eps)
+        att = ops.attention_f32(qkv, ws.get("att32", (rows, D), torch.float32), batch, pm.heads, D // pm.heads, seq)
+        self.gemm_exact(att, rows, w["w_o"], aw.b_o, xr, PK_EPI_BIAS_RESID_F32, resid=xr)
+        hid = self.gemm_exact(xr, rows, w["w_fc1"], mw.b_fc1, ws.get("hid32", (rows, F), torch.float32), PK_EPI_BIAS_F32,
+                              SPLIT_LAYERNORM, lw.ln2_w, lw.ln2_b, lw.eps)
+        self.gemm_exact(hid, rows, w["w_fc2"], mw.b_fc2, xr, PK_EPI_BIAS_RESID_F32, SPLIT_GELU, resid=xr)
+
     # ---- LayerNorm fused across GEMMs (dense layers of ViT / RankViT)
     def fold_ok(self, rows: int) -> bool:
         """The fused chain runs on the CTA-pair GEMM: more than one 256-row tile and 16-byte aligned rows."""
@@ -442,6 +500,10 @@ class Forward:
         else:
             ops.gemm(hid, mw.w_fc2, mw.b_fc2, x[:rows], PK_EPI_BIAS_RESID_F32, resid=x[:rows])
 
+    def _bf16_only(self, what: str) -> None:
+        if self.exact:
+            raise NotImplementedError(f"the fp32-accurate mode covers the dense ViT and RankViT paths; {what} runs in bf16 mode only")
+
     def head(self, x: torch.Tensor, batch: int, seq: int, cu_seqlens=None, n_cls: Optional[int] = None) -> torch.Tensor:
         pm = self.pm
         return ops.cls_head(x, batch, seq, pm.n_cls if n_cls is None else n_cls, pm.ln_w, pm.ln_b, pm.ln_eps, pm.head_w, pm.head_b,
@@ -460,6 +522,14 @@ class Forward:
         pm = self.pm
         B, seq = images.shape[0], pm.seq_len
         rows = B * seq
+        if self.exact:
+            x = self.embed_exact(images)
+            for lw in pm.layers:
+                if lw.kind == "noise":
+                    apply_noise(lw.module, x, B, seq)
+                else:
+                    self.dense_block_exact(x, lw, rows, B, seq)
+            return self.head(x, B, seq)
         fold_all = self.fold_ok(rows) and all("fold" in lw.extra for lw in pm.layers)
         x, fold = self.embed(images, emit_fold=fold_all)
         if fold_all:
@@ -484,7 +554,10 @@ class Forward:
         pm, ws = self.pm, self.ws
         B, seq, D = images.shape[0], pm.seq_len, pm.dim
         # (xb, stats) of the current residual stream when valid; the patch GEMM emits them for layer 0
-        x, fold = self.embed(images, emit_fold=bool(pm.layers) and self.fold_ok(B * seq) and "fold" in pm.layers[0].extra)
+        if self.exact:
+            x, fold = self.embed_exact(images), None
+        else:
+            x, fold = self.embed(images, emit_fold=bool(pm.layers) and self.fold_ok(B * seq) and "fold" in pm.layers[0].extra)
         flip = 0
         L = len(pm.layers)
         for i, lw in enumerate(pm.layers):
@@ -509,7 +582,9 @@ class Forward:
             if aux is not None:
                 aux.setdefault("seq_lens", []).append(seq)
             rows = B * seq
-            if self.fold_ok(rows) and "fold" in lw.extra:
+            if self.exact:
+                self.dense_block_exact(x, lw, rows, B, seq)
+            elif self.fold_ok(rows) and "fold" in lw.extra:
                 if fold is None:
                     fold = self.fold_begin(x, rows)
                 self.dense_block_fused(x, lw, rows, B, seq, fold[0], fold[1], emit_last=i + 1 < L)
@@ -523,6 +598,7 @@ class Forward:
         """Budget-token gating with real compaction (reference residualvit.py:587-616, block :197-260).
         Local row layout of a sample: [cls, budget token, live image rows ..., ghost slot]."""
         pm, ws = self.pm, self.ws
+        self._bf16_only("ResidualViT")
         ex = pm.extra
         abt = ex["add_budget_token"]
         B, D, dev = images.shape[0], pm.dim, images.device
@@ -619,6 +695,7 @@ class Forward:
         """ACT halting with real token removal (reference adavit.py:140-219): halted tokens leave the packed
         batch and survive only as a virtual bias key; a sample retires once its class token halts."""
         pm, ws = self.pm, self.ws
+        self._bf16_only("A-ViT")
         ex = pm.extra
         B, D, seq, dev = images.shape[0], pm.dim, pm.seq_len, images.device
         rows_cap = B * seq
@@ -670,6 +747,7 @@ class Forward:
         """Expert MLPs computed only for the tokens routed to them (reference moevit.py:49-61 evaluates every
         expert on every token and selects with a one-hot einsum)."""
         pm, ws = self.pm, self.ws
+        self._bf16_only("MoE-ViT")
         B, seq, D, dev = images.shape[0], pm.seq_len, pm.dim, images.device
         rows = B * seq
         x = self.embed(images)

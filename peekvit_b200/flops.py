@@ -29,7 +29,7 @@ def gflops_per_image(image_size: int, patch_size: int, hidden_dim: int, mlp_dim:
 
 def model_gflops_per_image(model, tokens_per_layer: Optional[Sequence[float]] = None) -> float:
     """Same, reading the shape from a (reference or drop-in) model instance."""
-    blk = model.encoder.layers[0]
+    blk = next(b for b in model.encoder.layers if hasattr(b, "mlp"))       # a NoiseBlock may sit at index 0
     mlp = blk.mlp.experts[0] if hasattr(blk.mlp, "experts") else blk.mlp
     extra = int(getattr(model, "num_class_tokens", 1) or 1) + int(getattr(model, "num_registers", 0) or 0)
     if getattr(model, "add_budget_token", False):

@@ -366,6 +366,44 @@ def zero_token_rows(x: torch.Tensor, batch: int, seq: int, tokens: torch.Tensor)
     return x
 
 
+SPLIT_NONE, SPLIT_GELU, SPLIT_LAYERNORM = 0, 1, 2
+
+
+def split3(x: torch.Tensor, out: torch.Tensor, mode: int = SPLIT_NONE, gamma: Optional[torch.Tensor] = None,
+           beta: Optional[torch.Tensor] = None, eps: float = 0.0, rows: Optional[int] = None) -> torch.Tensor:
+    """fp32 rows -> bf16 split activation rows [m|l|h|m|h|h] (out [rows, 6*dim]), optionally after exact GELU / LayerNorm."""
+    lib = _lib_for(x)
+    n = x.shape[0] if rows is None else rows
+    check(lib.pk_split3_bf16(_ptr(x, torch.float32), _ptr(out, torch.bfloat16), n, x.shape[-1], mode, _ptr(gamma, torch.float32),
+                             _ptr(beta, torch.float32), float(eps), _stream()), "pk_split3_bf16")
+    return out
+
+
+def split3_weight(w: torch.Tensor) -> torch.Tensor:
+    """Host-side prepack of an fp32 ``[N, K]`` weight into the split row [m|h|l|h|m|h] (bf16 [N, 6K]) that pairs with
+    ``split3`` activations: the six K-wide products are mm, lh, hl, mh, hm, hh."""
+    w = w.detach().float()
+    h = w.to(torch.bfloat16)
+    r = w - h.float()
+    m = r.to(torch.bfloat16)
+    l = (r - m.float()).to(torch.bfloat16)
+    return torch.cat([m, h, l, h, m, h], dim=1).contiguous()
+
+
+def patchify_split3(images: torch.Tensor, patch_size: int, out: torch.Tensor) -> torch.Tensor:
+    lib = _lib_for(images)
+    B, _, S, _ = images.shape
+    check(lib.pk_patchify_split3(_ptr(images, torch.float32), _ptr(out, torch.bfloat16), B, S, patch_size, _stream()), "pk_patchify_split3")
+    return out
+
+
+def attention_f32(qkv: torch.Tensor, out: torch.Tensor, batch: int, num_heads: int, head_dim: int, seq_len: int) -> torch.Tensor:
+    lib = _lib_for(qkv)
+    check(lib.pk_attention_f32(_ptr(qkv, torch.float32), _ptr(out, torch.float32), batch, num_heads, head_dim, seq_len,
+                               float(head_dim) ** -0.5, _stream()), "pk_attention_f32")
+    return out
+
+
 def gemm_row_stat_parts(n: int) -> int:
     """Statistics slots per row written by the LayerNorm-producer epilogue for an n-column output."""
     return int(_lib.load().pk_gemm_row_stat_parts(n))

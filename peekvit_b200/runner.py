@@ -14,6 +14,18 @@ import torch
 from . import engine
 
 DEFAULT_MICRO_BATCH = int(os.environ.get("PEEKVIT_B200_MICRO_BATCH", "512"))
+# Arithmetic mode: "bf16" (bf16 GEMM / attention operands, fp32 accumulation: the measured headline mode) or "fp32" (the
+# reference's shipped dtype: 3-way split operands on the same tcgen05 GEMMs + fp32 attention, logits within 1e-5; dense ViT
+# and RankViT).  Per model: ``model.pk_precision = "fp32"``.
+DEFAULT_PRECISION = os.environ.get("PEEKVIT_B200_PRECISION", "bf16")
+EXACT_MICRO_BATCH = 64          # the split activation rows are 6x wider: keep the workspace of the fp32 mode small
+
+
+def _exact(model) -> bool:
+    p = getattr(model, "pk_precision", DEFAULT_PRECISION)
+    if p not in ("bf16", "fp32"):
+        raise ValueError(f"pk_precision must be 'bf16' or 'fp32', got {p!r}")
+    return p == "fp32"
 
 
 def _state(model):
@@ -97,6 +109,8 @@ def _graphed(model, fwd: engine.Forward, chunk: torch.Tensor, aux: Optional[dict
         return None
     if any(lw.kind == "noise" for lw in fwd.pm.layers):      # fresh random draws (and host-side randperm) every forward
         return None
+    if fwd.exact:                                            # parity mode: eager launches
+        return None
     st = _state(model)
     graphs = st.setdefault("graphs", {})
     # The only kernel that reads the caller's image tensor is the im2col: it is launched eagerly into a workspace buffer,
@@ -161,6 +175,8 @@ def _forward_chunk(model, fwd: engine.Forward, chunk: torch.Tensor, aux: Optiona
 
 def _micro_batch(model, B: int) -> int:
     mb = int(getattr(model, "pk_micro_batch", DEFAULT_MICRO_BATCH))
+    if _exact(model):
+        mb = min(mb, EXACT_MICRO_BATCH)
     abt = model.add_budget_token if model._family == "residualvit" else model.budget if model._family == "eeresidualvit" else None
     if abt and abt not in ("learnable", "learnable_interpolate"):
         # a fixed-float budget token thresholds on the mean over the WHOLE batch (residualvit.py:208):
@@ -212,6 +228,7 @@ def run(model, x: torch.Tensor, aux: Optional[dict] = None) -> torch.Tensor:
     with torch.no_grad():
         fwd = engine.Forward(packed(model), workspace(model, dev))
         fwd.input_norm = getattr(model, "pk_input_norm", fwd.input_norm)
+        fwd.exact = _exact(model)
         B = x.shape[0]
         mb = _micro_batch(model, B)
         multi = model._family == "eeresidualvit"        # (L + 1, B, C): one early exit per layer, then the final logits
@@ -256,6 +273,7 @@ def run_host(model, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = Non
         ws = workspace(model, dev)
         fwd = engine.Forward(packed(model), ws)
         fwd.input_norm = getattr(model, "pk_input_norm", fwd.input_norm)
+        fwd.exact = _exact(model)
         mb = min(_micro_batch(model, B), max(B, 1))
         st = _state(model)
         if "copy_stream" not in st:

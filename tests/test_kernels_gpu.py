@@ -548,3 +548,74 @@ def test_gemm_layernorm_fused_chain(ops, shape):
     ops.row_stats_cast(x1_ref.contiguous(), xb2, st2)
     assert rel_err(st2.sum(1)[:, 0], x1_ref.sum(1)) < 1e-5 and torch.equal(xb2, x1_ref.to(torch.bfloat16))
     assert ops.device_flag() == 0
+
+
+# ------------------------------------------------------------------ fp32-accurate mode (csrc/pk_exact.cu)
+TOL_EXACT = 1e-5          # north star: fp32 mode within 1e-5
+
+
+def _split3_ref(x):
+    h = x.to(torch.bfloat16)
+    r = x - h.float()
+    m = r.to(torch.bfloat16)
+    l = (r - m.float()).to(torch.bfloat16)
+    return h, m, l
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_split3_rows(ops, mode):
+    """[m|l|h|m|h|h] segments, bit-exact against the same split written in torch; the three terms reproduce the fp32 value."""
+    rows, K = 37, 384
+    x = torch.randn(rows, K, device=DEV) * 3
+    g, b = torch.randn(K, device=DEV), torch.randn(K, device=DEV)
+    out = torch.zeros(rows, 6 * K, device=DEV, dtype=torch.bfloat16)
+    ops.split3(x, out, mode, g if mode == 2 else None, b if mode == 2 else None, 1e-5)
+    seg = out.view(rows, 6, K)
+    assert torch.equal(seg[:, 0], seg[:, 3]) and torch.equal(seg[:, 2], seg[:, 4]) and torch.equal(seg[:, 2], seg[:, 5])
+    val = seg[:, 2].float() + seg[:, 0].float() + seg[:, 1].float()          # h + m + l
+    if mode == 0:
+        pre = x
+        h, m, l = _split3_ref(x)
+        assert torch.equal(seg[:, 2], h) and torch.equal(seg[:, 0], m) and torch.equal(seg[:, 1], l)
+    elif mode == 1:
+        pre = torch.nn.functional.gelu(x.double()).float()
+    else:
+        pre = torch.nn.functional.layer_norm(x.double(), (K,), g.double(), b.double(), 1e-5).float()
+    assert rel_err(val, pre) < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 256, 192), (1000, 768, 3072)])
+def test_split_gemm_reaches_fp32_accuracy(ops, M, N, K):
+    """One bf16 tcgen05 GEMM over the six split products == the fp32 product (float64 reference), where the plain bf16 GEMM
+    is three decimal digits away."""
+    from peekvit_b200._lib import PK_EPI_BIAS_F32
+    a = torch.randn(M, K, device=DEV)
+    w = torch.randn(N, K, device=DEV) / math.sqrt(K)
+    bias = torch.randn(N, device=DEV) * 0.1
+    ref = a.double() @ w.double().t() + bias.double()
+    a6 = ops.split3(a, torch.empty(M, 6 * K, device=DEV, dtype=torch.bfloat16))
+    out = ops.gemm(a6, ops.split3_weight(w), bias, torch.empty(M, N, device=DEV), PK_EPI_BIAS_F32)
+    assert rel_err(out.double(), ref) < TOL_EXACT
+    plain = ops.gemm(a.to(torch.bfloat16), w.to(torch.bfloat16), bias, torch.empty(M, N, device=DEV), PK_EPI_BIAS_F32)
+    assert rel_err(plain.double(), ref) > 50 * TOL_EXACT
+
+
+@pytest.mark.parametrize("B,H,dh,n", [(3, 2, 64, 197), (2, 8, 32, 785), (5, 3, 64, 17), (2, 2, 32, 130)])
+def test_attention_f32(ops, B, H, dh, n):
+    D = H * dh
+    qkv = torch.randn(B * n, 3 * D, device=DEV)
+    out = ops.attention_f32(qkv, torch.zeros(B * n, D, device=DEV), B, H, dh, n)
+    q, k, v = (t.reshape(B, n, H, dh).transpose(1, 2).double() for t in qkv.view(B, n, 3 * D).split(D, dim=-1))
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * dh ** -0.5, -1) @ v).transpose(1, 2).reshape(B * n, D)
+    assert rel_err(out.double(), ref) < 2e-6
+
+
+def test_patchify_split3(ops):
+    img = torch.randn(3, 3, 48, 48, device=DEV)
+    P, Kp = 9, 3 * 16 * 16
+    out = ops.patchify_split3(img, 16, torch.zeros(3 * P, 6 * Kp, device=DEV, dtype=torch.bfloat16))
+    ref = torch.nn.functional.unfold(img, kernel_size=16, stride=16).transpose(1, 2).reshape(3 * P, Kp)
+    h, m, l = _split3_ref(ref)
+    seg = out.view(3 * P, 6, Kp)
+    assert torch.equal(seg[:, 2], h) and torch.equal(seg[:, 0], m) and torch.equal(seg[:, 1], l)
+    assert torch.equal(seg[:, 3], m) and torch.equal(seg[:, 4], h) and torch.equal(seg[:, 5], h)

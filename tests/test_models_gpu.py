@@ -310,3 +310,58 @@ def test_uint8_input_path_matches_float_path():
     assert torch.equal(model.forward_host(u8.pin_memory()), y_f.cpu())
     with pytest.raises(AssertionError):
         model(torch.zeros(2, 3, 64, 64, dtype=torch.uint8, device=DEV))       # uint8 must be HWC
+
+
+# ------------------------------------------------------------------ fp32-accurate mode
+TOL_FP32_MODE = 1e-5        # north star: logits within 1e-5 relative in fp32 mode
+
+
+@pytest.mark.parametrize("name", ["vit_d64_h2", "vit_d128_regs", "rankvit_b05", "rankvit_list"])
+def test_fp32_mode_matches_reference_fixture(name):
+    """model.pk_precision = 'fp32': split-operand tcgen05 GEMMs + fp32 attention reproduce the reference's fp32 logits to
+    1e-5, and (RankViT) select exactly the reference's kept-token indices."""
+    from peekvit_b200 import ops, runner
+    case = CASES[name]
+    model, sd, images = _model(case)
+    model.pk_precision = "fp32"
+    aux = {}
+    logits = runner.run(model, images.to(DEV), aux).cpu().numpy()
+    assert ops.device_flag() == 0
+    ref = np.load(os.path.join(GOLD, name + ".npz"))
+    assert np.abs(logits - ref["logits"]).max() / np.abs(ref["logits"]).max() < TOL_FP32_MODE
+    if case["family"] == "rankvit":
+        assert aux["seq_lens"] == list(ref["seq_lens"])
+        for i, kept in aux["kept"].items():
+            assert np.array_equal(kept.cpu().numpy(), ref[f"kept_{i}"])          # bit-exact index sets, in order
+    model.pk_precision = "bf16"
+    again = runner.run(model, images.to(DEV)).cpu().numpy()
+    assert 1e-4 < np.abs(again - ref["logits"]).max() / np.abs(ref["logits"]).max() < TOL_LOGITS
+
+
+def test_fp32_mode_config_a_and_vit_b16_against_oracle():
+    """BASELINE config A (vit_tiny p8, 785 tokens, dh 32, the reference's CPU-runnable fp32 case) and the ViT-B/16 shape."""
+    from oracle import peekvit_oracle as po, weights as ow
+    from peekvit_b200.models import VisionTransformer
+    for cfg, n_img in ((dict(image_size=224, patch_size=8, num_layers=4, num_heads=8, hidden_dim=256, mlp_dim=768, num_classes=10), 8),
+                       (dict(image_size=224, patch_size=16, num_layers=12, num_heads=12, hidden_dim=768, mlp_dim=3072, num_classes=1000), 6)):
+        sd = ow.make_state_dict("vit", cfg, seed=4321)
+        images = ow.synthetic_images(n_img, 224, seed=1234)
+        ref, _ = po.forward("vit", sd, cfg, images)
+        model = VisionTransformer(**cfg)
+        model.load_state_dict(sd)
+        model = model.to(DEV).eval()
+        model.pk_precision = "fp32"
+        logits = model(images.to(DEV)).cpu()
+        assert ((logits - ref).abs().max() / ref.abs().max()).item() < TOL_FP32_MODE
+        assert torch.equal(logits.argmax(1), ref.argmax(1))
+
+
+def test_fp32_mode_is_dense_families_only():
+    case = CASES["moevit"]
+    model, sd, images = _model(case)
+    model.pk_precision = "fp32"
+    with pytest.raises(NotImplementedError):
+        model(images.to(DEV))
+    model.pk_precision = "fp16"
+    with pytest.raises(ValueError):
+        model(images.to(DEV))
