@@ -13,12 +13,14 @@ t0 = time.time()
 ref = torch.cat([po.forward("vit", sd, cfg, images[s:s + 32])[0] for s in range(0, N, 32)])
 t_cpu = time.time() - t0
 model = VisionTransformer(**cfg); model.load_state_dict(sd); model = model.cuda().eval()
-logits = model(images.cuda()).cpu()
-err = ((logits - ref).abs().max() / ref.abs().max()).item()
-agree = (logits.argmax(1) == ref.argmax(1)).float().mean().item()
 top2 = ref.topk(2, dim=1).values
 margin = (top2[:, 0] - top2[:, 1])
-dis = (logits.argmax(1) != ref.argmax(1)).nonzero().flatten()
-print(json.dumps(dict(images=N, rel_err=err, top1_agreement=agree, disagreements=int(dis.numel()),
-                      oracle_margin_at_disagreements=[round(float(margin[i]), 5) for i in dis[:8]],
-                      median_margin=float(margin.median()), max_abs_logit=float(ref.abs().max()), cpu_s=round(t_cpu, 1))))
+for mode in ("bf16", "fp32"):
+    model.pk_precision = mode
+    logits = model(images.cuda()).cpu()
+    err = ((logits - ref).abs().max() / ref.abs().max()).item()
+    agree = (logits.argmax(1) == ref.argmax(1)).float().mean().item()
+    dis = (logits.argmax(1) != ref.argmax(1)).nonzero().flatten()
+    print(json.dumps(dict(mode=mode, images=N, rel_err=err, top1_agreement=agree, disagreements=int(dis.numel()),
+                          oracle_margin_at_disagreements=[round(float(margin[i]), 5) for i in dis[:8]],
+                          median_margin=float(margin.median()), max_abs_logit=float(ref.abs().max()), cpu_s=round(t_cpu, 1))))
