@@ -267,12 +267,16 @@ int pk_zero_token_rows(float* x, int batch, int seq, const int* tokens, int n_to
  * optionally after mode 1 = exact erf GELU (blocks.py:82) or mode 2 = LayerNorm(gamma, beta, eps) (vit.py:48,53).  The matching
  * WEIGHT-side row is [m|h|l|h|m|h]. */
 int pk_split3_bf16(const float* x, void* out, int rows, int dim, int mode, const float* gamma, const float* beta, float eps,
-                   void* stream);
+                   const float* rowscale /* optional: pre(x)[r] *= rowscale[r] (soft masks, residualvit.py:252,258) */,
+                   const int* row_index /* optional, LayerNorm mode: output row r reads x[row_index[r]] */,
+                   const int* rows_dev /* optional device-side row count */, void* stream);
 /* im2col of f32 NCHW images into split activation rows: patches6 bf16 [B*(S/p)^2, 6*3*p*p] (vit.py:203-222, fp32 mode). */
 int pk_patchify_split3(const float* images, void* patches6, int batch, int image_size, int patch_size, void* stream);
-/* fp32 attention core on the CUDA cores: qkv f32 [B*n, 3*H*dh] (q|k|v) -> out f32 [B*n, H*dh], uniform length n, dh 32 or 64
- * (blocks.py:93-95, fp32 mode). */
-int pk_attention_f32(const float* qkv, float* out, int batch, int num_heads, int head_dim, int seq_len, float scale, void* stream);
+/* fp32 attention core on the CUDA cores: qkv f32 [rows, 3*H*dh] (q|k|v) -> out f32 [rows, H*dh], dh 32 or 64 (blocks.py:93-95,
+ * fp32 mode).  Uniform samples of seq_len rows, or ragged ones (cu_seqlens int32 [B+1]; seq_len = longest sample); optional
+ * per-key multiplicities and one virtual key per sample, with the meaning they have in pk_attention_args. */
+int pk_attention_f32(const float* qkv, float* out, int batch, int num_heads, int head_dim, int seq_len, float scale,
+                     const int* cu_seqlens, const float* key_mult, const float* extra_kv, const float* extra_mult, void* stream);
 
 #ifdef __cplusplus
 }

@@ -115,9 +115,9 @@ SIGNATURES: Dict[str, tuple] = {
     "pk_avit_halt_plan": (c_int, [C.POINTER(AvitArgs), c_void_p]),
     "pk_scatter_add_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "pk_expert_onehot": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
-    "pk_split3_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p]),
+    "pk_split3_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pk_patchify_split3": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "pk_attention_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "pk_attention_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pk_noise_snr": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "pk_zero_token_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "pk_moe_route": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,

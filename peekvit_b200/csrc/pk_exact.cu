@@ -48,8 +48,10 @@ __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f +
 
 // MODE 0: split only; MODE 1: exact (erf) GELU first (reference blocks.py:82)
 template <int MODE>
-__global__ void split3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int K) {
+__global__ void split3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int K,
+                              const float* __restrict__ rowscale, const int* __restrict__ rows_dev) {
   const int k4 = K / 4;
+  if (rows_dev) rows = min(static_cast<long long>(*rows_dev), rows);
   const long long total = rows * k4;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -57,6 +59,7 @@ __global__ void split3_kernel(const float* __restrict__ x, __nv_bfloat16* __rest
     const int k = static_cast<int>(i - r * k4) * 4;
     float4 v = *reinterpret_cast<const float4*>(x + r * K + k);
     if (MODE == 1) { v.x = gelu_exact(v.x); v.y = gelu_exact(v.y); v.z = gelu_exact(v.z); v.w = gelu_exact(v.w); }
+    if (rowscale) { const float sc = rowscale[r]; v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; }
     store_split4(out + r * 6ll * K, K, k, v);
   }
 }
@@ -65,11 +68,15 @@ __global__ void split3_kernel(const float* __restrict__ x, __nv_bfloat16* __rest
 template <int MAXV>
 __global__ void __launch_bounds__(256)
 split3_layernorm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, const float* __restrict__ gamma,
-                        const float* __restrict__ beta, float eps, int rows, int K) {
+                        const float* __restrict__ beta, float eps, int rows, int K, const float* __restrict__ rowscale,
+                        const int* __restrict__ row_index, const int* __restrict__ rows_dev) {
   const int lane = lane_id();
   const int d4 = K / 4;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
+  if (rows_dev) rows = min(*rows_dev, rows);
   for (int r = blockIdx.x * (blockDim.x >> 5) + warp_id(); r < rows; r += warps_total) {
+    const long long src = row_index ? row_index[r] : r;          // output row r is LN(x[row_index[r]]) (expert-sorted order)
+    const float sc = rowscale ? rowscale[r] : 1.0f;
     float4 v[MAXV];
     float sum = 0.f;
 #pragma unroll
@@ -77,7 +84,7 @@ split3_layernorm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__
       const int c = lane + i * 32;
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < d4) {
-        v[i] = *reinterpret_cast<const float4*>(x + static_cast<long long>(r) * K + c * 4);
+        v[i] = *reinterpret_cast<const float4*>(x + src * K + c * 4);
         sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
       }
     }
@@ -99,10 +106,10 @@ split3_layernorm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__
       if (c < d4) {
         const float4 g = *reinterpret_cast<const float4*>(gamma + c * 4), b = *reinterpret_cast<const float4*>(beta + c * 4);
         float4 o;
-        o.x = (v[i].x - mean) * rstd * g.x + b.x;
-        o.y = (v[i].y - mean) * rstd * g.y + b.y;
-        o.z = (v[i].z - mean) * rstd * g.z + b.z;
-        o.w = (v[i].w - mean) * rstd * g.w + b.w;
+        o.x = sc * ((v[i].x - mean) * rstd * g.x + b.x);
+        o.y = sc * ((v[i].y - mean) * rstd * g.y + b.y);
+        o.z = sc * ((v[i].z - mean) * rstd * g.z + b.z);
+        o.w = sc * ((v[i].w - mean) * rstd * g.w + b.w);
         store_split4(orow, K, c * 4, o);
       }
     }
@@ -131,22 +138,29 @@ __global__ void patchify_split3_kernel(const float* __restrict__ img, __nv_bfloa
 }
 
 // ------------------------------------------------------------------------------ fp32 attention (CUDA cores)
-// softmax(q k^T * scale) v for uniform-length samples; qkv fp32 [B*n, 3*H*DH] (q | k | v, heads = DH-column slices), out fp32
-// [B*n, H*DH].  One thread = one query row (q and the output accumulator in registers); a CTA of 128 queries of one (sample,
+// softmax(q k^T * scale) v; qkv fp32 [rows, 3*H*DH] (q | k | v, heads = DH-column slices), out fp32 [rows, H*DH].  Samples are
+// uniform (n rows each) or ragged (cu_seqlens); a key may carry a multiplicity (logit + log mult: that many identical tokens)
+// and every sample one virtual key (k, v) = extra_kv with multiplicity extra_mult[b] — what the compacted ResidualViT / A-ViT
+// rows need.  One thread = one query row (q and the output accumulator in registers); a CTA of 128 queries of one (sample,
 // head) streams K / V through shared memory in tiles of 32 keys (every lane reads the same key element: broadcast), with the
 // usual running max / sum per tile.
 template <int DH>
 __global__ void __launch_bounds__(128)
-attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int batch, int heads, int n, float scale) {
+attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int batch, int heads, int n_uniform, float scale,
+                     const int* __restrict__ cu_seqlens, const float* __restrict__ key_mult, const float* __restrict__ extra_kv,
+                     const float* __restrict__ extra_mult) {
   constexpr int KT = 32;
   __shared__ __align__(16) float ks[KT][DH];
   __shared__ __align__(16) float vs[KT][DH];
   const int bh = blockIdx.y;
   const int b = bh / heads, h = bh - b * heads;
   const int D = heads * DH;
+  const long long row0 = cu_seqlens ? cu_seqlens[b] : static_cast<long long>(b) * n_uniform;
+  const int n = cu_seqlens ? cu_seqlens[b + 1] - cu_seqlens[b] : n_uniform;
+  if (blockIdx.x * 128 >= n) return;               // block-uniform: ragged grids are sized for the longest sample
   const int qi = blockIdx.x * 128 + threadIdx.x;
   const bool valid = qi < n;
-  const float* base = qkv + static_cast<long long>(b) * n * 3 * D + h * DH;
+  const float* base = qkv + row0 * 3 * D + h * DH;
   float q[DH], o[DH];
 #pragma unroll
   for (int d = 0; d < DH; d += 4) {
@@ -180,6 +194,7 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
         const float4 kk = *reinterpret_cast<const float4*>(&ks[j][d]);
         acc = fmaf(q[d], kk.x, acc); acc = fmaf(q[d + 1], kk.y, acc); acc = fmaf(q[d + 2], kk.z, acc); acc = fmaf(q[d + 3], kk.w, acc);
       }
+      if (key_mult && j0 + j < n) acc += logf(key_mult[row0 + j0 + j]);
       s[j] = (j0 + j < n) ? acc : -INFINITY;
       tmax = fmaxf(tmax, s[j]);
     }
@@ -199,9 +214,25 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
       }
     }
   }
+  const float em = extra_mult ? extra_mult[b] : 0.f;
+  if (extra_kv && em > 0.f) {
+    // the virtual key: what em zero tokens project to (k-bias | v-bias)
+    const float* ke = extra_kv + h * DH;
+    const float* ve = extra_kv + D + h * DH;
+    float acc = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc = fmaf(q[d], ke[d], acc);
+    acc += logf(em);
+    const float tmax = fmaxf(mx, acc);
+    const float corr = expf(mx - tmax);
+    const float pe = expf(acc - tmax);
+    sum = sum * corr + pe;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) o[d] = fmaf(pe, ve[d], o[d] * corr);
+  }
   if (valid) {
     const float inv = 1.0f / sum;
-    float* orow = out + (static_cast<long long>(b) * n + qi) * D + h * DH;
+    float* orow = out + (row0 + qi) * D + h * DH;
 #pragma unroll
     for (int d = 0; d < DH; d += 4)
       *reinterpret_cast<float4*>(orow + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
@@ -217,7 +248,7 @@ static int grid_1d(long long items, int per_block) {
 }  // namespace pk
 
 extern "C" int pk_split3_bf16(const float* x, void* out, int rows, int dim, int mode, const float* gamma, const float* beta, float eps,
-                              void* stream) {
+                              const float* rowscale, const int* row_index, const int* rows_dev, void* stream) {
   using namespace pk;
   PK_REQUIRE(x && out && rows >= 0 && dim > 0 && dim % 8 == 0, "pk_split3_bf16: null pointer or dim %% 8 != 0");
   PK_REQUIRE(mode >= 0 && mode <= 2, "pk_split3_bf16: mode must be 0 (none), 1 (GELU) or 2 (LayerNorm)");
@@ -228,14 +259,15 @@ extern "C" int pk_split3_bf16(const float* x, void* out, int rows, int dim, int 
     PK_REQUIRE(gamma && beta && dim <= 1024, "pk_split3_bf16: LayerNorm mode needs gamma / beta and dim <= 1024");
     const int grid = grid_1d(rows, 8);
     const int maxv = (dim / 4 + 31) / 32;
-    if (maxv <= 2) split3_layernorm_kernel<2><<<grid, 256, 0, s>>>(x, o, gamma, beta, eps, rows, dim);
-    else if (maxv <= 4) split3_layernorm_kernel<4><<<grid, 256, 0, s>>>(x, o, gamma, beta, eps, rows, dim);
-    else split3_layernorm_kernel<8><<<grid, 256, 0, s>>>(x, o, gamma, beta, eps, rows, dim);
+    if (maxv <= 2) split3_layernorm_kernel<2><<<grid, 256, 0, s>>>(x, o, gamma, beta, eps, rows, dim, rowscale, row_index, rows_dev);
+    else if (maxv <= 4) split3_layernorm_kernel<4><<<grid, 256, 0, s>>>(x, o, gamma, beta, eps, rows, dim, rowscale, row_index, rows_dev);
+    else split3_layernorm_kernel<8><<<grid, 256, 0, s>>>(x, o, gamma, beta, eps, rows, dim, rowscale, row_index, rows_dev);
     return check_cuda(cudaGetLastError(), "split3_layernorm_kernel");
   }
+  PK_REQUIRE(row_index == nullptr, "pk_split3_bf16: row_index is a LayerNorm-mode argument");
   const long long total = static_cast<long long>(rows) * (dim / 4);
-  if (mode == 1) split3_kernel<1><<<grid_1d(total, 256), 256, 0, s>>>(x, o, rows, dim);
-  else split3_kernel<0><<<grid_1d(total, 256), 256, 0, s>>>(x, o, rows, dim);
+  if (mode == 1) split3_kernel<1><<<grid_1d(total, 256), 256, 0, s>>>(x, o, rows, dim, rowscale, rows_dev);
+  else split3_kernel<0><<<grid_1d(total, 256), 256, 0, s>>>(x, o, rows, dim, rowscale, rows_dev);
   return check_cuda(cudaGetLastError(), "split3_kernel");
 }
 
@@ -252,15 +284,18 @@ extern "C" int pk_patchify_split3(const float* images, void* patches6, int batch
 }
 
 extern "C" int pk_attention_f32(const float* qkv, float* out, int batch, int num_heads, int head_dim, int seq_len, float scale,
+                                const int* cu_seqlens, const float* key_mult, const float* extra_kv, const float* extra_mult,
                                 void* stream) {
   using namespace pk;
-  PK_REQUIRE(qkv && out && batch >= 0 && num_heads > 0 && seq_len > 0, "pk_attention_f32: bad arguments");
+  PK_REQUIRE(qkv && out && batch >= 0 && num_heads > 0 && seq_len > 0, "pk_attention_f32: bad arguments (seq_len = longest sample)");
   PK_REQUIRE(head_dim == 32 || head_dim == 64, "pk_attention_f32: head_dim must be 32 or 64");
   if (batch == 0) return PK_OK;
   const dim3 grid((seq_len + 127) / 128, batch * num_heads);
   PK_REQUIRE(grid.y <= 65535u, "pk_attention_f32: batch * heads = %u exceeds 65535 (use smaller micro-batches)", grid.y);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (head_dim == 64) attention_f32_kernel<64><<<grid, 128, 0, s>>>(qkv, out, batch, num_heads, seq_len, scale);
-  else attention_f32_kernel<32><<<grid, 128, 0, s>>>(qkv, out, batch, num_heads, seq_len, scale);
+  if (head_dim == 64)
+    attention_f32_kernel<64><<<grid, 128, 0, s>>>(qkv, out, batch, num_heads, seq_len, scale, cu_seqlens, key_mult, extra_kv, extra_mult);
+  else
+    attention_f32_kernel<32><<<grid, 128, 0, s>>>(qkv, out, batch, num_heads, seq_len, scale, cu_seqlens, key_mult, extra_kv, extra_mult);
   return check_cuda(cudaGetLastError(), "attention_f32_kernel");
 }

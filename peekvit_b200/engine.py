@@ -382,6 +382,8 @@ class Forward:
     def attn_part(self, x, lw: LayerWeights, rows: int, batch: int, *, seq: int = 0, cu=None, max_len: int = 0, rows_dev=None,
                   rowscale=None, key_mult=None, extra_mult=None) -> None:
         """x += rowscale * out_proj(attention(in_proj(rowscale * LN1(x))))  (vit.py:48-51; residualvit.py:252-256)."""
+        if self.exact:
+            return self._attn_part_exact(x, lw, rows, batch, seq, cu, max_len, rows_dev, rowscale, key_mult, extra_mult)
         pm, ws = self.pm, self.ws
         D = pm.dim
         aw = lw.attn[0]
@@ -395,6 +397,8 @@ class Forward:
 
     def mlp_part(self, x, lw: LayerWeights, rows: int, *, rows_dev=None, rowscale=None) -> None:
         """x += fc2(gelu(fc1(rowscale * LN2(x))))  (vit.py:53-55; residualvit.py:258-260)."""
+        if self.exact:
+            return self._mlp_part_exact(x, lw, rows, rows_dev, rowscale)
         pm, ws = self.pm, self.ws
         D = pm.dim
         mw = lw.mlp[0]
@@ -410,31 +414,41 @@ class Forward:
         self.mlp_part(x, lw, rows)
 
     # ---- fp32-accurate mode (the reference's shipped dtype): same tcgen05 GEMM kernels on 3-way split bf16 operands
-    def _exact_weights(self, lw: LayerWeights) -> Dict[str, torch.Tensor]:
-        """Split weight rows [m|h|l|h|m|h] of a block, built from the fp32 masters on first use."""
+    def _exact_weights(self, lw: LayerWeights) -> Dict[str, List[torch.Tensor]]:
+        """Split weight rows [m|h|l|h|m|h] of a block (one entry per expert; plain blocks have one), built from the fp32
+        masters on first use."""
         c = lw.extra.get("x3")
         if c is None:
             blk = lw.module
-            mha = blk.self_attention.self_attention
-            c = lw.extra["x3"] = dict(w_qkv=ops.split3_weight(mha.in_proj_weight), w_o=ops.split3_weight(mha.out_proj.weight),
-                                      w_fc1=ops.split3_weight(blk.mlp.fc1.weight), w_fc2=ops.split3_weight(blk.mlp.fc2.weight))
+            if lw.kind == "moe":
+                mhas = [e.self_attention for e in blk.self_attention.experts]
+                mlps = list(blk.mlp.experts)
+            else:
+                mhas, mlps = [blk.self_attention.self_attention], [blk.mlp]
+            c = lw.extra["x3"] = dict(w_qkv=[ops.split3_weight(m.in_proj_weight) for m in mhas],
+                                      w_o=[ops.split3_weight(m.out_proj.weight) for m in mhas],
+                                      w_fc1=[ops.split3_weight(m.fc1.weight) for m in mlps],
+                                      w_fc2=[ops.split3_weight(m.fc2.weight) for m in mlps])
         return c
 
     def gemm_exact(self, a32: torch.Tensor, rows: int, w6: torch.Tensor, bias, out, epilogue: int, mode: int = SPLIT_NONE,
-                   gamma=None, beta=None, eps: float = 0.0, resid=None):
-        """out = epilogue(pre(a32) @ W^T + bias) at fp32 accuracy: pre = none / exact GELU / LayerNorm is applied by the
-        kernel that splits the activation rows, the product runs as one bf16 GEMM over K' = 6K."""
+                   gamma=None, beta=None, eps: float = 0.0, resid=None, *, in_scale=None, row_index=None, rows_dev=None,
+                   a6=None, **gemm_kw):
+        """out = epilogue(in_scale * pre(a32) @ W^T + bias) at fp32 accuracy: pre = none / exact GELU / LayerNorm is applied
+        by the kernel that splits the activation rows, the product runs as one bf16 GEMM over K' = 6K.  ``a6``: reuse rows
+        that are already split (several experts reading the same activations)."""
         K = a32.shape[-1]
-        a6 = self.ws.get(f"a6_{K}", (rows, 6 * K), torch.bfloat16)
-        ops.split3(a32, a6, mode, gamma, beta, eps, rows=rows)
-        return ops.gemm(a6, w6, bias, out, epilogue, resid=resid)
+        if a6 is None:
+            a6 = self.ws.get(f"a6_{K}", (rows, 6 * K), torch.bfloat16)
+            ops.split3(a32, a6, mode, gamma, beta, eps, rows=rows, rowscale=in_scale, row_index=row_index, rows_dev=rows_dev)
+        return ops.gemm(a6, w6, bias, out, epilogue, resid=resid, **gemm_kw)
 
-    def embed_exact(self, images: torch.Tensor) -> torch.Tensor:
+    def embed_exact(self, images: torch.Tensor, shift: int = 0) -> torch.Tensor:
         pm = self.pm
         if images.dtype != torch.float32:
             raise NotImplementedError("the fp32-accurate mode takes float images (the uint8 input path is a bf16-mode feature)")
         B = images.shape[0]
-        P, D, T, R, seq = pm.num_patches, pm.dim, pm.n_cls, pm.n_reg, pm.seq_len
+        P, D, T, R, seq = pm.num_patches, pm.dim, pm.n_cls, pm.n_reg, pm.seq_len + shift
         Kp = pm.w_patch.shape[1]
         w6 = pm.extra.get("w_patch6")
         if w6 is None:
@@ -442,26 +456,42 @@ class Forward:
         patches6 = ops.patchify_split3(images, pm.patch_size, self.ws.get("patches6", (B * P, 6 * Kp), torch.bfloat16))
         x = self.ws.get("x", (B * seq, D), torch.float32)
         ops.gemm(patches6, w6, pm.b_patch, x, PK_EPI_BIAS_RESID_F32, resid=pm.pos,
-                 rows_per_group=P, group_stride=seq, group_offset=T + R, resid_is_pos=True, pos_offset=T + R)
-        ops.fill_token_rows(x, B, seq, 0, pm.cls_tokens, pm.pos)
+                 rows_per_group=P, group_stride=seq, group_offset=T + R + shift, resid_is_pos=True, pos_offset=T + R)
+        ops.fill_token_rows(x, B, seq, 0, pm.cls_tokens[:1], pm.pos)
+        if T > 1:
+            ops.fill_token_rows(x, B, seq, 1 + shift, pm.cls_tokens[1:], pm.pos, pos_offset=1)
         if R > 0:
-            ops.fill_token_rows(x, B, seq, T, pm.reg_tokens, pm.pos, pos_offset=T)
+            ops.fill_token_rows(x, B, seq, T + shift, pm.reg_tokens, pm.pos, pos_offset=T)
         return x
 
     def dense_block_exact(self, x: torch.Tensor, lw: LayerWeights, rows: int, batch: int, seq: int) -> None:
         """ViTBlock (vit.py:45-55) at fp32 accuracy, in place on the residual stream."""
+        self.attn_part(x, lw, rows, batch, seq=seq)
+        self.mlp_part(x, lw, rows)
+
+    def _attn_part_exact(self, x, lw, rows, batch, seq, cu, max_len, rows_dev, rowscale, key_mult, extra_mult, expert=0,
+                         out_scale=None, a6=None):
         pm, ws = self.pm, self.ws
         D = pm.dim
-        w, aw, mw = self._exact_weights(lw), lw.attn[0], lw.mlp[0]
+        w, aw = self._exact_weights(lw), lw.attn[expert]
+        xr = x[:rows]
+        qkv = self.gemm_exact(xr, rows, w["w_qkv"][expert], aw.b_qkv, ws.get("qkv32", (rows, 3 * D), torch.float32), PK_EPI_BIAS_F32,
+                              SPLIT_LAYERNORM, lw.ln1_w, lw.ln1_b, lw.eps, in_scale=rowscale, rows_dev=rows_dev, m_dev=rows_dev, a6=a6)
+        att = ops.attention_f32(qkv, ws.get("att32", (rows, D), torch.float32), batch, pm.heads, D // pm.heads, seq,
+                                cu_seqlens=cu, max_seq_len=max_len, key_mult=key_mult,
+                                extra_kv=aw.b_qkv[D:] if extra_mult is not None else None, extra_mult=extra_mult)
+        self.gemm_exact(att, rows, w["w_o"][expert], aw.b_o, xr, PK_EPI_BIAS_RESID_F32, resid=xr, rows_dev=rows_dev, m_dev=rows_dev,
+                        rowscale=rowscale if out_scale is None else out_scale)
+
+    def _mlp_part_exact(self, x, lw, rows, rows_dev, rowscale):
+        ws = self.ws
+        w, mw = self._exact_weights(lw), lw.mlp[0]
         F = mw.b_fc1.shape[0]
         xr = x[:rows]
-        qkv = self.gemm_exact(xr, rows, w["w_qkv"], aw.b_qkv, ws.get("qkv32", (rows, 3 * D), torch.float32), PK_EPI_BIAS_F32,
-                              SPLIT_LAYERNORM, lw.ln1_w, lw.ln1_b, lw.eps)
-        att = ops.attention_f32(qkv, ws.get("att32", (rows, D), torch.float32), batch, pm.heads, D // pm.heads, seq)
-        self.gemm_exact(att, rows, w["w_o"], aw.b_o, xr, PK_EPI_BIAS_RESID_F32, resid=xr)
-        hid = self.gemm_exact(xr, rows, w["w_fc1"], mw.b_fc1, ws.get("hid32", (rows, F), torch.float32), PK_EPI_BIAS_F32,
-                              SPLIT_LAYERNORM, lw.ln2_w, lw.ln2_b, lw.eps)
-        self.gemm_exact(hid, rows, w["w_fc2"], mw.b_fc2, xr, PK_EPI_BIAS_RESID_F32, SPLIT_GELU, resid=xr)
+        hid = self.gemm_exact(xr, rows, w["w_fc1"][0], mw.b_fc1, ws.get("hid32", (rows, F), torch.float32), PK_EPI_BIAS_F32,
+                              SPLIT_LAYERNORM, lw.ln2_w, lw.ln2_b, lw.eps, in_scale=rowscale, rows_dev=rows_dev, m_dev=rows_dev)
+        self.gemm_exact(hid, rows, w["w_fc2"][0], mw.b_fc2, xr, PK_EPI_BIAS_RESID_F32, SPLIT_GELU, resid=xr, rows_dev=rows_dev,
+                        m_dev=rows_dev)
 
     # ---- LayerNorm fused across GEMMs (dense layers of ViT / RankViT)
     def fold_ok(self, rows: int) -> bool:
@@ -499,10 +529,6 @@ class Forward:
             ops.gemm(hid, mw.w_fc2, mw.b_fc2, x[:rows], PK_EPI_BIAS_RESID_F32, resid=x[:rows], xb_out=xb, row_stats=stats)
         else:
             ops.gemm(hid, mw.w_fc2, mw.b_fc2, x[:rows], PK_EPI_BIAS_RESID_F32, resid=x[:rows])
-
-    def _bf16_only(self, what: str) -> None:
-        if self.exact:
-            raise NotImplementedError(f"the fp32-accurate mode covers the dense ViT and RankViT paths; {what} runs in bf16 mode only")
 
     def head(self, x: torch.Tensor, batch: int, seq: int, cu_seqlens=None, n_cls: Optional[int] = None) -> torch.Tensor:
         pm = self.pm
@@ -598,7 +624,6 @@ class Forward:
         """Budget-token gating with real compaction (reference residualvit.py:587-616, block :197-260).
         Local row layout of a sample: [cls, budget token, live image rows ..., ghost slot]."""
         pm, ws = self.pm, self.ws
-        self._bf16_only("ResidualViT")
         ex = pm.extra
         abt = ex["add_budget_token"]
         B, D, dev = images.shape[0], pm.dim, images.device
@@ -608,7 +633,7 @@ class Forward:
         seq0 = pm.seq_len + nb
         cap = seq0 + 1                                           # + ghost slot
         rows_cap = B * cap
-        x = self.embed(images, shift=nb)
+        x = self.embed_exact(images, shift=nb) if self.exact else self.embed(images, shift=nb)
         if abt:
             if budget is None:
                 raise AssertionError("Budget token not set. Call set_budget() before forward() to evaluate the model on a chosen budget.")
@@ -695,11 +720,10 @@ class Forward:
         """ACT halting with real token removal (reference adavit.py:140-219): halted tokens leave the packed
         batch and survive only as a virtual bias key; a sample retires once its class token halts."""
         pm, ws = self.pm, self.ws
-        self._bf16_only("A-ViT")
         ex = pm.extra
         B, D, seq, dev = images.shape[0], pm.dim, pm.seq_len, images.device
         rows_cap = B * seq
-        x = self.embed(images)
+        x = self.embed_exact(images) if self.exact else self.embed(images)
         cu = self._const(f"cu0_{B}_{seq}", lambda: (torch.arange(B + 1, device=dev, dtype=torch.int32) * seq))
         rows_dev = self._const(f"rows0_{B}_{seq}", lambda: torch.tensor([B * seq], device=dev, dtype=torch.int32))
         tokid0 = self._const(f"tokid0_{B}_{seq}", lambda: torch.arange(seq, device=dev, dtype=torch.float32).repeat(B).contiguous())
@@ -747,10 +771,9 @@ class Forward:
         """Expert MLPs computed only for the tokens routed to them (reference moevit.py:49-61 evaluates every
         expert on every token and selects with a one-hot einsum)."""
         pm, ws = self.pm, self.ws
-        self._bf16_only("MoE-ViT")
         B, seq, D, dev = images.shape[0], pm.seq_len, pm.dim, images.device
         rows = B * seq
-        x = self.embed(images)
+        x = self.embed_exact(images) if self.exact else self.embed(images)
         for i, lw in enumerate(pm.layers):
             if lw.kind == "noise":
                 apply_noise(lw.module, x, B, seq)
@@ -769,8 +792,15 @@ class Forward:
                               ws.get("moe_src", (rows,), torch.int32),
                               scratch=ws.get("moe_sort_scratch", (ops.MOE_SORT_SCRATCH_INTS,), torch.int32))
                 onehot = ops.expert_onehot(expert, EA, ws.get(f"amoe_onehot_{EA}", (EA, rows), torch.float32), rows)
-                a = ops.layernorm(x, lw.ln1_w, lw.ln1_b, lw.eps, ws.get("ln", (rows, D), torch.bfloat16), rows=rows)
-                for e, aw in enumerate(lw.attn):
+                if self.exact:
+                    # every expert reads the same split LN1 rows; they are produced by the first expert's in-proj call
+                    a6 = ws.get(f"a6_shared_{D}", (rows, 6 * D), torch.bfloat16)     # not the buffer the out-proj splits into
+                    ops.split3(x, a6, SPLIT_LAYERNORM, lw.ln1_w, lw.ln1_b, lw.eps, rows=rows)
+                    for e in range(EA):
+                        self._attn_part_exact(x, lw, rows, B, seq, None, 0, None, None, None, None, expert=e,
+                                              out_scale=onehot[e], a6=a6)
+                a = None if self.exact else ops.layernorm(x, lw.ln1_w, lw.ln1_b, lw.eps, ws.get("ln", (rows, D), torch.bfloat16), rows=rows)
+                for e, aw in enumerate(() if self.exact else lw.attn):
                     qkv = ops.gemm(a, aw.w_qkv, aw.b_qkv, ws.get("qkv", (rows, 3 * D), torch.bfloat16), PK_EPI_BIAS_BF16)
                     att = ops.attention(qkv, ws.get("att", (rows, D), torch.bfloat16), B, pm.heads, D // pm.heads, seq_len=seq)
                     ops.gemm(att, aw.w_o, aw.b_o, x, PK_EPI_BIAS_RESID_F32, resid=x, rowscale=onehot[e])
@@ -786,13 +816,29 @@ class Forward:
             src_of = ws.get("moe_src", (rows,), torch.int32)
             ops.moe_route(x, lw.ln2_w, lw.ln2_b, lw.eps, lw.extra["mlp_gate_w"], lw.extra["mlp_gate_b"], rows, expert, offsets,
                           counts, src_of, scratch=ws.get("moe_sort_scratch", (ops.MOE_SORT_SCRATCH_INTS,), torch.int32))
-            a = ops.layernorm(x, lw.ln2_w, lw.ln2_b, lw.eps, ws.get("ln", (rows, D), torch.bfloat16), rows=rows, row_index=src_of)
             F = lw.mlp[0].w_fc1.shape[0]
+            y_sorted = ws.get("moe_y", (rows, D), torch.float32)
+            if self.exact:
+                # same expert-sorted segments at fp32 accuracy: split(LN2) gathered into sorted order, per-expert fc1 over its
+                # segment, one exact-GELU split of all hidden rows, per-expert fc2
+                w6 = self._exact_weights(lw)
+                a6 = ws.get(f"a6_shared_{D}", (rows, 6 * D), torch.bfloat16)
+                ops.split3(x, a6, SPLIT_LAYERNORM, lw.ln2_w, lw.ln2_b, lw.eps, rows=rows, row_index=src_of)
+                hid32 = ws.get("hid32", (rows, F), torch.float32)
+                for e, mw in enumerate(lw.mlp):
+                    ops.gemm(a6, w6["w_fc1"][e], mw.b_fc1, hid32, PK_EPI_BIAS_F32, m_dev=counts[e:e + 1], row_begin_dev=offsets[e:e + 1])
+                h6 = ops.split3(hid32, ws.get(f"a6_{F}", (rows, 6 * F), torch.bfloat16), SPLIT_GELU, rows=rows)
+                for e, mw in enumerate(lw.mlp):
+                    ops.gemm(h6, w6["w_fc2"][e], mw.b_fc2, y_sorted, PK_EPI_BIAS_F32, m_dev=counts[e:e + 1], row_begin_dev=offsets[e:e + 1])
+                ops.scatter_add_rows(x, y_sorted, src_of, rows)
+                if aux is not None:
+                    aux.setdefault("mlp_expert", {})[i] = expert.view(B, seq).clone()
+                continue
+            a = ops.layernorm(x, lw.ln2_w, lw.ln2_b, lw.eps, ws.get("ln", (rows, D), torch.bfloat16), rows=rows, row_index=src_of)
             hid = ws.get("hid", (rows, F), torch.bfloat16)
             # Expert-sorted rows: each expert's segment [offsets[e], offsets[e] + counts[e]) runs through the CTA-pair GEMMs
             # (device-side segment start and length); the fc2 outputs land in sorted order and one gather-add un-permutes
             # them into the residual stream.
-            y_sorted = ws.get("moe_y", (rows, D), torch.float32)
             for e, mw in enumerate(lw.mlp):
                 ops.gemm(a, mw.w_fc1, mw.b_fc1, hid, PK_EPI_BIAS_GELU_BF16, m_dev=counts[e:e + 1], row_begin_dev=offsets[e:e + 1])
                 ops.gemm(hid, mw.w_fc2, mw.b_fc2, y_sorted, PK_EPI_BIAS_F32, m_dev=counts[e:e + 1], row_begin_dev=offsets[e:e + 1])

@@ -370,12 +370,15 @@ SPLIT_NONE, SPLIT_GELU, SPLIT_LAYERNORM = 0, 1, 2
 
 
 def split3(x: torch.Tensor, out: torch.Tensor, mode: int = SPLIT_NONE, gamma: Optional[torch.Tensor] = None,
-           beta: Optional[torch.Tensor] = None, eps: float = 0.0, rows: Optional[int] = None) -> torch.Tensor:
-    """fp32 rows -> bf16 split activation rows [m|l|h|m|h|h] (out [rows, 6*dim]), optionally after exact GELU / LayerNorm."""
+           beta: Optional[torch.Tensor] = None, eps: float = 0.0, rows: Optional[int] = None, rowscale: Optional[torch.Tensor] = None,
+           row_index: Optional[torch.Tensor] = None, rows_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 rows -> bf16 split activation rows [m|l|h|m|h|h] (out [rows, 6*dim]), optionally after exact GELU / LayerNorm
+    (times ``rowscale``; LayerNorm mode may gather its input rows through ``row_index``)."""
     lib = _lib_for(x)
     n = x.shape[0] if rows is None else rows
     check(lib.pk_split3_bf16(_ptr(x, torch.float32), _ptr(out, torch.bfloat16), n, x.shape[-1], mode, _ptr(gamma, torch.float32),
-                             _ptr(beta, torch.float32), float(eps), _stream()), "pk_split3_bf16")
+                             _ptr(beta, torch.float32), float(eps), _ptr(rowscale, torch.float32), _ptr(row_index, torch.int32),
+                             _ptr(rows_dev, torch.int32), _stream()), "pk_split3_bf16")
     return out
 
 
@@ -397,10 +400,14 @@ def patchify_split3(images: torch.Tensor, patch_size: int, out: torch.Tensor) ->
     return out
 
 
-def attention_f32(qkv: torch.Tensor, out: torch.Tensor, batch: int, num_heads: int, head_dim: int, seq_len: int) -> torch.Tensor:
+def attention_f32(qkv: torch.Tensor, out: torch.Tensor, batch: int, num_heads: int, head_dim: int, seq_len: int = 0, *,
+                  cu_seqlens: Optional[torch.Tensor] = None, max_seq_len: int = 0, key_mult: Optional[torch.Tensor] = None,
+                  extra_kv: Optional[torch.Tensor] = None, extra_mult: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 attention core; same sample / multiplicity / virtual-key arguments as ``attention`` (extra_kv fp32 [2*D])."""
     lib = _lib_for(qkv)
-    check(lib.pk_attention_f32(_ptr(qkv, torch.float32), _ptr(out, torch.float32), batch, num_heads, head_dim, seq_len,
-                               float(head_dim) ** -0.5, _stream()), "pk_attention_f32")
+    check(lib.pk_attention_f32(_ptr(qkv, torch.float32), _ptr(out, torch.float32), batch, num_heads, head_dim, max_seq_len or seq_len,
+                               float(head_dim) ** -0.5, _ptr(cu_seqlens, torch.int32), _ptr(key_mult, torch.float32),
+                               _ptr(extra_kv, torch.float32), _ptr(extra_mult, torch.float32), _stream()), "pk_attention_f32")
     return out
 
 

@@ -15,8 +15,8 @@ from . import engine
 
 DEFAULT_MICRO_BATCH = int(os.environ.get("PEEKVIT_B200_MICRO_BATCH", "512"))
 # Arithmetic mode: "bf16" (bf16 GEMM / attention operands, fp32 accumulation: the measured headline mode) or "fp32" (the
-# reference's shipped dtype: 3-way split operands on the same tcgen05 GEMMs + fp32 attention, logits within 1e-5; dense ViT
-# and RankViT).  Per model: ``model.pk_precision = "fp32"``.
+# reference's shipped dtype: 3-way split operands on the same tcgen05 GEMMs + fp32 attention, logits within 1e-5, every family).
+# Per model: ``model.pk_precision = "fp32"``.
 DEFAULT_PRECISION = os.environ.get("PEEKVIT_B200_PRECISION", "bf16")
 EXACT_MICRO_BATCH = 64          # the split activation rows are 6x wider: keep the workspace of the fp32 mode small
 

@@ -316,26 +316,53 @@ def test_uint8_input_path_matches_float_path():
 TOL_FP32_MODE = 1e-5        # north star: logits within 1e-5 relative in fp32 mode
 
 
-@pytest.mark.parametrize("name", ["vit_d64_h2", "vit_d128_regs", "rankvit_b05", "rankvit_list"])
+@pytest.mark.parametrize("name", [n for n in sorted(CASES) if CASES[n].get("noise") is None])
 def test_fp32_mode_matches_reference_fixture(name):
     """model.pk_precision = 'fp32': split-operand tcgen05 GEMMs + fp32 attention reproduce the reference's fp32 logits to
-    1e-5, and (RankViT) select exactly the reference's kept-token indices."""
+    1e-5 for every family, and with them the reference's discrete decisions: kept-token indices (RankViT), keep / drop
+    flags and soft mask values (ResidualViT, EE-ResidualViT), halting counters (A-ViT), expert routing (MoE)."""
     from peekvit_b200 import ops, runner
     case = CASES[name]
+    fam = case["family"]
     model, sd, images = _model(case)
     model.pk_precision = "fp32"
-    aux = {}
-    logits = runner.run(model, images.to(DEV), aux).cpu().numpy()
-    assert ops.device_flag() == 0
     ref = np.load(os.path.join(GOLD, name + ".npz"))
-    assert np.abs(logits - ref["logits"]).max() / np.abs(ref["logits"]).max() < TOL_FP32_MODE
-    if case["family"] == "rankvit":
+    scale = np.abs(ref["logits"]).max()
+    aux = {}
+    if fam == "eeresidualvit":
+        outs = model(images.to(DEV))
+        for i in range(case["cfg"]["num_layers"]):
+            r = ref[f"exit_{i}"]
+            assert np.abs(outs[i].cpu().numpy() - r).max() / np.abs(r).max() < TOL_FP32_MODE
+        logits = outs[-1].cpu().numpy()
+    else:
+        if fam == "adavit":
+            model.pk_early_exit = False           # per-token ACT bookkeeping of every sample to the last layer
+        logits = runner.run(model, images.to(DEV), aux).cpu().numpy()
+    assert ops.device_flag() == 0
+    assert np.abs(logits - ref["logits"]).max() / scale < TOL_FP32_MODE
+    if fam == "rankvit":
         assert aux["seq_lens"] == list(ref["seq_lens"])
         for i, kept in aux["kept"].items():
             assert np.array_equal(kept.cpu().numpy(), ref[f"kept_{i}"])          # bit-exact index sets, in order
-    model.pk_precision = "bf16"
-    again = runner.run(model, images.to(DEV)).cpu().numpy()
-    assert 1e-4 < np.abs(again - ref["logits"]).max() / np.abs(ref["logits"]).max() < TOL_LOGITS
+    if fam in ("residualvit", "eeresidualvit"):
+        for i, blk in enumerate(model.encoder.layers):
+            g = ref[f"mask_{i}"]
+            m = blk.mask.cpu().numpy()
+            assert np.array_equal(m > 0, g > 0)                                  # identical keep / drop decisions
+            assert np.abs(m - g).max() < 2e-6
+    if fam == "adavit":
+        assert np.array_equal(model.encoder.counter_token.cpu().numpy(), ref["counter_token"])
+        assert np.allclose(model.encoder.rho_token.cpu().numpy(), ref["rho_token"], atol=1e-5)
+    if fam == "moevit":
+        for i, blk in enumerate(model.encoder.layers):
+            for moe, key in ((blk.mlp, "mlp_gating"), (blk.self_attention, "attn_gating")):
+                if moe.num_experts > 1:
+                    assert np.array_equal(moe.gating_probs.argmax(-1).cpu().numpy(), ref[f"{key}_{i}"])
+    if fam in ("vit", "rankvit"):
+        model.pk_precision = "bf16"
+        again = runner.run(model, images.to(DEV)).cpu().numpy()
+        assert 1e-4 < np.abs(again - ref["logits"]).max() / scale < TOL_LOGITS
 
 
 def test_fp32_mode_config_a_and_vit_b16_against_oracle():
@@ -356,12 +383,9 @@ def test_fp32_mode_config_a_and_vit_b16_against_oracle():
         assert torch.equal(logits.argmax(1), ref.argmax(1))
 
 
-def test_fp32_mode_is_dense_families_only():
-    case = CASES["moevit"]
+def test_precision_flag_is_validated():
+    case = CASES["vit_d64_h2"]
     model, sd, images = _model(case)
-    model.pk_precision = "fp32"
-    with pytest.raises(NotImplementedError):
-        model(images.to(DEV))
     model.pk_precision = "fp16"
     with pytest.raises(ValueError):
         model(images.to(DEV))
