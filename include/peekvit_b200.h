@@ -272,7 +272,7 @@ int pk_split3_bf16(const float* x, void* out, int rows, int dim, int mode, const
                    const int* rows_dev /* optional device-side row count */, void* stream);
 /* im2col of f32 NCHW images into split activation rows: patches6 bf16 [B*(S/p)^2, 6*3*p*p] (vit.py:203-222, fp32 mode). */
 int pk_patchify_split3(const float* images, void* patches6, int batch, int image_size, int patch_size, void* stream);
-/* fp32 attention core on the CUDA cores: qkv f32 [rows, 3*H*dh] (q|k|v) -> out f32 [rows, H*dh], dh 32 or 64 (blocks.py:93-95,
+/* fp32 attention core on the CUDA cores: qkv f32 [rows, 3*H*dh] (q|k|v) -> out f32 [rows, H*dh], dh 32, 48 or 64 (blocks.py:93-95,
  * fp32 mode).  Uniform samples of seq_len rows, or ragged ones (cu_seqlens int32 [B+1]; seq_len = longest sample); optional
  * per-key multiplicities and one virtual key per sample, with the meaning they have in pk_attention_args. */
 int pk_attention_f32(const float* qkv, float* out, int batch, int num_heads, int head_dim, int seq_len, float scale,

@@ -5,7 +5,7 @@
 // materialising the (B,H,N,N) weights the reference asks for (need_weights=True) and discards.
 //
 // This is the general path: any sequence length (online softmax over 64-key tiles), head_dim
-// 32 or 64, ragged batches through cu_seqlens, per-key multiplicities (+log mult on the logit)
+// 32, 48 or 64, ragged batches through cu_seqlens, per-key multiplicities (+log mult on the logit)
 // and one virtual "bias key" per head standing for the tokens a sparse model dropped
 // (SURVEY.md Appendix A).  One CTA = 64 queries of one (sample, head); 4 warps x 16 query rows;
 // K/V tiles double-buffered in shared memory with cp.async, XOR-swizzled for conflict-free
@@ -67,8 +67,11 @@ __global__ void __launch_bounds__(kAttThreads, 2)
 attention_fwd_kernel(const AttParams p) {
   constexpr int CPR = DH / 8;
   constexpr int KS = DH / 16;                       // k-steps over head_dim for QK^T
-  constexpr int TILE_BYTES = kAttBKV * DH * 2;
-  __shared__ __align__(128) uint8_t s_q[kAttBQ * DH * 2];
+  // shared-memory row pitch: the XOR swizzle needs a power-of-two chunk count, so head_dim 48 (ViT-S with 8 heads,
+  // configs/model/vit_small.yaml) is stored in 64-element rows with the last two chunks unused
+  constexpr int SDH = DH <= 32 ? 32 : 64;
+  constexpr int TILE_BYTES = kAttBKV * SDH * 2;
+  __shared__ __align__(128) uint8_t s_q[kAttBQ * SDH * 2];
   __shared__ __align__(128) uint8_t s_k[2][TILE_BYTES];
   __shared__ __align__(128) uint8_t s_v[2][TILE_BYTES];
   __shared__ float s_bias[2][kAttBKV];
@@ -110,8 +113,8 @@ attention_fwd_kernel(const AttParams p) {
         vsrc = p.extra_kv + D + h * DH + c * 8;
         bytes = 16;
       }
-      cp_async16(sk + tile_off<DH>(r, c), ksrc, bytes);
-      cp_async16(sv + tile_off<DH>(r, c), vsrc, bytes);
+      cp_async16(sk + tile_off<SDH>(r, c), ksrc, bytes);
+      cp_async16(sv + tile_off<SDH>(r, c), vsrc, bytes);
     }
     if (tid < kAttBKV) {
       const int key = kv0 + tid;
@@ -129,7 +132,7 @@ attention_fwd_kernel(const AttParams p) {
       const int r = i / CPR, c = i % CPR;
       const int q = q0 + r;
       const bool ok = q < len;
-      cp_async16(sq + tile_off<DH>(r, c), ok ? q_base + (long long)q * ld + c * 8 : q_base, ok ? 16 : 0);
+      cp_async16(sq + tile_off<SDH>(r, c), ok ? q_base + (long long)q * ld + c * 8 : q_base, ok ? 16 : 0);
     }
     load_kv_tile(0, 0);
     cp_async_commit();
@@ -156,7 +159,7 @@ attention_fwd_kernel(const AttParams p) {
       const uint32_t sq = smem_u32(s_q);
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks)
-        ldsm_x4(sq + tile_off<DH>(warp * 16 + (lane & 15), ks * 2 + (lane >> 4)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+        ldsm_x4(sq + tile_off<SDH>(warp * 16 + (lane & 15), ks * 2 + (lane >> 4)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
     }
     const uint32_t sk = smem_u32(s_k[buf]), sv = smem_u32(s_v[buf]);
 
@@ -171,7 +174,7 @@ attention_fwd_kernel(const AttParams p) {
         uint32_t b0, b1, b2, b3;
         const int key = np * 16 + (lane & 7) + ((lane >> 4) << 3);
         const int chunk = ks * 2 + ((lane >> 3) & 1);
-        ldsm_x4(sk + tile_off<DH>(key, chunk), b0, b1, b2, b3);
+        ldsm_x4(sk + tile_off<SDH>(key, chunk), b0, b1, b2, b3);
         mma_bf16_16816(s[np * 2], qf[ks], b0, b1);
         mma_bf16_16816(s[np * 2 + 1], qf[ks], b2, b3);
       }
@@ -224,7 +227,7 @@ attention_fwd_kernel(const AttParams p) {
         uint32_t b0, b1, b2, b3;
         const int key = kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
         const int chunk = nd * 2 + (lane >> 4);
-        ldsm_x4_trans(sv + tile_off<DH>(key, chunk), b0, b1, b2, b3);
+        ldsm_x4_trans(sv + tile_off<SDH>(key, chunk), b0, b1, b2, b3);
         mma_bf16_16816(o[nd * 2], pf[kk], b0, b1);
         mma_bf16_16816(o[nd * 2 + 1], pf[kk], b2, b3);
       }
@@ -245,8 +248,8 @@ attention_fwd_kernel(const AttParams p) {
 #pragma unroll
     for (int n = 0; n < DH / 8; ++n) {
       const int r0 = warp * 16 + g, r1 = r0 + 8;
-      *reinterpret_cast<uint32_t*>(s_q + tile_off<DH>(r0, n) + tq * 4) = pack_bf16(o[n][0] * inv0, o[n][1] * inv0);
-      *reinterpret_cast<uint32_t*>(s_q + tile_off<DH>(r1, n) + tq * 4) = pack_bf16(o[n][2] * inv1, o[n][3] * inv1);
+      *reinterpret_cast<uint32_t*>(s_q + tile_off<SDH>(r0, n) + tq * 4) = pack_bf16(o[n][0] * inv0, o[n][1] * inv0);
+      *reinterpret_cast<uint32_t*>(s_q + tile_off<SDH>(r1, n) + tq * 4) = pack_bf16(o[n][2] * inv1, o[n][3] * inv1);
     }
   }
   __syncthreads();
@@ -254,7 +257,7 @@ attention_fwd_kernel(const AttParams p) {
     const int r = i / CPR, c = i % CPR;
     const int q = q0 + r;
     if (q < len) {
-      const uint4 v = *reinterpret_cast<const uint4*>(s_q + tile_off<DH>(r, c));
+      const uint4 v = *reinterpret_cast<const uint4*>(s_q + tile_off<SDH>(r, c));
       *reinterpret_cast<uint4*>(p.out + (start + q) * (long long)D + h * DH + c * 8) = v;
     }
   }
@@ -270,7 +273,7 @@ int attention_trace_copy(unsigned long long* host_dst);
 extern "C" int pk_attention_fwd(const pk_attention_args* a, void* stream) {
   using namespace pk;
   PK_REQUIRE(a && a->qkv && a->out, "pk_attention_fwd: null pointer");
-  PK_REQUIRE(a->head_dim == 32 || a->head_dim == 64, "pk_attention_fwd: head_dim %d not in {32, 64}", a->head_dim);
+  PK_REQUIRE(a->head_dim == 32 || a->head_dim == 48 || a->head_dim == 64, "pk_attention_fwd: head_dim %d not in {32, 48, 64}", a->head_dim);
   PK_REQUIRE(a->batch >= 0 && a->num_heads > 0 && a->max_seq_len >= 0, "pk_attention_fwd: bad shape");
   PK_REQUIRE(a->cu_seqlens || a->seq_len > 0, "pk_attention_fwd: need cu_seqlens or seq_len");
   PK_REQUIRE((a->extra_kv == nullptr) == (a->extra_mult == nullptr), "pk_attention_fwd: extra_kv and extra_mult go together");
@@ -292,6 +295,7 @@ extern "C" int pk_attention_fwd(const pk_attention_args* a, void* stream) {
   PK_REQUIRE(a->batch <= 65535 && a->num_heads <= 65535, "pk_attention_fwd: batch/heads exceed grid limits; split the batch");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (a->head_dim == 64) attention_fwd_kernel<64><<<grid, kAttThreads, 0, s>>>(p);
+  else if (a->head_dim == 48) attention_fwd_kernel<48><<<grid, kAttThreads, 0, s>>>(p);
   else attention_fwd_kernel<32><<<grid, kAttThreads, 0, s>>>(p);
   return check_cuda(cudaGetLastError(), "attention_fwd_kernel");
 }

@@ -288,13 +288,15 @@ extern "C" int pk_attention_f32(const float* qkv, float* out, int batch, int num
                                 void* stream) {
   using namespace pk;
   PK_REQUIRE(qkv && out && batch >= 0 && num_heads > 0 && seq_len > 0, "pk_attention_f32: bad arguments (seq_len = longest sample)");
-  PK_REQUIRE(head_dim == 32 || head_dim == 64, "pk_attention_f32: head_dim must be 32 or 64");
+  PK_REQUIRE(head_dim == 32 || head_dim == 48 || head_dim == 64, "pk_attention_f32: head_dim must be 32, 48 or 64");
   if (batch == 0) return PK_OK;
   const dim3 grid((seq_len + 127) / 128, batch * num_heads);
   PK_REQUIRE(grid.y <= 65535u, "pk_attention_f32: batch * heads = %u exceeds 65535 (use smaller micro-batches)", grid.y);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (head_dim == 64)
     attention_f32_kernel<64><<<grid, 128, 0, s>>>(qkv, out, batch, num_heads, seq_len, scale, cu_seqlens, key_mult, extra_kv, extra_mult);
+  else if (head_dim == 48)
+    attention_f32_kernel<48><<<grid, 128, 0, s>>>(qkv, out, batch, num_heads, seq_len, scale, cu_seqlens, key_mult, extra_kv, extra_mult);
   else
     attention_f32_kernel<32><<<grid, 128, 0, s>>>(qkv, out, batch, num_heads, seq_len, scale, cu_seqlens, key_mult, extra_kv, extra_mult);
   return check_cuda(cudaGetLastError(), "attention_f32_kernel");

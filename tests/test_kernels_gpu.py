@@ -208,7 +208,7 @@ def ref_attention(qkv, B, H, dh, lens, key_mult=None, extra_kv=None, extra_mult=
     return out
 
 
-@pytest.mark.parametrize("cfg", [(3, 2, 64, 17), (2, 12, 64, 197), (2, 8, 32, 785), (4, 6, 64, 64), (1, 3, 64, 1),
+@pytest.mark.parametrize("cfg", [(3, 2, 64, 17), (2, 12, 64, 197), (2, 8, 32, 785), (4, 6, 64, 64), (1, 3, 64, 1), (2, 8, 48, 197), (3, 2, 48, 70),
                                  (2, 2, 32, 65), (3, 6, 64, 198), (1, 12, 64, 257)])
 def test_attention_dense(ops, cfg):
     B, H, dh, N = cfg
@@ -600,7 +600,7 @@ def test_split_gemm_reaches_fp32_accuracy(ops, M, N, K):
     assert rel_err(plain.double(), ref) > 50 * TOL_EXACT
 
 
-@pytest.mark.parametrize("B,H,dh,n", [(3, 2, 64, 197), (2, 8, 32, 785), (5, 3, 64, 17), (2, 2, 32, 130)])
+@pytest.mark.parametrize("B,H,dh,n", [(3, 2, 64, 197), (2, 8, 32, 785), (5, 3, 64, 17), (2, 2, 32, 130), (2, 8, 48, 197)])
 def test_attention_f32(ops, B, H, dh, n):
     D = H * dh
     qkv = torch.randn(B * n, 3 * D, device=DEV)

@@ -389,3 +389,41 @@ def test_precision_flag_is_validated():
     model.pk_precision = "fp16"
     with pytest.raises(ValueError):
         model(images.to(DEV))
+
+
+# ------------------------------------------------------------------ the reference's shipped model configs
+_REF_CONFIGS = {
+    # configs/model/<name>.yaml of the reference: (class alias, kwargs); image 224 unless the config is an Imagenette one
+    "deit_t_16_224": ("vit", dict(patch_size=16, num_layers=12, hidden_dim=192, mlp_dim=768, num_heads=3)),
+    "deit_s_16_224": ("vit", dict(patch_size=16, num_layers=12, hidden_dim=384, mlp_dim=1536, num_heads=6)),
+    "vit_small": ("vit", dict(patch_size=16, num_layers=8, hidden_dim=384, mlp_dim=1536, num_heads=8)),          # head_dim 48
+    "vit_tiny": ("vit", dict(patch_size=8, num_layers=4, hidden_dim=256, mlp_dim=768, num_heads=8)),              # head_dim 32
+    "rankvit": ("rankvit", dict(patch_size=8, num_layers=4, hidden_dim=256, mlp_dim=768, num_heads=4, rankvit_layers=[1, 2, 3])),
+    "rankdeit_t_16_224": ("rankvit", dict(patch_size=16, num_layers=12, hidden_dim=192, mlp_dim=768, num_heads=3,
+                                          rankvit_layers=[3, 6, 9])),
+}
+
+
+@pytest.mark.parametrize("name", sorted(_REF_CONFIGS))
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_reference_model_configs_run_and_match_the_oracle(name, precision):
+    """Every dense / rank model shape the reference ships a config for (configs/model/*.yaml): head_dim 32 / 48 / 64,
+    hidden 192 - 384, patch 8 / 16, at 224 px; both arithmetic modes against the fp32 oracle."""
+    from oracle import peekvit_oracle as po, weights as ow
+    from peekvit_b200.models import build_model
+    fam, kw = _REF_CONFIGS[name]
+    cfg = dict(kw, image_size=224, num_classes=10)
+    sd = ow.make_state_dict(fam, cfg, seed=77)
+    images = ow.synthetic_images(3, 224, seed=78)
+    budget = 0.5 if fam == "rankvit" else None
+    ref, _ = po.forward(fam, sd, cfg, images, budget)
+    model = build_model(NAMES[fam], cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    if budget is not None:
+        model.set_budget(budget)
+    model.pk_precision = precision
+    logits = model(images.to(DEV)).cpu()
+    err = ((logits - ref).abs().max() / ref.abs().max()).item()
+    # RankViT in bf16 mode may swap tokens at the cut (discontinuous selection): its band is the fixture tests' one
+    assert err < (TOL_FP32_MODE if precision == "fp32" else (5e-2 if fam == "rankvit" else TOL_LOGITS)), err
