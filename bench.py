@@ -222,13 +222,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
+    # pinned host copies of the batch for the end-to-end leg (allocated and warmed up here so that the two timed regions
+    # below run back to back in the same thermal / power state)
+    host_images = torch.empty(B, 3, 224, 224, dtype=torch.float32, pin_memory=True)
+    host_images.copy_(images)
+    host_logits = torch.empty(B, CFG_B["num_classes"], dtype=torch.float32, pin_memory=True)
+    for _ in range(2):
+        model.forward_host(host_images, host_logits)
+    # the clock sampler starts BEFORE the warm-up (idle samples are filtered by power draw), so that the timed region follows
+    # the warm-up steps without an idle gap: a pause right before it lets the GPU boost above its sustained clocks
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
+    barrier()
+    for _ in range(args.warmup):
+        step()
     ops.launch_count = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -244,6 +253,21 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
 
+    # ---- e2e: pinned host batch -> module API -> host logits, copies inside the timed region
+    e2e_steps = max(2, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(e2e_steps):
+        model.forward_host(host_images, host_logits)
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+
     # ---- roofline pass: the same K steps again with CUDA events around every GEMM launch (the per-launch
     # events cannot be recorded from inside the CUDA-graph replay the timed region uses, so this pass runs
     # the identical launch sequence eagerly; clocks are sampled over both regions)
@@ -258,26 +282,6 @@ def main():
     eager_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     flag = ops.device_flag()
-
-    # ---- e2e: pinned host batch -> module API -> host logits, copies inside the timed region
-    host_images = torch.empty(B, 3, 224, 224, dtype=torch.float32, pin_memory=True)
-    host_images.copy_(images)
-    host_logits = torch.empty(B, CFG_B["num_classes"], dtype=torch.float32, pin_memory=True)
-    for _ in range(2):
-        model.forward_host(host_images, host_logits)
-    barrier()
-    e2e_steps = max(2, min(args.steps, 5))
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(e2e_steps):
-        model.forward_host(host_images, host_logits)
-    e1.record()
-    barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
 
     # ---- same end-to-end call fed with uint8 HWC images (ToTensor + Normalize fused into the im2col):
     # informational, the headline e2e above is the reference-facing float API
