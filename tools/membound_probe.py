@@ -85,6 +85,24 @@ ys = torch.empty(B * cap, Ds, device=DEV); rs = torch.empty(B * cap, device=DEV)
 def compact():
     ops.compact_rows(xs, ys, cu, cu_out, B, B * cap, dst, smp, scale_in=mask, scale_out=rs, attrs=[(mult, mo)], ghost=True)
 report(f"compact_rows (K13, {kept_rows} of {B * n} rows kept)", time_us(compact, flush=flush), kept_rows * Ds * 8 + B * n * 12)
+# kernels added later in the round: fp32-mode split rows, NoiseBlock, MoE routing helpers
+a6 = torch.empty(rows, 6 * D, device=DEV, dtype=torch.bfloat16)
+report("split3 + LayerNorm (fp32 mode, ViT-B, 512 img)", time_us(lambda: ops.split3(x, a6, ops.SPLIT_LAYERNORM, g, b, 1e-5), flush=flush), rows * D * 16)
+hid32 = torch.randn(B // 4 * seq, 3072, device=DEV)
+h6 = torch.empty(B // 4 * seq, 6 * 3072, device=DEV, dtype=torch.bfloat16)
+report("split3 + exact GELU (fp32 mode, 128 img hidden rows)", time_us(lambda: ops.split3(hid32, h6, ops.SPLIT_GELU), flush=flush), hid32.numel() * 16)
+noise = torch.randn(rows, D, device=DEV)
+report("noise_snr (NoiseBlock, ViT-B, 512 img)", time_us(lambda: ops.noise_snr(x, noise, 10.0), flush=flush), rows * D * 12)
+xs2 = torch.randn(rows, 384, device=DEV); ysrt = torch.randn(rows, 384, device=DEV)
+perm = torch.randperm(rows, device=DEV).to(torch.int32)
+report("scatter_add_rows (MoE un-permute, ViT-S, 512 img)", time_us(lambda: ops.scatter_add_rows(xs2, ysrt, perm), flush=flush), rows * 384 * 12)
+gwm, gbm = torch.randn(4, 384, device=DEV), torch.zeros(4, device=DEV)
+gs, bs = torch.ones(384, device=DEV), torch.zeros(384, device=DEV)
+ex = torch.empty(rows, device=DEV, dtype=torch.int32); off = torch.empty(5, device=DEV, dtype=torch.int32); cnt = torch.empty(4, device=DEV, dtype=torch.int32)
+src = torch.empty(rows, device=DEV, dtype=torch.int32); scr = torch.empty(ops.MOE_SORT_SCRATCH_INTS, device=DEV, dtype=torch.int32)
+report("moe_route (LN + gate + arg-max + counting sort, ViT-S, 4 experts)",
+       time_us(lambda: ops.moe_route(xs2, gs, bs, 1e-5, gwm, gbm, rows, ex, off, cnt, src, scratch=scr), flush=flush), rows * (384 * 4 + 8),
+       note="four kernels: route, histogram, scan, scatter")
 if "--json" in sys.argv:
     p = sys.argv[sys.argv.index("--json") + 1]
     os.makedirs(os.path.dirname(p), exist_ok=True)
