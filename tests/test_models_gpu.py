@@ -427,3 +427,44 @@ def test_reference_model_configs_run_and_match_the_oracle(name, precision):
     err = ((logits - ref).abs().max() / ref.abs().max()).item()
     # RankViT in bf16 mode may swap tokens at the cut (discontinuous selection): its band is the fixture tests' one
     assert err < (TOL_FP32_MODE if precision == "fp32" else (5e-2 if fam == "rankvit" else TOL_LOGITS)), err
+
+
+# ------------------------------------------------------------------ evaluation loop (validate/test.py:97-156)
+def test_evaluate_loop_accuracy_and_analytic_cost():
+    """peekvit_b200.evaluate: per-budget accuracy with the count kept on the device, cost per image from the token counts
+    of the forward (against the oracle's predictions and the oracle's FLOP formula on its own kept-token counts)."""
+    from oracle import peekvit_oracle as po
+    from peekvit_b200.evaluate import evaluate
+    case = CASES["rankvit_b05"]
+    model, sd, images = _model(case)
+    model.pk_precision = "fp32"                     # exact selections -> exact comparisons
+    ref, oaux = po.forward("rankvit", sd, case["cfg"], images, 0.5)
+    labels = ref.argmax(1)
+    labels[0] = (labels[0] + 1) % case["cfg"]["num_classes"]            # one deliberately wrong label
+    batches = [(images[:3], labels[:3]), (images[3:], labels[3:])]
+    res = evaluate(model, batches, budgets=[1.0, 0.5])
+    assert set(res) == {1.0, 0.5}
+    assert res[0.5]["accuracy"] == pytest.approx((len(images) - 1) / len(images))
+    assert res[0.5]["tokens_per_layer"] == [float(n) for n in oaux["seq_lens"]]
+    assert res[0.5]["gmacs_per_image"] == pytest.approx(po.flops_per_image(case["cfg"], oaux["seq_lens"]) / 2e9, rel=1e-6)
+    assert res[1.0]["gmacs_per_image"] == pytest.approx(po.flops_per_image(case["cfg"]) / 2e9, rel=1e-6)
+    assert res[0.5]["gmacs_per_image"] < res[1.0]["gmacs_per_image"] and res[0.5]["images_per_second"] > 0
+    # ResidualViT: live-row counts stay on the device until the end of the pass; fewer tokens at the smaller budget
+    rcase = CASES["residual_learnable_cal04"]
+    rmodel, rsd, rimg = _model(rcase)
+    rres = evaluate(rmodel, [(rimg, torch.zeros(len(rimg), dtype=torch.long))], budgets=[0.9, 0.2])
+    for b in (0.9, 0.2):
+        assert len(rres[b]["tokens_per_layer"]) == rcase["cfg"]["num_layers"] and rres[b]["gmacs_per_image"] > 0
+    # reference accounting of the last pass (budget 0.2): class + budget token + the tokens the published masks keep; the
+    # rows actually computed are at most that + one ghost row (re-admitted dropped tokens travel as one row)
+    for i, blk in enumerate(rmodel.encoder.layers):
+        kept = (blk.mask[..., 0] > 0).sum(1).float()
+        assert rres[0.2]["tokens_per_layer"][i] == pytest.approx(float((2 + kept).mean()))
+        assert rres[0.2]["computed_rows_per_layer"][i] <= rres[0.2]["tokens_per_layer"][i] + 1
+    # noise sweep (validate/test.py:108-112): results keyed by noise value
+    from peekvit_b200.models import add_noise
+    vcase = CASES["vit_d64_h2"]
+    vmodel, vsd, vimg = _model(vcase)
+    nb = add_noise(vmodel, layer=1, noise_type="gaussian", snr=10.0)
+    vres = evaluate(vmodel, [(vimg, torch.zeros(len(vimg), dtype=torch.long))], noise_module=nb, noise_vals=[0.0, 5.0])
+    assert set(vres[None]) == {0.0, 5.0} and "accuracy" in vres[None][5.0]
