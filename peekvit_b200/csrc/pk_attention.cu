@@ -42,6 +42,12 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ float fmax3_att(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 // Byte offset of 16-byte chunk `c` of row `r` in a [rows][DH] bf16 tile, XOR-swizzled so that 8
 // consecutive rows at one logical chunk hit 8 distinct 16-byte bank groups.
 template <int DH>
@@ -63,7 +69,7 @@ struct AttParams {
 };
 
 template <int DH>
-__global__ void __launch_bounds__(kAttThreads, 2)
+__global__ void __launch_bounds__(kAttThreads, 3)
 attention_fwd_kernel(const AttParams p) {
   constexpr int CPR = DH / 8;
   constexpr int KS = DH / 16;                       // k-steps over head_dim for QK^T
@@ -95,26 +101,45 @@ attention_fwd_kernel(const AttParams p) {
   const __nv_bfloat16* k_base = q_base + D;
   const __nv_bfloat16* v_base = q_base + 2 * D;
 
+  // Per-thread constants of the K/V tile loader: chunk i = tid + k * 128 of a tile always maps to the same (row, 16-byte
+  // chunk), so its shared-memory offset and its source offset inside the tile are computed once (the loader's address
+  // arithmetic was a fifth of the kernel's issue slots: ncu showed 62 - 70 % issue-active against 33 - 40 % tensor-active).
+  constexpr int LD_ITERS = kAttBKV * CPR / kAttThreads;
+  static_assert(kAttBKV * CPR % kAttThreads == 0, "loader assumes a whole number of chunks per thread");
+  int ld_row[LD_ITERS];
+  uint32_t ld_soff[LD_ITERS];
+  int ld_goff[LD_ITERS];                            // element offset inside a tile: < 64 * 3D
+#pragma unroll
+  for (int k = 0; k < LD_ITERS; ++k) {
+    const int i = tid + k * kAttThreads;
+    const int r = i / CPR, c = i % CPR;
+    ld_row[k] = r;
+    ld_soff[k] = tile_off<SDH>(r, c);
+    ld_goff[k] = r * static_cast<int>(ld) + c * 8;
+  }
   auto load_kv_tile = [&](int t, int buf) {
     const int kv0 = t * kAttBKV;
     const uint32_t sk = smem_u32(s_k[buf]), sv = smem_u32(s_v[buf]);
-    for (int i = tid; i < kAttBKV * CPR; i += kAttThreads) {
-      const int r = i / CPR, c = i % CPR;
-      const int key = kv0 + r;
+    const __nv_bfloat16* kt = k_base + (long long)kv0 * ld;
+    const __nv_bfloat16* vt = v_base + (long long)kv0 * ld;
+#pragma unroll
+    for (int k = 0; k < LD_ITERS; ++k) {
+      const int key = kv0 + ld_row[k];
       const __nv_bfloat16* ksrc = k_base;
       const __nv_bfloat16* vsrc = v_base;
       int bytes = 0;
       if (key < len) {
-        ksrc = k_base + (long long)key * ld + c * 8;
-        vsrc = v_base + (long long)key * ld + c * 8;
+        ksrc = kt + ld_goff[k];
+        vsrc = vt + ld_goff[k];
         bytes = 16;
       } else if (has_extra && key == len) {
-        ksrc = p.extra_kv + h * DH + c * 8;
-        vsrc = p.extra_kv + D + h * DH + c * 8;
+        const int eoff = h * DH + (ld_goff[k] - ld_row[k] * static_cast<int>(ld));      // h * DH + c * 8
+        ksrc = p.extra_kv + eoff;
+        vsrc = p.extra_kv + D + eoff;
         bytes = 16;
       }
-      cp_async16(sk + tile_off<SDH>(r, c), ksrc, bytes);
-      cp_async16(sv + tile_off<SDH>(r, c), vsrc, bytes);
+      cp_async16(sk + ld_soff[k], ksrc, bytes);
+      cp_async16(sv + ld_soff[k], vsrc, bytes);
     }
     if (tid < kAttBKV) {
       const int key = kv0 + tid;
@@ -138,6 +163,14 @@ attention_fwd_kernel(const AttParams p) {
     cp_async_commit();
   }
 
+  // ldmatrix offsets of this lane inside a 16-key group: the swizzle term depends on the row only modulo 8, so stepping to
+  // the next 16 keys is a constant add
+  uint32_t koff[KS], voff[DH / 16];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) koff[ks] = tile_off<SDH>((lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1));
+#pragma unroll
+  for (int nd = 0; nd < DH / 16; ++nd) voff[nd] = tile_off<SDH>((lane & 7) + (((lane >> 3) & 1) << 3), nd * 2 + (lane >> 4));
+  const bool warp_live = q0 + warp * 16 < len;       // warp-uniform
   uint32_t qf[KS][4];
   float o[DH / 8][4];
 #pragma unroll
@@ -161,6 +194,9 @@ attention_fwd_kernel(const AttParams p) {
       for (int ks = 0; ks < KS; ++ks)
         ldsm_x4(sq + tile_off<SDH>(warp * 16 + (lane & 15), ks * 2 + (lane >> 4)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
     }
+    // a warp whose 16 query rows all lie past the end of the sample (the last query tile of n = 197 has 5 valid rows) only
+    // helps with the loads: its MMAs and softmax would be issue slots taken from the CTAs that share the SM
+    if (warp_live) {
     const uint32_t sk = smem_u32(s_k[buf]), sv = smem_u32(s_v[buf]);
 
     // ---- S = Q K^T for 64 keys: 8 n-tiles of 8 keys
@@ -172,27 +208,26 @@ attention_fwd_kernel(const AttParams p) {
 #pragma unroll
       for (int np = 0; np < 4; ++np) {               // 16 keys per ldmatrix.x4
         uint32_t b0, b1, b2, b3;
-        const int key = np * 16 + (lane & 7) + ((lane >> 4) << 3);
-        const int chunk = ks * 2 + ((lane >> 3) & 1);
-        ldsm_x4(sk + tile_off<SDH>(key, chunk), b0, b1, b2, b3);
+        ldsm_x4(sk + koff[ks] + np * (16 * SDH * 2), b0, b1, b2, b3);
         mma_bf16_16816(s[np * 2], qf[ks], b0, b1);
         mma_bf16_16816(s[np * 2 + 1], qf[ks], b2, b3);
       }
     }
-    // ---- scale, key bias / mask, online softmax (rows g = lane/4 and g+8)
+    // ---- scale, key bias / mask, online softmax (rows g = lane/4 and g+8) on packed f32x2 arithmetic: every accumulator
+    // pair (two adjacent keys of one row) is one FFMA2 / FADD2, the row maxima use 3-input max
+    const uint64_t sc2 = f2_pack(p.scale_log2, p.scale_log2);
     float tmax[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
       const int kc = n * 8 + (lane & 3) * 2;
-      const float b0 = s_bias[buf][kc], b1 = s_bias[buf][kc + 1];
-      s[n][0] = fmaf(s[n][0], p.scale_log2, b0);
-      s[n][1] = fmaf(s[n][1], p.scale_log2, b1);
-      s[n][2] = fmaf(s[n][2], p.scale_log2, b0);
-      s[n][3] = fmaf(s[n][3], p.scale_log2, b1);
-      tmax[0] = fmaxf(tmax[0], fmaxf(s[n][0], s[n][1]));
-      tmax[1] = fmaxf(tmax[1], fmaxf(s[n][2], s[n][3]));
+      const float2 bb = *reinterpret_cast<const float2*>(&s_bias[buf][kc]);
+      const uint64_t b2 = f2_pack(bb.x, bb.y);
+      f2_unpack(f2_fma(f2_pack(s[n][0], s[n][1]), sc2, b2), s[n][0], s[n][1]);      // scaled + biased logits, in place
+      f2_unpack(f2_fma(f2_pack(s[n][2], s[n][3]), sc2, b2), s[n][2], s[n][3]);
+      tmax[0] = fmax3_att(tmax[0], s[n][0], s[n][1]);
+      tmax[1] = fmax3_att(tmax[1], s[n][2], s[n][3]);
     }
-    float corr[2], m_use[2], rsum[2] = {0.f, 0.f};
+    float corr[2], m_use[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 1));
@@ -203,21 +238,33 @@ attention_fwd_kernel(const AttParams p) {
       m_run[r] = m_new;
     }
     uint32_t pf[4][4];                                // P as bf16 A-fragments, 4 k-steps of 16 keys
+    const uint64_t nm0 = f2_pack(-m_use[0], -m_use[0]), nm1 = f2_pack(-m_use[1], -m_use[1]);
+    uint64_t rs0 = f2_pack(0.f, 0.f), rs1 = rs0;
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
-      const float p0 = exp2f(s[n][0] - m_use[0]), p1 = exp2f(s[n][1] - m_use[0]);
-      const float p2 = exp2f(s[n][2] - m_use[1]), p3 = exp2f(s[n][3] - m_use[1]);
-      rsum[0] += p0 + p1;
-      rsum[1] += p2 + p3;
+      float x0, x1, x2, x3;
+      f2_unpack(f2_add(f2_pack(s[n][0], s[n][1]), nm0), x0, x1);
+      f2_unpack(f2_add(f2_pack(s[n][2], s[n][3]), nm1), x2, x3);
+      const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2), p3 = ex2_approx(x3);
+      rs0 = f2_add(rs0, f2_pack(p0, p1));
+      rs1 = f2_add(rs1, f2_pack(p2, p3));
       pf[n >> 1][(n & 1) * 2] = pack_bf16(p0, p1);
       pf[n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2, p3);
     }
+    {
+      float a, b;
+      f2_unpack(rs0, a, b);
+      l_run[0] = l_run[0] * corr[0] + (a + b);       // per-thread partial; reduced at the end
+      f2_unpack(rs1, a, b);
+      l_run[1] = l_run[1] * corr[1] + (a + b);
+    }
+    {
+      const uint64_t c0 = f2_pack(corr[0], corr[0]), c1 = f2_pack(corr[1], corr[1]);
 #pragma unroll
-    for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rsum[r];   // per-thread partial; reduced at the end
-#pragma unroll
-    for (int n = 0; n < DH / 8; ++n) {
-      o[n][0] *= corr[0]; o[n][1] *= corr[0];
-      o[n][2] *= corr[1]; o[n][3] *= corr[1];
+      for (int n = 0; n < DH / 8; ++n) {
+        f2_unpack(f2_mul(f2_pack(o[n][0], o[n][1]), c0), o[n][0], o[n][1]);
+        f2_unpack(f2_mul(f2_pack(o[n][2], o[n][3]), c1), o[n][2], o[n][3]);
+      }
     }
     // ---- O += P V
 #pragma unroll
@@ -225,12 +272,11 @@ attention_fwd_kernel(const AttParams p) {
 #pragma unroll
       for (int nd = 0; nd < DH / 16; ++nd) {         // 16 head-dim columns per ldmatrix.x4.trans
         uint32_t b0, b1, b2, b3;
-        const int key = kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
-        const int chunk = nd * 2 + (lane >> 4);
-        ldsm_x4_trans(sv + tile_off<SDH>(key, chunk), b0, b1, b2, b3);
+        ldsm_x4_trans(sv + voff[nd] + kk * (16 * SDH * 2), b0, b1, b2, b3);
         mma_bf16_16816(o[nd * 2], pf[kk], b0, b1);
         mma_bf16_16816(o[nd * 2 + 1], pf[kk], b2, b3);
       }
+    }
     }
     __syncthreads();   // everyone done with buf before it is refilled two iterations later
   }
