@@ -18,7 +18,8 @@ DEFAULT_MICRO_BATCH = int(os.environ.get("PEEKVIT_B200_MICRO_BATCH", "512"))
 # reference's shipped dtype: 3-way split operands on the same tcgen05 GEMMs + fp32 attention, logits within 1e-5, every family).
 # Per model: ``model.pk_precision = "fp32"``.
 DEFAULT_PRECISION = os.environ.get("PEEKVIT_B200_PRECISION", "bf16")
-EXACT_MICRO_BATCH = 64          # the split activation rows are 6x wider: keep the workspace of the fp32 mode small
+# the split activation rows are 6x wider: the fp32 mode runs in smaller micro-batches (workspace 15 MB per image at ViT-B/16)
+EXACT_MICRO_BATCH = int(os.environ.get("PEEKVIT_B200_EXACT_MICRO_BATCH", "256"))
 
 
 def _exact(model) -> bool:
