@@ -104,12 +104,30 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def synthetic_weights_(model, seed: int = 4321) -> None:
+    """the reference constructor zero-initialises head.*, the class token and every MHA bias, which makes
+    random-init logits identically zero; the tensors it leaves at zero / one are re-drawn from a seeded generator (N(0, 0.02),
+    LayerNorm gains 1 + N(0, 0.02)), everything else keeps the constructor's initialisation (under torch.manual_seed(0))."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if ".ln" in name and name.endswith("weight") or name.startswith("encoder.ln.weight"):
+                p.copy_(1.0 + 0.02 * torch.randn(p.shape, generator=g))
+            elif name.endswith("bias") or name in ("class_tokens", "class_token", "head.weight"):
+                if name == "head.weight":
+                    p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) / p.shape[1] ** 0.5)
+                else:
+                    p.copy_(0.02 * torch.randn(p.shape, generator=g))
+
+
 def build_model(device):
-    from oracle import weights as ow           # seeded synthetic weights only (no oracle compute on this path)
+    """The measured arm builds its model and synthetic weights without touching ``oracle/``; the returned CPU state dict
+    is what the cpu_baseline leg hands to the oracle port."""
     from peekvit_b200.models import VisionTransformer
-    sd = ow.make_state_dict("vit", CFG_B, seed=4321)
+    torch.manual_seed(0)
     model = VisionTransformer(**CFG_B)
-    model.load_state_dict(sd, strict=True)
+    synthetic_weights_(model)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     return model.to(device).eval(), sd
 
 
