@@ -157,6 +157,10 @@ int pk_attention_trace(unsigned long long* host_dst);
 int pk_cls_head(const float* x, int batch, int seq_len, const int* cu_seqlens, int n_cls, int dim,
                 const float* gamma, const float* beta, float eps,
                 const float* head_w, const float* head_b, int num_classes, float* logits, void* stream);
+/* feat[b, :] = sum_{t<n_cls} LN(x[row(b)+t, :]) (f32 [batch, dim]): the head's input on its own, for batches large enough
+ * that the head runs as a split-operand tensor-core GEMM (pk_split3_bf16 + pk_gemm_bf16) instead of inside pk_cls_head. */
+int pk_cls_features(const float* x, int batch, int seq_len, const int* cu_seqlens, int n_cls, int dim, const float* gamma,
+                    const float* beta, float eps, float* feat, void* stream);
 
 /* ---- eval loop: top-1 prediction and accuracy counts on the device (validate/test.py:116-129 does
  * logits.argmax + torchmetrics on the host side).  pred_out[b] = first arg-max of logits[b, :] (int32, optional);

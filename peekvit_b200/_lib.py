@@ -114,6 +114,7 @@ SIGNATURES: Dict[str, tuple] = {
     "pk_residual_publish": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "pk_avit_halt_plan": (c_int, [C.POINTER(AvitArgs), c_void_p]),
     "pk_scatter_add_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "pk_cls_features": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
     "pk_expert_onehot": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "pk_split3_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pk_patchify_split3": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

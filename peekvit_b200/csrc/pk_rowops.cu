@@ -226,6 +226,45 @@ cls_head_kernel(const float* __restrict__ x, int batch, int seq_len, const int* 
   }
 }
 
+// LN(x[class rows]) summed over the class tokens -> feat f32 [batch, dim]: the head's input (vit.py:95,242-243).  One warp per
+// sample.  Used when the head itself runs as a split-operand tensor-core GEMM (large batches); cls_head_kernel above fuses the
+// head in for small ones.
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+cls_features_kernel(const float* __restrict__ x, int batch, int seq_len, const int* __restrict__ cu_seqlens, int n_cls, int dim,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ feat) {
+  const int lane = lane_id();
+  const int d4 = dim / 4;
+  const int b = blockIdx.x * (blockDim.x >> 5) + warp_id();
+  if (b >= batch) return;
+  float4 acc[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long row0 = cu_seqlens ? cu_seqlens[b] : (long long)b * seq_len;
+  for (int t = 0; t < n_cls; ++t) {
+    float4 v[MAXV];
+    float sum, mean, rstd;
+    ln_row_load<MAXV>(x + (row0 + t) * dim, d4, lane, v, sum);
+    ln_row_stats<MAXV>(v, d4, lane, dim, sum, eps, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + i * 32;
+      if (c < d4) {
+        const float4 g = ldg4(gamma + c * 4), be = ldg4(beta + c * 4);
+        acc[i].x += fmaf((v[i].x - mean) * rstd, g.x, be.x);
+        acc[i].y += fmaf((v[i].y - mean) * rstd, g.y, be.y);
+        acc[i].z += fmaf((v[i].z - mean) * rstd, g.z, be.z);
+        acc[i].w += fmaf((v[i].w - mean) * rstd, g.w, be.w);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < d4) *reinterpret_cast<float4*>(feat + (long long)b * dim + c * 4) = acc[i];
+  }
+}
+
 // ------------------------------------------------------------------------------ RankViT
 __global__ void __launch_bounds__(256)
 token_norm_score_kernel(const float* __restrict__ x, float* __restrict__ scores, int batch, int seq_len, int dim) {
@@ -417,7 +456,12 @@ extern "C" int pk_cls_head(const float* x, int batch, int seq_len, const int* cu
   if (batch == 0) return PK_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int groups = (batch + kHeadGroup - 1) / kHeadGroup;
-  int chunks = (2 * num_sms() + groups - 1) / groups;                 // aim at >= 2 CTAs per SM
+  // the class sweep is bound by the latency of the head_w loads (L2), so the classes are split finely: >= PK_HEAD_CTAS_PER_SM
+  // (default 8) CTAs per SM keep enough loads in flight (145 -> see profiles; the LayerNorm of the 8 class rows is repeated
+  // per chunk and costs nothing)
+  static int per_sm = -1;
+  if (per_sm < 0) { const char* e = getenv("PK_HEAD_CTAS_PER_SM"); per_sm = e ? atoi(e) : 8; if (per_sm < 1) per_sm = 1; }
+  int chunks = (per_sm * num_sms() + groups - 1) / groups;
   chunks = std::max(1, std::min(chunks, (num_classes + 7) / 8));      // at least one class per warp
   const dim3 grid(groups, chunks);
   const size_t smem = (size_t)kHeadGroup * dim * sizeof(float);
@@ -427,6 +471,20 @@ extern "C" int pk_cls_head(const float* x, int batch, int seq_len, const int* cu
   else
     cls_head_kernel<8><<<grid, 256, smem, s>>>(x, batch, seq_len, cu_seqlens, n_cls, dim, gamma, beta, eps, head_w, head_b, num_classes, logits);
   return check_cuda(cudaGetLastError(), "cls_head_kernel");
+}
+
+extern "C" int pk_cls_features(const float* x, int batch, int seq_len, const int* cu_seqlens, int n_cls, int dim, const float* gamma,
+                               const float* beta, float eps, float* feat, void* stream) {
+  using namespace pk;
+  PK_REQUIRE(x && gamma && beta && feat, "pk_cls_features: null pointer");
+  PK_REQUIRE(dim % 4 == 0 && dim <= 1024 && n_cls >= 1, "pk_cls_features: dim %d must be a multiple of 4, <= 1024", dim);
+  if (batch == 0) return PK_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = (batch + 7) / 8;
+  const int maxv = (dim / 4 + 31) / 32;
+  if (maxv <= 3) cls_features_kernel<3><<<grid, 256, 0, s>>>(x, batch, seq_len, cu_seqlens, n_cls, dim, gamma, beta, eps, feat);
+  else cls_features_kernel<8><<<grid, 256, 0, s>>>(x, batch, seq_len, cu_seqlens, n_cls, dim, gamma, beta, eps, feat);
+  return check_cuda(cudaGetLastError(), "cls_features_kernel");
 }
 
 // ------------------------------------------------------------------ LayerNorm statistics + raw bf16 copy (fused-LN GEMM chain)

@@ -33,6 +33,8 @@ LN_FOLD = int(os.environ.get("PEEKVIT_B200_LN_FOLD", "1"))
 # 1: the im2col operand has one row per token, so the patch GEMM runs on the CTA-pair kernel and writes the residual
 # stream (and layer 0's LayerNorm statistics) directly; 0: densely packed patches + row-remap epilogue (single-CTA kernel)
 EMBED_TOKEN_ROWS = int(os.environ.get("PEEKVIT_B200_EMBED_TOKEN_ROWS", "1"))
+# 1: for more than 256 samples the classification head runs as a split-operand tensor-core GEMM; 0: always the fused kernel
+HEAD_GEMM = int(os.environ.get("PEEKVIT_B200_HEAD_GEMM", "1"))
 
 
 def _f32(t: torch.Tensor) -> torch.Tensor:
@@ -531,9 +533,21 @@ class Forward:
             ops.gemm(hid, mw.w_fc2, mw.b_fc2, x[:rows], PK_EPI_BIAS_RESID_F32, resid=x[:rows])
 
     def head(self, x: torch.Tensor, batch: int, seq: int, cu_seqlens=None, n_cls: Optional[int] = None) -> torch.Tensor:
+        """Final LayerNorm on the class rows, class-token sum, linear head (vit.py:95,242-246), in fp32.  Batches of more than
+        256 samples run the head as a tensor-core GEMM over 3-way split operands (the fp32-accurate form: 1e-6 of the fp32
+        product), fed by a one-warp-per-sample LayerNorm; smaller ones use the fused CUDA-core kernel."""
         pm = self.pm
-        return ops.cls_head(x, batch, seq, pm.n_cls if n_cls is None else n_cls, pm.ln_w, pm.ln_b, pm.ln_eps, pm.head_w, pm.head_b,
-                            cu_seqlens=cu_seqlens, out=self.ws.get("logits", (batch, pm.num_classes), torch.float32))
+        n_cls = pm.n_cls if n_cls is None else n_cls
+        logits = self.ws.get("logits", (batch, pm.num_classes), torch.float32)
+        if HEAD_GEMM and batch > 256 and pm.num_classes % 8 == 0 and pm.dim % 8 == 0:
+            w6 = pm.extra.get("head_w6")
+            if w6 is None:
+                w6 = pm.extra["head_w6"] = ops.split3_weight(pm.head_w)
+            feat = ops.cls_features(x, batch, seq, n_cls, pm.ln_w, pm.ln_b, pm.ln_eps, self.ws.get("cls_feat", (batch, pm.dim), torch.float32),
+                                    cu_seqlens=cu_seqlens)
+            f6 = ops.split3(feat, self.ws.get("cls_feat6", (batch, 6 * pm.dim), torch.bfloat16))
+            return ops.gemm(f6, w6, pm.head_b, logits, PK_EPI_BIAS_F32)
+        return ops.cls_head(x, batch, seq, n_cls, pm.ln_w, pm.ln_b, pm.ln_eps, pm.head_w, pm.head_b, cu_seqlens=cu_seqlens, out=logits)
 
     def _const(self, name: str, builder):
         """Device constants of the ragged paths (initial cu_seqlens, token ids ...), built once per shape."""

@@ -193,6 +193,16 @@ def cls_head(x: torch.Tensor, batch: int, seq_len: int, n_cls: int, gamma, beta,
     return out
 
 
+def cls_features(x: torch.Tensor, batch: int, seq_len: int, n_cls: int, gamma, beta, eps: float, out: torch.Tensor,
+                 cu_seqlens: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[b] = sum over the class tokens of LN(x[class rows of sample b]) (f32 [batch, dim])."""
+    lib = _lib_for(x)
+    check(lib.pk_cls_features(_ptr(x, torch.float32), batch, seq_len, _ptr(cu_seqlens, torch.int32), n_cls, x.shape[-1],
+                              _ptr(gamma, torch.float32), _ptr(beta, torch.float32), float(eps), _ptr(out, torch.float32), _stream()),
+          "pk_cls_features")
+    return out
+
+
 def argmax_count(logits: torch.Tensor, labels: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None,
                  pred: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
     """Top-1 prediction (int32) and/or accuracy counts (int64 [correct, total], accumulated) on the device."""

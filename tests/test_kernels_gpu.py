@@ -619,3 +619,22 @@ def test_patchify_split3(ops):
     seg = out.view(3 * P, 6, Kp)
     assert torch.equal(seg[:, 2], h) and torch.equal(seg[:, 0], m) and torch.equal(seg[:, 1], l)
     assert torch.equal(seg[:, 3], m) and torch.equal(seg[:, 4], h) and torch.equal(seg[:, 5], h)
+
+
+def test_head_as_split_gemm_matches_fused_head(ops):
+    """cls_features + split3 + GEMM (the large-batch head) == cls_head (fused CUDA-core kernel) == torch fp32."""
+    from peekvit_b200._lib import PK_EPI_BIAS_F32
+    B, seq, D, C, T = 300, 21, 256, 1000, 2
+    x = torch.randn(B * seq, D, device=DEV)
+    g, b = torch.randn(D, device=DEV), torch.randn(D, device=DEV)
+    w, hb = torch.randn(C, D, device=DEV) * 0.05, torch.randn(C, device=DEV)
+    fused = ops.cls_head(x, B, seq, T, g, b, 1e-5, w, hb)
+    feat = ops.cls_features(x, B, seq, T, g, b, 1e-5, torch.empty(B, D, device=DEV))
+    f6 = ops.split3(feat, torch.empty(B, 6 * D, device=DEV, dtype=torch.bfloat16))
+    got = ops.gemm(f6, ops.split3_weight(w), hb, torch.empty(B, C, device=DEV), PK_EPI_BIAS_F32)
+    ref = torch.nn.functional.linear(torch.nn.functional.layer_norm(x.view(B, seq, D)[:, :T].double(), (D,), g.double(), b.double(), 1e-5).sum(1),
+                                     w.double(), hb.double())
+    assert rel_err(got.double(), ref) < 5e-6 and rel_err(fused.double(), ref) < 5e-6
+    cu = (torch.arange(B + 1, device=DEV, dtype=torch.int32) * seq)
+    feat2 = ops.cls_features(x, B, 0, T, g, b, 1e-5, torch.empty(B, D, device=DEV), cu_seqlens=cu)
+    assert torch.equal(feat, feat2)
