@@ -21,3 +21,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _deterministic_inputs(request):
+    """Every test draws its random inputs from a generator seeded by the test's own name: failures reproduce, and a tolerance
+    that holds once holds on every run (torch.manual_seed also seeds the CUDA generator)."""
+    import zlib
+    import torch
+    torch.manual_seed(zlib.crc32(request.node.nodeid.encode()) & 0x7FFFFFFF)
+    yield

