@@ -162,11 +162,14 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
   const bool valid = qi < n;
   const float* base = qkv + row0 * 3 * D + h * DH;
   float q[DH], o[DH];
+  const float qs = scale * 1.4426950408889634f;
 #pragma unroll
   for (int d = 0; d < DH; d += 4) {
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) t = *reinterpret_cast<const float4*>(base + static_cast<long long>(qi) * 3 * D + d);
-    q[d] = t.x * scale; q[d + 1] = t.y * scale; q[d + 2] = t.z * scale; q[d + 3] = t.w * scale;   // q pre-scaled like nn.MultiheadAttention
+    // q pre-scaled like nn.MultiheadAttention, times log2(e): the softmax runs in the base-2 domain (one MUFU ex2 per
+    // exponential, 2 ulp, instead of the multi-instruction expf)
+    q[d] = t.x * qs; q[d + 1] = t.y * qs; q[d + 2] = t.z * qs; q[d + 3] = t.w * qs;
     o[d] = o[d + 1] = o[d + 2] = o[d + 3] = 0.f;
   }
   float mx = -INFINITY, sum = 0.f;
@@ -194,18 +197,18 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
         const float4 kk = *reinterpret_cast<const float4*>(&ks[j][d]);
         acc = fmaf(q[d], kk.x, acc); acc = fmaf(q[d + 1], kk.y, acc); acc = fmaf(q[d + 2], kk.z, acc); acc = fmaf(q[d + 3], kk.w, acc);
       }
-      if (key_mult && j0 + j < n) acc += logf(key_mult[row0 + j0 + j]);
+      if (key_mult && j0 + j < n) acc += log2f(key_mult[row0 + j0 + j]);
       s[j] = (j0 + j < n) ? acc : -INFINITY;
       tmax = fmaxf(tmax, s[j]);
     }
-    const float corr = expf(mx - tmax);          // exp(-inf) = 0 on the first tile
+    const float corr = exp2f(mx - tmax);         // 2^(-inf) = 0 on the first tile
     mx = tmax;
     sum *= corr;
 #pragma unroll
     for (int d = 0; d < DH; ++d) o[d] *= corr;
 #pragma unroll
     for (int j = 0; j < KT; ++j) {
-      const float pj = expf(s[j] - mx);           // masked keys: exp(-inf) = 0
+      const float pj = exp2f(s[j] - mx);          // masked keys: 2^(-inf) = 0
       sum += pj;
 #pragma unroll
       for (int d = 0; d < DH; d += 4) {
@@ -222,10 +225,10 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
     float acc = 0.f;
 #pragma unroll
     for (int d = 0; d < DH; ++d) acc = fmaf(q[d], ke[d], acc);
-    acc += logf(em);
+    acc += log2f(em);
     const float tmax = fmaxf(mx, acc);
-    const float corr = expf(mx - tmax);
-    const float pe = expf(acc - tmax);
+    const float corr = exp2f(mx - tmax);
+    const float pe = exp2f(acc - tmax);
     sum = sum * corr + pe;
 #pragma unroll
     for (int d = 0; d < DH; ++d) o[d] = fmaf(pe, ve[d], o[d] * corr);
