@@ -468,3 +468,25 @@ def test_evaluate_loop_accuracy_and_analytic_cost():
     nb = add_noise(vmodel, layer=1, noise_type="gaussian", snr=10.0)
     vres = evaluate(vmodel, [(vimg, torch.zeros(len(vimg), dtype=torch.long))], noise_module=nb, noise_vals=[0.0, 5.0])
     assert set(vres[None]) == {0.0, 5.0} and "accuracy" in vres[None][5.0]
+
+
+def test_evaluate_loop_other_families():
+    """A-ViT (live-row lists per micro-batch), EE-ResidualViT (list output -> final head) and MoE (dense accounting)."""
+    from peekvit_b200.evaluate import evaluate
+    for name in ("avit", "eeresidual_learnable_cal04", "moevit"):
+        case = CASES[name]
+        model, sd, images = _model(case)
+        model.pk_micro_batch = 3                    # two micro-batches: the per-layer counts are summed over both
+        labels = torch.zeros(len(images), dtype=torch.long)
+        res = evaluate(model, [(images, labels)], budgets=[case.get("budget")])[case.get("budget")]
+        assert 0.0 <= res["accuracy"] <= 1.0 and res["gmacs_per_image"] > 0
+        L = case["cfg"]["num_layers"]
+        if name == "moevit":
+            assert res["tokens_per_layer"] is None
+        else:
+            assert len(res["tokens_per_layer"]) == L
+            full = 65 + (1 if name.startswith("eeresidual") else 0)
+            assert all(0 <= t <= full for t in res["tokens_per_layer"]), res["tokens_per_layer"]
+        if name == "avit":
+            # halting removes tokens: later layers see fewer rows than the first
+            assert res["tokens_per_layer"][-1] < res["tokens_per_layer"][0] == 65
