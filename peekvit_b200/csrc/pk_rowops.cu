@@ -456,9 +456,9 @@ extern "C" int pk_cls_head(const float* x, int batch, int seq_len, const int* cu
   if (batch == 0) return PK_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int groups = (batch + kHeadGroup - 1) / kHeadGroup;
-  // the class sweep is bound by the latency of the head_w loads (L2), so the classes are split finely: >= PK_HEAD_CTAS_PER_SM
-  // (default 8) CTAs per SM keep enough loads in flight (145 -> see profiles; the LayerNorm of the 8 class rows is repeated
-  // per chunk and costs nothing)
+  // classes are split over enough CTAs to fill the machine (PK_HEAD_CTAS_PER_SM, default 8: 4 - 16 measured the same,
+  // 110 - 117 us per 512 samples; the kernel is bound by the shared-memory reads of the staged features, which is why large
+  // batches take the tensor-core head instead, see engine.Forward.head)
   static int per_sm = -1;
   if (per_sm < 0) { const char* e = getenv("PK_HEAD_CTAS_PER_SM"); per_sm = e ? atoi(e) : 8; if (per_sm < 1) per_sm = 1; }
   int chunks = (per_sm * num_sms() + groups - 1) / groups;
