@@ -490,3 +490,23 @@ def test_evaluate_loop_other_families():
         if name == "avit":
             # halting removes tokens: later layers see fewer rows than the first
             assert res["tokens_per_layer"][-1] < res["tokens_per_layer"][0] == 65
+
+
+@pytest.mark.parametrize("name", [n for n in sorted(CASES) if CASES[n].get("noise") is None])
+def test_single_image_and_empty_batches(name):
+    """Edge cases of the batch dimension for every family: one image (every GEMM falls back to the single-CTA kernel) gives
+    the logits it gets inside the batch; an empty batch returns an empty result instead of launching anything."""
+    from peekvit_b200 import ops
+    case = CASES[name]
+    if case["family"] == "residualvit" and case["cfg"].get("add_budget_token") is True:
+        pytest.skip("a fixed-float budget token thresholds on the batch mean: single-image results differ by construction")
+    model, sd, images = _model(case)
+    x = images.to(DEV)
+    full = model(x)
+    one = model(x[2:3])
+    none = model(x[:0])
+    if isinstance(full, list):
+        full, one, none = full[-1], one[-1], none[-1]
+    assert ops.device_flag() == 0
+    assert tuple(one.shape) == (1, case["cfg"]["num_classes"]) and tuple(none.shape) == (0, case["cfg"]["num_classes"])
+    assert ((one - full[2:3]).abs().max() / full.abs().max()).item() < TOL_LOGITS
