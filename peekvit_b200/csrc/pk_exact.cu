@@ -141,15 +141,18 @@ __global__ void patchify_split3_kernel(const float* __restrict__ img, __nv_bfloa
 // softmax(q k^T * scale) v; qkv fp32 [rows, 3*H*DH] (q | k | v, heads = DH-column slices), out fp32 [rows, H*DH].  Samples are
 // uniform (n rows each) or ragged (cu_seqlens); a key may carry a multiplicity (logit + log mult: that many identical tokens)
 // and every sample one virtual key (k, v) = extra_kv with multiplicity extra_mult[b] — what the compacted ResidualViT / A-ViT
-// rows need.  One thread = one query row (q and the output accumulator in registers); a CTA of 128 queries of one (sample,
-// head) streams K / V through shared memory in tiles of 32 keys (every lane reads the same key element: broadcast), with the
-// usual running max / sum per tile.
+// rows need.
+// A CTA of 128 threads serves 128 queries of one (sample, head) and streams K / V through shared memory in tiles of 16 keys.
+// Two adjacent lanes form a pair that owns TWO queries; each lane holds one half of the head dimension of both (q and the
+// output accumulator in registers), so every K / V value read from shared memory feeds two FMAs (one query per thread made
+// the kernel shared-memory-bound at a 1:4 load-to-FMA ratio); the two halves of a logit meet through one shuffle.
 template <int DH>
 __global__ void __launch_bounds__(128)
 attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int batch, int heads, int n_uniform, float scale,
                      const int* __restrict__ cu_seqlens, const float* __restrict__ key_mult, const float* __restrict__ extra_kv,
                      const float* __restrict__ extra_mult) {
-  constexpr int KT = 32;
+  constexpr int KT = 16;
+  constexpr int HD = DH / 2;                       // head-dim half owned by a lane
   __shared__ __align__(16) float ks[KT][DH];
   __shared__ __align__(16) float vs[KT][DH];
   const int bh = blockIdx.y;
@@ -158,21 +161,25 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
   const long long row0 = cu_seqlens ? cu_seqlens[b] : static_cast<long long>(b) * n_uniform;
   const int n = cu_seqlens ? cu_seqlens[b + 1] - cu_seqlens[b] : n_uniform;
   if (blockIdx.x * 128 >= n) return;               // block-uniform: ragged grids are sized for the longest sample
-  const int qi = blockIdx.x * 128 + threadIdx.x;
-  const bool valid = qi < n;
+  const int pair = threadIdx.x >> 1, hf = threadIdx.x & 1;
+  const int d0 = hf * HD;
+  const int qa = blockIdx.x * 128 + pair, qb = qa + 64;
+  const bool va = qa < n, vb = qb < n;
   const float* base = qkv + row0 * 3 * D + h * DH;
-  float q[DH], o[DH];
+  // q pre-scaled like nn.MultiheadAttention, times log2(e): the softmax runs in the base-2 domain (one MUFU ex2 per exponential)
   const float qs = scale * 1.4426950408889634f;
+  float qA[HD], qB[HD], oA[HD], oB[HD];
 #pragma unroll
-  for (int d = 0; d < DH; d += 4) {
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) t = *reinterpret_cast<const float4*>(base + static_cast<long long>(qi) * 3 * D + d);
-    // q pre-scaled like nn.MultiheadAttention, times log2(e): the softmax runs in the base-2 domain (one MUFU ex2 per
-    // exponential, 2 ulp, instead of the multi-instruction expf)
-    q[d] = t.x * qs; q[d + 1] = t.y * qs; q[d + 2] = t.z * qs; q[d + 3] = t.w * qs;
-    o[d] = o[d + 1] = o[d + 2] = o[d + 3] = 0.f;
+  for (int d = 0; d < HD; d += 4) {
+    float4 ta = make_float4(0.f, 0.f, 0.f, 0.f), tb = ta;
+    if (va) ta = *reinterpret_cast<const float4*>(base + static_cast<long long>(qa) * 3 * D + d0 + d);
+    if (vb) tb = *reinterpret_cast<const float4*>(base + static_cast<long long>(qb) * 3 * D + d0 + d);
+    qA[d] = ta.x * qs; qA[d + 1] = ta.y * qs; qA[d + 2] = ta.z * qs; qA[d + 3] = ta.w * qs;
+    qB[d] = tb.x * qs; qB[d + 1] = tb.y * qs; qB[d + 2] = tb.z * qs; qB[d + 3] = tb.w * qs;
+    oA[d] = oA[d + 1] = oA[d + 2] = oA[d + 3] = 0.f;
+    oB[d] = oB[d + 1] = oB[d + 2] = oB[d + 3] = 0.f;
   }
-  float mx = -INFINITY, sum = 0.f;
+  float mxA = -INFINITY, mxB = -INFINITY, sumA = 0.f, sumB = 0.f;
   for (int j0 = 0; j0 < n; j0 += KT) {
     __syncthreads();
     for (int i = threadIdx.x; i < KT * DH / 4; i += 128) {
@@ -187,58 +194,76 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
       *reinterpret_cast<float4*>(&vs[j][d]) = vv;
     }
     __syncthreads();
-    float s[KT];
-    float tmax = mx;
+    float sA[KT], sB[KT];
+    float tA = mxA, tB = mxB;
 #pragma unroll
     for (int j = 0; j < KT; ++j) {
-      float acc = 0.f;
+      float a = 0.f, c = 0.f;
 #pragma unroll
-      for (int d = 0; d < DH; d += 4) {
-        const float4 kk = *reinterpret_cast<const float4*>(&ks[j][d]);
-        acc = fmaf(q[d], kk.x, acc); acc = fmaf(q[d + 1], kk.y, acc); acc = fmaf(q[d + 2], kk.z, acc); acc = fmaf(q[d + 3], kk.w, acc);
+      for (int d = 0; d < HD; d += 4) {
+        const float4 kk = *reinterpret_cast<const float4*>(&ks[j][d0 + d]);
+        a = fmaf(qA[d], kk.x, a); a = fmaf(qA[d + 1], kk.y, a); a = fmaf(qA[d + 2], kk.z, a); a = fmaf(qA[d + 3], kk.w, a);
+        c = fmaf(qB[d], kk.x, c); c = fmaf(qB[d + 1], kk.y, c); c = fmaf(qB[d + 2], kk.z, c); c = fmaf(qB[d + 3], kk.w, c);
       }
-      if (key_mult && j0 + j < n) acc += log2f(key_mult[row0 + j0 + j]);
-      s[j] = (j0 + j < n) ? acc : -INFINITY;
-      tmax = fmaxf(tmax, s[j]);
+      a += __shfl_xor_sync(0xffffffffu, a, 1);      // the other half of the head dimension (commutative: both lanes agree)
+      c += __shfl_xor_sync(0xffffffffu, c, 1);
+      if (j0 + j < n) {
+        if (key_mult) { const float lm = log2f(key_mult[row0 + j0 + j]); a += lm; c += lm; }
+      } else {
+        a = -INFINITY; c = -INFINITY;
+      }
+      sA[j] = a; sB[j] = c;
+      tA = fmaxf(tA, a); tB = fmaxf(tB, c);
     }
-    const float corr = exp2f(mx - tmax);         // 2^(-inf) = 0 on the first tile
-    mx = tmax;
-    sum *= corr;
+    const float corrA = exp2f(mxA - tA), corrB = exp2f(mxB - tB);          // 2^(-inf) = 0 on the first tile
+    mxA = tA; mxB = tB;
+    sumA *= corrA; sumB *= corrB;
 #pragma unroll
-    for (int d = 0; d < DH; ++d) o[d] *= corr;
+    for (int d = 0; d < HD; ++d) { oA[d] *= corrA; oB[d] *= corrB; }
 #pragma unroll
     for (int j = 0; j < KT; ++j) {
-      const float pj = exp2f(s[j] - mx);          // masked keys: 2^(-inf) = 0
-      sum += pj;
+      const float pa = exp2f(sA[j] - mxA), pb = exp2f(sB[j] - mxB);        // masked keys: 2^(-inf) = 0
+      sumA += pa; sumB += pb;
 #pragma unroll
-      for (int d = 0; d < DH; d += 4) {
-        const float4 vv = *reinterpret_cast<const float4*>(&vs[j][d]);
-        o[d] = fmaf(pj, vv.x, o[d]); o[d + 1] = fmaf(pj, vv.y, o[d + 1]); o[d + 2] = fmaf(pj, vv.z, o[d + 2]); o[d + 3] = fmaf(pj, vv.w, o[d + 3]);
+      for (int d = 0; d < HD; d += 4) {
+        const float4 vv = *reinterpret_cast<const float4*>(&vs[j][d0 + d]);
+        oA[d] = fmaf(pa, vv.x, oA[d]); oA[d + 1] = fmaf(pa, vv.y, oA[d + 1]); oA[d + 2] = fmaf(pa, vv.z, oA[d + 2]); oA[d + 3] = fmaf(pa, vv.w, oA[d + 3]);
+        oB[d] = fmaf(pb, vv.x, oB[d]); oB[d + 1] = fmaf(pb, vv.y, oB[d + 1]); oB[d + 2] = fmaf(pb, vv.z, oB[d + 2]); oB[d + 3] = fmaf(pb, vv.w, oB[d + 3]);
       }
     }
   }
   const float em = extra_mult ? extra_mult[b] : 0.f;
   if (extra_kv && em > 0.f) {
     // the virtual key: what em zero tokens project to (k-bias | v-bias)
-    const float* ke = extra_kv + h * DH;
-    const float* ve = extra_kv + D + h * DH;
-    float acc = 0.f;
+    const float* ke = extra_kv + h * DH + d0;
+    const float* ve = extra_kv + D + h * DH + d0;
+    float a = 0.f, c = 0.f;
 #pragma unroll
-    for (int d = 0; d < DH; ++d) acc = fmaf(q[d], ke[d], acc);
-    acc += log2f(em);
-    const float tmax = fmaxf(mx, acc);
-    const float corr = exp2f(mx - tmax);
-    const float pe = exp2f(acc - tmax);
-    sum = sum * corr + pe;
+    for (int d = 0; d < HD; ++d) { a = fmaf(qA[d], ke[d], a); c = fmaf(qB[d], ke[d], c); }
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    const float lm = log2f(em);
+    a += lm; c += lm;
+    const float tA = fmaxf(mxA, a), tB = fmaxf(mxB, c);
+    const float corrA = exp2f(mxA - tA), corrB = exp2f(mxB - tB);
+    const float pa = exp2f(a - tA), pb = exp2f(c - tB);
+    sumA = sumA * corrA + pa; sumB = sumB * corrB + pb;
 #pragma unroll
-    for (int d = 0; d < DH; ++d) o[d] = fmaf(pe, ve[d], o[d] * corr);
+    for (int d = 0; d < HD; ++d) { oA[d] = fmaf(pa, ve[d], oA[d] * corrA); oB[d] = fmaf(pb, ve[d], oB[d] * corrB); }
   }
-  if (valid) {
-    const float inv = 1.0f / sum;
-    float* orow = out + (row0 + qi) * D + h * DH;
+  if (va) {
+    const float inv = 1.0f / sumA;
+    float* orow = out + (row0 + qa) * D + h * DH + d0;
 #pragma unroll
-    for (int d = 0; d < DH; d += 4)
-      *reinterpret_cast<float4*>(orow + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+    for (int d = 0; d < HD; d += 4)
+      *reinterpret_cast<float4*>(orow + d) = make_float4(oA[d] * inv, oA[d + 1] * inv, oA[d + 2] * inv, oA[d + 3] * inv);
+  }
+  if (vb) {
+    const float inv = 1.0f / sumB;
+    float* orow = out + (row0 + qb) * D + h * DH + d0;
+#pragma unroll
+    for (int d = 0; d < HD; d += 4)
+      *reinterpret_cast<float4*>(orow + d) = make_float4(oB[d] * inv, oB[d + 1] * inv, oB[d + 2] * inv, oB[d + 3] * inv);
   }
 }
 
