@@ -24,3 +24,13 @@ for mode in ("bf16", "fp32"):
     print(json.dumps(dict(mode=mode, images=N, rel_err=err, top1_agreement=agree, disagreements=int(dis.numel()),
                           oracle_margin_at_disagreements=[round(float(margin[i]), 5) for i in dis[:8]],
                           median_margin=float(margin.median()), max_abs_logit=float(ref.abs().max()), cpu_s=round(t_cpu, 1))))
+# context: what the reference's own bf16 path (.to(bfloat16)) gives against the same fp32 oracle on this GPU
+sd16 = {k: v.cuda().bfloat16() for k, v in sd.items()}
+with torch.no_grad():
+    logits = torch.cat([po.vit_forward(sd16, cfg, images[s:s + 128].cuda().bfloat16())[0].float().cpu() for s in range(0, N, 128)])
+err = ((logits - ref).abs().max() / ref.abs().max()).item()
+dis = (logits.argmax(1) != ref.argmax(1)).nonzero().flatten()
+print(json.dumps(dict(mode="reference torch ops, .to(bfloat16), eager on this GPU", images=N, rel_err=err,
+                      top1_agreement=1 - dis.numel() / N, disagreements=int(dis.numel()),
+                      oracle_margin_at_disagreements=[round(float(margin[i]), 5) for i in dis[:8]],
+                      max_margin_at_disagreements=round(float(margin[dis].max()), 5) if dis.numel() else 0.0)))
