@@ -11,7 +11,7 @@ from typing import Dict, Iterable, Optional, Sequence, Tuple
 
 import torch
 
-from . import flops, ops, runner
+from . import flops, ops, runner, sharding
 
 
 def _layer_token_totals(model, aux: dict, batch: int) -> Optional[list]:
@@ -101,9 +101,15 @@ def evaluate(model, batches: Iterable[Tuple[torch.Tensor, torch.Tensor]], budget
                             tot = _residual_mask_totals(model, images.shape[0])
                         tok_sum = tot if tok_sum is None else [a + t for a, t in zip(tok_sum, tot)]
                 n_img += images.shape[0]
+            counts = sharding.reduce_counts(counts[0], counts[1])                 # sample-sharded eval: one all-reduce per pass
             correct, total = (int(v) for v in counts.tolist())                    # the pass's only device -> host read
             dt = time.perf_counter() - t0
-            entry = {"accuracy": correct / max(total, 1), "images_per_second": n_img / dt}
+            if sharding.dist.is_available() and sharding.dist.is_initialized() and sharding.dist.get_world_size() > 1:
+                t_max = torch.tensor([dt], dtype=torch.float64, device=dev)        # whole-job rate: all images / slowest rank
+                sharding.dist.all_reduce(t_max, op=sharding.dist.ReduceOp.MAX)
+                dt = float(t_max.item())
+            # ``total`` is the global image count when sharded; token statistics below stay those of this rank's shard
+            entry = {"accuracy": correct / max(total, 1), "images_per_second": total / dt, "images": total}
             if count_flops:
                 tpl = [float(t) / n_img for t in tok_sum] if tok_sum is not None else None
                 entry["gmacs_per_image"] = flops.model_gflops_per_image(model, tpl) / 2.0

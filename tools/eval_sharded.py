@@ -1,0 +1,93 @@
+"""BASELINE.json config 5: A-ViT halting and MoE expert MLPs on the ViT-S shape, batch 1024, sample-sharded data-parallel
+eval over the GPUs of one box through ``peekvit_b200.evaluate.evaluate``.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+        tools/eval_sharded.py [--batch 1024] [--passes 5] [--json gpurun_out/eval_sharded.json]
+
+Every rank builds the same seeded weights, takes its contiguous slice of the same seeded images / labels
+(``sharding.shard_range``) and runs the eval loop; the only collectives are the all-reduce of the [correct, total] counts
+and of the pass time (maximum over ranks) inside ``evaluate``.  Labels are derived from each rank's own unsharded pass over the full batch (correct on even samples, wrong on odd), so the
+sharded count must be exactly half the batch; rank 0 prints one JSON object.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import weights as ow  # noqa: E402  (seeded synthetic weights only; nothing on the timed path)
+from peekvit_b200 import ops, runner, sharding  # noqa: E402
+from peekvit_b200.evaluate import evaluate  # noqa: E402
+from peekvit_b200.models import build_model  # noqa: E402
+
+VITS = dict(image_size=224, patch_size=16, num_layers=12, num_heads=6, hidden_dim=384, mlp_dim=1536, num_classes=1000)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--passes", type=int, default=5)
+    ap.add_argument("--json", default=None)
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    g = torch.Generator().manual_seed(1234)
+    images = torch.randn(B, 3, 224, 224, generator=g)
+    lo, hi = sharding.shard_range(B, rank, world)
+    res = {"world": world, "global_batch": B, "images_per_rank": hi - lo}
+    models = {
+        "avit_s": ("adavit", "adavit", dict(VITS, eps=0.01, gate_scale=1.0, gate_center=1.5)),
+        "moevit_s_4experts": ("vitmoe", "moevit", dict(VITS, mlp_moes=[4] * 12)),
+        "vit_s_16_dense": ("vit", "vit", VITS),
+    }
+    for key, (name, fam, cfg) in models.items():
+        m = build_model(name, cfg)
+        m.load_state_dict(ow.make_state_dict(fam, cfg, seed=4321), strict=True)
+        m = m.to(dev).eval()
+        # labels from this rank's own UNSHARDED pass over the full batch (runner.run has no collectives): the prediction for
+        # even samples, a wrong class for odd ones.  The sharded eval must then count exactly B/2 correct -- on every rank's
+        # shard -- or the sharded forward / count reduction differs from the unsharded one.
+        full = runner.run(m, images.to(dev), None)
+        full = full[-1] if full.dim() == 3 else full
+        pred = full.argmax(1)
+        labels = torch.where(torch.arange(B, device=dev) % 2 == 0, pred, (pred + 1) % 1000)
+        my_images, my_labels = images[lo:hi].to(dev), labels[lo:hi]
+        evaluate(m, [(my_images, my_labels)], count_flops=False)                       # warm-up: graphs, workspaces
+        best = None
+        for _ in range(args.passes):
+            r = evaluate(m, [(my_images, my_labels)], count_flops=False)[None]
+            best = r if best is None or r["images_per_second"] > best["images_per_second"] else best
+        correct = round(best["accuracy"] * best["images"])
+        entry = {"images_per_second": best["images_per_second"], "images": best["images"], "sharded_correct": correct,
+                 "expected_correct": (B + 1) // 2, "counts_agree": correct == (B + 1) // 2}
+        res[key] = entry
+    flag = torch.tensor([ops.device_flag()], device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    res["device_flag"] = int(flag.item())
+    if rank == 0:
+        for k in ("avit_s", "moevit_s_4experts"):
+            res[k]["speedup_vs_dense"] = res[k]["images_per_second"] / res["vit_s_16_dense"]["images_per_second"]
+        print(json.dumps(res), flush=True)
+        if args.json:
+            os.makedirs(os.path.dirname(args.json), exist_ok=True)
+            with open(args.json, "w") as f:
+                json.dump(res, f, indent=1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
