@@ -104,10 +104,7 @@ def evaluate(model, batches: Iterable[Tuple[torch.Tensor, torch.Tensor]], budget
             counts = sharding.reduce_counts(counts[0], counts[1])                 # sample-sharded eval: one all-reduce per pass
             correct, total = (int(v) for v in counts.tolist())                    # the pass's only device -> host read
             dt = time.perf_counter() - t0
-            if sharding.dist.is_available() and sharding.dist.is_initialized() and sharding.dist.get_world_size() > 1:
-                t_max = torch.tensor([dt], dtype=torch.float64, device=dev)        # whole-job rate: all images / slowest rank
-                sharding.dist.all_reduce(t_max, op=sharding.dist.ReduceOp.MAX)
-                dt = float(t_max.item())
+            dt = sharding.max_over_ranks(dt, dev)                                 # whole-job rate: all images / slowest rank
             # ``total`` is the global image count when sharded; token statistics below stay those of this rank's shard
             entry = {"accuracy": correct / max(total, 1), "images_per_second": total / dt, "images": total}
             if count_flops:

@@ -31,6 +31,15 @@ def reduce_counts(correct: torch.Tensor, total: torch.Tensor) -> torch.Tensor:
     return counts
 
 
+def max_over_ranks(value: float, device=None) -> float:
+    """The slowest rank's value (pass times: the whole job is as fast as its slowest shard)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def gather_logits(local_logits: torch.Tensor, total: int) -> torch.Tensor:
     """All ranks' logits in global sample order, [total, C] (ragged shards are padded for the collective)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

@@ -30,6 +30,7 @@ def _worker(rank, world, port, total, n_cls):
         local = logits[b:e]
         counts = sharding.reduce_counts((local.argmax(1) == labels[b:e]).sum(), torch.tensor(e - b))
         assert counts.tolist() == [int((logits.argmax(1) == labels).sum()), total]
+        assert sharding.max_over_ranks(1.0 + rank) == float(world)  # pass time of the slowest rank
         full = sharding.gather_logits(local, total)
         assert torch.equal(full, logits)                           # identical per-sample logits in global order
     finally:
