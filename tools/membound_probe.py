@@ -2,6 +2,9 @@
 config C: ResidualViT-S), against MEASURED_PEAKS.json hbm_gbs.  Algorithmic bytes per unit as in SURVEY.md §8(d)/DESIGN.md §4.
 
     python tools/membound_probe.py [--json gpurun_out/membound.json]
+
+DRAM counters of the same launches: PK_PROBE_ITERS=1 PK_PROBE_WARM=1 under ``ncu --metrics dram__bytes_read.sum,...`` (the L2 flush
+before every timed launch is a torch kernel and is filtered out by ``-k regex:``).
 """
 import json, os, sys
 import torch
@@ -18,7 +21,10 @@ except Exception:
 res = {}
 
 
-def time_us(fn, iters=20, warm=3, flush=None):
+ITERS, WARM = int(os.environ.get("PK_PROBE_ITERS", "20")), int(os.environ.get("PK_PROBE_WARM", "3"))   # 1 / 1 under ncu
+
+
+def time_us(fn, iters=ITERS, warm=WARM, flush=None):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
