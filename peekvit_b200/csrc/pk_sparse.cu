@@ -117,6 +117,50 @@ residual_gate_rows_kernel(const ResidualGateParams p, int batch) {
   }
 }
 
+// Register-resident variant for dim == 128 * MAXV (ViT-S 384, ViT-B 768): ROWS rows per warp iteration with *every* row load issued before the first
+// FMA.  The generic loop above keeps only ROWS float4 per lane in flight per trip and measured 4.1 TB/s on ViT-S rows (ncu,
+// profiles/r01/run27_ncu_membound.csv); same accumulation order, so the gate values are bit-identical.
+template <int MAXV, int ROWS>
+__global__ void __launch_bounds__(256)
+residual_gate_rows_reg_kernel(const ResidualGateParams p, int batch) {
+  const int lane = lane_id(), d4 = p.dim / 4;
+  const int rows = p.cu_in[batch];
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const float4* __restrict__ w4 = reinterpret_cast<const float4*>(p.gate_w);
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(p.x);
+  float4 wv[MAXV];                       // dim == 128 * MAXV exactly (host dispatch): no column predicates
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) wv[j] = __ldg(w4 + lane + 32 * j);
+  for (int r0 = (blockIdx.x * (blockDim.x >> 5) + warp_id()) * ROWS; r0 < rows; r0 += warps_total * ROWS) {
+    float4 xv[ROWS][MAXV];
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) {
+      const float4* row = x4 + static_cast<long long>(min(r0 + u, rows - 1)) * d4 + lane;     // clamped: unconditional loads
+#pragma unroll
+      for (int j = 0; j < MAXV; ++j) xv[u][j] = row[32 * j];
+    }
+    float acc[ROWS];
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) {
+      acc[u] = 0.f;
+#pragma unroll
+      for (int j = 0; j < MAXV; ++j)
+        acc[u] += (xv[u][j].x * wv[j].x + xv[u][j].y * wv[j].y) + (xv[u][j].z * wv[j].z + xv[u][j].w * wv[j].w);
+    }
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) acc[u] = warp_sum(acc[u]);
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) {
+      if (r0 + u >= rows) break;
+      const float logit = acc[u] + p.gate_b;
+      float g;
+      if (p.gate_type == 0) g = sigmoidf_exact(logit * p.inv_temp + p.gate_bias);
+      else g = rintf(sigmoidf_exact(logit));
+      if (lane == 0) p.mask[r0 + u] = g;
+    }
+  }
+}
+
 // Pass 2, one CTA per sample: threshold from the budget token, soft mask, keep decisions, positions in the compacted
 // sample, new length (+1 ghost slot when gated) and the multiplicity folded into the virtual key / ghost row.
 __global__ void __launch_bounds__(256)
@@ -379,57 +423,91 @@ avit_halt_plan_kernel(const AvitParams p) {
 // ------------------------------------------------------------------ MoE routing
 // expert[r] = argmax_e ( LN(x[r]) . Wg[e] + bg[e] ), first maximum wins like torch.argmax
 // (moevit.py:23-32 + blocks.py:23-25).  LN is recomputed in fp32 so routing does not see bf16 rounding.
+// Two rows per warp iteration, both rows' loads issued up front and their reduction chains interleaved: one row at a time,
+// the seven dependent warp reductions per row left the loads of the next row unissued (2.4 TB/s on ViT-S rows, ncu
+// profiles/r01/run27_ncu_membound.csv).  Per-row arithmetic and its order are unchanged, so routing is bit-identical.
 template <int MAXV>
 __global__ void __launch_bounds__(256)
 moe_route_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                  const float* __restrict__ gate_w, const float* __restrict__ gate_b, int n_experts, int rows, int dim,
                  int* __restrict__ expert) {
+  constexpr int R = 2;
   const int lane = lane_id();
   const int d4 = dim / 4;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
-  for (int r = blockIdx.x * (blockDim.x >> 5) + warp_id(); r < rows; r += warps_total) {
-    float4 v[MAXV];
-    float sum = 0.f;
+  for (int r0 = (blockIdx.x * (blockDim.x >> 5) + warp_id()) * R; r0 < rows; r0 += warps_total * R) {
+    float4 v[R][MAXV];
+    float sum[R], mean[R], sq[R], rstd[R];
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c = lane + i * 32;
-      v[i] = c < d4 ? *reinterpret_cast<const float4*>(x + static_cast<long long>(r) * dim + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-    const float mean = warp_sum(sum) / dim;
-    float sq = 0.f;
+    for (int u = 0; u < R; ++u) {
+      const int r = min(r0 + u, rows - 1);
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i)
-      if (lane + i * 32 < d4) {
-        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-        sq += (a * a + b * b) + (c * c + d * d);
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + i * 32;
+        // the column is clamped instead of predicated (unconditional loads issue back to back); the duplicate is zeroed
+        const float4 t = *reinterpret_cast<const float4*>(x + static_cast<long long>(r) * dim + min(c, d4 - 1) * 4);
+        v[u][i] = c < d4 ? t : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-    const float rstd = 1.0f / sqrtf(warp_sum(sq) / dim + eps);
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      sum[u] = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) sum[u] += (v[u][i].x + v[u][i].y) + (v[u][i].z + v[u][i].w);
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) mean[u] = warp_sum(sum[u]) / dim;
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      sq[u] = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i)
+        if (lane + i * 32 < d4) {
+          const float a = v[u][i].x - mean[u], b = v[u][i].y - mean[u], c = v[u][i].z - mean[u], d = v[u][i].w - mean[u];
+          sq[u] += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) rstd[u] = 1.0f / sqrtf(warp_sum(sq[u]) / dim + eps);
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int c = lane + i * 32;
       if (c < d4) {
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c * 4)), be = __ldg(reinterpret_cast<const float4*>(beta + c * 4));
-        v[i].x = fmaf((v[i].x - mean) * rstd, g.x, be.x); v[i].y = fmaf((v[i].y - mean) * rstd, g.y, be.y);
-        v[i].z = fmaf((v[i].z - mean) * rstd, g.z, be.z); v[i].w = fmaf((v[i].w - mean) * rstd, g.w, be.w);
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          v[u][i].x = fmaf((v[u][i].x - mean[u]) * rstd[u], g.x, be.x); v[u][i].y = fmaf((v[u][i].y - mean[u]) * rstd[u], g.y, be.y);
+          v[u][i].z = fmaf((v[u][i].z - mean[u]) * rstd[u], g.z, be.z); v[u][i].w = fmaf((v[u][i].w - mean[u]) * rstd[u], g.w, be.w);
+        }
       }
     }
-    float best = -INFINITY;
-    int best_e = 0;
+    float best[R];
+    int best_e[R];
+#pragma unroll
+    for (int u = 0; u < R; ++u) { best[u] = -INFINITY; best_e[u] = 0; }
     for (int e = 0; e < n_experts; ++e) {
-      float acc = 0.f;
+      float acc[R];
+#pragma unroll
+      for (int u = 0; u < R; ++u) acc[u] = 0.f;
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int c = lane + i * 32;
         if (c < d4) {
           const float4 w = __ldg(reinterpret_cast<const float4*>(gate_w + static_cast<long long>(e) * dim + c * 4));
-          acc += (v[i].x * w.x + v[i].y * w.y) + (v[i].z * w.z + v[i].w * w.w);
+#pragma unroll
+          for (int u = 0; u < R; ++u) acc[u] += (v[u][i].x * w.x + v[u][i].y * w.y) + (v[u][i].z * w.z + v[u][i].w * w.w);
         }
       }
-      acc = warp_sum(acc) + gate_b[e];
-      if (acc > best) { best = acc; best_e = e; }
+      const float gb = gate_b[e];
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        acc[u] = warp_sum(acc[u]) + gb;
+        if (acc[u] > best[u]) { best[u] = acc[u]; best_e[u] = e; }
+      }
     }
-    if (lane == 0) expert[r] = best_e;
+#pragma unroll
+    for (int u = 0; u < R; ++u)
+      if (lane == 0 && r0 + u < rows) expert[r0 + u] = best_e[u];
   }
 }
 
@@ -553,7 +631,10 @@ extern "C" int pk_residual_gate_plan(const pk_residual_gate_args* a, void* strea
   p.mask = a->mask; p.dst_local = a->dst_local; p.sample_of = a->sample_of; p.new_len = a->new_len; p.mdrop = a->mdrop;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (a->gated) {
-    residual_gate_rows_kernel<<<grid_rows(static_cast<long long>(a->batch) * a->max_seq_len), 256, 0, s>>>(p, a->batch);
+    const int grid = grid_rows(static_cast<long long>(a->batch) * a->max_seq_len);
+    if (a->dim == 384) residual_gate_rows_reg_kernel<3, 4><<<grid, 256, 0, s>>>(p, a->batch);
+    else if (a->dim == 768) residual_gate_rows_reg_kernel<6, 2><<<grid, 256, 0, s>>>(p, a->batch);
+    else residual_gate_rows_kernel<<<grid, 256, 0, s>>>(p, a->batch);
     PK_CHECK_CUDA(cudaGetLastError());
   }
   residual_gate_plan_kernel<<<a->batch, 256, static_cast<size_t>(a->max_seq_len), s>>>(p);
