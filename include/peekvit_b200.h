@@ -195,6 +195,9 @@ typedef struct pk_compact_args {
   const float* a1_in; float* a1_out;
   const float* a2_in; float* a2_out;
   int ghost;
+  /* optional, fused pk_residual_publish (same launch): pub_mask[b,i] = scale_in[pub_tok_row[b,i]], then pub_tok_row moves to
+   * the compacted layout.  NULL pub_mask = off; needs scale_in. */
+  int* pub_tok_row; float* pub_mask; int pub_n_img;
 } pk_compact_args;
 int pk_compact_rows(const pk_compact_args* args, void* stream);
 

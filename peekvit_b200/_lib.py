@@ -59,6 +59,7 @@ class CompactArgs(C.Structure):
         ("a1_in", c_void_p), ("a1_out", c_void_p),
         ("a2_in", c_void_p), ("a2_out", c_void_p),
         ("ghost", c_int),
+        ("pub_tok_row", c_void_p), ("pub_mask", c_void_p), ("pub_n_img", c_int),
     ]
 
 

@@ -264,6 +264,7 @@ struct CompactParams {
   const float* a1_in; float* a1_out;
   const float* a2_in; float* a2_out;
   int ghost;                             // ResidualViT: zero-initialise each sample's last output row (a0 = 0, scale = 1)
+  int* pub_tok_row; float* pub_mask; int pub_n_img;   // optional fused publish (see residual_publish_kernel)
 };
 
 // Four input rows per warp iteration: the dependent index chain (dst_local -> sample_of -> cu_out) of all four is resolved
@@ -316,6 +317,17 @@ compact_rows_kernel(const CompactParams p) {
         if (p.a1_out) p.a1_out[d] = p.a1_in[it];
         if (p.a2_out) p.a2_out[d] = p.a2_in[it];
       }
+    }
+  }
+  if (p.pub_mask) {
+    // fused residual_publish_kernel: reads only the plan (scale_in = soft mask, dst_local, cu_out), independent of the row copies
+    const int total = p.batch * p.pub_n_img;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const int b = i / p.pub_n_img;
+      const int r = p.pub_tok_row[i];
+      p.pub_mask[i] = p.scale_in[r];
+      const int dl = p.dst_local[r];
+      p.pub_tok_row[i] = dl >= 0 ? p.cu_out[b] + dl : p.cu_out[b + 1] - 1;
     }
   }
   if (p.ghost) {
@@ -659,6 +671,8 @@ extern "C" int pk_compact_rows(const pk_compact_args* a, void* stream) {
   p.scale_in = a->scale_in; p.scale_out = a->scale_out;
   p.a0_in = a->a0_in; p.a0_out = a->a0_out; p.a1_in = a->a1_in; p.a1_out = a->a1_out; p.a2_in = a->a2_in; p.a2_out = a->a2_out;
   p.ghost = a->ghost;
+  PK_REQUIRE(!a->pub_mask || (a->pub_tok_row && a->scale_in && a->pub_n_img >= 0), "pk_compact_rows: fused publish needs pub_tok_row and scale_in");
+  p.pub_tok_row = a->pub_tok_row; p.pub_mask = a->pub_mask; p.pub_n_img = a->pub_n_img;
   compact_rows_kernel<<<grid_rows(static_cast<long long>(a->rows_in_cap) + a->batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return check_cuda(cudaGetLastError(), "compact_rows_kernel");
 }

@@ -703,11 +703,12 @@ class Forward:
                 cu_out, rows_out, y, mult_out = cus[flip], rdevs[flip], bufs[flip], mults[flip]
                 flip ^= 1
                 ops.exclusive_scan(new_len, cu_out, rows_out)
+                # block.mask (B, N_img, 1) is published by the same launch (the token -> row map moves to the compacted layout)
+                mask_pub = torch.empty(B, n_img, 1, device=dev, dtype=torch.float32) if aux is not None else None
                 ops.compact_rows(x, y, cu, cu_out, B, rows_cap, dst_local, sample_of, scale_in=mask, scale_out=rowscale,
-                                 attrs=[(mult, mult_out)], ghost=True)
+                                 attrs=[(mult, mult_out)], ghost=True,
+                                 publish=(tok_row, mask_pub, n_img) if aux is not None else None)
                 if aux is not None:
-                    mask_pub = torch.empty(B, n_img, 1, device=dev, dtype=torch.float32)
-                    ops.residual_publish(mask, dst_local, cu_out, tok_row, mask_pub, B, n_img)
                     aux.setdefault("masks", {})[i] = mask_pub
                     aux.setdefault("rows", {})[i] = rows_out.clone()
                 x, cu, rows_dev, mult, have_mult = y, cu_out, rows_out, mult_out, True

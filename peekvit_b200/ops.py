@@ -258,8 +258,9 @@ def exclusive_scan(lens: torch.Tensor, cu_out: torch.Tensor, total_out: Optional
 
 
 def compact_rows(x_in, x_out, cu_in, cu_out, batch: int, rows_in_cap: int, dst_local, sample_of, *, scale_in=None, scale_out=None,
-                 attrs=(), ghost: bool = False) -> None:
-    """attrs: up to three (in, out) pairs of per-row fp32 attributes."""
+                 attrs=(), ghost: bool = False, publish=None) -> None:
+    """attrs: up to three (in, out) pairs of per-row fp32 attributes.  publish = (tok_row, mask_pub, n_img): the same launch
+    also does ``residual_publish`` with ``scale_in`` as the soft mask."""
     lib = _lib_for(x_in)
     a = CompactArgs()
     a.x_in, a.x_out, a.dim = _ptr(x_in, torch.float32), _ptr(x_out, torch.float32), x_in.shape[-1]
@@ -272,6 +273,10 @@ def compact_rows(x_in, x_out, cu_in, cu_out, batch: int, rows_in_cap: int, dst_l
     a.a1_in, a.a1_out = _ptr(pairs[1][0], torch.float32), _ptr(pairs[1][1], torch.float32)
     a.a2_in, a.a2_out = _ptr(pairs[2][0], torch.float32), _ptr(pairs[2][1], torch.float32)
     a.ghost = int(ghost)
+    if publish is not None:
+        if scale_in is None:
+            raise ValueError("compact_rows: the fused publish reads the soft mask from scale_in")
+        a.pub_tok_row, a.pub_mask, a.pub_n_img = _ptr(publish[0], torch.int32), _ptr(publish[1], torch.float32), int(publish[2])
     check(lib.pk_compact_rows(C.byref(a), _stream()), "pk_compact_rows")
 
 

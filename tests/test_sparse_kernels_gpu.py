@@ -107,6 +107,41 @@ def test_residual_publish_tracks_tokens(ops):
     assert tok_row.tolist() == [[2, 4, 3, 4, 4], [7, 7, 7, 7, 7]]        # dropped tokens -> ghost row (last of the sample)
 
 
+def test_compact_rows_fused_publish_matches_separate_kernel(ops):
+    """pk_compact_rows with pub_* set = pk_compact_rows + pk_residual_publish (block.mask, utils/utils.py:100-122)."""
+    g = torch.Generator(device=DEV).manual_seed(11)
+    B, n_special, n_img, D = 7, 2, 37, 64
+    seq, cap = n_special + n_img, n_special + n_img + 1
+    rows = B * seq
+    x = torch.randn(B * cap, D, device=DEV, generator=g)
+    cu = torch.arange(B + 1, device=DEV, dtype=torch.int32) * seq
+    mask = torch.rand(B * cap, device=DEV, generator=g)
+    keep = torch.rand(rows, device=DEV, generator=g) > 0.5
+    keep.view(B, seq)[:, :n_special] = True
+    mask[:rows][~keep] = 0.0
+    pos = keep.view(B, seq).int().cumsum(1) - 1
+    dst = torch.where(keep.view(B, seq), pos, torch.full_like(pos, -1)).reshape(-1).to(torch.int32).contiguous()
+    new_len = (keep.view(B, seq).sum(1) + 1).to(torch.int32)             # + ghost slot
+    cu_out = torch.zeros(B + 1, device=DEV, dtype=torch.int32)
+    cu_out[1:] = new_len.cumsum(0)
+    smp = torch.arange(B, device=DEV, dtype=torch.int32).repeat_interleave(seq).contiguous()
+    mult = torch.ones(B * cap, device=DEV)
+    tok0 = (torch.arange(B, device=DEV, dtype=torch.int32)[:, None] * seq + n_special
+            + torch.arange(n_img, device=DEV, dtype=torch.int32)[None, :]).contiguous()
+    outs = []
+    for fused in (False, True):
+        y = torch.full((B * cap, D), 7.0, device=DEV); rs = torch.zeros(B * cap, device=DEV); mo = torch.zeros(B * cap, device=DEV)
+        tok, pub = tok0.clone(), torch.empty(B, n_img, 1, device=DEV)
+        ops.compact_rows(x, y, cu, cu_out, B, B * cap, dst, smp, scale_in=mask, scale_out=rs, attrs=[(mult, mo)], ghost=True,
+                         publish=(tok, pub, n_img) if fused else None)
+        if not fused:
+            ops.residual_publish(mask, dst, cu_out, tok, pub, B, n_img)
+        outs.append((y, rs, mo, tok, pub))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert torch.equal(outs[1][4].view(B, n_img), mask[:rows].view(B, seq)[:, n_special:])
+
+
 @pytest.mark.parametrize("last_layer,early_exit", [(False, True), (False, False), (True, True)])
 def test_avit_halt_plan(ops, last_layer, early_exit):
     """adavit.py:186-210 on packed active rows."""
