@@ -438,7 +438,7 @@ avit_halt_plan_kernel(const AvitParams p) {
 // Two rows per warp iteration, both rows' loads issued up front and their reduction chains interleaved: one row at a time,
 // the seven dependent warp reductions per row left the loads of the next row unissued (2.4 TB/s on ViT-S rows, ncu
 // profiles/r01/run27_ncu_membound.csv).  Per-row arithmetic and its order are unchanged, so routing is bit-identical.
-template <int MAXV>
+template <int MAXV, int NE>
 __global__ void __launch_bounds__(256)
 moe_route_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                  const float* __restrict__ gate_w, const float* __restrict__ gate_b, int n_experts, int rows, int dim,
@@ -497,6 +497,37 @@ moe_route_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
     int best_e[R];
 #pragma unroll
     for (int u = 0; u < R; ++u) { best[u] = -INFINITY; best_e[u] = 0; }
+    if constexpr (NE > 0) {
+      // compile-time expert count: all NE x R dot products first, then their NE x R butterfly reductions interleaved
+      float acc[NE][R];
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+#pragma unroll
+        for (int u = 0; u < R; ++u) acc[e][u] = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+          const int c = lane + i * 32;
+          if (c < d4) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(gate_w + static_cast<long long>(e) * dim + c * 4));
+#pragma unroll
+            for (int u = 0; u < R; ++u) acc[e][u] += (v[u][i].x * w.x + v[u][i].y * w.y) + (v[u][i].z * w.z + v[u][i].w * w.w);
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < NE; ++e)
+#pragma unroll
+        for (int u = 0; u < R; ++u) acc[e][u] = warp_sum(acc[e][u]);
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const float gb = gate_b[e];
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          const float t = acc[e][u] + gb;
+          if (t > best[u]) { best[u] = t; best_e[u] = e; }
+        }
+      }
+    } else {
     for (int e = 0; e < n_experts; ++e) {
       float acc[R];
 #pragma unroll
@@ -516,6 +547,7 @@ moe_route_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
         acc[u] = warp_sum(acc[u]) + gb;
         if (acc[u] > best[u]) { best[u] = acc[u]; best_e[u] = e; }
       }
+    }
     }
 #pragma unroll
     for (int u = 0; u < R; ++u)
@@ -768,8 +800,9 @@ extern "C" int pk_moe_route(const float* x, const float* gamma, const float* bet
   if (rows == 0) return PK_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int maxv = (dim / 4 + 31) / 32;
-  if (maxv <= 3) moe_route_kernel<3><<<grid_rows(rows), 256, 0, s>>>(x, gamma, beta, eps, gate_w, gate_b, n_experts, rows, dim, expert);
-  else moe_route_kernel<8><<<grid_rows(rows), 256, 0, s>>>(x, gamma, beta, eps, gate_w, gate_b, n_experts, rows, dim, expert);
+  if (maxv <= 3 && n_experts == 4) moe_route_kernel<3, 4><<<grid_rows(rows), 256, 0, s>>>(x, gamma, beta, eps, gate_w, gate_b, n_experts, rows, dim, expert);
+  else if (maxv <= 3) moe_route_kernel<3, 0><<<grid_rows(rows), 256, 0, s>>>(x, gamma, beta, eps, gate_w, gate_b, n_experts, rows, dim, expert);
+  else moe_route_kernel<8, 0><<<grid_rows(rows), 256, 0, s>>>(x, gamma, beta, eps, gate_w, gate_b, n_experts, rows, dim, expert);
   PK_CHECK_CUDA(cudaGetLastError());
   int chunk = (rows + kSortBlocks - 1) / kSortBlocks;
   chunk = (chunk + 1023) / 1024 * 1024;
