@@ -25,17 +25,21 @@
 extern "C" {
 #endif
 
-#define PK_ABI_VERSION 1
+#define PK_ABI_VERSION 2
 
 /* ---- runtime ------------------------------------------------------------------------- */
 int pk_abi_version(void);
-/* Bind the calling process to `device`, create the context. Idempotent. */
+/* Create the context of `device` (one per device of the process; idempotent).  Every other entry point works on the
+ * context of the caller's CURRENT CUDA device, which must be the device its pointers live on. */
 int pk_init(int device);
 const char* pk_last_error(void);
 int pk_num_sms(void);
 /* Synchronises the device and returns the watchdog word (0 = healthy; otherwise the code of
  * the bounded mbarrier wait that expired); `reset` != 0 clears it. */
 int pk_device_flag(int reset);
+/* Stream-ordered copy of the watchdog word into pinned host memory (no synchronisation): lets the host notice an expired
+ * wait at its next call without stalling the pipeline. */
+int pk_device_flag_async(unsigned int* host_dst, void* stream);
 
 /* ---- K1/K3/K5/K6/K7: tcgen05 GEMM with fused epilogue ------------------------------- */
 enum pk_epilogue {

@@ -13,6 +13,7 @@ from . import build as _build
 
 c_void_p, c_int, c_float, c_longlong = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
+PK_ABI_VERSION = 2          # include/peekvit_b200.h
 PK_EPI_BIAS_BF16 = 0
 PK_EPI_BIAS_GELU_BF16 = 1
 PK_EPI_BIAS_RESID_F32 = 2
@@ -93,6 +94,7 @@ SIGNATURES: Dict[str, tuple] = {
     "pk_last_error": (C.c_char_p, []),
     "pk_num_sms": (c_int, []),
     "pk_device_flag": (c_int, [c_int]),
+    "pk_device_flag_async": (c_int, [c_void_p, c_void_p]),
     "pk_gemm_bf16": (c_int, [C.POINTER(GemmArgs), c_void_p]),
     "pk_gemm_row_stat_parts": (c_int, [c_int]),
     "pk_row_stats_cast": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -145,15 +147,19 @@ def load() -> C.CDLL:
     if _lib is not None:
         return _lib
     path = os.environ.get("PEEKVIT_B200_LIB") or _build.LIB_PATH      # override: A/B runs of two builds on the same box
-    if path == _build.LIB_PATH and (not os.path.exists(path) or os.environ.get("PEEKVIT_B200_REBUILD") == "1"):
-        path = _build.build(force=True)
+    if path == _build.LIB_PATH:
+        # never run a binary that was built from other sources than the ones in the tree (content hash, not file times)
+        if os.environ.get("PEEKVIT_B200_REBUILD") == "1" or _build.is_stale():
+            if not _build.have_nvcc():
+                raise RuntimeError(f"{path} is missing or was built from different sources and nvcc is not available to rebuild it")
+            path = _build.build(force=True)
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.pk_abi_version() != 1:
-        raise RuntimeError(f"libpeekvit_b200 ABI {lib.pk_abi_version()} != 1; rebuild with `python -m peekvit_b200.build --force`")
+    if lib.pk_abi_version() != PK_ABI_VERSION:
+        raise RuntimeError(f"libpeekvit_b200 ABI {lib.pk_abi_version()} != {PK_ABI_VERSION}; rebuild with `python -m peekvit_b200.build --force`")
     _lib = lib
     return lib
 
@@ -168,14 +174,13 @@ def check(rc: int, what: str = "") -> None:
         raise PkError(f"{what or 'peekvit_b200'} failed (status {rc}): {msg.decode() if msg else ''}")
 
 
-_initialised_device: Optional[int] = None
+_initialised_devices = set()
 
 
 def init(device_index: int) -> C.CDLL:
-    """Create the library context on ``device_index`` (must be a B200 / sm_100a)."""
-    global _initialised_device
+    """Create the library context of ``device_index`` (must be a B200 / sm_100a); one context per device of the process."""
     lib = load()
-    if _initialised_device != device_index:
+    if device_index not in _initialised_devices:
         check(lib.pk_init(device_index), "pk_init")
-        _initialised_device = device_index
+        _initialised_devices.add(device_index)
     return lib

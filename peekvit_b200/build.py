@@ -41,11 +41,34 @@ def _deps():
     return d
 
 
+HASH_PATH = os.path.join(OUT_DIR, "sources.sha256")
+
+
+def source_hash() -> str:
+    """Content hash of every source / header / flag the library is built from.  File times are useless here: the tree is
+    copied to the GPU box as a snapshot, and a stale binary with a changed argument struct would be memory corruption."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for p in sorted(_deps()):
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(p) > t for p in _deps())
+    with open(HASH_PATH) as f:
+        return f.read().strip() != source_hash()
+
+
+def have_nvcc() -> bool:
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -75,6 +98,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    with open(HASH_PATH, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB_PATH
 
 

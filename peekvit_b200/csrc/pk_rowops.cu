@@ -323,17 +323,26 @@ token_norm_score_kernel(const float* __restrict__ x, float* __restrict__ scores,
 // Exact stable descending rank by counting: rank_i = #{j : s_j > s_i or (s_j == s_i and j < i)}.
 // Every token gets a distinct rank, so the first k ranks are the reference's argsort[:k] with
 // ties broken to the lowest index; O(n^2) compares per row out of shared memory (n <= 4096).
+// The compare runs on an integer key that is a TOTAL order: floats in their numeric order (-0 == +0), every NaN equal to
+// every other and above +inf (torch's descending argsort puts NaN first) — with a float compare all NaN scores would get
+// rank 0 and leave slots of `kept` unwritten.
+__device__ __forceinline__ unsigned int score_key(float s) {
+  unsigned int u = __float_as_uint(s);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0xffffffffu;      // NaN
+  if (u == 0x80000000u) u = 0u;                                   // -0 == +0
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 __global__ void __launch_bounds__(256)
 topk_select_kernel(const float* __restrict__ scores, int* __restrict__ kept, int n, int k) {
-  extern __shared__ float s_sc[];
+  extern __shared__ unsigned int s_key[];
   const float* row = scores + (long long)blockIdx.x * n;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) s_sc[i] = row[i];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s_key[i] = score_key(row[i]);
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float si = s_sc[i];
+    const unsigned int si = s_key[i];
     int rank = 0;
     for (int j = 0; j < n; ++j) {
-      const float sj = s_sc[j];
+      const unsigned int sj = s_key[j];
       rank += (sj > si) || (sj == si && j < i);
     }
     if (rank < k) kept[(long long)blockIdx.x * k + rank] = i;

@@ -29,15 +29,33 @@ struct Context {
   unsigned int* flag = nullptr;
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
 };
-static Context g_ctx;
+// One context per device of the process (a model on cuda:1 next to one on cuda:0): every entry point works on the
+// context of the CALLER'S CURRENT device, which the host wrappers set to the device of the tensors they pass.
+constexpr int kMaxDevices = 64;
+static Context g_ctxs[kMaxDevices];
 static std::mutex g_mu;
+
+static Context& cur_ctx() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+  return g_ctxs[d];
+}
+#define g_ctx (cur_ctx())
 
 int num_sms() { return g_ctx.sms > 0 ? g_ctx.sms : 148; }
 unsigned int* device_flag_ptr() { return g_ctx.flag; }
 
 static int init_context(int device) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_ctx.device == device && g_ctx.flag) return PK_OK;
+  if (device < 0 || device >= kMaxDevices) {
+    set_last_error("pk_init: device %d out of range", device);
+    return PK_ERR_INVALID;
+  }
+  Context& c = g_ctxs[device];
+  if (c.device == device && c.flag) return PK_OK;
+  int prev = -1;
+  PK_CHECK_CUDA(cudaGetDevice(&prev));          // the caller's current device is left as it was
+  struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev};
   PK_CHECK_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   PK_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -45,9 +63,9 @@ static int init_context(int device) {
     set_last_error("peekvit_b200 needs an sm_100a device (B200); device %d is sm_%d%d", device, prop.major, prop.minor);
     return PK_ERR_UNSUPPORTED;
   }
-  g_ctx.sms = prop.multiProcessorCount;
-  PK_CHECK_CUDA(cudaMalloc(&g_ctx.flag, sizeof(unsigned int)));
-  PK_CHECK_CUDA(cudaMemset(g_ctx.flag, 0, sizeof(unsigned int)));
+  c.sms = prop.multiProcessorCount;
+  PK_CHECK_CUDA(cudaMalloc(&c.flag, sizeof(unsigned int)));
+  PK_CHECK_CUDA(cudaMemset(c.flag, 0, sizeof(unsigned int)));
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   PK_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -55,8 +73,8 @@ static int init_context(int device) {
     set_last_error("cuTensorMapEncodeTiled not available from the driver");
     return PK_ERR_UNSUPPORTED;
   }
-  g_ctx.encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-  g_ctx.device = device;
+  c.encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  c.device = device;
   return PK_OK;
 }
 
@@ -164,6 +182,16 @@ extern "C" int pk_init(int device) { return pk::init_context(device); }
 extern "C" const char* pk_last_error(void) { return pk::tl_error; }
 
 extern "C" int pk_num_sms(void) { return pk::num_sms(); }
+
+extern "C" int pk_device_flag_async(unsigned int* host_dst, void* stream) {
+  using namespace pk;
+  if (!g_ctx.flag || !host_dst) {
+    set_last_error("pk_device_flag_async: pk_init() has not been called or null destination");
+    return PK_ERR_INVALID;
+  }
+  return check_cuda(cudaMemcpyAsync(host_dst, g_ctx.flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)),
+                    "pk_device_flag_async");
+}
 
 extern "C" int pk_device_flag(int reset) {
   using namespace pk;

@@ -140,26 +140,51 @@ def _block_kind(blk) -> str:
             "ViTBlockMoE": "moe", "NoiseBlock": "noise"}.get(name, name)
 
 
-def apply_noise(blk, x: torch.Tensor, batch: int, seq: int) -> None:
-    """NoiseBlock.forward (reference blocks.py:159-170) on the fp32 token rows x [batch*seq, D], in place.  The random
-    draws are torch's, like the reference (``randn_like`` on the device generator, ``randperm`` on the host generator):
-    Gaussian noise scaled per token to the requested SNR, or the same randomly chosen token positions zeroed in every
-    sample.  ``blk`` is read live, so ``set_value`` between forwards takes effect without repacking."""
-    rows, D = batch * seq, x.shape[-1]
+def draw_noise(pm: "PackedModel", batch: int, device, budgets: Optional[Dict[int, float]] = None) -> Dict[int, tuple]:
+    """The random draws of every NoiseBlock for ONE forward of the whole batch, in layer order, from torch's generators like
+    the reference (``randn_like`` on the device generator, ``randperm`` on the host generator; blocks.py:117-157): the same
+    token positions are dropped in every sample of the batch whatever the micro-batch size, the Gaussian draw is one
+    (B, N, D) tensor, and it is made even at 0 dB (blocks.py:129) so that the generator state stays aligned with the reference."""
+    draws: Dict[int, tuple] = {}
+    seq = pm.seq_len
+    for i, lw in enumerate(pm.layers):
+        if lw.kind == "rank" and budgets is not None:
+            b = budgets.get(i, 1.0)
+            if b != 1:
+                seq = min(max(math.ceil((seq - 1) * b), 0), seq - 1) + 1
+        if lw.kind == "noise":
+            draws[i] = draw_block_noise(lw.module, batch, seq, pm.dim, device)
+    return draws
+
+
+def draw_block_noise(blk, batch: int, seq: int, dim: int, device) -> tuple:
+    """One NoiseBlock's draw for a (batch, seq, dim) input: ("snr", noise or None, dB) / ("drop", token indices or None, 0)."""
     if blk.snr_db is not None:
-        if blk.snr_db == 0:                      # blocks.py:125-127: an SNR of exactly 0 dB means "no noise" there
-            return
-        noise = torch.randn((batch, seq, D), dtype=torch.float32, device=x.device)
-        ops.noise_snr(x, noise.view(rows, D), float(blk.snr_db), rows)
-    elif blk.std is not None:
+        noise = torch.randn((batch, seq, dim), dtype=torch.float32, device=device)
+        return ("snr", noise if blk.snr_db != 0 else None, float(blk.snr_db))
+    if blk.std is not None:
         raise ValueError("std is not supported anymore. Please use snr instead.")
-    else:
-        if blk.prob == 0:
-            return
+    idx = None
+    if blk.prob != 0:
         num_mask = int(blk.prob * seq)           # blocks.py:151 (TypeError for an unset block, like the reference)
-        idx = torch.randperm(seq)[:num_mask]
-        if num_mask > 0:
-            ops.zero_token_rows(x, batch, seq, idx.to(device=x.device, dtype=torch.int32))
+        perm = torch.randperm(seq)[:num_mask]
+        idx = perm.to(device=device, dtype=torch.int32) if num_mask > 0 else None
+    return ("drop", idx, 0.0)
+
+
+def apply_noise(draw: tuple, x: torch.Tensor, batch: int, seq: int, offset: int = 0) -> None:
+    """NoiseBlock.forward (reference blocks.py:159-170) on the fp32 token rows x [batch*seq, D] of the samples
+    [offset, offset + batch) of the forward ``draw`` was made for (``draw_noise``), in place: Gaussian noise scaled per token
+    to the requested SNR, or the same token positions zeroed in every sample."""
+    kind, val, snr_db = draw
+    if val is None:
+        return
+    if kind == "snr":
+        if val.shape[1] != seq:
+            raise RuntimeError(f"NoiseBlock draw was made for {val.shape[1]} tokens per sample, the block sees {seq}")
+        ops.noise_snr(x, val[offset:offset + batch].reshape(batch * seq, x.shape[-1]), snr_db, batch * seq)
+    else:
+        ops.zero_token_rows(x, batch, seq, val)
 
 
 def pack_model(model, family: str) -> PackedModel:
@@ -291,6 +316,9 @@ class Forward:
         self.input_norm = (ops.IMAGENET_MEAN, ops.IMAGENET_STD)      # Normalize statistics of the uint8 input path
         # fp32-accurate mode (runner: model.pk_precision = "fp32"): split-operand GEMMs, fp32 attention (csrc/pk_exact.cu)
         self.exact = False
+        # NoiseBlock draws of the current forward (draw_noise) and the first sample of the micro-batch being run
+        self.noise_draws: Dict[int, tuple] = {}
+        self.sample_offset = 0
 
     def _embed_geometry(self, batch: int):
         """(tokens per sample of the embedded stream, shift rows after the first class token, token-row layout?).
@@ -564,9 +592,9 @@ class Forward:
         rows = B * seq
         if self.exact:
             x = self.embed_exact(images)
-            for lw in pm.layers:
+            for i, lw in enumerate(pm.layers):
                 if lw.kind == "noise":
-                    apply_noise(lw.module, x, B, seq)
+                    apply_noise(self.noise_draws[i], x, B, seq, self.sample_offset)
                 else:
                     self.dense_block_exact(x, lw, rows, B, seq)
             return self.head(x, B, seq)
@@ -577,9 +605,9 @@ class Forward:
             for i, lw in enumerate(pm.layers):
                 self.dense_block_fused(x, lw, rows, B, seq, xb, stats, emit_last=i + 1 < len(pm.layers))
         else:
-            for lw in pm.layers:
+            for i, lw in enumerate(pm.layers):
                 if lw.kind == "noise":
-                    apply_noise(lw.module, x, B, seq)
+                    apply_noise(self.noise_draws[i], x, B, seq, self.sample_offset)
                 else:
                     self.dense_block(x, lw, rows, B, seq)
         return self.head(x, B, seq)
@@ -602,15 +630,18 @@ class Forward:
         L = len(pm.layers)
         for i, lw in enumerate(pm.layers):
             if lw.kind == "noise":
-                apply_noise(lw.module, x, B, seq)
+                apply_noise(self.noise_draws[i], x, B, seq, self.sample_offset)
                 fold = None
                 continue
             b = budgets.get(i, 1.0) if lw.kind == "rank" else 1.0
             if lw.kind == "rank" and b != 1:
                 n = seq - 1
-                k = math.ceil(n * b)
+                # rankvit.py:69-71: idx[:, :ceil(n*b)] -- a budget of 0 keeps the class token alone, a budget above 1 every token
+                k = min(max(math.ceil(n * b), 0), n)
                 scores = ops.token_norm_score(x, B, seq, ws.get(f"rank_scores_{n}", (B, n), torch.float32))
-                kept = ops.topk_select(scores, k, ws.get(f"rank_kept_{n}_{k}", (B, k), torch.int32))
+                kept = ws.get(f"rank_kept_{n}_{k}", (B, k), torch.int32)
+                if k > 0:
+                    ops.topk_select(scores, k, kept)
                 y = ws.get(f"x_compact_{flip}", (B * (k + 1), D), torch.float32)
                 flip ^= 1
                 ops.gather_rows(x, kept, B, seq, y)
@@ -766,8 +797,9 @@ class Forward:
             self.mlp_part(xs[cur], lw, rows_cap, rows_dev=rows_dev)
             if aux is not None:
                 aux.setdefault("rows", []).append(rows_dev.clone())
-            ops.avit_halt_plan(xs[cur], cu, B, seq, cs[cur], Rs[cur], toks[cur], gate_scale=lw.extra["gate_scale"],
-                               gate_center=lw.extra["gate_center"], eps=ex["eps"], last_layer=(i == L - 1), early_exit=early_exit,
+            # the halting gate's scale / centre are plain attributes of the live block (adavit.py:32-33): read per forward
+            ops.avit_halt_plan(xs[cur], cu, B, seq, cs[cur], Rs[cur], toks[cur], gate_scale=float(lw.module.gate_scale),
+                               gate_center=float(lw.module.gate_center), eps=ex["eps"], last_layer=(i == L - 1), early_exit=early_exit,
                                out_acc=out_acc, rho=rho, counter=counter, dst_local=dst_local, sample_of=sample_of,
                                new_len=new_len, n_halted=n_halted)
             if i == L - 1:
@@ -791,7 +823,7 @@ class Forward:
         x = self.embed_exact(images) if self.exact else self.embed(images)
         for i, lw in enumerate(pm.layers):
             if lw.kind == "noise":
-                apply_noise(lw.module, x, B, seq)
+                apply_noise(self.noise_draws[i], x, B, seq, self.sample_offset)
                 continue
             EA = len(lw.attn)
             if EA == 1:

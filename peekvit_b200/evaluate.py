@@ -104,6 +104,8 @@ def evaluate(model, batches: Iterable[Tuple[torch.Tensor, torch.Tensor]], budget
             counts = sharding.reduce_counts(counts[0], counts[1])                 # sample-sharded eval: one all-reduce per pass
             correct, total = (int(v) for v in counts.tolist())                    # the pass's only device -> host read
             dt = time.perf_counter() - t0
+            with torch.cuda.device(dev):
+                ops.raise_if_flagged(dev.index, sync=True)                        # the read above synchronised: the watchdog word is final
             dt = sharding.max_over_ranks(dt, dev)                                 # whole-job rate: all images / slowest rank
             # ``total`` is the global image count when sharded; token statistics below stay those of this rank's shard
             entry = {"accuracy": correct / max(total, 1), "images_per_second": total / dt, "images": total}

@@ -79,7 +79,7 @@ class NoiseBlock(nn.Module):
         torch._assert(x.dim() == 3, f"Expected (batch_size, seq_length, hidden_dim) got {x.shape}")
         B, N, D = x.shape
         y = x.detach().to(torch.float32).contiguous().clone().view(B * N, D)
-        engine.apply_noise(self, y, B, N)
+        engine.apply_noise(engine.draw_block_noise(self, B, N, D, x.device), y, B, N)
         return y.view(B, N, D)
 
     def set_snr(self, snr: float):

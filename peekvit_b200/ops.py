@@ -28,7 +28,13 @@ def _lib_for(t: torch.Tensor):
     launch_count += 1
     if not t.is_cuda:
         raise RuntimeError("peekvit_b200 kernels need CUDA tensors on a B200; there is no CPU path")
-    return _lib.init(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    cur = torch.cuda.current_device()
+    idx = t.device.index if t.device.index is not None else cur
+    if idx != cur:
+        # the library works on the context and the stream of the CURRENT device (runner.run / run_host enter
+        # torch.cuda.device(model device) themselves); launching on another device's stream would be an illegal access
+        raise RuntimeError(f"tensor on cuda:{idx} but the current device is cuda:{cur}: wrap the call in torch.cuda.device({idx})")
+    return _lib.init(idx)
 
 
 def _stream() -> int:
@@ -344,8 +350,43 @@ def moe_route(x, gamma, beta, eps: float, gate_w, gate_b, rows: int, expert, off
 
 
 def device_flag(reset: bool = True) -> int:
-    """Watchdog word of the tcgen05 kernels (0 = healthy). Synchronises the device."""
-    return _lib.load().pk_device_flag(int(reset))
+    """Watchdog word of the tcgen05 kernels (0 = healthy) of the current device. Synchronises the device."""
+    return _lib.init(torch.cuda.current_device()).pk_device_flag(int(reset))
+
+
+_flag_mirrors = {}
+
+
+def device_flag_mirror(device_index: int) -> torch.Tensor:
+    """Pinned host word that ``device_flag_async`` refreshes in stream order (one per device)."""
+    m = _flag_mirrors.get(device_index)
+    if m is None:
+        m = _flag_mirrors[device_index] = torch.zeros(1, dtype=torch.int32, pin_memory=True)
+    return m
+
+
+def device_flag_async(device_index: int) -> None:
+    """Enqueue a copy of the watchdog word into its pinned host mirror on the current stream (no synchronisation)."""
+    lib = _lib.init(device_index)
+    check(lib.pk_device_flag_async(device_flag_mirror(device_index).data_ptr(), _stream()), "pk_device_flag_async")
+
+
+def raise_if_flagged(device_index: int, sync: bool = False) -> None:
+    """An expired bounded mbarrier wait makes the tcgen05 kernels bail out and leaves partial outputs: tell the caller.
+    ``sync`` reads the device word itself (after a synchronisation the caller has done anyway); otherwise the host mirror,
+    i.e. the state as of the last completed forward."""
+    if sync:
+        code = device_flag(reset=True)
+        device_flag_mirror(device_index).zero_()
+    else:
+        m = device_flag_mirror(device_index)
+        code = int(m[0])
+        if code != 0:
+            device_flag(reset=True)
+            m.zero_()
+    if code != 0:
+        raise _lib.PkError(f"peekvit_b200 watchdog: a bounded wait expired inside a tcgen05 kernel (code {code & 0xffffffff:#x}); "
+                           "the outputs produced since the previous check are invalid")
 
 
 def scatter_add_rows(x: torch.Tensor, y: torch.Tensor, src_of: torch.Tensor, rows: Optional[int] = None) -> torch.Tensor:

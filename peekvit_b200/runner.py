@@ -18,14 +18,15 @@ DEFAULT_MICRO_BATCH = int(os.environ.get("PEEKVIT_B200_MICRO_BATCH", "512"))
 # reference's shipped dtype: 3-way split operands on the same tcgen05 GEMMs + fp32 attention, logits within 1e-5, every family).
 # Per model: ``model.pk_precision = "fp32"``.
 DEFAULT_PRECISION = os.environ.get("PEEKVIT_B200_PRECISION", "bf16")
+PRECISIONS = ("bf16", "fp32")
 # the split activation rows are 6x wider: the fp32 mode runs in smaller micro-batches (workspace 15 MB per image at ViT-B/16)
 EXACT_MICRO_BATCH = int(os.environ.get("PEEKVIT_B200_EXACT_MICRO_BATCH", "256"))
 
 
 def _exact(model) -> bool:
     p = getattr(model, "pk_precision", DEFAULT_PRECISION)
-    if p not in ("bf16", "fp32"):
-        raise ValueError(f"pk_precision must be 'bf16' or 'fp32', got {p!r}")
+    if p not in PRECISIONS:
+        raise ValueError(f"pk_precision must be one of {PRECISIONS}, got {p!r}")
     return p == "fp32"
 
 
@@ -163,7 +164,8 @@ def _forward_chunk(model, fwd: engine.Forward, chunk: torch.Tensor, aux: Optiona
         fn, key = (lambda c, a: fwd.residualvit(c, b, a)), b
     elif family == "adavit":
         ee = bool(getattr(model, "pk_early_exit", True))
-        fn, key = (lambda c, a: fwd.adavit(c, a, early_exit=ee)), ee
+        gates = tuple((float(b.gate_scale), float(b.gate_center)) for b in model.encoder.layers if hasattr(b, "gate_center"))
+        fn, key = (lambda c, a: fwd.adavit(c, a, early_exit=ee)), (ee, gates)
     elif family == "moevit":
         fn, key = (lambda c, a: fwd.moevit(c, a)), None
     else:
@@ -226,7 +228,11 @@ def run(model, x: torch.Tensor, aux: Optional[dict] = None) -> torch.Tensor:
         raise RuntimeError(f"input is on {x.device} but the model is on {dev}")
     _check_images(model, x)
     x = x.detach().contiguous() if x.dtype == torch.uint8 else x.detach().to(torch.float32).contiguous()
-    with torch.no_grad():
+    from . import ops
+    capturing = torch.cuda.is_current_stream_capturing()
+    with torch.no_grad(), torch.cuda.device(dev):
+        if not capturing:
+            ops.raise_if_flagged(dev.index)        # watchdog state as of the last completed forward (no synchronisation)
         fwd = engine.Forward(packed(model), workspace(model, dev))
         fwd.input_norm = getattr(model, "pk_input_norm", fwd.input_norm)
         fwd.exact = _exact(model)
@@ -237,8 +243,12 @@ def run(model, x: torch.Tensor, aux: Optional[dict] = None) -> torch.Tensor:
                           dtype=torch.float32, device=dev)
         merged: dict = {}
         want_state = model._family in ("residualvit", "eeresidualvit", "adavit", "moevit") or aux is not None
+        if any(lw.kind == "noise" for lw in fwd.pm.layers):
+            # one draw per NoiseBlock for the whole batch, before it is cut into micro-batches (blocks.py:117-157)
+            fwd.noise_draws = engine.draw_noise(fwd.pm, B, dev, _rank_budgets(model) if model._family == "rankvit" else None)
         for s in range(0, B, mb):
             chunk = x[s:s + mb]
+            fwd.sample_offset = s
             part = {} if want_state else None
             res = _forward_chunk(model, fwd, chunk, part)
             (out[:, s:s + chunk.shape[0]] if multi else out[s:s + chunk.shape[0]]).copy_(res)
@@ -251,6 +261,8 @@ def run(model, x: torch.Tensor, aux: Optional[dict] = None) -> torch.Tensor:
                     aux[k] = {kk: vv[0] for kk, vv in v.items()} if isinstance(v, dict) else v[0]
             else:
                 aux.update(merged)
+        if not capturing:
+            ops.device_flag_async(dev.index)
     return out
 
 
@@ -270,7 +282,8 @@ def run_host(model, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = Non
     elif x_host.dtype != torch.float32 or not x_host.is_contiguous():
         x_host = x_host.to(torch.float32).contiguous()
     B, S = x_host.shape[0], model.image_size
-    with torch.no_grad():
+    from . import ops
+    with torch.no_grad(), torch.cuda.device(dev):
         ws = workspace(model, dev)
         fwd = engine.Forward(packed(model), ws)
         fwd.input_norm = getattr(model, "pk_input_norm", fwd.input_norm)
@@ -292,16 +305,22 @@ def run_host(model, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = Non
             free[i].record(cur)
         # Chunk schedule: the first copy cannot overlap any compute, so the batch starts with a quarter
         # micro-batch (then the rest of that micro-batch) before settling on full micro-batches.
+        # A batch that fits one micro-batch (256 images per GPU when BASELINE's 2048-image batch is split over 8 GPUs) is cut
+        # the same way, or nothing of its copy would be hidden.
         sizes = []
-        if B > mb and mb >= 64:
-            sizes += [mb // 4, mb - mb // 4]
+        first = min(mb, B)
+        if first >= 128:
+            sizes += [first // 4, first - first // 4]
         left = B - sum(sizes)
         while left > 0:
             sizes.append(min(mb, left))
             left -= sizes[-1]
+        if any(lw.kind == "noise" for lw in fwd.pm.layers):
+            fwd.noise_draws = engine.draw_noise(fwd.pm, B, dev, _rank_budgets(model) if model._family == "rankvit" else None)
         s = 0
         for i, n in enumerate(sizes):
             slot = i & 1
+            fwd.sample_offset = s
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(free[slot])
                 bufs[slot][:n].copy_(x_host[s:s + n], non_blocking=True)
@@ -314,4 +333,5 @@ def run_host(model, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = Non
             out_host = torch.empty(B, model.num_classes, dtype=torch.float32, pin_memory=True)
         out_host.copy_(out, non_blocking=True)
         cur.synchronize()
+        ops.raise_if_flagged(dev.index, sync=True)
     return out_host
