@@ -92,7 +92,19 @@ typedef struct pk_gemm_args {
   const float* ln_c1;    /* f32 [N] */
   int ln_parts, ln_dim;
   float ln_eps;
+  /* Two-term split operands (the "bf16x2" arithmetic mode: x = hi + lo, both bf16, 16 significant bits).  The product
+   * A*W^T ~ lo*Wh + hi*Wl + hi*Wh runs as ONE bf16 GEMM over K = 3k (small terms first, see pk_split2_bf16): the weight row
+   * is [Wh | Wl | Wh] (3k wide) and the activation row is stored ONCE as [lo | hi] (2k wide) -- with a_wrap_k = k the
+   * kernel reads A column c - k for every K index c >= 2k.  CTA-pair kernel only.  0 = off (A is K wide). */
+  int a_wrap_k;
+  /* Output format of the two 2-byte epilogues (PK_EPI_BIAS_BF16 / PK_EPI_BIAS_GELU_BF16), CTA-pair kernel only:
+   * PK_OUT_BF16 (default); PK_OUT_F16 = IEEE half (the fp16 attention operands of the bf16x2 mode);
+   * PK_OUT_BF16X2 = the value split into hi + lo (both bf16) and written as [lo | hi]: `out` is [*, 2N], lo at
+   * column n, hi at column N + n (N % 64 == 0) -- the A operand of the next split GEMM without an extra pass. */
+  int out_format;
 } pk_gemm_args;
+
+enum pk_out_format { PK_OUT_BF16 = 0, PK_OUT_F16 = 1, PK_OUT_BF16X2 = 2 };
 
 int pk_gemm_bf16(const pk_gemm_args* args, void* stream);
 /* Number of statistics slots per row the LayerNorm-producer epilogue writes for an N-column output. */
@@ -148,6 +160,10 @@ typedef struct pk_attention_args {
   const float* extra_mult;  /* f32 [batch] or NULL (<= 0 disables the virtual key for that sample) */
   int impl;                 /* 0 = auto (tcgen05/TMEM kernel for uniform 64 < seq_len <= 256, head_dim 64, no
                                multiplicities; general mma.sync kernel otherwise), 1 = general kernel, 2 = tcgen05 kernel */
+  /* bf16x2 arithmetic mode (tcgen05 kernel only, impl 0 / 2 on an eligible shape): qkv_format PK_OUT_F16 = q, k, v are IEEE
+   * half (11 significant bits; the probabilities are packed as half too); out_format PK_OUT_BF16X2 = `out` is
+   * [rows, 2*D] holding the fp32 result split into lo (column d) and hi (column D + d), both bf16. */
+  int qkv_format, out_format;
 } pk_attention_args;
 
 int pk_attention_fwd(const pk_attention_args* args, void* stream);
@@ -283,6 +299,14 @@ int pk_split3_bf16(const float* x, void* out, int rows, int dim, int mode, const
                    const int* rows_dev /* optional device-side row count */, void* stream);
 /* im2col of f32 NCHW images into split activation rows: patches6 bf16 [B*(S/p)^2, 6*3*p*p] (vit.py:203-222, fp32 mode). */
 int pk_patchify_split3(const float* images, void* patches6, int batch, int image_size, int patch_size, void* stream);
+/* Two-term variants of pk_split3_bf16 / pk_patchify_split3 (bf16x2 mode): x = hi + lo.  pk_split2_bf16 writes the
+ * activation row [lo | hi] (2*dim wide; read by pk_gemm_bf16 with a_wrap_k = dim); the matching weight row is
+ * [Wh | Wl | Wh].  pk_patchify_split2 writes [lo | hi | hi] (3*Kp wide: the patch GEMM's row remap runs on the
+ * single-CTA kernel, which has no a_wrap_k). */
+int pk_split2_bf16(const float* x, void* out, int rows, int dim, int mode, const float* gamma, const float* beta, float eps,
+                   const float* rowscale, const int* row_index, const int* rows_dev, void* stream);
+int pk_patchify_split2(const float* images, void* patches3, int batch, int image_size, int patch_size, void* stream);
+
 /* fp32 attention core on the CUDA cores: qkv f32 [rows, 3*H*dh] (q|k|v) -> out f32 [rows, H*dh], dh 32, 48 or 64 (blocks.py:93-95,
  * fp32 mode).  Uniform samples of seq_len rows, or ragged ones (cu_seqlens int32 [B+1]; seq_len = longest sample); optional
  * per-key multiplicities and one virtual key per sample, with the meaning they have in pk_attention_args. */

@@ -350,11 +350,14 @@ def _moe_route(x: Tensor, sd, prefix: str) -> Tensor:
     return F.one_hot(scores.argmax(dim=-1), num_classes=scores.shape[-1]).to(dt)
 
 
-def moevit_forward(sd, cfg, images: Tensor) -> Tuple[Tensor, Dict]:
+def moevit_forward(sd, cfg, images: Tensor, forced_mlp_expert: Optional[Dict[int, Tensor]] = None) -> Tuple[Tensor, Dict]:
     """``VisionTransformerMoE.forward`` (reference moevit.py:295-312; readout ``x[:, 0]``) with
     ``ViTBlockMoE`` (:131-141), ``MLPMoE.forward_moe`` (:49-61) and ``AttentionMoE`` (:71-102):
     every expert is evaluated densely and combined with the one-hot gate; a single expert
-    bypasses the gate (:45-47,:64-67)."""
+    bypasses the gate (:45-47,:64-67).  ``forced_mlp_expert`` (test hook, like ``forced_kept`` of the RankViT forward)
+    substitutes given expert indices (B, N) for the arg-max routing of the listed layers, to compare logits *given
+    identical routing*: arg-max is discontinuous, a bf16-level perturbation of a near-tied router score moves a token
+    to another expert."""
     L, H = cfg["num_layers"], cfg["num_heads"]
     mlp_moes = cfg.get("mlp_moes") or [1] * L
     attn_moes = cfg.get("attn_moes") or [1] * L
@@ -380,6 +383,8 @@ def moevit_forward(sd, cfg, images: Tensor) -> Tuple[Tensor, Dict]:
             y = mlp(m_in, sd, lp + ".mlp.experts.0")
         else:
             gp = _moe_route(m_in, sd, lp + ".mlp.gating_network")
+            if forced_mlp_expert is not None and i in forced_mlp_expert:
+                gp = F.one_hot(forced_mlp_expert[i].to(torch.int64), num_classes=mlp_moes[i]).to(dt)
             aux["mlp_gating"][i] = gp
             outs = torch.stack([mlp(m_in, sd, lp + f".mlp.experts.{e}") for e in range(mlp_moes[i])], dim=0)
             y = torch.einsum("ebsd,bse->bsd", outs, gp)

@@ -18,6 +18,7 @@ PK_EPI_BIAS_BF16 = 0
 PK_EPI_BIAS_GELU_BF16 = 1
 PK_EPI_BIAS_RESID_F32 = 2
 PK_EPI_BIAS_F32 = 3
+PK_OUT_BF16, PK_OUT_F16, PK_OUT_BF16X2 = 0, 1, 2
 
 
 class GemmArgs(C.Structure):
@@ -35,6 +36,7 @@ class GemmArgs(C.Structure):
         ("epilogue_mode", c_int), ("cta_pair", c_int),
         ("xb_out", c_void_p), ("ldxb", c_longlong), ("row_stats", c_void_p),
         ("ln_stats", c_void_p), ("ln_c1", c_void_p), ("ln_parts", c_int), ("ln_dim", c_int), ("ln_eps", c_float),
+        ("a_wrap_k", c_int), ("out_format", c_int),
     ]
 
 
@@ -45,7 +47,7 @@ class AttentionArgs(C.Structure):
         ("seq_len", c_int), ("cu_seqlens", c_void_p), ("max_seq_len", c_int),
         ("scale", c_float),
         ("key_mult", c_void_p), ("extra_kv", c_void_p), ("extra_mult", c_void_p),
-        ("impl", c_int),
+        ("impl", c_int), ("qkv_format", c_int), ("out_format", c_int),
     ]
 
 
@@ -121,6 +123,8 @@ SIGNATURES: Dict[str, tuple] = {
     "pk_expert_onehot": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "pk_split3_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pk_patchify_split3": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "pk_split2_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pk_patchify_split2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pk_attention_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pk_noise_snr": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "pk_zero_token_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),

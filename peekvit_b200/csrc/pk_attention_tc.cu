@@ -36,15 +36,18 @@ constexpr int kTcMaxKeys = 256;
 // Shared-memory rings.  Q (both tiles) and K of an item are dead as soon as both S = Q K^T are done, V only after
 // both PV: the Q/K ring (2 slots) is released right after the QK MMAs, V has its own, deeper ring, so the ~2 us TMA
 // latency of the next items' operands is off the critical path of the two staggered regions.
-template <int NPAD>
+// SPLIT_OUT (bf16x2 mode): the output leaves as two bf16 tiles (hi and lo) per 32-row block, so the staging area doubles and the
+// V ring drops to two slots to make room.
+template <int NPAD, int SPLIT_OUT = 0>
 struct TcSmem {
   static constexpr int kKBytes = NPAD * 128;                          // NPAD keys x 64 bf16 (multiple of 1024 since NPAD % 16 == 0 -> 2048)
   static constexpr int kQKSlotBytes = 2 * kTcQTileBytes + kKBytes;
   static constexpr int kQKSlots = 2;
-  static constexpr int kVSlots = NPAD <= 224 ? 3 : 2;
+  static constexpr int kVSlots = (NPAD <= 224 && !SPLIT_OUT) ? 3 : 2;
   static constexpr int kVOff = kQKSlots * kQKSlotBytes;
   static constexpr int kStageOff = kVOff + kVSlots * kKBytes;
-  static constexpr int kBytes = kStageOff + 4 * 4096 /* output staging */ + 1024 /* inv_sum */ + 256 /* barriers */ + 1024 /* alignment */;
+  static constexpr int kStageBytes = (1 + SPLIT_OUT) * 4 * 4096;      // one (or two) 32-row x 128-byte tiles per output warp
+  static constexpr int kBytes = kStageOff + kStageBytes + 1024 /* inv_sum */ + 256 /* barriers */ + 1024 /* alignment */;
   static_assert(kBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 };
 constexpr int kTcBarBytes = 256;
@@ -174,7 +177,7 @@ __device__ __forceinline__ void exp2_poly_x2(uint64_t x, float& r0, float& r1) {
 
 // One 16-column group of the S row -> 8 packed bf16x2 probabilities; returns the partial row sum.
 // POLY of every 4 column pairs take the FMA-pipe exp2, the rest the MUFU.
-template <bool MASK, int POLY>
+template <bool MASK, int POLY, int F16 = 0>
 __device__ __forceinline__ float softmax_group16(const uint32_t* s, uint32_t* p, float scale_log2, float neg_max_scaled, int col0, int n) {
   if constexpr (MASK) {
     float sum0 = 0.f, sum1 = 0.f;
@@ -186,7 +189,7 @@ __device__ __forceinline__ float softmax_group16(const uint32_t* s, uint32_t* p,
       if (col0 + e + 1 >= n) p1 = 0.f;
       sum0 += p0;
       sum1 += p1;
-      p[e >> 1] = pack_bf16(p0, p1);
+      p[e >> 1] = F16 ? pack_f16(p0, p1) : pack_bf16(p0, p1);
     }
     return sum0 + sum1;
   } else {
@@ -205,7 +208,7 @@ __device__ __forceinline__ float softmax_group16(const uint32_t* s, uint32_t* p,
         p1 = ex2_approx(x1);
       }
       acc = f2_add(acc, f2_pack(p0, p1));
-      p[i] = pack_bf16(p0, p1);
+      p[i] = F16 ? pack_f16(p0, p1) : pack_bf16(p0, p1);
     }
     float a0, a1;
     f2_unpack(acc, a0, a1);
@@ -556,10 +559,10 @@ constexpr int kTc3RegsOther = 40;                  // TMA producer, idle warp
 constexpr int kTc3RegsMma = 56;
 constexpr int kTc3RegsOut = 88;                    // both 32-column halves of the O row in flight
 constexpr int kTc3OCol = 192;
-template <int NPAD>
+template <int NPAD, int SPLIT_OUT = 0>
 struct Tc3Smem {
-  using B = TcSmem<NPAD>;
-  static constexpr int kPartOff = B::kStageOff + kTcOutStageBytes;            // row-max and row-sum partials: [2][region][half][128] f32
+  using B = TcSmem<NPAD, SPLIT_OUT>;
+  static constexpr int kPartOff = B::kStageOff + B::kStageBytes;              // row-max and row-sum partials: [2][region][half][128] f32
   static constexpr int kBarOff = kPartOff + 4096;
   static constexpr int kBytes = kBarOff + 256 /* barriers */ + 1024 /* alignment */;
   static_assert(kBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
@@ -576,7 +579,7 @@ __device__ __forceinline__ void tc3_trace(const TcAttParams& p, int it, int ev) 
 }
 
 // Softmax of one item for the column groups of one half of the row.
-template <int NPAD, int HALF, int POLY>
+template <int NPAD, int HALF, int POLY, int F16>
 __device__ __forceinline__ void tc3_softmax_item(uint32_t t_base, int n, float scale_log2, float* mx_mine, const float* mx_other,
                                                  float* sum_mine, int bar_id, const TcAttParams& p, int it) {
   const int debug = p.debug;
@@ -626,8 +629,8 @@ __device__ __forceinline__ void tc3_softmax_item(uint32_t t_base, int n, float s
       uint32_t (&nxt)[16] = (j & 1) ? ha : hb;
       if (j + 1 < GN) tmem_ld_32x32_x16(s_col + static_cast<uint32_t>(16 * (j + 1)), nxt);
       uint32_t pk[8];
-      if (HALF == 1 && j == GN - 1) sum += softmax_group16<true, POLY>(cur, pk, scale_log2, neg_max_scaled, 16 * (GB + j), n);
-      else sum += softmax_group16<false, POLY>(cur, pk, scale_log2, neg_max_scaled, 0, n);
+      if (HALF == 1 && j == GN - 1) sum += softmax_group16<true, POLY, F16>(cur, pk, scale_log2, neg_max_scaled, 16 * (GB + j), n);
+      else sum += softmax_group16<false, POLY, F16>(cur, pk, scale_log2, neg_max_scaled, 0, n);
       if (j + 1 < GN) tmem_ld_wait();
       tmem_st_32x32_x8(t_base + static_cast<uint32_t>(PCOL0 + 8 * j), pk);   // lands on S group GB + j/2: already in registers
     }
@@ -638,14 +641,17 @@ __device__ __forceinline__ void tc3_softmax_item(uint32_t t_base, int n, float s
   tmem_st_wait();
 }
 
-template <int NPAD, int POLY = 0>
+// FMT 0: bf16 q / k / v / probabilities, bf16 output [rows, D].  FMT 1 (bf16x2 arithmetic mode): IEEE-half q / k / v and
+// probabilities (11 significant bits, same tensor-core rate), output split into hi + lo (both bf16) as [lo | hi] in a
+// [rows, 2D] buffer: the A operand of the split out-projection GEMM.
+template <int NPAD, int POLY = 0, int FMT = 0>
 __global__ void __launch_bounds__(kTc3Threads, 1)
 attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_constant__ CUtensorMap tmap_kv,
                      const __grid_constant__ CUtensorMap tmap_out, const TcAttParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  using SM = TcSmem<NPAD>;
-  using SM3 = Tc3Smem<NPAD>;
+  using SM = TcSmem<NPAD, FMT>;
+  using SM3 = Tc3Smem<NPAD, FMT>;
   uint8_t* out_stage = smem + SM::kStageOff;
   float* mx_part = reinterpret_cast<float*>(smem + SM3::kPartOff);                 // [region][half][128]
   float* sum_part = mx_part + 512;                                                  // [region][half][128]
@@ -731,8 +737,8 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
     // ------------------------------------------------------------------ MMA issuers: warp 1 -> query tile 0, warp 2 -> tile 1
     setmaxnreg_dec<kTc3RegsMma>();
     const int r = warp - 1;
-    constexpr uint32_t idesc_qk = umma_idesc_bf16(128, NPAD);
-    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, kTcDH, /*b_mn_major=*/1);
+    constexpr uint32_t idesc_qk = FMT ? umma_idesc_f16(128, NPAD) : umma_idesc_bf16(128, NPAD);
+    constexpr uint32_t idesc_pv = FMT ? umma_idesc_f16(128, kTcDH, /*b_mn_major=*/1) : umma_idesc_bf16(128, kTcDH, /*b_mn_major=*/1);
     const uint32_t s_tmem = tmem_base + static_cast<uint32_t>(r * kTcRegionCols);
     int qs = 0, vs = 0;
     uint32_t qph = 0, vph = 0, rph = 0;
@@ -804,8 +810,8 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
       tcgen05_fence_after();
       tc3_trace(p, it, 1);
       if (warp_has_rows) {
-        if (half == 0) tc3_softmax_item<NPAD, 0, POLY>(t_base, n, scale_log2, mx_mine, mx_other, sum_mine, bar_id, p, it);
-        else tc3_softmax_item<NPAD, 1, POLY>(t_base, n, scale_log2, mx_mine, mx_other, sum_mine, bar_id, p, it);
+        if (half == 0) tc3_softmax_item<NPAD, 0, POLY, FMT>(t_base, n, scale_log2, mx_mine, mx_other, sum_mine, bar_id, p, it);
+        else tc3_softmax_item<NPAD, 1, POLY, FMT>(t_base, n, scale_log2, mx_mine, mx_other, sum_mine, bar_id, p, it);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -820,7 +826,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
     // ------------------------------------------------------------------ output warps (one per TMEM lane quarter, both regions)
     setmaxnreg_inc<kTc3RegsOut>();
     const int q = warp & 3;
-    uint8_t* stg = out_stage + q * 4096;
+    uint8_t* stg = out_stage + q * (FMT ? 8192 : 4096);          // FMT 1: hi tile, then lo tile
     uint32_t rph = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int it = (item - blockIdx.x) / gridDim.x;
@@ -848,25 +854,44 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
         if (has_rows && !(p.debug & 4)) {
           if (lane == 0) bulk_wait_read<0>();                     // the previous store has drained this staging tile
           __syncwarp();
+          if constexpr (FMT == 0) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
-                make_uint4(pack_bf16(__uint_as_float(o0[8 * c]) * inv, __uint_as_float(o0[8 * c + 1]) * inv),
-                           pack_bf16(__uint_as_float(o0[8 * c + 2]) * inv, __uint_as_float(o0[8 * c + 3]) * inv),
-                           pack_bf16(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv),
-                           pack_bf16(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv));
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                  make_uint4(pack_bf16(__uint_as_float(o0[8 * c]) * inv, __uint_as_float(o0[8 * c + 1]) * inv),
+                             pack_bf16(__uint_as_float(o0[8 * c + 2]) * inv, __uint_as_float(o0[8 * c + 3]) * inv),
+                             pack_bf16(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv),
+                             pack_bf16(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv));
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + c) ^ (lane & 7)) << 4)) =
-                make_uint4(pack_bf16(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv),
-                           pack_bf16(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv),
-                           pack_bf16(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv),
-                           pack_bf16(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv));
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + c) ^ (lane & 7)) << 4)) =
+                  make_uint4(pack_bf16(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv),
+                             pack_bf16(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv),
+                             pack_bf16(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv),
+                             pack_bf16(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv));
+          } else {
+            // hi / lo split of the scaled fp32 row: 16-byte chunk c of the hi tile and of the lo tile (4 KB further)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint32_t* src = c < 4 ? &o0[8 * c] : &o[8 * (c - 4)];
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                split2_pack(__uint_as_float(src[2 * e]) * inv, __uint_as_float(src[2 * e + 1]) * inv, hi[e], lo[e]);
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(stg + 4096 + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
           tc3_trace(p, it, r * 3 + 1);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&tmap_out, smem_u32(stg), h * kTcDH, row0, b);
+            if constexpr (FMT == 0) {
+              tma_store_3d(&tmap_out, smem_u32(stg), h * kTcDH, row0, b);
+            } else {
+              tma_store_3d(&tmap_out, smem_u32(stg), D + h * kTcDH, row0, b);        // hi plane
+              tma_store_3d(&tmap_out, smem_u32(stg) + 4096, h * kTcDH, row0, b);     // lo plane
+            }
             bulk_commit();
           }
         }
@@ -874,6 +899,426 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
       }
       if (!ok) break;
       rph ^= 1u;
+    }
+    if (lane == 0) bulk_wait_read<0>();       // smem must outlive the last store's reads
+  }
+
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ======================================================================================================================
+// Ragged variant ("tcr"): the tcgen05/TMEM attention for packed rows of unequal sample lengths (cu_seqlens), per-key
+// multiplicities and the virtual bias key -- what the compacted ResidualViT / A-ViT rows need (call sites
+// reference models/residualvit.py:252-256, adavit.py:53-80 via blocks.py:93-95) -- and for short uniform sequences.
+//
+// One work unit = one 128-query tile of one (sample, head); units whose tile starts past the end of their sample are skipped by
+// every role alike.  The k-th PROCESSED unit of a CTA runs in TMEM region k & 1, so the two regions always hold two different
+// units (with samples of ~80 rows a second query tile never exists: tying both regions to one (sample, head) like the dense
+// kernel would idle half the softmax warps).  Per unit the producer TMA-loads the Q tile and the sample's K / V rows through 2-D
+// maps over the packed [rows, 3D] buffer: rows past the end of the sample belong to the next sample (or are zero-filled past
+// the end of the buffer); they are neutralised by the per-key bias row below, never by the tensor map.
+//   * key count per unit is a run-time value: n_keys = len (+1 virtual key), padded to 16 for the MMA's N and the loop bounds;
+//   * warp 3 ("patch" warp) writes the virtual key (k-bias | v-bias of the head, what a zeroed token projects to) into row
+//     `len` of the K and V tiles after the TMA has landed, and builds the unit's bias row  lm[j] = log2(mult_j)  (0 for a
+//     plain key, log2(M_drop) for the virtual key, -inf for padding): multiplicities and masking are one FFMA in the softmax;
+//   * softmax as in tc3 (two warps per TMEM lane quarter split the S row by 16-column groups), on x = s*scale*log2e + lm;
+//   * output: full 32-row blocks leave through one 2-D TMA store, the block that straddles the end of the sample is written
+//     row by row from registers (rows past the end belong to the next sample).
+constexpr int kTcrThreads = 768;
+template <int NMAX>
+struct TcrSmem {
+  static constexpr int kKBytes = NMAX * 128;
+  static constexpr int kQKSlotBytes = kTcQTileBytes + kKBytes;            // one Q tile + K rows
+  static constexpr int kQKSlots = 2;                                       // slot == region (units alternate regions)
+  static constexpr int kVSlots = 3;
+  static constexpr int kVOff = kQKSlots * kQKSlotBytes;
+  static constexpr int kStageOff = kVOff + kVSlots * kKBytes;
+  static constexpr int kLmOff = kStageOff + 4 * 4096;                      // bias rows: 4 x NMAX f32 (unit k uses row k & 3)
+  static constexpr int kPartOff = kLmOff + 4 * 256 * 4;                    // row-max / row-sum partials: [2][region][half][128] f32
+  static constexpr int kBarOff = kPartOff + 4096;
+  static constexpr int kBytes = kBarOff + 512 + 1024;
+  static_assert(NMAX % 16 == 0 && NMAX <= 256, "key tile");
+  static_assert(kBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
+};
+
+struct TcrParams {
+  const int* cu_seqlens;       // [batch + 1] or nullptr (uniform seq_len)
+  const float* key_mult;       // [rows] or nullptr
+  const __nv_bfloat16* extra_kv;   // [2D] or nullptr
+  const float* extra_mult;     // [batch] or nullptr
+  __nv_bfloat16* out;          // [rows, D]
+  int batch, num_heads, seq_len, q_tiles;   // q_tiles = 128-row tiles per sample the grid is sized for
+  int box_small;               // key rows of the small K / V box (the full box is NMAX)
+  float scale_log2;
+  unsigned int* flag;
+};
+
+struct TcrUnit {
+  int b, h, qt, row0, len, n_keys, npad;
+  float extra;                 // multiplicity of the virtual key (0: none)
+};
+__device__ __forceinline__ bool tcr_unit(const TcrParams& p, int u, TcrUnit& t) {
+  const int item = u / p.q_tiles;
+  t.qt = u - item * p.q_tiles;
+  t.b = item / p.num_heads;
+  t.h = item - t.b * p.num_heads;
+  if (p.cu_seqlens) {
+    t.row0 = p.cu_seqlens[t.b];
+    t.len = p.cu_seqlens[t.b + 1] - t.row0;
+  } else {
+    t.row0 = t.b * p.seq_len;
+    t.len = p.seq_len;
+  }
+  if (t.qt * 128 >= t.len) return false;
+  t.extra = (p.extra_kv && p.extra_mult) ? p.extra_mult[t.b] : 0.f;
+  if (!(t.extra > 0.f)) t.extra = 0.f;
+  t.n_keys = t.len + (t.extra > 0.f ? 1 : 0);
+  t.npad = (t.n_keys + 15) & ~15;
+  return true;
+}
+
+template <int NMAX>
+__global__ void __launch_bounds__(kTcrThreads, 1)
+attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv_small,
+                     const __grid_constant__ CUtensorMap tmap_kv_full, const __grid_constant__ CUtensorMap tmap_out, const TcrParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using SM = TcrSmem<NMAX>;
+  uint8_t* out_stage = smem + SM::kStageOff;
+  float* lm_rows = reinterpret_cast<float*>(smem + SM::kLmOff);                   // [4][256]
+  float* mx_part = reinterpret_cast<float*>(smem + SM::kPartOff);                 // [region][half][128]
+  float* sum_part = mx_part + 512;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kBarOff);
+  uint64_t* qk_full = bars;            // [2] TMA landed
+  uint64_t* qk_ready = bars + 2;       // [2] virtual key + bias row written (patch warp)
+  uint64_t* qk_empty = bars + 4;       // [2] QK MMA retired
+  uint64_t* v_full = bars + 6;         // [3]
+  uint64_t* v_ready = bars + 9;        // [3]
+  uint64_t* v_empty = bars + 12;       // [3] PV MMA retired
+  uint64_t* s_full = bars + 15;        // [2] region: S ready
+  uint64_t* p_ready = bars + 17;       // [2] region: P written (8 softmax-warp arrivals)
+  uint64_t* o_full = bars + 19;        // [2] region: O ready
+  uint64_t* s_free = bars + 21;        // [2] region: O read out (4 output-warp arrivals)
+  uint64_t* sum_ready = bars + 23;     // [2] region: row-sum partials published (8 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+
+  const int warp = warp_id();
+  const int lane = lane_id();
+  const int D = p.num_heads * kTcDH;
+  const int num_units = p.batch * p.num_heads * p.q_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_kv_small);
+    tma_prefetch_desc(&tmap_kv_full);
+    tma_prefetch_desc(&tmap_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(smem_u32(&v_full[i]), 1);
+      mbar_init(smem_u32(&v_ready[i]), 1);
+      mbar_init(smem_u32(&v_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&qk_full[i]), 1);
+      mbar_init(smem_u32(&qk_ready[i]), 1);
+      mbar_init(smem_u32(&qk_empty[i]), 1);
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&p_ready[i]), 8);
+      mbar_init(smem_u32(&o_full[i]), 1);
+      mbar_init(smem_u32(&s_free[i]), 4);
+      mbar_init(smem_u32(&sum_ready[i]), 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Every role walks the same unit sequence; k counts the units actually processed: region = QK slot = k & 1 (phase (k >> 1) & 1),
+  // V slot = k % 3 (phase (k / 3) & 1), bias row = k & 3.
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    setmaxnreg_dec<kTc3RegsOther>();
+    int k = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      TcrUnit t;
+      if (!tcr_unit(p, u, t)) continue;
+      const int qs = k & 1, vs = k % 3;
+      const uint32_t qph = (k >> 1) & 1u, vph = (k / 3) & 1u;
+      const bool small = t.npad <= p.box_small;
+      const uint32_t kv_bytes = static_cast<uint32_t>(small ? p.box_small : NMAX) * 128u;
+      const CUtensorMap* kvmap = small ? &tmap_kv_small : &tmap_kv_full;
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&qk_empty[qs]), qph ^ 1u, p.flag, 0x3100u + qs))) break;
+      if (elect_one()) {
+        const uint32_t bar = smem_u32(&qk_full[qs]);
+        const uint32_t base = smem_u32(smem + qs * SM::kQKSlotBytes);
+        mbar_expect_tx(bar, kTcQTileBytes + kv_bytes);
+        tma_load_2d(base, &tmap_q, bar, t.h * kTcDH, t.row0 + t.qt * 128);
+        tma_load_2d(base + kTcQTileBytes, kvmap, bar, D + t.h * kTcDH, t.row0);
+      }
+      __syncwarp();
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&v_empty[vs]), vph ^ 1u, p.flag, 0x3110u + vs))) break;
+      if (elect_one()) {
+        const uint32_t bar = smem_u32(&v_full[vs]);
+        mbar_expect_tx(bar, kv_bytes);
+        tma_load_2d(smem_u32(smem + SM::kVOff + vs * SM::kKBytes), kvmap, bar, 2 * D + t.h * kTcDH, t.row0);
+      }
+      __syncwarp();
+      ++k;
+    }
+  } else if (warp == 1 || warp == 2) {
+    // ------------------------------------------------------------------ MMA issuers: warp 1 -> region 0 (even units), warp 2 -> region 1
+    setmaxnreg_dec<kTc3RegsMma>();
+    const int r = warp - 1;
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, kTcDH, /*b_mn_major=*/1);
+    const uint32_t s_tmem = tmem_base + static_cast<uint32_t>(r * kTcRegionCols);
+    int k = 0;
+    bool first = true;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      TcrUnit t;
+      if (!tcr_unit(p, u, t)) continue;
+      const int kk = k++;
+      if ((kk & 1) != r) continue;
+      const int qs = r, vs = kk % 3;
+      const uint32_t qph = (kk >> 1) & 1u, vph = (kk / 3) & 1u, rph = qph;
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&qk_ready[qs]), qph, p.flag, 0x3200u + qs))) break;
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&s_free[r]), rph ^ 1u, p.flag, 0x3300u + r))) break;
+      if (first && r == 1) {      // start half a period after region 0: the two softmax groups then use the MUFU alternately
+        if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&p_ready[0]), 0u, p.flag, 0x3310u))) break;
+      }
+      first = false;
+      tcgen05_fence_after();
+      const uint32_t base = smem_u32(smem + qs * SM::kQKSlotBytes);
+      const uint32_t idesc_qk = umma_idesc_bf16(128, t.npad);
+      if (elect_one()) {                       // S = Q K^T over the unit's padded key count
+        const uint64_t a_desc = umma_desc_kmajor_sw128(base);
+        const uint64_t b_desc = umma_desc_kmajor_sw128(base + kTcQTileBytes);
+#pragma unroll
+        for (int ks = 0; ks < kTcDH / 16; ++ks)
+          umma_bf16(s_tmem, a_desc + static_cast<uint64_t>(2 * ks), b_desc + static_cast<uint64_t>(2 * ks), idesc_qk, ks != 0 ? 1u : 0u);
+        umma_commit(smem_u32(&s_full[r]));
+        umma_commit(smem_u32(&qk_empty[qs]));
+      }
+      __syncwarp();
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&p_ready[r]), rph, p.flag, 0x3400u + r))) break;
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&v_ready[vs]), vph, p.flag, 0x3410u + vs))) break;
+      tcgen05_fence_after();
+      const int G = t.npad >> 4, G0 = (G + 1) >> 1;
+      if (elect_one()) {                       // O = P V; P of key group g sits where the half that owns it packed it
+        const uint64_t v_desc = umma_desc_mnmajor_sw128(smem_u32(smem + SM::kVOff + vs * SM::kKBytes));
+        const uint32_t o_tmem = s_tmem + kTc3OCol;
+        for (int g = 0; g < G; ++g) {
+          const uint32_t p_col = g < G0 ? static_cast<uint32_t>(8 * g) : static_cast<uint32_t>(16 * G0 + 8 * (g - G0));
+          umma_bf16_ts(o_tmem, s_tmem + p_col, v_desc + static_cast<uint64_t>(128 * g), idesc_pv, g != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&o_full[r]));
+        umma_commit(smem_u32(&v_empty[vs]));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ patch warp: virtual key rows + bias row of every unit
+    setmaxnreg_dec<kTc3RegsOther>();
+    int k = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      TcrUnit t;
+      if (!tcr_unit(p, u, t)) continue;
+      const int qs = k & 1, vs = k % 3;
+      const uint32_t qph = (k >> 1) & 1u, vph = (k / 3) & 1u;
+      float* lm = lm_rows + (k & 3) * 256;
+      // bias row (its previous user, unit k - 4, finished its softmax before this unit's Q/K slot could even be refilled)
+      for (int j = lane; j < NMAX; j += 32) {
+        float v = -INFINITY;
+        if (j < t.len) v = p.key_mult ? __log2f(p.key_mult[t.row0 + j]) : 0.f;
+        else if (j == t.len && t.extra > 0.f) v = __log2f(t.extra);
+        lm[j] = v;
+      }
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&qk_full[qs]), qph, p.flag, 0x3800u + qs))) break;
+      if (t.extra > 0.f && lane < 8) {
+        // K row `len`: 16-byte chunk c of row j lives at chunk c ^ (j & 7) of its 128-byte line (SWIZZLE_128B)
+        const uint4 kb = *reinterpret_cast<const uint4*>(p.extra_kv + t.h * kTcDH + lane * 8);
+        *reinterpret_cast<uint4*>(smem + qs * SM::kQKSlotBytes + kTcQTileBytes + t.len * 128 + ((lane ^ (t.len & 7)) << 4)) = kb;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&qk_ready[qs]));
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&v_full[vs]), vph, p.flag, 0x3810u + vs))) break;
+      if (t.extra > 0.f && lane < 8) {
+        const uint4 vb = *reinterpret_cast<const uint4*>(p.extra_kv + D + t.h * kTcDH + lane * 8);
+        *reinterpret_cast<uint4*>(smem + SM::kVOff + vs * SM::kKBytes + t.len * 128 + ((lane ^ (t.len & 7)) << 4)) = vb;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&v_ready[vs]));
+      ++k;
+    }
+  } else if (warp < 20) {
+    // ------------------------------------------------------------------ softmax warps: 8 per region = 4 lane quarters x 2 column halves
+    setmaxnreg_inc<kTc3RegsSoftmax>();
+    const int r = (warp - 4) >> 3;
+    const int half = ((warp - 4) >> 2) & 1;
+    const int q = warp & 3;
+    const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(r * kTcRegionCols);
+    float* mx_mine = mx_part + (r * 2 + half) * 128 + q * 32 + lane;
+    const float* mx_other = mx_part + (r * 2 + (half ^ 1)) * 128 + q * 32 + lane;
+    float* sum_mine = sum_part + (r * 2 + half) * 128 + q * 32 + lane;
+    const int bar_id = 1 + r * 4 + q;
+    const float scale_log2 = p.scale_log2;
+    int k = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      TcrUnit t;
+      if (!tcr_unit(p, u, t)) continue;
+      const int kk = k++;
+      if ((kk & 1) != r) continue;
+      const uint32_t rph = (kk >> 1) & 1u;
+      const float* lm = lm_rows + (kk & 3) * 256;
+      if (!mbar_wait(smem_u32(&s_full[r]), rph, p.flag, 0x3500u + r)) break;
+      tcgen05_fence_after();
+      const bool warp_has_rows = t.qt * 128 + q * 32 < t.len;           // warp-uniform, same for both halves of a quarter
+      if (warp_has_rows) {
+        const int G = t.npad >> 4, G0 = (G + 1) >> 1;
+        const int gb = half ? G0 : 0, gn = half ? G - G0 : G0;          // this half's 16-column groups
+        const uint32_t pcol0 = half ? static_cast<uint32_t>(16 * G0) : 0u;
+        const uint64_t sc2 = f2_pack(scale_log2, scale_log2);
+        uint32_t ha[16], hb[16];
+        // ---- pass 1: partial row maximum of x = s * scale * log2e + lm (padding columns carry lm = -inf)
+        float mx = -INFINITY;
+        if (gn > 0) {
+          tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(16 * gb), ha);
+          tmem_ld_wait();
+        }
+        for (int j = 0; j < gn; ++j) {
+          uint32_t (&cur)[16] = (j & 1) ? hb : ha;
+          uint32_t (&nxt)[16] = (j & 1) ? ha : hb;
+          if (j + 1 < gn) tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(16 * (gb + j + 1)), nxt);
+          const float4* l4 = reinterpret_cast<const float4*>(lm + 16 * (gb + j));
+          float xs[16];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float4 l = l4[e];
+            float a0, a1, a2, a3;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(cur[4 * e]), __uint_as_float(cur[4 * e + 1])), sc2, f2_pack(l.x, l.y)), a0, a1);
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(cur[4 * e + 2]), __uint_as_float(cur[4 * e + 3])), sc2, f2_pack(l.z, l.w)), a2, a3);
+            xs[4 * e] = a0; xs[4 * e + 1] = a1; xs[4 * e + 2] = a2; xs[4 * e + 3] = a3;
+          }
+          const float m0 = fmax3(xs[0], xs[1], xs[2]), m1 = fmax3(xs[3], xs[4], xs[5]);
+          const float m2 = fmax3(xs[6], xs[7], xs[8]), m3 = fmax3(xs[9], xs[10], xs[11]);
+          mx = fmax3(mx, fmax3(fmax3(m0, xs[12], xs[13]), fmax3(m1, xs[14], xs[15]), m2), m3);
+          if (j + 1 < gn) tmem_ld_wait();
+        }
+        *mx_mine = mx;
+        named_bar_sync(bar_id, 64);
+        mx = fmaxf(mx, *mx_other);
+        const uint64_t nm2 = f2_pack(-mx, -mx);
+        // ---- pass 2: p = exp2(x - max), partial row sum, bf16 P packed over this half's own consumed S columns
+        float sum = 0.f;
+        if (gn > 0) {
+          tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(16 * gb), ha);
+          tmem_ld_wait();
+        }
+        for (int j = 0; j < gn; ++j) {
+          uint32_t (&cur)[16] = (j & 1) ? hb : ha;
+          uint32_t (&nxt)[16] = (j & 1) ? ha : hb;
+          if (j + 1 < gn) tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(16 * (gb + j + 1)), nxt);
+          const float4* l4 = reinterpret_cast<const float4*>(lm + 16 * (gb + j));
+          uint32_t pk[8];
+          uint64_t acc = f2_pack(0.f, 0.f);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float4 l = l4[e];
+            float x0, x1, x2, x3;
+            f2_unpack(f2_add(f2_fma(f2_pack(__uint_as_float(cur[4 * e]), __uint_as_float(cur[4 * e + 1])), sc2, f2_pack(l.x, l.y)), nm2), x0, x1);
+            f2_unpack(f2_add(f2_fma(f2_pack(__uint_as_float(cur[4 * e + 2]), __uint_as_float(cur[4 * e + 3])), sc2, f2_pack(l.z, l.w)), nm2), x2, x3);
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2), p3 = ex2_approx(x3);
+            acc = f2_add(acc, f2_add(f2_pack(p0, p1), f2_pack(p2, p3)));
+            pk[2 * e] = pack_bf16(p0, p1);
+            pk[2 * e + 1] = pack_bf16(p2, p3);
+          }
+          float a0, a1;
+          f2_unpack(acc, a0, a1);
+          sum += a0 + a1;
+          if (j + 1 < gn) tmem_ld_wait();        // the next group is in registers before its columns may be overwritten
+          tmem_st_32x32_x8(t_base + pcol0 + static_cast<uint32_t>(8 * j), pk);
+        }
+        *sum_mine = sum;
+        tmem_st_wait();
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&p_ready[r]));
+        mbar_arrive(smem_u32(&sum_ready[r]));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ output warps (one per TMEM lane quarter, both regions)
+    setmaxnreg_inc<kTc3RegsOut>();
+    const int q = warp & 3;
+    uint8_t* stg = out_stage + q * 4096;
+    int k = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      TcrUnit t;
+      if (!tcr_unit(p, u, t)) continue;
+      const int kk = k++;
+      const int r = kk & 1;
+      const uint32_t rph = (kk >> 1) & 1u;
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(r * kTcRegionCols);
+      if (!mbar_wait(smem_u32(&sum_ready[r]), rph, p.flag, 0x3700u + r)) break;
+      if (!mbar_wait(smem_u32(&o_full[r]), rph, p.flag, 0x3600u + r)) break;
+      tcgen05_fence_after();
+      const int lrow0 = t.qt * 128 + q * 32;               // first row of this warp's block inside the sample
+      const bool has_rows = lrow0 < t.len;                 // warp-uniform
+      const bool full = lrow0 + 32 <= t.len;
+      uint32_t o0[32], o[32];
+      float inv = 0.f;
+      if (has_rows) {
+        inv = 1.0f / (sum_part[(r * 2 + 0) * 128 + q * 32 + lane] + sum_part[(r * 2 + 1) * 128 + q * 32 + lane]);
+        tmem_ld_32x32(t_base + kTc3OCol, o0);
+        tmem_ld_32x32(t_base + kTc3OCol + 32, o);
+        tmem_ld_wait();
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_free[r]));     // the region may take its next unit's S
+      if (!has_rows) continue;
+      uint4 c8[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t* src = c < 4 ? &o0[8 * c] : &o[8 * (c - 4)];
+        c8[c] = make_uint4(pack_bf16(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv),
+                           pack_bf16(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv),
+                           pack_bf16(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv),
+                           pack_bf16(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv));
+      }
+      if (full) {
+        if (lane == 0) bulk_wait_read<0>();                 // the previous store has drained this staging tile
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) = c8[c];
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmap_out, smem_u32(stg), t.h * kTcDH, t.row0 + lrow0);
+          bulk_commit();
+        }
+      } else if (lrow0 + lane < t.len) {
+        // the block that straddles the end of the sample: the rows after it are the next sample's
+        uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<long long>(t.row0 + lrow0 + lane) * D + t.h * kTcDH);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) dst[c] = c8[c];
+      }
     }
     if (lane == 0) bulk_wait_read<0>();       // smem must outlive the last store's reads
   }
@@ -914,6 +1359,13 @@ bool attention_tc_eligible(const pk_attention_args* a) {
   if (a->impl == 1) return false;
   if (a->cu_seqlens || a->key_mult || a->extra_kv || a->extra_mult) return false;
   if (a->head_dim != kTcDH) return false;
+  const bool x2 = a->qkv_format == PK_OUT_F16 || a->out_format == PK_OUT_BF16X2;
+  if (x2) {
+    // the bf16x2 variant takes half operands AND writes the split output (one kernel variant), on the column-split kernel
+    if (a->qkv_format != PK_OUT_F16 || a->out_format != PK_OUT_BF16X2) return false;
+    if (a->seq_len < 17 || a->seq_len > 224) return false;           // two staging tiles per output warp: n_pad <= 224
+    return (reinterpret_cast<uintptr_t>(a->qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0;
+  }
   // n <= 128 runs with the second query tile empty (its region only keeps the barrier protocol alive); PK_ATT_TC_MIN_SEQ
   // (default 65: measured 92 vs 138 us at n = 99, but 68 vs 54 us at n = 50, B = 512, H = 12) is the shortest sequence routed here
   static int min_seq = -1;
@@ -935,8 +1387,9 @@ int launch_attention_tc(const pk_attention_args* a, cudaStream_t stream) {
                          static_cast<uint32_t>(n_pad));
   if (rc != PK_OK) return rc;
   CUtensorMap tout;
-  rc = make_tmap_bf16_3d(&tout, a->out, static_cast<uint64_t>(D), static_cast<uint64_t>(n), static_cast<uint64_t>(a->batch),
-                         static_cast<uint64_t>(D), 32);
+  const bool x2 = a->out_format == PK_OUT_BF16X2;
+  rc = make_tmap_bf16_3d(&tout, a->out, static_cast<uint64_t>(x2 ? 2 * D : D), static_cast<uint64_t>(n), static_cast<uint64_t>(a->batch),
+                         static_cast<uint64_t>(x2 ? 2 * D : D), 32);
   if (rc != PK_OK) return rc;
   TcAttParams p;
   p.out = static_cast<__nv_bfloat16*>(a->out);
@@ -960,6 +1413,27 @@ int launch_attention_tc(const pk_attention_args* a, cudaStream_t stream) {
   if (split < 0) { const char* e = getenv("PK_ATT_TC_SPLIT"); split = e ? atoi(e) : 1; }
   static int poly = -1;        // experiment: PK_ATT_TC_POLY=1|2 of every 4 column pairs take the FMA-pipe exp2 (n_pad 208 only)
   if (poly < 0) { const char* e = getenv("PK_ATT_TC_POLY"); poly = e ? atoi(e) : 0; }
+  if (x2) {
+    switch (n_pad) {
+#define PK_TC3X_CASE(NP)                                                                                                \
+  case NP: {                                                                                                            \
+    static bool attr_set = false;                                                                                       \
+    if (!attr_set) {                                                                                                    \
+      PK_CHECK_CUDA(cudaFuncSetAttribute(attention_tc3_kernel<NP, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc3Smem<NP, 1>::kBytes)); \
+      attr_set = true;                                                                                                  \
+    }                                                                                                                   \
+    attention_tc3_kernel<NP, 0, 1><<<grid, kTc3Threads, Tc3Smem<NP, 1>::kBytes, stream>>>(tq, tkv, tout, p);              \
+    break;                                                                                                              \
+  }
+      PK_TC3X_CASE(32) PK_TC3X_CASE(48) PK_TC3X_CASE(64) PK_TC3X_CASE(80) PK_TC3X_CASE(96) PK_TC3X_CASE(112) PK_TC3X_CASE(128)
+      PK_TC3X_CASE(144) PK_TC3X_CASE(160) PK_TC3X_CASE(176) PK_TC3X_CASE(192) PK_TC3X_CASE(208) PK_TC3X_CASE(224)
+#undef PK_TC3X_CASE
+      default:
+        set_last_error("pk_attention_fwd: unsupported padded length %d for the half-operand variant", n_pad);
+        return PK_ERR_INVALID;
+    }
+    return check_cuda(cudaGetLastError(), "attention_tc3_kernel<half> launch");
+  }
   if (split && n_pad == 208 && (poly == 1 || poly == 2)) {
     static bool attr_set = false;
     if (!attr_set) {

@@ -28,26 +28,43 @@ __device__ __forceinline__ uint2 pack4(__nv_bfloat16 a, __nv_bfloat16 b, __nv_bf
                     static_cast<uint32_t>(__bfloat16_as_ushort(c)) | (static_cast<uint32_t>(__bfloat16_as_ushort(d)) << 16));
 }
 
-// four consecutive fp32 values of one row -> the six K-wide segments of the split operand row (activation order)
+// four consecutive fp32 values of one row -> the K-wide segments of the split operand row (activation order).
+// LAYOUT 6: three terms, [m | l | h | m | h | h] (fp32-accurate mode); LAYOUT 2: two terms, [lo | hi] (bf16x2 mode, read
+// with a_wrap_k); LAYOUT 3: two terms, [lo | hi | hi] (bf16x2 patch operand, no wrap).
+template <int LAYOUT>
 __device__ __forceinline__ void store_split4(__nv_bfloat16* orow, int K, int k, float4 v) {
-  __nv_bfloat16 h[4], m[4], l[4];
-  split3(v.x, h[0], m[0], l[0]);
-  split3(v.y, h[1], m[1], l[1]);
-  split3(v.z, h[2], m[2], l[2]);
-  split3(v.w, h[3], m[3], l[3]);
-  const uint2 ph = pack4(h[0], h[1], h[2], h[3]), pm = pack4(m[0], m[1], m[2], m[3]), pl = pack4(l[0], l[1], l[2], l[3]);
-  *reinterpret_cast<uint2*>(orow + 0 * K + k) = pm;
-  *reinterpret_cast<uint2*>(orow + 1 * K + k) = pl;
-  *reinterpret_cast<uint2*>(orow + 2 * K + k) = ph;
-  *reinterpret_cast<uint2*>(orow + 3 * K + k) = pm;
-  *reinterpret_cast<uint2*>(orow + 4 * K + k) = ph;
-  *reinterpret_cast<uint2*>(orow + 5 * K + k) = ph;
+  if constexpr (LAYOUT == 6) {
+    __nv_bfloat16 h[4], m[4], l[4];
+    split3(v.x, h[0], m[0], l[0]);
+    split3(v.y, h[1], m[1], l[1]);
+    split3(v.z, h[2], m[2], l[2]);
+    split3(v.w, h[3], m[3], l[3]);
+    const uint2 ph = pack4(h[0], h[1], h[2], h[3]), pm = pack4(m[0], m[1], m[2], m[3]), pl = pack4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint2*>(orow + 0 * K + k) = pm;
+    *reinterpret_cast<uint2*>(orow + 1 * K + k) = pl;
+    *reinterpret_cast<uint2*>(orow + 2 * K + k) = ph;
+    *reinterpret_cast<uint2*>(orow + 3 * K + k) = pm;
+    *reinterpret_cast<uint2*>(orow + 4 * K + k) = ph;
+    *reinterpret_cast<uint2*>(orow + 5 * K + k) = ph;
+  } else {
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      h[i] = __float2bfloat16_rn(x[i]);
+      l[i] = __float2bfloat16_rn(x[i] - __bfloat162float(h[i]));
+    }
+    const uint2 ph = pack4(h[0], h[1], h[2], h[3]), pl = pack4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint2*>(orow + 0 * K + k) = pl;
+    *reinterpret_cast<uint2*>(orow + 1 * K + k) = ph;
+    if constexpr (LAYOUT == 3) *reinterpret_cast<uint2*>(orow + 2 * K + k) = ph;
+  }
 }
 
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 // MODE 0: split only; MODE 1: exact (erf) GELU first (reference blocks.py:82)
-template <int MODE>
+template <int MODE, int LAYOUT>
 __global__ void split3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int K,
                               const float* __restrict__ rowscale, const int* __restrict__ rows_dev) {
   const int k4 = K / 4;
@@ -60,12 +77,12 @@ __global__ void split3_kernel(const float* __restrict__ x, __nv_bfloat16* __rest
     float4 v = *reinterpret_cast<const float4*>(x + r * K + k);
     if (MODE == 1) { v.x = gelu_exact(v.x); v.y = gelu_exact(v.y); v.z = gelu_exact(v.z); v.w = gelu_exact(v.w); }
     if (rowscale) { const float sc = rowscale[r]; v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; }
-    store_split4(out + r * 6ll * K, K, k, v);
+    store_split4<LAYOUT>(out + r * static_cast<long long>(LAYOUT) * K, K, k, v);
   }
 }
 
 // LayerNorm (two-pass fp32 statistics, biased variance: nn.LayerNorm) then split.  One warp per row, the row in registers.
-template <int MAXV>
+template <int MAXV, int LAYOUT>
 __global__ void __launch_bounds__(256)
 split3_layernorm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, const float* __restrict__ gamma,
                         const float* __restrict__ beta, float eps, int rows, int K, const float* __restrict__ rowscale,
@@ -99,7 +116,7 @@ split3_layernorm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__
       }
     }
     const float rstd = 1.0f / sqrtf(warp_sum(sq) / static_cast<float>(K) + eps);
-    __nv_bfloat16* orow = out + static_cast<long long>(r) * 6ll * K;
+    __nv_bfloat16* orow = out + static_cast<long long>(r) * LAYOUT * K;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int c = lane + i * 32;
@@ -110,13 +127,14 @@ split3_layernorm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__
         o.y = sc * ((v[i].y - mean) * rstd * g.y + b.y);
         o.z = sc * ((v[i].z - mean) * rstd * g.z + b.z);
         o.w = sc * ((v[i].w - mean) * rstd * g.w + b.w);
-        store_split4(orow, K, c * 4, o);
+        store_split4<LAYOUT>(orow, K, c * 4, o);
       }
     }
   }
 }
 
 // im2col of fp32 NCHW images straight into split rows (patch q of sample b -> row b*P + q, K order (c,i,j)).
+template <int LAYOUT>
 __global__ void patchify_split3_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int S, int p, int n_side,
                                        long long total_chunks) {
   const int Kp = 3 * p * p;
@@ -133,7 +151,7 @@ __global__ void patchify_split3_kernel(const float* __restrict__ img, __nv_bfloa
     const int patch = static_cast<int>(row - b * P);
     const int py = patch / n_side, px = patch - py * n_side;
     const float4 v = *reinterpret_cast<const float4*>(img + ((b * 3 + c) * S + (py * p + i)) * static_cast<long long>(S) + px * p + j);
-    store_split4(out + row * 6ll * Kp, Kp, k, v);
+    store_split4<LAYOUT>(out + row * static_cast<long long>(LAYOUT) * Kp, Kp, k, v);
   }
 }
 
@@ -275,40 +293,60 @@ static int grid_1d(long long items, int per_block) {
 
 }  // namespace pk
 
-extern "C" int pk_split3_bf16(const float* x, void* out, int rows, int dim, int mode, const float* gamma, const float* beta, float eps,
-                              const float* rowscale, const int* row_index, const int* rows_dev, void* stream) {
-  using namespace pk;
-  PK_REQUIRE(x && out && rows >= 0 && dim > 0 && dim % 8 == 0, "pk_split3_bf16: null pointer or dim %% 8 != 0");
-  PK_REQUIRE(mode >= 0 && mode <= 2, "pk_split3_bf16: mode must be 0 (none), 1 (GELU) or 2 (LayerNorm)");
+namespace pk {
+template <int LAYOUT>
+static int launch_split(const char* who, const float* x, void* out, int rows, int dim, int mode, const float* gamma, const float* beta,
+                        float eps, const float* rowscale, const int* row_index, const int* rows_dev, void* stream) {
+  PK_REQUIRE(x && out && rows >= 0 && dim > 0 && dim % 8 == 0, "%s: null pointer or dim %% 8 != 0", who);
+  PK_REQUIRE(mode >= 0 && mode <= 2, "%s: mode must be 0 (none), 1 (GELU) or 2 (LayerNorm)", who);
   if (rows == 0) return PK_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   if (mode == 2) {
-    PK_REQUIRE(gamma && beta && dim <= 1024, "pk_split3_bf16: LayerNorm mode needs gamma / beta and dim <= 1024");
+    PK_REQUIRE(gamma && beta && dim <= 1024, "%s: LayerNorm mode needs gamma / beta and dim <= 1024", who);
     const int grid = grid_1d(rows, 8);
     const int maxv = (dim / 4 + 31) / 32;
-    if (maxv <= 2) split3_layernorm_kernel<2><<<grid, 256, 0, s>>>(x, o, gamma, beta, eps, rows, dim, rowscale, row_index, rows_dev);
-    else if (maxv <= 4) split3_layernorm_kernel<4><<<grid, 256, 0, s>>>(x, o, gamma, beta, eps, rows, dim, rowscale, row_index, rows_dev);
-    else split3_layernorm_kernel<8><<<grid, 256, 0, s>>>(x, o, gamma, beta, eps, rows, dim, rowscale, row_index, rows_dev);
-    return check_cuda(cudaGetLastError(), "split3_layernorm_kernel");
+    if (maxv <= 2) split3_layernorm_kernel<2, LAYOUT><<<grid, 256, 0, s>>>(x, o, gamma, beta, eps, rows, dim, rowscale, row_index, rows_dev);
+    else if (maxv <= 4) split3_layernorm_kernel<4, LAYOUT><<<grid, 256, 0, s>>>(x, o, gamma, beta, eps, rows, dim, rowscale, row_index, rows_dev);
+    else split3_layernorm_kernel<8, LAYOUT><<<grid, 256, 0, s>>>(x, o, gamma, beta, eps, rows, dim, rowscale, row_index, rows_dev);
+    return check_cuda(cudaGetLastError(), "split_layernorm_kernel");
   }
-  PK_REQUIRE(row_index == nullptr, "pk_split3_bf16: row_index is a LayerNorm-mode argument");
+  PK_REQUIRE(row_index == nullptr, "%s: row_index is a LayerNorm-mode argument", who);
   const long long total = static_cast<long long>(rows) * (dim / 4);
-  if (mode == 1) split3_kernel<1><<<grid_1d(total, 256), 256, 0, s>>>(x, o, rows, dim, rowscale, rows_dev);
-  else split3_kernel<0><<<grid_1d(total, 256), 256, 0, s>>>(x, o, rows, dim, rowscale, rows_dev);
-  return check_cuda(cudaGetLastError(), "split3_kernel");
+  if (mode == 1) split3_kernel<1, LAYOUT><<<grid_1d(total, 256), 256, 0, s>>>(x, o, rows, dim, rowscale, rows_dev);
+  else split3_kernel<0, LAYOUT><<<grid_1d(total, 256), 256, 0, s>>>(x, o, rows, dim, rowscale, rows_dev);
+  return check_cuda(cudaGetLastError(), "split_kernel");
 }
 
-extern "C" int pk_patchify_split3(const float* images, void* patches6, int batch, int image_size, int patch_size, void* stream) {
-  using namespace pk;
-  PK_REQUIRE(images && patches6, "pk_patchify_split3: null pointer");
-  PK_REQUIRE(patch_size % 8 == 0 && image_size % patch_size == 0, "pk_patchify_split3: patch_size must be a multiple of 8 dividing image_size");
+template <int LAYOUT>
+static int launch_patchify_split(const char* who, const float* images, void* patches, int batch, int image_size, int patch_size, void* stream) {
+  PK_REQUIRE(images && patches, "%s: null pointer", who);
+  PK_REQUIRE(patch_size % 8 == 0 && image_size % patch_size == 0, "%s: patch_size must be a multiple of 8 dividing image_size", who);
   if (batch == 0) return PK_OK;
   const int n_side = image_size / patch_size;
   const long long total = static_cast<long long>(batch) * n_side * n_side * 3 * patch_size * patch_size / 4;
-  patchify_split3_kernel<<<grid_1d(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      images, static_cast<__nv_bfloat16*>(patches6), image_size, patch_size, n_side, total);
-  return check_cuda(cudaGetLastError(), "patchify_split3_kernel");
+  patchify_split3_kernel<LAYOUT><<<grid_1d(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      images, static_cast<__nv_bfloat16*>(patches), image_size, patch_size, n_side, total);
+  return check_cuda(cudaGetLastError(), "patchify_split_kernel");
+}
+}  // namespace pk
+
+extern "C" int pk_split3_bf16(const float* x, void* out, int rows, int dim, int mode, const float* gamma, const float* beta, float eps,
+                              const float* rowscale, const int* row_index, const int* rows_dev, void* stream) {
+  return pk::launch_split<6>("pk_split3_bf16", x, out, rows, dim, mode, gamma, beta, eps, rowscale, row_index, rows_dev, stream);
+}
+
+extern "C" int pk_split2_bf16(const float* x, void* out, int rows, int dim, int mode, const float* gamma, const float* beta, float eps,
+                              const float* rowscale, const int* row_index, const int* rows_dev, void* stream) {
+  return pk::launch_split<2>("pk_split2_bf16", x, out, rows, dim, mode, gamma, beta, eps, rowscale, row_index, rows_dev, stream);
+}
+
+extern "C" int pk_patchify_split3(const float* images, void* patches6, int batch, int image_size, int patch_size, void* stream) {
+  return pk::launch_patchify_split<6>("pk_patchify_split3", images, patches6, batch, image_size, patch_size, stream);
+}
+
+extern "C" int pk_patchify_split2(const float* images, void* patches3, int batch, int image_size, int patch_size, void* stream) {
+  return pk::launch_patchify_split<3>("pk_patchify_split2", images, patches3, batch, image_size, patch_size, stream);
 }
 
 extern "C" int pk_attention_f32(const float* qkv, float* out, int batch, int num_heads, int head_dim, int seq_len, float scale,

@@ -536,6 +536,21 @@ extern "C" int pk_gemm_bf16(const pk_gemm_args* a, void* stream) {
   if (a->M == 0) return PK_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool ln_fused = a->xb_out != nullptr || a->ln_stats != nullptr;
+  if (a->a_wrap_k > 0 || a->out_format != PK_OUT_BF16) {
+    // two-term split operands / fp16 / split outputs (bf16x2 mode): CTA-pair kernel only
+    PK_REQUIRE(pair_gemm_eligible(a) && a->cta_pair != 1 && !ln_fused,
+               "pk_gemm_bf16: a_wrap_k / out_format need the CTA-pair kernel (contiguous rows, aligned) without fused LayerNorm");
+    PK_REQUIRE(a->a_wrap_k == 0 || (a->K == 3 * a->a_wrap_k && a->a_wrap_k % kBK == 0 && a->lda >= 2ll * a->a_wrap_k),
+               "pk_gemm_bf16: a_wrap_k=%d needs K == 3*a_wrap_k (K=%d), a_wrap_k %% 64 == 0 and lda >= 2*a_wrap_k", a->a_wrap_k, a->K);
+    if (a->out_format != PK_OUT_BF16) {
+      PK_REQUIRE(a->epilogue == PK_EPI_BIAS_BF16 || a->epilogue == PK_EPI_BIAS_GELU_BF16, "pk_gemm_bf16: out_format applies to the 2-byte epilogues");
+      PK_REQUIRE(a->out_format == PK_OUT_F16 ? a->epilogue == PK_EPI_BIAS_BF16 : a->out_format == PK_OUT_BF16X2,
+                 "pk_gemm_bf16: out_format %d is not available for epilogue %d", a->out_format, a->epilogue);
+      if (a->out_format == PK_OUT_BF16X2)
+        PK_REQUIRE(a->N % 64 == 0 && a->ldo >= 2ll * a->N, "pk_gemm_bf16: split output needs N %% 64 == 0 and ldo >= 2N (N=%d)", a->N);
+    }
+    return launch_pair_gemm(a, s);
+  }
   if (ln_fused) {
     PK_REQUIRE(pair_gemm_eligible(a) && a->cta_pair != 1 && a->block_n == 0,
                "pk_gemm_bf16: the fused-LayerNorm epilogues need the CTA-pair kernel (contiguous rows, aligned, block_n auto)");

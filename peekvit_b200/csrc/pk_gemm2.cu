@@ -34,7 +34,9 @@ constexpr int kP_BufBytes = 4096;   // one 32-row x 128-byte staging tile
 // per-row partial sums / sums of squares); 2 = LayerNorm *consumer* (bf16 epilogues whose A operand is that raw bf16 copy
 // and whose weights carry the LayerNorm gain: out = rstd*acc - rstd*mean*c1[n] + c2[n]).  Together they remove the separate
 // LayerNorm kernel: x -> LN -> Linear becomes one GEMM epilogue feeding the next GEMM (vit.py:48-55).
-template <int BN, int EPI, bool RED, int EW = 8, int LN = 0>
+// OUTF (2-byte epilogues only): 0 = bf16, 1 = IEEE half, 2 = value split into hi + lo (both bf16) written as [lo | hi]
+// planes N columns apart (the "bf16x2" arithmetic mode, include/peekvit_b200.h pk_out_format).
+template <int BN, int EPI, bool RED, int EW = 8, int LN = 0, int OUTF = 0>
 struct PairCfg {
   static constexpr int kEpiWarps = EW;
   static constexpr int kThreads = 128 + EW * 32;
@@ -50,6 +52,7 @@ struct PairCfg {
   static constexpr int kStoreSwizzle = kOutBf16 ? (kUnitsPerStore == 2 ? 128 : 64) : 128;
   static constexpr int kBufs = EW == 16 ? 1 : (kResid ? 3 : 2);               // staging buffers per epilogue warp
   static_assert(EW != 16 || !kResid, "the staged-residual epilogue needs its 3-deep ring");
+  static_assert(OUTF == 0 || (kOutBf16 && EW == 8 && LN == 0), "fp16 / split outputs are variants of the plain 2-byte epilogues");
   static constexpr int kABytes = kP_BM * kP_BK * 2;
   static constexpr int kBBytes = (BN / 2) * kP_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -93,6 +96,7 @@ struct PairParams {
   int ln_parts;
   float ln_inv_dim, ln_eps;
   int debug;      // PK_GEMM_DEBUG bits (timing experiments only): 1 = no operand loads, 2 = no epilogue math/stores
+  int a_wrap_k;   // two-term split A operand stored as [lo | hi]: K index c >= 2*a_wrap_k reads A column c - a_wrap_k (0 = off)
 };
 
 // ---------------------------------------------------------------- cluster / cta_group::2 PTX
@@ -147,12 +151,12 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 }
 __device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
 
-template <int BN, int EPI, bool RED, int EW, int LN>
+template <int BN, int EPI, bool RED, int EW, int LN, int OUTF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + EW * 32, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                       const __grid_constant__ CUtensorMap tmap_xb, const PairParams p) {
-  using Cfg = PairCfg<BN, EPI, RED, EW, LN>;
+  using Cfg = PairCfg<BN, EPI, RED, EW, LN, OUTF>;
   constexpr int kP_EpiWarps = EW;
   constexpr bool kOutBf16 = Cfg::kOutBf16;
   constexpr bool kResid = Cfg::kResid;
@@ -223,7 +227,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     int pf_t = pair, pf_kb = 0;
     auto prefetch_next = [&]() {        // elected lane
       if (pf_t < num_tiles) {
-        tma_prefetch_l2_2d(&tmap_a, pf_kb * kP_BK, row0 + (pf_t / n_tiles) * 2 * kP_BM + a_row_off);
+        int pf_col = pf_kb * kP_BK;
+        if (p.a_wrap_k > 0 && pf_col >= 2 * p.a_wrap_k) pf_col -= p.a_wrap_k;
+        tma_prefetch_l2_2d(&tmap_a, pf_col, row0 + (pf_t / n_tiles) * 2 * kP_BM + a_row_off);
         tma_prefetch_l2_2d(&tmap_b, pf_kb * kP_BK, (pf_t % n_tiles) * BN + b_row_off);
       }
     };
@@ -251,7 +257,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           if (rank == 0) mbar_expect_tx(fb_local, 2 * Cfg::kStageBytes);   // both CTAs' bytes land on the leader's barrier
           const uint32_t fb = mapa_u32(fb_local, 0);
           const uint32_t a_dst = smem_u32(smem_ab + s * Cfg::kStageBytes);
-          tma_load_2d_pair(a_dst, &tmap_a, fb, kb * kP_BK, row0 + m_blk * 2 * kP_BM + a_row_off);
+          int a_col = kb * kP_BK;
+          if (p.a_wrap_k > 0 && a_col >= 2 * p.a_wrap_k) a_col -= p.a_wrap_k;       // [lo | hi] read as lo, hi, hi
+          tma_load_2d_pair(a_dst, &tmap_a, fb, a_col, row0 + m_blk * 2 * kP_BM + a_row_off);
           tma_load_2d_pair(a_dst + Cfg::kABytes, &tmap_b, fb, kb * kP_BK, n_blk * BN + b_row_off);
           }
           if (p.l2_prefetch) prefetch_next();
@@ -375,7 +383,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         uint32_t (&vn)[32] = (u & 1) ? va : vb;
         const int ch = u / kUPS;              // store chunk inside the tile
         const int sub = u % kUPS;             // unit inside the store chunk
-        const uint32_t b = kBufs == 1 ? 0u : (kResid ? (g % 3u) : (g & 1u));
+        // split output: the two staging buffers hold the hi and the lo tile of the SAME chunk (no double buffering)
+        const uint32_t b = (kBufs == 1 || OUTF == 2) ? 0u : (kResid ? (g % 3u) : (g & 1u));
         uint8_t* bufp = ebuf + b * kSlot;
         const int col0 = (t % n_tiles) * BN + half * kPartCols + u * 32;     // first output column of this unit
         float4 bias4[8];
@@ -406,11 +415,12 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             if (!mbar_wait(smem_u32(&rbar[b]), (g / 3u) & 1u, p.flag, 0x1500u + ew)) { ok = false; break; }
           } else {
             // the store that last used this buffer (two chunks ago; the previous one with a single buffer) has drained
-            if (lane == 0) { if constexpr (kBufs == 1) bulk_wait_read<0>(); else bulk_wait_read<1>(); }
+            if (lane == 0) { if constexpr (kBufs == 1 || OUTF == 2) bulk_wait_read<0>(); else bulk_wait_read<1>(); }
             __syncwarp();
           }
         }
         uint32_t xbp[LN == 1 ? 16 : 1];
+        uint32_t lo2[OUTF == 2 ? 16 : 1];         // lo plane of the split output (v holds the hi plane)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 b4 = bias4[j];
@@ -443,8 +453,16 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             xbp[2 * j + 1] = pack_bf16(a2, a3);
           }
           if constexpr (kOutBf16) {
-            v[2 * j] = pack_bf16(a0, a1);
-            v[2 * j + 1] = pack_bf16(a2, a3);
+            if constexpr (OUTF == 1) {
+              v[2 * j] = pack_f16(a0, a1);
+              v[2 * j + 1] = pack_f16(a2, a3);
+            } else if constexpr (OUTF == 2) {
+              split2_pack(a0, a1, v[2 * j], lo2[2 * j]);
+              split2_pack(a2, a3, v[2 * j + 1], lo2[2 * j + 1]);
+            } else {
+              v[2 * j] = pack_bf16(a0, a1);
+              v[2 * j + 1] = pack_bf16(a2, a3);
+            }
           } else {
             v[4 * j] = __float_as_uint(a0); v[4 * j + 1] = __float_as_uint(a1);
             v[4 * j + 2] = __float_as_uint(a2); v[4 * j + 3] = __float_as_uint(a3);
@@ -458,12 +476,24 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
               for (int j = 0; j < 4; ++j)
                 *reinterpret_cast<uint4*>(bufp + lane * 128 + (((sub * 4 + j) ^ (lane & 7)) << 4)) =
                     make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if constexpr (OUTF == 2) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  *reinterpret_cast<uint4*>(bufp + kSlot + lane * 128 + (((sub * 4 + j) ^ (lane & 7)) << 4)) =
+                      make_uint4(lo2[4 * j], lo2[4 * j + 1], lo2[4 * j + 2], lo2[4 * j + 3]);
+              }
             } else {
               // 64-byte rows, 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3) (SWIZZLE_64B)
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 *reinterpret_cast<uint4*>(bufp + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
                     make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if constexpr (OUTF == 2) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  *reinterpret_cast<uint4*>(bufp + kSlot + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                      make_uint4(lo2[4 * j], lo2[4 * j + 1], lo2[4 * j + 2], lo2[4 * j + 3]);
+              }
             }
           } else {
 #pragma unroll
@@ -482,7 +512,13 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              if constexpr (RED) tma_reduce_add_2d(&tmap_out, ebuf_u32 + b * kSlot, col0 - sub * 32, row_base);
+              if constexpr (OUTF == 2) {
+                // hi plane N columns after the lo plane; a chunk that starts at or past N lies entirely outside (N % 64 == 0)
+                if (col0 - sub * 32 < p.N) {
+                  tma_store_2d(&tmap_out, ebuf_u32, p.N + col0 - sub * 32, row_base);
+                  tma_store_2d(&tmap_out, ebuf_u32 + kSlot, col0 - sub * 32, row_base);
+                }
+              } else if constexpr (RED) tma_reduce_add_2d(&tmap_out, ebuf_u32 + b * kSlot, col0 - sub * 32, row_base);
               else tma_store_2d(&tmap_out, ebuf_u32 + b * kSlot, col0 - sub * 32, row_base);
               if constexpr (LN == 1) tma_store_2d(&tmap_xb, ebuf_u32 + kBufs * kSlot + (g & 1u) * 2048, col0, row_base);
               bulk_commit();
@@ -495,10 +531,15 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         }
         if (!full_tile && grow < row_end) {
           if constexpr (kOutBf16) {
-            __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(grow) * p.ldo + col0;
+            __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(grow) * p.ldo + col0 + (OUTF == 2 ? p.N : 0);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               if (col0 + 8 * j < p.N) *reinterpret_cast<uint4*>(orow + 8 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if constexpr (OUTF == 2) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (col0 + 8 * j < p.N) *reinterpret_cast<uint4*>(orow - p.N + 8 * j) = make_uint4(lo2[4 * j], lo2[4 * j + 1], lo2[4 * j + 2], lo2[4 * j + 3]);
+            }
           } else {
             float* orow = static_cast<float*>(p.out) + static_cast<long long>(grow) * p.ldo + col0;
 #pragma unroll
@@ -594,23 +635,24 @@ static int pair_debug() {
   return v;
 }
 
-template <int BN, int EPI, bool RED = false, int EW = 8, int LN = 0>
+template <int BN, int EPI, bool RED = false, int EW = 8, int LN = 0, int OUTF = 0>
 static int launch_pair(const pk_gemm_args* a, cudaStream_t stream) {
-  using Cfg = PairCfg<BN, EPI, RED, EW, LN>;
+  using Cfg = PairCfg<BN, EPI, RED, EW, LN, OUTF>;
   static bool attr_set = false;
-  auto kfn = gemm_bf16_pair_kernel<BN, EPI, RED, EW, LN>;
+  auto kfn = gemm_bf16_pair_kernel<BN, EPI, RED, EW, LN, OUTF>;
   if (!attr_set) {
     PK_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   CUtensorMap ta, tb, tout, tres;
-  int rc = make_tmap_bf16_2d(&ta, a->A, static_cast<uint64_t>(a->M), static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->lda),
+  const int a_cols = a->a_wrap_k > 0 ? 2 * a->a_wrap_k : a->K;          // [lo | hi] is stored once, read as lo, hi, hi
+  int rc = make_tmap_bf16_2d(&ta, a->A, static_cast<uint64_t>(a->M), static_cast<uint64_t>(a_cols), static_cast<uint64_t>(a->lda),
                              kP_BM, kP_BK);
   if (rc != PK_OK) return rc;
   rc = make_tmap_bf16_2d(&tb, a->W, static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->ldw), BN / 2,
                          kP_BK);
   if (rc != PK_OK) return rc;
-  rc = make_tmap_2d(&tout, a->out, Cfg::kOutBf16 ? 2 : 4, static_cast<uint64_t>(a->M), static_cast<uint64_t>(a->N),
+  rc = make_tmap_2d(&tout, a->out, Cfg::kOutBf16 ? 2 : 4, static_cast<uint64_t>(a->M), static_cast<uint64_t>(OUTF == 2 ? 2 * a->N : a->N),
                     static_cast<uint64_t>(a->ldo), 32, Cfg::kStoreCols, Cfg::kStoreSwizzle);
   if (rc != PK_OK) return rc;
   tres = tout;
@@ -640,6 +682,7 @@ static int launch_pair(const pk_gemm_args* a, cudaStream_t stream) {
   p.flag = device_flag_ptr();
   p.l2_prefetch = pair_l2_prefetch();
   p.debug = pair_debug();
+  p.a_wrap_k = a->a_wrap_k;
   const int m_tiles = (a->M + 2 * kP_BM - 1) / (2 * kP_BM), n_tiles = (a->N + BN - 1) / BN;
   int pairs = m_tiles * n_tiles;
   const int sms = a->max_ctas > 0 ? a->max_ctas : num_sms();
@@ -653,9 +696,12 @@ template <int BN>
 static int dispatch_pair_epi(const pk_gemm_args* a, cudaStream_t stream) {
   switch (a->epilogue) {
     case PK_EPI_BIAS_BF16:
+      if (a->out_format == PK_OUT_F16) return launch_pair<BN, PK_EPI_BIAS_BF16, false, 8, 0, 1>(a, stream);
+      if (a->out_format == PK_OUT_BF16X2) return launch_pair<BN, PK_EPI_BIAS_BF16, false, 8, 0, 2>(a, stream);
       if (a->ln_stats) return launch_pair<BN, PK_EPI_BIAS_BF16, false, 8, 2>(a, stream);
       return launch_pair<BN, PK_EPI_BIAS_BF16>(a, stream);
     case PK_EPI_BIAS_GELU_BF16:
+      if (a->out_format == PK_OUT_BF16X2) return launch_pair<BN, PK_EPI_BIAS_GELU_BF16, false, 8, 0, 2>(a, stream);
       if (a->ln_stats) return launch_pair<BN, PK_EPI_BIAS_GELU_BF16, false, 8, 2>(a, stream);
       if constexpr (BN != 192) {
         if (pair_gelu_warps() == 16) return launch_pair<BN, PK_EPI_BIAS_GELU_BF16, false, 16>(a, stream);

@@ -21,7 +21,7 @@ import torch
 import os
 
 from . import ops
-from ._lib import PK_EPI_BIAS_BF16, PK_EPI_BIAS_F32, PK_EPI_BIAS_GELU_BF16, PK_EPI_BIAS_RESID_F32
+from ._lib import PK_EPI_BIAS_BF16, PK_EPI_BIAS_F32, PK_EPI_BIAS_GELU_BF16, PK_EPI_BIAS_RESID_F32, PK_OUT_BF16X2, PK_OUT_F16
 from .ops import SPLIT_GELU, SPLIT_LAYERNORM, SPLIT_NONE
 
 
@@ -314,11 +314,22 @@ class Forward:
         # sequence does not depend on where the caller's image tensor lives
         self.patches_ready = False
         self.input_norm = (ops.IMAGENET_MEAN, ops.IMAGENET_STD)      # Normalize statistics of the uint8 input path
-        # fp32-accurate mode (runner: model.pk_precision = "fp32"): split-operand GEMMs, fp32 attention (csrc/pk_exact.cu)
-        self.exact = False
+        # Split-operand arithmetic modes (runner: model.pk_precision; csrc/pk_exact.cu).  terms = 3: "fp32", three bf16 terms
+        # per operand (K' = 6K) + fp32 attention: logits within 1e-5.  terms = 2: "bf16x2", hi + lo (K' = 3K, the activation
+        # row stored once as [lo | hi]) with the split produced by the GEMM / attention epilogues themselves and the tcgen05
+        # attention on IEEE-half operands: 16 significant bits on every linear operand, 11 in the attention core.
+        self.terms = 0
         # NoiseBlock draws of the current forward (draw_noise) and the first sample of the micro-batch being run
         self.noise_draws: Dict[int, tuple] = {}
         self.sample_offset = 0
+
+    @property
+    def exact(self) -> bool:
+        return self.terms > 0
+
+    def _wrap(self, k: int) -> dict:
+        """gemm() keyword for a split activation operand of unsplit width k."""
+        return dict(a_wrap_k=k, cta_pair=2) if self.terms == 2 else {}
 
     def _embed_geometry(self, batch: int):
         """(tokens per sample of the embedded stream, shift rows after the first class token, token-row layout?).
@@ -343,9 +354,17 @@ class Forward:
         return t
 
     def patchify(self, images: torch.Tensor) -> torch.Tensor:
-        """im2col of float NCHW images, or of uint8 NHWC images with ToTensor + Normalize fused in."""
+        """im2col of float NCHW images, or of uint8 NHWC images with ToTensor + Normalize fused in; in the
+        split-operand modes straight into split rows.  The only kernel that reads the caller's image tensor: the CUDA-graph
+        runner launches it eagerly in front of every replay."""
         pm = self.pm
         B = images.shape[0]
+        if self.exact:
+            if images.dtype != torch.float32:
+                raise NotImplementedError("the split-operand modes take float images (the uint8 input path is a bf16-mode feature)")
+            t, Kp = self.terms, pm.w_patch.shape[1]
+            return ops.patchify_split(images, pm.patch_size,
+                                      self.ws.get(f"patches_x{t}", (B * pm.num_patches, (6 if t == 3 else 3) * Kp), torch.bfloat16), t)
         seq, shift, token_rows = self._embed_geometry(B)
         out = self._patch_operand(B)
         lay = dict(rows_per_sample=seq, row_offset=pm.n_cls + pm.n_reg + shift) if token_rows else {}
@@ -445,45 +464,48 @@ class Forward:
 
     # ---- fp32-accurate mode (the reference's shipped dtype): same tcgen05 GEMM kernels on 3-way split bf16 operands
     def _exact_weights(self, lw: LayerWeights) -> Dict[str, List[torch.Tensor]]:
-        """Split weight rows [m|h|l|h|m|h] of a block (one entry per expert; plain blocks have one), built from the fp32
-        masters on first use."""
-        c = lw.extra.get("x3")
+        """Split weight rows of a block ([m|h|l|h|m|h] for three terms, [h|l|h] for two; one entry per expert, plain blocks
+        have one), built from the fp32 masters on first use."""
+        key = f"x{self.terms}"
+        c = lw.extra.get(key)
         if c is None:
-            blk = lw.module
+            blk, t = lw.module, self.terms
             if lw.kind == "moe":
                 mhas = [e.self_attention for e in blk.self_attention.experts]
                 mlps = list(blk.mlp.experts)
             else:
                 mhas, mlps = [blk.self_attention.self_attention], [blk.mlp]
-            c = lw.extra["x3"] = dict(w_qkv=[ops.split3_weight(m.in_proj_weight) for m in mhas],
-                                      w_o=[ops.split3_weight(m.out_proj.weight) for m in mhas],
-                                      w_fc1=[ops.split3_weight(m.fc1.weight) for m in mlps],
-                                      w_fc2=[ops.split3_weight(m.fc2.weight) for m in mlps])
+            c = lw.extra[key] = dict(w_qkv=[ops.split_weight(m.in_proj_weight, t) for m in mhas],
+                                     w_o=[ops.split_weight(m.out_proj.weight, t) for m in mhas],
+                                     w_fc1=[ops.split_weight(m.fc1.weight, t) for m in mlps],
+                                     w_fc2=[ops.split_weight(m.fc2.weight, t) for m in mlps])
         return c
 
     def gemm_exact(self, a32: torch.Tensor, rows: int, w6: torch.Tensor, bias, out, epilogue: int, mode: int = SPLIT_NONE,
                    gamma=None, beta=None, eps: float = 0.0, resid=None, *, in_scale=None, row_index=None, rows_dev=None,
                    a6=None, **gemm_kw):
-        """out = epilogue(in_scale * pre(a32) @ W^T + bias) at fp32 accuracy: pre = none / exact GELU / LayerNorm is applied
-        by the kernel that splits the activation rows, the product runs as one bf16 GEMM over K' = 6K.  ``a6``: reuse rows
-        that are already split (several experts reading the same activations)."""
+        """out = epilogue(in_scale * pre(a32) @ W^T + bias) at split-operand accuracy: pre = none / exact GELU / LayerNorm is
+        applied by the kernel that splits the activation rows, the product runs as one bf16 GEMM over K' = 6K (three terms) or
+        3K (two terms, rows stored as [lo | hi]).  ``a6``: reuse rows that are already split (several experts reading the same
+        activations)."""
         K = a32.shape[-1]
         if a6 is None:
-            a6 = self.ws.get(f"a6_{K}", (rows, 6 * K), torch.bfloat16)
-            ops.split3(a32, a6, mode, gamma, beta, eps, rows=rows, rowscale=in_scale, row_index=row_index, rows_dev=rows_dev)
-        return ops.gemm(a6, w6, bias, out, epilogue, resid=resid, **gemm_kw)
+            a6 = self.ws.get(f"a{self.terms}_{K}", (rows, ops.split_width(self.terms) * K), torch.bfloat16)
+            ops.split(a32, a6, self.terms, mode, gamma, beta, eps, rows=rows, rowscale=in_scale, row_index=row_index, rows_dev=rows_dev)
+        return ops.gemm(a6, w6, bias, out, epilogue, resid=resid, **self._wrap(K), **gemm_kw)
 
     def embed_exact(self, images: torch.Tensor, shift: int = 0) -> torch.Tensor:
         pm = self.pm
-        if images.dtype != torch.float32:
-            raise NotImplementedError("the fp32-accurate mode takes float images (the uint8 input path is a bf16-mode feature)")
         B = images.shape[0]
         P, D, T, R, seq = pm.num_patches, pm.dim, pm.n_cls, pm.n_reg, pm.seq_len + shift
         Kp = pm.w_patch.shape[1]
-        w6 = pm.extra.get("w_patch6")
+        t = self.terms
+        w6 = pm.extra.get(f"w_patch_x{t}")
         if w6 is None:
-            w6 = pm.extra["w_patch6"] = ops.split3_weight(pm.extra["conv_weight"].reshape(D, -1))
-        patches6 = ops.patchify_split3(images, pm.patch_size, self.ws.get("patches6", (B * P, 6 * Kp), torch.bfloat16))
+            w6 = pm.extra[f"w_patch_x{t}"] = ops.split_weight(pm.extra["conv_weight"].reshape(D, -1), t)
+        # the patch GEMM's row remap runs on the single-CTA kernel: the two-term operand is stored unwrapped, [lo | hi | hi]
+        patches6 = (self.ws.get(f"patches_x{t}", (B * P, (6 if t == 3 else 3) * Kp), torch.bfloat16) if self.patches_ready
+                    else self.patchify(images))
         x = self.ws.get("x", (B * seq, D), torch.float32)
         ops.gemm(patches6, w6, pm.b_patch, x, PK_EPI_BIAS_RESID_F32, resid=pm.pos,
                  rows_per_group=P, group_stride=seq, group_offset=T + R + shift, resid_is_pos=True, pos_offset=T + R)
@@ -503,21 +525,43 @@ class Forward:
                          out_scale=None, a6=None):
         pm, ws = self.pm, self.ws
         D = pm.dim
+        dh = D // pm.heads
         w, aw = self._exact_weights(lw), lw.attn[expert]
         xr = x[:rows]
+        o_scale = rowscale if out_scale is None else out_scale
+        if (self.terms == 2 and cu is None and key_mult is None and extra_mult is None and dh == 64 and 17 <= seq <= 224):
+            # bf16x2 fast path: the in-projection writes IEEE-half q | k | v, the tcgen05 attention takes them as they are and
+            # writes its fp32 result already split [lo | hi] -- the out-projection's operand, with no pass in between
+            if a6 is None:
+                a6 = ws.get(f"a2_{D}", (rows, 2 * D), torch.bfloat16)
+                ops.split(xr, a6, 2, SPLIT_LAYERNORM, lw.ln1_w, lw.ln1_b, lw.eps, rows=rows, rowscale=rowscale, rows_dev=rows_dev)
+            qkv = ops.gemm(a6, w["w_qkv"][expert], aw.b_qkv, ws.get("qkv16", (rows, 3 * D), torch.float16), PK_EPI_BIAS_BF16,
+                           m_dev=rows_dev, out_format=PK_OUT_F16, **self._wrap(D))
+            att = ops.attention(qkv, ws.get("att_x2", (rows, 2 * D), torch.bfloat16), batch, pm.heads, dh, seq_len=seq, half_split=True)
+            ops.gemm(att, w["w_o"][expert], aw.b_o, xr, PK_EPI_BIAS_RESID_F32, resid=xr, m_dev=rows_dev, rowscale=o_scale, **self._wrap(D))
+            return
         qkv = self.gemm_exact(xr, rows, w["w_qkv"][expert], aw.b_qkv, ws.get("qkv32", (rows, 3 * D), torch.float32), PK_EPI_BIAS_F32,
                               SPLIT_LAYERNORM, lw.ln1_w, lw.ln1_b, lw.eps, in_scale=rowscale, rows_dev=rows_dev, m_dev=rows_dev, a6=a6)
-        att = ops.attention_f32(qkv, ws.get("att32", (rows, D), torch.float32), batch, pm.heads, D // pm.heads, seq,
+        att = ops.attention_f32(qkv, ws.get("att32", (rows, D), torch.float32), batch, pm.heads, dh, seq,
                                 cu_seqlens=cu, max_seq_len=max_len, key_mult=key_mult,
                                 extra_kv=aw.b_qkv[D:] if extra_mult is not None else None, extra_mult=extra_mult)
         self.gemm_exact(att, rows, w["w_o"][expert], aw.b_o, xr, PK_EPI_BIAS_RESID_F32, resid=xr, rows_dev=rows_dev, m_dev=rows_dev,
-                        rowscale=rowscale if out_scale is None else out_scale)
+                        rowscale=o_scale)
 
     def _mlp_part_exact(self, x, lw, rows, rows_dev, rowscale):
         ws = self.ws
         w, mw = self._exact_weights(lw), lw.mlp[0]
         F = mw.b_fc1.shape[0]
         xr = x[:rows]
+        if self.terms == 2 and F % 64 == 0:
+            # bf16x2 fast path: fc1's epilogue applies bias + GELU and writes the hidden row already split [lo | hi]
+            D = xr.shape[-1]
+            a2 = ws.get(f"a2_{D}", (rows, 2 * D), torch.bfloat16)
+            ops.split(xr, a2, 2, SPLIT_LAYERNORM, lw.ln2_w, lw.ln2_b, lw.eps, rows=rows, rowscale=rowscale, rows_dev=rows_dev)
+            hid = ops.gemm(a2, w["w_fc1"][0], mw.b_fc1, ws.get("hid_x2", (rows, 2 * F), torch.bfloat16), PK_EPI_BIAS_GELU_BF16,
+                           m_dev=rows_dev, out_format=PK_OUT_BF16X2, **self._wrap(D))
+            ops.gemm(hid, w["w_fc2"][0], mw.b_fc2, xr, PK_EPI_BIAS_RESID_F32, resid=xr, m_dev=rows_dev, **self._wrap(F))
+            return
         hid = self.gemm_exact(xr, rows, w["w_fc1"][0], mw.b_fc1, ws.get("hid32", (rows, F), torch.float32), PK_EPI_BIAS_F32,
                               SPLIT_LAYERNORM, lw.ln2_w, lw.ln2_b, lw.eps, in_scale=rowscale, rows_dev=rows_dev, m_dev=rows_dev)
         self.gemm_exact(hid, rows, w["w_fc2"][0], mw.b_fc2, xr, PK_EPI_BIAS_RESID_F32, SPLIT_GELU, resid=xr, rows_dev=rows_dev,
@@ -634,7 +678,7 @@ class Forward:
                 fold = None
                 continue
             b = budgets.get(i, 1.0) if lw.kind == "rank" else 1.0
-            if lw.kind == "rank" and b != 1:
+            if lw.kind == "rank" and b != 1 and seq > 1:            # nothing left to rank once only the class token survives
                 n = seq - 1
                 # rankvit.py:69-71: idx[:, :ceil(n*b)] -- a budget of 0 keeps the class token alone, a budget above 1 every token
                 k = min(max(math.ceil(n * b), 0), n)
@@ -841,8 +885,9 @@ class Forward:
                 onehot = ops.expert_onehot(expert, EA, ws.get(f"amoe_onehot_{EA}", (EA, rows), torch.float32), rows)
                 if self.exact:
                     # every expert reads the same split LN1 rows; they are produced by the first expert's in-proj call
-                    a6 = ws.get(f"a6_shared_{D}", (rows, 6 * D), torch.bfloat16)     # not the buffer the out-proj splits into
-                    ops.split3(x, a6, SPLIT_LAYERNORM, lw.ln1_w, lw.ln1_b, lw.eps, rows=rows)
+                    sw = ops.split_width(self.terms)
+                    a6 = ws.get(f"a{self.terms}_shared_{D}", (rows, sw * D), torch.bfloat16)     # not the buffer the out-proj splits into
+                    ops.split(x, a6, self.terms, SPLIT_LAYERNORM, lw.ln1_w, lw.ln1_b, lw.eps, rows=rows)
                     for e in range(EA):
                         self._attn_part_exact(x, lw, rows, B, seq, None, 0, None, None, None, None, expert=e,
                                               out_scale=onehot[e], a6=a6)
@@ -869,14 +914,24 @@ class Forward:
                 # same expert-sorted segments at fp32 accuracy: split(LN2) gathered into sorted order, per-expert fc1 over its
                 # segment, one exact-GELU split of all hidden rows, per-expert fc2
                 w6 = self._exact_weights(lw)
-                a6 = ws.get(f"a6_shared_{D}", (rows, 6 * D), torch.bfloat16)
-                ops.split3(x, a6, SPLIT_LAYERNORM, lw.ln2_w, lw.ln2_b, lw.eps, rows=rows, row_index=src_of)
-                hid32 = ws.get("hid32", (rows, F), torch.float32)
+                t, sw = self.terms, ops.split_width(self.terms)
+                a6 = ws.get(f"a{t}_shared_{D}", (rows, sw * D), torch.bfloat16)
+                ops.split(x, a6, t, SPLIT_LAYERNORM, lw.ln2_w, lw.ln2_b, lw.eps, rows=rows, row_index=src_of)
+                if t == 2 and F % 64 == 0:
+                    # bf16x2: every expert's fc1 epilogue writes its segment of the hidden rows already split [lo | hi]
+                    h6 = ws.get("hid_x2", (rows, 2 * F), torch.bfloat16)
+                    for e, mw in enumerate(lw.mlp):
+                        ops.gemm(a6, w6["w_fc1"][e], mw.b_fc1, h6, PK_EPI_BIAS_GELU_BF16, m_dev=counts[e:e + 1],
+                                 row_begin_dev=offsets[e:e + 1], out_format=PK_OUT_BF16X2, **self._wrap(D))
+                else:
+                    hid32 = ws.get("hid32", (rows, F), torch.float32)
+                    for e, mw in enumerate(lw.mlp):
+                        ops.gemm(a6, w6["w_fc1"][e], mw.b_fc1, hid32, PK_EPI_BIAS_F32, m_dev=counts[e:e + 1], row_begin_dev=offsets[e:e + 1],
+                                 **self._wrap(D))
+                    h6 = ops.split(hid32, ws.get(f"a{t}_{F}", (rows, sw * F), torch.bfloat16), t, SPLIT_GELU, rows=rows)
                 for e, mw in enumerate(lw.mlp):
-                    ops.gemm(a6, w6["w_fc1"][e], mw.b_fc1, hid32, PK_EPI_BIAS_F32, m_dev=counts[e:e + 1], row_begin_dev=offsets[e:e + 1])
-                h6 = ops.split3(hid32, ws.get(f"a6_{F}", (rows, 6 * F), torch.bfloat16), SPLIT_GELU, rows=rows)
-                for e, mw in enumerate(lw.mlp):
-                    ops.gemm(h6, w6["w_fc2"][e], mw.b_fc2, y_sorted, PK_EPI_BIAS_F32, m_dev=counts[e:e + 1], row_begin_dev=offsets[e:e + 1])
+                    ops.gemm(h6, w6["w_fc2"][e], mw.b_fc2, y_sorted, PK_EPI_BIAS_F32, m_dev=counts[e:e + 1], row_begin_dev=offsets[e:e + 1],
+                             **self._wrap(F))
                 ops.scatter_add_rows(x, y_sorted, src_of, rows)
                 if aux is not None:
                     aux.setdefault("mlp_expert", {})[i] = expert.view(B, seq).clone()

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from ._lib import (AttentionArgs, AvitArgs, CompactArgs, GemmArgs, ResidualGateArgs, PK_EPI_BIAS_BF16, PK_EPI_BIAS_F32, PK_EPI_BIAS_GELU_BF16,
-                   PK_EPI_BIAS_RESID_F32, check)
+                   PK_EPI_BIAS_RESID_F32, PK_OUT_BF16, PK_OUT_BF16X2, PK_OUT_F16, check)
 
 
 # Launch accounting for bench.py: every wrapper below launches exactly one kernel of ours.
@@ -65,15 +65,25 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
          out_row_index: Optional[torch.Tensor] = None, block_n: int = 0, max_ctas: int = 0,
          m: Optional[int] = None, epilogue_mode: int = 0, cta_pair: int = 0,
          xb_out: Optional[torch.Tensor] = None, row_stats: Optional[torch.Tensor] = None,
-         ln_stats: Optional[torch.Tensor] = None, ln_c1: Optional[torch.Tensor] = None, ln_dim: int = 0, ln_eps: float = 0.0) -> torch.Tensor:
-    """out = epilogue(a @ w.T + bias): a bf16 [M,K], w bf16 [N,K] (nn.Linear layout)."""
+         ln_stats: Optional[torch.Tensor] = None, ln_c1: Optional[torch.Tensor] = None, ln_dim: int = 0, ln_eps: float = 0.0,
+         a_wrap_k: int = 0, out_format: int = PK_OUT_BF16) -> torch.Tensor:
+    """out = epilogue(a @ w.T + bias): a bf16 [M,K], w bf16 [N,K] (nn.Linear layout).  ``a_wrap_k`` = k: a is the two-term
+    split row [lo | hi] (2k wide) read as lo, hi, hi against w = [Wh | Wl | Wh] (3k wide); ``out_format``: PK_OUT_F16 (half
+    output) or PK_OUT_BF16X2 (out is [M, 2N]: the value split into [lo | hi])."""
     lib = _lib_for(a)
     lda, ldw, ldo = _rowmajor(a, "a"), _rowmajor(w, "w"), _rowmajor(out, "out")
-    M, K = a.shape if m is None else (m, a.shape[1])
+    M = a.shape[0] if m is None else m
+    K = 3 * a_wrap_k if a_wrap_k > 0 else a.shape[1]
+    if a_wrap_k > 0 and a.shape[1] != 2 * a_wrap_k:
+        raise ValueError(f"a_wrap_k={a_wrap_k} needs a [M, {2 * a_wrap_k}] split operand, got {tuple(a.shape)}")
     N = w.shape[0]
     if w.shape[1] != K:
         raise ValueError(f"K mismatch: a {tuple(a.shape)} w {tuple(w.shape)}")
     out_dtype = torch.bfloat16 if epilogue in (PK_EPI_BIAS_BF16, PK_EPI_BIAS_GELU_BF16) else torch.float32
+    if out_format == PK_OUT_F16:
+        out_dtype = torch.float16
+    if out_format == PK_OUT_BF16X2 and out.shape[1] != 2 * N:
+        raise ValueError(f"split output needs out [M, {2 * N}], got {tuple(out.shape)}")
     args = GemmArgs()
     args.A, args.W = _ptr(a, torch.bfloat16), _ptr(w, torch.bfloat16)
     args.M, args.N, args.K = M, N, K
@@ -100,6 +110,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
     args.ln_c1 = _ptr(ln_c1, torch.float32)
     args.ln_parts = ln_stats.shape[1] if ln_stats is not None else 0
     args.ln_dim, args.ln_eps = ln_dim, ln_eps
+    args.a_wrap_k, args.out_format = a_wrap_k, out_format
     if gemm_timeline is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -165,13 +176,16 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 def attention(qkv: torch.Tensor, out: torch.Tensor, batch: int, num_heads: int, head_dim: int, *, seq_len: int = 0,
               cu_seqlens: Optional[torch.Tensor] = None, max_seq_len: int = 0, key_mult: Optional[torch.Tensor] = None,
-              extra_kv: Optional[torch.Tensor] = None, extra_mult: Optional[torch.Tensor] = None, impl: int = 0) -> torch.Tensor:
+              extra_kv: Optional[torch.Tensor] = None, extra_mult: Optional[torch.Tensor] = None, impl: int = 0,
+              half_split: bool = False) -> torch.Tensor:
+    """``half_split`` (bf16x2 mode, tcgen05 kernel): qkv is IEEE half, out is bf16 [rows, 2*D] = the result split [lo | hi]."""
     lib = _lib_for(qkv)
     D = num_heads * head_dim
-    if qkv.shape[-1] != 3 * D or not qkv.is_contiguous() or not out.is_contiguous():
-        raise ValueError("qkv must be contiguous [rows, 3*D] and out contiguous [rows, D]")
+    if qkv.shape[-1] != 3 * D or not qkv.is_contiguous() or not out.is_contiguous() or out.shape[-1] != (2 * D if half_split else D):
+        raise ValueError("qkv must be contiguous [rows, 3*D] and out contiguous [rows, D] ([rows, 2*D] for the split output)")
     a = AttentionArgs()
-    a.qkv, a.out = _ptr(qkv, torch.bfloat16), _ptr(out, torch.bfloat16)
+    a.qkv, a.out = _ptr(qkv, torch.float16 if half_split else torch.bfloat16), _ptr(out, torch.bfloat16)
+    a.qkv_format, a.out_format = (PK_OUT_F16, PK_OUT_BF16X2) if half_split else (PK_OUT_BF16, PK_OUT_BF16)
     a.batch, a.num_heads, a.head_dim = batch, num_heads, head_dim
     a.seq_len = seq_len
     a.cu_seqlens = _ptr(cu_seqlens, torch.int32)
@@ -435,6 +449,47 @@ def split3(x: torch.Tensor, out: torch.Tensor, mode: int = SPLIT_NONE, gamma: Op
     check(lib.pk_split3_bf16(_ptr(x, torch.float32), _ptr(out, torch.bfloat16), n, x.shape[-1], mode, _ptr(gamma, torch.float32),
                              _ptr(beta, torch.float32), float(eps), _ptr(rowscale, torch.float32), _ptr(row_index, torch.int32),
                              _ptr(rows_dev, torch.int32), _stream()), "pk_split3_bf16")
+    return out
+
+
+def split(x: torch.Tensor, out: torch.Tensor, terms: int, mode: int = SPLIT_NONE, gamma: Optional[torch.Tensor] = None,
+          beta: Optional[torch.Tensor] = None, eps: float = 0.0, rows: Optional[int] = None, rowscale: Optional[torch.Tensor] = None,
+          row_index: Optional[torch.Tensor] = None, rows_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``split3`` (terms == 3: out [rows, 6*dim]) or its two-term form (terms == 2: out [rows, 2*dim] = [lo | hi], read by
+    ``gemm(..., a_wrap_k=dim)``)."""
+    if terms == 3:
+        return split3(x, out, mode, gamma, beta, eps, rows, rowscale, row_index, rows_dev)
+    lib = _lib_for(x)
+    n = x.shape[0] if rows is None else rows
+    check(lib.pk_split2_bf16(_ptr(x, torch.float32), _ptr(out, torch.bfloat16), n, x.shape[-1], mode, _ptr(gamma, torch.float32),
+                             _ptr(beta, torch.float32), float(eps), _ptr(rowscale, torch.float32), _ptr(row_index, torch.int32),
+                             _ptr(rows_dev, torch.int32), _stream()), "pk_split2_bf16")
+    return out
+
+
+def split_weight(w: torch.Tensor, terms: int) -> torch.Tensor:
+    """Host-side prepack of an fp32 ``[N, K]`` weight for the split-operand GEMMs: three terms -> ``split3_weight``; two terms
+    -> [Wh | Wl | Wh] (bf16 [N, 3K]) against activations read as lo, hi, hi: the products lo*Wh, hi*Wl, hi*Wh, small first."""
+    if terms == 3:
+        return split3_weight(w)
+    w = w.detach().float()
+    h = w.to(torch.bfloat16)
+    l = (w - h.float()).to(torch.bfloat16)
+    return torch.cat([h, l, h], dim=1).contiguous()
+
+
+def split_width(terms: int) -> int:
+    """Width of a split activation row in units of the unsplit width (the GEMM's A operand)."""
+    return 6 if terms == 3 else 2
+
+
+def patchify_split(images: torch.Tensor, patch_size: int, out: torch.Tensor, terms: int) -> torch.Tensor:
+    """im2col straight into split rows: [m|l|h|m|h|h] (terms 3, 6*Kp wide) or [lo|hi|hi] (terms 2, 3*Kp wide, no wrap)."""
+    if terms == 3:
+        return patchify_split3(images, patch_size, out)
+    lib = _lib_for(images)
+    B, _, S, _ = images.shape
+    check(lib.pk_patchify_split2(_ptr(images, torch.float32), _ptr(out, torch.bfloat16), B, S, patch_size, _stream()), "pk_patchify_split2")
     return out
 
 

@@ -18,16 +18,23 @@ DEFAULT_MICRO_BATCH = int(os.environ.get("PEEKVIT_B200_MICRO_BATCH", "512"))
 # reference's shipped dtype: 3-way split operands on the same tcgen05 GEMMs + fp32 attention, logits within 1e-5, every family).
 # Per model: ``model.pk_precision = "fp32"``.
 DEFAULT_PRECISION = os.environ.get("PEEKVIT_B200_PRECISION", "bf16")
-PRECISIONS = ("bf16", "fp32")
+PRECISIONS = ("bf16", "fp32", "bf16x2")
+_TERMS = {"bf16": 0, "fp32": 3, "bf16x2": 2}
 # the split activation rows are 6x wider: the fp32 mode runs in smaller micro-batches (workspace 15 MB per image at ViT-B/16)
 EXACT_MICRO_BATCH = int(os.environ.get("PEEKVIT_B200_EXACT_MICRO_BATCH", "256"))
 
 
-def _exact(model) -> bool:
+def _terms(model) -> int:
+    """Operand terms of the model's arithmetic mode: 0 = bf16 operands, 3 = "fp32" (three-term split, fp32 attention),
+    2 = "bf16x2" (two-term split produced by the GEMM epilogues, IEEE-half tcgen05 attention)."""
     p = getattr(model, "pk_precision", DEFAULT_PRECISION)
     if p not in PRECISIONS:
         raise ValueError(f"pk_precision must be one of {PRECISIONS}, got {p!r}")
-    return p == "fp32"
+    return _TERMS[p]
+
+
+def _exact(model) -> bool:
+    return _terms(model) == 3
 
 
 def _state(model):
@@ -111,13 +118,11 @@ def _graphed(model, fwd: engine.Forward, chunk: torch.Tensor, aux: Optional[dict
         return None
     if any(lw.kind == "noise" for lw in fwd.pm.layers):      # fresh random draws (and host-side randperm) every forward
         return None
-    if fwd.exact:                                            # parity mode: eager launches
-        return None
     st = _state(model)
     graphs = st.setdefault("graphs", {})
     # The only kernel that reads the caller's image tensor is the im2col: it is launched eagerly into a workspace buffer,
     # and the graph (everything after it) is independent of where the images live.
-    key = (tuple(chunk.shape), id(fwd.pm), aux is not None, extra_key)
+    key = (tuple(chunk.shape), id(fwd.pm), aux is not None, extra_key, fwd.terms)
     hit = graphs.get(key)
     if hit is None:
         if len(graphs) >= _MAX_GRAPHS:
@@ -235,7 +240,7 @@ def run(model, x: torch.Tensor, aux: Optional[dict] = None) -> torch.Tensor:
             ops.raise_if_flagged(dev.index)        # watchdog state as of the last completed forward (no synchronisation)
         fwd = engine.Forward(packed(model), workspace(model, dev))
         fwd.input_norm = getattr(model, "pk_input_norm", fwd.input_norm)
-        fwd.exact = _exact(model)
+        fwd.terms = _terms(model)
         B = x.shape[0]
         mb = _micro_batch(model, B)
         multi = model._family == "eeresidualvit"        # (L + 1, B, C): one early exit per layer, then the final logits
@@ -287,7 +292,7 @@ def run_host(model, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = Non
         ws = workspace(model, dev)
         fwd = engine.Forward(packed(model), ws)
         fwd.input_norm = getattr(model, "pk_input_norm", fwd.input_norm)
-        fwd.exact = _exact(model)
+        fwd.terms = _terms(model)
         mb = min(_micro_batch(model, B), max(B, 1))
         st = _state(model)
         if "copy_stream" not in st:

@@ -33,12 +33,22 @@ CFG_C = dict(VITS, gate_type="sigmoid", gate_temp=1.0, gate_bias=0.0, gate_thres
              add_input=False, residual_layers=["attention+mlp"] * 12)
 CFG_E_AVIT = dict(VITS, eps=0.01, gate_scale=10, gate_center=30)
 SEED = 4321
+GATE_STD = 4.0       # wide token scores: the keep / drop decision varies token by token instead of sample by sample
+BT_GATE_SCALE = 0.05  # ... and a budget-token gate that does not saturate: its threshold stays near sigmoid(bias) for every sample
+                      # (the budget row grows layer after layer; at the constructor's scale its threshold is 0 or 1 per sample)
+
+
+def config_c_state_dict(seed=SEED, gate_std=GATE_STD, bt_gate_scale=BT_GATE_SCALE):
+    sd = ow.make_state_dict("residualvit", CFG_C, seed=seed, gate_std=gate_std)
+    for i in range(CFG_C["num_layers"]):
+        sd[f"encoder.layers.{i}.budget_token_gate.weight"] = sd[f"encoder.layers.{i}.budget_token_gate.weight"] * bt_gate_scale
+    return sd
 
 
 def main():
-    out = {"seed": SEED, "config_C": {}, "config_E_avit": {}}
-    sd0 = ow.make_state_dict("residualvit", CFG_C, seed=SEED)
-    probe = ow.synthetic_images(2, 224, seed=99)
+    out = {"seed": SEED, "gate_std": GATE_STD, "bt_gate_scale": BT_GATE_SCALE, "config_C": {}, "config_E_avit": {}}
+    sd0 = config_c_state_dict()
+    probe = ow.synthetic_images(8, 224, seed=99)
     for budget in (0.2, 0.4, 0.8, 1.0):
         sd = ow.calibrate_residual_gates(sd0, CFG_C, min(budget, 0.97), images=probe)
         out["config_C"][str(budget)] = [float(sd[f"encoder.layers.{i}.residual_gate.projection.bias"][0]) for i in range(12)]

@@ -6,8 +6,12 @@ eval over the GPUs of one box through ``peekvit_b200.evaluate.evaluate`` (SURVEY
 
 Every rank builds the same seeded weights, takes its contiguous slice of the same seeded images / labels
 (``sharding.shard_range``) and runs the eval loop; the only collectives are the all-reduce of the [correct, total] counts
-and of the pass time (maximum over ranks) inside ``evaluate``.  Labels are derived from each rank's own unsharded pass over the full batch (correct on even samples, wrong on odd), so the
-sharded count must be exactly half the batch; rank 0 prints one JSON object.
+and of the pass time (maximum over ranks) inside ``evaluate``.  Two checks: (1) against the CPU ORACLE: rank 0 runs the
+oracle forward on the first ``--oracle-images`` images, their arg-max is broadcast as the labels of those images, and a
+sharded evaluation of that slice must count them correct up to bf16 near-tie flips (``oracle_agreement``, asserted
+>= 0.95; with ``--precision bf16x2`` or ``fp32`` it is ~1.0); (2) sharding itself: for the whole batch, labels derived from
+each rank's own unsharded pass (correct on even samples, wrong on odd) must give exactly half the batch.  Rank 0 prints one
+JSON object.
 """
 from __future__ import annotations
 
@@ -35,6 +39,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--passes", type=int, default=5)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--oracle-images", type=int, default=128)
+    ap.add_argument("--precision", default="bf16")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
@@ -55,7 +61,20 @@ def main():
         m = build_model(name, cfg)
         m.load_state_dict(ow.make_state_dict(fam, cfg, seed=4321), strict=True)
         m = m.to(dev).eval()
-        # labels from this rank's own UNSHARDED pass over the full batch (runner.run has no collectives): the prediction for
+        m.pk_precision = args.precision
+        # (1) the CPU oracle's predictions for the first images are the labels of a sharded evaluation of that slice
+        K = min(args.oracle_images, B)
+        olab = torch.zeros(K, dtype=torch.long, device=dev)
+        if rank == 0:
+            from oracle import peekvit_oracle as po
+            sd = ow.make_state_dict(fam, cfg, seed=4321)
+            olab.copy_(torch.cat([po.forward(fam, sd, cfg, images[s:s + 32])[0] for s in range(0, K, 32)]).argmax(1).to(dev))
+        if world > 1:
+            dist.broadcast(olab, src=0)
+        klo, khi = sharding.shard_range(K, rank, world)
+        r = evaluate(m, [(images[klo:khi].to(dev), olab[klo:khi])], count_flops=False)[None]
+        oracle_agreement = r["accuracy"]
+        # (2) labels from this rank's own UNSHARDED pass over the full batch (runner.run has no collectives): the prediction for
         # even samples, a wrong class for odd ones.  The sharded eval must then count exactly B/2 correct -- on every rank's
         # shard -- or the sharded forward / count reduction differs from the unsharded one.
         full = runner.run(m, images.to(dev), None)
@@ -70,7 +89,8 @@ def main():
             best = r if best is None or r["images_per_second"] > best["images_per_second"] else best
         correct = round(best["accuracy"] * best["images"])
         entry = {"images_per_second": best["images_per_second"], "images": best["images"], "sharded_correct": correct,
-                 "expected_correct": (B + 1) // 2, "counts_agree": correct == (B + 1) // 2}
+                 "expected_correct": (B + 1) // 2, "counts_agree": correct == (B + 1) // 2,
+                 "oracle_images": K, "oracle_agreement": oracle_agreement, "oracle_ok": oracle_agreement >= 0.95}
         res[key] = entry
     flag = torch.tensor([ops.device_flag()], device=dev)
     if world > 1:
