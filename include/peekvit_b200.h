@@ -158,12 +158,17 @@ typedef struct pk_attention_args {
   const float* key_mult;    /* f32 [rows] or NULL */
   const void* extra_kv;     /* bf16 [2*D]: k-bias | v-bias, or NULL */
   const float* extra_mult;  /* f32 [batch] or NULL (<= 0 disables the virtual key for that sample) */
-  int impl;                 /* 0 = auto (tcgen05/TMEM kernel for uniform 64 < seq_len <= 256, head_dim 64, no
-                               multiplicities; general mma.sync kernel otherwise), 1 = general kernel, 2 = tcgen05 kernel */
+  int impl;                 /* 0 = auto: head_dim 64 runs on tcgen05/TMEM -- the dense kernel for uniform 64 < seq_len <= 256
+                               without multiplicities, the ragged kernel for cu_seqlens / multiplicities / the virtual key /
+                               short uniform sequences (<= 256 keys per sample) -- everything else on the general mma.sync
+                               kernel; 1 = general kernel, 2 = dense tcgen05 kernel, 3 = ragged tcgen05 kernel */
   /* bf16x2 arithmetic mode (tcgen05 kernel only, impl 0 / 2 on an eligible shape): qkv_format PK_OUT_F16 = q, k, v are IEEE
    * half (11 significant bits; the probabilities are packed as half too); out_format PK_OUT_BF16X2 = `out` is
    * [rows, 2*D] holding the fp32 result split into lo (column d) and hi (column D + d), both bf16. */
   int qkv_format, out_format;
+  int total_rows;           /* rows of the qkv / out buffers (the ragged tcgen05 kernel's 2-D tensor maps need the extent: a
+                               key tile that starts near the end of the buffer is zero-filled past it); 0 = unknown (the ragged
+                               kernel is then not used).  Rows of `qkv` past the live ones must hold finite values. */
 } pk_attention_args;
 
 int pk_attention_fwd(const pk_attention_args* args, void* stream);

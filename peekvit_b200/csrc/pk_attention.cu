@@ -312,6 +312,8 @@ attention_fwd_kernel(const AttParams p) {
 // pk_attention_tc.cu: tcgen05/TMEM kernel for uniform 128 < n <= 256, head_dim 64
 bool attention_tc_eligible(const pk_attention_args* a);
 int launch_attention_tc(const pk_attention_args* a, cudaStream_t stream);
+bool attention_tcr_eligible(const pk_attention_args* a);
+int launch_attention_tcr(const pk_attention_args* a, cudaStream_t stream);
 int attention_trace_copy(unsigned long long* host_dst);
 
 }  // namespace pk
@@ -325,6 +327,8 @@ extern "C" int pk_attention_fwd(const pk_attention_args* a, void* stream) {
   PK_REQUIRE((a->extra_kv == nullptr) == (a->extra_mult == nullptr), "pk_attention_fwd: extra_kv and extra_mult go together");
   if (a->batch == 0 || a->max_seq_len == 0) return PK_OK;
   if (attention_tc_eligible(a)) return launch_attention_tc(a, static_cast<cudaStream_t>(stream));
+  if (attention_tcr_eligible(a)) return launch_attention_tcr(a, static_cast<cudaStream_t>(stream));
+  PK_REQUIRE(a->impl != 3, "pk_attention_fwd: the ragged tcgen05 kernel needs head_dim 64, <= 256 keys per sample, 16-byte aligned buffers and total_rows");
   PK_REQUIRE(a->qkv_format == PK_OUT_BF16 && a->out_format == PK_OUT_BF16,
              "pk_attention_fwd: half operands / split output exist on the tcgen05 kernel only (uniform 16 < seq_len <= 224, head_dim 64)");
   PK_REQUIRE(a->impl != 2, "pk_attention_fwd: the tcgen05 kernel needs uniform 128 < seq_len <= 256, head_dim 64, no key multiplicities");

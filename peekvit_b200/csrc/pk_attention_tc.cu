@@ -1095,8 +1095,10 @@ attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const uint32_t qph = (kk >> 1) & 1u, vph = (kk / 3) & 1u, rph = qph;
       if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&qk_ready[qs]), qph, p.flag, 0x3200u + qs))) break;
       if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&s_free[r]), rph ^ 1u, p.flag, 0x3300u + r))) break;
-      if (first && r == 1) {      // start half a period after region 0: the two softmax groups then use the MUFU alternately
-        if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&p_ready[0]), 0u, p.flag, 0x3310u))) break;
+      if (first && r == 1) {
+        // start half a period after region 0 (the two softmax groups then use the MUFU alternately).  A scheduling hint, not a
+        // dependency: bounded polling, because region 0 may legitimately be two phases ahead by the time this warp looks
+        for (int i = 0; i < 4096 && !mbar_try_wait(smem_u32(&p_ready[0]), 0u); ++i) {}
       }
       first = false;
       tcgen05_fence_after();
@@ -1293,20 +1295,18 @@ attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s_free[r]));     // the region may take its next unit's S
       if (!has_rows) continue;
-      uint4 c8[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      auto chunk = [&](int c) {                             // 8 scaled bf16 values = 16-byte chunk c of this thread's row
         const uint32_t* src = c < 4 ? &o0[8 * c] : &o[8 * (c - 4)];
-        c8[c] = make_uint4(pack_bf16(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv),
-                           pack_bf16(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv),
-                           pack_bf16(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv),
-                           pack_bf16(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv));
-      }
+        return make_uint4(pack_bf16(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv),
+                          pack_bf16(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv),
+                          pack_bf16(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv),
+                          pack_bf16(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv));
+      };
       if (full) {
         if (lane == 0) bulk_wait_read<0>();                 // the previous store has drained this staging tile
         __syncwarp();
 #pragma unroll
-        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) = c8[c];
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) = chunk(c);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -1317,7 +1317,7 @@ attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         // the block that straddles the end of the sample: the rows after it are the next sample's
         uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<long long>(t.row0 + lrow0 + lane) * D + t.h * kTcDH);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) dst[c] = c8[c];
+        for (int c = 0; c < 8; ++c) dst[c] = chunk(c);
       }
     }
     if (lane == 0) bulk_wait_read<0>();       // smem must outlive the last store's reads
@@ -1356,7 +1356,7 @@ int attention_trace_copy(unsigned long long* host_dst) {
 }
 
 bool attention_tc_eligible(const pk_attention_args* a) {
-  if (a->impl == 1) return false;
+  if (a->impl == 1 || a->impl == 3) return false;
   if (a->cu_seqlens || a->key_mult || a->extra_kv || a->extra_mult) return false;
   if (a->head_dim != kTcDH) return false;
   const bool x2 = a->qkv_format == PK_OUT_F16 || a->out_format == PK_OUT_BF16X2;
@@ -1485,6 +1485,85 @@ int launch_attention_tc(const pk_attention_args* a, cudaStream_t stream) {
       return PK_ERR_INVALID;
   }
   return check_cuda(cudaGetLastError(), "attention_tc_kernel launch");
+}
+
+// ---------------------------------------------------------------------------------------------------- ragged kernel launch
+// Eligible: head_dim 64 and at most 256 keys per sample (longest sample + the virtual key); ragged (cu_seqlens), with key
+// multiplicities / a virtual key, or uniform sequences the dense kernels do not take (seq_len <= 64).  PK_ATT_TCR=0 routes
+// everything back to the general mma.sync kernel (A/B runs).
+static int tcr_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PK_ATT_TCR"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
+}
+// PK_ATT_TCR_UNIFORM_MAX: longest UNIFORM plain sequence routed to the ragged kernel instead of the general one (default 64:
+// the dense tc3 kernel takes 65 .. 256)
+static int tcr_uniform_max() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PK_ATT_TCR_UNIFORM_MAX"); v = e ? atoi(e) : 64; }
+  return v;
+}
+bool attention_tcr_eligible(const pk_attention_args* a) {
+  if (a->impl == 1 || !tcr_enabled()) return false;
+  if (a->head_dim != kTcDH) return false;
+  if (a->qkv_format != PK_OUT_BF16 || a->out_format != PK_OUT_BF16) return false;
+  const bool ragged = a->cu_seqlens || a->key_mult || a->extra_kv;
+  const int max_len = a->cu_seqlens ? a->max_seq_len : a->seq_len;
+  if (max_len < 1 || max_len + (a->extra_kv ? 1 : 0) > 256) return false;
+  if (!ragged && max_len > tcr_uniform_max() && a->impl != 3) return false;
+  if ((reinterpret_cast<uintptr_t>(a->qkv) & 15) != 0 || (reinterpret_cast<uintptr_t>(a->out) & 15) != 0) return false;
+  if (a->extra_kv && (reinterpret_cast<uintptr_t>(a->extra_kv) & 15) != 0) return false;
+  return a->total_rows > 0;
+}
+
+template <int NMAX>
+static int launch_tcr(const pk_attention_args* a, cudaStream_t stream, int max_len) {
+  const int D = a->num_heads * kTcDH;
+  const uint64_t rows = static_cast<uint64_t>(a->total_rows);
+  int box_small = ((NMAX / 2) + 15) & ~15;
+  if (box_small < 16) box_small = 16;
+  CUtensorMap tq, tks, tkf, tout;
+  int rc = make_tmap_bf16_2d(&tq, a->qkv, rows, 3ull * D, 3ull * D, 128, 64);
+  if (rc != PK_OK) return rc;
+  rc = make_tmap_bf16_2d(&tks, a->qkv, rows, 3ull * D, 3ull * D, static_cast<uint32_t>(box_small), 64);
+  if (rc != PK_OK) return rc;
+  rc = make_tmap_bf16_2d(&tkf, a->qkv, rows, 3ull * D, 3ull * D, NMAX, 64);
+  if (rc != PK_OK) return rc;
+  rc = make_tmap_bf16_2d(&tout, a->out, rows, static_cast<uint64_t>(D), static_cast<uint64_t>(D), 32, 64);
+  if (rc != PK_OK) return rc;
+  TcrParams p;
+  p.cu_seqlens = a->cu_seqlens;
+  p.key_mult = a->key_mult;
+  p.extra_kv = static_cast<const __nv_bfloat16*>(a->extra_kv);
+  p.extra_mult = a->extra_mult;
+  p.out = static_cast<__nv_bfloat16*>(a->out);
+  p.batch = a->batch;
+  p.num_heads = a->num_heads;
+  p.seq_len = a->seq_len;
+  p.q_tiles = (max_len + 127) / 128;
+  p.box_small = box_small;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.flag = device_flag_ptr();
+  const long long units = static_cast<long long>(a->batch) * a->num_heads * p.q_tiles;
+  int grid = num_sms();
+  if (units < grid) grid = static_cast<int>(units);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PK_CHECK_CUDA(cudaFuncSetAttribute(attention_tcr_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcrSmem<NMAX>::kBytes));
+    attr_set = true;
+  }
+  attention_tcr_kernel<NMAX><<<grid, kTcrThreads, TcrSmem<NMAX>::kBytes, stream>>>(tq, tks, tkf, tout, p);
+  return check_cuda(cudaGetLastError(), "attention_tcr_kernel launch");
+}
+
+int launch_attention_tcr(const pk_attention_args* a, cudaStream_t stream) {
+  const int max_len = a->cu_seqlens ? a->max_seq_len : a->seq_len;
+  const int need = (max_len + (a->extra_kv ? 1 : 0) + 15) & ~15;
+  if (need <= 32) return launch_tcr<32>(a, stream, max_len);
+  if (need <= 64) return launch_tcr<64>(a, stream, max_len);
+  if (need <= 128) return launch_tcr<128>(a, stream, max_len);
+  if (need <= 208) return launch_tcr<208>(a, stream, max_len);
+  return launch_tcr<256>(a, stream, max_len);
 }
 
 }  // namespace pk

@@ -296,11 +296,13 @@ class Workspace:
         self.device = device
         self._bufs: Dict[tuple, torch.Tensor] = {}
 
-    def get(self, name: str, shape: Sequence[int], dtype) -> torch.Tensor:
+    def get(self, name: str, shape: Sequence[int], dtype, zero: bool = False) -> torch.Tensor:
+        """``zero``: cleared when first allocated (buffers whose rows past the live ones are read -- and masked -- by a kernel
+        must hold finite values there: 0 x NaN is NaN)."""
         key = (name, tuple(shape), dtype)
         t = self._bufs.get(key)
         if t is None:
-            t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+            t = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
             self._bufs[key] = t
         return t
 
@@ -438,7 +440,8 @@ class Forward:
         aw = lw.attn[0]
         a = ops.layernorm(x, lw.ln1_w, lw.ln1_b, lw.eps, ws.get("ln", (rows, D), torch.bfloat16), rows=rows, rowscale=rowscale,
                           rows_dev=rows_dev)
-        qkv = ops.gemm(a, aw.w_qkv, aw.b_qkv, ws.get("qkv", (rows, 3 * D), torch.bfloat16), PK_EPI_BIAS_BF16, m_dev=rows_dev)
+        # zeroed once: the ragged tcgen05 attention loads fixed-size key tiles, i.e. also rows past the live ones (masked)
+        qkv = ops.gemm(a, aw.w_qkv, aw.b_qkv, ws.get("qkv", (rows, 3 * D), torch.bfloat16, zero=True), PK_EPI_BIAS_BF16, m_dev=rows_dev)
         att = ops.attention(qkv, ws.get("att", (rows, D), torch.bfloat16), batch, pm.heads, D // pm.heads, seq_len=seq,
                             cu_seqlens=cu, max_seq_len=max_len, key_mult=key_mult,
                             extra_kv=aw.bias_kv if extra_mult is not None else None, extra_mult=extra_mult)
@@ -588,7 +591,7 @@ class Forward:
         D = pm.dim
         aw, mw, f = lw.attn[0], lw.mlp[0], lw.extra["fold"]
         F = mw.w_fc1.shape[0]
-        qkv = ops.gemm(xb, f["w_qkv"], f["c2_qkv"], ws.get("qkv", (rows, 3 * D), torch.bfloat16), PK_EPI_BIAS_BF16,
+        qkv = ops.gemm(xb, f["w_qkv"], f["c2_qkv"], ws.get("qkv", (rows, 3 * D), torch.bfloat16, zero=True), PK_EPI_BIAS_BF16,
                        ln_stats=stats, ln_c1=f["c1_qkv"], ln_dim=D, ln_eps=lw.eps)
         att = ops.attention(qkv, ws.get("att", (rows, D), torch.bfloat16), batch, pm.heads, D // pm.heads, seq_len=seq)
         if LN_FOLD >= 2:
@@ -893,7 +896,7 @@ class Forward:
                                               out_scale=onehot[e], a6=a6)
                 a = None if self.exact else ops.layernorm(x, lw.ln1_w, lw.ln1_b, lw.eps, ws.get("ln", (rows, D), torch.bfloat16), rows=rows)
                 for e, aw in enumerate(() if self.exact else lw.attn):
-                    qkv = ops.gemm(a, aw.w_qkv, aw.b_qkv, ws.get("qkv", (rows, 3 * D), torch.bfloat16), PK_EPI_BIAS_BF16)
+                    qkv = ops.gemm(a, aw.w_qkv, aw.b_qkv, ws.get("qkv", (rows, 3 * D), torch.bfloat16, zero=True), PK_EPI_BIAS_BF16)
                     att = ops.attention(qkv, ws.get("att", (rows, D), torch.bfloat16), B, pm.heads, D // pm.heads, seq_len=seq)
                     ops.gemm(att, aw.w_o, aw.b_o, x, PK_EPI_BIAS_RESID_F32, resid=x, rowscale=onehot[e])
                 if aux is not None:

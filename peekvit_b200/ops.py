@@ -195,6 +195,7 @@ def attention(qkv: torch.Tensor, out: torch.Tensor, batch: int, num_heads: int, 
     a.extra_kv = _ptr(extra_kv, torch.bfloat16)
     a.extra_mult = _ptr(extra_mult, torch.float32)
     a.impl = impl
+    a.total_rows = qkv.shape[0]
     check(lib.pk_attention_fwd(C.byref(a), _stream()), "pk_attention_fwd")
     return out
 

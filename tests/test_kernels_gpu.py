@@ -638,3 +638,74 @@ def test_head_as_split_gemm_matches_fused_head(ops):
     cu = (torch.arange(B + 1, device=DEV, dtype=torch.int32) * seq)
     feat2 = ops.cls_features(x, B, 0, T, g, b, 1e-5, torch.empty(B, D, device=DEV), cu_seqlens=cu)
     assert torch.equal(feat, feat2)
+
+
+# ------------------------------------------------------------------ ragged tcgen05 attention (csrc/pk_attention_tc.cu, "tcr")
+def _ragged_case(lens, H, seed, with_mult, with_extra, pad_rows=0):
+    dh, D = 64, H * 64
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    rows = sum(lens)
+    qkv = torch.zeros(rows + pad_rows, 3 * D, device=DEV, dtype=torch.bfloat16)
+    qkv[:rows] = (torch.randn(rows, 3 * D, device=DEV, generator=g) * 1.2).to(torch.bfloat16)
+    cu = torch.tensor([0] + torch.tensor(lens).cumsum(0).tolist(), device=DEV, dtype=torch.int32)
+    km = ekv = em = None
+    if with_mult:
+        km = torch.randint(1, 60, (rows + pad_rows,), device=DEV, generator=g).float()
+        km[torch.rand(rows + pad_rows, device=DEV, generator=g) < 0.7] = 1.0          # mostly plain keys, like the ghost-row layout
+    if with_extra:
+        ekv = (torch.randn(2 * D, device=DEV, generator=g) * 0.5).to(torch.bfloat16)
+        em = torch.randint(0, 150, (len(lens),), device=DEV, generator=g).float()
+        em[::3] = 0.0
+    return qkv, cu, km, ekv, em, rows
+
+
+@pytest.mark.parametrize("with_mult,with_extra", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("lens", [[3, 70, 198, 1, 129, 64], [199, 199, 16, 17, 31, 32, 33, 127, 128, 1], [255, 200, 130, 5], [12] * 9,
+                                  [80, 77, 91, 64, 85, 79, 102, 60, 66, 71, 93, 88]])
+def test_attention_ragged_tcgen05_against_reference(ops, lens, with_mult, with_extra):
+    """impl=3 forces the ragged tcgen05 kernel: samples of unequal length (one or two 128-query tiles, key counts on both sides
+    of every 16-key group boundary), per-key multiplicities, the virtual bias key, rows of the buffer past the live ones; rows
+    past the live ones stay untouched.  Compared with the fp32 reference and with the general mma.sync kernel (impl=1)."""
+    B, H, dh = len(lens), 6, 64
+    D = H * dh
+    if max(lens) + (1 if with_extra else 0) > 256:
+        pytest.skip("more than 256 keys")
+    qkv, cu, km, ekv, em, rows = _ragged_case(lens, H, 7 * sum(lens) + with_mult + 2 * with_extra, with_mult, with_extra, pad_rows=40)
+    out = torch.full((rows + 40, D), 3.0, device=DEV, dtype=torch.bfloat16)
+    ops.attention(qkv, out, B, H, dh, cu_seqlens=cu, max_seq_len=max(lens), key_mult=km, extra_kv=ekv, extra_mult=em, impl=3)
+    assert ops.device_flag() == 0
+    ref = ref_attention(qkv[:rows], B, H, dh, lens, km[:rows] if km is not None else None, ekv, em)
+    assert rel_err(out[:rows], ref) < TOL_BF16
+    assert bool((out[rows:] == 3.0).all())
+    out1 = torch.zeros_like(out)
+    ops.attention(qkv, out1, B, H, dh, cu_seqlens=cu, max_seq_len=max(lens), key_mult=km, extra_kv=ekv, extra_mult=em, impl=1)
+    assert rel_err(out[:rows], out1[:rows]) < TOL_BF16
+
+
+@pytest.mark.parametrize("N", [1, 5, 14, 17, 26, 33, 50, 64, 99, 128, 129, 197, 256])
+def test_attention_ragged_tcgen05_uniform_lengths(ops, N):
+    """The same kernel on uniform samples (what the pruned RankViT layers run: 5 / 14 / 26 / 50 tokens)."""
+    B, H, dh = 7, 12, 64
+    D = H * dh
+    qkv = (torch.randn(B * N, 3 * D, device=DEV) * 1.5).to(torch.bfloat16)
+    out = torch.full((B * N, D), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.attention(qkv, out, B, H, dh, seq_len=N, impl=3)
+    assert ops.device_flag() == 0
+    assert rel_err(out, ref_attention(qkv, B, H, dh, [N] * B)) < TOL_BF16
+
+
+def test_attention_ragged_tcgen05_full_size_row_sum_property(ops):
+    """ResidualViT-S at budget 0.4 size (512 images x 6 heads, ~80 live rows each, multiplicities and virtual keys): with
+    V = ones and a virtual value of ones every output element is exactly 1, whatever Q, K and the multiplicities are."""
+    B, H, dh = 512, 6, 64
+    D = H * dh
+    g = torch.Generator().manual_seed(3)
+    lens = torch.randint(20, 200, (B,), generator=g).tolist()
+    qkv, cu, km, ekv, em, rows = _ragged_case(lens, H, 11, True, True, pad_rows=300)
+    qkv[:, 2 * D:] = 1.0
+    ekv[D:] = 1.0
+    out = torch.zeros(rows + 300, D, device=DEV, dtype=torch.bfloat16)
+    ops.attention(qkv, out, B, H, dh, cu_seqlens=cu, max_seq_len=max(lens), key_mult=km, extra_kv=ekv, extra_mult=em, impl=3)
+    assert ops.device_flag() == 0
+    assert float((out[:rows].float() - 1.0).abs().max()) < 1e-2
+    assert bool((out[rows:] == 0).all())
