@@ -293,6 +293,11 @@ int pk_noise_snr(float* x, const float* noise, int rows, int dim, float snr_db, 
  * (the same randperm prefix for the whole batch). */
 int pk_zero_token_rows(float* x, int batch, int seq, const int* tokens, int n_tokens, int dim, void* stream);
 
+/* Masked row arithmetic of the dense-layout ResidualViT modes (models/residualvit.py:130-194 forward_skip_attention /
+ * forward_skip_mlp, :239-242 add_input): out[r,:] = (accumulate ? out[r,:] : 0) + w(r) * a[r,:] with w(r) = scale[r], or
+ * 1 - scale[r] when one_minus -- ``mask * img_tokens`` and ``img_tokens * (1 - mask)``.  out may alias a when !accumulate. */
+int pk_row_scale_add(float* out, const float* a, const float* scale, int rows, int dim, int one_minus, int accumulate, void* stream);
+
 /* ---- fp32-accurate mode (the reference's shipped dtype; north star: logits within 1e-5).  GEMMs run on the same bf16
  * tcgen05 kernels with 3-way split operands: x = h + m + l in bf16, products {mm, lh, hl, mh, hm, hh} laid along K' = 6K,
  * small terms first.  pk_split3_bf16 writes the ACTIVATION-side row [m|l|h|m|h|h] (out bf16 [rows, 6*dim]) of x f32 [rows, dim],

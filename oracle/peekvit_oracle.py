@@ -218,15 +218,21 @@ def _residual_plain(x: Tensor, sd, lp: str, H: int, mask: Union[Tensor, float]) 
 
 
 def residualvit_forward(sd, cfg, images: Tensor, budget: float, stop_after_layer: Optional[int] = None,
-                        early_exits: Optional[List[Tensor]] = None) -> Tuple[Tensor, Dict]:
+                        early_exits: Optional[List[Tensor]] = None, noise: Optional[Dict] = None,
+                        forced_masks: Optional[Dict[int, Tensor]] = None) -> Tuple[Tensor, Dict]:
     """``ResidualVisionTransformer.forward`` in eval (reference residualvit.py:587-616):
     budget token built by ``_add_budget_token`` (:552-585) and appended last; encoder adds
     ``pos_embedding`` to all but the budget token (:335-348); blocks dispatch on ``skip``
-    (:263-273); only ``'attention+mlp'`` (:197-244) and ``None``/``'none'`` (plain) are
-    restated — the modes every shipped config uses."""
+    (:263-273): ``'attention+mlp'`` (:197-244), ``'attention'`` (:130-157), ``'mlp'`` (:160-194), ``None``/``'none'``
+    (plain).  Tensor shapes follow the reference literally, so the combinations it cannot run (``'attention'`` with a
+    budget token, ``add_input`` with a budget token, ``'attention+mlp'`` without one) fail here with the same shape
+    errors.  ``noise`` describes a NoiseBlock spliced in front of block ``noise['layer']`` (utils/utils.py:162-191).
+    ``forced_masks`` (test aid, like ``moevit_forward``'s forced routing): gate values to use instead of the computed ones, so a
+    path whose hard 0/1 gumbel decisions flipped at a near-tie can be checked given identical decisions."""
     abt = cfg.get("add_budget_token", False)
     L, H, D = cfg["num_layers"], cfg["num_heads"], cfg["hidden_dim"]
     skips = cfg.get("residual_layers") or ["attention+mlp"] * L
+    add_input = cfg.get("add_input", False)
     x = _tokens(images, sd, cfg)
     n, dt = x.shape[0], x.dtype
     x = x + sd["encoder.pos_embedding"].to(dt)
@@ -241,11 +247,15 @@ def residualvit_forward(sd, cfg, images: Tensor, budget: float, stop_after_layer
             bt = torch.full((n, 1, D), float(budget), dtype=dt)                          # :581-583
         x = torch.cat([x, bt], dim=1)
     aux = {"masks": {}, "thresholds": {}}
+    ln = lambda t, lp, k: layer_norm(t, sd[f"{lp}.{k}.weight"], sd[f"{lp}.{k}.bias"], 1e-6)
     for i in range(L):
+        if noise is not None and noise["layer"] == i:
+            x = noise_block(x, noise)
         lp = f"encoder.layers.{i}"
         skip = skips[i]
+        # the model builds its encoder without num_class_tokens / num_registers (:452-467): blocks see ONE special token
         if skip == "attention+mlp":
-            special, img = x[:, :1], x[:, 1:]            # num_special_tokens is always 1 (:200-201)
+            special, img = x[:, :1], x[:, 1:]
             cur_b = thr = None
             if abt:
                 btok, img = img[:, -1:], img[:, :-1]
@@ -256,19 +266,50 @@ def residualvit_forward(sd, cfg, images: Tensor, budget: float, stop_after_layer
                 cur_b = None
                 aux["thresholds"][i] = thr
             mask = residual_gate(img, sd, lp, cfg, budget=cur_b, threshold=thr)          # :217
+            if forced_masks is not None:
+                mask = forced_masks[i].to(dt)
             aux["masks"][i] = mask
             parts = [special, mask * img]
-            fm = [torch.ones(n, 1, 1, dtype=dt), mask]
             if abt:
                 parts.append(btok)
-            fm.append(torch.ones(n, 1, 1, dtype=dt))      # :230-235 hard-codes cls + one trailing token
-            x = _residual_plain(torch.cat(parts, dim=1), sd, lp, H, torch.cat(fm, dim=1))
-            if cfg.get("add_input", False):
-                x = x + torch.cat([torch.zeros_like(special), img * (1 - mask)] + ([torch.zeros_like(btok)] if abt else []), dim=1)
+            fm = torch.cat([torch.ones(n, 1, 1, dtype=dt), mask, torch.ones(n, 1, 1, dtype=dt)], dim=1)   # :230-235
+            y = _residual_plain(torch.cat(parts, dim=1), sd, lp, H, fm)
+            if add_input:
+                y = y + torch.cat([torch.zeros_like(special), img * (1 - mask)], dim=1)  # :239-242
+            x = y
+        elif skip == "attention":
+            special, img = x[:, :1], x[:, 1:]
+            cur_b = None
+            if abt:
+                btok, img = img[:, -1:], img[:, :-1]
+                cur_b = btok.mean()                                                       # :142
+            mask = residual_gate(img, sd, lp, cfg, budget=cur_b)
+            if forced_masks is not None:
+                mask = forced_masks[i].to(dt)
+            aux["masks"][i] = mask
+            mi = torch.cat([special, mask * img], dim=1)                                  # :145-148 (the budget token is not put back)
+            x1 = mha(ln(mi, lp, "ln_1"), sd, lp + ".self_attention.self_attention", H) + x   # :150-153
+            x = mlp(ln(x1, lp, "ln_2"), sd, lp + ".mlp")                                  # :155-157: no residual around the MLP
+        elif skip == "mlp":
+            x1 = mha(ln(x, lp, "ln_1"), sd, lp + ".self_attention.self_attention", H) + x    # :162-165
+            special, img = x1[:, :1], x1[:, 1:]
+            cur_b = None
+            if abt:
+                btok, img = img[:, -1:], img[:, :-1]
+                cur_b = btok.mean()                                                       # :177
+            mask = residual_gate(img, sd, lp, cfg, budget=cur_b)
+            if forced_masks is not None:
+                mask = forced_masks[i].to(dt)
+            aux["masks"][i] = mask
+            parts = [special, mask * img] + ([btok] if abt else [])
+            y = mlp(ln(torch.cat(parts, dim=1), lp, "ln_2"), sd, lp + ".mlp")             # :186-187: no residual
+            if add_input:
+                y = y + torch.cat([torch.zeros_like(special), img * (1 - mask)], dim=1)   # :189-192
+            x = y
         elif skip in (None, "none"):
             x = _residual_plain(x, sd, lp, H, 1.0)
         else:
-            raise NotImplementedError(f"skip mode {skip!r} is outside the hot-path scope (SURVEY.md §8 f3)")
+            raise ValueError(f"unknown skip mode {skip!r}")
         if stop_after_layer is not None and i == stop_after_layer:
             return x, aux
         if early_exits is not None:

@@ -127,6 +127,7 @@ SIGNATURES: Dict[str, tuple] = {
     "pk_patchify_split2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pk_attention_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pk_noise_snr": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
+    "pk_row_scale_add": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "pk_zero_token_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "pk_moe_route": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -493,6 +493,37 @@ extern "C" int pk_zero_token_rows(float* x, int batch, int seq, const int* token
   return check_cuda(cudaGetLastError(), "zero_token_rows_kernel");
 }
 
+// Masked row arithmetic of the dense-layout ResidualViT modes (residualvit.py:130-194, :239-242):
+//   out[r,:] = (accumulate ? out[r,:] : 0) + w(r) * a[r,:],   w(r) = scale[r] or 1 - scale[r]
+// i.e. ``mask * img_tokens`` and the add_input term ``img_tokens * (1 - mask)``; out may alias a when !accumulate.
+__global__ void row_scale_add_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ scale, int rows,
+                                     int dim, int one_minus, int accumulate) {
+  const int d4 = dim / 4;
+  const long long total = static_cast<long long>(rows) * d4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / d4;
+    const float s = scale[r];
+    const float w = one_minus ? 1.0f - s : s;
+    const float4 v = reinterpret_cast<const float4*>(a)[i];
+    float4 o = make_float4(w * v.x, w * v.y, w * v.z, w * v.w);
+    if (accumulate) {
+      const float4 p = reinterpret_cast<const float4*>(out)[i];
+      o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+}
+
+extern "C" int pk_row_scale_add(float* out, const float* a, const float* scale, int rows, int dim, int one_minus, int accumulate,
+                                void* stream) {
+  PK_REQUIRE(out && a && scale && rows >= 0 && dim > 0 && dim % 4 == 0, "pk_row_scale_add: bad arguments");
+  if (rows == 0) return PK_OK;
+  const long long total = static_cast<long long>(rows) * (dim / 4);
+  row_scale_add_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, a, scale, rows, dim, one_minus, accumulate);
+  return check_cuda(cudaGetLastError(), "row_scale_add_kernel");
+}
+
 extern "C" int pk_fill_token_rows(float* x, int batch, int seq_stride, int row_offset, int n_tokens, int dim,
                                   const float* tokens, const float* pos, float scale, void* stream) {
   PK_REQUIRE(x && dim % 4 == 0, "pk_fill_token_rows: null x or dim %% 4 != 0");

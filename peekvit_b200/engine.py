@@ -147,13 +147,26 @@ def draw_noise(pm: "PackedModel", batch: int, device, budgets: Optional[Dict[int
     (B, N, D) tensor, and it is made even at 0 dB (blocks.py:129) so that the generator state stays aligned with the reference."""
     draws: Dict[int, tuple] = {}
     seq = pm.seq_len
+    # ResidualViT: the reference's budget token is the LAST token of the sequence (residualvit.py:572-583); the dense row layout
+    # keeps it at local row 1 (Forward.residualvit_dense), so draws made in the reference's token order are permuted
+    budget_last = pm.family == "residualvit" and bool(pm.extra.get("add_budget_token"))
+    if budget_last:
+        seq += 1
     for i, lw in enumerate(pm.layers):
         if lw.kind == "rank" and budgets is not None:
             b = budgets.get(i, 1.0)
             if b != 1:
                 seq = min(max(math.ceil((seq - 1) * b), 0), seq - 1) + 1
         if lw.kind == "noise":
-            draws[i] = draw_block_noise(lw.module, batch, seq, pm.dim, device)
+            kind, val, db = draw_block_noise(lw.module, batch, seq, pm.dim, device)
+            if budget_last and val is not None:
+                if kind == "snr":
+                    order = torch.tensor([0, seq - 1] + list(range(1, seq - 1)), device=device)     # layout row -> reference token
+                    val = val[:, order].contiguous()
+                else:
+                    v = val.long()
+                    val = torch.where(v == 0, v, torch.where(v == seq - 1, torch.ones_like(v), v + 1)).to(torch.int32)
+            draws[i] = (kind, val, db)
     return draws
 
 
@@ -193,9 +206,10 @@ def pack_model(model, family: str) -> PackedModel:
     for blk in model.encoder.layers:
         kind = _block_kind(blk)
         if kind == "noise":
-            if family not in ("vit", "rankvit", "moevit"):
-                # the compacted ResidualViT / A-ViT row layouts do not materialise dropped rows, which independent per-row
-                # noise would make distinct (and the reference's A-ViT loop cannot run a NoiseBlock either, adavit.py:170-176)
+            if family not in ("vit", "rankvit", "moevit", "residualvit", "eeresidualvit"):
+                # the compacted A-ViT row layout does not materialise halted rows, which independent per-row noise would make
+                # distinct -- and the reference's A-ViT loop cannot run a NoiseBlock either (adavit.py:170-176).  A ResidualViT
+                # encoder with a NoiseBlock runs on the dense (masked, uncompacted) row layout instead.
                 raise NotImplementedError(f"NoiseBlock inside a {family} encoder is not supported on the B200 path")
             layers.append(LayerWeights("noise", None, None, None, None, 0.0, [], [], {}, blk))
             continue
@@ -219,14 +233,12 @@ def pack_model(model, family: str) -> PackedModel:
             extra = {}
         if kind == "residual":
             extra["skip"] = blk.skip
-            if blk.skip in ("attention", "mlp"):
-                raise NotImplementedError(f"ResidualViT skip mode {blk.skip!r} is a 'next' row (SURVEY.md §8 f3)")
-            if blk.skip == "attention+mlp":
+            if blk.skip in ("attention", "mlp", "attention+mlp"):
                 g = blk.residual_gate
                 extra.update(gate_w=_f32(g.projection.weight).reshape(-1), gate_b=float(g.projection.bias.detach().float().cpu()[0]),
                              gate_type=g.gate_type, gate_temp=float(g.temp), gate_bias=float(g.sigmoid_bias),
                              gate_threshold=g.threshold, budget_token=blk.budget_token, add_input=bool(blk.add_input))
-                if blk.budget_token == "learnable":
+                if blk.budget_token == "learnable" and blk.skip == "attention+mlp":     # the one mode that reads it (:212)
                     extra["bt_gate_w"] = _f32(blk.budget_token_gate.weight).reshape(-1)
                     extra["bt_gate_b"] = float(blk.budget_token_gate.bias.detach().float().cpu()[0])
         if kind == "avit":
@@ -259,17 +271,22 @@ def pack_model(model, family: str) -> PackedModel:
     elif family == "residualvit":
         pm.extra["add_budget_token"] = model.add_budget_token
     if family == "residualvit":
-        if pm.n_cls != 1:
-            raise NotImplementedError("the B200 ResidualViT path supports num_class_tokens == 1 (all shipped configs)")
         model_abt = pm.extra["add_budget_token"]
+        gated = [lw for lw in pm.layers if lw.extra.get("skip") in ("attention", "mlp", "attention+mlp")]
+        # Compacted rows (dropped tokens leave the batch) need every gated layer to be the shipped 'attention+mlp' block with
+        # one class token and no add_input; everything else the reference can run -- the 'attention' / 'mlp' skip modes
+        # (residualvit.py:130-194), add_input (:189-192), several class tokens, a NoiseBlock between the blocks -- makes
+        # dropped rows distinct again (or readable by the head) and runs on the dense masked layout (Forward.residualvit_dense).
+        pm.extra["dense_layout"] = bool(
+            any(lw.kind == "noise" for lw in pm.layers)
+            or any(lw.extra["skip"] != "attention+mlp" or lw.extra["add_input"] for lw in gated)
+            or (gated and pm.n_cls != 1))            # further class tokens are gated like image tokens but read by the head
         if model_abt in ("learnable", "learnable_interpolate"):
             pm.extra["budget_token_1"] = _f32(model.learnable_budget_token_1.reshape(1, D))
         if model_abt == "learnable_interpolate":
             pm.extra["budget_token_2"] = _f32(model.learnable_budget_token_2.reshape(1, D))
         for lw in pm.layers:
-            if lw.extra.get("skip") == "attention+mlp":
-                if lw.extra["add_input"]:
-                    raise NotImplementedError("add_input=True (residualvit.py:239-242) is a 'next' row (SURVEY.md §8 f3)")
+            if lw.extra.get("skip") == "attention+mlp" and not pm.extra["dense_layout"]:
                 blk = lw.module
                 # what a dropped (zero) row equals when it leaves the block: fc2(gelu(fc1.bias)) + fc2.bias
                 h = torch.nn.functional.gelu(blk.mlp.fc1.bias.detach().float())
@@ -447,10 +464,11 @@ class Forward:
                             extra_kv=aw.bias_kv if extra_mult is not None else None, extra_mult=extra_mult)
         ops.gemm(att, aw.w_o, aw.b_o, x[:rows], PK_EPI_BIAS_RESID_F32, resid=x[:rows], rowscale=rowscale, m_dev=rows_dev)
 
-    def mlp_part(self, x, lw: LayerWeights, rows: int, *, rows_dev=None, rowscale=None) -> None:
-        """x += fc2(gelu(fc1(rowscale * LN2(x))))  (vit.py:53-55; residualvit.py:258-260)."""
+    def mlp_part(self, x, lw: LayerWeights, rows: int, *, rows_dev=None, rowscale=None, residual: bool = True) -> None:
+        """x += fc2(gelu(fc1(rowscale * LN2(x))))  (vit.py:53-55; residualvit.py:258-260); ``residual=False``: x = fc2(...) alone,
+        what forward_skip_attention / forward_skip_mlp return (residualvit.py:153-157,186-187)."""
         if self.exact:
-            return self._mlp_part_exact(x, lw, rows, rows_dev, rowscale)
+            return self._mlp_part_exact(x, lw, rows, rows_dev, rowscale, residual)
         pm, ws = self.pm, self.ws
         D = pm.dim
         mw = lw.mlp[0]
@@ -458,7 +476,10 @@ class Forward:
         a = ops.layernorm(x, lw.ln2_w, lw.ln2_b, lw.eps, ws.get("ln", (rows, D), torch.bfloat16), rows=rows, rowscale=rowscale,
                           rows_dev=rows_dev)
         hid = ops.gemm(a, mw.w_fc1, mw.b_fc1, ws.get("hid", (rows, F), torch.bfloat16), PK_EPI_BIAS_GELU_BF16, m_dev=rows_dev)
-        ops.gemm(hid, mw.w_fc2, mw.b_fc2, x[:rows], PK_EPI_BIAS_RESID_F32, resid=x[:rows], m_dev=rows_dev)
+        if residual:
+            ops.gemm(hid, mw.w_fc2, mw.b_fc2, x[:rows], PK_EPI_BIAS_RESID_F32, resid=x[:rows], m_dev=rows_dev)
+        else:
+            ops.gemm(hid, mw.w_fc2, mw.b_fc2, x[:rows], PK_EPI_BIAS_F32, m_dev=rows_dev)
 
     def dense_block(self, x: torch.Tensor, lw: LayerWeights, rows: int, batch: int, seq: int) -> None:
         """ViTBlock on uniform-length samples, in place on the fp32 residual stream (vit.py:45-55)."""
@@ -551,8 +572,9 @@ class Forward:
         self.gemm_exact(att, rows, w["w_o"][expert], aw.b_o, xr, PK_EPI_BIAS_RESID_F32, resid=xr, rows_dev=rows_dev, m_dev=rows_dev,
                         rowscale=o_scale)
 
-    def _mlp_part_exact(self, x, lw, rows, rows_dev, rowscale):
+    def _mlp_part_exact(self, x, lw, rows, rows_dev, rowscale, residual: bool = True):
         ws = self.ws
+        epi, res = (PK_EPI_BIAS_RESID_F32, x[:rows]) if residual else (PK_EPI_BIAS_F32, None)
         w, mw = self._exact_weights(lw), lw.mlp[0]
         F = mw.b_fc1.shape[0]
         xr = x[:rows]
@@ -563,12 +585,11 @@ class Forward:
             ops.split(xr, a2, 2, SPLIT_LAYERNORM, lw.ln2_w, lw.ln2_b, lw.eps, rows=rows, rowscale=rowscale, rows_dev=rows_dev)
             hid = ops.gemm(a2, w["w_fc1"][0], mw.b_fc1, ws.get("hid_x2", (rows, 2 * F), torch.bfloat16), PK_EPI_BIAS_GELU_BF16,
                            m_dev=rows_dev, out_format=PK_OUT_BF16X2, **self._wrap(D))
-            ops.gemm(hid, w["w_fc2"][0], mw.b_fc2, xr, PK_EPI_BIAS_RESID_F32, resid=xr, m_dev=rows_dev, **self._wrap(F))
+            ops.gemm(hid, w["w_fc2"][0], mw.b_fc2, xr, epi, resid=res, m_dev=rows_dev, **self._wrap(F))
             return
         hid = self.gemm_exact(xr, rows, w["w_fc1"][0], mw.b_fc1, ws.get("hid32", (rows, F), torch.float32), PK_EPI_BIAS_F32,
                               SPLIT_LAYERNORM, lw.ln2_w, lw.ln2_b, lw.eps, in_scale=rowscale, rows_dev=rows_dev, m_dev=rows_dev)
-        self.gemm_exact(hid, rows, w["w_fc2"][0], mw.b_fc2, xr, PK_EPI_BIAS_RESID_F32, SPLIT_GELU, resid=xr, rows_dev=rows_dev,
-                        m_dev=rows_dev)
+        self.gemm_exact(hid, rows, w["w_fc2"][0], mw.b_fc2, xr, epi, SPLIT_GELU, resid=res, rows_dev=rows_dev, m_dev=rows_dev)
 
     # ---- LayerNorm fused across GEMMs (dense layers of ViT / RankViT)
     def fold_ok(self, rows: int) -> bool:
@@ -717,6 +738,8 @@ class Forward:
         Local row layout of a sample: [cls, budget token, live image rows ..., ghost slot]."""
         pm, ws = self.pm, self.ws
         ex = pm.extra
+        if ex.get("dense_layout"):
+            return self.residualvit_dense(images, budget, aux)
         abt = ex["add_budget_token"]
         B, D, dev = images.shape[0], pm.dim, images.device
         nb = 1 if abt else 0
@@ -807,6 +830,132 @@ class Forward:
             ops.cls_head(x, B, 0, 1, pm.ln_w, pm.ln_b, pm.ln_eps, pm.head_w, pm.head_b, cu_seqlens=cu, out=exits[len(pm.layers)])
             return exits
         return self.head(x, B, 0, cu_seqlens=cu, n_cls=1)
+
+    def residualvit_dense(self, images: torch.Tensor, budget, aux: Optional[dict] = None) -> torch.Tensor:
+        """ResidualViT on the dense masked row layout -- every token keeps its row, like in the reference -- for the
+        configurations whose dropped rows do not stay identical: skip modes 'attention' (residualvit.py:130-157) and 'mlp'
+        (:160-194), ``add_input`` (:239-242), two special tokens without a budget token, a NoiseBlock between blocks.
+        Local row layout of a sample: [cls0, budget token (if any), other class tokens, registers, patches]."""
+        pm, ws = self.pm, self.ws
+        ex = pm.extra
+        abt = ex["add_budget_token"]
+        B, D, dev = images.shape[0], pm.dim, images.device
+        nb = 1 if abt else 0
+        # ResidualViTBlock.num_special_tokens (:99): the model builds its encoder without telling it about further class tokens
+        # or registers (:452-467), so those are gated like image tokens and only the first class token is special
+        n_special = next((int(lw.module.num_special_tokens) for lw in pm.layers if lw.kind == "residual"), 1)
+        front = n_special + nb                                 # rows never gated: specials + the budget token
+        seq = pm.seq_len + nb
+        n_img = seq - front
+        rows = B * seq
+        x = self.embed_exact(images, shift=nb) if self.exact else self.embed(images, shift=nb)
+        if abt:
+            if budget is None:
+                raise AssertionError("Budget token not set. Call set_budget() before forward() to evaluate the model on a chosen budget.")
+            if abt == "learnable":
+                ops.fill_token_rows(x, B, seq, 1, ex["budget_token_1"], None, scale=float(budget))
+            elif abt == "learnable_interpolate":
+                ops.fill_token_rows(x, B, seq, 1, ex["budget_token_1"] * float(budget) + ex["budget_token_2"] * (1.0 - float(budget)), None)
+            else:
+                ops.fill_token_rows(x, B, seq, 1, None, None, scale=float(budget), n_tokens=1)
+        cu = self._const(f"cu0_{B}_{seq}", lambda: (torch.arange(B + 1, device=dev, dtype=torch.int32) * seq))
+        ones = self._const(f"ones_{rows}", lambda: torch.ones(rows, device=dev, dtype=torch.float32))
+        t = ws.get("resd_x1", (rows, D), torch.float32)
+        mask = ws.get("resd_mask", (rows,), torch.float32)
+        scratch_i = [ws.get(f"resd_i{j}", (rows,), torch.int32) for j in range(2)]
+        new_len, mdrop = ws.get("resd_newlen", (B,), torch.int32), ws.get("resd_mdrop", (B,), torch.float32)
+        thr_dev = ws.get("resd_thr", (1,), torch.float32)
+        ee = ex.get("ee_heads")
+        if ee is not None and len(ee) != len([lw for lw in pm.layers if lw.kind != "noise"]):
+            raise RuntimeError("EEResidualViT: one early-exit head per encoder layer is required (eeresidualvit.py:93-94)")
+        n_blocks = len(ee) if ee is not None else 0
+        exits = ws.get("ee_logits", (n_blocks + 1, B, pm.num_classes), torch.float32) if ee is not None else None
+
+        def gate(src, g, mode: str) -> None:
+            """block.mask of this layer for the rows of ``src`` (ResidualGate.forward, residualvit.py:47-74) -> ``mask`` (1 on
+            the special / budget rows)."""
+            sig = g["gate_type"] == "sigmoid"
+            if abt and mode == "attention+mlp" and abt == "learnable":
+                thr_mode = 0                                   # threshold = sigmoid(budget_token_gate(budget token)) (:212)
+            elif abt:
+                if not sig:
+                    raise AssertionError("Gumbel gate does not support budget")
+                thr_mode = 1                                   # budget = mean of the budget token over the batch (:142,177,208)
+                ops.budget_mean_threshold(src, cu, B, 1, thr_dev)
+            else:
+                thr_mode = 2                                   # the gate's own threshold (:69)
+            ops.residual_gate_plan(src, cu, ones, B, seq, n_special=front, budget_pos=1 if abt else -1, gated=True,
+                                   gate_w=g["gate_w"], gate_b=g["gate_b"], gate_temp=g["gate_temp"], gate_bias=g["gate_bias"],
+                                   gate_type=0 if sig else 1, thr_mode=thr_mode, bt_w=g.get("bt_gate_w"), bt_b=g.get("bt_gate_b", 0.0),
+                                   thr_dev=thr_dev, thr_const=float(g["gate_threshold"]), mask=mask, dst_local=scratch_i[0],
+                                   sample_of=scratch_i[1], new_len=new_len, mdrop=mdrop)
+
+        def publish(i: int) -> None:
+            if aux is not None:
+                aux.setdefault("masks", {})[i] = mask.view(B, seq)[:, front:].reshape(B, n_img, 1).clone()
+
+        blk_i = 0
+        for i, lw in enumerate(pm.layers):
+            if lw.kind == "noise":
+                apply_noise(self.noise_draws[i], x, B, seq, self.sample_offset)
+                continue
+            skip, g = lw.extra.get("skip"), lw.extra
+            if skip == "attention+mlp":
+                if front != 2:
+                    raise RuntimeError("ResidualViT 'attention+mlp' layers need exactly two ungated tokens, i.e. a budget token "
+                                       "(the reference's forward mask hard-codes them, residualvit.py:230-235)")
+                if g["add_input"] and abt:
+                    raise RuntimeError("add_input with a budget token: the reference adds a tensor one token short here "
+                                       "(residualvit.py:239-242)")
+                gate(x, g, skip)
+                publish(i)
+                ops.row_scale_add(t, x, mask, rows)                                     # masked_input (:220-227)
+                self.attn_part(t, lw, rows, B, seq=seq, rowscale=mask)
+                self.mlp_part(t, lw, rows, rowscale=mask)
+                if g["add_input"]:
+                    ops.row_scale_add(t, x, mask, rows, one_minus=True, accumulate=True)   # + img_tokens * (1 - mask)
+                x, t = t, x
+            elif skip == "attention":
+                if abt:
+                    raise RuntimeError("ResidualViT skip mode 'attention' cannot run with a budget token (the reference adds "
+                                       "tensors of different lengths, residualvit.py:137-152)")
+                gate(x, g, skip)
+                publish(i)
+                ops.row_scale_add(t, x, mask, rows)                                     # masked_input (:145-148)
+                self.attn_part(t, lw, rows, B, seq=seq)                                 # t = masked_input + attention(ln_1(masked_input))
+                ops.row_scale_add(t, x, mask, rows, one_minus=True, accumulate=True)    # ... + input instead (:150-153)
+                self.mlp_part(t, lw, rows, residual=False)                              # returns mlp(ln_2(x)) alone (:155-157)
+                x, t = t, x
+            elif skip == "mlp":
+                if g["add_input"] and abt:
+                    raise RuntimeError("add_input with a budget token: the reference adds a tensor one token short here "
+                                       "(residualvit.py:189-192)")
+                self.attn_part(x, lw, rows, B, seq=seq)                                 # :162-165
+                gate(x, g, skip)
+                publish(i)
+                ops.row_scale_add(t, x, mask, rows)                                     # masked_input (:178-184)
+                self.mlp_part(t, lw, rows, residual=False)                              # :186-187
+                if g["add_input"]:
+                    ops.row_scale_add(t, x, mask, rows, one_minus=True, accumulate=True)
+                x, t = t, x
+            elif skip in (None, "none"):
+                self.attn_part(x, lw, rows, B, seq=seq)
+                self.mlp_part(x, lw, rows)
+            else:
+                raise NotImplementedError(f"skip mode {skip!r}")
+            if ee is not None:
+                ln_w, ln_b, ln_eps, hw, hb = ee[blk_i]
+                ops.cls_head(x, B, seq, 1, ln_w, ln_b, ln_eps, hw, hb, out=exits[blk_i])
+            blk_i += 1
+        if ee is not None:
+            ops.cls_head(x, B, seq, 1, pm.ln_w, pm.ln_b, pm.ln_eps, pm.head_w, pm.head_b, out=exits[n_blocks])
+            return exits
+        if pm.n_cls > 1 and nb:
+            # the class tokens sit at local rows 0, 2, 3, ...: gather them behind each other for the sum readout (:609-611)
+            pick = self._const(f"cls_pick_{B}_{pm.n_cls}", lambda: torch.arange(1, pm.n_cls, device=dev, dtype=torch.int32).repeat(B, 1).contiguous())
+            y = ops.gather_rows(x, pick, B, seq, ws.get("resd_cls", (B * pm.n_cls, D), torch.float32))
+            return self.head(y, B, pm.n_cls, n_cls=pm.n_cls)
+        return self.head(x, B, seq, n_cls=pm.n_cls)
 
     # ---------------------------------------------------------------- AdaViT (A-ViT)
     def adavit(self, images: torch.Tensor, aux: Optional[dict] = None, early_exit: bool = True) -> torch.Tensor:

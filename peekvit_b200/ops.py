@@ -437,6 +437,15 @@ def zero_token_rows(x: torch.Tensor, batch: int, seq: int, tokens: torch.Tensor)
     return x
 
 
+def row_scale_add(out: torch.Tensor, a: torch.Tensor, scale: torch.Tensor, rows: int, *, one_minus: bool = False,
+                  accumulate: bool = False) -> torch.Tensor:
+    """out[r] = (out[r] if accumulate else 0) + w[r] * a[r], w = scale or 1 - scale (residualvit.py:145,176,239-242)."""
+    lib = _lib_for(a)
+    check(lib.pk_row_scale_add(_ptr(out, torch.float32), _ptr(a, torch.float32), _ptr(scale, torch.float32), rows, a.shape[-1],
+                               int(one_minus), int(accumulate), _stream()), "pk_row_scale_add")
+    return out
+
+
 SPLIT_NONE, SPLIT_GELU, SPLIT_LAYERNORM = 0, 1, 2
 
 

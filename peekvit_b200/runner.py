@@ -186,6 +186,8 @@ def _micro_batch(model, B: int) -> int:
     if _exact(model):
         mb = min(mb, EXACT_MICRO_BATCH)
     abt = model.add_budget_token if model._family == "residualvit" else model.budget if model._family == "eeresidualvit" else None
+    if abt and any(getattr(blk, "skip", None) == "mlp" for blk in model.encoder.layers):
+        return max(B, 1)        # forward_skip_mlp thresholds on the batch-wide mean of the budget token whatever its kind (:177)
     if abt and abt not in ("learnable", "learnable_interpolate"):
         # a fixed-float budget token thresholds on the mean over the WHOLE batch (residualvit.py:208):
         # the batch cannot be split without changing the reference semantics

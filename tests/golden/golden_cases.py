@@ -62,6 +62,43 @@ CASES = {
         family="vit", batch=3, weight_seed=22, image_seed=32, noise_seed=78,
         noise=dict(layer=2, noise_type="token_drop", prob=0.3),
         cfg=dict(_BASE, num_layers=3)),
+    # ---- the ResidualViT configurations that run on the dense masked row layout (Forward.residualvit_dense)
+    # skip mode 'attention' (residualvit.py:130-157): no budget token possible, the gate's own threshold
+    "residual_skip_attention": dict(
+        family="residualvit", batch=3, weight_seed=31, image_seed=41,
+        cfg=dict(_BASE, gate_type="sigmoid", gate_temp=1.0, gate_bias=0.0, gate_threshold=0.5,
+                 residual_layers=["attention", None, "attention", "none"])),
+    # skip mode 'mlp' (:160-194) thresholds on the batch mean of the (fixed-float) budget token; mixed with the other modes
+    "residual_skip_mlp_fixed": dict(
+        family="residualvit", batch=3, weight_seed=32, image_seed=42, budget=0.5,
+        cfg=dict(_BASE, gate_type="sigmoid", gate_temp=1.0, gate_bias=0.0, gate_threshold=0.5,
+                 add_budget_token=True, residual_layers=["attention+mlp", "mlp", None, "mlp"])),
+    # 'mlp' with add_input (:189-192; only without a budget token) followed by an 'attention' layer
+    "residual_skip_mlp_add_input": dict(
+        family="residualvit", batch=3, weight_seed=33, image_seed=43,
+        cfg=dict(_BASE, gate_type="sigmoid", gate_temp=1.0, gate_bias=0.0, gate_threshold=0.5, add_input=True,
+                 residual_layers=["mlp", None, "mlp", "attention"])),
+    # gumbel gate in eval = round(sigmoid(logit)) (blocks.py:55-57)
+    "residual_gumbel_modes": dict(
+        family="residualvit", batch=3, weight_seed=34, image_seed=44,
+        cfg=dict(_BASE, gate_type="gumbel", residual_layers=["attention", "mlp", None, "mlp"])),
+    # two class tokens + a register: the further class token and the register are gated like image tokens, the head sums both
+    # class tokens (:609-611)
+    "residual_two_cls_cal05": dict(
+        family="residualvit", batch=4, weight_seed=35, image_seed=45, budget=0.5, calibrate=0.5,
+        cfg=dict(_BASE, gate_type="sigmoid", gate_temp=1.0, gate_bias=0.0, gate_threshold=0.5, num_class_tokens=2,
+                 num_registers=1, add_budget_token="learnable", residual_layers=["attention+mlp"] * 4)),
+    # NoiseBlock inside a ResidualViT encoder (utils/utils.py:162-191): dropped rows stop being identical
+    "residual_noise_snr": dict(
+        family="residualvit", batch=3, weight_seed=18, image_seed=46, budget=0.4, calibrate=0.4, noise_seed=79,
+        noise=dict(layer=2, noise_type="gaussian", snr=8.0),
+        cfg=dict(_BASE, gate_type="sigmoid", gate_temp=1.0, gate_bias=0.0, gate_threshold=0.5,
+                 add_budget_token="learnable", residual_layers=["attention+mlp"] * 4)),
+    "residual_noise_token_drop": dict(
+        family="residualvit", batch=3, weight_seed=18, image_seed=47, budget=0.4, calibrate=0.4, noise_seed=80,
+        noise=dict(layer=1, noise_type="token_drop", prob=0.25),
+        cfg=dict(_BASE, gate_type="sigmoid", gate_temp=1.0, gate_bias=0.0, gate_threshold=0.5,
+                 add_budget_token="learnable", residual_layers=["attention+mlp"] * 4)),
 }
 
 
@@ -72,6 +109,8 @@ def oracle_noise(case, device="cpu"):
     import torch
     nz, cfg = case["noise"], case["cfg"]
     n_tok = (cfg["image_size"] // cfg["patch_size"]) ** 2 + cfg.get("num_class_tokens", 1) + cfg.get("num_registers", 0)
+    if cfg.get("add_budget_token"):
+        n_tok += 1                                     # ResidualViT: the budget token is part of the sequence the block sees
     torch.manual_seed(case["noise_seed"])
     if nz["noise_type"] == "gaussian":
         return dict(layer=nz["layer"], snr_db=nz["snr"],

@@ -66,7 +66,10 @@ def stable_argsort_patch():
 def main():
     classes = import_reference()
     torch.manual_seed(0)
+    only = set(sys.argv[1:])                         # optional: regenerate just the named cases
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         fam, cfg, budget = case["family"], dict(case["cfg"]), case.get("budget")
         sd, images = build_case(case)
         model = classes[fam](**cfg)
@@ -94,9 +97,12 @@ def main():
                 logits = model(images)
         if noise is not None:
             with torch.no_grad():
-                o_logits, aux = po.vit_forward(sd, cfg, images, noise=noise)
-            with torch.no_grad():
-                clean, _ = po.vit_forward(sd, cfg, images)
+                if fam == "residualvit":
+                    o_logits, aux = po.residualvit_forward(sd, cfg, images, budget, noise=noise)
+                    clean, _ = po.residualvit_forward(sd, cfg, images, budget)
+                else:
+                    o_logits, aux = po.vit_forward(sd, cfg, images, noise=noise)
+                    clean, _ = po.vit_forward(sd, cfg, images)
             assert (clean - logits).abs().max() > 1e-3, "the noise block had no effect: vacuous fixture"
         else:
             o_logits, aux = po.forward(fam, sd, cfg, images, budget)
@@ -113,7 +119,8 @@ def main():
         print(f"{name:28s} max|logit|={logits.abs().max():.3f} oracle-vs-reference rel err {err:.2e}")
         assert err < 2e-5, (name, err)
         if fam in ("residualvit", "eeresidualvit"):
-            for i, blk in enumerate(model.encoder.layers):
+            blocks = [b for b in model.encoder.layers if type(b).__name__ != "NoiseBlock"]     # fixture keys: block index
+            for i, blk in enumerate(blocks):
                 if getattr(blk, "mask", None) is not None:
                     out[f"mask_{i}"] = blk.mask.numpy()
                     assert torch.allclose(aux["masks"][i], blk.mask, atol=2e-5), (name, i)

@@ -131,7 +131,8 @@ def test_vit_b16_bf16x2_meets_all_three_north_star_numbers():
 
 
 @pytest.mark.parametrize("name", ["vit_d64_h2", "vit_d128_regs", "rankvit_b05", "residual_learnable_cal04", "avit", "moevit", "moevit_attn",
-                                  "eeresidual_learnable_cal04"])
+                                  "eeresidual_learnable_cal04", "residual_skip_attention", "residual_skip_mlp_add_input",
+                                  "residual_skip_mlp_fixed", "residual_two_cls_cal05"])
 def test_bf16x2_mode_matches_reference_fixture(name):
     """Every family runs in the mode (ragged / small-head shapes take the fp32 attention core): logits within 1e-3 of the
     reference fixture -- 10x inside the bf16 tolerance."""

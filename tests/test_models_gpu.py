@@ -46,16 +46,32 @@ def test_noise_block_matches_oracle_and_fixture(name):
     torch.manual_seed(case["noise_seed"])
     logits = model(images.to(DEV)).cpu()
     assert ops.device_flag() == 0
+    residual = case["family"] == "residualvit"
     with torch.no_grad():
-        ref, _ = po.vit_forward(sd, case["cfg"], images, noise=oracle_noise(case, device=DEV))
+        if residual:
+            ref, raux = po.residualvit_forward(sd, case["cfg"], images, case["budget"], noise=oracle_noise(case, device=DEV))
+        else:
+            ref, _ = po.vit_forward(sd, case["cfg"], images, noise=oracle_noise(case, device=DEV))
     scale = ref.abs().max()
     assert ((logits - ref).abs().max() / scale).item() < TOL_LOGITS
     assert ((logits - clean).abs().max() / scale).item() > 5 * TOL_LOGITS          # the noise really acted
     if case["noise"]["noise_type"] == "token_drop":
         gold = np.load(os.path.join(GOLD, name + ".npz"))["logits"]
         assert np.abs(logits.numpy() - gold).max() / np.abs(gold).max() < TOL_LOGITS
+    if residual:
+        # block.mask of the layers behind the NoiseBlock (encoder.layers index = block index + 1 there)
+        blocks = [b for b in model.encoder.layers if not isinstance(b, NoiseBlock)]
+        for j, blk in enumerate(blocks):
+            m, g = blk.mask.cpu(), raux["masks"][j]
+            assert m.shape == g.shape and (m - g).abs().max().item() < 5e-3
     nb.set_value(0.0)                                   # 0 dB / probability 0 switch the block off (blocks.py:125-127,:145)
-    assert torch.equal(model(images.to(DEV)).cpu(), clean)
+    off = model(images.to(DEV)).cpu()
+    if residual:
+        # with the block spliced in the model runs on the dense masked row layout, without it on compacted rows: the same
+        # function, two summation orders
+        assert ((off - clean).abs().max() / scale).item() < TOL_LOGITS
+    else:
+        assert torch.equal(off, clean)
     # standalone call on a (B, N, D) tensor
     x = torch.randn(2, 7, 64, device=DEV)
     g = NoiseBlock("gaussian", snr=5.0)
@@ -88,8 +104,24 @@ def test_model_matches_reference_fixture(name):
         logits = runner.run(model, images.to(DEV), aux).cpu().numpy()
     assert ops.device_flag() == 0
     scale = np.abs(ref["logits"]).max()
-    assert np.abs(logits - ref["logits"]).max() / scale < TOL_LOGITS
-    assert (logits.argmax(1) == ref["logits"].argmax(1)).mean() >= 0.75   # 3-4 images: at most one near-tie flip
+    if case["cfg"].get("gate_type") == "gumbel":
+        # hard 0 / 1 gates (round(sigmoid), blocks.py:55-57): a bf16-level difference in a gate logit next to 0 flips a whole
+        # token, so -- like the RankViT selections -- the logits are compared given identical decisions: the oracle replayed
+        # with the masks this path published (the decisions themselves are compared with the fixture below, and are identical
+        # in the fp32 mode: test_fp32_mode_matches_reference_fixture)
+        from oracle import peekvit_oracle as po
+        with torch.no_grad():
+            replay, _ = po.residualvit_forward(sd, case["cfg"], images, case.get("budget"),
+                                               forced_masks={i: torch.cat(m).cpu() for i, m in aux["masks"].items()})
+        assert np.abs(logits - replay.numpy()).max() / scale < TOL_LOGITS
+    else:
+        # the 'attention' / 'mlp' skip modes return mlp(...) WITHOUT the residual around it (residualvit.py:155-157,186-187):
+        # the stream is then a bare bf16-operand GEMM output, re-normalised by the next LayerNorm, instead of a small update
+        # on an fp32 stream -- operand rounding shows up at a few 1e-2 over four such layers.  The same cases are held to
+        # 1e-3 in the bf16x2 mode (tests/test_bf16x2_gpu.py) and to 1e-5 in the fp32 mode (below).
+        no_resid = any(m in ("attention", "mlp") for m in (case["cfg"].get("residual_layers") or []))
+        assert np.abs(logits - ref["logits"]).max() / scale < (4 * TOL_LOGITS if no_resid else TOL_LOGITS)
+        assert (logits.argmax(1) == ref["logits"].argmax(1)).mean() >= 0.75   # 3-4 images: at most one near-tie flip
     if case["family"] == "rankvit":
         assert aux["seq_lens"] == list(ref["seq_lens"])
         for i, kept in aux["kept"].items():
@@ -106,10 +138,13 @@ def test_model_matches_reference_fixture(name):
         # threshold, where the soft value itself is ~0.
         agree = []
         for i, blk in enumerate(model.encoder.layers):
+            if f"mask_{i}" not in ref:                 # plain layers (skip None / 'none') publish no mask
+                continue
             g = torch.from_numpy(ref[f"mask_{i}"])
             m = blk.mask.cpu()
             assert m.shape == g.shape
-            assert (m - g).abs().max().item() < 5e-3
+            if case["cfg"].get("gate_type") != "gumbel":           # hard gates: a near-tie flip is a difference of 1
+                assert (m - g).abs().max().item() < 5e-3
             agree.append(((m > 0) == (g > 0)).float().mean().item())
         assert np.mean(agree) >= 0.9
     if case["family"] == "adavit":
@@ -347,6 +382,8 @@ def test_fp32_mode_matches_reference_fixture(name):
             assert np.array_equal(kept.cpu().numpy(), ref[f"kept_{i}"])          # bit-exact index sets, in order
     if fam in ("residualvit", "eeresidualvit"):
         for i, blk in enumerate(model.encoder.layers):
+            if f"mask_{i}" not in ref:
+                continue
             g = ref[f"mask_{i}"]
             m = blk.mask.cpu().numpy()
             assert np.array_equal(m > 0, g > 0)                                  # identical keep / drop decisions

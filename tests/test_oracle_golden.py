@@ -20,7 +20,10 @@ def test_oracle_matches_reference_fixture(name):
     if case.get("noise") is not None:
         # NoiseBlock cases: the reference drew from torch's CPU generator under noise_seed; the same draw is regenerated here
         with torch.no_grad():
-            logits, aux = po.vit_forward(sd, case["cfg"], images, noise=oracle_noise(case))
+            if case["family"] == "residualvit":
+                logits, aux = po.residualvit_forward(sd, case["cfg"], images, case["budget"], noise=oracle_noise(case))
+            else:
+                logits, aux = po.vit_forward(sd, case["cfg"], images, noise=oracle_noise(case))
     else:
         logits, aux = po.forward(case["family"], sd, case["cfg"], images, case.get("budget"))
     if case["family"] == "eeresidualvit":
