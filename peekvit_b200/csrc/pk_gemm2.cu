@@ -79,6 +79,7 @@ struct PairParams {
   int M, N, K;
   const int* m_dev;
   const int* row_begin_dev;
+  const int* out_row_index;  // RED only: GEMM row r accumulates into out row out_row_index[r] (un-permute of expert-sorted rows)
   const float* bias;
   void* out;
   long long ldo;
@@ -350,7 +351,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       const int row_base = row0 + m_blk * 2 * kP_BM + row_in_pair;                         // this warp's first row
       const int grow = row_base + lane;
       const int row_end = row0 + M;                                                        // rows >= row_end stay untouched
-      const bool full_tile = row_base + 32 <= row_end;                                     // warp-uniform
+      // warp-uniform; a row-indexed launch (MoE un-permute) writes every tile row by row
+      const bool full_tile = row_base + 32 <= row_end && !(RED && p.out_row_index);
       float sc = 1.0f;
       if constexpr (kResid || RED) {
         if (p.rowscale && grow < row_end) sc = p.rowscale[grow];
@@ -541,13 +543,25 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 if (col0 + 8 * j < p.N) *reinterpret_cast<uint4*>(orow - p.N + 8 * j) = make_uint4(lo2[4 * j], lo2[4 * j + 1], lo2[4 * j + 2], lo2[4 * j + 3]);
             }
           } else {
-            float* orow = static_cast<float*>(p.out) + static_cast<long long>(grow) * p.ldo + col0;
+            long long orow_i = grow;
+            if constexpr (RED) {
+              if (p.out_row_index) orow_i = p.out_row_index[grow];
+            }
+            float* orow = static_cast<float*>(p.out) + orow_i * p.ldo + col0;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               if (col0 + 4 * j < p.N) {
                 float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                                        __uint_as_float(v[4 * j + 3]));
-                if constexpr (RED) {          // each element belongs to exactly one thread: plain read-modify-write
+                if constexpr (RED) {
+                  if (p.out_row_index) {
+                    // fire-and-forget vector reduction at L2 (no load round trip in the epilogue warp); the index is a
+                    // permutation, so no two rows collide and the sum is order-independent
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + 4 * j), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                                 : "memory");
+                    continue;
+                  }
+                  // each element belongs to exactly one thread: plain read-modify-write
                   const float4 r = *reinterpret_cast<const float4*>(orow + 4 * j);
                   o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
                 }
@@ -676,6 +690,7 @@ static int launch_pair(const pk_gemm_args* a, cudaStream_t stream) {
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.m_dev = a->m_dev;
   p.row_begin_dev = a->row_begin_dev;
+  p.out_row_index = a->out_row_index;
   p.bias = a->bias;
   p.out = a->out; p.ldo = a->ldo;
   p.rowscale = a->rowscale;
@@ -734,7 +749,11 @@ static int pick_pair_block_n(int N) {
 // The pair kernel needs plain row mapping (TMA tile stores), 16-byte aligned rows and N % 8 == 0.
 bool pair_gemm_eligible(const pk_gemm_args* a) {
   if (a->epilogue_mode == 2) return false;
-  if (a->rows_per_group > 0 || a->out_row_index) return false;
+  if (a->rows_per_group > 0) return false;
+  // row-indexed output: only as the in-place accumulate x[idx[r]] += ... (the TMA-reduce variant's row-store path)
+  if (a->out_row_index && !(a->epilogue == PK_EPI_BIAS_RESID_F32 && a->resid == a->out && a->ldr == a->ldo && !a->xb_out &&
+                            pair_tma_reduce()))
+    return false;
   const bool bf = a->epilogue == PK_EPI_BIAS_BF16 || a->epilogue == PK_EPI_BIAS_GELU_BF16;
   const long long eb = bf ? 2 : 4;
   if ((a->ldo * eb) % 16 != 0 || (reinterpret_cast<uintptr_t>(a->out) & 15) != 0) return false;

@@ -35,6 +35,9 @@ LN_FOLD = int(os.environ.get("PEEKVIT_B200_LN_FOLD", "1"))
 EMBED_TOKEN_ROWS = int(os.environ.get("PEEKVIT_B200_EMBED_TOKEN_ROWS", "1"))
 # 1: for more than 256 samples the classification head runs as a split-operand tensor-core GEMM; 0: always the fused kernel
 HEAD_GEMM = int(os.environ.get("PEEKVIT_B200_HEAD_GEMM", "1"))
+# MoE expert fc2: un-permute + residual add inside the GEMM epilogue (row-indexed reductions) instead of a sorted fp32 output
+# followed by pk_scatter_add_rows (A/B switch)
+MOE_FUSED_SCATTER = int(os.environ.get("PEEKVIT_B200_MOE_FUSED_SCATTER", "1"))
 
 
 def _f32(t: torch.Tensor) -> torch.Tensor:
@@ -1093,10 +1096,18 @@ class Forward:
             # Expert-sorted rows: each expert's segment [offsets[e], offsets[e] + counts[e]) runs through the CTA-pair GEMMs
             # (device-side segment start and length); the fc2 outputs land in sorted order and one gather-add un-permutes
             # them into the residual stream.
+            fused = MOE_FUSED_SCATTER and rows > 256 and D % 8 == 0
             for e, mw in enumerate(lw.mlp):
                 ops.gemm(a, mw.w_fc1, mw.b_fc1, hid, PK_EPI_BIAS_GELU_BF16, m_dev=counts[e:e + 1], row_begin_dev=offsets[e:e + 1])
-                ops.gemm(hid, mw.w_fc2, mw.b_fc2, y_sorted, PK_EPI_BIAS_F32, m_dev=counts[e:e + 1], row_begin_dev=offsets[e:e + 1])
-            ops.scatter_add_rows(x, y_sorted, src_of, rows)
+                if fused:
+                    # the fc2 epilogue un-permutes and adds into the residual stream itself: x[src_of[r]] += fc2(hid[r]) + b
+                    # (vector reductions at L2; src_of is a permutation) -- no sorted fp32 output, no gather-add pass
+                    ops.gemm(hid, mw.w_fc2, mw.b_fc2, x, PK_EPI_BIAS_RESID_F32, resid=x, m_dev=counts[e:e + 1],
+                             row_begin_dev=offsets[e:e + 1], out_row_index=src_of, cta_pair=2)
+                else:
+                    ops.gemm(hid, mw.w_fc2, mw.b_fc2, y_sorted, PK_EPI_BIAS_F32, m_dev=counts[e:e + 1], row_begin_dev=offsets[e:e + 1])
+            if not fused:
+                ops.scatter_add_rows(x, y_sorted, src_of, rows)
             if aux is not None:
                 aux.setdefault("mlp_expert", {})[i] = expert.view(B, seq).clone()
         return self.head(x, B, seq, n_cls=1)

@@ -530,7 +530,10 @@ class EEResidualVisionTransformer(_ModelBase):
         return [out[i].unsqueeze(1).squeeze() for i in range(n)] + [out[n]]
 
     def forward_host(self, x_host, out_host=None):
-        raise NotImplementedError("forward_host returns one logits matrix; EEResidualViT's list output goes through model(x)")
+        """Host images in, the same list as ``forward`` out (host tensors; ``out_host``: optional pinned (L + 1, B, C) buffer)."""
+        out = runner.run_host(self, x_host, out_host)   # (L + 1, B, C)
+        n = out.shape[0] - 1
+        return [out[i].unsqueeze(1).squeeze() for i in range(n)] + [out[n]]
 
 
 class AdaptiveVisionTransformer(_ModelBase):

@@ -281,8 +281,7 @@ def run_host(model, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = Non
     if x_host.device.type != "cpu":
         raise RuntimeError("run_host expects a CPU (ideally pinned) tensor; use model(x) for device tensors")
     _check_images(model, x_host)
-    if model._family == "eeresidualvit":
-        raise NotImplementedError("forward_host returns one logits matrix; EEResidualViT's list output goes through model(x)")
+    multi = model._family == "eeresidualvit"            # (L + 1, B, C): one early exit per layer, then the final logits
     u8 = x_host.dtype == torch.uint8
     if u8:
         x_host = x_host.contiguous()
@@ -306,7 +305,8 @@ def run_host(model, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = Non
             bufs = [ws.get("img_stage0_u8", (mb, S, S, 3), torch.uint8), ws.get("img_stage1_u8", (mb, S, S, 3), torch.uint8)]
         else:
             bufs = [ws.get("img_stage0", (mb, 3, S, S), torch.float32), ws.get("img_stage1", (mb, 3, S, S), torch.float32)]
-        out = ws.get("logits_all", (B, model.num_classes), torch.float32)
+        out_shape = (len(model.encoder.layers) + 1, B, model.num_classes) if multi else (B, model.num_classes)
+        out = ws.get("logits_all", out_shape, torch.float32)
         cur = torch.cuda.current_stream(dev)
         for i in range(2):
             free[i].record(cur)
@@ -333,11 +333,11 @@ def run_host(model, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = Non
                 bufs[slot][:n].copy_(x_host[s:s + n], non_blocking=True)
                 ready[slot].record(copy_stream)
             cur.wait_event(ready[slot])
-            out[s:s + n].copy_(_forward_chunk(model, fwd, bufs[slot][:n], None))
+            (out[:, s:s + n] if multi else out[s:s + n]).copy_(_forward_chunk(model, fwd, bufs[slot][:n], None))
             free[slot].record(cur)
             s += n
         if out_host is None:
-            out_host = torch.empty(B, model.num_classes, dtype=torch.float32, pin_memory=True)
+            out_host = torch.empty(out_shape, dtype=torch.float32, pin_memory=True)
         out_host.copy_(out, non_blocking=True)
         cur.synchronize()
         ops.raise_if_flagged(dev.index, sync=True)

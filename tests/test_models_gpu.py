@@ -100,6 +100,10 @@ def test_model_matches_reference_fixture(name):
             assert tuple(outs[i].shape) == r.shape
             assert np.abs(outs[i].cpu().numpy() - r).max() / np.abs(r).max() < TOL_LOGITS
         logits = outs[-1].cpu().numpy()
+        # the host-resident entry returns the same list (host tensors)
+        host = model.forward_host(images.pin_memory())
+        assert len(host) == L + 1 and all(h.device.type == "cpu" for h in host)
+        assert all(torch.allclose(h, o.cpu(), atol=1e-6) for h, o in zip(host, outs))
     else:
         logits = runner.run(model, images.to(DEV), aux).cpu().numpy()
     assert ops.device_flag() == 0

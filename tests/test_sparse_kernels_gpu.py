@@ -217,16 +217,18 @@ def test_moe_route_and_grouped_mlp(ops, E, D):
     b2 = [torch.randn(D, device=DEV, generator=g) * 0.1 for _ in range(E)]
     a = ops.layernorm(x, gamma, beta, 1e-5, row_index=src_of)
     hid = torch.zeros(rows, F, device=DEV, dtype=torch.bfloat16)
-    y = x.clone()
-    for e in range(E):
-        ops.gemm(a, w1[e], b1[e], hid, PK_EPI_BIAS_GELU_BF16, m_dev=counts[e:e + 1], row_begin_dev=offsets[e:e + 1])
-        ops.gemm(hid, w2[e], b2[e], y, PK_EPI_BIAS_RESID_F32, resid=y, m_dev=counts[e:e + 1], row_begin_dev=offsets[e:e + 1],
-                 out_row_index=src_of)
-    assert ops.device_flag() == 0
     lnb = ln.to(torch.bfloat16).float()
     ref = x.clone()
     for e in range(E):
         sel = expert.long() == e
         h = torch.nn.functional.gelu(lnb[sel] @ w1[e].float().t() + b1[e]).to(torch.bfloat16).float()
         ref[sel] += h @ w2[e].float().t() + b2[e]
-    assert ((y - ref).abs().max() / ref.abs().max()).item() < 1e-2
+    # the un-permuting fc2 on the CTA-pair kernel (row-indexed reductions at L2; what the model runs) and on the single-CTA one
+    for cta_pair in (2, 1):
+        y = x.clone()
+        for e in range(E):
+            ops.gemm(a, w1[e], b1[e], hid, PK_EPI_BIAS_GELU_BF16, m_dev=counts[e:e + 1], row_begin_dev=offsets[e:e + 1])
+            ops.gemm(hid, w2[e], b2[e], y, PK_EPI_BIAS_RESID_F32, resid=y, m_dev=counts[e:e + 1], row_begin_dev=offsets[e:e + 1],
+                     out_row_index=src_of, cta_pair=cta_pair)
+        assert ops.device_flag() == 0
+        assert ((y - ref).abs().max() / ref.abs().max()).item() < 1e-2
