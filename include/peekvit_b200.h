@@ -166,6 +166,10 @@ typedef struct pk_attention_args {
    * half (11 significant bits; the probabilities are packed as half too); out_format PK_OUT_BF16X2 = `out` is
    * [rows, 2*D] holding the fp32 result split into lo (column d) and hi (column D + d), both bf16. */
   int qkv_format, out_format;
+  /* Device-side choice between the two ragged kernels (both are launched, the one not chosen exits at once): with
+   * route_rows set, the ragged tcgen05 kernel runs when *route_rows >= route_min_rows (long samples), the general mma.sync
+   * kernel otherwise (the two-region TMEM pipeline does not pay off below ~130 rows per sample: profiles/r02). */
+  const int* route_rows; int route_min_rows;
   int total_rows;           /* rows of the qkv / out buffers (the ragged tcgen05 kernel's 2-D tensor maps need the extent: a
                                key tile that starts near the end of the buffer is zero-filled past it); 0 = unknown (the ragged
                                kernel is then not used).  Rows of `qkv` past the live ones must hold finite values. */

@@ -47,7 +47,8 @@ class AttentionArgs(C.Structure):
         ("seq_len", c_int), ("cu_seqlens", c_void_p), ("max_seq_len", c_int),
         ("scale", c_float),
         ("key_mult", c_void_p), ("extra_kv", c_void_p), ("extra_mult", c_void_p),
-        ("impl", c_int), ("qkv_format", c_int), ("out_format", c_int), ("total_rows", c_int),
+        ("impl", c_int), ("qkv_format", c_int), ("out_format", c_int), ("route_rows", c_void_p), ("route_min_rows", c_int),
+        ("total_rows", c_int),
     ]
 
 

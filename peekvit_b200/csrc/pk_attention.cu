@@ -66,6 +66,8 @@ struct AttParams {
   const float* key_mult;
   const __nv_bfloat16* extra_kv;
   const float* extra_mult;
+  const int* route_rows;   // device-side routing: run only when *route_rows < route_min_rows (the tcgen05 kernel takes the rest)
+  int route_min_rows;
 };
 
 template <int DH>
@@ -82,6 +84,7 @@ attention_fwd_kernel(const AttParams p) {
   __shared__ __align__(128) uint8_t s_v[2][TILE_BYTES];
   __shared__ float s_bias[2][kAttBKV];
 
+  if (p.route_rows && *p.route_rows >= p.route_min_rows) return;     // the ragged tcgen05 kernel's launch takes this batch
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int h = blockIdx.y, b = blockIdx.z;
   const int D = p.num_heads * DH;
@@ -327,7 +330,13 @@ extern "C" int pk_attention_fwd(const pk_attention_args* a, void* stream) {
   PK_REQUIRE((a->extra_kv == nullptr) == (a->extra_mult == nullptr), "pk_attention_fwd: extra_kv and extra_mult go together");
   if (a->batch == 0 || a->max_seq_len == 0) return PK_OK;
   if (attention_tc_eligible(a)) return launch_attention_tc(a, static_cast<cudaStream_t>(stream));
-  if (attention_tcr_eligible(a)) return launch_attention_tcr(a, static_cast<cudaStream_t>(stream));
+  const bool routed = a->route_rows != nullptr && a->impl == 0 && attention_tcr_eligible(a);
+  if (routed) {
+    const int rc = launch_attention_tcr(a, static_cast<cudaStream_t>(stream));
+    if (rc != PK_OK) return rc;
+  } else if (attention_tcr_eligible(a)) {
+    return launch_attention_tcr(a, static_cast<cudaStream_t>(stream));
+  }
   PK_REQUIRE(a->impl != 3, "pk_attention_fwd: the ragged tcgen05 kernel needs head_dim 64, <= 256 keys per sample, 16-byte aligned buffers and total_rows");
   PK_REQUIRE(a->qkv_format == PK_OUT_BF16 && a->out_format == PK_OUT_BF16,
              "pk_attention_fwd: half operands / split output exist on the tcgen05 kernel only (uniform 16 < seq_len <= 224, head_dim 64)");
@@ -342,6 +351,8 @@ extern "C" int pk_attention_fwd(const pk_attention_args* a, void* stream) {
   p.key_mult = a->key_mult;
   p.extra_kv = static_cast<const __nv_bfloat16*>(a->extra_kv);
   p.extra_mult = a->extra_mult;
+  p.route_rows = routed ? a->route_rows : nullptr;
+  p.route_min_rows = a->route_min_rows;
   const int max_len = a->cu_seqlens ? a->max_seq_len : a->seq_len;
   dim3 grid((max_len + kAttBQ - 1) / kAttBQ, a->num_heads, a->batch);
   PK_REQUIRE(a->batch <= 65535 && a->num_heads <= 65535, "pk_attention_fwd: batch/heads exceed grid limits; split the batch");

@@ -957,7 +957,20 @@ struct TcrParams {
   int box_small;               // key rows of the small K / V box (the full box is NMAX)
   float scale_log2;
   unsigned int* flag;
+  unsigned long long* trace;   // PK_ATT_TRACE=1: CTA 0 records clock64 at pipeline events of its first 16 units (tools/attn_trace_tcr.py)
+  const int* route_rows;       // device-side routing: run only when *route_rows >= route_min_rows
+  int route_min_rows;
 };
+
+// trace slot layout: [unit(0..15)][slot(0..15)][event(0..7)]; slots: warps 0-3 as they are, softmax warps 4 / 8 / 12 / 16 -> 4..7
+// (region 0 half 0, region 0 half 1, region 1 half 0, region 1 half 1; lane quarter 0 each), output warps 20-23 -> 8..11
+__device__ __forceinline__ void tcr_trace(const TcrParams& p, int k, int ev) {
+  if (p.trace && blockIdx.x == 0 && k < 16 && (threadIdx.x & 31) == 0) {
+    const int w = threadIdx.x >> 5;
+    const int slot = w < 4 ? w : (w >= 20 ? w - 12 : ((w & 3) == 0 ? 4 + ((w - 4) >> 2) : -1));
+    if (slot >= 0) p.trace[(k * 16 + slot) * 8 + ev] = clock64();
+  }
+}
 
 struct TcrUnit {
   int b, h, qt, row0, len, n_keys, npad;
@@ -983,10 +996,50 @@ __device__ __forceinline__ bool tcr_unit(const TcrParams& p, int u, TcrUnit& t) 
   return true;
 }
 
+// The groups of a unit that hold special keys (multiplicity != 1, the virtual key, padding): x = s * scale + lm[j] with the
+// bias row read from shared memory by its shared-space address (the generic-pointer form costs an address computation and
+// an LD.E per 4 keys).  Volatile without a memory clobber: ordered after the mbarrier wait, invisible to everything else.
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float tcr_lm_max16(const uint32_t* s, uint32_t lm_addr, uint64_t sc2, float mx) {
+  float xs[16];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float4 l = lds_f4(lm_addr + 16 * e);
+    f2_unpack(f2_fma(f2_pack(__uint_as_float(s[4 * e]), __uint_as_float(s[4 * e + 1])), sc2, f2_pack(l.x, l.y)), xs[4 * e], xs[4 * e + 1]);
+    f2_unpack(f2_fma(f2_pack(__uint_as_float(s[4 * e + 2]), __uint_as_float(s[4 * e + 3])), sc2, f2_pack(l.z, l.w)), xs[4 * e + 2], xs[4 * e + 3]);
+  }
+  const float m0 = fmax3(xs[0], xs[1], xs[2]), m1 = fmax3(xs[3], xs[4], xs[5]);
+  const float m2 = fmax3(xs[6], xs[7], xs[8]), m3 = fmax3(xs[9], xs[10], xs[11]);
+  return fmax3(mx, fmax3(fmax3(m0, xs[12], xs[13]), fmax3(m1, xs[14], xs[15]), m2), m3);
+}
+__device__ __forceinline__ float tcr_lm_group16(const uint32_t* s, uint32_t* pk, uint32_t lm_addr, uint64_t sc2, float neg_max) {
+  const uint64_t nm2 = f2_pack(neg_max, neg_max);
+  uint64_t acc = f2_pack(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float4 l = lds_f4(lm_addr + 16 * e);
+    float x0, x1, x2, x3;
+    f2_unpack(f2_add(f2_fma(f2_pack(__uint_as_float(s[4 * e]), __uint_as_float(s[4 * e + 1])), sc2, f2_pack(l.x, l.y)), nm2), x0, x1);
+    f2_unpack(f2_add(f2_fma(f2_pack(__uint_as_float(s[4 * e + 2]), __uint_as_float(s[4 * e + 3])), sc2, f2_pack(l.z, l.w)), nm2), x2, x3);
+    const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2), p3 = ex2_approx(x3);
+    acc = f2_add(acc, f2_add(f2_pack(p0, p1), f2_pack(p2, p3)));
+    pk[2 * e] = pack_bf16(p0, p1);
+    pk[2 * e + 1] = pack_bf16(p2, p3);
+  }
+  float a0, a1;
+  f2_unpack(acc, a0, a1);
+  return a0 + a1;
+}
+
 template <int NMAX>
 __global__ void __launch_bounds__(kTcrThreads, 1)
 attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv_small,
                      const __grid_constant__ CUtensorMap tmap_kv_full, const __grid_constant__ CUtensorMap tmap_out, const TcrParams p) {
+  if (p.route_rows && *p.route_rows < p.route_min_rows) return;      // short samples: the general kernel's launch takes this batch
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using SM = TcrSmem<NMAX>;
@@ -1007,6 +1060,7 @@ attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint64_t* s_free = bars + 21;        // [2] region: O read out (4 output-warp arrivals)
   uint64_t* sum_ready = bars + 23;     // [2] region: row-sum partials published (8 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+  int* plain_groups = reinterpret_cast<int*>(bars + 32);   // [4] leading 16-key groups of unit k & 3 whose bias is all zero
 
   const int warp = warp_id();
   const int lane = lane_id();
@@ -1060,7 +1114,9 @@ attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const bool small = t.npad <= p.box_small;
       const uint32_t kv_bytes = static_cast<uint32_t>(small ? p.box_small : NMAX) * 128u;
       const CUtensorMap* kvmap = small ? &tmap_kv_small : &tmap_kv_full;
+      tcr_trace(p, k, 0);
       if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&qk_empty[qs]), qph ^ 1u, p.flag, 0x3100u + qs))) break;
+      tcr_trace(p, k, 1);
       if (elect_one()) {
         const uint32_t bar = smem_u32(&qk_full[qs]);
         const uint32_t base = smem_u32(smem + qs * SM::kQKSlotBytes);
@@ -1070,6 +1126,7 @@ attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
       __syncwarp();
       if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&v_empty[vs]), vph ^ 1u, p.flag, 0x3110u + vs))) break;
+      tcr_trace(p, k, 2);
       if (elect_one()) {
         const uint32_t bar = smem_u32(&v_full[vs]);
         mbar_expect_tx(bar, kv_bytes);
@@ -1093,8 +1150,11 @@ attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       if ((kk & 1) != r) continue;
       const int qs = r, vs = kk % 3;
       const uint32_t qph = (kk >> 1) & 1u, vph = (kk / 3) & 1u, rph = qph;
+      tcr_trace(p, kk, 0);
       if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&qk_ready[qs]), qph, p.flag, 0x3200u + qs))) break;
+      tcr_trace(p, kk, 1);
       if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&s_free[r]), rph ^ 1u, p.flag, 0x3300u + r))) break;
+      tcr_trace(p, kk, 2);
       if (first && r == 1) {
         // start half a period after region 0 (the two softmax groups then use the MUFU alternately).  A scheduling hint, not a
         // dependency: bounded polling, because region 0 may legitimately be two phases ahead by the time this warp looks
@@ -1114,8 +1174,11 @@ attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         umma_commit(smem_u32(&qk_empty[qs]));
       }
       __syncwarp();
+      tcr_trace(p, kk, 3);
       if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&p_ready[r]), rph, p.flag, 0x3400u + r))) break;
+      tcr_trace(p, kk, 4);
       if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&v_ready[vs]), vph, p.flag, 0x3410u + vs))) break;
+      tcr_trace(p, kk, 5);
       tcgen05_fence_after();
       const int G = t.npad >> 4, G0 = (G + 1) >> 1;
       if (elect_one()) {                       // O = P V; P of key group g sits where the half that owns it packed it
@@ -1141,13 +1204,21 @@ attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const uint32_t qph = (k >> 1) & 1u, vph = (k / 3) & 1u;
       float* lm = lm_rows + (k & 3) * 256;
       // bias row (its previous user, unit k - 4, finished its softmax before this unit's Q/K slot could even be refilled)
+      int first_special = NMAX;                    // first key whose bias is not zero (multiplicity != 1, virtual key, padding)
       for (int j = lane; j < NMAX; j += 32) {
         float v = -INFINITY;
         if (j < t.len) v = p.key_mult ? __log2f(p.key_mult[t.row0 + j]) : 0.f;
         else if (j == t.len && t.extra > 0.f) v = __log2f(t.extra);
         lm[j] = v;
+        if (v != 0.f && j < first_special) first_special = j;
       }
+      // Multiplicities other than 1 sit at the END of a sample (its ghost row, then the virtual key, then padding), so nearly
+      // every 16-key group is "plain": the softmax takes x = s * scale there without reading the bias row.
+      first_special = warp_min_i32(first_special);
+      if (lane == 0) plain_groups[k & 3] = first_special >> 4;
+      tcr_trace(p, k, 0);
       if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&qk_full[qs]), qph, p.flag, 0x3800u + qs))) break;
+      tcr_trace(p, k, 1);
       if (t.extra > 0.f && lane < 8) {
         // K row `len`: 16-byte chunk c of row j lives at chunk c ^ (j & 7) of its 128-byte line (SWIZZLE_128B)
         const uint4 kb = *reinterpret_cast<const uint4*>(p.extra_kv + t.h * kTcDH + lane * 8);
@@ -1157,6 +1228,7 @@ attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&qk_ready[qs]));
       if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&v_full[vs]), vph, p.flag, 0x3810u + vs))) break;
+      tcr_trace(p, k, 2);
       if (t.extra > 0.f && lane < 8) {
         const uint4 vb = *reinterpret_cast<const uint4*>(p.extra_kv + D + t.h * kTcDH + lane * 8);
         *reinterpret_cast<uint4*>(smem + SM::kVOff + vs * SM::kKBytes + t.len * 128 + ((lane ^ (t.len & 7)) << 4)) = vb;
@@ -1186,7 +1258,9 @@ attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       if ((kk & 1) != r) continue;
       const uint32_t rph = (kk >> 1) & 1u;
       const float* lm = lm_rows + (kk & 3) * 256;
+      tcr_trace(p, kk, 0);
       if (!mbar_wait(smem_u32(&s_full[r]), rph, p.flag, 0x3500u + r)) break;
+      tcr_trace(p, kk, 1);
       tcgen05_fence_after();
       const bool warp_has_rows = t.qt * 128 + q * 32 < t.len;           // warp-uniform, same for both halves of a quarter
       if (warp_has_rows) {
@@ -1195,68 +1269,55 @@ attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint32_t pcol0 = half ? static_cast<uint32_t>(16 * G0) : 0u;
         const uint64_t sc2 = f2_pack(scale_log2, scale_log2);
         uint32_t ha[16], hb[16];
-        // ---- pass 1: partial row maximum of x = s * scale * log2e + lm (padding columns carry lm = -inf)
-        float mx = -INFINITY;
-        if (gn > 0) {
-          tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(16 * gb), ha);
+        // ---- pass 1: partial row maximum of x = s * scale * log2e + lm (padding columns carry lm = -inf).  Groups of plain
+        // keys (lm == 0: all but the last one or two of a sample) take the maximum of the raw scores, scaled once at the end
+        // (scale > 0), 32 columns per TMEM round trip like the dense kernel.
+        const int n_plain = plain_groups[kk & 3];
+        const int np = min(gn, max(n_plain - gb, 0));               // this half's leading plain groups
+        const uint32_t lm_s = smem_u32(lm);
+        float mx = -INFINITY, mraw = -INFINITY;
+        int j = 0;
+        for (; j + 2 <= np; j += 2) {
+          uint32_t w[32];
+          tmem_ld_32x32(t_base + static_cast<uint32_t>(16 * (gb + j)), w);
           tmem_ld_wait();
+          mraw = row_max16<false>(w, mraw, 0, 0);
+          mraw = row_max16<false>(w + 16, mraw, 0, 0);
         }
-        for (int j = 0; j < gn; ++j) {
-          uint32_t (&cur)[16] = (j & 1) ? hb : ha;
-          uint32_t (&nxt)[16] = (j & 1) ? ha : hb;
-          if (j + 1 < gn) tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(16 * (gb + j + 1)), nxt);
-          const float4* l4 = reinterpret_cast<const float4*>(lm + 16 * (gb + j));
-          float xs[16];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float4 l = l4[e];
-            float a0, a1, a2, a3;
-            f2_unpack(f2_fma(f2_pack(__uint_as_float(cur[4 * e]), __uint_as_float(cur[4 * e + 1])), sc2, f2_pack(l.x, l.y)), a0, a1);
-            f2_unpack(f2_fma(f2_pack(__uint_as_float(cur[4 * e + 2]), __uint_as_float(cur[4 * e + 3])), sc2, f2_pack(l.z, l.w)), a2, a3);
-            xs[4 * e] = a0; xs[4 * e + 1] = a1; xs[4 * e + 2] = a2; xs[4 * e + 3] = a3;
-          }
-          const float m0 = fmax3(xs[0], xs[1], xs[2]), m1 = fmax3(xs[3], xs[4], xs[5]);
-          const float m2 = fmax3(xs[6], xs[7], xs[8]), m3 = fmax3(xs[9], xs[10], xs[11]);
-          mx = fmax3(mx, fmax3(fmax3(m0, xs[12], xs[13]), fmax3(m1, xs[14], xs[15]), m2), m3);
-          if (j + 1 < gn) tmem_ld_wait();
+        for (; j < gn; ++j) {
+          tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(16 * (gb + j)), ha);
+          tmem_ld_wait();
+          if (j < np) mraw = row_max16<false>(ha, mraw, 0, 0);
+          else mx = tcr_lm_max16(ha, lm_s + static_cast<uint32_t>(64 * (gb + j)), sc2, mx);
         }
+        mx = fmaxf(mx, mraw * scale_log2);           // -inf * scale stays -inf
         *mx_mine = mx;
+        tcr_trace(p, kk, 2);
         named_bar_sync(bar_id, 64);
         mx = fmaxf(mx, *mx_other);
-        const uint64_t nm2 = f2_pack(-mx, -mx);
+        tcr_trace(p, kk, 3);
         // ---- pass 2: p = exp2(x - max), partial row sum, bf16 P packed over this half's own consumed S columns
         float sum = 0.f;
         if (gn > 0) {
           tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(16 * gb), ha);
           tmem_ld_wait();
         }
-        for (int j = 0; j < gn; ++j) {
+        tcr_trace(p, kk, 5);
+        for (j = 0; j < gn; ++j) {
           uint32_t (&cur)[16] = (j & 1) ? hb : ha;
           uint32_t (&nxt)[16] = (j & 1) ? ha : hb;
           if (j + 1 < gn) tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(16 * (gb + j + 1)), nxt);
-          const float4* l4 = reinterpret_cast<const float4*>(lm + 16 * (gb + j));
           uint32_t pk[8];
-          uint64_t acc = f2_pack(0.f, 0.f);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float4 l = l4[e];
-            float x0, x1, x2, x3;
-            f2_unpack(f2_add(f2_fma(f2_pack(__uint_as_float(cur[4 * e]), __uint_as_float(cur[4 * e + 1])), sc2, f2_pack(l.x, l.y)), nm2), x0, x1);
-            f2_unpack(f2_add(f2_fma(f2_pack(__uint_as_float(cur[4 * e + 2]), __uint_as_float(cur[4 * e + 3])), sc2, f2_pack(l.z, l.w)), nm2), x2, x3);
-            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2), p3 = ex2_approx(x3);
-            acc = f2_add(acc, f2_add(f2_pack(p0, p1), f2_pack(p2, p3)));
-            pk[2 * e] = pack_bf16(p0, p1);
-            pk[2 * e + 1] = pack_bf16(p2, p3);
-          }
-          float a0, a1;
-          f2_unpack(acc, a0, a1);
-          sum += a0 + a1;
+          if (j < np) sum += softmax_group16<false, 0, 0>(cur, pk, scale_log2, -mx, 0, 0);
+          else sum += tcr_lm_group16(cur, pk, lm_s + static_cast<uint32_t>(64 * (gb + j)), sc2, -mx);
           if (j + 1 < gn) tmem_ld_wait();        // the next group is in registers before its columns may be overwritten
           tmem_st_32x32_x8(t_base + pcol0 + static_cast<uint32_t>(8 * j), pk);
         }
+        tcr_trace(p, kk, 7);
         *sum_mine = sum;
         tmem_st_wait();
       }
+      tcr_trace(p, kk, 4);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -1277,8 +1338,10 @@ attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const int r = kk & 1;
       const uint32_t rph = (kk >> 1) & 1u;
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(r * kTcRegionCols);
+      tcr_trace(p, kk, 0);
       if (!mbar_wait(smem_u32(&sum_ready[r]), rph, p.flag, 0x3700u + r)) break;
       if (!mbar_wait(smem_u32(&o_full[r]), rph, p.flag, 0x3600u + r)) break;
+      tcr_trace(p, kk, 1);
       tcgen05_fence_after();
       const int lrow0 = t.qt * 128 + q * 32;               // first row of this warp's block inside the sample
       const bool has_rows = lrow0 < t.len;                 // warp-uniform
@@ -1294,6 +1357,7 @@ attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s_free[r]));     // the region may take its next unit's S
+      tcr_trace(p, kk, 2);
       if (!has_rows) continue;
       auto chunk = [&](int c) {                             // 8 scaled bf16 values = 16-byte chunk c of this thread's row
         const uint32_t* src = c < 4 ? &o0[8 * c] : &o[8 * (c - 4)];
@@ -1319,6 +1383,7 @@ attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
         for (int c = 0; c < 8; ++c) dst[c] = chunk(c);
       }
+      tcr_trace(p, kk, 3);
     }
     if (lane == 0) bulk_wait_read<0>();       // smem must outlive the last store's reads
   }
@@ -1496,11 +1561,12 @@ static int tcr_enabled() {
   if (v < 0) { const char* e = getenv("PK_ATT_TCR"); v = (e && e[0] == '0') ? 0 : 1; }
   return v;
 }
-// PK_ATT_TCR_UNIFORM_MAX: longest UNIFORM plain sequence routed to the ragged kernel instead of the general one (default 64:
-// the dense tc3 kernel takes 65 .. 256)
+// PK_ATT_TCR_UNIFORM_MAX: longest UNIFORM plain sequence routed to the ragged kernel instead of the general one.  Default 0:
+// on the pruned RankViT layers (50 / 33 / 26 / 14 tokens) the general kernel is 2x faster (profiles/r02/run16_attn_ragged.json:
+// 49.9 vs 109.8 us at 50 tokens), and the dense tc3 kernel takes 65 .. 256.
 static int tcr_uniform_max() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("PK_ATT_TCR_UNIFORM_MAX"); v = e ? atoi(e) : 64; }
+  if (v < 0) { const char* e = getenv("PK_ATT_TCR_UNIFORM_MAX"); v = e ? atoi(e) : 0; }
   return v;
 }
 bool attention_tcr_eligible(const pk_attention_args* a) {
@@ -1544,6 +1610,9 @@ static int launch_tcr(const pk_attention_args* a, cudaStream_t stream, int max_l
   p.box_small = box_small;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.flag = device_flag_ptr();
+  p.trace = tc_trace_buffer();
+  p.route_rows = (a->impl == 0) ? a->route_rows : nullptr;
+  p.route_min_rows = a->route_min_rows;
   const long long units = static_cast<long long>(a->batch) * a->num_heads * p.q_tiles;
   int grid = num_sms();
   if (units < grid) grid = static_cast<int>(units);

@@ -76,6 +76,8 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+__device__ __forceinline__ int warp_min_i32(int v) { return __reduce_min_sync(0xffffffffu, v); }
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -136,6 +138,24 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return done;
 }
+// try_wait with a suspend-time hint: the waiting thread is parked by the hardware until the phase completes or `ns`
+// nanoseconds pass, instead of coming back at once and re-issuing the probe.  Measured on the ragged attention kernel (ncu,
+// profiles/r02): the plain form returned immediately, and the softmax warps of the idle TMEM region spent a quarter of the
+// SM's issued instructions polling s_full -- on the very schedulers the other region's softmax warps were running on.
+#ifndef PK_MBAR_SUSPEND_NS
+#define PK_MBAR_SUSPEND_NS 2000
+#endif
+__device__ __forceinline__ uint32_t mbar_try_wait_suspend(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity), "r"(PK_MBAR_SUSPEND_NS)
+      : "memory");
+  return done;
+}
 __device__ __forceinline__ unsigned long long global_timer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -146,7 +166,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, unsigne
   if (mbar_try_wait(bar, parity)) return true;
   unsigned long long t0 = 0;
   for (uint32_t it = 1;; ++it) {
-    if (mbar_try_wait(bar, parity)) return true;
+    if (mbar_try_wait_suspend(bar, parity)) return true;
     if ((it & 0x3ffu) == 0) {
       if (*(volatile unsigned int*)flag != 0u) return false;
       const unsigned long long now = global_timer_ns();

@@ -37,6 +37,9 @@ EMBED_TOKEN_ROWS = int(os.environ.get("PEEKVIT_B200_EMBED_TOKEN_ROWS", "1"))
 HEAD_GEMM = int(os.environ.get("PEEKVIT_B200_HEAD_GEMM", "1"))
 # MoE expert fc2: un-permute + residual add inside the GEMM epilogue (row-indexed reductions) instead of a sorted fp32 output
 # followed by pk_scatter_add_rows (A/B switch)
+# ragged attention: mean live rows per sample from which the two-region tcgen05 kernel beats the general mma.sync kernel
+# (tools/attn_ragged_bench.py, profiles/r02)
+ATT_TCR_MIN_MEAN_ROWS = int(os.environ.get("PEEKVIT_B200_ATT_TCR_MIN_MEAN_ROWS", "140"))
 MOE_FUSED_SCATTER = int(os.environ.get("PEEKVIT_B200_MOE_FUSED_SCATTER", "1"))
 
 
@@ -462,9 +465,12 @@ class Forward:
                           rows_dev=rows_dev)
         # zeroed once: the ragged tcgen05 attention loads fixed-size key tiles, i.e. also rows past the live ones (masked)
         qkv = ops.gemm(a, aw.w_qkv, aw.b_qkv, ws.get("qkv", (rows, 3 * D), torch.bfloat16, zero=True), PK_EPI_BIAS_BF16, m_dev=rows_dev)
+        # ragged batches: the tcgen05 kernel when the live rows average ATT_TCR_MIN_MEAN_ROWS per sample or more, the general
+        # mma.sync kernel below that -- decided on the device from the live row count (both launches are in the graph)
         att = ops.attention(qkv, ws.get("att", (rows, D), torch.bfloat16), batch, pm.heads, D // pm.heads, seq_len=seq,
                             cu_seqlens=cu, max_seq_len=max_len, key_mult=key_mult,
-                            extra_kv=aw.bias_kv if extra_mult is not None else None, extra_mult=extra_mult)
+                            extra_kv=aw.bias_kv if extra_mult is not None else None, extra_mult=extra_mult,
+                            route_rows=rows_dev if cu is not None else None, route_min_rows=batch * ATT_TCR_MIN_MEAN_ROWS)
         ops.gemm(att, aw.w_o, aw.b_o, x[:rows], PK_EPI_BIAS_RESID_F32, resid=x[:rows], rowscale=rowscale, m_dev=rows_dev)
 
     def mlp_part(self, x, lw: LayerWeights, rows: int, *, rows_dev=None, rowscale=None, residual: bool = True) -> None:

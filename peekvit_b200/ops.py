@@ -177,7 +177,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 def attention(qkv: torch.Tensor, out: torch.Tensor, batch: int, num_heads: int, head_dim: int, *, seq_len: int = 0,
               cu_seqlens: Optional[torch.Tensor] = None, max_seq_len: int = 0, key_mult: Optional[torch.Tensor] = None,
               extra_kv: Optional[torch.Tensor] = None, extra_mult: Optional[torch.Tensor] = None, impl: int = 0,
-              half_split: bool = False) -> torch.Tensor:
+              half_split: bool = False, route_rows: Optional[torch.Tensor] = None, route_min_rows: int = 0) -> torch.Tensor:
     """``half_split`` (bf16x2 mode, tcgen05 kernel): qkv is IEEE half, out is bf16 [rows, 2*D] = the result split [lo | hi]."""
     lib = _lib_for(qkv)
     D = num_heads * head_dim
@@ -196,6 +196,7 @@ def attention(qkv: torch.Tensor, out: torch.Tensor, batch: int, num_heads: int, 
     a.extra_mult = _ptr(extra_mult, torch.float32)
     a.impl = impl
     a.total_rows = qkv.shape[0]
+    a.route_rows, a.route_min_rows = _ptr(route_rows, torch.int32), int(route_min_rows)
     check(lib.pk_attention_fwd(C.byref(a), _stream()), "pk_attention_fwd")
     return out
 

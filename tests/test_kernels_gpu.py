@@ -709,3 +709,25 @@ def test_attention_ragged_tcgen05_full_size_row_sum_property(ops):
     assert ops.device_flag() == 0
     assert float((out[:rows].float() - 1.0).abs().max()) < 1e-2
     assert bool((out[rows:] == 0).all())
+
+
+@pytest.mark.parametrize("min_rows", [1, 10 ** 9])
+def test_attention_ragged_device_side_routing(ops, min_rows):
+    """route_rows / route_min_rows: both ragged kernels are launched and the device-side live row count picks the one that
+    runs (threshold 1: the tcgen05 kernel; threshold 1e9: the general kernel); the other leaves the output untouched."""
+    lens = [150, 33, 198, 77, 120]
+    B, H, dh = len(lens), 6, 64
+    D = H * dh
+    qkv, cu, km, ekv, em, rows = _ragged_case(lens, H, 5, True, True, pad_rows=16)
+    out = torch.full((rows + 16, D), 3.0, device=DEV, dtype=torch.bfloat16)
+    rows_dev = torch.tensor([rows], device=DEV, dtype=torch.int32)
+    ops.attention(qkv, out, B, H, dh, cu_seqlens=cu, max_seq_len=199, key_mult=km, extra_kv=ekv, extra_mult=em,
+                  route_rows=rows_dev, route_min_rows=min_rows)
+    assert ops.device_flag() == 0
+    ref = ref_attention(qkv[:rows], B, H, dh, lens, km[:rows], ekv, em)
+    assert rel_err(out[:rows], ref) < TOL_BF16
+    assert bool((out[rows:] == 3.0).all())
+    forced = torch.zeros_like(out)
+    ops.attention(qkv, forced, B, H, dh, cu_seqlens=cu, max_seq_len=199, key_mult=km, extra_kv=ekv, extra_mult=em,
+                  impl=3 if min_rows == 1 else 1)
+    assert torch.equal(out[:rows], forced[:rows])          # bit-identical to the kernel the threshold selects
