@@ -467,6 +467,33 @@ def run_variants(dev, rank, world, timer: Timer, sampler, images_full, steps_hin
     out["E_moevit_s_4experts"].update(config="E", x_dense=v / dense_s, experts=4,
                                       note="same FLOPs as the dense ViT-S (arg-max routing); the reference evaluates all experts densely")
     del m
+    # ---- fine-tuning step: forward + cross-entropy + backward of the class-token / head regime on ViT-B/16
+    # (train/train.py:97-127 with the backbone frozen), gradients averaged over the ranks by one NCCL all-reduce per step
+    try:
+        from peekvit_b200.finetune import FineTuner
+        m = make_model("vit", CFG_B, dev)
+        m.train()
+        ft = FineTuner(m, micro_batch=128)
+        nb = 512
+        xb, yb = images_full[:nb], torch.randint(0, CFG_B["num_classes"], (nb,), device=dev)
+        opt = torch.optim.SGD([p for p in m.parameters() if p.requires_grad], lr=1e-3)
+
+        def train_step():
+            opt.zero_grad()
+            ft.forward_backward(xb, yb)
+            opt.step()
+        for _ in range(2):
+            train_step()
+        ms, t0, t1 = timer.run(train_step, 3)
+        entry = {"value": world * nb * 3 / (ms * 1e-3), "unit": "images/sec", "images_per_gpu_per_step": nb, "steps": 3,
+                 "ms_per_step": ms / 3, "config": "f4", "regime": "class_tokens + head trainable, backbone frozen (activation gradients only)",
+                 "includes": "forward, cross-entropy, backward, gradient all-reduce, SGD step"}
+        if rank == 0 and sampler is not None:
+            entry["clocks"] = sampler.window(t0, t1)
+        out["F_finetune_vit_b_16_cls_head"] = entry
+        del m, ft, opt
+    except Exception as e:      # noqa: BLE001  (a bench line must not die on the optional leg)
+        out["F_finetune_vit_b_16_cls_head"] = {"error": str(e)[:300]}
     out["device_flag"] = ops.device_flag()
     torch.cuda.empty_cache()
     return out

@@ -327,6 +327,37 @@ int pk_patchify_split2(const float* images, void* patches3, int batch, int image
 int pk_attention_f32(const float* qkv, float* out, int batch, int num_heads, int head_dim, int seq_len, float scale,
                      const int* cu_seqlens, const float* key_mult, const float* extra_kv, const float* extra_mult, void* stream);
 
+/* ---- fine-tuning path: backward of the frozen-backbone regime ---------------------------------------
+ * The reference trains with `train_only_these_params(model, ['gate', 'class', 'head', 'threshold', 'budget'])`
+ * (train/train.py:97-127, models/topology.py:128-158): gradients are needed for a few small parameters only, but the class
+ * tokens are an INPUT of the encoder, so the loss gradient travels back through every block as an activation gradient.
+ * The four dX GEMMs of a block are pk_gemm_bf16 calls on the transposed weights; the entry points below are the rest
+ * (what torch autograd runs as LayerNormBackward / GeluBackward / the MHA core backward / NllLossBackward / AddmmBackward in
+ * `loss.backward()`, train/train.py:113). */
+int pk_cast_f32_bf16(const float* x, void* y_bf16, long long n, void* stream);
+/* hid = gelu(h_pre) and dh_pre = dhid * gelu'(h_pre), exact erf form (models/blocks.py:82), bf16 in / out; the training
+ * forward keeps the fc1 pre-activation instead of fusing the GELU into the fc1 epilogue. */
+int pk_gelu_bf16(const void* h_pre, void* hid, long long n, void* stream);
+int pk_gelu_bwd_bf16(const void* h_pre, const void* dhid, void* dh_pre, long long n, void* stream);
+/* Input gradient of LayerNorm (gamma / beta frozen): dx (+)= rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma.
+ * row_index (optional) maps launch row r to row row_index[r] of x / dx; dy row = r / dy_div (the class rows of the final
+ * LayerNorm share one feature gradient, vit.py:242-243). */
+int pk_layernorm_bwd(const float* x, const float* dy, const float* gamma, float eps, float* dx, int rows, int dim,
+                     const int* row_index, int dy_div, int accumulate, void* stream);
+/* Backward of the attention core softmax(Q K^T * scale) V for uniform sequences (<= 256 tokens, head_dim 32 / 64):
+ * qkv [rows, 3D] and out = the forward result [rows, D], dout [rows, D] -> dqkv [rows, 3D], all bf16 (blocks.py:93-95). */
+int pk_attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv, int batch, int num_heads, int head_dim,
+                     int seq_len, float scale, void* stream);
+/* Cross-entropy of int64 labels (train/train.py:106-107, nn.CrossEntropyLoss mean): *loss_sum += sum_b -log p[label] *
+ * inv_count, dlogits = (softmax - onehot) * inv_count, *correct += #(argmax == label) (optional). */
+int pk_softmax_xent(const float* logits, const long long* labels, int batch, int classes, float inv_count, float* loss_sum,
+                    float* dlogits, int* correct, void* stream);
+/* Linear head backward (vit.py:246): d_weight += dlogits^T feat, d_bias += sum_b dlogits, d_feat = dlogits weight. */
+int pk_head_bwd(const float* dlogits, const float* feat, const float* weight, int batch, int classes, int dim, float* d_weight,
+                float* d_bias, float* d_feat, void* stream);
+/* out[t, :] += sum_b x[b * seq + row0 + t, :]: gradient of the class / register token parameters (vit.py:230-236). */
+int pk_sum_token_rows(const float* x, int batch, int seq, int row0, int n_rows, int dim, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -128,6 +128,14 @@ SIGNATURES: Dict[str, tuple] = {
     "pk_patchify_split2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pk_attention_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pk_noise_snr": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
+    "pk_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
+    "pk_gelu_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
+    "pk_gelu_bwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
+    "pk_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "pk_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "pk_softmax_xent": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pk_head_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pk_sum_token_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pk_row_scale_add": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "pk_zero_token_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "pk_moe_route": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,

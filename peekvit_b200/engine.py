@@ -305,6 +305,20 @@ def pack_model(model, family: str) -> PackedModel:
     return pm
 
 
+LIGHT_PARAMS = ("class_tokens", "class_token", "head.weight", "head.bias")
+
+
+def refresh_light(pm: "PackedModel", model) -> None:
+    """Re-read the class tokens and the head from the live module into an existing weight pack (same storage), and drop
+    what was derived from them: the embedding's initial rows and the split head weight."""
+    cls = model.class_token if pm.family == "moevit" else model.class_tokens
+    pm.cls_tokens.copy_(cls.detach().reshape(-1, pm.dim))
+    pm.head_w.copy_(model.head.weight.detach())
+    pm.head_b.copy_(model.head.bias.detach())
+    pm.__dict__.pop("_embed_consts", None)
+    pm.extra.pop("head_w6", None)
+
+
 def params_fingerprint(model) -> tuple:
     """Changes whenever a parameter is rebound, moved or modified in place, or ``encoder.layers`` is edited
     (layers deleted, a parameter-free NoiseBlock spliced in)."""

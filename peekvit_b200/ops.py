@@ -564,3 +564,65 @@ def patchify_u8(images_hwc: torch.Tensor, patch_size: int, out: Optional[torch.T
     check(lib.pk_patchify_u8(_ptr(images_hwc, torch.uint8), _ptr(out, torch.bfloat16), B, S, patch_size, m, s, rows_per_sample, row_offset,
                              _stream()), "pk_patchify_u8")
     return out
+
+
+# ---------------------------------------------------------------- fine-tuning path (csrc/pk_train.cu)
+def cast_bf16(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    lib = _lib_for(x)
+    check(lib.pk_cast_f32_bf16(_ptr(x, torch.float32), _ptr(out, torch.bfloat16), x.numel(), _stream()), "pk_cast_f32_bf16")
+    return out
+
+
+def gelu_bf16(h_pre: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    lib = _lib_for(h_pre)
+    check(lib.pk_gelu_bf16(_ptr(h_pre, torch.bfloat16), _ptr(out, torch.bfloat16), h_pre.numel(), _stream()), "pk_gelu_bf16")
+    return out
+
+
+def gelu_bwd_bf16(h_pre: torch.Tensor, dhid: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    lib = _lib_for(h_pre)
+    check(lib.pk_gelu_bwd_bf16(_ptr(h_pre, torch.bfloat16), _ptr(dhid, torch.bfloat16), _ptr(out, torch.bfloat16), h_pre.numel(), _stream()),
+          "pk_gelu_bwd_bf16")
+    return out
+
+
+def layernorm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: float, dx: torch.Tensor, rows: int, *,
+                  row_index: Optional[torch.Tensor] = None, dy_div: int = 1, accumulate: bool = True) -> torch.Tensor:
+    lib = _lib_for(x)
+    check(lib.pk_layernorm_bwd(_ptr(x, torch.float32), _ptr(dy, torch.float32), _ptr(gamma, torch.float32), float(eps),
+                               _ptr(dx, torch.float32), rows, x.shape[-1], _ptr(row_index, torch.int32), dy_div, int(accumulate),
+                               _stream()), "pk_layernorm_bwd")
+    return dx
+
+
+def attention_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, dqkv: torch.Tensor, batch: int, num_heads: int,
+                  head_dim: int, seq_len: int) -> torch.Tensor:
+    lib = _lib_for(qkv)
+    check(lib.pk_attention_bwd(_ptr(qkv, torch.bfloat16), _ptr(out, torch.bfloat16), _ptr(dout, torch.bfloat16),
+                               _ptr(dqkv, torch.bfloat16), batch, num_heads, head_dim, seq_len, 1.0 / math.sqrt(head_dim), _stream()),
+          "pk_attention_bwd")
+    return dqkv
+
+
+def softmax_xent(logits: torch.Tensor, labels: torch.Tensor, inv_count: float, loss_sum: torch.Tensor, dlogits: torch.Tensor,
+                 correct: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib_for(logits)
+    check(lib.pk_softmax_xent(_ptr(logits, torch.float32), _ptr(labels, torch.int64), logits.shape[0], logits.shape[1], float(inv_count),
+                              _ptr(loss_sum, torch.float32), _ptr(dlogits, torch.float32), _ptr(correct, torch.int32), _stream()),
+          "pk_softmax_xent")
+    return dlogits
+
+
+def head_bwd(dlogits: torch.Tensor, feat: torch.Tensor, weight: torch.Tensor, d_weight: torch.Tensor, d_bias: torch.Tensor,
+             d_feat: torch.Tensor) -> None:
+    lib = _lib_for(dlogits)
+    B, C_ = dlogits.shape
+    check(lib.pk_head_bwd(_ptr(dlogits, torch.float32), _ptr(feat, torch.float32), _ptr(weight, torch.float32), B, C_, feat.shape[1],
+                          _ptr(d_weight, torch.float32), _ptr(d_bias, torch.float32), _ptr(d_feat, torch.float32), _stream()), "pk_head_bwd")
+
+
+def sum_token_rows(x: torch.Tensor, batch: int, seq: int, row0: int, n_rows: int, out: torch.Tensor) -> torch.Tensor:
+    lib = _lib_for(x)
+    check(lib.pk_sum_token_rows(_ptr(x, torch.float32), batch, seq, row0, n_rows, x.shape[-1], _ptr(out, torch.float32), _stream()),
+          "pk_sum_token_rows")
+    return out

@@ -51,9 +51,20 @@ def packed(model) -> engine.PackedModel:
     st = _state(model)
     fp = engine.params_fingerprint(model)
     if st["fp"] != fp:
-        st["pm"] = engine.pack_model(model, model._family)
+        old, pm = st["fp"], st["pm"]
+        light = False
+        if pm is not None and old is not None and len(old) == len(fp):
+            # an optimiser step of the fine-tuning regime (class tokens / head only, peekvit_b200.finetune) changes three small
+            # tensors: refresh them in place instead of converting 86 M frozen weights again
+            names = [n for n, _ in model.named_parameters()]
+            changed = [i for i, (a, b) in enumerate(zip(old, fp)) if a != b]
+            light = bool(changed) and all(i < len(names) and names[i] in engine.LIGHT_PARAMS for i in changed)
+        if light:
+            engine.refresh_light(pm, model)
+        else:
+            st["pm"] = engine.pack_model(model, model._family)
         st["fp"] = fp
-        st.pop("graphs", None)          # captured launch sequences point at the old weight pack
+        st.pop("graphs", None)          # captured launch sequences point at the old weight pack / its derived constants
     return st["pm"]
 
 
