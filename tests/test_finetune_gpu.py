@@ -70,6 +70,10 @@ def test_attention_bwd_against_autograd(B, H, dh, n):
     ops.attention_bwd(qkv, o.detach().to(torch.bfloat16), dout, dqkv, B, H, dh, n)
     assert ops.device_flag() == 0
     for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+        if n == 1 and name != "dv":
+            # a single key: the softmax is the constant 1 and dq = dk = 0 exactly; here dS is the bf16 rounding residue of O
+            assert dqkv[:, sl].float().abs().max().item() < 1e-2 * ref.abs().max().item(), name
+            continue
         assert _rel(dqkv[:, sl], ref[:, sl]) < 1e-2, name                               # bf16 rounding of the stored O and of the result
 
 
