@@ -13,6 +13,8 @@
 #include "peekvit_b200.h"
 #include "pk_common.cuh"
 
+#include <cstdlib>
+
 namespace pk {
 
 static int train_grid(long long items, int per_block) {
@@ -276,6 +278,228 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
   }
 }
 
+// ------------------------------------------------------------------ attention core backward on the tensor cores (head_dim 64)
+// Same contract as attention_bwd_kernel, five matrix products per (sample, head) -- S = Q K^T, dP = dO V^T, dQ = dS K,
+// dK = dS^T Q, dV = P^T dO -- as mma.sync m16n8k16 bf16 tiles with fp32 accumulation (the backward is a training-only path
+// next to tcgen05 forward kernels; its products are 197 x 197 x 64, far below one tcgen05 tile pipeline's start-up cost).
+// Q, K, V, dO of the head sit in shared memory (bf16, 144-byte rows: conflict-free ldmatrix).  Phase 1, warp = block of 16
+// queries: sweep the keys once for the row statistics (log2-sum-exp), once more for P, dP, dS and dQ (dS leaves the
+// accumulator registers as the A operand of dS K).  Phase 2, warp = block of 16 keys: sweep the query blocks with the
+// TRANSPOSED tiles S^T = K Q^T, dP^T = V dO^T, so P^T and dS^T come out of the accumulators in A-operand layout for
+// dV += P^T dO and dK += dS^T Q.  S and dP are computed twice; nothing is reduced across warps, nothing is atomic.
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+constexpr int kMmaPitch = 72;                   // bf16 elements per shared row (64 + 8)
+
+// C tiles (16 x 16 as two n8 tiles) of  X_blk[16 rows] . Y_blk[16 rows]^T  over head_dim 64: A fragments of X preloaded,
+// B fragments of Y (rows = the product's columns) by non-transposed ldmatrix.
+__device__ __forceinline__ void tile_xyT(float (&c)[2][4], const uint32_t (&ax)[4][4], uint32_t y_rows_addr, int lane) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
+  const uint32_t lane_off = static_cast<uint32_t>((((lane & 7) + ((lane >> 4) << 3)) * kMmaPitch + ((lane >> 3) & 1) * 8) * 2);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t b[4];
+    ldsm_x4(y_rows_addr + lane_off + ks * 32, b);
+    mma_bf16(c[0], ax[ks], b[0], b[1]);
+    mma_bf16(c[1], ax[ks], b[2], b[3]);
+  }
+}
+// A fragments (4 k-steps over head_dim 64) of a block of 16 rows
+__device__ __forceinline__ void load_a64(uint32_t (&a)[4][4], uint32_t rows_addr, int lane) {
+  const uint32_t lane_off = static_cast<uint32_t>(((lane & 15) * kMmaPitch + (lane >> 4) * 8) * 2);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) ldsm_x4(rows_addr + lane_off + ks * 32, a[ks]);
+}
+// acc[16 x 64] += A[16 x 16] . Z_blk[16 rows x 64]   (Z rows = the contraction index: transposed ldmatrix)
+__device__ __forceinline__ void acc_a_z(float (&acc)[8][4], const uint32_t (&a)[4], uint32_t z_rows_addr, int lane) {
+  const uint32_t lane_off = static_cast<uint32_t>((((lane & 7) + ((lane >> 3) & 1) * 8) * kMmaPitch + (lane >> 4) * 8) * 2);
+#pragma unroll
+  for (int dt2 = 0; dt2 < 4; ++dt2) {
+    uint32_t b[4];
+    ldsm_x4_t(z_rows_addr + lane_off + dt2 * 32, b);
+    mma_bf16(acc[2 * dt2], a, b[0], b[1]);
+    mma_bf16(acc[2 * dt2 + 1], a, b[2], b[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+attention_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                         __nv_bfloat16* __restrict__ dqkv, int num_heads, int n, float scale) {
+  constexpr int DH = 64;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int NP = (n + 15) & ~15;
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* Ks = Qs + NP * kMmaPitch;
+  __nv_bfloat16* Vs = Ks + NP * kMmaPitch;
+  __nv_bfloat16* Gs = Vs + NP * kMmaPitch;
+  float* lse = reinterpret_cast<float*>(Gs + NP * kMmaPitch);
+  float* Dv = lse + NP;
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int D = num_heads * DH;
+  const long long row0 = static_cast<long long>(b) * n;
+  // ---- phase 0: the head's Q, K, V, dO tiles (rows >= n zero)
+  for (int i = tid; i < NP * 8; i += blockDim.x) {
+    const int r = i >> 3, c = i & 7;
+    uint4 q4 = make_uint4(0, 0, 0, 0), k4 = q4, v4 = q4, g4 = q4;
+    if (r < n) {
+      const __nv_bfloat16* src = qkv + (row0 + r) * 3ll * D + h * DH + c * 8;
+      q4 = *reinterpret_cast<const uint4*>(src);
+      k4 = *reinterpret_cast<const uint4*>(src + D);
+      v4 = *reinterpret_cast<const uint4*>(src + 2 * D);
+      g4 = *reinterpret_cast<const uint4*>(dout + (row0 + r) * static_cast<long long>(D) + h * DH + c * 8);
+    }
+    *reinterpret_cast<uint4*>(Qs + r * kMmaPitch + c * 8) = q4;
+    *reinterpret_cast<uint4*>(Ks + r * kMmaPitch + c * 8) = k4;
+    *reinterpret_cast<uint4*>(Vs + r * kMmaPitch + c * 8) = v4;
+    *reinterpret_cast<uint4*>(Gs + r * kMmaPitch + c * 8) = g4;
+  }
+  __syncthreads();
+  for (int r = tid; r < NP; r += blockDim.x) {       // D_i = dO_i . O_i
+    float acc = 0.f;
+    if (r < n) {
+      const __nv_bfloat16* orow = o + (row0 + r) * static_cast<long long>(D) + h * DH;
+      for (int c = 0; c < DH; c += 2) {
+        const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(Gs + r * kMmaPitch + c);
+        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(orow + c);
+        acc += __low2float(a2) * __low2float(b2) + __high2float(a2) * __high2float(b2);
+      }
+    }
+    Dv[r] = acc;
+  }
+  __syncthreads();
+  const uint32_t qs = smem_u32(Qs), ks_ = smem_u32(Ks), vs = smem_u32(Vs), gs = smem_u32(Gs);
+  const float scale2 = scale * 1.4426950408889634f;
+  const int nblk = NP >> 4;
+  const uint32_t blk_bytes = 16 * kMmaPitch * 2;
+  // ---- phase 1: warp = block of 16 queries
+  for (int qb = warp; qb < nblk; qb += 8) {
+    uint32_t aq[4][4];
+    load_a64(aq, qs + qb * blk_bytes, lane);
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;           // rows g and g + 8
+    for (int kb = 0; kb < nblk; ++kb) {
+      float c[2][4];
+      tile_xyT(c, aq, ks_ + kb * blk_bytes, lane);
+      float v0[4], v1[4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int col = kb * 16 + nt * 8 + 2 * t;
+        v0[2 * nt] = col < n ? c[nt][0] * scale2 : -INFINITY;
+        v0[2 * nt + 1] = col + 1 < n ? c[nt][1] * scale2 : -INFINITY;
+        v1[2 * nt] = col < n ? c[nt][2] * scale2 : -INFINITY;
+        v1[2 * nt + 1] = col + 1 < n ? c[nt][3] * scale2 : -INFINITY;
+      }
+      const float n0 = fmaxf(fmaxf(m0, fmaxf(v0[0], v0[1])), fmaxf(v0[2], v0[3]));
+      const float n1 = fmaxf(fmaxf(m1, fmaxf(v1[0], v1[1])), fmaxf(v1[2], v1[3]));
+      if (n0 > -INFINITY) l0 = l0 * exp2f(m0 - n0) + (exp2f(v0[0] - n0) + exp2f(v0[1] - n0)) + (exp2f(v0[2] - n0) + exp2f(v0[3] - n0));
+      if (n1 > -INFINITY) l1 = l1 * exp2f(m1 - n1) + (exp2f(v1[0] - n1) + exp2f(v1[1] - n1)) + (exp2f(v1[2] - n1) + exp2f(v1[3] - n1));
+      m0 = n0;
+      m1 = n1;
+    }
+#pragma unroll
+    for (int off = 1; off <= 2; off <<= 1) {          // the four lanes of a quad hold one row
+      const float om0 = __shfl_xor_sync(0xffffffffu, m0, off), ol0 = __shfl_xor_sync(0xffffffffu, l0, off);
+      const float om1 = __shfl_xor_sync(0xffffffffu, m1, off), ol1 = __shfl_xor_sync(0xffffffffu, l1, off);
+      const float n0 = fmaxf(m0, om0), n1 = fmaxf(m1, om1);
+      l0 = (m0 > -INFINITY ? l0 * exp2f(m0 - n0) : 0.f) + (om0 > -INFINITY ? ol0 * exp2f(om0 - n0) : 0.f);
+      l1 = (m1 > -INFINITY ? l1 * exp2f(m1 - n1) : 0.f) + (om1 > -INFINITY ? ol1 * exp2f(om1 - n1) : 0.f);
+      m0 = n0;
+      m1 = n1;
+    }
+    const int r0 = qb * 16 + g, r1 = r0 + 8;
+    const float lse0 = r0 < n ? m0 + log2f(l0) : INFINITY, lse1 = r1 < n ? m1 + log2f(l1) : INFINITY;
+    if (t == 0) {
+      lse[r0] = lse0;
+      lse[r1] = lse1;
+    }
+    const float D0 = Dv[r0], D1 = Dv[r1];
+    uint32_t ag[4][4];
+    load_a64(ag, gs + qb * blk_bytes, lane);
+    float dq[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
+    for (int kb = 0; kb < nblk; ++kb) {
+      float c[2][4], e[2][4];
+      tile_xyT(c, aq, ks_ + kb * blk_bytes, lane);
+      tile_xyT(e, ag, vs + kb * blk_bytes, lane);
+      uint32_t ads[4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int col = kb * 16 + nt * 8 + 2 * t;
+        const float p00 = col < n ? exp2f(c[nt][0] * scale2 - lse0) : 0.f, p01 = col + 1 < n ? exp2f(c[nt][1] * scale2 - lse0) : 0.f;
+        const float p10 = col < n ? exp2f(c[nt][2] * scale2 - lse1) : 0.f, p11 = col + 1 < n ? exp2f(c[nt][3] * scale2 - lse1) : 0.f;
+        ads[2 * nt] = pack_bf16(p00 * (e[nt][0] - D0) * scale, p01 * (e[nt][1] - D0) * scale);
+        ads[2 * nt + 1] = pack_bf16(p10 * (e[nt][2] - D1) * scale, p11 * (e[nt][3] - D1) * scale);
+      }
+      acc_a_z(dq, ads, ks_ + kb * blk_bytes, lane);             // dQ += dS K
+    }
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      const int col = h * DH + dt * 8 + 2 * t;
+      if (r0 < n) *reinterpret_cast<uint32_t*>(dqkv + (row0 + r0) * 3ll * D + col) = pack_bf16(dq[dt][0], dq[dt][1]);
+      if (r1 < n) *reinterpret_cast<uint32_t*>(dqkv + (row0 + r1) * 3ll * D + col) = pack_bf16(dq[dt][2], dq[dt][3]);
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: warp = block of 16 keys, transposed tiles
+  for (int kb = warp; kb < nblk; kb += 8) {
+    uint32_t ak[4][4], av[4][4];
+    load_a64(ak, ks_ + kb * blk_bytes, lane);
+    load_a64(av, vs + kb * blk_bytes, lane);
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dk[i][j] = dv[i][j] = 0.f;
+    const int k0 = kb * 16 + g, k1 = k0 + 8;                     // this thread's key rows
+    for (int qb = 0; qb < nblk; ++qb) {
+      float c[2][4], e[2][4];
+      tile_xyT(c, ak, qs + qb * blk_bytes, lane);                // S^T  [keys x queries]
+      tile_xyT(e, av, gs + qb * blk_bytes, lane);                // dP^T
+      uint32_t ap[4], ads[4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int q = qb * 16 + nt * 8 + 2 * t;
+        const float2 ls = *reinterpret_cast<const float2*>(lse + q), dd = *reinterpret_cast<const float2*>(Dv + q);
+        const float p00 = k0 < n ? exp2f(c[nt][0] * scale2 - ls.x) : 0.f, p01 = k0 < n ? exp2f(c[nt][1] * scale2 - ls.y) : 0.f;
+        const float p10 = k1 < n ? exp2f(c[nt][2] * scale2 - ls.x) : 0.f, p11 = k1 < n ? exp2f(c[nt][3] * scale2 - ls.y) : 0.f;
+        ap[2 * nt] = pack_bf16(p00, p01);
+        ap[2 * nt + 1] = pack_bf16(p10, p11);
+        ads[2 * nt] = pack_bf16(p00 * (e[nt][0] - dd.x) * scale, p01 * (e[nt][1] - dd.y) * scale);
+        ads[2 * nt + 1] = pack_bf16(p10 * (e[nt][2] - dd.x) * scale, p11 * (e[nt][3] - dd.y) * scale);
+      }
+      acc_a_z(dv, ap, gs + qb * blk_bytes, lane);                // dV += P^T dO
+      acc_a_z(dk, ads, qs + qb * blk_bytes, lane);               // dK += dS^T Q
+    }
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      const int col = h * DH + dt * 8 + 2 * t;
+      if (k0 < n) {
+        *reinterpret_cast<uint32_t*>(dqkv + (row0 + k0) * 3ll * D + D + col) = pack_bf16(dk[dt][0], dk[dt][1]);
+        *reinterpret_cast<uint32_t*>(dqkv + (row0 + k0) * 3ll * D + 2 * D + col) = pack_bf16(dv[dt][0], dv[dt][1]);
+      }
+      if (k1 < n) {
+        *reinterpret_cast<uint32_t*>(dqkv + (row0 + k1) * 3ll * D + D + col) = pack_bf16(dk[dt][2], dk[dt][3]);
+        *reinterpret_cast<uint32_t*>(dqkv + (row0 + k1) * 3ll * D + 2 * D + col) = pack_bf16(dv[dt][2], dv[dt][3]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ cross-entropy (mean over `inv_count`^-1 samples) + its gradient
 // One warp per sample: loss_sum += -log softmax(logits)[label]; dlogits = (softmax - onehot) * inv_count; correct += argmax == label.
 __global__ void __launch_bounds__(256)
@@ -422,7 +646,26 @@ extern "C" int pk_attention_bwd(const void* qkv, const void* out, const void* do
   PK_REQUIRE(seq_len >= 1 && seq_len <= 256 && batch >= 0 && num_heads > 0, "pk_attention_bwd: uniform sequences of 1 .. 256 tokens (got %d)", seq_len);
   if (batch == 0) return PK_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (head_dim == 64) return launch_attention_bwd<64>(qkv, out, dout, dqkv, batch, num_heads, seq_len, scale, s);
+  if (head_dim == 64) {
+    // PK_ATT_BWD_MMA=0: the CUDA-core kernel (A/B runs; it is also the head_dim 32 path)
+    static int use_mma = -1;
+    if (use_mma < 0) { const char* e = getenv("PK_ATT_BWD_MMA"); use_mma = (e && e[0] == '0') ? 0 : 1; }
+    const bool aligned = ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dqkv)) & 15) == 0;
+    if (use_mma && aligned) {
+      const int NP = (seq_len + 15) & ~15;
+      const size_t bytes = static_cast<size_t>(4) * NP * kMmaPitch * 2 + static_cast<size_t>(2) * NP * 4;
+      static bool attr_set = false;
+      if (!attr_set) {
+        PK_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        attr_set = true;
+      }
+      attention_bwd_mma_kernel<<<dim3(num_heads, batch), 256, bytes, s>>>(
+          static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout),
+          static_cast<__nv_bfloat16*>(dqkv), num_heads, seq_len, scale);
+      return check_cuda(cudaGetLastError(), "attention_bwd_mma_kernel");
+    }
+    return launch_attention_bwd<64>(qkv, out, dout, dqkv, batch, num_heads, seq_len, scale, s);
+  }
   return launch_attention_bwd<32>(qkv, out, dout, dqkv, batch, num_heads, seq_len, scale, s);
 }
 
