@@ -355,6 +355,9 @@ int pk_softmax_xent(const float* logits, const long long* labels, int batch, int
 /* Linear head backward (vit.py:246): d_weight += dlogits^T feat, d_bias += sum_b dlogits, d_feat = dlogits weight. */
 int pk_head_bwd(const float* dlogits, const float* feat, const float* weight, int batch, int classes, int dim, float* d_weight,
                 float* d_bias, float* d_feat, void* stream);
+/* Backward of pk_gather_rows (RankViTBlock.sort_and_drop, rankvit.py:55-77; no gradient through the indices):
+ * x[b * seq_len + tok(o), :] = y[b * (k + 1) + o, :], tok(0) = 0, tok(o) = 1 + kept[b, o - 1]; x is zeroed by the caller. */
+int pk_scatter_rows(const float* y, float* x, const int* kept, int batch, int seq_len, int k, int dim, void* stream);
 /* out[t, :] += sum_b x[b * seq + row0 + t, :]: gradient of the class / register token parameters (vit.py:230-236). */
 int pk_sum_token_rows(const float* x, int batch, int seq, int row0, int n_rows, int dim, float* out, void* stream);
 

@@ -580,9 +580,36 @@ sum_token_rows_kernel(const float* __restrict__ x, int batch, int seq, int row0,
   }
 }
 
+// Backward of RankViT's gather (rankvit.py:69-77: class token + the kept tokens, no gradient through the indices):
+// x[b * seq + tok(o)] = y[b * (k + 1) + o] with tok(0) = 0, tok(o) = 1 + kept[b, o - 1]; the caller zeroes x first (dropped
+// tokens receive no gradient).  One warp per row.
+__global__ void __launch_bounds__(256)
+scatter_rows_kernel(const float* __restrict__ y, float* __restrict__ x, const int* __restrict__ kept, int batch, int seq_len, int k, int dim) {
+  const int lane = lane_id(), d4 = dim / 4;
+  const int k1 = k + 1;
+  const long long total = static_cast<long long>(batch) * k1;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (long long r = blockIdx.x * (blockDim.x >> 5) + warp_id(); r < total; r += warps_total) {
+    const long long b = r / k1;
+    const int o = static_cast<int>(r - b * k1);
+    const int tok = o == 0 ? 0 : 1 + kept[b * k + (o - 1)];
+    const float4* src = reinterpret_cast<const float4*>(y + r * dim);
+    float4* dst = reinterpret_cast<float4*>(x + (b * seq_len + tok) * dim);
+    for (int c = lane; c < d4; c += 32) dst[c] = src[c];
+  }
+}
+
 }  // namespace pk
 
 using namespace pk;
+
+extern "C" int pk_scatter_rows(const float* y, float* x, const int* kept, int batch, int seq_len, int k, int dim, void* stream) {
+  PK_REQUIRE(y && x && (kept || k == 0) && dim % 4 == 0 && batch >= 0 && k >= 0 && k < seq_len, "pk_scatter_rows: bad arguments");
+  if (batch == 0) return PK_OK;
+  scatter_rows_kernel<<<train_grid(static_cast<long long>(batch) * (k + 1), 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      y, x, kept, batch, seq_len, k, dim);
+  return check_cuda(cudaGetLastError(), "scatter_rows_kernel");
+}
 
 extern "C" int pk_cast_f32_bf16(const float* x, void* y, long long n, void* stream) {
   PK_REQUIRE(x && y && n >= 0 && n % 4 == 0, "pk_cast_f32_bf16: bad arguments (n must be a multiple of 4)");

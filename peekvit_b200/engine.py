@@ -1012,7 +1012,12 @@ class Forward:
         cur = 0
         L = len(pm.layers)
         for i, lw in enumerate(pm.layers):
-            self.attn_part(xs[cur], lw, rows_cap, B, cu=cu, max_len=seq, rows_dev=rows_dev, extra_mult=n_halted if i > 0 else None)
+            if i == 0:
+                # nothing has halted yet: every sample still has all its tokens, so the first block's attention is the dense
+                # uniform-sequence kernel (135 us per 512 x 12 heads x 197 tokens; the ragged kernels 245 / 395 us)
+                self.attn_part(xs[cur], lw, rows_cap, B, seq=seq)
+            else:
+                self.attn_part(xs[cur], lw, rows_cap, B, cu=cu, max_len=seq, rows_dev=rows_dev, extra_mult=n_halted)
             self.mlp_part(xs[cur], lw, rows_cap, rows_dev=rows_dev)
             if aux is not None:
                 aux.setdefault("rows", []).append(rows_dev.clone())

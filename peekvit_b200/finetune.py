@@ -23,12 +23,14 @@ transposed bf16 weights (``pk_gemm_bf16``), ``pk_layernorm_bwd``, ``pk_gelu_bwd_
 initialised ``torch.distributed`` process group the gradients are averaged over the ranks with ONE all-reduce of a flat
 bucket (NCCL on GPUs), which is what DistributedDataParallel does for the reference.
 
-Scope: the dense ``VisionTransformer`` with trainable ``class_tokens`` / ``head.*``; dropout must be 0 (every shipped
-config).  The gate / threshold / budget parameters of the ResidualViT family train through its training-mode forward
+Scope: ``VisionTransformer`` and ``RankVisionTransformer`` (its blocks rank and drop tokens in training exactly as in eval,
+rankvit.py:55-97; the gather's backward is a scatter of the gradient rows, no gradient flows through the indices) with
+trainable ``class_tokens`` / ``head.*``; dropout must be 0 (every shipped config).  The gate / threshold / budget parameters of the ResidualViT family train through its training-mode forward
 (sampled budgets, soft masks), which is not built: constructing a FineTuner for such a model raises.
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -81,12 +83,12 @@ def all_reduce_mean_(params: Sequence[torch.Tensor], group=None) -> int:
 
 class FineTuner:
     def __init__(self, model, train_words: Sequence[str] = TRAIN_WORDS, micro_batch: int = 128, process_group=None):
-        if getattr(model, "_family", None) != "vit":
+        if getattr(model, "_family", None) not in ("vit", "rankvit"):
             raise NotImplementedError(
-                f"FineTuner: the backward path is built for the dense VisionTransformer (class tokens + head regime); "
-                f"{type(model).__name__} trains gates / thresholds / budget tokens through a training-mode forward that is not built")
+                f"FineTuner: the backward path is built for VisionTransformer and RankVisionTransformer (class tokens + head "
+                f"regime); {type(model).__name__} trains gates / thresholds / budget tokens through a training-mode forward that is not built")
         for blk in model.encoder.layers:
-            if type(blk).__name__ != "ViTBlock":
+            if type(blk).__name__ not in ("ViTBlock", "RankViTBlock"):
                 raise NotImplementedError(f"FineTuner: encoder.layers holds a {type(blk).__name__}")
         drops = [m.p for m in model.modules() if isinstance(m, torch.nn.Dropout)] + \
                 [m.dropout for m in model.modules() if isinstance(m, torch.nn.MultiheadAttention)]
@@ -102,6 +104,9 @@ class FineTuner:
         self.params: Dict[str, torch.nn.Parameter] = {n: p for n, p in model.named_parameters() if n in self.names}
         self._wt: Dict[int, tuple] = {}             # layer -> transposed bf16 weights, keyed by the weight pack they came from
         self._wt_pack = None
+        # RankViT: the kept-token indices of the last micro-batch, {layer: int32 [B, k]} (what a caller / test needs to
+        # reproduce the step given identical selections; top-k is discontinuous in the bf16 scores)
+        self.last_kept: Dict[int, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ helpers
     def _transposed(self, pm: engine.PackedModel, l: int):
@@ -163,14 +168,28 @@ class FineTuner:
     def _micro_step(self, pm, ws, images, labels, inv_count, loss_sum, g_head_w, g_head_b, g_cls) -> torch.Tensor:
         B, seq, D, H = images.shape[0], pm.seq_len, pm.dim, pm.heads
         dh = D // H
-        rows = B * seq
         L = len(pm.layers)
         fwd = engine.Forward(pm, ws)
         x = fwd.embed(images)                                              # fp32 [rows, D] (workspace "x": layer 0's input)
-        xs = [x]
+        xs = [x]                                                            # xs[l]: what block l's LayerNorm / residual read
         saved = []
+        picks = {}                                                          # l -> (kept indices, tokens per sample before the drop)
+        budgets = runner._rank_budgets(self.model) if pm.family == "rankvit" else {}
         bf, f32 = torch.bfloat16, torch.float32
         for l, lw in enumerate(pm.layers):
+            b_l = budgets.get(l, 1.0) if lw.kind == "rank" else 1.0
+            if lw.kind == "rank" and b_l != 1 and seq > 1:
+                # RankViTBlock.sort_and_drop (rankvit.py:55-77), same kernels as inference; the selection is kept for the backward
+                n_tok = seq - 1
+                k = min(max(math.ceil(n_tok * b_l), 0), n_tok)
+                scores = ops.token_norm_score(xs[-1], B, seq, ws.get(f"ft_scores_{l}", (B, n_tok), f32))
+                kept = ws.get(f"ft_kept_{l}", (B, k), torch.int32)
+                if k > 0:
+                    ops.topk_select(scores, k, kept)
+                xs[-1] = ops.gather_rows(xs[-1], kept, B, seq, ws.get(f"ft_xg_{l}", (B * (k + 1), D), f32))
+                picks[l] = (kept, seq)
+                seq = k + 1
+            rows = B * seq
             aw, mw = lw.attn[0], lw.mlp[0]
             F = mw.w_fc1.shape[0]
             qkv = ws.get(f"ft_qkv_{l}", (rows, 3 * D), bf, zero=True)
@@ -186,7 +205,7 @@ class FineTuner:
             ops.gemm(a, mw.w_fc1, mw.b_fc1, hpre, PK_EPI_BIAS_BF16)              # pre-activation kept for the backward
             hid = ops.gelu_bf16(hpre, ws.get("hid", (rows, F), bf))
             ops.gemm(hid, mw.w_fc2, mw.b_fc2, xo, PK_EPI_BIAS_RESID_F32, resid=x1)
-            saved.append((qkv, att, x1, hpre))
+            saved.append((qkv, att, x1, hpre, seq))
             xs.append(xo)
         xl = xs[-1]
         n_cls = pm.n_cls
@@ -199,6 +218,7 @@ class FineTuner:
         dfeat = ws.get("ft_dfeat", (B, D), f32)
         ops.head_bwd(dlogits, feat, pm.head_w, g_head_w, g_head_b, dfeat)
         # ---- final LayerNorm on the class rows (sum readout: every class row of a sample gets the same feature gradient)
+        rows = B * seq
         g = ws.get("ft_g", (rows, D), f32)
         g.zero_()
         cls_rows = fwd._const(f"ft_cls_rows_{B}_{seq}_{n_cls}", lambda: (
@@ -206,12 +226,13 @@ class FineTuner:
             + torch.arange(n_cls, device=g.device, dtype=torch.int32)[None, :]).reshape(-1).contiguous())
         ops.layernorm_bwd(xl, dfeat, pm.ln_w, pm.ln_eps, g, B * n_cls, row_index=cls_rows, dy_div=n_cls, accumulate=False)
         # ---- blocks, last to first
-        gb = ws.get("ft_gb", (rows, D), bf)
-        da = ws.get("ft_da", (rows, D), f32)
         for l in range(L - 1, -1, -1):
             lw = pm.layers[l]
             F = lw.mlp[0].w_fc1.shape[0]
-            qkv, att, x1, hpre = saved[l]
+            qkv, att, x1, hpre, seq = saved[l]
+            rows = B * seq
+            gb = ws.get("ft_gb", (rows, D), bf)
+            da = ws.get("ft_da", (rows, D), f32)
             w2t, w1t, wot, wqkvt = self._transposed(pm, l)
             # MLP branch: x2 = x1 + W2 gelu(W1 LN2(x1) + b1) + b2
             ops.cast_bf16(g, gb)
@@ -225,6 +246,14 @@ class FineTuner:
             dqkv = ops.attention_bwd(qkv, att, datt, ws.get("ft_dqkv", (rows, 3 * D), bf), B, H, dh, seq)
             ops.gemm(dqkv, wqkvt, None, da, PK_EPI_BIAS_F32)
             ops.layernorm_bwd(xs[l], da, lw.ln1_w, lw.eps, g, rows)               # g = dL/dx_in
+            if l in picks:
+                # backward of the gather in front of this block: gradient rows go back to their tokens, dropped tokens get none
+                kept, seq_before = picks[l]
+                g_full = ws.get("ft_g", (B * seq_before, D), f32)
+                g_full.zero_()
+                g = ops.scatter_rows(g, g_full, kept, B, seq_before)
+                seq = seq_before
         # ---- the class tokens are rows 0 .. n_cls-1 of every sample (x0 = class token + position, vit.py:230-236,:92)
         ops.sum_token_rows(g, B, seq, 0, n_cls, g_cls)
+        self.last_kept = {l: kept.clone() for l, (kept, _) in picks.items()}
         return logits

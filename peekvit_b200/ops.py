@@ -626,3 +626,11 @@ def sum_token_rows(x: torch.Tensor, batch: int, seq: int, row0: int, n_rows: int
     check(lib.pk_sum_token_rows(_ptr(x, torch.float32), batch, seq, row0, n_rows, x.shape[-1], _ptr(out, torch.float32), _stream()),
           "pk_sum_token_rows")
     return out
+
+
+def scatter_rows(y: torch.Tensor, x: torch.Tensor, kept: torch.Tensor, batch: int, seq_len: int) -> torch.Tensor:
+    """Backward of gather_rows: x[b*seq_len + tok] = y rows (x zeroed by the caller)."""
+    lib = _lib_for(y)
+    check(lib.pk_scatter_rows(_ptr(y, torch.float32), _ptr(x, torch.float32), _ptr(kept, torch.int32), batch, seq_len, kept.shape[1],
+                              y.shape[-1], _stream()), "pk_scatter_rows")
+    return x

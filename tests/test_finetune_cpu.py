@@ -29,6 +29,7 @@ def test_train_only_these_params_matches_the_reference_rule():
 def test_finetuner_accepts_the_dense_regime_only():
     ft = finetune.FineTuner(build_model("vit", _BASE))
     assert sorted(ft.params) == ["class_tokens", "head.bias", "head.weight"]
+    assert sorted(finetune.FineTuner(build_model("RankVisionTransformer", dict(_BASE, rankvit_layers=[1]))).params) == sorted(ft.params)
     with pytest.raises(NotImplementedError):                          # gates / budget tokens: training-mode forward not built
         finetune.FineTuner(build_model("residualvit", dict(_BASE, gate_type="sigmoid", gate_bias=0.0, add_budget_token="learnable",
                                                            residual_layers=["attention+mlp"] * 2)))

@@ -184,3 +184,50 @@ def test_a_few_sgd_steps_reduce_the_loss_and_eval_follows_the_new_weights():
     after = model(images)                                                   # inference path sees the updated class tokens / head
     assert (after - before).abs().max().item() > 1e-2
     assert torch.nn.functional.cross_entropy(after, labels).item() < torch.nn.functional.cross_entropy(before, labels).item()
+
+
+@pytest.mark.parametrize("budget", [0.5, [1, 0.5, 1, 0.25]])
+def test_rankvit_gradients_match_autograd_given_identical_selections(budget):
+    """RankVisionTransformer in the same regime: the blocks rank and drop tokens in training as in eval (rankvit.py:85-88),
+    the backward scatters the gradient rows back through the gather.  top-k is discontinuous in the (bf16-level) scores, so
+    the autograd reference runs the oracle with the selections the CUDA path made (forced_kept), like the inference tests."""
+    from oracle import peekvit_oracle as po, weights as ow
+    from peekvit_b200 import ops
+    from peekvit_b200.finetune import FineTuner
+    from peekvit_b200.models import RankVisionTransformer
+    cfg = dict(image_size=64, patch_size=8, num_layers=4, num_heads=2, hidden_dim=128, mlp_dim=256, num_classes=10, rankvit_layers=[1, 3])
+    sd = ow.make_state_dict("rankvit", cfg, seed=13)
+    images = ow.synthetic_images(5, 64, seed=23)
+    labels = torch.tensor([1, 7, 3, 3, 9])
+    model = RankVisionTransformer(**cfg)
+    model.load_state_dict(sd)
+    model = model.to(DEV).train()
+    model.set_budget(budget)
+    ft = FineTuner(model)
+    loss, logits = ft.forward_backward(images.to(DEV), labels.to(DEV))
+    assert ops.device_flag() == 0 and sorted(ft.last_kept) == [1, 3]
+    assert ft.last_kept[1].shape == (5, 32) and ft.last_kept[3].shape == (5, 16 if budget == 0.5 else 8)
+    names = ("class_tokens", "head.weight", "head.bias")
+    sdg = {k: v.to(DEV) for k, v in sd.items()}
+    for n in names:
+        sdg[n] = sdg[n].clone().requires_grad_(True)
+    ref_logits, _ = po.rankvit_forward(sdg, cfg, images.to(DEV), budget, forced_kept={l: k.long() for l, k in ft.last_kept.items()})
+    ref_loss = torch.nn.functional.cross_entropy(ref_logits, labels.to(DEV))
+    ref_loss.backward()
+    assert _rel(logits, ref_logits.detach()) < 1e-2 and abs(loss.item() - ref_loss.item()) < 1e-2 * ref_loss.item()
+    for n, p in ft.params.items():
+        err = _rel(p.grad, sdg[n].grad.view_as(p.grad))
+        print(f"rankvit {n}: rel err {err:.2e}")
+        assert err < 3e-2, n
+
+
+def test_scatter_rows_is_the_adjoint_of_gather_rows():
+    from peekvit_b200 import ops
+    B, seq, k, D = 3, 9, 4, 64
+    x = torch.randn(B * seq, D, device=DEV)
+    kept = torch.stack([torch.randperm(seq - 1, device=DEV)[:k] for _ in range(B)]).to(torch.int32)
+    y = ops.gather_rows(x, kept, B, seq)
+    g = torch.randn_like(y)
+    back = ops.scatter_rows(g, torch.zeros_like(x), kept, B, seq)
+    assert abs(float((y * g).sum()) - float((x * back).sum())) < 1e-3            # <gather(x), g> == <x, scatter(g)>
+    assert int((back.abs().sum(1) > 0).sum()) == B * (k + 1)
