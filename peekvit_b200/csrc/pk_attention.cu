@@ -12,6 +12,8 @@
 // ldmatrix; QK^T and PV on tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate); softmax
 // statistics in fp32 registers (exp2 domain).
 #include "pk_common.cuh"
+
+#include <cstdlib>
 #include "../../include/peekvit_b200.h"
 
 namespace pk {
@@ -70,8 +72,11 @@ struct AttParams {
   int route_min_rows;
 };
 
-template <int DH>
-__global__ void __launch_bounds__(kAttThreads, 3)
+// OCC = resident CTAs per SM the register allocation is capped for.  3 for uniform long sequences (steady-state tiles, no
+// spills); ragged batches of short samples are fill / drain bound (one or two key tiles per CTA), where more CTAs in flight
+// hide the load latency better than a spill-free inner loop (PK_ATT_GENERAL_OCC, profiles/r02).
+template <int DH, int OCC = 3>
+__global__ void __launch_bounds__(kAttThreads, OCC)
 attention_fwd_kernel(const AttParams p) {
   constexpr int CPR = DH / 8;
   constexpr int KS = DH / 16;                       // k-steps over head_dim for QK^T
@@ -357,7 +362,11 @@ extern "C" int pk_attention_fwd(const pk_attention_args* a, void* stream) {
   dim3 grid((max_len + kAttBQ - 1) / kAttBQ, a->num_heads, a->batch);
   PK_REQUIRE(a->batch <= 65535 && a->num_heads <= 65535, "pk_attention_fwd: batch/heads exceed grid limits; split the batch");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (a->head_dim == 64) attention_fwd_kernel<64><<<grid, kAttThreads, 0, s>>>(p);
+  static int occ_ragged = -1;
+  if (occ_ragged < 0) { const char* e = getenv("PK_ATT_GENERAL_OCC"); occ_ragged = e ? atoi(e) : 4; }     // measured 66.2 / 59.9 / 58.2 us at 3 / 4 / 5 (mean 79 rows), 160.0 / 151.5 / 159.9 (mean 165)
+  if (a->head_dim == 64 && a->cu_seqlens && occ_ragged == 4) attention_fwd_kernel<64, 4><<<grid, kAttThreads, 0, s>>>(p);
+  else if (a->head_dim == 64 && a->cu_seqlens && occ_ragged == 5) attention_fwd_kernel<64, 5><<<grid, kAttThreads, 0, s>>>(p);
+  else if (a->head_dim == 64) attention_fwd_kernel<64><<<grid, kAttThreads, 0, s>>>(p);
   else if (a->head_dim == 48) attention_fwd_kernel<48><<<grid, kAttThreads, 0, s>>>(p);
   else attention_fwd_kernel<32><<<grid, kAttThreads, 0, s>>>(p);
   return check_cuda(cudaGetLastError(), "attention_fwd_kernel");
