@@ -102,6 +102,12 @@ typedef struct pk_gemm_args {
    * PK_OUT_BF16X2 = the value split into hi + lo (both bf16) and written as [lo | hi]: `out` is [*, 2N], lo at
    * column n, hi at column N + n (N % 64 == 0) -- the A operand of the next split GEMM without an extra pass. */
   int out_format;
+  /* Grouped launch (MoE expert MLPs, moevit.py:49-61 for the routed tokens only; CTA-pair kernel, epilogues without a staged
+   * residual): group_offsets != NULL makes ONE launch cover n_groups row segments [group_offsets[g], group_offsets[g + 1]) of
+   * A / out (device-side int32[n_groups + 1], the expert-sorted layout of pk_moe_route), each multiplied by its own weight:
+   * W is the groups' weights stacked ([n_groups * N, K]), bias their biases ([n_groups * N]); N stays one group's width.
+   * The tile scheduler walks the segments' 256-row tiles; m_dev / row_begin_dev are ignored. */
+  const int* group_offsets; int n_groups;
 } pk_gemm_args;
 
 enum pk_out_format { PK_OUT_BF16 = 0, PK_OUT_F16 = 1, PK_OUT_BF16X2 = 2 };

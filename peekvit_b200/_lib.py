@@ -37,6 +37,7 @@ class GemmArgs(C.Structure):
         ("xb_out", c_void_p), ("ldxb", c_longlong), ("row_stats", c_void_p),
         ("ln_stats", c_void_p), ("ln_c1", c_void_p), ("ln_parts", c_int), ("ln_dim", c_int), ("ln_eps", c_float),
         ("a_wrap_k", c_int), ("out_format", c_int),
+        ("group_offsets", c_void_p), ("n_groups", c_int),
     ]
 
 

@@ -535,6 +535,12 @@ extern "C" int pk_gemm_bf16(const pk_gemm_args* a, void* stream) {
     PK_REQUIRE(a->resid != nullptr && a->ldr % 4 == 0, "pk_gemm_bf16: residual epilogue needs resid with ldr %% 4 == 0");
   if (a->M == 0) return PK_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a->group_offsets) {
+    PK_REQUIRE(a->n_groups >= 1 && pair_gemm_eligible(a) && a->cta_pair != 1,
+               "pk_gemm_bf16: a grouped launch needs the CTA-pair kernel (contiguous aligned rows, no staged residual / LayerNorm "
+               "fusion / rowscale, 1 <= n_groups <= 64)");
+    return launch_pair_gemm(a, s);
+  }
   const bool ln_fused = a->xb_out != nullptr || a->ln_stats != nullptr;
   if (a->a_wrap_k > 0 || a->out_format != PK_OUT_BF16) {
     // two-term split operands / fp16 / split outputs (bf16x2 mode): CTA-pair kernel only

@@ -80,6 +80,8 @@ struct PairParams {
   const int* m_dev;
   const int* row_begin_dev;
   const int* out_row_index;  // RED only: GEMM row r accumulates into out row out_row_index[r] (un-permute of expert-sorted rows)
+  const int* group_offsets;  // grouped launch: row segments [off[g], off[g + 1]) with weight rows g * N .. (g + 1) * N - 1
+  int n_groups;
   const float* bias;
   void* out;
   long long ldo;
@@ -180,10 +182,37 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   const int num_pairs = gridDim.x >> 1;
   const int row0 = p.row_begin_dev ? *p.row_begin_dev : 0;     // first row of this launch's segment (MoE expert segments)
   const int M = p.m_dev ? max(0, min(*p.m_dev, p.M - row0)) : p.M - row0;
-  const int m_tiles = (M + 2 * kP_BM - 1) / (2 * kP_BM);
   const int n_tiles = (p.N + BN - 1) / BN;
+  int m_tiles = (M + 2 * kP_BM - 1) / (2 * kP_BM);
+  if (p.group_offsets) {                           // grouped launch: the segments' row tiles, one after the other
+    m_tiles = 0;
+    for (int g = 0; g < p.n_groups; ++g) m_tiles += (p.group_offsets[g + 1] - p.group_offsets[g] + 2 * kP_BM - 1) / (2 * kP_BM);
+  }
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = p.K / kP_BK;
+  // tile t -> first row of its 256-row block, end of the rows it may write, column block, first weight / bias row
+  auto tile_map = [&](int t, int& row_blk, int& row_end, int& n_blk, int& w_row0) {
+    int mt = t / n_tiles;
+    n_blk = t - mt * n_tiles;
+    if (!p.group_offsets) {
+      row_blk = row0 + mt * 2 * kP_BM;
+      row_end = row0 + M;
+      w_row0 = 0;
+      return;
+    }
+    int g = 0, o0 = p.group_offsets[0], o1 = p.group_offsets[1];
+    for (;;) {
+      const int tg = (o1 - o0 + 2 * kP_BM - 1) / (2 * kP_BM);
+      if (mt < tg || g + 1 >= p.n_groups) break;
+      mt -= tg;
+      ++g;
+      o0 = o1;
+      o1 = p.group_offsets[g + 1];
+    }
+    row_blk = o0 + mt * 2 * kP_BM;
+    row_end = o1;
+    w_row0 = g * p.N;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -245,7 +274,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       }
     }
     for (int t = pair; t < num_tiles; t += num_pairs) {
-      const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+      int row_blk, row_end_unused, n_blk, w_row0;
+      tile_map(t, row_blk, row_end_unused, n_blk, w_row0);
       bool ok = true;
       for (int kb = 0; kb < num_kb; ++kb) {
         ok = __all_sync(0xffffffffu, mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u, p.flag, 0x1100u + s));
@@ -260,8 +290,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           const uint32_t a_dst = smem_u32(smem_ab + s * Cfg::kStageBytes);
           int a_col = kb * kP_BK;
           if (p.a_wrap_k > 0 && a_col >= 2 * p.a_wrap_k) a_col -= p.a_wrap_k;       // [lo | hi] read as lo, hi, hi
-          tma_load_2d_pair(a_dst, &tmap_a, fb, a_col, row0 + m_blk * 2 * kP_BM + a_row_off);
-          tma_load_2d_pair(a_dst + Cfg::kABytes, &tmap_b, fb, kb * kP_BK, n_blk * BN + b_row_off);
+          tma_load_2d_pair(a_dst, &tmap_a, fb, a_col, row_blk + a_row_off);
+          tma_load_2d_pair(a_dst + Cfg::kABytes, &tmap_b, fb, kb * kP_BK, w_row0 + n_blk * BN + b_row_off);
           }
           if (p.l2_prefetch) prefetch_next();
         }
@@ -347,10 +377,11 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     uint32_t aph = 0;
     bool ok = true;
     for (int t = pair; t < num_tiles && ok; t += num_pairs) {
-      const int m_blk = t / n_tiles;
-      const int row_base = row0 + m_blk * 2 * kP_BM + row_in_pair;                         // this warp's first row
+      int row_blk, row_end, n_blk_t, w_row0;                                               // rows >= row_end stay untouched
+      tile_map(t, row_blk, row_end, n_blk_t, w_row0);
+      const int row_base = row_blk + row_in_pair;                                          // this warp's first row
       const int grow = row_base + lane;
-      const int row_end = row0 + M;                                                        // rows >= row_end stay untouched
+      const float* bias_g = p.bias ? p.bias + w_row0 : nullptr;                            // this group's bias
       // warp-uniform; a row-indexed launch (MoE un-permute) writes every tile row by row
       const bool full_tile = row_base + 32 <= row_end && !(RED && p.out_row_index);
       float sc = 1.0f;
@@ -393,7 +424,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           bias4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias && col0 + 4 * j < p.N) bias4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
+          if (bias_g && col0 + 4 * j < p.N) bias4[j] = __ldg(reinterpret_cast<const float4*>(bias_g + col0 + 4 * j));
           if constexpr (LN == 2) {
             if (col0 + 4 * j < p.N) {
               const float4 c1 = __ldg(reinterpret_cast<const float4*>(p.ln_c1 + col0 + 4 * j));
@@ -663,8 +694,8 @@ static int launch_pair(const pk_gemm_args* a, cudaStream_t stream) {
   int rc = make_tmap_bf16_2d(&ta, a->A, static_cast<uint64_t>(a->M), static_cast<uint64_t>(a_cols), static_cast<uint64_t>(a->lda),
                              kP_BM, kP_BK);
   if (rc != PK_OK) return rc;
-  rc = make_tmap_bf16_2d(&tb, a->W, static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->ldw), BN / 2,
-                         kP_BK);
+  const uint64_t w_rows = static_cast<uint64_t>(a->N) * (a->group_offsets ? a->n_groups : 1);       // stacked group weights
+  rc = make_tmap_bf16_2d(&tb, a->W, w_rows, static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->ldw), BN / 2, kP_BK);
   if (rc != PK_OK) return rc;
   rc = make_tmap_2d(&tout, a->out, Cfg::kOutBf16 ? 2 : 4, static_cast<uint64_t>(a->M), static_cast<uint64_t>(OUTF == 2 ? 2 * a->N : a->N),
                     static_cast<uint64_t>(a->ldo), 32, Cfg::kStoreCols, Cfg::kStoreSwizzle);
@@ -691,14 +722,17 @@ static int launch_pair(const pk_gemm_args* a, cudaStream_t stream) {
   p.m_dev = a->m_dev;
   p.row_begin_dev = a->row_begin_dev;
   p.out_row_index = a->out_row_index;
+  p.group_offsets = a->group_offsets;
+  p.n_groups = a->n_groups;
   p.bias = a->bias;
   p.out = a->out; p.ldo = a->ldo;
   p.rowscale = a->rowscale;
   p.flag = device_flag_ptr();
-  p.l2_prefetch = pair_l2_prefetch();
+  p.l2_prefetch = a->group_offsets ? 0 : pair_l2_prefetch();
   p.debug = pair_debug();
   p.a_wrap_k = a->a_wrap_k;
-  const int m_tiles = (a->M + 2 * kP_BM - 1) / (2 * kP_BM), n_tiles = (a->N + BN - 1) / BN;
+  // grouped launch: every segment may end in a partial row tile
+  const int m_tiles = (a->M + 2 * kP_BM - 1) / (2 * kP_BM) + (a->group_offsets ? a->n_groups : 0), n_tiles = (a->N + BN - 1) / BN;
   int pairs = m_tiles * n_tiles;
   const int sms = a->max_ctas > 0 ? a->max_ctas : num_sms();
   if (pairs > sms / 2) pairs = sms / 2;
@@ -750,6 +784,11 @@ static int pick_pair_block_n(int N) {
 bool pair_gemm_eligible(const pk_gemm_args* a) {
   if (a->epilogue_mode == 2) return false;
   if (a->rows_per_group > 0) return false;
+  if (a->group_offsets) {
+    // grouped launch: no staged residual / LayerNorm variants, and a group's weight rows must tile by the column block
+    const bool staged = a->epilogue == PK_EPI_BIAS_RESID_F32 && !(a->resid == a->out && a->ldr == a->ldo && pair_tma_reduce());
+    if (a->n_groups < 1 || a->n_groups > 64 || staged || a->xb_out || a->ln_stats || a->rowscale) return false;
+  }
   // row-indexed output: only as the in-place accumulate x[idx[r]] += ... (the TMA-reduce variant's row-store path)
   if (a->out_row_index && !(a->epilogue == PK_EPI_BIAS_RESID_F32 && a->resid == a->out && a->ldr == a->ldo && !a->xb_out &&
                             pair_tma_reduce()))

@@ -41,6 +41,8 @@ HEAD_GEMM = int(os.environ.get("PEEKVIT_B200_HEAD_GEMM", "1"))
 # (tools/attn_ragged_bench.py, profiles/r02)
 ATT_TCR_MIN_MEAN_ROWS = int(os.environ.get("PEEKVIT_B200_ATT_TCR_MIN_MEAN_ROWS", "140"))
 MOE_FUSED_SCATTER = int(os.environ.get("PEEKVIT_B200_MOE_FUSED_SCATTER", "1"))
+# ... and one grouped launch per projection over all expert segments instead of one launch per expert (A/B switch)
+MOE_GROUPED = int(os.environ.get("PEEKVIT_B200_MOE_GROUPED", "1"))
 
 
 def _f32(t: torch.Tensor) -> torch.Tensor:
@@ -1122,6 +1124,19 @@ class Forward:
             # (device-side segment start and length); the fc2 outputs land in sorted order and one gather-add un-permutes
             # them into the residual stream.
             fused = MOE_FUSED_SCATTER and rows > 256 and D % 8 == 0
+            if fused and MOE_GROUPED:
+                # ONE launch per projection over all expert segments: the tile scheduler of the CTA-pair GEMM walks the
+                # segments [offsets[e], offsets[e + 1]) and takes expert e's rows of the stacked weight / bias
+                st = lw.extra.get("moe_stacked")
+                if st is None:
+                    st = lw.extra["moe_stacked"] = (torch.cat([m.w_fc1 for m in lw.mlp]).contiguous(), torch.cat([m.b_fc1 for m in lw.mlp]).contiguous(),
+                                                    torch.cat([m.w_fc2 for m in lw.mlp]).contiguous(), torch.cat([m.b_fc2 for m in lw.mlp]).contiguous())
+                ops.gemm(a, st[0], st[1], hid, PK_EPI_BIAS_GELU_BF16, group_offsets=offsets, n_groups=E, cta_pair=2)
+                ops.gemm(hid, st[2], st[3], x, PK_EPI_BIAS_RESID_F32, resid=x, out_row_index=src_of, group_offsets=offsets, n_groups=E,
+                         cta_pair=2)
+                if aux is not None:
+                    aux.setdefault("mlp_expert", {})[i] = expert.view(B, seq).clone()
+                continue
             for e, mw in enumerate(lw.mlp):
                 ops.gemm(a, mw.w_fc1, mw.b_fc1, hid, PK_EPI_BIAS_GELU_BF16, m_dev=counts[e:e + 1], row_begin_dev=offsets[e:e + 1])
                 if fused:

@@ -66,7 +66,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
          m: Optional[int] = None, epilogue_mode: int = 0, cta_pair: int = 0,
          xb_out: Optional[torch.Tensor] = None, row_stats: Optional[torch.Tensor] = None,
          ln_stats: Optional[torch.Tensor] = None, ln_c1: Optional[torch.Tensor] = None, ln_dim: int = 0, ln_eps: float = 0.0,
-         a_wrap_k: int = 0, out_format: int = PK_OUT_BF16) -> torch.Tensor:
+         a_wrap_k: int = 0, out_format: int = PK_OUT_BF16, group_offsets: Optional[torch.Tensor] = None,
+         n_groups: int = 0) -> torch.Tensor:
     """out = epilogue(a @ w.T + bias): a bf16 [M,K], w bf16 [N,K] (nn.Linear layout).  ``a_wrap_k`` = k: a is the two-term
     split row [lo | hi] (2k wide) read as lo, hi, hi against w = [Wh | Wl | Wh] (3k wide); ``out_format``: PK_OUT_F16 (half
     output) or PK_OUT_BF16X2 (out is [M, 2N]: the value split into [lo | hi])."""
@@ -77,6 +78,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
     if a_wrap_k > 0 and a.shape[1] != 2 * a_wrap_k:
         raise ValueError(f"a_wrap_k={a_wrap_k} needs a [M, {2 * a_wrap_k}] split operand, got {tuple(a.shape)}")
     N = w.shape[0]
+    if group_offsets is not None:                 # grouped launch: w is the groups' weights stacked, N one group's width
+        if n_groups < 1 or N % n_groups != 0:
+            raise ValueError(f"grouped GEMM: {N} stacked weight rows do not split into {n_groups} groups")
+        N //= n_groups
     if w.shape[1] != K:
         raise ValueError(f"K mismatch: a {tuple(a.shape)} w {tuple(w.shape)}")
     out_dtype = torch.bfloat16 if epilogue in (PK_EPI_BIAS_BF16, PK_EPI_BIAS_GELU_BF16) else torch.float32
@@ -111,6 +116,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
     args.ln_parts = ln_stats.shape[1] if ln_stats is not None else 0
     args.ln_dim, args.ln_eps = ln_dim, ln_eps
     args.a_wrap_k, args.out_format = a_wrap_k, out_format
+    args.group_offsets, args.n_groups = _ptr(group_offsets, torch.int32), n_groups
     if gemm_timeline is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -232,3 +232,11 @@ def test_moe_route_and_grouped_mlp(ops, E, D):
                      out_row_index=src_of, cta_pair=cta_pair)
         assert ops.device_flag() == 0
         assert ((y - ref).abs().max() / ref.abs().max()).item() < 1e-2
+    # the same as ONE grouped launch per projection (stacked weights, the tile scheduler walks the expert segments)
+    y = x.clone()
+    hid.fill_(float("nan"))
+    ops.gemm(a, torch.cat(w1), torch.cat(b1), hid, PK_EPI_BIAS_GELU_BF16, group_offsets=offsets, n_groups=E, cta_pair=2)
+    ops.gemm(hid, torch.cat(w2), torch.cat(b2), y, PK_EPI_BIAS_RESID_F32, resid=y, out_row_index=src_of, group_offsets=offsets,
+             n_groups=E, cta_pair=2)
+    assert ops.device_flag() == 0
+    assert ((y - ref).abs().max() / ref.abs().max()).item() < 1e-2
