@@ -524,11 +524,13 @@ softmax_xent_kernel(const float* __restrict__ logits, const long long* __restric
   float sum = 0.f;
   for (int c = lane; c < classes; c += 32) sum += __expf(z[c] - mx);
   sum = warp_sum(sum);
-  const int label = static_cast<int>(labels[b]);
+  const long long lab64 = labels[b];
+  const bool valid = lab64 >= 0 && lab64 < classes;          // an out-of-range label contributes nothing (no out-of-bounds read);
+  const int label = valid ? static_cast<int>(lab64) : -1;    // the host wrapper reports it (torch._assert_async)
   const float inv = 1.0f / sum;
   for (int c = lane; c < classes; c += 32)
-    dlogits[static_cast<long long>(b) * classes + c] = (__expf(z[c] - mx) * inv - (c == label ? 1.0f : 0.0f)) * inv_count;
-  if (lane == 0) {
+    dlogits[static_cast<long long>(b) * classes + c] = valid ? (__expf(z[c] - mx) * inv - (c == label ? 1.0f : 0.0f)) * inv_count : 0.f;
+  if (lane == 0 && valid) {
     atomicAdd(loss_sum, (logf(sum) + mx - z[label]) * inv_count);
     if (correct && arg == label) atomicAdd(correct, 1);
   }

@@ -143,6 +143,10 @@ class FineTuner:
         images = images.detach().to(torch.float32).contiguous()
         labels = labels.detach().to(torch.int64).contiguous()
         B = images.shape[0]
+        if labels.shape != (B,):
+            raise ValueError(f"labels must be a ({B},) class-index tensor, got {tuple(labels.shape)}")
+        # like nn.CrossEntropyLoss: class indices in [0, C); checked on the device without a host sync
+        torch._assert_async(((labels >= 0) & (labels < model.num_classes)).all())
         with torch.no_grad(), torch.cuda.device(dev):
             ops.raise_if_flagged(dev.index)
             pm = runner.packed(model)                       # rebuilt whenever optimizer.step() changed a parameter
