@@ -167,7 +167,8 @@ typedef struct pk_attention_args {
   int impl;                 /* 0 = auto: head_dim 64 runs on tcgen05/TMEM -- the dense kernel for uniform 64 < seq_len <= 256
                                without multiplicities, the ragged kernel for cu_seqlens / multiplicities / the virtual key /
                                short uniform sequences (<= 256 keys per sample) -- everything else on the general mma.sync
-                               kernel; 1 = general kernel, 2 = dense tcgen05 kernel, 3 = ragged tcgen05 kernel */
+                               kernel; 1 = general kernel, 2 = dense tcgen05 kernel, 3 = ragged tcgen05 kernel, 4 = quad-region
+                               ragged tcgen05 kernel (cu_seqlens, <= 128 keys per sample) */
   /* bf16x2 arithmetic mode (tcgen05 kernel only, impl 0 / 2 on an eligible shape): qkv_format PK_OUT_F16 = q, k, v are IEEE
    * half (11 significant bits; the probabilities are packed as half too); out_format PK_OUT_BF16X2 = `out` is
    * [rows, 2*D] holding the fp32 result split into lo (column d) and hi (column D + d), both bf16. */
@@ -176,6 +177,9 @@ typedef struct pk_attention_args {
    * route_rows set, the ragged tcgen05 kernel runs when *route_rows >= route_min_rows (long samples), the general mma.sync
    * kernel otherwise (the two-region TMEM pipeline does not pay off below ~130 rows per sample: profiles/r02). */
   const int* route_rows; int route_min_rows;
+  /* ... and, first, the quad-region tcgen05 kernel (four samples in flight per SM, at most 128 keys per sample) when
+   * *route_max_rows (+ 1 with a virtual key) <= 128: the longest sample of the batch, written by pk_exclusive_scan_i32. */
+  const int* route_max_rows;
   int total_rows;           /* rows of the qkv / out buffers (the ragged tcgen05 kernel's 2-D tensor maps need the extent: a
                                key tile that starts near the end of the buffer is zero-filled past it); 0 = unknown (the ragged
                                kernel is then not used).  Rows of `qkv` past the live ones must hold finite values. */
@@ -214,7 +218,8 @@ int pk_gather_rows(const float* x, float* y, const int* kept, int batch, int seq
 
 /* ---- ragged-batch plumbing shared by the sparse models -------------------------------- */
 /* cu_out[0..n] = exclusive prefix sum of lens[0..n) (cu_out[n] = total, also written to *total_out). */
-int pk_exclusive_scan_i32(const int* lens, int n, int* cu_out, int* total_out, void* stream);
+/* (max_out, optional: the largest of the n lengths -- the longest sample, for pk_attention_args.route_max_rows) */
+int pk_exclusive_scan_i32(const int* lens, int n, int* cu_out, int* total_out, int* max_out, void* stream);
 
 /* Gather the kept rows of every sample into a new packed buffer:
  * x_out[cu_out[b] + dst_local[r]] = scale_in[r] * x_in[r] for rows with dst_local[r] >= 0, carrying up to three

@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(OUT_DIR, "libpeekvit_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("PEEKVIT_B200_NVCC_FLAGS", "").split()        # e.g. -DPK_ATT_TRACE_BUILD for the pipeline-trace tools
 
 
 def _nvcc() -> str:

@@ -70,6 +70,8 @@ struct AttParams {
   const float* extra_mult;
   const int* route_rows;   // device-side routing: run only when *route_rows < route_min_rows (the tcgen05 kernel takes the rest)
   int route_min_rows;
+  const int* route_max_rows;   // ... and not when the longest sample has <= route_quad_keys rows (the quad-region kernel's batch)
+  int route_quad_keys;
 };
 
 // OCC = resident CTAs per SM the register allocation is capped for.  3 for uniform long sequences (steady-state tiles, no
@@ -89,6 +91,7 @@ attention_fwd_kernel(const AttParams p) {
   __shared__ __align__(128) uint8_t s_v[2][TILE_BYTES];
   __shared__ float s_bias[2][kAttBKV];
 
+  if (p.route_max_rows && *p.route_max_rows <= p.route_quad_keys) return;     // the quad-region tcgen05 kernel's launch takes this batch
   if (p.route_rows && *p.route_rows >= p.route_min_rows) return;     // the ragged tcgen05 kernel's launch takes this batch
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -322,6 +325,8 @@ bool attention_tc_eligible(const pk_attention_args* a);
 int launch_attention_tc(const pk_attention_args* a, cudaStream_t stream);
 bool attention_tcr_eligible(const pk_attention_args* a);
 int launch_attention_tcr(const pk_attention_args* a, cudaStream_t stream);
+bool attention_tcq_eligible(const pk_attention_args* a);
+int launch_attention_tcq(const pk_attention_args* a, cudaStream_t stream);
 int attention_trace_copy(unsigned long long* host_dst);
 
 }  // namespace pk
@@ -335,6 +340,15 @@ extern "C" int pk_attention_fwd(const pk_attention_args* a, void* stream) {
   PK_REQUIRE((a->extra_kv == nullptr) == (a->extra_mult == nullptr), "pk_attention_fwd: extra_kv and extra_mult go together");
   if (a->batch == 0 || a->max_seq_len == 0) return PK_OK;
   if (attention_tc_eligible(a)) return launch_attention_tc(a, static_cast<cudaStream_t>(stream));
+  // Quad-region tcgen05 kernel (every sample <= 128 keys): alone when the host knows it (static max_seq_len, or impl 4),
+  // otherwise launched next to the other kernels with the device-side longest-sample count deciding.
+  const bool quad = attention_tcq_eligible(a);
+  const bool quad_known = quad && a->max_seq_len + (a->extra_kv ? 1 : 0) <= 128;
+  PK_REQUIRE(a->impl != 4 || quad_known, "pk_attention_fwd: the quad-region tcgen05 kernel needs cu_seqlens, head_dim 64 and at most 128 keys per sample");
+  if (quad) {
+    const int rc = launch_attention_tcq(a, static_cast<cudaStream_t>(stream));
+    if (rc != PK_OK || quad_known) return rc;
+  }
   const bool routed = a->route_rows != nullptr && a->impl == 0 && attention_tcr_eligible(a);
   if (routed) {
     const int rc = launch_attention_tcr(a, static_cast<cudaStream_t>(stream));
@@ -358,6 +372,8 @@ extern "C" int pk_attention_fwd(const pk_attention_args* a, void* stream) {
   p.extra_mult = a->extra_mult;
   p.route_rows = routed ? a->route_rows : nullptr;
   p.route_min_rows = a->route_min_rows;
+  p.route_max_rows = (quad && !quad_known) ? a->route_max_rows : nullptr;
+  p.route_quad_keys = 128 - (a->extra_kv ? 1 : 0);
   const int max_len = a->cu_seqlens ? a->max_seq_len : a->seq_len;
   dim3 grid((max_len + kAttBQ - 1) / kAttBQ, a->num_heads, a->batch);
   PK_REQUIRE(a->batch <= 65535 && a->num_heads <= 65535, "pk_attention_fwd: batch/heads exceed grid limits; split the batch");

@@ -118,6 +118,9 @@ __device__ __forceinline__ void tmem_st_32x32_x8(uint32_t taddr, const uint32_t*
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
       : "memory");
 }
+// The clock64 trace is compiled in only with -DPK_ATT_TRACE_BUILD (PEEKVIT_B200_NVCC_FLAGS=-DPK_ATT_TRACE_BUILD python -m
+// peekvit_b200.build --force): even the untaken `if (p.trace && ...)` of ~25 call sites sat on the single-warp critical paths
+// of these kernels and cost the quad-region kernel 18 % and the ragged kernel 7 % (same-box A/B, profiles/r02).
 // trace slot layout: [item(0..15)][warp(0..15)][event(0..7)]
 __device__ __forceinline__ void tc_trace(const TcAttParams& p, int it, int ev) {
   if (p.trace && blockIdx.x == 0 && it < 16 && (threadIdx.x & 31) == 0) p.trace[(it * 16 + (threadIdx.x >> 5)) * 8 + ev] = clock64();
@@ -570,11 +573,20 @@ struct Tc3Smem {
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 // trace slots: warps 0-11 as they are, output warps 20-23 in slots 12-15
+// Compiled in for the trace build -- and, as it always was, for NPAD >= 192: the ViT-B/16 kernel (NPAD 208) owes its register
+// allocation to the scheduling points these calls are (without them ptxas spills 200 bytes and the kernel runs 184 us instead
+// of 134); the smaller tiles lose nothing and run 11 % faster without (uniform 99 tokens: 89 -> 79 us).
+template <int NPAD>
 __device__ __forceinline__ void tc3_trace(const TcAttParams& p, int it, int ev) {
+#ifndef PK_ATT_TRACE_BUILD
+  if constexpr (NPAD >= 192)
+#endif
+  {
   if (p.trace && blockIdx.x == 0 && it < 16 && (threadIdx.x & 31) == 0) {
     const int w = threadIdx.x >> 5;
     const int slot = w < 12 ? w : (w >= 20 ? w - 8 : -1);
     if (slot >= 0) p.trace[(it * 16 + slot) * 8 + ev] = clock64();
+  }
   }
 }
 
@@ -613,10 +625,10 @@ __device__ __forceinline__ void tc3_softmax_item(uint32_t t_base, int n, float s
     mx = 0.f;
   }
   *mx_mine = mx;
-  tc3_trace(p, it, 4);
+  tc3_trace<NPAD>(p, it, 4);
   named_bar_sync(bar_id, 64);
   mx = fmaxf(mx, *mx_other);
-  tc3_trace(p, it, 2);
+  tc3_trace<NPAD>(p, it, 2);
   const float neg_max_scaled = -mx * scale_log2;
   // ---- pass 2: p = exp2(s*scale - max*scale), partial row sum, bf16 P packed over this half's own consumed S columns
   float sum = 0.f;
@@ -712,7 +724,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int b = item / p.num_heads, h = item - b * p.num_heads;
       if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&qk_empty[qs]), qph ^ 1u, p.flag, 0x2100u + qs))) break;
-      tc3_trace(p, (item - blockIdx.x) / gridDim.x, 0);
+      tc3_trace<NPAD>(p, (item - blockIdx.x) / gridDim.x, 0);
       if (elect_one()) {
         const uint32_t bar = smem_u32(&qk_full[qs]);
         const uint32_t base = smem_u32(smem + qs * SM::kQKSlotBytes);
@@ -723,7 +735,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
       }
       __syncwarp();
       if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&v_empty[vs]), vph ^ 1u, p.flag, 0x2110u + vs))) break;
-      tc3_trace(p, (item - blockIdx.x) / gridDim.x, 1);
+      tc3_trace<NPAD>(p, (item - blockIdx.x) / gridDim.x, 1);
       if (elect_one()) {
         const uint32_t bar = smem_u32(&v_full[vs]);
         mbar_expect_tx(bar, SM::kKBytes);
@@ -746,7 +758,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int it = (item - blockIdx.x) / gridDim.x;
       if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&qk_full[qs]), qph, p.flag, 0x2200u + qs))) break;
-      tc3_trace(p, it, 4);
+      tc3_trace<NPAD>(p, it, 4);
       if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&s_free[r]), rph ^ 1u, p.flag, 0x2300u + r))) break;
       if (first && r == 1) {
         if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&p_ready[0]), 0u, p.flag, 0x2310u))) break;
@@ -754,7 +766,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
       first = false;
       tcgen05_fence_after();
       const uint32_t base = smem_u32(smem + qs * SM::kQKSlotBytes);
-      tc3_trace(p, it, 0);
+      tc3_trace<NPAD>(p, it, 0);
       if (elect_one()) {                       // S_r = Q_r K^T
         const uint64_t a_desc = umma_desc_kmajor_sw128(base + r * kTcQTileBytes);
         const uint64_t b_desc = umma_desc_kmajor_sw128(base + 2 * kTcQTileBytes);
@@ -765,11 +777,11 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
         umma_commit(smem_u32(&qk_empty[qs]));
       }
       __syncwarp();
-      tc3_trace(p, it, 1);
+      tc3_trace<NPAD>(p, it, 1);
       if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&p_ready[r]), rph, p.flag, 0x2400u + r))) break;
       if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&v_full[vs]), vph, p.flag, 0x2410u + vs))) break;
       tcgen05_fence_after();
-      tc3_trace(p, it, 2);
+      tc3_trace<NPAD>(p, it, 2);
       if (elect_one()) {                       // O_r = P_r V; P of key group k sits where the half that owns it packed it
         const uint64_t v_desc = umma_desc_mnmajor_sw128(smem_u32(smem + SM::kVOff + vs * SM::kKBytes));
         const uint32_t o_tmem = s_tmem + kTc3OCol;
@@ -782,7 +794,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
         umma_commit(smem_u32(&v_empty[vs]));
       }
       __syncwarp();
-      tc3_trace(p, it, 3);
+      tc3_trace<NPAD>(p, it, 3);
       rph ^= 1u;
       if (++qs == SM::kQKSlots) { qs = 0; qph ^= 1u; }
       if (++vs == SM::kVSlots) { vs = 0; vph ^= 1u; }
@@ -805,10 +817,10 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
     uint32_t rph = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int it = (item - blockIdx.x) / gridDim.x;
-      tc3_trace(p, it, 0);
+      tc3_trace<NPAD>(p, it, 0);
       if (!mbar_wait(smem_u32(&s_full[r]), rph, p.flag, 0x2500u + r)) break;
       tcgen05_fence_after();
-      tc3_trace(p, it, 1);
+      tc3_trace<NPAD>(p, it, 1);
       if (warp_has_rows) {
         if (half == 0) tc3_softmax_item<NPAD, 0, POLY, FMT>(t_base, n, scale_log2, mx_mine, mx_other, sum_mine, bar_id, p, it);
         else tc3_softmax_item<NPAD, 1, POLY, FMT>(t_base, n, scale_log2, mx_mine, mx_other, sum_mine, bar_id, p, it);
@@ -819,7 +831,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
         mbar_arrive(smem_u32(&p_ready[r]));
         mbar_arrive(smem_u32(&sum_ready[r]));
       }
-      tc3_trace(p, it, 3);
+      tc3_trace<NPAD>(p, it, 3);
       rph ^= 1u;
     }
   } else {
@@ -838,7 +850,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
         if (!mbar_wait(smem_u32(&sum_ready[r]), rph, p.flag, 0x2700u + r)) { ok = false; break; }
         if (!mbar_wait(smem_u32(&o_full[r]), rph, p.flag, 0x2600u + r)) { ok = false; break; }
         tcgen05_fence_after();
-        tc3_trace(p, it, r * 3 + 0);
+        tc3_trace<NPAD>(p, it, r * 3 + 0);
         const bool has_rows = row0 < n;          // warp-uniform
         const float inv = 1.0f / (sum_part[(r * 2 + 0) * 128 + q * 32 + lane] + sum_part[(r * 2 + 1) * 128 + q * 32 + lane]);
         // O row: both 32-column halves in flight at once, so the region is handed back after a single TMEM round trip
@@ -882,7 +894,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
               *reinterpret_cast<uint4*>(stg + 4096 + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
           }
-          tc3_trace(p, it, r * 3 + 1);
+          tc3_trace<NPAD>(p, it, r * 3 + 1);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -895,7 +907,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
             bulk_commit();
           }
         }
-        tc3_trace(p, it, r * 3 + 2);
+        tc3_trace<NPAD>(p, it, r * 3 + 2);
       }
       if (!ok) break;
       rph ^= 1u;
@@ -960,16 +972,19 @@ struct TcrParams {
   unsigned long long* trace;   // PK_ATT_TRACE=1: CTA 0 records clock64 at pipeline events of its first 16 units (tools/attn_trace_tcr.py)
   const int* route_rows;       // device-side routing: run only when *route_rows >= route_min_rows
   int route_min_rows;
+  const int* route_max_rows;   // device-side routing: longest sample of the batch; <= 128 keys -> the quad-region kernel runs
 };
 
 // trace slot layout: [unit(0..15)][slot(0..15)][event(0..7)]; slots: warps 0-3 as they are, softmax warps 4 / 8 / 12 / 16 -> 4..7
 // (region 0 half 0, region 0 half 1, region 1 half 0, region 1 half 1; lane quarter 0 each), output warps 20-23 -> 8..11
 __device__ __forceinline__ void tcr_trace(const TcrParams& p, int k, int ev) {
+#ifdef PK_ATT_TRACE_BUILD
   if (p.trace && blockIdx.x == 0 && k < 16 && (threadIdx.x & 31) == 0) {
     const int w = threadIdx.x >> 5;
     const int slot = w < 4 ? w : (w >= 20 ? w - 12 : ((w & 3) == 0 ? 4 + ((w - 4) >> 2) : -1));
     if (slot >= 0) p.trace[(k * 16 + slot) * 8 + ev] = clock64();
   }
+#endif
 }
 
 struct TcrUnit {
@@ -1040,6 +1055,7 @@ __global__ void __launch_bounds__(kTcrThreads, 1)
 attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv_small,
                      const __grid_constant__ CUtensorMap tmap_kv_full, const __grid_constant__ CUtensorMap tmap_out, const TcrParams p) {
   if (p.route_rows && *p.route_rows < p.route_min_rows) return;      // short samples: the general kernel's launch takes this batch
+  if (p.route_max_rows && *p.route_max_rows + (p.extra_kv ? 1 : 0) <= 128) return;      // ... or the quad-region kernel's
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using SM = TcrSmem<NMAX>;
@@ -1205,12 +1221,25 @@ attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       float* lm = lm_rows + (k & 3) * 256;
       // bias row (its previous user, unit k - 4, finished its softmax before this unit's Q/K slot could even be refilled)
       int first_special = NMAX;                    // first key whose bias is not zero (multiplicity != 1, virtual key, padding)
-      for (int j = lane; j < NMAX; j += 32) {
-        float v = -INFINITY;
-        if (j < t.len) v = p.key_mult ? __log2f(p.key_mult[t.row0 + j]) : 0.f;
-        else if (j == t.len && t.extra > 0.f) v = __log2f(t.extra);
-        lm[j] = v;
-        if (v != 0.f && j < first_special) first_special = j;
+      // all multiplicity loads in flight at once (one dependent L2 round trip per 32 keys made this warp, which every unit
+      // passes through in order, the kernel's bottleneck: tools/attn_trace_tcq.py)
+      constexpr int kIt = (NMAX + 31) / 32;
+      float kmv[kIt];
+#pragma unroll
+      for (int i = 0; i < kIt; ++i) {
+        const int j = lane + 32 * i;
+        kmv[i] = (p.key_mult && j < t.len) ? p.key_mult[t.row0 + j] : 1.0f;
+      }
+#pragma unroll
+      for (int i = 0; i < kIt; ++i) {
+        const int j = lane + 32 * i;
+        if (j < NMAX) {
+          float v = -INFINITY;
+          if (j < t.len) v = p.key_mult ? __log2f(kmv[i]) : 0.f;
+          else if (j == t.len && t.extra > 0.f) v = __log2f(t.extra);
+          lm[j] = v;
+          if (v != 0.f && j < first_special) first_special = j;
+        }
       }
       // Multiplicities other than 1 sit at the END of a sample (its ghost row, then the virtual key, then padding), so nearly
       // every 16-key group is "plain": the softmax takes x = s * scale there without reading the bias row.
@@ -1386,6 +1415,379 @@ attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tcr_trace(p, kk, 3);
     }
     if (lane == 0) bulk_wait_read<0>();       // smem must outlive the last store's reads
+  }
+
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ======================================================================================================================
+// Quad-region variant ("tcq") for batches whose samples all have at most 128 keys (ResidualViT at budgets <= ~0.5, the late
+// A-ViT layers): the ragged kernel above keeps two units in flight per SM, and its per-unit chain (S ready -> row max -> exp
+// -> P.V -> O read-out -> next Q.K^T, ~10 000 cycles) is the same whether a sample has 80 rows or 200 -- short samples cannot
+// amortise it.  With at most 128 keys a TMEM region needs only 128 columns (S at [0, npad), bf16 P packed over the consumed
+// S columns at [0, npad / 2), O at [64, 128)), so FOUR units run concurrently: unit k of a CTA uses region / Q-K slot / V slot
+// k & 3.  One MMA-issuing warp per region (on four different schedulers), one softmax + output warp per TMEM lane quarter and region
+// (no column split, hence no partial maxima to exchange) -- the issuing warp also writes its region's bias row and virtual
+// key rows; every softmax warp also reads its rows of O out, scales them and stores them (staged in the region's V slot).
+// Units = one (sample, head); q_tiles == 1.  Launched next to the other two ragged kernels; *route_max_rows decides on the
+// device which one runs (pk_attention_args.route_max_rows).
+constexpr int kTcqThreads = 768;                   // warps: 0 Q/K TMA, 1-4 MMA + patch (region 0-3), 6 V TMA, 5 / 7 idle, 8-23 softmax + output
+constexpr int kTcqNMax = 128;
+constexpr int kTcqRegionCols = 128;
+constexpr int kTcqOCol = 64;
+constexpr int kTcqRegsSoftmax = 96, kTcqRegsMma = 56, kTcqRegsOther = 40;
+// The pool is what the CTA was LAUNCHED with (768 threads x 80 registers = 61 440), not the SM's 65 536: a setmaxnreg.inc
+// that asks for more than the other warps have released blocks for ever (no watchdog can see it).
+// (16 x 96 + 4 x 56 + 4 x 40) warps x 32 = 61 440 registers
+static_assert((16 * kTcqRegsSoftmax + 4 * kTcqRegsMma + 4 * kTcqRegsOther) * 32 <= kTcqThreads * 80, "setmaxnreg budget exceeds the launch allocation");
+struct TcqSmem {
+  static constexpr int kKBytes = kTcqNMax * 128;
+  static constexpr int kQKSlotBytes = kTcQTileBytes + kKBytes;            // one Q tile + K rows: 32 KB
+  static constexpr int kVOff = 4 * kQKSlotBytes;                           // 128 KB
+  static constexpr int kLmOff = kVOff + 4 * kKBytes;                       // + 64 KB (the V slots double as output staging)
+  static constexpr int kBarOff = kLmOff + 4 * kTcqNMax * 4;                // bias rows: 4 x 128 f32
+  static constexpr int kBytes = kBarOff + 512 + 1024;
+  static_assert(kBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
+};
+
+// trace slots: warps 0-7 as they are, softmax warps 8 / 12 / 16 / 20 (lane quarter 0 of region 0-3) -> 8..11, output warps -> 12..15
+__device__ __forceinline__ void tcq_trace(const TcrParams& p, int k, int ev) {
+#ifdef PK_ATT_TRACE_BUILD
+  if (p.trace && blockIdx.x == 0 && k >= 8 && k < 24 && (threadIdx.x & 31) == 0) {
+    const int w = threadIdx.x >> 5;
+    const int slot = w < 8 ? w : (w >= 24 ? w - 12 : ((w & 3) == 0 ? 8 + ((w - 8) >> 2) : -1));
+    if (slot >= 0) p.trace[((k - 8) * 16 + slot) * 8 + ev] = clock64();
+  }
+#endif
+}
+__device__ __forceinline__ bool tcq_selected(const TcrParams& p) {
+  return p.route_max_rows && *p.route_max_rows + (p.extra_kv ? 1 : 0) <= kTcqNMax;
+}
+
+__global__ void __launch_bounds__(kTcqThreads, 1)
+attention_tcq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv_small,
+                     const __grid_constant__ CUtensorMap tmap_kv_full, const __grid_constant__ CUtensorMap tmap_out, const TcrParams p) {
+  if (p.route_max_rows && !tcq_selected(p)) return;          // a sample with more than 128 keys: the other launches take the batch
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using SM = TcqSmem;
+  float* lm_rows = reinterpret_cast<float*>(smem + SM::kLmOff);                   // [4][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kBarOff);
+  uint64_t* qk_full = bars;            // [4] TMA landed
+  uint64_t* qk_ready = bars + 4;       // [4] virtual key + bias row written (patch warp)
+  uint64_t* qk_empty = bars + 8;       // [4] QK MMA retired
+  uint64_t* v_full = bars + 12;        // [4]
+  uint64_t* v_ready = bars + 16;       // [4]
+  uint64_t* v_empty = bars + 20;       // [4] PV MMA retired
+  uint64_t* s_full = bars + 24;        // [4] S ready
+  uint64_t* p_ready = bars + 28;       // [4] P written + row sums published (4 softmax-warp arrivals)
+  uint64_t* o_full = bars + 32;        // [4] O ready
+  uint64_t* s_free = bars + 36;        // [4] O read out (4 output-warp arrivals)
+  uint64_t* sum_ready = bars + 40;     // [4] row sums published (4 softmax-warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 44);
+  int* plain_groups = reinterpret_cast<int*>(bars + 48);   // [4] leading 16-key groups of unit k & 3 whose bias is all zero
+
+  const int warp = warp_id();
+  const int lane = lane_id();
+  const int D = p.num_heads * kTcDH;
+  const int num_units = p.batch * p.num_heads;             // q_tiles == 1
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_kv_small);
+    tma_prefetch_desc(&tmap_kv_full);
+    tma_prefetch_desc(&tmap_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(smem_u32(&qk_full[i]), 1);
+      mbar_init(smem_u32(&qk_ready[i]), 1);
+      mbar_init(smem_u32(&qk_empty[i]), 1);
+      mbar_init(smem_u32(&v_full[i]), 1);
+      mbar_init(smem_u32(&v_ready[i]), 1);
+      mbar_init(smem_u32(&v_empty[i]), 4);             // the region's four softmax / output warps, after their stores
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&p_ready[i]), 4);
+      mbar_init(smem_u32(&o_full[i]), 1);
+      mbar_init(smem_u32(&s_free[i]), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Every role walks the same unit sequence; the k-th unit of this CTA uses region = slot = bias row k & 3.  Empty samples are
+  // skipped by every role alike (their position still counts), so barrier parities are kept per region, not derived from k.
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    setmaxnreg_dec<kTcqRegsOther>();
+    int k = 0;
+    uint32_t phases = 0, used = 0;        // per region: parity of its next handshake / whether it has run a unit yet
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++k) {
+      TcrUnit t;
+      if (!tcr_unit(p, u, t)) continue;   // empty sample (an A-ViT sample whose class token has halted): every role skips it
+      const int r = k & 3;
+      const uint32_t ph = (phases >> r) & 1u;
+      phases ^= 1u << r;
+      const bool first_use = !((used >> r) & 1u);
+      used |= 1u << r;
+      const bool small = t.npad <= p.box_small;
+      const uint32_t kv_bytes = static_cast<uint32_t>(small ? p.box_small : kTcqNMax) * 128u;
+      const CUtensorMap* kvmap = small ? &tmap_kv_small : &tmap_kv_full;
+      tcq_trace(p, k, 0);
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&qk_empty[r]), ph ^ 1u, p.flag, 0x4100u + r))) break;
+      tcq_trace(p, k, 1);
+      if (elect_one()) {
+        const uint32_t bar = smem_u32(&qk_full[r]);
+        const uint32_t base = smem_u32(smem + r * SM::kQKSlotBytes);
+        mbar_expect_tx(bar, kTcQTileBytes + kv_bytes);
+        tma_load_2d(base, &tmap_q, bar, t.h * kTcDH, t.row0);
+        tma_load_2d(base + kTcQTileBytes, kvmap, bar, D + t.h * kTcDH, t.row0);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 6) {
+    // ------------------------------------------------------------------ V producer (its own warp: a V slot frees up at the END of
+    // its previous unit's chain, a Q / K slot right after that unit's Q K^T -- one in-order producer would hold the next
+    // regions' Q / K loads back behind this unit's V wait)
+    setmaxnreg_dec<kTcqRegsOther>();
+    int k = 0;
+    uint32_t phases = 0, used = 0;        // per region: parity of its next handshake / whether it has run a unit yet
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++k) {
+      TcrUnit t;
+      if (!tcr_unit(p, u, t)) continue;   // empty sample (an A-ViT sample whose class token has halted): every role skips it
+      const int r = k & 3;
+      const uint32_t ph = (phases >> r) & 1u;
+      phases ^= 1u << r;
+      const bool first_use = !((used >> r) & 1u);
+      used |= 1u << r;
+      const bool small = t.npad <= p.box_small;
+      const uint32_t kv_bytes = static_cast<uint32_t>(small ? p.box_small : kTcqNMax) * 128u;
+      const CUtensorMap* kvmap = small ? &tmap_kv_small : &tmap_kv_full;
+      tcq_trace(p, k, 0);
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&v_empty[r]), ph ^ 1u, p.flag, 0x4110u + r))) break;
+      tcq_trace(p, k, 1);
+      if (elect_one()) {
+        const uint32_t bar = smem_u32(&v_full[r]);
+        mbar_expect_tx(bar, kv_bytes);
+        tma_load_2d(smem_u32(smem + SM::kVOff + r * SM::kKBytes), kvmap, bar, 2 * D + t.h * kTcDH, t.row0);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 1 && warp <= 4) {
+    // ------------------------------------------------------------------ MMA issuers: warp 1 + r -> region r
+    setmaxnreg_dec<kTcqRegsMma>();
+    const int r = warp - 1;
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, kTcDH, /*b_mn_major=*/1);
+    const uint32_t s_tmem = tmem_base + static_cast<uint32_t>(r * kTcqRegionCols);
+    const uint32_t qk_base = smem_u32(smem + r * SM::kQKSlotBytes);
+    const uint64_t a_desc = umma_desc_kmajor_sw128(qk_base);
+    const uint64_t b_desc = umma_desc_kmajor_sw128(qk_base + kTcQTileBytes);
+    const uint64_t v_desc = umma_desc_mnmajor_sw128(smem_u32(smem + SM::kVOff + r * SM::kKBytes));
+    uint32_t ph_next = 0;
+    int k = r - 4;
+    for (int u = blockIdx.x + r * gridDim.x; u < num_units; u += 4 * gridDim.x) {
+      k += 4;
+      TcrUnit t;
+      if (!tcr_unit(p, u, t)) continue;
+      const uint32_t ph = ph_next;
+      ph_next ^= 1u;
+      // ---- this unit's bias row and virtual key, by the region's own issuing warp (a shared in-order patch warp was the
+      // bottleneck of the whole kernel: 4 500 cycles per unit, every region queueing behind it).  The region's previous
+      // softmax is over (its p_ready was waited for below), so the bias row is free; all multiplicity loads go out at once.
+      tcq_trace(p, k, 0);
+      {
+        float kmv[kTcqNMax / 32];
+#pragma unroll
+        for (int i = 0; i < kTcqNMax / 32; ++i) {
+          const int j = lane + 32 * i;
+          kmv[i] = (p.key_mult && j < t.len) ? p.key_mult[t.row0 + j] : 1.0f;
+        }
+        float* lm = lm_rows + r * kTcqNMax;
+        int first_special = kTcqNMax;
+#pragma unroll
+        for (int i = 0; i < kTcqNMax / 32; ++i) {
+          const int j = lane + 32 * i;
+          float v = -INFINITY;
+          if (j < t.len) v = p.key_mult ? __log2f(kmv[i]) : 0.f;
+          else if (j == t.len && t.extra > 0.f) v = __log2f(t.extra);
+          lm[j] = v;
+          if (v != 0.f && j < first_special) first_special = j;
+        }
+        first_special = warp_min_i32(first_special);
+        if (lane == 0) plain_groups[r] = first_special >> 4;
+      }
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&qk_full[r]), ph, p.flag, 0x4200u + r))) break;
+      tcq_trace(p, k, 1);
+      if (t.extra > 0.f && lane < 8) {
+        // K row `len`: 16-byte chunk c of row j lives at chunk c ^ (j & 7) of its 128-byte line (SWIZZLE_128B)
+        const uint4 kb = *reinterpret_cast<const uint4*>(p.extra_kv + t.h * kTcDH + lane * 8);
+        *reinterpret_cast<uint4*>(smem + r * SM::kQKSlotBytes + kTcQTileBytes + t.len * 128 + ((lane ^ (t.len & 7)) << 4)) = kb;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&qk_ready[r]));          // publishes the bias row to the softmax warps
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&s_free[r]), ph ^ 1u, p.flag, 0x4300u + r))) break;
+      tcq_trace(p, k, 2);
+      tcgen05_fence_after();
+      const uint32_t idesc_qk = umma_idesc_bf16(128, t.npad);
+      if (elect_one()) {                       // S = Q K^T over the unit's padded key count
+#pragma unroll
+        for (int ks = 0; ks < kTcDH / 16; ++ks)
+          umma_bf16(s_tmem, a_desc + static_cast<uint64_t>(2 * ks), b_desc + static_cast<uint64_t>(2 * ks), idesc_qk, ks != 0 ? 1u : 0u);
+        umma_commit(smem_u32(&s_full[r]));
+        umma_commit(smem_u32(&qk_empty[r]));
+      }
+      __syncwarp();
+      tcq_trace(p, k, 3);
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&v_full[r]), ph, p.flag, 0x4410u + r))) break;
+      if (t.extra > 0.f && lane < 8) {
+        const uint4 vb = *reinterpret_cast<const uint4*>(p.extra_kv + D + t.h * kTcDH + lane * 8);
+        *reinterpret_cast<uint4*>(smem + SM::kVOff + r * SM::kKBytes + t.len * 128 + ((lane ^ (t.len & 7)) << 4)) = vb;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      tcq_trace(p, k, 4);
+      if (!__all_sync(0xffffffffu, mbar_wait(smem_u32(&p_ready[r]), ph, p.flag, 0x4400u + r))) break;
+      tcq_trace(p, k, 5);
+      tcgen05_fence_after();
+      const int G = t.npad >> 4;
+      if (elect_one()) {                       // O = P V; the probabilities of key group g sit at region columns [8g, 8g + 8)
+        const uint32_t o_tmem = s_tmem + kTcqOCol;
+#pragma unroll
+        for (int g = 0; g < kTcqNMax / 16; ++g)
+          if (g < G) umma_bf16_ts(o_tmem, s_tmem + static_cast<uint32_t>(8 * g), v_desc + static_cast<uint64_t>(128 * g), idesc_pv, g != 0 ? 1u : 0u);
+        umma_commit(smem_u32(&o_full[r]));
+      }
+      __syncwarp();
+      tcq_trace(p, k, 6);
+    }
+  } else if (warp == 5 || warp == 7) {
+    setmaxnreg_dec<kTcqRegsOther>();          // idle
+  } else {
+    // ------------------------------------------------------------------ softmax + output warps: one per region and TMEM lane quarter
+    setmaxnreg_inc<kTcqRegsSoftmax>();
+    const int r = (warp - 8) >> 2;
+    const int q = warp & 3;
+    const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(r * kTcqRegionCols);
+    const float scale_log2 = p.scale_log2;
+    const uint32_t lm_s = smem_u32(lm_rows + r * kTcqNMax);
+    uint32_t ph_next = 0;
+    int k = r - 4;
+    for (int u = blockIdx.x + r * gridDim.x; u < num_units; u += 4 * gridDim.x) {
+      k += 4;
+      TcrUnit t;
+      if (!tcr_unit(p, u, t)) continue;
+      const uint32_t ph = ph_next;
+      ph_next ^= 1u;
+      tcq_trace(p, k, 0);
+      if (!mbar_wait(smem_u32(&qk_ready[r]), ph, p.flag, 0x4510u + r)) break;      // the bias row of this unit is published
+      if (!mbar_wait(smem_u32(&s_full[r]), ph, p.flag, 0x4500u + r)) break;
+      tcq_trace(p, k, 1);
+      tcgen05_fence_after();
+      const bool has_rows = q * 32 < t.len;              // warp-uniform: this lane quarter holds query rows
+      float row_sum = 1.0f;
+      if (has_rows) {
+        const int G = t.npad >> 4;
+        const int np = min(G, plain_groups[r]);           // leading groups of plain keys
+        const uint64_t sc2 = f2_pack(scale_log2, scale_log2);
+        uint32_t ha[16], hb[16];
+        // ---- pass 1: row maximum of x = s * scale * log2e + lm
+        float mx = -INFINITY, mraw = -INFINITY;
+        int j = 0;
+        for (; j + 2 <= np; j += 2) {
+          uint32_t w[32];
+          tmem_ld_32x32(t_base + static_cast<uint32_t>(16 * j), w);
+          tmem_ld_wait();
+          mraw = row_max16<false>(w, mraw, 0, 0);
+          mraw = row_max16<false>(w + 16, mraw, 0, 0);
+        }
+        for (; j < G; ++j) {
+          tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(16 * j), ha);
+          tmem_ld_wait();
+          if (j < np) mraw = row_max16<false>(ha, mraw, 0, 0);
+          else mx = tcr_lm_max16(ha, lm_s + static_cast<uint32_t>(64 * j), sc2, mx);
+        }
+        mx = fmaxf(mx, mraw * scale_log2);
+        tcq_trace(p, k, 2);
+        // ---- pass 2: p = exp2(x - max), row sum, bf16 P packed over the S columns already consumed
+        float sum = 0.f;
+        tmem_ld_32x32_x16(t_base, ha);
+        tmem_ld_wait();
+        for (j = 0; j < G; ++j) {
+          uint32_t (&cur)[16] = (j & 1) ? hb : ha;
+          uint32_t (&nxt)[16] = (j & 1) ? ha : hb;
+          if (j + 1 < G) tmem_ld_32x32_x16(t_base + static_cast<uint32_t>(16 * (j + 1)), nxt);
+          uint32_t pk[8];
+          if (j < np) sum += softmax_group16<false, 0, 0>(cur, pk, scale_log2, -mx, 0, 0);
+          else sum += tcr_lm_group16(cur, pk, lm_s + static_cast<uint32_t>(64 * j), sc2, -mx);
+          if (j + 1 < G) tmem_ld_wait();                 // the next group is in registers before its columns may be overwritten
+          tmem_st_32x32_x8(t_base + static_cast<uint32_t>(8 * j), pk);
+        }
+        tmem_st_wait();
+        row_sum = sum;
+      }
+      tcq_trace(p, k, 3);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&p_ready[r]));
+      // ---- output of the same rows by the same warp (a shared set of output warps took ~3 000 cycles per unit, every
+      // region queueing behind it): O out of TMEM, scaled by 1 / row sum, staged in the region's V slot -- dead once P.V has
+      // retired, and not needed again before the next unit's softmax is over -- and stored by TMA (full 32-row blocks) or row
+      // by row (the block that straddles the end of the sample)
+      if (!mbar_wait(smem_u32(&o_full[r]), ph, p.flag, 0x4600u + r)) break;
+      tcgen05_fence_after();
+      const bool full = q * 32 + 32 <= t.len;
+      uint32_t pk[32];                                       // this thread's row of O, scaled, as 32 bf16 pairs
+      if (has_rows) {
+        const float inv = 1.0f / row_sum;
+        uint32_t raw[32];
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {                  // two 32-column reads: the raw fp32 half is dead before the next
+          tmem_ld_32x32(t_base + kTcqOCol + 32 * hlf, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[16 * hlf + i] = pack_bf16(__uint_as_float(raw[2 * i]) * inv, __uint_as_float(raw[2 * i + 1]) * inv);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_free[r]));     // the region may take its next unit's S
+      if (has_rows) {
+        auto chunk = [&](int c) { return make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]); };
+        if (full) {
+          uint8_t* stg = smem + SM::kVOff + r * SM::kKBytes + q * 4096;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) = chunk(c);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_out, smem_u32(stg), t.h * kTcDH, t.row0 + q * 32);
+            bulk_commit();
+            bulk_wait_read<0>();                            // the V slot may be refilled once the store has read it
+          }
+        } else if (q * 32 + lane < t.len) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<long long>(t.row0 + q * 32 + lane) * D + t.h * kTcDH);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) dst[c] = chunk(c);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&v_empty[r]));
+      tcq_trace(p, k, 4);
+    }
   }
 
   __syncwarp();
@@ -1582,6 +1984,8 @@ bool attention_tcr_eligible(const pk_attention_args* a) {
   return a->total_rows > 0;
 }
 
+bool attention_tcq_eligible(const pk_attention_args* a);
+
 template <int NMAX>
 static int launch_tcr(const pk_attention_args* a, cudaStream_t stream, int max_len) {
   const int D = a->num_heads * kTcDH;
@@ -1613,6 +2017,7 @@ static int launch_tcr(const pk_attention_args* a, cudaStream_t stream, int max_l
   p.trace = tc_trace_buffer();
   p.route_rows = (a->impl == 0) ? a->route_rows : nullptr;
   p.route_min_rows = a->route_min_rows;
+  p.route_max_rows = (a->impl == 0 && attention_tcq_eligible(a)) ? a->route_max_rows : nullptr;
   const long long units = static_cast<long long>(a->batch) * a->num_heads * p.q_tiles;
   int grid = num_sms();
   if (units < grid) grid = static_cast<int>(units);
@@ -1623,6 +2028,68 @@ static int launch_tcr(const pk_attention_args* a, cudaStream_t stream, int max_l
   }
   attention_tcr_kernel<NMAX><<<grid, kTcrThreads, TcrSmem<NMAX>::kBytes, stream>>>(tq, tks, tkf, tout, p);
   return check_cuda(cudaGetLastError(), "attention_tcr_kernel launch");
+}
+
+// ---------------------------------------------------------------------------------------------------- quad-region kernel launch
+// Eligible: what the ragged kernel takes, for batches whose samples have at most 128 keys -- known on the host (max_seq_len) or
+// decided on the device (route_max_rows).  PK_ATT_TCQ=0 switches it off (A/B runs).
+static int tcq_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PK_ATT_TCQ"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
+}
+bool attention_tcq_eligible(const pk_attention_args* a) {
+  if (!tcq_enabled() || !(a->impl == 0 || a->impl == 4)) return false;
+  if (a->head_dim != kTcDH || a->qkv_format != PK_OUT_BF16 || a->out_format != PK_OUT_BF16) return false;
+  if (!a->cu_seqlens) return false;                                        // packed ragged rows only
+  if ((reinterpret_cast<uintptr_t>(a->qkv) & 15) != 0 || (reinterpret_cast<uintptr_t>(a->out) & 15) != 0) return false;
+  if (a->extra_kv && (reinterpret_cast<uintptr_t>(a->extra_kv) & 15) != 0) return false;
+  if (a->total_rows <= 0) return false;
+  const bool host_knows = a->max_seq_len + (a->extra_kv ? 1 : 0) <= kTcqNMax;
+  return host_knows || (a->impl == 0 && a->route_max_rows != nullptr);
+}
+
+int launch_attention_tcq(const pk_attention_args* a, cudaStream_t stream) {
+  const int D = a->num_heads * kTcDH;
+  const uint64_t rows = static_cast<uint64_t>(a->total_rows);
+  const int box_small = 64;
+  CUtensorMap tq, tks, tkf, tout;
+  int rc = make_tmap_bf16_2d(&tq, a->qkv, rows, 3ull * D, 3ull * D, 128, 64);
+  if (rc != PK_OK) return rc;
+  rc = make_tmap_bf16_2d(&tks, a->qkv, rows, 3ull * D, 3ull * D, box_small, 64);
+  if (rc != PK_OK) return rc;
+  rc = make_tmap_bf16_2d(&tkf, a->qkv, rows, 3ull * D, 3ull * D, kTcqNMax, 64);
+  if (rc != PK_OK) return rc;
+  rc = make_tmap_bf16_2d(&tout, a->out, rows, static_cast<uint64_t>(D), static_cast<uint64_t>(D), 32, 64);
+  if (rc != PK_OK) return rc;
+  TcrParams p;
+  p.cu_seqlens = a->cu_seqlens;
+  p.key_mult = a->key_mult;
+  p.extra_kv = static_cast<const __nv_bfloat16*>(a->extra_kv);
+  p.extra_mult = a->extra_mult;
+  p.out = static_cast<__nv_bfloat16*>(a->out);
+  p.batch = a->batch;
+  p.num_heads = a->num_heads;
+  p.seq_len = a->seq_len;
+  p.q_tiles = 1;
+  p.box_small = box_small;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.flag = device_flag_ptr();
+  p.trace = tc_trace_buffer();
+  p.route_rows = nullptr;
+  p.route_min_rows = 0;
+  // the device-side choice applies unless the host already knows that every sample fits
+  p.route_max_rows = (a->max_seq_len + (a->extra_kv ? 1 : 0) <= kTcqNMax) ? nullptr : a->route_max_rows;
+  const long long units = static_cast<long long>(a->batch) * a->num_heads;
+  int grid = num_sms();
+  if (units < grid) grid = static_cast<int>(units);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PK_CHECK_CUDA(cudaFuncSetAttribute(attention_tcq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcqSmem::kBytes));
+    attr_set = true;
+  }
+  attention_tcq_kernel<<<grid, kTcqThreads, TcqSmem::kBytes, stream>>>(tq, tks, tkf, tout, p);
+  return check_cuda(cudaGetLastError(), "attention_tcq_kernel launch");
 }
 
 int launch_attention_tcr(const pk_attention_args* a, cudaStream_t stream) {

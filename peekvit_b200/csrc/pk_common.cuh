@@ -167,6 +167,9 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, unsigne
   unsigned long long t0 = 0;
   for (uint32_t it = 1;; ++it) {
     if (mbar_try_wait_suspend(bar, parity)) return true;
+#ifdef PK_MBAR_SLEEP_NS
+    if (it > 2) __nanosleep(PK_MBAR_SLEEP_NS);
+#endif
     if ((it & 0x3ffu) == 0) {
       if (*(volatile unsigned int*)flag != 0u) return false;
       const unsigned long long now = global_timer_ns();

@@ -731,3 +731,51 @@ def test_attention_ragged_device_side_routing(ops, min_rows):
     ops.attention(qkv, forced, B, H, dh, cu_seqlens=cu, max_seq_len=199, key_mult=km, extra_kv=ekv, extra_mult=em,
                   impl=3 if min_rows == 1 else 1)
     assert torch.equal(out[:rows], forced[:rows])          # bit-identical to the kernel the threshold selects
+
+
+# ------------------------------------------------------------------ quad-region ragged tcgen05 attention ("tcq", <= 128 keys per sample)
+@pytest.mark.parametrize("with_mult,with_extra", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("lens", [[3, 70, 127, 1, 64, 65, 33, 16, 17], [80, 77, 91, 64, 85, 79, 102, 60, 66, 71, 93, 88] * 3,
+                                  [12] * 9, [127, 127, 127, 127, 5], [40, 0, 23, 0, 0, 90, 1]])
+def test_attention_quad_region_tcgen05_against_reference(ops, lens, with_mult, with_extra):
+    """impl=4 forces the quad-region kernel: four samples in flight per SM, one (sample, head) per unit, key counts on both
+    sides of every 16-key group boundary, per-key multiplicities, the virtual bias key, EMPTY samples (an A-ViT sample whose
+    class token has halted), rows of the buffer past the live ones left untouched."""
+    B, H, dh = len(lens), 6, 64
+    D = H * dh
+    if max(lens) + (1 if with_extra else 0) > 128:
+        pytest.skip("more than 128 keys")
+    qkv, cu, km, ekv, em, rows = _ragged_case(lens, H, 5 * sum(lens) + with_mult + 2 * with_extra, with_mult, with_extra, pad_rows=40)
+    out = torch.full((rows + 40, D), 3.0, device=DEV, dtype=torch.bfloat16)
+    ops.attention(qkv, out, B, H, dh, cu_seqlens=cu, max_seq_len=max(lens), key_mult=km, extra_kv=ekv, extra_mult=em, impl=4)
+    assert ops.device_flag() == 0
+    ref = ref_attention(qkv[:rows], B, H, dh, lens, km[:rows] if km is not None else None, ekv, em)
+    assert rel_err(out[:rows], ref) < TOL_BF16
+    assert bool((out[rows:] == 3.0).all())
+
+
+@pytest.mark.parametrize("longest,expect_quad", [(100, True), (127, True), (128, False), (190, False)])
+def test_attention_three_way_device_side_routing(ops, longest, expect_quad):
+    """route_max_rows: the longest sample (written by pk_exclusive_scan_i32) decides on the device whether the quad-region
+    kernel runs (<= 128 keys incl. the virtual key) or one of the other two; whichever runs, the result is the reference's and
+    bit-identical to that kernel launched alone."""
+    lens = [longest, 33, 77, 5, 64]
+    B, H, dh = len(lens), 6, 64
+    D = H * dh
+    qkv, cu, km, ekv, em, rows = _ragged_case(lens, H, 9, True, True, pad_rows=16)
+    lens_dev = torch.tensor(lens, device=DEV, dtype=torch.int32)
+    cu2, tot, mx = torch.empty(B + 1, device=DEV, dtype=torch.int32), torch.empty(1, device=DEV, dtype=torch.int32), torch.empty(1, device=DEV, dtype=torch.int32)
+    ops.exclusive_scan(lens_dev, cu2, tot, mx)
+    assert int(mx) == longest and int(tot) == rows and torch.equal(cu2, cu)
+    out = torch.full((rows + 16, D), 3.0, device=DEV, dtype=torch.bfloat16)
+    ops.attention(qkv, out, B, H, dh, cu_seqlens=cu, max_seq_len=199, key_mult=km, extra_kv=ekv, extra_mult=em,
+                  route_rows=tot, route_min_rows=10 ** 9, route_max_rows=mx)
+    assert ops.device_flag() == 0
+    ref = ref_attention(qkv[:rows], B, H, dh, lens, km[:rows], ekv, em)
+    assert rel_err(out[:rows], ref) < TOL_BF16 and bool((out[rows:] == 3.0).all())
+    alone = torch.zeros_like(out)
+    if expect_quad:
+        ops.attention(qkv, alone, B, H, dh, cu_seqlens=cu, max_seq_len=127, key_mult=km, extra_kv=ekv, extra_mult=em, impl=4)
+    else:
+        ops.attention(qkv, alone, B, H, dh, cu_seqlens=cu, max_seq_len=199, key_mult=km, extra_kv=ekv, extra_mult=em, impl=1)
+    assert torch.equal(out[:rows], alone[:rows])

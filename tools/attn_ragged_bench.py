@@ -64,6 +64,13 @@ def case(name, lens, H, mult, extra, res):
             entry[label] = {"us": us, "tflops": flops / us / 1e6}
         except Exception as e:      # noqa: BLE001
             entry[label] = {"error": str(e)[:200]}
+    if not uniform and max(lens) + (1 if extra else 0) <= 128:
+        kw4 = dict(kw, max_seq_len=max(lens))
+        try:
+            us = timed(lambda: ops.attention(qkv, out, B, H, dh, impl=4, **kw4))
+            entry["tcgen05_quad"] = {"us": us, "tflops": flops / us / 1e6}
+        except Exception as e:      # noqa: BLE001
+            entry["tcgen05_quad"] = {"error": str(e)[:200]}
     entry["device_flag"] = ops.device_flag()
     res[name] = entry
     print(name, json.dumps(entry), flush=True)
@@ -84,6 +91,8 @@ def main():
     case("avit_s_layer", (torch.randint(30, 198, (512,), generator=g)).tolist(), 6, False, True, res)
     for n in (99, 80, 50, 33, 26, 14):
         case(f"rankvit_b_uniform_{n}", [n] * 512, 12, False, False, res)
+    for n in (50, 26):
+        case(f"ragged_layout_uniform_{n}", [n] * 511 + [n - 1], 12, False, False, res)
     case("vit_b_uniform_197", [197] * 512, 12, False, False, res)
     case("vit_s_uniform_198", [198] * 512, 6, False, False, res)
     if args.json:
