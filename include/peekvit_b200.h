@@ -175,11 +175,10 @@ typedef struct pk_attention_args {
   int qkv_format, out_format;
   /* Device-side choice between the two ragged kernels (both are launched, the one not chosen exits at once): with
    * route_rows set, the ragged tcgen05 kernel runs when *route_rows >= route_min_rows (long samples), the general mma.sync
-   * kernel otherwise (the two-region TMEM pipeline does not pay off below ~130 rows per sample: profiles/r02). */
+   * kernel otherwise (the two-region TMEM pipeline does not pay off below ~130 rows per sample: profiles/r02).  Independent
+   * of that, ragged head_dim-64 calls split PER SAMPLE: the quad-region tcgen05 kernel takes the samples of at most 128 keys
+   * (four in flight per SM), the kernel chosen above only the longer ones. */
   const int* route_rows; int route_min_rows;
-  /* ... and, first, the quad-region tcgen05 kernel (four samples in flight per SM, at most 128 keys per sample) when
-   * *route_max_rows (+ 1 with a virtual key) <= 128: the longest sample of the batch, written by pk_exclusive_scan_i32. */
-  const int* route_max_rows;
   int total_rows;           /* rows of the qkv / out buffers (the ragged tcgen05 kernel's 2-D tensor maps need the extent: a
                                key tile that starts near the end of the buffer is zero-filled past it); 0 = unknown (the ragged
                                kernel is then not used).  Rows of `qkv` past the live ones must hold finite values. */
@@ -218,8 +217,7 @@ int pk_gather_rows(const float* x, float* y, const int* kept, int batch, int seq
 
 /* ---- ragged-batch plumbing shared by the sparse models -------------------------------- */
 /* cu_out[0..n] = exclusive prefix sum of lens[0..n) (cu_out[n] = total, also written to *total_out). */
-/* (max_out, optional: the largest of the n lengths -- the longest sample, for pk_attention_args.route_max_rows) */
-int pk_exclusive_scan_i32(const int* lens, int n, int* cu_out, int* total_out, int* max_out, void* stream);
+int pk_exclusive_scan_i32(const int* lens, int n, int* cu_out, int* total_out, void* stream);
 
 /* Gather the kept rows of every sample into a new packed buffer:
  * x_out[cu_out[b] + dst_local[r]] = scale_in[r] * x_in[r] for rows with dst_local[r] >= 0, carrying up to three

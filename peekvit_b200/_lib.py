@@ -48,7 +48,7 @@ class AttentionArgs(C.Structure):
         ("seq_len", c_int), ("cu_seqlens", c_void_p), ("max_seq_len", c_int),
         ("scale", c_float),
         ("key_mult", c_void_p), ("extra_kv", c_void_p), ("extra_mult", c_void_p),
-        ("impl", c_int), ("qkv_format", c_int), ("out_format", c_int), ("route_rows", c_void_p), ("route_min_rows", c_int), ("route_max_rows", c_void_p),
+        ("impl", c_int), ("qkv_format", c_int), ("out_format", c_int), ("route_rows", c_void_p), ("route_min_rows", c_int),
         ("total_rows", c_int),
     ]
 
@@ -113,7 +113,7 @@ SIGNATURES: Dict[str, tuple] = {
     "pk_token_norm_score": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pk_topk_select": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pk_gather_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "pk_exclusive_scan_i32": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pk_exclusive_scan_i32": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "pk_compact_rows": (c_int, [C.POINTER(CompactArgs), c_void_p]),
     "pk_budget_mean_threshold": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pk_residual_gate_plan": (c_int, [C.POINTER(ResidualGateArgs), c_void_p]),

@@ -70,8 +70,7 @@ struct AttParams {
   const float* extra_mult;
   const int* route_rows;   // device-side routing: run only when *route_rows < route_min_rows (the tcgen05 kernel takes the rest)
   int route_min_rows;
-  const int* route_max_rows;   // ... and not when the longest sample has <= route_quad_keys rows (the quad-region kernel's batch)
-  int route_quad_keys;
+  int skip_max_keys;       // samples of at most this many keys belong to the quad-region tcgen05 launch of the same call (0: none)
 };
 
 // OCC = resident CTAs per SM the register allocation is capped for.  3 for uniform long sequences (steady-state tiles, no
@@ -91,7 +90,6 @@ attention_fwd_kernel(const AttParams p) {
   __shared__ __align__(128) uint8_t s_v[2][TILE_BYTES];
   __shared__ float s_bias[2][kAttBKV];
 
-  if (p.route_max_rows && *p.route_max_rows <= p.route_quad_keys) return;     // the quad-region tcgen05 kernel's launch takes this batch
   if (p.route_rows && *p.route_rows >= p.route_min_rows) return;     // the ragged tcgen05 kernel's launch takes this batch
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -105,6 +103,7 @@ attention_fwd_kernel(const AttParams p) {
   if (p.extra_kv && p.extra_mult) extra_m = p.extra_mult[b];
   const bool has_extra = extra_m > 0.f;
   const int n_keys = len + (has_extra ? 1 : 0);
+  if (n_keys <= p.skip_max_keys) return;             // a short sample: the quad-region tcgen05 launch of this call takes it
   const int n_tiles = (n_keys + kAttBKV - 1) / kAttBKV;
   constexpr float kLog2e = 1.4426950408889634f;
 
@@ -326,6 +325,7 @@ int launch_attention_tc(const pk_attention_args* a, cudaStream_t stream);
 bool attention_tcr_eligible(const pk_attention_args* a);
 int launch_attention_tcr(const pk_attention_args* a, cudaStream_t stream);
 bool attention_tcq_eligible(const pk_attention_args* a);
+bool attention_split_active(const pk_attention_args* a);
 int launch_attention_tcq(const pk_attention_args* a, cudaStream_t stream);
 int attention_trace_copy(unsigned long long* host_dst);
 
@@ -340,14 +340,14 @@ extern "C" int pk_attention_fwd(const pk_attention_args* a, void* stream) {
   PK_REQUIRE((a->extra_kv == nullptr) == (a->extra_mult == nullptr), "pk_attention_fwd: extra_kv and extra_mult go together");
   if (a->batch == 0 || a->max_seq_len == 0) return PK_OK;
   if (attention_tc_eligible(a)) return launch_attention_tc(a, static_cast<cudaStream_t>(stream));
-  // Quad-region tcgen05 kernel (every sample <= 128 keys): alone when the host knows it (static max_seq_len, or impl 4),
-  // otherwise launched next to the other kernels with the device-side longest-sample count deciding.
-  const bool quad = attention_tcq_eligible(a);
-  const bool quad_known = quad && a->max_seq_len + (a->extra_kv ? 1 : 0) <= 128;
-  PK_REQUIRE(a->impl != 4 || quad_known, "pk_attention_fwd: the quad-region tcgen05 kernel needs cu_seqlens, head_dim 64 and at most 128 keys per sample");
+  // Quad-region tcgen05 kernel: alone when the static bound says every sample has at most 128 keys (or with impl 4); with the
+  // per-sample split it takes the short samples of a mixed batch and the kernels below, which skip those, the longer ones.
+  const bool quad_only = attention_tcq_eligible(a) && a->max_seq_len + (a->extra_kv ? 1 : 0) <= 128;
+  PK_REQUIRE(a->impl != 4 || quad_only, "pk_attention_fwd: the quad-region tcgen05 kernel needs cu_seqlens, head_dim 64 and at most 128 keys per sample");
+  const bool quad = quad_only || attention_split_active(a);      // the split itself is opt-in (PK_ATT_SPLIT=1, see pk_attention_tc.cu)
   if (quad) {
     const int rc = launch_attention_tcq(a, static_cast<cudaStream_t>(stream));
-    if (rc != PK_OK || quad_known) return rc;
+    if (rc != PK_OK || quad_only) return rc;
   }
   const bool routed = a->route_rows != nullptr && a->impl == 0 && attention_tcr_eligible(a);
   if (routed) {
@@ -372,8 +372,7 @@ extern "C" int pk_attention_fwd(const pk_attention_args* a, void* stream) {
   p.extra_mult = a->extra_mult;
   p.route_rows = routed ? a->route_rows : nullptr;
   p.route_min_rows = a->route_min_rows;
-  p.route_max_rows = (quad && !quad_known) ? a->route_max_rows : nullptr;
-  p.route_quad_keys = 128 - (a->extra_kv ? 1 : 0);
+  p.skip_max_keys = quad ? 128 : 0;
   const int max_len = a->cu_seqlens ? a->max_seq_len : a->seq_len;
   dim3 grid((max_len + kAttBQ - 1) / kAttBQ, a->num_heads, a->batch);
   PK_REQUIRE(a->batch <= 65535 && a->num_heads <= 65535, "pk_attention_fwd: batch/heads exceed grid limits; split the batch");

@@ -972,7 +972,7 @@ struct TcrParams {
   unsigned long long* trace;   // PK_ATT_TRACE=1: CTA 0 records clock64 at pipeline events of its first 16 units (tools/attn_trace_tcr.py)
   const int* route_rows;       // device-side routing: run only when *route_rows >= route_min_rows
   int route_min_rows;
-  const int* route_max_rows;   // device-side routing: longest sample of the batch; <= 128 keys -> the quad-region kernel runs
+  int min_keys, max_keys;      // unit filter: samples whose key count (rows + virtual key) lies outside are another launch's
 };
 
 // trace slot layout: [unit(0..15)][slot(0..15)][event(0..7)]; slots: warps 0-3 as they are, softmax warps 4 / 8 / 12 / 16 -> 4..7
@@ -1008,7 +1008,9 @@ __device__ __forceinline__ bool tcr_unit(const TcrParams& p, int u, TcrUnit& t) 
   if (!(t.extra > 0.f)) t.extra = 0.f;
   t.n_keys = t.len + (t.extra > 0.f ? 1 : 0);
   t.npad = (t.n_keys + 15) & ~15;
-  return true;
+  // per-sample split between the ragged kernels of one attention call: the quad-region kernel takes the samples of at most
+  // 128 keys, the two-region / general kernel the longer ones; every role of a kernel skips the others' units alike
+  return t.n_keys >= p.min_keys && t.n_keys <= p.max_keys;
 }
 
 // The groups of a unit that hold special keys (multiplicity != 1, the virtual key, padding): x = s * scale + lm[j] with the
@@ -1055,7 +1057,6 @@ __global__ void __launch_bounds__(kTcrThreads, 1)
 attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv_small,
                      const __grid_constant__ CUtensorMap tmap_kv_full, const __grid_constant__ CUtensorMap tmap_out, const TcrParams p) {
   if (p.route_rows && *p.route_rows < p.route_min_rows) return;      // short samples: the general kernel's launch takes this batch
-  if (p.route_max_rows && *p.route_max_rows + (p.extra_kv ? 1 : 0) <= 128) return;      // ... or the quad-region kernel's
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using SM = TcrSmem<NMAX>;
@@ -1427,7 +1428,7 @@ attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 }
 
 // ======================================================================================================================
-// Quad-region variant ("tcq") for batches whose samples all have at most 128 keys (ResidualViT at budgets <= ~0.5, the late
+// Quad-region variant ("tcq") for the samples of at most 128 keys (most of a ResidualViT batch at budgets <= ~0.5, the late
 // A-ViT layers): the ragged kernel above keeps two units in flight per SM, and its per-unit chain (S ready -> row max -> exp
 // -> P.V -> O read-out -> next Q.K^T, ~10 000 cycles) is the same whether a sample has 80 rows or 200 -- short samples cannot
 // amortise it.  With at most 128 keys a TMEM region needs only 128 columns (S at [0, npad), bf16 P packed over the consumed
@@ -1435,8 +1436,8 @@ attention_tcr_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 // k & 3.  One MMA-issuing warp per region (on four different schedulers), one softmax + output warp per TMEM lane quarter and region
 // (no column split, hence no partial maxima to exchange) -- the issuing warp also writes its region's bias row and virtual
 // key rows; every softmax warp also reads its rows of O out, scales them and stores them (staged in the region's V slot).
-// Units = one (sample, head); q_tiles == 1.  Launched next to the other two ragged kernels; *route_max_rows decides on the
-// device which one runs (pk_attention_args.route_max_rows).
+// Units = one (sample, head); q_tiles == 1.  Samples with more than 128 keys are skipped (TcrParams.max_keys) and taken by the
+// two-region / general kernel launched next to this one, which in turn skip the short ones: a per-sample split on the device.
 constexpr int kTcqThreads = 768;                   // warps: 0 Q/K TMA, 1-4 MMA + patch (region 0-3), 6 V TMA, 5 / 7 idle, 8-23 softmax + output
 constexpr int kTcqNMax = 128;
 constexpr int kTcqRegionCols = 128;
@@ -1466,14 +1467,9 @@ __device__ __forceinline__ void tcq_trace(const TcrParams& p, int k, int ev) {
   }
 #endif
 }
-__device__ __forceinline__ bool tcq_selected(const TcrParams& p) {
-  return p.route_max_rows && *p.route_max_rows + (p.extra_kv ? 1 : 0) <= kTcqNMax;
-}
-
 __global__ void __launch_bounds__(kTcqThreads, 1)
 attention_tcq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv_small,
                      const __grid_constant__ CUtensorMap tmap_kv_full, const __grid_constant__ CUtensorMap tmap_out, const TcrParams p) {
-  if (p.route_max_rows && !tcq_selected(p)) return;          // a sample with more than 128 keys: the other launches take the batch
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using SM = TcqSmem;
@@ -1985,6 +1981,7 @@ bool attention_tcr_eligible(const pk_attention_args* a) {
 }
 
 bool attention_tcq_eligible(const pk_attention_args* a);
+bool attention_split_active(const pk_attention_args* a);
 
 template <int NMAX>
 static int launch_tcr(const pk_attention_args* a, cudaStream_t stream, int max_len) {
@@ -2017,7 +2014,8 @@ static int launch_tcr(const pk_attention_args* a, cudaStream_t stream, int max_l
   p.trace = tc_trace_buffer();
   p.route_rows = (a->impl == 0) ? a->route_rows : nullptr;
   p.route_min_rows = a->route_min_rows;
-  p.route_max_rows = (a->impl == 0 && attention_tcq_eligible(a)) ? a->route_max_rows : nullptr;
+  p.min_keys = attention_split_active(a) ? kTcqNMax + 1 : 0;      // the quad-region launch takes the short samples
+  p.max_keys = 1 << 30;
   const long long units = static_cast<long long>(a->batch) * a->num_heads * p.q_tiles;
   int grid = num_sms();
   if (units < grid) grid = static_cast<int>(units);
@@ -2031,22 +2029,31 @@ static int launch_tcr(const pk_attention_args* a, cudaStream_t stream, int max_l
 }
 
 // ---------------------------------------------------------------------------------------------------- quad-region kernel launch
-// Eligible: what the ragged kernel takes, for batches whose samples have at most 128 keys -- known on the host (max_seq_len) or
-// decided on the device (route_max_rows).  PK_ATT_TCQ=0 switches it off (A/B runs).
-static int tcq_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("PK_ATT_TCQ"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v;
+// Eligible: what the ragged kernel takes; it computes the samples of at most 128 keys and skips the others (the caller launches
+// the two-region / general kernel for those unless max_seq_len says there are none).  PK_ATT_TCQ=0 switches it off (A/B runs).
+static int tcq_enabled() {                       // read per call (a test compares both dispatches in one process)
+  const char* e = getenv("PK_ATT_TCQ");
+  return (e && e[0] == '0') ? 0 : 1;
 }
+// Per-sample split of one ragged call (quad-region kernel for the samples of <= 128 keys, the two-region / general kernel for
+// the longer ones): correct and tested, but OFF unless PK_ATT_SPLIT=1.  It pays when a batch mixes mid-length (40 - 125 rows)
+// and long samples; on the batches the calibrated ResidualViT-S / A-ViT-S models realise (bimodal: most samples keep either
+// ~3 rows or all 199) the short samples are launch-bound on either kernel and the second launch only adds its fill and drain
+// (profiles/r02/run39_attn_model_lens.txt: 125 vs 104 us, 58 vs 46 us per layer).  Read per call, so a test can toggle it.
+bool attention_split_active(const pk_attention_args* a) {
+  if (a->impl != 0 || !attention_tcq_eligible(a)) return false;
+  if (a->max_seq_len + (a->extra_kv ? 1 : 0) <= kTcqNMax) return false;      // every sample fits: the quad-region kernel alone
+  const char* e = getenv("PK_ATT_SPLIT");
+  return e && e[0] == '1';
+}
+
 bool attention_tcq_eligible(const pk_attention_args* a) {
   if (!tcq_enabled() || !(a->impl == 0 || a->impl == 4)) return false;
   if (a->head_dim != kTcDH || a->qkv_format != PK_OUT_BF16 || a->out_format != PK_OUT_BF16) return false;
   if (!a->cu_seqlens) return false;                                        // packed ragged rows only
   if ((reinterpret_cast<uintptr_t>(a->qkv) & 15) != 0 || (reinterpret_cast<uintptr_t>(a->out) & 15) != 0) return false;
   if (a->extra_kv && (reinterpret_cast<uintptr_t>(a->extra_kv) & 15) != 0) return false;
-  if (a->total_rows <= 0) return false;
-  const bool host_knows = a->max_seq_len + (a->extra_kv ? 1 : 0) <= kTcqNMax;
-  return host_knows || (a->impl == 0 && a->route_max_rows != nullptr);
+  return a->total_rows > 0;
 }
 
 int launch_attention_tcq(const pk_attention_args* a, cudaStream_t stream) {
@@ -2078,8 +2085,8 @@ int launch_attention_tcq(const pk_attention_args* a, cudaStream_t stream) {
   p.trace = tc_trace_buffer();
   p.route_rows = nullptr;
   p.route_min_rows = 0;
-  // the device-side choice applies unless the host already knows that every sample fits
-  p.route_max_rows = (a->max_seq_len + (a->extra_kv ? 1 : 0) <= kTcqNMax) ? nullptr : a->route_max_rows;
+  p.min_keys = 0;
+  p.max_keys = kTcqNMax;                              // longer samples are skipped: another launch of the same call takes them
   const long long units = static_cast<long long>(a->batch) * a->num_heads;
   int grid = num_sms();
   if (units < grid) grid = static_cast<int>(units);

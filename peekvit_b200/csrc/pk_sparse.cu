@@ -213,20 +213,15 @@ residual_gate_plan_kernel(const ResidualGateParams p) {
 
 // ------------------------------------------------------------------ exclusive scan of per-sample lengths
 __global__ void __launch_bounds__(1024)
-exclusive_scan_kernel(const int* __restrict__ len, int n, int* __restrict__ cu_out, int* __restrict__ total_out,
-                      int* __restrict__ max_out) {
+exclusive_scan_kernel(const int* __restrict__ len, int n, int* __restrict__ cu_out, int* __restrict__ total_out) {
   __shared__ int s_warp[32];
-  __shared__ int s_carry, s_max;
-  if (threadIdx.x == 0) { s_carry = 0; s_max = 0; }
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
   const int lane = lane_id(), warp = warp_id();
   for (int base = 0; base < n; base += 1024) {
     const int i = base + threadIdx.x;
     const int v = i < n ? len[i] : 0;
-    if (max_out) {                                  // longest sample (device-side routing of the ragged attention kernels)
-      const int wm = __reduce_max_sync(0xffffffffu, v);
-      if (lane == 0 && wm > 0) atomicMax(&s_max, wm);
-    }
     int incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -255,7 +250,6 @@ exclusive_scan_kernel(const int* __restrict__ len, int n, int* __restrict__ cu_o
   if (threadIdx.x == 0) {
     cu_out[n] = s_carry;
     if (total_out) total_out[0] = s_carry;
-    if (max_out) max_out[0] = s_max;
   }
 }
 
@@ -691,9 +685,9 @@ extern "C" int pk_residual_gate_plan(const pk_residual_gate_args* a, void* strea
   return check_cuda(cudaGetLastError(), "residual_gate_plan_kernel");
 }
 
-extern "C" int pk_exclusive_scan_i32(const int* lens, int n, int* cu_out, int* total_out, int* max_out, void* stream) {
+extern "C" int pk_exclusive_scan_i32(const int* lens, int n, int* cu_out, int* total_out, void* stream) {
   PK_REQUIRE(lens && cu_out && n >= 0, "pk_exclusive_scan_i32: bad arguments");
-  exclusive_scan_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(lens, n, cu_out, total_out, max_out);
+  exclusive_scan_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(lens, n, cu_out, total_out);
   return check_cuda(cudaGetLastError(), "exclusive_scan_kernel");
 }
 

@@ -470,7 +470,7 @@ class Forward:
         return x if emit_fold is None else (x, None)
 
     def attn_part(self, x, lw: LayerWeights, rows: int, batch: int, *, seq: int = 0, cu=None, max_len: int = 0, rows_dev=None,
-                  rowscale=None, key_mult=None, extra_mult=None, max_rows_dev=None) -> None:
+                  rowscale=None, key_mult=None, extra_mult=None) -> None:
         """x += rowscale * out_proj(attention(in_proj(rowscale * LN1(x))))  (vit.py:48-51; residualvit.py:252-256)."""
         if self.exact:
             return self._attn_part_exact(x, lw, rows, batch, seq, cu, max_len, rows_dev, rowscale, key_mult, extra_mult)
@@ -481,13 +481,13 @@ class Forward:
                           rows_dev=rows_dev)
         # zeroed once: the ragged tcgen05 attention loads fixed-size key tiles, i.e. also rows past the live ones (masked)
         qkv = ops.gemm(a, aw.w_qkv, aw.b_qkv, ws.get("qkv", (rows, 3 * D), torch.bfloat16, zero=True), PK_EPI_BIAS_BF16, m_dev=rows_dev)
-        # ragged batches: the tcgen05 kernel when the live rows average ATT_TCR_MIN_MEAN_ROWS per sample or more, the general
-        # mma.sync kernel below that -- decided on the device from the live row count (both launches are in the graph)
+        # ragged batches: the quad-region tcgen05 kernel takes the samples of <= 128 keys; the longer ones go to the two-region
+        # tcgen05 kernel when the live rows average ATT_TCR_MIN_MEAN_ROWS per sample or more, to the general mma.sync kernel
+        # below that -- all decided on the device from cu_seqlens / the live row count (every launch is in the graph)
         att = ops.attention(qkv, ws.get("att", (rows, D), torch.bfloat16), batch, pm.heads, D // pm.heads, seq_len=seq,
                             cu_seqlens=cu, max_seq_len=max_len, key_mult=key_mult,
                             extra_kv=aw.bias_kv if extra_mult is not None else None, extra_mult=extra_mult,
-                            route_rows=rows_dev if cu is not None else None, route_min_rows=batch * ATT_TCR_MIN_MEAN_ROWS,
-                            route_max_rows=max_rows_dev if cu is not None else None)
+                            route_rows=rows_dev if cu is not None else None, route_min_rows=batch * ATT_TCR_MIN_MEAN_ROWS)
         ops.gemm(att, aw.w_o, aw.b_o, x[:rows], PK_EPI_BIAS_RESID_F32, resid=x[:rows], rowscale=rowscale, m_dev=rows_dev)
 
     def mlp_part(self, x, lw: LayerWeights, rows: int, *, rows_dev=None, rowscale=None, residual: bool = True) -> None:
@@ -798,8 +798,6 @@ class Forward:
         mults = [ws.get("res_mult0", (rows_cap,), torch.float32), ws.get("res_mult1", (rows_cap,), torch.float32)]
         cus = [ws.get("res_cu0", (B + 1,), torch.int32), ws.get("res_cu1", (B + 1,), torch.int32)]
         rdevs = [ws.get("res_rows0", (1,), torch.int32), ws.get("res_rows1", (1,), torch.int32)]
-        mdevs = [ws.get("res_maxrows0", (1,), torch.int32), ws.get("res_maxrows1", (1,), torch.int32)]     # longest sample
-        max_rows_dev = None
         mask = ws.get("res_mask", (rows_cap,), torch.float32)
         rowscale = ws.get("res_rowscale", (rows_cap,), torch.float32)
         dst_local = ws.get("res_dst", (rows_cap,), torch.int32)
@@ -829,9 +827,9 @@ class Forward:
                                        gate_type=0 if g["gate_type"] == "sigmoid" else 1, thr_mode=thr_mode, bt_w=g.get("bt_gate_w"),
                                        bt_b=g.get("bt_gate_b", 0.0), thr_dev=thr_dev,
                                        mask=mask, dst_local=dst_local, sample_of=sample_of, new_len=new_len, mdrop=mdrop)
-                cu_out, rows_out, y, mult_out, max_rows_dev = cus[flip], rdevs[flip], bufs[flip], mults[flip], mdevs[flip]
+                cu_out, rows_out, y, mult_out = cus[flip], rdevs[flip], bufs[flip], mults[flip]
                 flip ^= 1
-                ops.exclusive_scan(new_len, cu_out, rows_out, max_rows_dev)
+                ops.exclusive_scan(new_len, cu_out, rows_out)
                 # block.mask (B, N_img, 1) is published by the same launch (the token -> row map moves to the compacted layout)
                 mask_pub = torch.empty(B, n_img, 1, device=dev, dtype=torch.float32) if aux is not None else None
                 ops.compact_rows(x, y, cu, cu_out, B, rows_cap, dst_local, sample_of, scale_in=mask, scale_out=rowscale,
@@ -842,12 +840,11 @@ class Forward:
                     aux.setdefault("rows", {})[i] = rows_out.clone()
                 x, cu, rows_dev, mult, have_mult = y, cu_out, rows_out, mult_out, True
                 self.attn_part(x, lw, rows_cap, B, cu=cu, max_len=cap, rows_dev=rows_dev, rowscale=rowscale, key_mult=mult,
-                               extra_mult=mdrop, max_rows_dev=max_rows_dev)
+                               extra_mult=mdrop)
                 self.mlp_part(x, lw, rows_cap, rows_dev=rows_dev, rowscale=rowscale)
                 ops.residual_ghost(x, mult, cu, mdrop, g["mlp0"], B)
             elif skip in (None, "none"):
-                self.attn_part(x, lw, rows_cap, B, cu=cu, max_len=cap, rows_dev=rows_dev, key_mult=mult if have_mult else None,
-                               max_rows_dev=max_rows_dev)
+                self.attn_part(x, lw, rows_cap, B, cu=cu, max_len=cap, rows_dev=rows_dev, key_mult=mult if have_mult else None)
                 self.mlp_part(x, lw, rows_cap, rows_dev=rows_dev)
             else:
                 raise NotImplementedError(f"skip mode {skip!r}")
@@ -1004,8 +1001,6 @@ class Forward:
         toks = [ws.get("avit_tok0", (rows_cap,), torch.float32), ws.get("avit_tok1", (rows_cap,), torch.float32)]
         cus = [ws.get("avit_cu0", (B + 1,), torch.int32), ws.get("avit_cu1", (B + 1,), torch.int32)]
         rdevs = [ws.get("avit_rows0", (1,), torch.int32), ws.get("avit_rows1", (1,), torch.int32)]
-        mdevs = [ws.get("avit_maxrows0", (1,), torch.int32), ws.get("avit_maxrows1", (1,), torch.int32)]   # longest sample
-        max_rows_dev = None
         cs[0].zero_()
         Rs[0].fill_(1.0)
         toks[0].copy_(tokid0)
@@ -1025,8 +1020,7 @@ class Forward:
                 # uniform-sequence kernel (135 us per 512 x 12 heads x 197 tokens; the ragged kernels 245 / 395 us)
                 self.attn_part(xs[cur], lw, rows_cap, B, seq=seq)
             else:
-                self.attn_part(xs[cur], lw, rows_cap, B, cu=cu, max_len=seq, rows_dev=rows_dev, extra_mult=n_halted,
-                               max_rows_dev=max_rows_dev)
+                self.attn_part(xs[cur], lw, rows_cap, B, cu=cu, max_len=seq, rows_dev=rows_dev, extra_mult=n_halted)
             self.mlp_part(xs[cur], lw, rows_cap, rows_dev=rows_dev)
             if aux is not None:
                 aux.setdefault("rows", []).append(rows_dev.clone())
@@ -1038,8 +1032,7 @@ class Forward:
             if i == L - 1:
                 break
             nxt = cur ^ 1
-            ops.exclusive_scan(new_len, cus[nxt], rdevs[nxt], mdevs[nxt])
-            max_rows_dev = mdevs[nxt]
+            ops.exclusive_scan(new_len, cus[nxt], rdevs[nxt])
             ops.compact_rows(xs[cur], xs[nxt], cu, cus[nxt], B, rows_cap, dst_local, sample_of,
                              attrs=[(cs[cur], cs[nxt]), (Rs[cur], Rs[nxt]), (toks[cur], toks[nxt])])
             cu, rows_dev, cur = cus[nxt], rdevs[nxt], nxt

@@ -183,8 +183,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 def attention(qkv: torch.Tensor, out: torch.Tensor, batch: int, num_heads: int, head_dim: int, *, seq_len: int = 0,
               cu_seqlens: Optional[torch.Tensor] = None, max_seq_len: int = 0, key_mult: Optional[torch.Tensor] = None,
               extra_kv: Optional[torch.Tensor] = None, extra_mult: Optional[torch.Tensor] = None, impl: int = 0,
-              half_split: bool = False, route_rows: Optional[torch.Tensor] = None, route_min_rows: int = 0,
-              route_max_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+              half_split: bool = False, route_rows: Optional[torch.Tensor] = None, route_min_rows: int = 0) -> torch.Tensor:
     """``half_split`` (bf16x2 mode, tcgen05 kernel): qkv is IEEE half, out is bf16 [rows, 2*D] = the result split [lo | hi]."""
     lib = _lib_for(qkv)
     D = num_heads * head_dim
@@ -204,7 +203,6 @@ def attention(qkv: torch.Tensor, out: torch.Tensor, batch: int, num_heads: int, 
     a.impl = impl
     a.total_rows = qkv.shape[0]
     a.route_rows, a.route_min_rows = _ptr(route_rows, torch.int32), int(route_min_rows)
-    a.route_max_rows = _ptr(route_max_rows, torch.int32)
     check(lib.pk_attention_fwd(C.byref(a), _stream()), "pk_attention_fwd")
     return out
 
@@ -279,12 +277,11 @@ def gather_rows(x: torch.Tensor, kept: torch.Tensor, batch: int, seq_len: int, o
     return out
 
 
-def exclusive_scan(lens: torch.Tensor, cu_out: torch.Tensor, total_out: Optional[torch.Tensor] = None,
-                   max_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def exclusive_scan(lens: torch.Tensor, cu_out: torch.Tensor, total_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib_for(lens)
     n = lens.numel()
-    check(lib.pk_exclusive_scan_i32(_ptr(lens, torch.int32), n, _ptr(cu_out, torch.int32), _ptr(total_out, torch.int32),
-                                    _ptr(max_out, torch.int32), _stream()), "pk_exclusive_scan_i32")
+    check(lib.pk_exclusive_scan_i32(_ptr(lens, torch.int32), n, _ptr(cu_out, torch.int32), _ptr(total_out, torch.int32), _stream()),
+          "pk_exclusive_scan_i32")
     return cu_out
 
 

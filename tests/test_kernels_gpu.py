@@ -754,28 +754,40 @@ def test_attention_quad_region_tcgen05_against_reference(ops, lens, with_mult, w
     assert bool((out[rows:] == 3.0).all())
 
 
-@pytest.mark.parametrize("longest,expect_quad", [(100, True), (127, True), (128, False), (190, False)])
-def test_attention_three_way_device_side_routing(ops, longest, expect_quad):
-    """route_max_rows: the longest sample (written by pk_exclusive_scan_i32) decides on the device whether the quad-region
-    kernel runs (<= 128 keys incl. the virtual key) or one of the other two; whichever runs, the result is the reference's and
-    bit-identical to that kernel launched alone."""
-    lens = [longest, 33, 77, 5, 64]
+@pytest.mark.parametrize("lens", [[100, 33, 77, 5, 64], [190, 33, 127, 128, 0, 129, 64], [197, 150, 129, 199], [128, 127, 1, 140, 90, 16]])
+@pytest.mark.parametrize("tcr_long", [False, True])
+def test_attention_per_sample_split_between_ragged_kernels(ops, lens, tcr_long, monkeypatch):
+    """PK_ATT_SPLIT=1 (opt-in, read per call): one ragged call, split per sample on the device: the quad-region tcgen05 kernel takes the samples of at most 128 keys
+    (rows + the virtual key), the two-region tcgen05 kernel (tcr_long) or the general mma.sync kernel the longer ones; each
+    sample's rows are bit-identical to the kernel that owns it launched alone, and the whole is the reference's."""
+    monkeypatch.setenv("PK_ATT_SPLIT", "1")
     B, H, dh = len(lens), 6, 64
     D = H * dh
     qkv, cu, km, ekv, em, rows = _ragged_case(lens, H, 9, True, True, pad_rows=16)
-    lens_dev = torch.tensor(lens, device=DEV, dtype=torch.int32)
-    cu2, tot, mx = torch.empty(B + 1, device=DEV, dtype=torch.int32), torch.empty(1, device=DEV, dtype=torch.int32), torch.empty(1, device=DEV, dtype=torch.int32)
-    ops.exclusive_scan(lens_dev, cu2, tot, mx)
-    assert int(mx) == longest and int(tot) == rows and torch.equal(cu2, cu)
+    tot = torch.tensor([rows], device=DEV, dtype=torch.int32)
     out = torch.full((rows + 16, D), 3.0, device=DEV, dtype=torch.bfloat16)
     ops.attention(qkv, out, B, H, dh, cu_seqlens=cu, max_seq_len=199, key_mult=km, extra_kv=ekv, extra_mult=em,
-                  route_rows=tot, route_min_rows=10 ** 9, route_max_rows=mx)
+                  route_rows=tot, route_min_rows=0 if tcr_long else 10 ** 9)
     assert ops.device_flag() == 0
     ref = ref_attention(qkv[:rows], B, H, dh, lens, km[:rows], ekv, em)
     assert rel_err(out[:rows], ref) < TOL_BF16 and bool((out[rows:] == 3.0).all())
     alone = torch.zeros_like(out)
-    if expect_quad:
-        ops.attention(qkv, alone, B, H, dh, cu_seqlens=cu, max_seq_len=127, key_mult=km, extra_kv=ekv, extra_mult=em, impl=4)
-    else:
-        ops.attention(qkv, alone, B, H, dh, cu_seqlens=cu, max_seq_len=199, key_mult=km, extra_kv=ekv, extra_mult=em, impl=1)
-    assert torch.equal(out[:rows], alone[:rows])
+    ops.attention(qkv, alone, B, H, dh, cu_seqlens=cu, max_seq_len=199, key_mult=km, extra_kv=ekv, extra_mult=em,
+                  impl=3 if tcr_long else 1)
+    keys = [n + (1 if e > 0 else 0) for n, e in zip(lens, em.tolist())]      # extra_mult <= 0: no virtual key for that sample
+    start = 0
+    for n, k in zip(lens, keys):
+        if k > 128:                          # a long sample: the other kernel's, exactly
+            assert torch.equal(out[start:start + n], alone[start:start + n])
+        start += n
+    short = [n if k <= 128 else 0 for n, k in zip(lens, keys)]
+    if any(short):                           # the short samples: exactly the quad-region kernel's rows
+        idx = torch.cat([torch.arange(s0, s0 + n) for s0, n in zip(cu.tolist(), short)]).to(DEV)
+        cu_s = torch.tensor([0] + list(torch.tensor(short).cumsum(0)), device=DEV, dtype=torch.int32)
+        qkv_s = torch.zeros(idx.numel() + 128, 3 * D, device=DEV, dtype=torch.bfloat16)
+        qkv_s[:idx.numel()] = qkv[idx]
+        km_s = torch.ones(idx.numel() + 128, device=DEV, dtype=torch.float32)
+        km_s[:idx.numel()] = km[idx]
+        out_s = torch.zeros(idx.numel() + 128, D, device=DEV, dtype=torch.bfloat16)
+        ops.attention(qkv_s, out_s, B, H, dh, cu_seqlens=cu_s, max_seq_len=127, key_mult=km_s, extra_kv=ekv, extra_mult=em, impl=4)
+        assert torch.equal(out[idx], out_s[:idx.numel()])

@@ -302,6 +302,56 @@ def test_residualvit_really_compacts_and_scales_with_budget():
         assert (blk.mask.cpu() - oaux["masks"][i]).abs().max().item() < 5e-3
 
 
+def test_short_sequence_models_run_on_the_quad_region_attention(monkeypatch):
+    """160-px images, patch 16: at most 103 rows per sample (+ the virtual key), so the static bound sends every ragged attention
+    call of ResidualViT and A-ViT to the quad-region tcgen05 kernel alone (head_dim 64).  Logits within the bf16 band of the
+    oracle, masks / halting counters as in the 224-px tests; PK_ATT_TCQ is not touched, i.e. this is the default dispatch."""
+    from oracle import peekvit_oracle as po, weights as ow
+    from peekvit_b200 import ops, runner
+    from peekvit_b200.models import AdaptiveVisionTransformer, ResidualVisionTransformer
+    base = dict(image_size=160, patch_size=16, num_layers=6, num_heads=4, hidden_dim=256, mlp_dim=512, num_classes=100)
+    images = ow.synthetic_images(9, 160, seed=77)
+    cfg = dict(base, gate_type="sigmoid", gate_temp=1.0, gate_bias=0.0, gate_threshold=0.5, add_budget_token="learnable",
+               residual_layers=["attention+mlp"] * 6)
+    sd = ow.calibrate_residual_gates(ow.make_state_dict("residualvit", cfg, seed=11), cfg, 0.5, images=ow.synthetic_images(2, 160, seed=5))
+    model = ResidualVisionTransformer(**cfg)
+    model.load_state_dict(sd)
+    model = model.to(DEV).eval()
+    model.set_budget(0.5)
+    aux = {}
+    logits = runner.run(model, images.to(DEV), aux).cpu()
+    ref, oaux = po.forward("residualvit", sd, cfg, images, 0.5)
+    err = ((logits - ref).abs().max() / ref.abs().max()).item()
+    rows = [int(r[0][0]) for _, r in sorted(aux["rows"].items())]
+    print(f"residualvit 160 px budget 0.5: rel err {err:.3e}; packed rows/layer {rows} (dense {9 * 102})")
+    assert ops.device_flag() == 0 and err < TOL_LOGITS
+    assert 0 < min(rows) and np.mean(rows) < 0.9 * 9 * 102
+    for i, blk in enumerate(model.encoder.layers):
+        assert (blk.mask.cpu() - oaux["masks"][i]).abs().max().item() < 5e-3
+    # A-ViT: halting is discontinuous (a counter that moves by one layer re-weighs that token's output), so the bf16 band of
+    # this family is the config-E test's 5e-2; the same model with the quad-region kernel switched off (general mma.sync
+    # kernel; a fresh module, i.e. a fresh captured graph) must land in the same band with the same counters
+    cfg = dict(base, eps=0.01, gate_scale=1.0, gate_center=1.5)
+    sd = ow.make_state_dict("adavit", cfg, seed=12)
+    ref, oaux = po.forward("adavit", sd, cfg, images)
+    got = {}
+    for tcq in ("1", "0"):
+        monkeypatch.setenv("PK_ATT_TCQ", tcq)
+        model = AdaptiveVisionTransformer(**cfg)
+        model.load_state_dict(sd)
+        model = model.to(DEV).eval()
+        logits = runner.run(model, images.to(DEV)).cpu()
+        err = ((logits - ref).abs().max() / ref.abs().max()).item()
+        cnt = model.encoder.counter_token.cpu()
+        agree = (cnt == oaux["counter_token"]).float().mean().item()
+        print(f"adavit 160 px (PK_ATT_TCQ={tcq}): rel err {err:.3e}; mean layers per token {float(cnt.mean()):.2f}; counter agreement {agree:.4f}")
+        assert ops.device_flag() == 0 and err < 5e-2 and agree > 0.98
+        assert float(cnt.mean()) < 5.9          # tokens really halt
+        got[tcq] = (logits, cnt)
+    assert (got["1"][1] == got["0"][1]).float().mean().item() > 0.99
+    assert ((got["1"][0] - got["0"][0]).abs().max() / ref.abs().max()).item() < 5e-2
+
+
 def test_vit_b16_top1_agreement_outside_the_tolerance_band():
     """North star: logits within 1e-2 relative and top-1 agreement >= 99.9 %.  With random-init weights the fp32 top-2
     margins are tiny (median 0.15 against max|logit| 2.7), so a few arg-max flips inside the bf16 error band are
