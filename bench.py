@@ -494,6 +494,38 @@ def run_variants(dev, rank, world, timer: Timer, sampler, images_full, steps_hin
         del m, ft, opt
     except Exception as e:      # noqa: BLE001  (a bench line must not die on the optional leg)
         out["F_finetune_vit_b_16_cls_head"] = {"error": str(e)[:300]}
+    # ---- the gate regime on the ResidualViT-S shape (config C kwargs): training-mode forward with one sampled budget per image,
+    # soft masks on all tokens, backward through the masks into the gate projections / budget-token gates / learnable budget
+    # token / class token / head; cross-entropy only (a mask regulariser is the caller's torch function)
+    try:
+        from peekvit_b200.finetune import FineTuner
+        cfg = dict(CFG_S, gate_type="sigmoid", gate_temp=1.0, gate_bias=0.0, gate_threshold=0.5, add_budget_token="learnable",
+                   add_input=False, residual_layers=["attention+mlp"] * 12)
+        m = make_model("residualvit", cfg, dev)
+        calibrate_residual_gates_(m, 0.5, images_full[:32], target=0.5)
+        m.train()
+        ft = FineTuner(m, micro_batch=256)
+        nb = 512
+        xb, yb = images_full[:nb], torch.randint(0, cfg["num_classes"], (nb,), device=dev)
+        opt = torch.optim.SGD([p for p in m.parameters() if p.requires_grad], lr=1e-3)
+
+        def gate_step():
+            opt.zero_grad()
+            ft.forward_backward(xb, yb)
+            opt.step()
+        for _ in range(2):
+            gate_step()
+        ms, t0, t1 = timer.run(gate_step, 3)
+        entry = {"value": world * nb * 3 / (ms * 1e-3), "unit": "images/sec", "images_per_gpu_per_step": nb, "steps": 3,
+                 "ms_per_step": ms / 3, "config": "f4", "trainable_tensors": len(ft.params),
+                 "regime": "gates + budget-token gates + learnable budget token + class token + head trainable, backbone frozen",
+                 "includes": "budget sampling, training-mode forward (all tokens, soft masks), cross-entropy, backward, gradient all-reduce, SGD step"}
+        if rank == 0 and sampler is not None:
+            entry["clocks"] = sampler.window(t0, t1)
+        out["F_finetune_residualvit_s_gates"] = entry
+        del m, ft, opt
+    except Exception as e:      # noqa: BLE001
+        out["F_finetune_residualvit_s_gates"] = {"error": str(e)[:300]}
     out["device_flag"] = ops.device_flag()
     torch.cuda.empty_cache()
     return out

@@ -367,6 +367,34 @@ int pk_head_bwd(const float* dlogits, const float* feat, const float* weight, in
 /* Backward of pk_gather_rows (RankViTBlock.sort_and_drop, rankvit.py:55-77; no gradient through the indices):
  * x[b * seq_len + tok(o), :] = y[b * (k + 1) + o, :], tok(0) = 0, tok(o) = 1 + kept[b, o - 1]; x is zeroed by the caller. */
 int pk_scatter_rows(const float* y, float* x, const int* kept, int batch, int seq_len, int k, int dim, void* stream);
+
+/* --- gate regime of ResidualViT (train/train.py:99-100 with models/residualvit.py:47-74,197-260; sigmoid gate, learnable budget
+ * token).  Training-mode block on the dense layout [class, budget, image tokens ...] with a soft mask m >= 0 per image token:
+ *   mi = m*x,  a = m*LN1(mi),  x1 = mi + m*(Wo attention(Wqkv a) + bo),  y = m*LN2(x1),  out = x1 + mlp(y)
+ *   m = relu(sigmoid((x.w_g + b_g)/temp + bias) - thr_b),  thr_b = sigmoid(x_budget.w_bt + b_bt)       (:212,:47-74)
+ * Forward reuses the inference kernels (row-scaled LayerNorm / GEMM epilogues); these entry points are the gate itself and
+ * the backward pieces the masks add. */
+/* rowscale [batch*seq] (1 on the n_special leading rows), mask / sig [batch, seq - n_special], thr [batch]; gate_b / bt_b point
+ * at the live one-element bias parameters on the device (an optimiser updates them every step: no host copy). */
+int pk_residual_gate_train_fwd(const float* x, int batch, int seq, int n_special, int budget_pos, int dim, const float* gate_w,
+                               const float* gate_b, float gate_temp, float gate_bias, const float* bt_w, const float* bt_b,
+                               float* rowscale, float* mask, float* sig, float* thr, void* stream);
+/* dm [batch*seq] = the block's d mask row sums; dmask_ext [batch, n_img] or NULL = gradient of a regulariser on the published
+ * mask (utils/losses.py).  Adds into dx (image rows: dlogit * w_g, budget row: dz * w_bt) and into the four parameter
+ * gradients (fp32 atomics). */
+int pk_residual_gate_train_bwd(const float* x, const float* dm, const float* dmask_ext, const float* mask, const float* sig,
+                               const float* thr, int batch, int seq, int n_special, int budget_pos, int dim, const float* gate_w,
+                               float gate_temp, const float* bt_w, float* dx, float* g_gate_w, float* g_gate_b, float* g_bt_w,
+                               float* g_bt_b, void* stream);
+/* pk_layernorm_bwd for a LayerNorm whose OUTPUT is multiplied by rowscale[r]: dx (+)= LN_bwd(rowscale[r] * dy[r]) and
+ * dot_out[r] += dy[r] . LN(x)[r]  (the mask's gradient from this site). */
+int pk_layernorm_bwd_gated(const float* x, const float* dy, const float* gamma, const float* beta, float eps, float* dx, int rows,
+                           int dim, const float* rowscale, float* dot_out, int accumulate, void* stream);
+/* y_bf16[r, :] = rowscale[r] * x[r, :] */
+int pk_cast_rows_f32_bf16(const float* x, void* y_bf16, const float* rowscale, int rows, int dim, void* stream);
+/* out[r] (+)= alpha * sum_d a[r,d] * (b[r,d] - c[r,d]) / div[r]   (c, div optional; rows with div[r] <= 0 contribute 0) */
+int pk_rowdot(const float* a, const float* b, const float* c, const float* div, float* out, int rows, int dim, float alpha,
+              int accumulate, void* stream);
 /* out[t, :] += sum_b x[b * seq + row0 + t, :]: gradient of the class / register token parameters (vit.py:230-236). */
 int pk_sum_token_rows(const float* x, int batch, int seq, int row0, int n_rows, int dim, float* out, void* stream);
 

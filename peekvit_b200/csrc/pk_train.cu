@@ -78,7 +78,8 @@ __global__ void gelu_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ h, const 
 template <int MAXV>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma, float eps,
-                     float* __restrict__ dx, int rows, int dim, const int* __restrict__ row_index, int dy_div, int accumulate) {
+                     float* __restrict__ dx, int rows, int dim, const int* __restrict__ row_index, int dy_div, int accumulate,
+                     const float* __restrict__ beta, const float* __restrict__ rowscale, float* __restrict__ dot_out) {
   const int lane = lane_id(), d4 = dim / 4;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
   for (int r = blockIdx.x * (blockDim.x >> 5) + warp_id(); r < rows; r += warps_total) {
@@ -86,7 +87,7 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
     const float4* x4 = reinterpret_cast<const float4*>(x + xr * dim);
     const float4* g4 = reinterpret_cast<const float4*>(dy + static_cast<long long>(r / dy_div) * dim);
     float4 xv[MAXV], gv[MAXV];
-    float s1 = 0.f;
+    float s1 = 0.f, sb = 0.f;
 #pragma unroll
     for (int j = 0; j < MAXV; ++j) {
       const int c = lane + 32 * j;
@@ -97,6 +98,10 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
         const float4 d = g4[c], w = __ldg(reinterpret_cast<const float4*>(gamma) + c);
         gv[j] = make_float4(d.x * w.x, d.y * w.y, d.z * w.z, d.w * w.w);
         s1 += (xv[j].x + xv[j].y) + (xv[j].z + xv[j].w);
+        if (dot_out && beta) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+          sb += (d.x * b.x + d.y * b.y) + (d.z * b.z + d.w * b.w);
+        }
       }
     }
     const float mean = warp_sum(s1) / static_cast<float>(dim);
@@ -118,14 +123,24 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
         sgx += (gv[j].x * xv[j].x + gv[j].y * xv[j].y) + (gv[j].z * xv[j].z + gv[j].w * xv[j].w);
       }
     }
-    const float mg = warp_sum(sg) / static_cast<float>(dim), mgx = warp_sum(sgx) / static_cast<float>(dim);
+    const float tgx = warp_sum(sgx);
+    const float mg = warp_sum(sg) / static_cast<float>(dim), mgx = tgx / static_cast<float>(dim);
+    // gated blocks (residualvit.py:249-260): the LayerNorm output is multiplied by the row's mask m before it is used, so
+    // d mask = dy . LN(x) = sum(dy * gamma * xhat) + sum(dy * beta) and the gradient that enters the LayerNorm is m * dy
+    if (dot_out) {
+      const float tb = warp_sum(sb);
+      if (lane == 0) dot_out[xr] += tgx + tb;
+    }
+    const float rs = rowscale ? rowscale[xr] : 1.f;
+    if (rowscale && rs == 0.f && accumulate) continue;
+    const float rstd_s = rstd * rs;
     float4* o4 = reinterpret_cast<float4*>(dx + xr * dim);
 #pragma unroll
     for (int j = 0; j < MAXV; ++j) {
       const int c = lane + 32 * j;
       if (c < d4) {
-        float4 o = make_float4(rstd * (gv[j].x - mg - xv[j].x * mgx), rstd * (gv[j].y - mg - xv[j].y * mgx),
-                               rstd * (gv[j].z - mg - xv[j].z * mgx), rstd * (gv[j].w - mg - xv[j].w * mgx));
+        float4 o = make_float4(rstd_s * (gv[j].x - mg - xv[j].x * mgx), rstd_s * (gv[j].y - mg - xv[j].y * mgx),
+                               rstd_s * (gv[j].z - mg - xv[j].z * mgx), rstd_s * (gv[j].w - mg - xv[j].w * mgx));
         if (accumulate) {
           const float4 p = o4[c];
           o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
@@ -601,6 +616,165 @@ scatter_rows_kernel(const float* __restrict__ y, float* __restrict__ x, const in
   }
 }
 
+
+// ------------------------------------------------------------------ gate regime of ResidualViT (residualvit.py:47-74,197-260)
+// Training-mode block with a soft mask m >= 0 per image token (m = 1 on the class and budget rows):
+//     mi = m * x      a = m * LN1(mi)      x1 = mi + m * (Wo attention(Wqkv a) + bo)      y = m * LN2(x1)      out = x1 + mlp(y)
+//     m  = relu(sigmoid((x . w_g + b_g) / temp + bias) - thr_b),   thr_b = sigmoid(x_budget . w_bt + b_bt)
+// The backbone is frozen; what trains is (w_g, b_g), (w_bt, b_bt), the learnable budget token, the class token and the head.
+// d m collects four row dot products (dy . LN2(x1), dx1 . proj, da . LN1(mi), dmi . x); where m == 0 the relu passes nothing.
+
+// y_bf16[r, :] = rowscale[r] * x[r, :]
+__global__ void cast_rows_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ rowscale,
+                                          long long n4, int d4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float sc = rowscale[i / d4];
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_bf16(v.x * sc, v.y * sc), pack_bf16(v.z * sc, v.w * sc));
+  }
+}
+
+// out[r] (+)= alpha * sum_d a[r,d] * (b[r,d] - c[r,d]) / div[r]      (c, div optional; div[r] <= 0 -> 0).  One warp per row.
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c, const float* __restrict__ div,
+              float* __restrict__ out, int rows, int dim, float alpha, int accumulate) {
+  const int lane = lane_id(), d4 = dim / 4;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int r = blockIdx.x * (blockDim.x >> 5) + warp_id(); r < rows; r += warps_total) {
+    float dv = 1.f;
+    if (div) {
+      dv = div[r];
+      if (dv <= 0.f) {
+        if (lane == 0 && !accumulate) out[r] = 0.f;
+        continue;
+      }
+    }
+    const float4* a4 = reinterpret_cast<const float4*>(a + static_cast<long long>(r) * dim);
+    const float4* b4 = reinterpret_cast<const float4*>(b + static_cast<long long>(r) * dim);
+    const float4* c4 = c ? reinterpret_cast<const float4*>(c + static_cast<long long>(r) * dim) : nullptr;
+    float acc = 0.f;
+    for (int k = lane; k < d4; k += 32) {
+      const float4 av = a4[k];
+      float4 bv = b4[k];
+      if (c4) { const float4 cv = c4[k]; bv.x -= cv.x; bv.y -= cv.y; bv.z -= cv.z; bv.w -= cv.w; }
+      acc += (av.x * bv.x + av.y * bv.y) + (av.z * bv.z + av.w * bv.w);
+    }
+    acc = warp_sum(acc) * alpha / dv;
+    if (lane == 0) out[r] = accumulate ? out[r] + acc : acc;
+  }
+}
+
+__device__ __forceinline__ float warp_rowdot(const float* __restrict__ xrow, const float* __restrict__ w, int d4, int lane) {
+  float acc = 0.f;
+  for (int k = lane; k < d4; k += 32) {
+    const float4 xv = reinterpret_cast<const float4*>(xrow)[k], wv = __ldg(reinterpret_cast<const float4*>(w) + k);
+    acc += (xv.x * wv.x + xv.y * wv.y) + (xv.z * wv.z + xv.w * wv.w);
+  }
+  return warp_sum(acc);
+}
+__device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + __expf(-z)); }
+
+// Forward of the gate on the dense training layout [class, budget, image tokens ...] of every sample: one warp per row.
+//   rowscale[r] = 1 on the special rows, m on image rows;  mask[b, t] = m,  sig[b, t] = the sigmoid value,  thr[b].
+__global__ void __launch_bounds__(256)
+gate_train_fwd_kernel(const float* __restrict__ x, int batch, int seq, int n_special, int budget_pos, const float* __restrict__ gate_w,
+                      const float* __restrict__ gate_b_p, float inv_temp, float gate_bias, const float* __restrict__ bt_w,
+                      const float* __restrict__ bt_b_p,
+                      float* __restrict__ rowscale, float* __restrict__ mask, float* __restrict__ sig, float* __restrict__ thr, int dim) {
+  const int lane = lane_id(), d4 = dim / 4, n_img = seq - n_special;
+  const int rows = batch * seq, warps_total = gridDim.x * (blockDim.x >> 5);
+  const float gate_b = __ldg(gate_b_p), bt_b = __ldg(bt_b_p);       // live parameters: read on the device, no host sync
+  for (int r = blockIdx.x * (blockDim.x >> 5) + warp_id(); r < rows; r += warps_total) {
+    const int b = r / seq, t = r - b * seq;
+    const float z = warp_rowdot(x + (static_cast<long long>(b) * seq + budget_pos) * dim, bt_w, d4, lane) + bt_b;
+    const float th = sigmoidf_(z);                                 // residualvit.py:212
+    if (t < n_special) {
+      if (lane == 0) {
+        rowscale[r] = 1.f;
+        if (t == budget_pos) thr[b] = th;
+      }
+      continue;
+    }
+    const float logit = warp_rowdot(x + static_cast<long long>(r) * dim, gate_w, d4, lane) + gate_b;
+    const float sg = sigmoidf_(logit * inv_temp + gate_bias);      // blocks.py:62-69
+    const float m = fmaxf(sg - th, 0.f);                           // residualvit.py:63-64
+    if (lane == 0) {
+      rowscale[r] = m;
+      mask[b * n_img + (t - n_special)] = m;
+      sig[b * n_img + (t - n_special)] = sg;
+    }
+  }
+}
+
+// Backward of the gate: one CTA per sample.  dm[r] = the block's row dot products, dmask_ext (optional) = the gradient of a
+// regulariser on the published mask (utils/losses.py).  For image rows with m > 0:
+//   ds = dm + dmask_ext,  d thr -= ds,  dlogit = ds * s (1 - s) / temp,  dx[r] += dlogit * w_g,  d w_g += dlogit * x[r],  d b_g += dlogit
+// then  dz = d thr * thr (1 - thr),  dx[budget row] += dz * w_bt,  d w_bt += dz * x[budget row],  d b_bt += dz.
+constexpr int kGateBwdMaxV = 8;      // dim <= 1024
+__global__ void __launch_bounds__(256)
+gate_train_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dm, const float* __restrict__ dmask_ext,
+                      const float* __restrict__ mask, const float* __restrict__ sig, const float* __restrict__ thr,
+                      const float* __restrict__ gate_w, float inv_temp, const float* __restrict__ bt_w, int seq, int n_special,
+                      int budget_pos, int dim, float* __restrict__ dx, float* __restrict__ g_gate_w, float* __restrict__ g_gate_b,
+                      float* __restrict__ g_bt_w, float* __restrict__ g_bt_b) {
+  extern __shared__ float gsm[];                 // [8 warps][dim] partial d w_g, then 8 + 8 scalars
+  const int lane = lane_id(), warp = warp_id(), d4 = dim / 4, n_img = seq - n_special, b = blockIdx.x;
+  float4 acc[kGateBwdMaxV];
+#pragma unroll
+  for (int j = 0; j < kGateBwdMaxV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float dthr = 0.f, dbias = 0.f;
+  for (int t = warp; t < n_img; t += 8) {
+    const float m = mask[b * n_img + t];
+    if (m <= 0.f) continue;                      // relu: nothing passes
+    const long long r = static_cast<long long>(b) * seq + n_special + t;
+    const float ds = dm[r] + (dmask_ext ? dmask_ext[b * n_img + t] : 0.f);
+    const float sg = sig[b * n_img + t];
+    const float dlogit = ds * sg * (1.f - sg) * inv_temp;
+    dthr -= ds;
+    dbias += dlogit;
+    const float4* x4 = reinterpret_cast<const float4*>(x + r * dim);
+    float4* dx4 = reinterpret_cast<float4*>(dx + r * dim);
+#pragma unroll
+    for (int j = 0; j < kGateBwdMaxV; ++j) {
+      const int c = lane + 32 * j;
+      if (c < d4) {
+        const float4 xv = x4[c], wv = __ldg(reinterpret_cast<const float4*>(gate_w) + c);
+        acc[j].x += dlogit * xv.x; acc[j].y += dlogit * xv.y; acc[j].z += dlogit * xv.z; acc[j].w += dlogit * xv.w;
+        float4 o = dx4[c];
+        o.x += dlogit * wv.x; o.y += dlogit * wv.y; o.z += dlogit * wv.z; o.w += dlogit * wv.w;
+        dx4[c] = o;
+      }
+    }
+  }
+  float* part = gsm + warp * dim;
+#pragma unroll
+  for (int j = 0; j < kGateBwdMaxV; ++j) {
+    const int c = lane + 32 * j;
+    if (c < d4) reinterpret_cast<float4*>(part)[c] = acc[j];
+  }
+  float* scal = gsm + 8 * dim;
+  if (lane == 0) { scal[warp] = dthr; scal[8 + warp] = dbias; }      // every lane of a warp holds the same dthr / dbias
+  __syncthreads();
+  for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += gsm[w * dim + d];
+    if (v != 0.f) atomicAdd(g_gate_w + d, v);
+  }
+  float dthr_b = 0.f, dbias_b = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { dthr_b += scal[w]; dbias_b += scal[8 + w]; }
+  if (threadIdx.x == 0 && dbias_b != 0.f) atomicAdd(g_gate_b, dbias_b);
+  const float th = thr[b];
+  const float dz = dthr_b * th * (1.f - th);
+  if (dz == 0.f) return;
+  const long long rb = static_cast<long long>(b) * seq + budget_pos;
+  for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+    atomicAdd(g_bt_w + d, dz * x[rb * dim + d]);
+    dx[rb * dim + d] += dz * __ldg(bt_w + d);
+  }
+  if (threadIdx.x == 0) atomicAdd(g_bt_b, dz);
+}
 }  // namespace pk
 
 using namespace pk;
@@ -636,19 +810,77 @@ extern "C" int pk_gelu_bwd_bf16(const void* h_pre, const void* dhid, void* dh_pr
   return check_cuda(cudaGetLastError(), "gelu_bwd_bf16_kernel");
 }
 
+static int launch_layernorm_bwd(const float* x, const float* dy, const float* gamma, const float* beta, float eps, float* dx, int rows,
+                                int dim, const int* row_index, int dy_div, int accumulate, const float* rowscale, float* dot_out,
+                                cudaStream_t s) {
+  const int grid = train_grid(rows, 8);
+  const int maxv = (dim / 4 + 31) / 32;
+  if (maxv <= 2) layernorm_bwd_kernel<2><<<grid, 256, 0, s>>>(x, dy, gamma, eps, dx, rows, dim, row_index, dy_div, accumulate, beta, rowscale, dot_out);
+  else if (maxv <= 3) layernorm_bwd_kernel<3><<<grid, 256, 0, s>>>(x, dy, gamma, eps, dx, rows, dim, row_index, dy_div, accumulate, beta, rowscale, dot_out);
+  else if (maxv <= 6) layernorm_bwd_kernel<6><<<grid, 256, 0, s>>>(x, dy, gamma, eps, dx, rows, dim, row_index, dy_div, accumulate, beta, rowscale, dot_out);
+  else layernorm_bwd_kernel<8><<<grid, 256, 0, s>>>(x, dy, gamma, eps, dx, rows, dim, row_index, dy_div, accumulate, beta, rowscale, dot_out);
+  return check_cuda(cudaGetLastError(), "layernorm_bwd_kernel");
+}
+
 extern "C" int pk_layernorm_bwd(const float* x, const float* dy, const float* gamma, float eps, float* dx, int rows, int dim,
                                 const int* row_index, int dy_div, int accumulate, void* stream) {
   PK_REQUIRE(x && dy && gamma && dx, "pk_layernorm_bwd: null pointer");
   PK_REQUIRE(dim % 4 == 0 && dim >= 4 && dim <= 1024 && rows >= 0 && dy_div >= 1, "pk_layernorm_bwd: dim %d must be a multiple of 4 in [4,1024]", dim);
   if (rows == 0) return PK_OK;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int grid = train_grid(rows, 8);
-  const int maxv = (dim / 4 + 31) / 32;
-  if (maxv <= 2) layernorm_bwd_kernel<2><<<grid, 256, 0, s>>>(x, dy, gamma, eps, dx, rows, dim, row_index, dy_div, accumulate);
-  else if (maxv <= 3) layernorm_bwd_kernel<3><<<grid, 256, 0, s>>>(x, dy, gamma, eps, dx, rows, dim, row_index, dy_div, accumulate);
-  else if (maxv <= 6) layernorm_bwd_kernel<6><<<grid, 256, 0, s>>>(x, dy, gamma, eps, dx, rows, dim, row_index, dy_div, accumulate);
-  else layernorm_bwd_kernel<8><<<grid, 256, 0, s>>>(x, dy, gamma, eps, dx, rows, dim, row_index, dy_div, accumulate);
-  return check_cuda(cudaGetLastError(), "layernorm_bwd_kernel");
+  return launch_layernorm_bwd(x, dy, gamma, nullptr, eps, dx, rows, dim, row_index, dy_div, accumulate, nullptr, nullptr,
+                              static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pk_layernorm_bwd_gated(const float* x, const float* dy, const float* gamma, const float* beta, float eps, float* dx,
+                                      int rows, int dim, const float* rowscale, float* dot_out, int accumulate, void* stream) {
+  PK_REQUIRE(x && dy && gamma && beta && dx && rowscale && dot_out, "pk_layernorm_bwd_gated: null pointer");
+  PK_REQUIRE(dim % 4 == 0 && dim >= 4 && dim <= 1024 && rows >= 0, "pk_layernorm_bwd_gated: dim %d must be a multiple of 4 in [4,1024]", dim);
+  if (rows == 0) return PK_OK;
+  return launch_layernorm_bwd(x, dy, gamma, beta, eps, dx, rows, dim, nullptr, 1, accumulate, rowscale, dot_out,
+                              static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pk_cast_rows_f32_bf16(const float* x, void* y, const float* rowscale, int rows, int dim, void* stream) {
+  PK_REQUIRE(x && y && rowscale && rows >= 0 && dim > 0 && dim % 4 == 0, "pk_cast_rows_f32_bf16: bad arguments (dim must be a multiple of 4)");
+  if (rows == 0) return PK_OK;
+  const long long n4 = static_cast<long long>(rows) * (dim / 4);
+  cast_rows_f32_bf16_kernel<<<train_grid(n4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(y), rowscale, n4, dim / 4);
+  return check_cuda(cudaGetLastError(), "cast_rows_f32_bf16_kernel");
+}
+
+extern "C" int pk_rowdot(const float* a, const float* b, const float* c, const float* div, float* out, int rows, int dim, float alpha,
+                         int accumulate, void* stream) {
+  PK_REQUIRE(a && b && out && rows >= 0 && dim > 0 && dim % 4 == 0, "pk_rowdot: bad arguments (dim must be a multiple of 4)");
+  if (rows == 0) return PK_OK;
+  rowdot_kernel<<<train_grid(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, c, div, out, rows, dim, alpha, accumulate);
+  return check_cuda(cudaGetLastError(), "rowdot_kernel");
+}
+
+extern "C" int pk_residual_gate_train_fwd(const float* x, int batch, int seq, int n_special, int budget_pos, int dim, const float* gate_w,
+                                          const float* gate_b, float gate_temp, float gate_bias, const float* bt_w, const float* bt_b,
+                                          float* rowscale, float* mask, float* sig, float* thr, void* stream) {
+  PK_REQUIRE(x && gate_w && gate_b && bt_w && bt_b && rowscale && mask && sig && thr, "pk_residual_gate_train_fwd: null pointer");
+  PK_REQUIRE(batch >= 0 && n_special >= 1 && seq > n_special && budget_pos >= 0 && budget_pos < n_special && dim % 4 == 0 && dim >= 4 &&
+             gate_temp != 0.f, "pk_residual_gate_train_fwd: bad shape");
+  if (batch == 0) return PK_OK;
+  gate_train_fwd_kernel<<<train_grid(static_cast<long long>(batch) * seq, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, batch, seq, n_special, budget_pos, gate_w, gate_b, 1.f / gate_temp, gate_bias, bt_w, bt_b, rowscale, mask, sig, thr, dim);
+  return check_cuda(cudaGetLastError(), "gate_train_fwd_kernel");
+}
+
+extern "C" int pk_residual_gate_train_bwd(const float* x, const float* dm, const float* dmask_ext, const float* mask, const float* sig,
+                                          const float* thr, int batch, int seq, int n_special, int budget_pos, int dim,
+                                          const float* gate_w, float gate_temp, const float* bt_w, float* dx, float* g_gate_w,
+                                          float* g_gate_b, float* g_bt_w, float* g_bt_b, void* stream) {
+  PK_REQUIRE(x && dm && mask && sig && thr && gate_w && bt_w && dx && g_gate_w && g_gate_b && g_bt_w && g_bt_b,
+             "pk_residual_gate_train_bwd: null pointer");
+  PK_REQUIRE(batch >= 0 && n_special >= 1 && seq > n_special && budget_pos >= 0 && budget_pos < n_special && dim % 4 == 0 && dim >= 4 &&
+             dim <= 1024 && gate_temp != 0.f, "pk_residual_gate_train_bwd: bad shape (dim a multiple of 4, <= 1024)");
+  if (batch == 0) return PK_OK;
+  const size_t smem = (static_cast<size_t>(8) * dim + 16) * sizeof(float);
+  gate_train_bwd_kernel<<<batch, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      x, dm, dmask_ext, mask, sig, thr, gate_w, 1.f / gate_temp, bt_w, seq, n_special, budget_pos, dim, dx, g_gate_w, g_gate_b, g_bt_w, g_bt_b);
+  return check_cuda(cudaGetLastError(), "gate_train_bwd_kernel");
 }
 
 template <int DH>

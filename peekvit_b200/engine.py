@@ -308,17 +308,38 @@ def pack_model(model, family: str) -> PackedModel:
 
 
 LIGHT_PARAMS = ("class_tokens", "class_token", "head.weight", "head.bias")
+_LIGHT_GATE_SUFFIXES = (".residual_gate.projection.weight", ".residual_gate.projection.bias", ".budget_token_gate.weight",
+                        ".budget_token_gate.bias")
+
+
+def is_light_param(name: str) -> bool:
+    """Parameters of the fine-tuning regimes (train/train.py:99-100) that an optimiser step changes while the backbone stays
+    frozen: class tokens and head; for ResidualViT also the gate projections, budget-token gates and learnable budget tokens."""
+    return (name in LIGHT_PARAMS or name.startswith("learnable_budget_token_")
+            or (name.startswith("encoder.layers.") and name.endswith(_LIGHT_GATE_SUFFIXES)))
 
 
 def refresh_light(pm: "PackedModel", model) -> None:
-    """Re-read the class tokens and the head from the live module into an existing weight pack (same storage), and drop
-    what was derived from them: the embedding's initial rows and the split head weight."""
+    """Re-read the light parameters from the live module into an existing weight pack (same storage), and drop what was
+    derived from them: the embedding's initial rows and the split head weight."""
     cls = model.class_token if pm.family == "moevit" else model.class_tokens
     pm.cls_tokens.copy_(cls.detach().reshape(-1, pm.dim))
     pm.head_w.copy_(model.head.weight.detach())
     pm.head_b.copy_(model.head.bias.detach())
     pm.__dict__.pop("_embed_consts", None)
     pm.extra.pop("head_w6", None)
+    if pm.family == "residualvit":
+        for k, attr in (("budget_token_1", "learnable_budget_token_1"), ("budget_token_2", "learnable_budget_token_2")):
+            if k in pm.extra:
+                pm.extra[k].copy_(getattr(model, attr).detach().reshape(1, pm.dim))
+        for lw in pm.layers:
+            if "gate_w" in lw.extra:
+                g = lw.module.residual_gate
+                lw.extra["gate_w"].copy_(g.projection.weight.detach().reshape(-1))
+                lw.extra["gate_b"] = float(g.projection.bias.detach().float().cpu()[0])
+            if "bt_gate_w" in lw.extra:
+                lw.extra["bt_gate_w"].copy_(lw.module.budget_token_gate.weight.detach().reshape(-1))
+                lw.extra["bt_gate_b"] = float(lw.module.budget_token_gate.bias.detach().float().cpu()[0])
 
 
 def params_fingerprint(model) -> tuple:

@@ -19,6 +19,8 @@ import math
 from abc import ABC
 from typing import List, Literal, Optional, Union
 
+import random
+
 import torch
 from torch import nn
 
@@ -476,6 +478,17 @@ class ResidualVisionTransformer(_ModelBase):
         self._no_pretrained(torch_pretrained_weights, timm_pretrained_weights)
         if remove_layers:
             self.remove_layers(remove_layers)
+
+    def _sample_budget(self, n: int) -> torch.Tensor:
+        """models/residualvit.py:541-550: the budgets of a training batch -- one draw per image from the list or from
+        ``budget_interval``, or the fixed float.  Used by ``peekvit_b200.finetune.FineTuner`` (the training-mode forward)."""
+        abt = self.add_budget_token
+        if isinstance(abt, (list, tuple)):
+            return torch.tensor([random.choice(abt) for _ in range(n)])
+        if isinstance(abt, float):
+            return torch.tensor(abt)
+        lo, hi = self.budget_interval
+        return torch.rand(n) * (hi - lo) + lo
 
     def set_budget(self, budget: float):
         """models/residualvit.py:619-622."""

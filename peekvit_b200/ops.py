@@ -601,6 +601,56 @@ def layernorm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: f
     return dx
 
 
+def layernorm_bwd_gated(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, dx: torch.Tensor,
+                        rows: int, rowscale: torch.Tensor, dot_out: torch.Tensor, *, accumulate: bool = True) -> torch.Tensor:
+    """dx (+)= LN_bwd(rowscale * dy); dot_out[r] += dy[r] . LN(x)[r]  (a LayerNorm whose output is masked, residualvit.py:252,258)."""
+    lib = _lib_for(x)
+    check(lib.pk_layernorm_bwd_gated(_ptr(x, torch.float32), _ptr(dy, torch.float32), _ptr(gamma, torch.float32), _ptr(beta, torch.float32),
+                                     float(eps), _ptr(dx, torch.float32), rows, x.shape[-1], _ptr(rowscale, torch.float32),
+                                     _ptr(dot_out, torch.float32), int(accumulate), _stream()), "pk_layernorm_bwd_gated")
+    return dx
+
+
+def cast_rows_bf16(x: torch.Tensor, out: torch.Tensor, rowscale: torch.Tensor, rows: int) -> torch.Tensor:
+    lib = _lib_for(x)
+    check(lib.pk_cast_rows_f32_bf16(_ptr(x, torch.float32), _ptr(out, torch.bfloat16), _ptr(rowscale, torch.float32), rows, x.shape[-1],
+                                    _stream()), "pk_cast_rows_f32_bf16")
+    return out
+
+
+def rowdot(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, rows: int, *, c: Optional[torch.Tensor] = None,
+           div: Optional[torch.Tensor] = None, alpha: float = 1.0, accumulate: bool = True) -> torch.Tensor:
+    """out[r] (+)= alpha * sum_d a[r,d] * (b[r,d] - c[r,d]) / div[r]; rows with div[r] <= 0 contribute nothing."""
+    lib = _lib_for(a)
+    check(lib.pk_rowdot(_ptr(a, torch.float32), _ptr(b, torch.float32), _ptr(c, torch.float32), _ptr(div, torch.float32),
+                        _ptr(out, torch.float32), rows, a.shape[-1], float(alpha), int(accumulate), _stream()), "pk_rowdot")
+    return out
+
+
+def residual_gate_train_fwd(x: torch.Tensor, batch: int, seq: int, n_special: int, budget_pos: int, gate_w: torch.Tensor,
+                            gate_b: torch.Tensor, gate_temp: float, gate_bias: float, bt_w: torch.Tensor, bt_b: torch.Tensor, rowscale: torch.Tensor,
+                            mask: torch.Tensor, sig: torch.Tensor, thr: torch.Tensor) -> None:
+    lib = _lib_for(x)
+    check(lib.pk_residual_gate_train_fwd(_ptr(x, torch.float32), batch, seq, n_special, budget_pos, x.shape[-1], _ptr(gate_w, torch.float32),
+                                         _ptr(gate_b, torch.float32), float(gate_temp), float(gate_bias), _ptr(bt_w, torch.float32),
+                                         _ptr(bt_b, torch.float32),
+                                         _ptr(rowscale, torch.float32), _ptr(mask, torch.float32), _ptr(sig, torch.float32),
+                                         _ptr(thr, torch.float32), _stream()), "pk_residual_gate_train_fwd")
+
+
+def residual_gate_train_bwd(x: torch.Tensor, dm: torch.Tensor, dmask_ext: Optional[torch.Tensor], mask: torch.Tensor, sig: torch.Tensor,
+                            thr: torch.Tensor, batch: int, seq: int, n_special: int, budget_pos: int, gate_w: torch.Tensor,
+                            gate_temp: float, bt_w: torch.Tensor, dx: torch.Tensor, g_gate_w: torch.Tensor, g_gate_b: torch.Tensor,
+                            g_bt_w: torch.Tensor, g_bt_b: torch.Tensor) -> None:
+    lib = _lib_for(x)
+    check(lib.pk_residual_gate_train_bwd(_ptr(x, torch.float32), _ptr(dm, torch.float32), _ptr(dmask_ext, torch.float32),
+                                         _ptr(mask, torch.float32), _ptr(sig, torch.float32), _ptr(thr, torch.float32), batch, seq,
+                                         n_special, budget_pos, x.shape[-1], _ptr(gate_w, torch.float32), float(gate_temp),
+                                         _ptr(bt_w, torch.float32), _ptr(dx, torch.float32), _ptr(g_gate_w, torch.float32),
+                                         _ptr(g_gate_b, torch.float32), _ptr(g_bt_w, torch.float32), _ptr(g_bt_b, torch.float32),
+                                         _stream()), "pk_residual_gate_train_bwd")
+
+
 def attention_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, dqkv: torch.Tensor, batch: int, num_heads: int,
                   head_dim: int, seq_len: int) -> torch.Tensor:
     lib = _lib_for(qkv)

@@ -54,11 +54,12 @@ def packed(model) -> engine.PackedModel:
         old, pm = st["fp"], st["pm"]
         light = False
         if pm is not None and old is not None and len(old) == len(fp):
-            # an optimiser step of the fine-tuning regime (class tokens / head only, peekvit_b200.finetune) changes three small
-            # tensors: refresh them in place instead of converting 86 M frozen weights again
+            # an optimiser step of a fine-tuning regime (class tokens / head; ResidualViT: also the gates and budget tokens --
+            # peekvit_b200.finetune) changes a few small tensors: refresh them in place instead of converting 86 M frozen
+            # weights again
             names = [n for n, _ in model.named_parameters()]
             changed = [i for i, (a, b) in enumerate(zip(old, fp)) if a != b]
-            light = bool(changed) and all(i < len(names) and names[i] in engine.LIGHT_PARAMS for i in changed)
+            light = bool(changed) and all(i < len(names) and engine.is_light_param(names[i]) for i in changed)
         if light:
             engine.refresh_light(pm, model)
         else:
@@ -170,6 +171,11 @@ def _forward_chunk(model, fwd: engine.Forward, chunk: torch.Tensor, aux: Optiona
         fn, key = (lambda c, a: fwd.rankvit(c, budgets, a)), tuple(sorted(budgets.items()))
     elif family == "residualvit":
         b = model.current_budget
+        if isinstance(b, torch.Tensor) and b.numel() > 1:
+            # what a training step leaves behind (one sampled budget per image, residualvit.py:565-566); evaluation is per
+            # budget (validate/test.py:107-121 calls set_budget for each): the compacted forward takes one budget per batch
+            raise ValueError("current_budget holds one budget per image (left by a training step): call set_budget(b) before "
+                             "evaluating")
         b = None if b is None else float(b)
         fn, key = (lambda c, a: fwd.residualvit(c, b, a)), b
     elif family == "eeresidualvit":

@@ -30,9 +30,22 @@ def test_finetuner_accepts_the_dense_regime_only():
     ft = finetune.FineTuner(build_model("vit", _BASE))
     assert sorted(ft.params) == ["class_tokens", "head.bias", "head.weight"]
     assert sorted(finetune.FineTuner(build_model("RankVisionTransformer", dict(_BASE, rankvit_layers=[1]))).params) == sorted(ft.params)
-    with pytest.raises(NotImplementedError):                          # gates / budget tokens: training-mode forward not built
-        finetune.FineTuner(build_model("residualvit", dict(_BASE, gate_type="sigmoid", gate_bias=0.0, add_budget_token="learnable",
+    # the gate regime of ResidualViT as shipped (sigmoid gates, learnable budget token): gates, budget-token gates, the
+    # learnable budget token, class token and head train; other configurations have no backward
+    res = finetune.FineTuner(build_model("residualvit", dict(_BASE, gate_type="sigmoid", gate_bias=0.0, add_budget_token="learnable",
+                                                            residual_layers=["attention+mlp", "none"])))
+    assert sorted(res.params) == sorted(
+        ["class_tokens", "head.bias", "head.weight", "learnable_budget_token_1"]
+        + [f"encoder.layers.0.residual_gate.projection.{k}" for k in ("weight", "bias")]
+        + [f"encoder.layers.{i}.budget_token_gate.{k}" for i in (0, 1) for k in ("weight", "bias")])
+    with pytest.raises(NotImplementedError):
+        finetune.FineTuner(build_model("residualvit", dict(_BASE, gate_type="gumbel", gate_bias=0.0, add_budget_token="learnable",
                                                            residual_layers=["attention+mlp"] * 2)))
+    with pytest.raises(NotImplementedError):
+        finetune.FineTuner(build_model("residualvit", dict(_BASE, gate_type="sigmoid", gate_bias=0.0, add_budget_token=[0.3, 0.6],
+                                                           residual_layers=["attention+mlp"] * 2)))
+    with pytest.raises(NotImplementedError):
+        finetune.FineTuner(build_model("adavit", _BASE))
     with pytest.raises(NotImplementedError):                          # a trainable backbone parameter has no weight-gradient kernel
         finetune.FineTuner(build_model("vit", _BASE), train_words=("head", "fc1"))
     with pytest.raises(NotImplementedError):
@@ -71,3 +84,36 @@ def test_all_reduce_is_a_no_op_without_a_process_group():
     p = torch.nn.Parameter(torch.zeros(4))
     p.grad = torch.arange(4.0)
     assert finetune.all_reduce_mean_([p]) == 1 and torch.equal(p.grad, torch.arange(4.0))
+
+
+def test_oracle_reproduces_the_reference_gate_regime_gradients():
+    """tests/golden/finetune_residual_learnable.npz holds logits, loss, masks and the 20 parameter gradients of the REFERENCE
+    ResidualViT in train() mode (make_finetune_residual.py).  The oracle restatement, differentiated by torch autograd with the
+    same per-image budgets and the same regulariser, must reproduce them: this pins the checker of the GPU gradient tests."""
+    import os
+    import numpy as np
+    from golden_cases import CASES, build_case
+    from oracle import peekvit_oracle as po
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "finetune_residual_learnable.npz"))
+    case = CASES["residual_learnable_cal04"]
+    sd, images = build_case(case)
+    B = images.shape[0]
+    labels, budgets = torch.from_numpy(fx["labels"]), torch.from_numpy(fx["budgets"])
+    names = [k[5:] for k in fx.files if k.startswith("grad.")]
+    assert len(names) == 20 and "learnable_budget_token_1" in names and "encoder.layers.3.budget_token_gate.bias" in names
+    sdg = {k: v.clone() for k, v in sd.items()}
+    for n in names:
+        sdg[n].requires_grad_(True)
+    logits, aux = po.residualvit_forward(sdg, case["cfg"], images, budgets.view(B, 1, 1))
+    masks = [aux["masks"][i] for i in sorted(aux["masks"])]
+    sp = torch.stack([m.mean(dim=(1, 2)) for m in masks]).mean()
+    reg = ((sp - budgets) ** 2).sum().mul(2 - budgets).mean()          # utils/losses.py:111-142, per_layer=False, strict=True
+    loss = torch.nn.functional.cross_entropy(logits, labels) + 0.5 * reg
+    loss.backward()
+    assert abs(loss.item() - float(fx["loss"])) < 1e-5
+    assert (logits.detach() - torch.from_numpy(fx["logits"])).abs().max().item() < 1e-5
+    for i, m in enumerate(masks):
+        assert (m.detach() - torch.from_numpy(fx[f"mask.{i}"])).abs().max().item() < 1e-6
+    for n in names:
+        want = torch.from_numpy(fx["grad." + n])
+        assert ((sdg[n].grad - want).abs().max() / want.abs().max()).item() < 1e-4, n

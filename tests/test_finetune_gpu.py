@@ -231,3 +231,212 @@ def test_scatter_rows_is_the_adjoint_of_gather_rows():
     back = ops.scatter_rows(g, torch.zeros_like(x), kept, B, seq)
     assert abs(float((y * g).sum()) - float((x * back).sum())) < 1e-3            # <gather(x), g> == <x, scatter(g)>
     assert int((back.abs().sum(1) > 0).sum()) == B * (k + 1)
+
+
+# ------------------------------------------------------------------------------------------------ ResidualViT, gate regime
+def _mask_regulariser(masks, budget, strict=True):
+    """utils/losses.py:111-142 solo_mse(per_layer=False): mean mask over layers, images and tokens against the per-image budgets."""
+    sp = torch.stack([m.mean(dim=(1, 2)) for m in masks]).mean()
+    d = (sp - budget) if strict else torch.relu(sp - budget)
+    return (d ** 2).sum().mul(2 - budget).mean()
+
+
+@pytest.mark.parametrize("rows,D", [(300, 384), (40, 128), (9, 768)])
+def test_gated_layernorm_bwd_rowdot_and_row_cast_against_autograd(rows, D):
+    from peekvit_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(rows)
+    x = torch.randn(rows, D, device=DEV, generator=g, requires_grad=True)
+    gamma = (1 + 0.1 * torch.randn(D, device=DEV, generator=g))
+    beta = 0.1 * torch.randn(D, device=DEV, generator=g)
+    m = torch.rand(rows, device=DEV, generator=g)
+    m[::3] = 0.0
+    m = m.requires_grad_(True)
+    dy = torch.randn(rows, D, device=DEV, generator=g)
+    y = m[:, None] * torch.nn.functional.layer_norm(x, (D,), gamma, beta, 1e-6)
+    y.backward(dy)
+    dx = torch.ones(rows, D, device=DEV)
+    dot = torch.full((rows,), 2.0, device=DEV)
+    ops.layernorm_bwd_gated(x.detach(), dy, gamma, beta, 1e-6, dx, rows, m.detach(), dot)
+    assert _rel(dx - 1, x.grad) < 1e-4
+    assert _rel(dot - 2, m.grad) < 1e-4
+    # rowdot with the (b - c) / div form and zero rows of div
+    a, b, c = (torch.randn(rows, D, device=DEV, generator=g) for _ in range(3))
+    out = torch.full((rows,), 5.0, device=DEV)
+    ops.rowdot(a, b, out, rows, c=c, div=m.detach(), alpha=0.5)
+    want = torch.where(m.detach() > 0, 0.5 * (a * (b - c)).sum(1) / m.detach().clamp_min(1e-30), torch.zeros_like(out))
+    assert _rel(out - 5, want) < 1e-4
+    ops.rowdot(a, b, out, rows, accumulate=False)
+    assert _rel(out, (a * b).sum(1)) < 1e-4
+    yb = torch.empty(rows, D, device=DEV, dtype=torch.bfloat16)
+    ops.cast_rows_bf16(a, yb, m.detach(), rows)
+    assert torch.equal(yb, (a * m.detach()[:, None]).to(torch.bfloat16))
+    assert ops.device_flag() == 0
+
+
+@pytest.mark.parametrize("B,n_img,D", [(5, 64, 128), (3, 196, 384)])
+def test_gate_forward_backward_kernels_against_autograd(B, n_img, D):
+    """relu(sigmoid((x.w + b)/temp + bias) - sigmoid(x_budget.w_bt + b_bt)) on the layout [class, budget, image tokens]
+    (residualvit.py:47-74,:212): masks, and with upstream d mask the gradients of the four gate parameters and of x."""
+    from peekvit_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(B * n_img)
+    seq = n_img + 2
+    x = torch.randn(B, seq, D, device=DEV, generator=g, requires_grad=True)
+    w = (0.2 * torch.randn(D, device=DEV, generator=g)).requires_grad_(True)
+    b = torch.tensor([0.1], device=DEV, requires_grad=True)
+    wbt = (0.05 * torch.randn(D, device=DEV, generator=g)).requires_grad_(True)
+    bbt = torch.tensor([-0.3], device=DEV, requires_grad=True)
+    temp, bias = 0.7, 0.2
+    thr = torch.sigmoid(x[:, 1] @ wbt + bbt)
+    sg = torch.sigmoid((x[:, 2:] @ w + b) / temp + bias)
+    mask = torch.relu(sg - thr[:, None])
+    dm_img = torch.randn(B, n_img, device=DEV, generator=g)
+    ext = torch.randn(B, n_img, device=DEV, generator=g)
+    (mask * (dm_img + ext)).sum().backward()
+    rs, mk, sgo, tho = (torch.empty(s, device=DEV) for s in ((B * seq,), (B, n_img), (B, n_img), (B,)))
+    xd = x.detach().reshape(B * seq, D)
+    ops.residual_gate_train_fwd(xd, B, seq, 2, 1, w.detach(), b.detach(), temp, bias, wbt.detach(), bbt.detach(), rs, mk, sgo, tho)
+    assert _rel(mk, mask.detach()) < 1e-5 and _rel(tho, thr.detach()) < 1e-5
+    assert 0.1 < (mk > 0).float().mean().item() < 0.9
+    assert torch.equal(rs.view(B, seq)[:, 2:], mk) and bool((rs.view(B, seq)[:, :2] == 1).all())
+    dm = torch.randn(B, seq, device=DEV, generator=g)          # the special rows' entries must be ignored
+    dm[:, 2:] = dm_img
+    dx = torch.zeros(B * seq, D, device=DEV)
+    gw, gb, gbw, gbb = torch.zeros(D, device=DEV), torch.zeros(1, device=DEV), torch.zeros(D, device=DEV), torch.zeros(1, device=DEV)
+    ops.residual_gate_train_bwd(xd, dm.reshape(-1), ext, mk, sgo, tho, B, seq, 2, 1, w.detach(), temp, wbt.detach(), dx, gw, gb, gbw, gbb)
+    assert _rel(gw, w.grad) < 1e-4 and _rel(gb, b.grad) < 1e-4
+    assert _rel(gbw, wbt.grad) < 1e-4 and _rel(gbb, bbt.grad) < 1e-4
+    assert _rel(dx.view(B, seq, D), x.grad) < 1e-4
+    assert ops.device_flag() == 0
+
+
+def _residual_autograd(sd, cfg, images, labels, budgets, names, reg_weight, strict=True):
+    """fp32 autograd through the oracle on the CPU (its ResidualViT restatement builds its masks there)."""
+    from oracle import peekvit_oracle as po
+    sdg = {k: v.clone() for k, v in sd.items()}
+    for n in names:
+        sdg[n].requires_grad_(True)
+    B = images.shape[0]
+    logits, aux = po.residualvit_forward(sdg, cfg, images, budgets.view(B, 1, 1))
+    masks = [aux["masks"][i] for i in sorted(aux["masks"])]
+    loss = torch.nn.functional.cross_entropy(logits, labels) + reg_weight * _mask_regulariser(masks, budgets, strict)
+    loss.backward()
+    return loss.detach(), logits.detach(), {n: sdg[n].grad for n in names}, [m.detach() for m in masks]
+
+
+def test_residualvit_gate_regime_gradients_match_the_reference_fixture():
+    """tests/golden/finetune_residual_learnable.npz: the REFERENCE model in train() mode with train_only_these_params([...]),
+    fixed per-image budgets, loss = CE + 0.5 * strict mask regulariser, loss.backward() (make_finetune_residual.py).  The CUDA
+    path (bf16 operands) must reproduce logits, loss, masks and all 20 parameter gradients."""
+    import os
+    import numpy as np
+    from golden_cases import CASES, build_case
+    from peekvit_b200 import ops
+    from peekvit_b200.finetune import FineTuner
+    from peekvit_b200.models import ResidualVisionTransformer
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "finetune_residual_learnable.npz"))
+    case = CASES["residual_learnable_cal04"]
+    sd, images = build_case(case)
+    labels = torch.from_numpy(fx["labels"]).to(DEV)
+    budgets = torch.from_numpy(fx["budgets"]).to(DEV)
+    model = ResidualVisionTransformer(**case["cfg"])
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).train()
+    ft = FineTuner(model)
+    assert len(ft.params) == len([k for k in fx.files if k.startswith("grad.")]) == 20
+    extra = lambda m: 0.5 * _mask_regulariser([blk.mask for blk in m.encoder.layers], m.current_budget)
+    loss, logits = ft.forward_backward(images.to(DEV), labels, budgets=budgets, extra_loss=extra)
+    assert ops.device_flag() == 0
+    assert _rel(logits.cpu(), torch.from_numpy(fx["logits"])) < 1e-2
+    assert abs(loss.item() - float(fx["loss"])) < 1e-2 * float(fx["loss"])
+    for i, blk in enumerate(model.encoder.layers):
+        assert blk.mask.shape == fx[f"mask.{i}"].shape
+        assert (blk.mask.cpu() - torch.from_numpy(fx[f"mask.{i}"])).abs().max().item() < 5e-3
+    for n, p in ft.params.items():
+        want = torch.from_numpy(fx["grad." + n])
+        err = _rel(p.grad.cpu(), want.view_as(p.grad))
+        print(f"{n}: rel err {err:.2e} (max |grad| {want.abs().max().item():.2e})")
+        assert err < 3e-2, n
+
+
+def test_residualvit_s_gate_regime_against_autograd_and_sgd_steps():
+    """BASELINE config C shape (residualdeit_s_16_224.yaml kwargs, calibrated gates), 6 images with sampled budgets: gradients
+    of every trainable parameter against fp32 autograd through the oracle; then a few SGD steps on the gate regime lower the
+    loss and the inference path (compacted rows) follows the updated gates without a full weight repack."""
+    from oracle import weights as ow
+    from peekvit_b200 import ops, runner
+    from peekvit_b200.finetune import FineTuner
+    from peekvit_b200.models import ResidualVisionTransformer
+    cfg = dict(image_size=224, patch_size=16, num_layers=12, num_heads=6, hidden_dim=384, mlp_dim=1536, num_classes=1000,
+               gate_type="sigmoid", gate_temp=1.0, gate_bias=0.0, gate_threshold=0.5, add_budget_token="learnable",
+               residual_layers=["attention+mlp"] * 12)
+    sd = ow.calibrate_residual_gates(ow.make_state_dict("residualvit", cfg, seed=4321), cfg, 0.5, images=ow.synthetic_images(2, 224, seed=99))
+    images = ow.synthetic_images(6, 224, seed=1234)
+    labels = torch.randint(0, 1000, (6,), generator=torch.Generator().manual_seed(2))
+    model = ResidualVisionTransformer(**cfg)
+    model.load_state_dict(sd)
+    model = model.to(DEV).train()
+    ft = FineTuner(model)
+    torch.manual_seed(11)
+    budgets = model._sample_budget(6)
+    extra = lambda m: 0.5 * _mask_regulariser([blk.mask for blk in m.encoder.layers], m.current_budget)
+    loss, logits = ft.forward_backward(images.to(DEV), labels.to(DEV), budgets=budgets, extra_loss=extra)
+    assert ops.device_flag() == 0 and torch.equal(model.current_budget.cpu(), budgets)
+    loss_ref, logits_ref, grads, masks = _residual_autograd(sd, cfg, images, labels, budgets, list(ft.params), 0.5)
+    keep = [float((m > 0).float().mean()) for m in masks]
+    print(f"loss {loss.item():.4f} (autograd {loss_ref.item():.4f}); keep fraction per layer {[round(k, 2) for k in keep]}")
+    assert _rel(logits.cpu(), logits_ref) < 1e-2 and abs(loss.item() - loss_ref.item()) < 1e-2 * abs(loss_ref.item())
+    flips = [int(((blk.mask.cpu() > 0) != (m > 0)).sum()) for blk, m in zip(model.encoder.layers, masks)]
+    print("tokens whose relu gate flipped against the fp32 oracle, per layer:", flips)
+    errs = {n: _rel(p.grad.cpu(), grads[n].view_as(p.grad)) for n, p in ft.params.items()}
+    for n, e in errs.items():
+        print(f"  {n}: {e:.2e} (max |grad| {grads[n].abs().max().item():.2e})")
+    # relu(sigmoid - thr) is discontinuous in its derivative: with these random-init gates all tokens of an image sit at nearly
+    # the same gate value, so an image whose value is within bf16 noise of its threshold flips as a whole in one layer and that
+    # layer's gate gradients lose / gain 1/6 of their terms.  Such a layer (at most one) is excluded, and the parameters every
+    # layer's gradient flows into get the wider band; everything else is held to 5e-2 of max |grad|.
+    flipped = [i for i, f in enumerate(flips) if f > 2]
+    assert len(flipped) <= 1, flips
+    for n, e in errs.items():
+        if any(n.startswith(f"encoder.layers.{i}.") for i in flipped):
+            continue
+        tol = 1e-1 if (flipped and n in ("learnable_budget_token_1", "class_tokens")) else 5e-2
+        assert e < tol, (n, e)
+    worst = max(e for n, e in errs.items() if not any(n.startswith(f"encoder.layers.{i}.") for i in flipped))
+    print(f"{len(ft.params)} parameter gradients, worst rel err {worst:.2e} (layers with a flipped image: {flipped})")
+    # SGD on the gate regime, CE only, whole batch in micro-batches of 4
+    ft.micro_batch = 4
+    opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=0.02)
+    model.eval()
+    model.set_budget(0.6)
+    before = model(images.to(DEV))
+    pm_before = runner.packed(model)
+    model.train()
+    losses = []
+    for _ in range(8):
+        opt.zero_grad()
+        loss, _ = ft.forward_backward(images.to(DEV), labels.to(DEV), budgets=budgets)
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < 0.8 * losses[0], losses
+    model.eval()
+    with pytest.raises(ValueError, match="set_budget"):     # the training step left one budget per image behind
+        model(images.to(DEV))
+    model.set_budget(0.6)
+    after = model(images.to(DEV))
+    assert runner.packed(model) is pm_before                 # light refresh: the 22 M frozen weights were not converted again
+    assert (after - before).abs().max().item() > 1e-2 and ops.device_flag() == 0
+    ref_after, _ = __import__("oracle.peekvit_oracle", fromlist=["x"]).forward(
+        "residualvit", {k: v.detach().cpu() for k, v in model.state_dict().items()}, cfg, images, 0.6)
+    assert _rel(after.cpu(), ref_after) < 1e-2
+
+
+def test_finetuner_rejects_unsupported_residual_configurations():
+    from peekvit_b200.finetune import FineTuner
+    from peekvit_b200.models import ResidualVisionTransformer
+    base = dict(image_size=64, patch_size=8, num_layers=2, num_heads=2, hidden_dim=128, mlp_dim=256, num_classes=10)
+    for kw in (dict(gate_type="gumbel", add_budget_token="learnable", gate_bias=0.0),
+               dict(gate_type="sigmoid", add_budget_token=0.5),
+               dict(gate_type="sigmoid", add_budget_token="learnable", residual_layers=["mlp", "mlp"]),
+               dict(gate_type="sigmoid", add_budget_token="learnable", num_class_tokens=2)):
+        with pytest.raises(NotImplementedError):
+            FineTuner(ResidualVisionTransformer(**base, **kw).to(DEV).train())
