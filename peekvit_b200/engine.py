@@ -319,26 +319,34 @@ def is_light_param(name: str) -> bool:
             or (name.startswith("encoder.layers.") and name.endswith(_LIGHT_GATE_SUFFIXES)))
 
 
+def _refresh(dst: torch.Tensor, src: torch.Tensor) -> None:
+    """dst <- src unless dst already IS the live parameter's storage (fp32 parameters are packed without a copy; an in-place
+    copy onto itself would bump the parameter's version counter and make every later call look like another update)."""
+    src = src.detach()
+    if dst.data_ptr() != src.data_ptr():
+        dst.copy_(src.reshape(dst.shape))
+
+
 def refresh_light(pm: "PackedModel", model) -> None:
     """Re-read the light parameters from the live module into an existing weight pack (same storage), and drop what was
     derived from them: the embedding's initial rows and the split head weight."""
     cls = model.class_token if pm.family == "moevit" else model.class_tokens
-    pm.cls_tokens.copy_(cls.detach().reshape(-1, pm.dim))
-    pm.head_w.copy_(model.head.weight.detach())
-    pm.head_b.copy_(model.head.bias.detach())
+    _refresh(pm.cls_tokens, cls)
+    _refresh(pm.head_w, model.head.weight)
+    _refresh(pm.head_b, model.head.bias)
     pm.__dict__.pop("_embed_consts", None)
     pm.extra.pop("head_w6", None)
     if pm.family == "residualvit":
         for k, attr in (("budget_token_1", "learnable_budget_token_1"), ("budget_token_2", "learnable_budget_token_2")):
             if k in pm.extra:
-                pm.extra[k].copy_(getattr(model, attr).detach().reshape(1, pm.dim))
+                _refresh(pm.extra[k], getattr(model, attr))
         for lw in pm.layers:
             if "gate_w" in lw.extra:
                 g = lw.module.residual_gate
-                lw.extra["gate_w"].copy_(g.projection.weight.detach().reshape(-1))
+                _refresh(lw.extra["gate_w"], g.projection.weight)
                 lw.extra["gate_b"] = float(g.projection.bias.detach().float().cpu()[0])
             if "bt_gate_w" in lw.extra:
-                lw.extra["bt_gate_w"].copy_(lw.module.budget_token_gate.weight.detach().reshape(-1))
+                _refresh(lw.extra["bt_gate_w"], lw.module.budget_token_gate.weight)
                 lw.extra["bt_gate_b"] = float(lw.module.budget_token_gate.bias.detach().float().cpu()[0])
 
 

@@ -62,6 +62,7 @@ def packed(model) -> engine.PackedModel:
             light = bool(changed) and all(i < len(names) and engine.is_light_param(names[i]) for i in changed)
         if light:
             engine.refresh_light(pm, model)
+            fp = engine.params_fingerprint(model)      # taken after the refresh: nothing it does may look like a new update
         else:
             st["pm"] = engine.pack_model(model, model._family)
         st["fp"] = fp

@@ -182,6 +182,10 @@ def test_a_few_sgd_steps_reduce_the_loss_and_eval_follows_the_new_weights():
     assert losses[-1] < 0.7 * losses[0], losses
     model.eval()
     after = model(images)                                                   # inference path sees the updated class tokens / head
+    from peekvit_b200 import engine
+    fp = engine.params_fingerprint(model)
+    model(images)
+    assert engine.params_fingerprint(model) == fp                           # the in-place pack refresh leaves the parameters' versions alone
     assert (after - before).abs().max().item() > 1e-2
     assert torch.nn.functional.cross_entropy(after, labels).item() < torch.nn.functional.cross_entropy(before, labels).item()
 
@@ -424,6 +428,10 @@ def test_residualvit_s_gate_regime_against_autograd_and_sgd_steps():
     model.set_budget(0.6)
     after = model(images.to(DEV))
     assert runner.packed(model) is pm_before                 # light refresh: the 22 M frozen weights were not converted again
+    from peekvit_b200 import engine
+    fp = engine.params_fingerprint(model)
+    model(images.to(DEV))
+    assert engine.params_fingerprint(model) == fp            # ... and the refresh itself does not look like another update
     assert (after - before).abs().max().item() > 1e-2 and ops.device_flag() == 0
     ref_after, _ = __import__("oracle.peekvit_oracle", fromlist=["x"]).forward(
         "residualvit", {k: v.detach().cpu() for k, v in model.state_dict().items()}, cfg, images, 0.6)
