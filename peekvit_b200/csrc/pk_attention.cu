@@ -383,7 +383,14 @@ extern "C" int pk_attention_fwd(const pk_attention_args* a, void* stream) {
   else if (a->head_dim == 64 && a->cu_seqlens && occ_ragged == 5) attention_fwd_kernel<64, 5><<<grid, kAttThreads, 0, s>>>(p);
   else if (a->head_dim == 64) attention_fwd_kernel<64><<<grid, kAttThreads, 0, s>>>(p);
   else if (a->head_dim == 48) attention_fwd_kernel<48><<<grid, kAttThreads, 0, s>>>(p);
-  else attention_fwd_kernel<32><<<grid, kAttThreads, 0, s>>>(p);
+  else {
+    const char* e32 = getenv("PK_ATT_GENERAL_OCC32");
+    const int occ32 = e32 ? atoi(e32) : 4;      // config A (64 x 8 heads x 785 tokens): 221.9 / 202.7 / 205.1 / 208.6 us at 3 / 4 / 5 / 6 (profiles/r02/run47)
+    if (occ32 == 4) attention_fwd_kernel<32, 4><<<grid, kAttThreads, 0, s>>>(p);
+    else if (occ32 == 5) attention_fwd_kernel<32, 5><<<grid, kAttThreads, 0, s>>>(p);
+    else if (occ32 == 6) attention_fwd_kernel<32, 6><<<grid, kAttThreads, 0, s>>>(p);
+    else attention_fwd_kernel<32><<<grid, kAttThreads, 0, s>>>(p);
+  }
   return check_cuda(cudaGetLastError(), "attention_fwd_kernel");
 }
 
