@@ -418,8 +418,12 @@ class FineTuner:
                 leaves[l] = leaf
         if extra_loss is not None and leaves:
             with torch.enable_grad():
-                val = extra_loss(model)
-                grads = torch.autograd.grad(val, list(leaves.values()), allow_unused=True)
+                val = torch.as_tensor(extra_loss(model), device=images.device)
+                if val.numel() != 1:
+                    raise ValueError(f"extra_loss must return a scalar, got shape {tuple(val.shape)}")
+                # a term that does not depend on the masks (e.g. weight 0) adds to the loss and has no gradient here
+                grads = (torch.autograd.grad(val, list(leaves.values()), allow_unused=True) if val.requires_grad
+                         else [None] * len(leaves))
             loss_sum.add_(val.detach().to(f32).reshape(1))
             for (l, leaf), gr in zip(leaves.items(), grads):
                 leaf.requires_grad_(False)
