@@ -176,8 +176,10 @@ typedef struct pk_attention_args {
   /* Device-side choice between the two ragged kernels (both are launched, the one not chosen exits at once): with
    * route_rows set, the ragged tcgen05 kernel runs when *route_rows >= route_min_rows (long samples), the general mma.sync
    * kernel otherwise (the two-region TMEM pipeline does not pay off below ~130 rows per sample: profiles/r02).  Independent
-   * of that, ragged head_dim-64 calls split PER SAMPLE: the quad-region tcgen05 kernel takes the samples of at most 128 keys
-   * (four in flight per SM), the kernel chosen above only the longer ones. */
+   * of that, a call whose max_seq_len (+ the virtual key) is at most 128 runs on the quad-region tcgen05 kernel alone (four
+   * samples in flight per SM); with PK_ATT_SPLIT=1 in the environment a mixed batch is split PER SAMPLE on the device: the
+   * quad-region kernel takes the samples of at most 128 keys, the kernel chosen above only the longer ones (opt-in: it loses
+   * on batches whose short samples are nearly empty). */
   const int* route_rows; int route_min_rows;
   int total_rows;           /* rows of the qkv / out buffers (the ragged tcgen05 kernel's 2-D tensor maps need the extent: a
                                key tile that starts near the end of the buffer is zero-filled past it); 0 = unknown (the ragged
