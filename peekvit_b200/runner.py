@@ -14,6 +14,13 @@ import torch
 from . import engine
 
 DEFAULT_MICRO_BATCH = int(os.environ.get("PEEKVIT_B200_MICRO_BATCH", "512"))
+# Device-resident forwards of the families that run on compacted / routed rows (ResidualViT, A-ViT, MoE): their layers are a
+# dozen small launches each, so launch gaps and kernel fill / drain weigh more than for the dense ViT and a larger micro-batch
+# pays -- ResidualViT-S at budget 0.4: 258k / 337k / 395k / 422k img/s at 512 / 1024 / 2048 / 4096 images per micro-batch,
+# A-ViT-S 128k / 135k / 144k / 142k, MoE-ViT-S 56.0k / 56.6k / 58.1k; the dense ViT-B and RankViT-B are flat (26.4k, 52k)
+# (profiles/r02/run50).  The host-resident path keeps DEFAULT_MICRO_BATCH: its chunks exist to overlap the H2D copies.
+SPARSE_MICRO_BATCH = int(os.environ.get("PEEKVIT_B200_SPARSE_MICRO_BATCH", "2048"))
+_SPARSE_FAMILIES = ("residualvit", "eeresidualvit", "adavit", "moevit")
 # Arithmetic mode: "bf16" (bf16 GEMM / attention operands, fp32 accumulation: the measured headline mode) or "fp32" (the
 # reference's shipped dtype: 3-way split operands on the same tcgen05 GEMMs + fp32 attention, logits within 1e-5, every family).
 # Per model: ``model.pk_precision = "fp32"``.
@@ -199,8 +206,9 @@ def _forward_chunk(model, fwd: engine.Forward, chunk: torch.Tensor, aux: Optiona
     return fn(chunk, aux)
 
 
-def _micro_batch(model, B: int) -> int:
-    mb = int(getattr(model, "pk_micro_batch", DEFAULT_MICRO_BATCH))
+def _micro_batch(model, B: int, host: bool = False) -> int:
+    default = SPARSE_MICRO_BATCH if (model._family in _SPARSE_FAMILIES and not host) else DEFAULT_MICRO_BATCH
+    mb = int(getattr(model, "pk_micro_batch", None) or default)
     if _exact(model):
         mb = min(mb, EXACT_MICRO_BATCH)
     abt = model.add_budget_token if model._family == "residualvit" else model.budget if model._family == "eeresidualvit" else None
@@ -312,7 +320,7 @@ def run_host(model, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = Non
         fwd = engine.Forward(packed(model), ws)
         fwd.input_norm = getattr(model, "pk_input_norm", fwd.input_norm)
         fwd.terms = _terms(model)
-        mb = min(_micro_batch(model, B), max(B, 1))
+        mb = min(_micro_batch(model, B, host=True), max(B, 1))
         st = _state(model)
         if "copy_stream" not in st:
             st["copy_stream"] = torch.cuda.Stream(device=dev)
