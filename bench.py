@@ -473,7 +473,7 @@ def run_variants(dev, rank, world, timer: Timer, sampler, images_full, steps_hin
         from peekvit_b200.finetune import FineTuner
         m = make_model("vit", CFG_B, dev)
         m.train()
-        ft = FineTuner(m, micro_batch=128)
+        ft = FineTuner(m, micro_batch=256)
         nb = 512
         xb, yb = images_full[:nb], torch.randint(0, CFG_B["num_classes"], (nb,), device=dev)
         opt = torch.optim.SGD([p for p in m.parameters() if p.requires_grad], lr=1e-3)
@@ -504,7 +504,7 @@ def run_variants(dev, rank, world, timer: Timer, sampler, images_full, steps_hin
         m = make_model("residualvit", cfg, dev)
         calibrate_residual_gates_(m, 0.5, images_full[:32], target=0.5)
         m.train()
-        ft = FineTuner(m, micro_batch=256)
+        ft = FineTuner(m, micro_batch=512)
         nb = 512
         xb, yb = images_full[:nb], torch.randint(0, cfg["num_classes"], (nb,), device=dev)
         opt = torch.optim.SGD([p for p in m.parameters() if p.requires_grad], lr=1e-3)
