@@ -22,3 +22,8 @@ a.record(); out = m(x); b.record(); torch.cuda.synchronize()
 keep = [round(float((blk.mask > 0).float().mean()), 2) for blk in m.encoder.layers]
 print("keep", keep)
 print("ms", a.elapsed_time(b), "img/s", B / a.elapsed_time(b) * 1e3, "flag", ops.device_flag())
+# for `ncu --profile-from-start off`: one more forward inside a profiler range (the calibration above is ~30k launches)
+torch.cuda.profiler.start()
+out = m(x)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
