@@ -314,6 +314,10 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 constexpr int kMmaPitch = 72;                   // bf16 elements per shared row (64 + 8)
+// Sixteen warps per CTA: the four tiles of a 197-token head take 120 KB of shared memory, so one CTA per SM is all there is,
+// and with eight warps the 13 row blocks of a phase ran as two rounds (8 + 5) of latency-bound warps.  At the 128 registers per
+// thread that 512 threads leave, ptxas spills 56 bytes (phase 2 holds two A operands and two 16 x 64 accumulators).
+constexpr int kBwdMmaThreads = 512, kBwdMmaWarps = kBwdMmaThreads / 32;
 
 // C tiles (16 x 16 as two n8 tiles) of  X_blk[16 rows] . Y_blk[16 rows]^T  over head_dim 64: A fragments of X preloaded,
 // B fragments of Y (rows = the product's columns) by non-transposed ldmatrix.
@@ -349,7 +353,7 @@ __device__ __forceinline__ void acc_a_z(float (&acc)[8][4], const uint32_t (&a)[
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kBwdMmaThreads)
 attention_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                          __nv_bfloat16* __restrict__ dqkv, int num_heads, int n, float scale) {
   constexpr int DH = 64;
@@ -400,7 +404,7 @@ attention_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
   const int nblk = NP >> 4;
   const uint32_t blk_bytes = 16 * kMmaPitch * 2;
   // ---- phase 1: warp = block of 16 queries
-  for (int qb = warp; qb < nblk; qb += 8) {
+  for (int qb = warp; qb < nblk; qb += kBwdMmaWarps) {
     uint32_t aq[4][4];
     load_a64(aq, qs + qb * blk_bytes, lane);
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;           // rows g and g + 8
@@ -471,7 +475,7 @@ attention_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
   }
   __syncthreads();
   // ---- phase 2: warp = block of 16 keys, transposed tiles
-  for (int kb = warp; kb < nblk; kb += 8) {
+  for (int kb = warp; kb < nblk; kb += kBwdMmaWarps) {
     uint32_t ak[4][4], av[4][4];
     load_a64(ak, ks_ + kb * blk_bytes, lane);
     load_a64(av, vs + kb * blk_bytes, lane);
@@ -920,7 +924,7 @@ extern "C" int pk_attention_bwd(const void* qkv, const void* out, const void* do
         PK_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         attr_set = true;
       }
-      attention_bwd_mma_kernel<<<dim3(num_heads, batch), 256, bytes, s>>>(
+      attention_bwd_mma_kernel<<<dim3(num_heads, batch), kBwdMmaThreads, bytes, s>>>(
           static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout),
           static_cast<__nv_bfloat16*>(dqkv), num_heads, seq_len, scale);
       return check_cuda(cudaGetLastError(), "attention_bwd_mma_kernel");
