@@ -19,6 +19,8 @@ DEFAULT_MICRO_BATCH = int(os.environ.get("PEEKVIT_B200_MICRO_BATCH", "512"))
 # pays -- ResidualViT-S at budget 0.4: 258k / 337k / 395k / 422k img/s at 512 / 1024 / 2048 / 4096 images per micro-batch,
 # A-ViT-S 128k / 135k / 144k / 142k, MoE-ViT-S 56.0k / 56.6k / 58.1k; the dense ViT-B and RankViT-B are flat (26.4k, 52k)
 # (profiles/r02/run50).  The host-resident path keeps DEFAULT_MICRO_BATCH: its chunks exist to overlap the H2D copies.
+# How the host-resident path cuts its first micro-batch (fractions): the first copy is exposed, the later ones overlap compute
+HOST_FIRST_SPLIT = tuple(float(f) for f in os.environ.get("PEEKVIT_B200_HOST_FIRST_SPLIT", "0.25,0.75").split(","))
 SPARSE_MICRO_BATCH = int(os.environ.get("PEEKVIT_B200_SPARSE_MICRO_BATCH", "2048"))
 _SPARSE_FAMILIES = ("residualvit", "eeresidualvit", "adavit", "moevit")
 # Arithmetic mode: "bf16" (bf16 GEMM / attention operands, fp32 accumulation: the measured headline mode) or "fp32" (the
@@ -343,7 +345,9 @@ def run_host(model, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = Non
         sizes = []
         first = min(mb, B)
         if first >= 128:
-            sizes += [first // 4, first - first // 4]
+            cuts = [int(first * f) for f in HOST_FIRST_SPLIT[:-1]]
+            sizes += [c for c in cuts if c > 0]
+            sizes.append(first - sum(sizes))
         left = B - sum(sizes)
         while left > 0:
             sizes.append(min(mb, left))
