@@ -16,3 +16,8 @@ torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record(); out = m(x); b.record(); torch.cuda.synchronize()
 print("ms", a.elapsed_time(b), "img/s", B / a.elapsed_time(b) * 1e3, "flag", ops.device_flag())
+# for `ncu --profile-from-start off`: one more forward inside a profiler range
+torch.cuda.profiler.start()
+out = m(x)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
