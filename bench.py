@@ -398,7 +398,8 @@ def run_variants(dev, rank, world, timer: Timer, sampler, images_full, steps_hin
         steps = min(steps, 400)
         ms, t0, t1 = timer.run(lambda: model(images), steps)
         v = world * images.shape[0] * steps / (ms * 1e-3)
-        entry = {"value": v, "unit": "images/sec", "images_per_gpu_per_step": images.shape[0], "steps": steps, "ms_per_step": ms / steps}
+        entry = {"value": v, "unit": "images/sec", "images_per_gpu_per_step": images.shape[0], "steps": steps, "ms_per_step": ms / steps,
+                 "micro_batch": min(runner._micro_batch(model, images.shape[0]), images.shape[0])}
         if rank == 0 and sampler is not None:
             entry["clocks"] = sampler.window(t0, t1)
         entry.update(extra or {})
