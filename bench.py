@@ -411,6 +411,7 @@ def run_variants(dev, rank, world, timer: Timer, sampler, images_full, steps_hin
     dense_b = timed(vitb, images_full, "vit_b_16_dense", {"config": "B", "gflop_per_image": gflop_per_image(CFG_B)})
     del vitb
     vits = make_model("vit", CFG_S, dev)
+    vits.pk_micro_batch = runner.SPARSE_MICRO_BATCH        # the denominator of configs C / E runs at the micro-batch its numerators use (+2 % for the dense model)
     dense_s = timed(vits, images_full, "vit_s_16_dense", {"gflop_per_image": gflop_per_image(CFG_S)})
     del vits
 
