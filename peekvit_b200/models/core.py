@@ -381,12 +381,15 @@ class _ModelBase(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return runner.run(self, x)
 
-    def forward_host(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward_host(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,
+                     next_host: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Host batch in, host logits out; H2D copies overlap compute (runner.run_host).  Besides the reference's float
         (B,3,S,S) tensors this (and forward) accepts uint8 (B,S,S,3) images as decoded: ToTensor + Normalize
         (data/imagenette.py:69-73; statistics in ``self.pk_input_norm = (mean, std)``, ImageNet by default) are then fused
-        into the im2col kernel and the host->device copy is 4x smaller."""
-        return runner.run_host(self, x_host, out_host)
+        into the im2col kernel and the host->device copy is 4x smaller.  ``next_host``: the batch the NEXT call will get (what a
+        prefetching loader already holds); its first chunk is copied while this batch still computes, so that call starts
+        without an exposed copy.  Its leading rows must not change until then."""
+        return runner.run_host(self, x_host, out_host, next_host)
 
 
 class VisionTransformer(_ModelBase):
@@ -542,9 +545,9 @@ class EEResidualVisionTransformer(_ModelBase):
         n = out.shape[0] - 1
         return [out[i].unsqueeze(1).squeeze() for i in range(n)] + [out[n]]
 
-    def forward_host(self, x_host, out_host=None):
+    def forward_host(self, x_host, out_host=None, next_host=None):
         """Host images in, the same list as ``forward`` out (host tensors; ``out_host``: optional pinned (L + 1, B, C) buffer)."""
-        out = runner.run_host(self, x_host, out_host)   # (L + 1, B, C)
+        out = runner.run_host(self, x_host, out_host, next_host)   # (L + 1, B, C)
         n = out.shape[0] - 1
         return [out[i].unsqueeze(1).squeeze() for i in range(n)] + [out[n]]
 

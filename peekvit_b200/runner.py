@@ -301,10 +301,17 @@ def run(model, x: torch.Tensor, aux: Optional[dict] = None) -> torch.Tensor:
     return out
 
 
-def run_host(model, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+def _host_key(t: torch.Tensor, n: int, mb: int) -> tuple:
+    return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, n, mb)
+
+
+def run_host(model, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,
+             next_host: Optional[torch.Tensor] = None) -> torch.Tensor:
     """End-to-end entry for host-resident batches (the eval loop's ``batch.to(device); model(batch)``,
     validate/test.py:117-121, as one call): micro-batches are copied host->device on a side stream,
-    double-buffered against compute, and the logits are returned in host memory."""
+    double-buffered against compute, and the logits are returned in host memory.  ``next_host`` (optional) is the batch of
+    the next call -- same shape and dtype, already in (pinned) host memory as a prefetching loader has it: its first chunk
+    is staged while the last chunk of this batch computes, so the next call begins without an exposed copy."""
     dev = _check_model(model)
     if x_host.device.type != "cpu":
         raise RuntimeError("run_host expects a CPU (ideally pinned) tensor; use model(x) for device tensors")
@@ -354,18 +361,32 @@ def run_host(model, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = Non
             left -= sizes[-1]
         if any(lw.kind == "noise" for lw in fwd.pm.layers):
             fwd.noise_draws = engine.draw_noise(fwd.pm, B, dev, _rank_budgets(model) if model._family == "rankvit" else None)
+        # a first chunk staged by the previous call (its ``next_host``): same host tensor, same cut -> start from that slot
+        pf, st["prefetch"] = st.get("prefetch"), None
+        staged = pf is not None and pf["key"] == _host_key(x_host, sizes[0], mb)
+        slot0 = pf["slot"] if staged else 0
         s = 0
         for i, n in enumerate(sizes):
-            slot = i & 1
+            slot = (slot0 + i) & 1
             fwd.sample_offset = s
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(free[slot])
-                bufs[slot][:n].copy_(x_host[s:s + n], non_blocking=True)
-                ready[slot].record(copy_stream)
+            if not (i == 0 and staged):
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(free[slot])
+                    bufs[slot][:n].copy_(x_host[s:s + n], non_blocking=True)
+                    ready[slot].record(copy_stream)
             cur.wait_event(ready[slot])
             (out[:, s:s + n] if multi else out[s:s + n]).copy_(_forward_chunk(model, fwd, bufs[slot][:n], None))
             free[slot].record(cur)
             s += n
+        if (next_host is not None and next_host.device.type == "cpu" and next_host.dtype == x_host.dtype
+                and next_host.shape == x_host.shape and next_host.is_contiguous()):
+            # the other staging slot is free once the chunk before the last one has computed; the copy runs under the last chunk
+            nslot = (slot0 + len(sizes)) & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[nslot])
+                bufs[nslot][:sizes[0]].copy_(next_host[:sizes[0]], non_blocking=True)
+                ready[nslot].record(copy_stream)
+            st["prefetch"] = {"key": _host_key(next_host, sizes[0], mb), "slot": nslot}
         if out_host is None:
             out_host = torch.empty(out_shape, dtype=torch.float32, pin_memory=True)
         out_host.copy_(out, non_blocking=True)

@@ -405,6 +405,36 @@ def test_uint8_input_path_matches_float_path():
 TOL_FP32_MODE = 1e-5        # north star: logits within 1e-5 relative in fp32 mode
 
 
+def test_forward_host_prefetch_of_the_next_batch_changes_nothing_but_the_schedule():
+    """forward_host(x, next_host=y): the first chunk of y is staged while x still computes.  Three different batches in a row
+    (prefetched, prefetched, last), then a call whose tensor is NOT the one that was announced, then a batch of another size:
+    every result equals the plain call's, bit for bit."""
+    from oracle import weights as ow
+    from peekvit_b200.models import VisionTransformer
+    cfg = dict(image_size=64, patch_size=8, num_layers=2, num_heads=2, hidden_dim=128, mlp_dim=256, num_classes=10)
+    model = VisionTransformer(**cfg)
+    model.load_state_dict(ow.make_state_dict("vit", cfg, seed=5))
+    model = model.to(DEV).eval()
+    model.pk_micro_batch = 160                      # 300 images: chunks [40, 120, 140]
+    batches = [ow.synthetic_images(300, 64, seed=s).pin_memory() for s in (1, 2, 3, 4)]
+    plain = [model.forward_host(b).clone() for b in batches]
+    got = [model.forward_host(batches[0], next_host=batches[1]).clone(),
+           model.forward_host(batches[1], next_host=batches[2]).clone(),
+           model.forward_host(batches[2], next_host=batches[0]).clone(),       # announces batch 0 ...
+           model.forward_host(batches[3]).clone()]                              # ... but batch 3 arrives
+    for a, b in zip(plain, got):
+        assert torch.equal(a, b)
+    small = ow.synthetic_images(50, 64, seed=9).pin_memory()
+    ref_small = model.forward_host(small).clone()
+    model.forward_host(batches[0], next_host=small)                             # another shape: not staged
+    assert torch.equal(model.forward_host(small, next_host=small), ref_small)
+    assert torch.equal(model.forward_host(small), ref_small)                    # staged by the call before (same tensor)
+    u8 = (torch.rand(200, 64, 64, 3) * 255).to(torch.uint8).pin_memory()
+    ref_u8 = model.forward_host(u8).clone()
+    model.forward_host(u8, next_host=u8)
+    assert torch.equal(model.forward_host(u8), ref_u8)
+
+
 @pytest.mark.parametrize("name", [n for n in sorted(CASES) if CASES[n].get("noise") is None])
 def test_fp32_mode_matches_reference_fixture(name):
     """model.pk_precision = 'fp32': split-operand tcgen05 GEMMs + fp32 attention reproduce the reference's fp32 logits to
