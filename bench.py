@@ -608,6 +608,10 @@ def main():
         i = count[0] & 1
         count[0] += 1
         model.forward_host(pair[i], logits, next_host=pair[i ^ 1])
+        if world > 1:
+            # the same per-step exchange as the device-resident step (the accuracy counters): both legs run the ranks in
+            # lockstep, so the end-to-end number cannot come out ahead by skipping the collective
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     for _ in range(2):
         e2e_step()
     # the clock sampler starts BEFORE the warm-up (idle samples are filtered by power draw), so that the timed region follows
