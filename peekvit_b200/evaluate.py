@@ -67,6 +67,20 @@ def tokens_per_layer(model, aux: dict, batch: int) -> Optional[list]:
 
 
 @torch.no_grad()
+def _stage(batch, dev, copy_stream):
+    """(images, labels) on ``dev``; host tensors are copied on ``copy_stream`` (asynchronously when pinned) and come with the
+    event the compute stream has to wait for."""
+    images, labels = batch
+    if images.device == dev and labels.device == dev:
+        return images, labels, None
+    with torch.cuda.stream(copy_stream):
+        images = images.to(dev, non_blocking=True)
+        labels = labels.to(dev, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(copy_stream)
+    return images, labels, ready
+
+
 def evaluate(model, batches: Iterable[Tuple[torch.Tensor, torch.Tensor]], budgets: Sequence = (None,),
              noise_module=None, noise_vals: Sequence = (None,), count_flops: bool = True) -> Dict:
     """``{budget: {noise: {accuracy, images_per_second, gmacs_per_image, tokens_per_layer, computed_rows_per_layer}}}`` (noise
@@ -75,6 +89,7 @@ def evaluate(model, batches: Iterable[Tuple[torch.Tensor, torch.Tensor]], budget
     set, throughput from the wall clock of the pass, cost in MACs per image like ``compute_flops(..., flops_units='Mac')``."""
     dev = next(model.parameters()).device
     batches = list(batches)
+    copy_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
     results: Dict = {}
     for budget in budgets:
         if budget is not None and hasattr(model, "set_budget"):
@@ -87,8 +102,17 @@ def evaluate(model, batches: Iterable[Tuple[torch.Tensor, torch.Tensor]], budget
             tok_sum, row_sum, n_img = None, None, 0
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
-            for images, labels in batches:
-                images, labels = images.to(dev, non_blocking=True), labels.to(dev, non_blocking=True)
+            # host-resident batches: the next batch's copy runs on a side stream while this one computes (the reference's loop
+            # copies in front of every forward, validate/test.py:117-118); device-resident batches pass through
+            cur = torch.cuda.current_stream(dev)
+            staged = _stage(batches[0], dev, copy_stream) if batches else None
+            for bi in range(len(batches)):
+                images, labels, ready = staged
+                staged = _stage(batches[bi + 1], dev, copy_stream) if bi + 1 < len(batches) else None
+                if ready is not None:
+                    cur.wait_event(ready)
+                    images.record_stream(cur)
+                    labels.record_stream(cur)
                 aux = {} if count_flops else None
                 logits = runner.run(model, images, aux)
                 logits = logits[-1] if logits.dim() == 3 else logits            # EE-ResidualViT: final head
