@@ -117,3 +117,32 @@ def test_oracle_reproduces_the_reference_gate_regime_gradients():
     for n in names:
         want = torch.from_numpy(fx["grad." + n])
         assert ((sdg[n].grad - want).abs().max() / want.abs().max()).item() < 1e-4, n
+
+
+@pytest.mark.parametrize("name", ["vit_d128_regs", "rankvit_b05"])
+def test_oracle_reproduces_the_reference_class_token_and_head_gradients(name):
+    """tests/golden/finetune_<case>.npz: logits, loss and the class_tokens / head gradients of the REFERENCE model in train()
+    mode under train_only_these_params (make_finetune_vit.py).  The oracle under torch autograd must reproduce them."""
+    import os
+    import numpy as np
+    from golden_cases import CASES, build_case
+    from oracle import peekvit_oracle as po
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", f"finetune_{name}.npz"))
+    case = CASES[name]
+    sd, images = build_case(case)
+    labels = torch.from_numpy(fx["labels"])
+    names = ["class_tokens", "head.weight", "head.bias"]
+    sdg = {k: v.clone() for k, v in sd.items()}
+    for n in names:
+        sdg[n].requires_grad_(True)
+    if case["family"] == "vit":
+        logits, _ = po.vit_forward(sdg, case["cfg"], images)
+    else:
+        logits, _ = po.rankvit_forward(sdg, case["cfg"], images, case["budget"])
+    loss = torch.nn.functional.cross_entropy(logits, labels)
+    loss.backward()
+    assert abs(loss.item() - float(fx["loss"])) < 1e-5
+    assert (logits.detach() - torch.from_numpy(fx["logits"])).abs().max().item() < 1e-5
+    for n in names:
+        want = torch.from_numpy(fx["grad." + n])
+        assert ((sdg[n].grad.view_as(want) - want).abs().max() / want.abs().max()).item() < 1e-4, n

@@ -158,6 +158,32 @@ def test_class_token_and_head_gradients_match_autograd(cfg, batch, mb):
     assert _rel(model.head.bias.grad, 2 * grads["head.bias"]) < 3e-2
 
 
+def test_class_token_and_head_gradients_match_the_reference_fixture():
+    """tests/golden/finetune_vit_d128_regs.npz: the REFERENCE VisionTransformer (two class tokens, registers) in train() mode
+    with train_only_these_params, loss = CrossEntropyLoss, loss.backward() (make_finetune_vit.py).  The CUDA path reproduces
+    logits, loss and the three gradients."""
+    import os
+    import numpy as np
+    from golden_cases import CASES, build_case
+    from peekvit_b200 import ops
+    from peekvit_b200.finetune import FineTuner
+    from peekvit_b200.models import VisionTransformer
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "finetune_vit_d128_regs.npz"))
+    case = CASES["vit_d128_regs"]
+    sd, images = build_case(case)
+    model = VisionTransformer(**case["cfg"])
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).train()
+    ft = FineTuner(model)
+    loss, logits = ft.forward_backward(images.to(DEV), torch.from_numpy(fx["labels"]).to(DEV))
+    assert ops.device_flag() == 0
+    assert _rel(logits.cpu(), torch.from_numpy(fx["logits"])) < 1e-2
+    assert abs(loss.item() - float(fx["loss"])) < 1e-2 * float(fx["loss"])
+    for n, p in ft.params.items():
+        want = torch.from_numpy(fx["grad." + n])
+        assert _rel(p.grad.cpu(), want.view_as(p.grad)) < 3e-2, n
+
+
 def test_a_few_sgd_steps_reduce_the_loss_and_eval_follows_the_new_weights():
     from oracle import weights as ow
     from peekvit_b200.finetune import FineTuner
