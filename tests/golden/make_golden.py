@@ -148,8 +148,14 @@ def main():
                 out[f"kept_{i}"] = seen[j][:, :idx.shape[1]].numpy().astype(np.int32)
             out["seq_lens"] = np.asarray(aux["seq_lens"], dtype=np.int32)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
-    with open(os.path.join(HERE, "MANIFEST.json"), "w") as f:
-        json.dump({"torch": torch.__version__, "cases": sorted(CASES)}, f, indent=1)
+    manifest_path = os.path.join(HERE, "MANIFEST.json")
+    manifest = {}
+    if os.path.exists(manifest_path):                 # keep what the other generators recorded (gradient fixtures)
+        with open(manifest_path) as f:
+            manifest = json.load(f)
+    manifest.update({"torch": torch.__version__, "cases": sorted(CASES)})
+    with open(manifest_path, "w") as f:
+        json.dump(manifest, f, indent=1)
 
 
 if __name__ == "__main__":
